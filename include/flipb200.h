@@ -1,0 +1,166 @@
+/* flipb200.h -- C ABI of libflipb200: the B200 (sm_100a) implementation of the hot path of
+ * Zeno's FastFLIP solver.  This is the drop-in boundary: the Zeno node shims in
+ * zeno_b200/plugin/ (same ZENDEFNODE names and sockets as projects/FastFLIP/nosys/ in the
+ * reference) unpack their sockets, flatten the OpenVDB leaves into the arrays below and
+ * call these entry points instead of the FLIP_vdb statics. Each entry point cites the
+ * reference interface it replaces (paths relative to the reference root, FF = projects/FastFLIP).
+ *
+ * Conventions
+ *  - plain C: opaque handles, pointers + sizes, int error codes (0 = ok); the message of
+ *    the last error on the calling thread is returned by flipb200_last_error().
+ *  - all calls block the host thread until their device work is complete, unless stated.
+ *  - pointers are HOST pointers unless the name ends in _dev.
+ *  - there is no CPU fallback: every entry point fails with FLIPB200_ERR_CUDA when no
+ *    sm_100 device is usable.
+ *
+ * Data layout shared by every grid call (exactly OpenVDB's leaf layout, so a shim can
+ * memcpy leaf buffers):
+ *  - a grid is a set of 8^3 leaves; leaf l has origin[l] = (x,y,z) int32, multiples of 8
+ *    (openvdb/tree/LeafNode.h:1051-1057: voxel offset = x<<6 | y<<3 | z)
+ *  - active mask: 8 x uint64 per leaf, bit n of the 512-bit mask is word n>>6, bit n&63
+ *    (openvdb/util/NodeMasks.h NodeMask<3>)
+ *  - values: float32; scalar grids [leaf][512]; vector grids either
+ *    FLIPB200_SOA  [leaf][3][512]  or  FLIPB200_AOS [leaf][512][3] (= Vec3f leaf buffer)
+ *  - a voxel in no leaf reads as (background, inactive), like a VDB accessor.
+ *  - particles (openvdb::points::PointDataGrid with the FastFLIP codecs, FF/FLIP_vdb.h:28-37):
+ *    per leaf 512 uint32 cumulative end offsets in voxel order, attribute "P" = 3 x uint16
+ *    (FixedPointCodec<false>, voxel-local [-0.5,0.5)) and "v" = 3 x IEEE half bits
+ *    (TruncateCodec), concatenated over leaves in the order of origin[].
+ */
+#ifndef FLIPB200_H
+#define FLIPB200_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct flipb200_world flipb200_world;
+
+enum {
+    FLIPB200_OK = 0,
+    FLIPB200_ERR_ARG = 1,      /* bad argument */
+    FLIPB200_ERR_CUDA = 2,     /* CUDA runtime / no device */
+    FLIPB200_ERR_DOMAIN = 3,   /* leaf bounding box too large for the dense directory */
+    FLIPB200_ERR_STATE = 4,    /* call needs state that has not been provided */
+    FLIPB200_ERR_COMM = 5      /* NCCL */
+};
+
+/* Grid ids = the world objects created by SetFLIPWorld (FF/nosys/FLIP_Creator.cpp:121-143). */
+enum {
+    FLIPB200_VELOCITY = 0,        /* "Velocity"          Vec3f staggered */
+    FLIPB200_POSTADV_VELOCITY = 1,/* "PostAdvVelocity"   Vec3f staggered (velocity right after P2G) */
+    FLIPB200_VISCOUS_VELOCITY = 2,/* "ViscousVelocity"   Vec3f staggered */
+    FLIPB200_SOLID_VELOCITY = 3,  /* "SolidVelocity"     Vec3f staggered */
+    FLIPB200_FACE_WEIGHT = 4,     /* "CellFWeight"       Vec3f staggered */
+    FLIPB200_LIQUID_SDF = 5,      /* "LiquidSDF"         float, cell centred, background dx */
+    FLIPB200_SOLID_SDF = 6,       /* "SolidSDF"          float, VERTEX centred, background 3dx */
+    FLIPB200_PRESSURE = 7,        /* "Pressure"          float */
+    FLIPB200_DIVERGENCE = 8,      /* "Divergence"        float (the PPE right-hand side) */
+    FLIPB200_CURVATURE = 9,       /* "Curvature"         float (unused: tension path is out of scope) */
+    FLIPB200_NUM_GRIDS = 10
+};
+enum { FLIPB200_SOA = 0, FLIPB200_AOS = 1 };
+
+const char* flipb200_last_error(void);
+/* compile-time facts for the loader test: "sm_100a", CUDA runtime version, ABI version */
+const char* flipb200_build_info(void);
+int flipb200_abi_version(void);
+int flipb200_device_count(void);
+
+/* SetFLIPWorld (FF/nosys/FLIP_Creator.cpp:9-118): creates the empty world objects with the
+ * reference backgrounds (liquid SDF = dx, solid SDF = 3dx, everything else 0). */
+int flipb200_world_create(int device, float dx, flipb200_world** out);
+int flipb200_world_destroy(flipb200_world* w);
+
+/* VDB <-> device marshalling (replaces the shared openvdb grid objects behind
+ * VDBGridWrapper::m_grid, projects/zenvdb/include/zeno/VDBGrid.h:80-86). */
+int flipb200_grid_upload(flipb200_world* w, int grid, int nLeaves, const int32_t* origins,
+                         const uint64_t* masks, const float* values, int layout, const float* background);
+int flipb200_grid_leaf_count(flipb200_world* w, int grid, int* nLeaves);
+/* downloads only leaves with at least one active voxel unless keepEmpty != 0 */
+int flipb200_grid_download(flipb200_world* w, int grid, int32_t* origins, uint64_t* masks, float* values,
+                           int layout, float* background);
+int flipb200_particles_upload(flipb200_world* w, int nLeaves, const int32_t* origins,
+                              const uint32_t* voxelEnd, uint64_t nParticles, const uint16_t* P,
+                              const uint16_t* v);
+int flipb200_particles_info(flipb200_world* w, int* nLeaves, uint64_t* nParticles);
+int flipb200_particles_download(flipb200_world* w, int32_t* origins, uint32_t* voxelEnd, uint16_t* P,
+                                uint16_t* v);
+
+/* K1: PrimToVDBPointDataGrid / particleArrayToGrid (projects/zenvdb/SetVDBPointDataGrid.cpp:17-72):
+ * world positions + velocities -> voxel-sorted quantised particle store. vel may be NULL (zeros). */
+int flipb200_bin_from_points(flipb200_world* w, const float* pos, const float* vel, uint64_t n);
+
+/* FLIP_P2G::apply (FF/nosys/P2G.cpp:11-42): FLIP_vdb::particle_to_grid_collect_style
+ * (FF/FLIP_vdb.cpp:1282-1388) + union_extrapolate (FF/vdb_velocity_extrapolator.cpp:584-661).
+ * in: particles; out: Velocity, PostAdvVelocity, LiquidSDF. */
+int flipb200_p2g(flipb200_world* w, float dx, int velExtraLayer);
+
+/* G2PAdvectorSheet::apply (FF/nosys/SheetG2PAdvector.cpp:15-54) -> FLIP_vdb::AdvectSheetty ->
+ * custom_move_points_and_set_flip_vel (FF/FLIP_vdb.cpp:3221-3490).
+ * flags bit0: the ViscousVelocity socket carries the Velocity object itself. */
+int flipb200_g2p_advect_sheetty(flipb200_world* w, float dt, float dx, int surfaceSize, int rkOrder,
+                                float picMin, float picMax, int flags);
+/* particles dropped by the last advect (deep in solid, FF/FLIP_vdb.cpp:682-685, or voxel cap :711-714) */
+int flipb200_dropped(flipb200_world* w, uint64_t* n);
+/* debug: keep / fetch the fp32 position (index space) and velocity before the codecs, in the
+ * order of the particle store the advect call started from (codec caveat). */
+int flipb200_capture_precodec(flipb200_world* w, int on);
+int flipb200_get_precodec(flipb200_world* w, float* pos, float* vel, uint8_t* alive);
+
+/* CutCellWeightEval::apply (FF/nosys/EvalFaceWeight.cpp:17-24) -> calculate_face_weights (FF/FLIP_vdb.cpp:2644-2718) */
+int flipb200_face_weights(flipb200_world* w);
+/* PushOutLiquidSDF::apply (FF/nosys/FixLiquidSDF.cpp:16-29) -> immerse_liquid_phi_in_solids (FF/FLIP_vdb.cpp:2720-2803) */
+int flipb200_pushout_sdf(flipb200_world* w, float dx);
+/* FieldAddVector::apply (FF/nosys/FieldAddVector.cpp:16-31) -> field_add_vector (FF/FLIP_vdb.cpp:3145-3158), dt = 1 */
+int flipb200_add_vector(flipb200_world* w, float x, float y, float z);
+/* CFL_dt (FF/nosys/CFL.cpp) -> FLIP_vdb::cfl (FF/FLIP_vdb.cpp:3160-3207) */
+int flipb200_cfl(flipb200_world* w, float* dtOut);
+
+/* AssembleSolvePPE::apply (FF/nosys/SolvePoissonPressureEqn.cpp:23-64) -> solve_pressure_simd_uaamg
+ * (FF/FLIP_vdb.cpp:3034-3100): builds the variational Laplacian + multigrid hierarchy
+ * (FF/simd_vdb_poisson_uaamg.cpp:357-747,1962-1991), the RHS (:18-93) and runs solveMultigridPCG
+ * (:2332-2403; relative L-inf tolerance 5e-5, <=100 iterations, RBGS smoother), falling back to
+ * solvePureMultigrid on failure. out: Pressure (new grid on the DOF mask), Divergence (= RHS).
+ * status: 0 = PCG converged, 1 = fell back to pure multigrid. */
+int flipb200_solve_ppe(flipb200_world* w, float dt, float dx, int* iterations, float* relResidual, int* status);
+/* same, with the tolerance / iteration cap exposed (BASELINE config C4 uses 1e-6) */
+int flipb200_solve_ppe_ex(flipb200_world* w, float dt, float dx, float relTol, int maxIter,
+                          int* iterations, float* relResidual, int* status);
+int flipb200_solver_info(flipb200_world* w, int* levels, int* numDof, int* nHistory);
+int flipb200_residual_history(flipb200_world* w, float* out);
+
+/* SubtractPressureGradient::apply (FF/nosys/SubtractPressureGradient.cpp:25-66) ->
+ * apply_pressure_gradient (FF/FLIP_vdb.cpp:2863-2967) + union_extrapolate */
+int flipb200_subtract_grad(flipb200_world* w, float dt, float dx, int velExtraLayer);
+
+/* One substep of the packaged chain, device resident (no host copies in between):
+ * G2PAdvectorSheetty -> FLIP_P2G -> CutCellWeight -> PushOutLiquidSDF -> FieldAddVector(g*dt)
+ * -> AssembleSolvePPE -> SubtractPressureGradient (projects/tools/FLIPtools/stub.cpp:5-17).
+ * stageMs (optional, 5 floats): device time of advect, p2g, small stencils, ppe, gradient. */
+int flipb200_substep(flipb200_world* w, float dt, float dx, int surfaceSize, int rkOrder, float picMin,
+                     float picMax, float gx, float gy, float gz, int velExtraLayer, int flags,
+                     float* stageMs);
+
+/* ---- measurement hooks used by bench.py (device timing on the world's stream) ---- */
+/* number of kernels this library launched since the world was created */
+int flipb200_launch_count(flipb200_world* w, uint64_t* n);
+/* per-kernel-family accumulated device time and launch counts since the last reset;
+ * names is a ';'-separated list written into buf */
+int flipb200_profile_enable(flipb200_world* w, int on);
+int flipb200_profile_reset(flipb200_world* w);
+int flipb200_profile_get(flipb200_world* w, char* names, size_t namesCap, float* ms, uint64_t* launches,
+                         uint64_t* bytes, int cap, int* nOut);
+/* the CUDA stream all work of this world is issued on (cudaStream_t as void*) */
+int flipb200_stream(flipb200_world* w, void** stream);
+
+/* ---- multi-GPU (one process per GPU; slab decomposition along x) ---- */
+/* 128-byte NCCL unique id created on rank 0 and distributed by the host (torch.distributed / MPI) */
+int flipb200_comm_unique_id(uint8_t id[128]);
+int flipb200_comm_init(flipb200_world* w, int rank, int nRanks, const uint8_t id[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,307 @@
+// TEST INFRASTRUCTURE ONLY -- see flip_oracle.h.
+// G2P + advection + re-binning (K2, K7, K8).
+#include "flip_oracle.h"
+#include <cmath>
+#include <numeric>
+
+namespace orc {
+namespace {
+
+// local fp32 sampler (FF/FLIP_vdb.cpp:25-110)
+inline float mixf(float a, float b, float w) { return a + (b - a) * w; }
+float samplec(const Vec3Grid& g, int c, float x, float y, float z) {
+    int bx = int(std::floor(double(x))), by = int(std::floor(double(y))), bz = int(std::floor(double(z)));
+    float d[8];
+    // index = i*4 + j*2 + k (:27-54)
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 2; j++)
+            for (int k = 0; k < 2; k++) d[i * 4 + j * 2 + k] = g.get(c, bx + i, by + j, bz + k);
+    float wx = x - float(bx), wy = y - float(by), wz = z - float(bz);
+    return mixf(mixf(mixf(d[0], d[1], wz), mixf(d[2], d[3], wz), wy),
+                mixf(mixf(d[4], d[5], wz), mixf(d[6], d[7], wz), wy), wx);
+}
+void staggered_sample_f32(const Vec3Grid& g, const float p[3], float out[3]) {
+    out[0] = samplec(g, 0, p[0] + 0.5f, p[1], p[2]);
+    out[1] = samplec(g, 1, p[0], p[1] + 0.5f, p[2]);
+    out[2] = samplec(g, 2, p[0], p[1], p[2] + 0.5f);
+}
+
+// openvdb::tools::BoxSampler::sample with double weights
+// (openvdb/tools/Interpolation.h:712-737,763-778): a + float((b-a)*w)
+template <int NC>
+float box_sample_f64(const Grid<NC>& g, int c, double x, double y, double z) {
+    int bx = int(std::floor(x)), by = int(std::floor(y)), bz = int(std::floor(z));
+    double u = x - bx, v = y - by, w = z - bz;
+    float d[2][2][2];
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 2; j++)
+            for (int k = 0; k < 2; k++) d[i][j][k] = g.get(c, bx + i, by + j, bz + k);
+    auto ip = [](float a, float b, double wt) { return a + float(double(b - a) * wt); };
+    return ip(ip(ip(d[0][0][0], d[0][0][1], w), ip(d[0][1][0], d[0][1][1], w), v),
+              ip(ip(d[1][0][0], d[1][0][1], w), ip(d[1][1][0], d[1][1][1], w), v), u);
+}
+// openvdb::tools::StaggeredBoxSampler::sample (Interpolation.h:944-953); input Vec3f -> Vec3R
+void staggered_sample_f64(const Vec3Grid& g, const float p[3], float out[3]) {
+    out[0] = box_sample_f64(g, 0, double(p[0]) + 0.5, double(p[1]), double(p[2]));
+    out[1] = box_sample_f64(g, 1, double(p[0]), double(p[1]) + 0.5, double(p[2]));
+    out[2] = box_sample_f64(g, 2, double(p[0]), double(p[1]), double(p[2]) + 0.5);
+}
+
+// custom_integrator (FF/FLIP_vdb.cpp:169-214)
+void integrate(int order, const Vec3Grid& vel, float dtinvx, float ipos[3], const float V0[3]) {
+    float q[3], V1[3], V2[3], V3[3];
+    switch (order) {
+    case 2:
+        for (int a = 0; a < 3; a++) q[a] = ipos[a] + 0.5f * V0[a] * dtinvx;
+        staggered_sample_f64(vel, q, V1);
+        for (int a = 0; a < 3; a++) ipos[a] += V1[a] * dtinvx;
+        break;
+    case 3:
+        for (int a = 0; a < 3; a++) q[a] = ipos[a] + 0.5f * V0[a] * dtinvx;
+        staggered_sample_f64(vel, q, V1);
+        for (int a = 0; a < 3; a++) q[a] = ipos[a] + dtinvx * (2.0f * V1[a] - V0[a]);
+        staggered_sample_f64(vel, q, V2);
+        for (int a = 0; a < 3; a++) ipos[a] += dtinvx * (V0[a] + 4.0f * V1[a] + V2[a]) * (1.0f / 6.0f);
+        break;
+    case 4:
+        for (int a = 0; a < 3; a++) q[a] = ipos[a] + 0.5f * V0[a] * dtinvx;
+        staggered_sample_f64(vel, q, V1);
+        for (int a = 0; a < 3; a++) q[a] = ipos[a] + 0.5f * V1[a] * dtinvx;
+        staggered_sample_f64(vel, q, V2);
+        for (int a = 0; a < 3; a++) q[a] = ipos[a] + V2[a] * dtinvx;
+        staggered_sample_f64(vel, q, V3);
+        for (int a = 0; a < 3; a++)
+            ipos[a] += dtinvx * (V0[a] + 2.0f * (V1[a] + V2[a]) + V3[a]) * (1.0f / 6.0f);
+        break;
+    case 1:
+    default:
+        for (int a = 0; a < 3; a++) ipos[a] += V0[a] * dtinvx;
+    }
+}
+
+// K8: voxel-centre solid normal and normal velocity (FF/FLIP_vdb.cpp:3270-3367)
+void build_solid_normals(const World& w, float dx, Vec3Grid& normal, FloatGrid& vn) {
+    normal = Vec3Grid(0.f);
+    normal.topologyCopyFrom(w.liquidSDF);
+    normal.dilate(5, true);
+    vn = FloatGrid(0.f);
+    vn.topologyCopyFrom(normal);
+    // AT(:,i) = {a-.5, b-.5, c-.5, 1} * dx ; invATA = {.5,.5,.5,.125}/dx^2 (:3292-3308)
+    float AT[4][8];
+    for (int i = 0; i < 8; i++) {
+        int a = i / 4, b = (i - a * 4) / 2, c = i - a * 4 - b * 2;
+        AT[0][i] = (a - 0.5f) * dx;
+        AT[1][i] = (b - 0.5f) * dx;
+        AT[2][i] = (c - 0.5f) * dx;
+        AT[3][i] = 1.0f * dx;
+    }
+    float s = 1.0f / (dx * dx);
+    float invATA[4] = {0.5f * s, 0.5f * s, 0.5f * s, 0.125f * s};
+    for (int l = 0; l < normal.leafCount(); l++) {
+        Coord o = normal.origins[l];
+        for (int off = 0; off < 512; off++) {
+            if (!maskGet(normal.masks[l], off)) continue;
+            int i = o.x + (off >> 6), j = o.y + ((off >> 3) & 7), k = o.z + (off & 7);
+            float data[8];
+            for (int a = 0; a < 2; a++)
+                for (int b = 0; b < 2; b++)
+                    for (int c = 0; c < 2; c++) data[a * 4 + b * 2 + c] = w.solidSDF.get(0, i + a, j + b, k + c);
+            float abcd[4];
+            for (int r = 0; r < 4; r++) {
+                float acc = 0.f;  // Eigen's dense product order is not pinned (third-party, absent); sequential here
+                for (int q = 0; q < 8; q++) acc += AT[r][q] * data[q];
+                abcd[r] = invATA[r] * acc;
+            }
+            if (abcd[3] < 0.5f) {
+                float n[3] = {abcd[0], abcd[1], abcd[2]};
+                // Vec3::normalize (openvdb/math/Vec3.h:204-210,366-374)
+                float d = float(std::sqrt(double(n[0] * n[0] + n[1] * n[1] + n[2] * n[2])));
+                if (!(std::fabs(d - 0.f) <= 1.0e-7f)) {
+                    float inv = 1.0f / d;
+                    n[0] *= inv; n[1] *= inv; n[2] *= inv;
+                }
+                for (int c = 0; c < 3; c++) normal.leafVals(l, c)[off] = n[c];
+                float sv[3] = {w.solidVelocity.get(0, i, j, k), w.solidVelocity.get(1, i, j, k),
+                               w.solidVelocity.get(2, i, j, k)};
+                // Vec3::dot: x*x' + y*y' + z*z'
+                vn.leafVals(l)[off] = sv[0] * n[0] + sv[1] * n[1] + sv[2] * n[2];
+                maskSet(vn.masks[l], off, true);
+            } else {
+                maskSet(normal.masks[l], off, false);
+                maskSet(vn.masks[l], off, false);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// FLIP_vdb::custom_move_points_and_set_flip_vel (FF/FLIP_vdb.cpp:3237-3490) with
+// point_to_counter_reducer2::operator() (:513-754) and set_new_attribute_list (:3406-3476).
+static void custom_move_points_and_set_flip_vel(World& w, const FloatGrid* liquidSdfIn,
+                                                const Vec3Grid& velocity, const Vec3Grid& velToAdvect,
+                                                bool advSameField, const Vec3Grid& oldVelocity,
+                                                bool hasSolid, float picMin, float picMax, float dt,
+                                                float surfacedist, int rkOrder) {
+    Points& pts = w.particles;
+    const float dx = w.dx;
+    FloatGrid solidBg(3 * dx);
+    Vec3Grid solidVelBg(0.f);
+    const FloatGrid& solidSdf = hasSolid ? w.solidSDF : solidBg;
+    Vec3Grid normal(0.f);
+    FloatGrid vn(0.f);
+    if (hasSolid) build_solid_normals(w, dx, normal, vn);
+    FloatGrid liquidBg(dx);
+    const FloatGrid& liquidSdf = liquidSdfIn ? *liquidSdfIn : liquidBg;
+
+    const size_t n = pts.size();
+    std::vector<uint8_t> alive(n, 0);
+    std::vector<uint64_t> tkey(n);
+    std::vector<uint16_t> toff(n);
+    std::vector<std::array<int, 3>> tijk(n);
+    if (w.capturePreCodec) {
+        w.preCodecPos.assign(3 * n, 0.f);
+        w.preCodecVel.assign(3 * n, 0.f);
+        w.preCodecAlive.assign(n, 0);
+    }
+    const float deep_threshold = float(-4.0 * dx);
+    const float invdx = 1.0f / dx;
+    const float dtinvx = dt / dx;
+
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int l = 0; l < pts.leafCount(); l++) {
+        Coord o = pts.origins[l];
+        for (int off = 0; off < 512; off++) {
+            uint32_t end = pts.voxelEnd[l][off];
+            uint32_t beg = off == 0 ? 0u : pts.voxelEnd[l][off - 1];
+            for (uint32_t it = beg; it < end; it++) {
+                size_t gi = pts.leafBegin[l] + it;
+                float pIs[3] = {float(o.x + (off >> 6)) + fxpt16_decode(pts.P[3 * gi + 0]),
+                                float(o.y + ((off >> 3) & 7)) + fxpt16_decode(pts.P[3 * gi + 1]),
+                                float(o.z + (off & 7)) + fxpt16_decode(pts.P[3 * gi + 2])};
+                float pvel[3] = {half_decode(pts.v[3 * gi + 0]), half_decode(pts.v[3 * gi + 1]),
+                                 half_decode(pts.v[3 * gi + 2])};
+                float adv[3], old[3], carried[3];
+                staggered_sample_f32(velocity, pIs, adv);
+                staggered_sample_f32(oldVelocity, pIs, old);
+                // FLIP/PIC blend factor (:628-648)
+                float flip = 1.0f - picMin;
+                float pls = box_sample_f64(liquidSdf, 0, double(pIs[0]), double(pIs[1]), double(pIs[2]));
+                float t_coef = 1;
+                if (pls < 0 && pls >= -surfacedist) {
+                    t_coef = pls / -surfacedist;
+                    t_coef = std::min(std::max(t_coef, 0.0f), 1.0f);
+                }
+                if (pls >= 0) t_coef = 0;
+                if (surfacedist > 0)
+                    flip = t_coef * flip + (1.0f - t_coef) * std::min(1.0f - picMax, flip);
+                // pIspos + Vec3f{0.5f} is a float add, then promoted to Vec3R (:642-643)
+                float pss = box_sample_f64(solidSdf, 0, double(pIs[0] + 0.5f), double(pIs[1] + 0.5f),
+                                           double(pIs[2] + 0.5f));
+                if (pss >= 0 && pss <= 2.0 * dx) {  // double comparison in the reference (2.0*m_dx)
+                    float scoef = pss / (2.0f * dx);
+                    flip = scoef * flip + (1.0f - scoef) * 1.0f;
+                }
+                if (advSameField) { carried[0] = adv[0]; carried[1] = adv[1]; carried[2] = adv[2]; }
+                else staggered_sample_f32(velToAdvect, pIs, carried);
+                for (int a = 0; a < 3; a++) pvel[a] = carried[a] + flip * (-old[a] + pvel[a]);  // (:668)
+
+                float pIt[3] = {pIs[0], pIs[1], pIs[2]};
+                if (pls >= -surfacedist) integrate(1, velocity, dtinvx, pIt, adv);
+                else integrate(rkOrder, velocity, dtinvx, pIt, adv);
+                int pt[3];
+                for (int a = 0; a < 3; a++) pt[a] = int(std::floor(double(pIt[a] + 0.5f)));
+                // pItpos + Vec3f{0.5}: Vec3f(double 0.5) -> float add (:677-678)
+                float nps = box_sample_f64(solidSdf, 0, double(pIt[0] + 0.5f), double(pIt[1] + 0.5f),
+                                           double(pIt[2] + 0.5f));
+                if (nps < 0) {
+                    if (nps < deep_threshold) continue;  // dropped (:682-685)
+                    float sn[3] = {normal.get(0, pt[0], pt[1], pt[2]), normal.get(1, pt[0], pt[1], pt[2]),
+                                   normal.get(2, pt[0], pt[1], pt[2])};
+                    // pItpos -= new_pos_solid_sdf * snormal * invdx * 1.0f  (:690)
+                    for (int a = 0; a < 3; a++) pIt[a] -= ((nps * sn[a]) * invdx) * 1.0f;
+                    for (int a = 0; a < 3; a++) pt[a] = int(std::floor(double(pIt[a] + 0.5f)));
+                    float vnv = vn.get(0, pt[0], pt[1], pt[2]);
+                    float dot = sn[0] * pvel[0] + sn[1] * pvel[1] + sn[2] * pvel[2];
+                    float coef = vnv - dot;
+                    for (int a = 0; a < 3; a++) pvel[a] += coef * sn[a];  // (:693-694)
+                }
+                // codec write-back in place (:702-703)
+                for (int a = 0; a < 3; a++) {
+                    float local = float(double(pIt[a]) - double(pt[a]));
+                    pts.P[3 * gi + a] = fxpt16_encode(local);
+                    pts.v[3 * gi + a] = half_encode(pvel[a]);
+                }
+                if (w.capturePreCodec) {
+                    for (int a = 0; a < 3; a++) { w.preCodecPos[3 * gi + a] = pIt[a]; w.preCodecVel[3 * gi + a] = pvel[a]; }
+                    w.preCodecAlive[gi] = 1;
+                }
+                alive[gi] = 1;
+                tijk[gi] = {pt[0], pt[1], pt[2]};
+                tkey[gi] = leafKeyOf(pt[0], pt[1], pt[2]);
+                toff[gi] = uint16_t(voxelOffset(pt[0], pt[1], pt[2]));
+            }
+        }
+    }
+
+    // K2: per-target-voxel counters with the >27 cap (:706-751), applied in source order.
+    // (The reference applies the cap per TBB sub-range before the join, so which particle
+    // is dropped is not deterministic there)
+    std::unordered_map<uint64_t, uint32_t> counter;
+    counter.reserve(n / 4 + 16);
+    uint64_t dropped = 0;
+    std::vector<uint32_t> order;
+    order.reserve(n);
+    for (size_t gi = 0; gi < n; gi++) {
+        if (!alive[gi]) { dropped++; continue; }
+        uint64_t vk = (tkey[gi] << 9) | toff[gi];
+        uint32_t& c = counter[vk];
+        if (c > 27) { dropped++; continue; }
+        c++;
+        order.push_back(uint32_t(gi));
+    }
+    w.droppedParticles = dropped;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        if (tkey[a] != tkey[b]) return tkey[a] < tkey[b];
+        return toff[a] < toff[b];
+    });
+    Points np;
+    const size_t m = order.size();
+    np.P.resize(3 * m);
+    np.v.resize(3 * m);
+    for (size_t s = 0; s < m; s++) {
+        uint32_t gi = order[s];
+        int l;
+        auto it = np.dir.find(tkey[gi]);
+        if (it == np.dir.end()) {
+            l = np.leafCount();
+            np.dir.emplace(tkey[gi], l);
+            np.origins.push_back(Coord(tijk[gi][0] & ~7, tijk[gi][1] & ~7, tijk[gi][2] & ~7));
+            std::array<uint32_t, 512> z; z.fill(0);
+            np.voxelEnd.push_back(z);
+            np.leafBegin.push_back(s);
+        } else l = it->second;
+        np.voxelEnd[l][toff[gi]]++;
+        for (int a = 0; a < 3; a++) {
+            np.P[3 * s + a] = pts.P[3 * gi + a];
+            np.v[3 * s + a] = pts.v[3 * gi + a];
+        }
+    }
+    np.leafBegin.push_back(m);
+    for (auto& ve : np.voxelEnd)
+        for (int o = 1; o < 512; o++) ve[o] += ve[o - 1];
+    pts = std::move(np);
+}
+
+// G2PAdvectorSheet::apply (FF/nosys/SheetG2PAdvector.cpp:15-54) -> FLIP_vdb::AdvectSheetty (:3221-3235)
+void node_G2PAdvectorSheetty(World& w, float dt, float dx, int surfaceSize, int rkOrder, float picMin,
+                             float picMax) {
+    picMin = picMin > picMax ? picMax : picMin;
+    // velocity and ViscousVelocity are distinct grid objects in the graph, so
+    // adv_same_field (tree pointer equality, :617-618) is false.
+    custom_move_points_and_set_flip_vel(w, &w.liquidSDF, w.velocity, w.viscousVelocity, false,
+                                        w.postAdvVelocity, w.hasSolidSDF, picMin, picMax, dt,
+                                        float(surfaceSize) * dx, rkOrder);
+}
+
+}  // namespace orc

@@ -1,0 +1,71 @@
+// TEST INFRASTRUCTURE ONLY -- CPU oracle for the FastFLIP hot path (see sgrid.h).
+// A plain, single-file-per-stage C++ restatement of the reference algorithms;
+// every function cites the reference file:line it follows
+// (paths relative to /root/reference; FF = projects/FastFLIP).
+//
+// PARITY STATUS: the reference ships no tests or golden vectors for this path
+// (SURVEY.md section 4). The oracle is pinned against the real reference
+// sources compiled by oracle/ref/build_ref.sh when that build is available
+// (oracle/_ref/); see DESIGN.md "Oracle" for what is pinned and what is not.
+#pragma once
+#include "sgrid.h"
+
+namespace orc {
+
+// ---- codecs (openvdb/points/AttributeArray.h:50-65,940-976; math/Half.h:430-490)
+uint16_t fxpt16_encode(float p);
+float fxpt16_decode(uint16_t u);
+uint16_t half_encode(float f);
+float half_decode(uint16_t h);
+
+struct Packed3 {  // packed_FloatGrid3 (projects/zenvdb/include/zeno/packed3grids.h:6-26)
+    FloatGrid v[3];
+};
+void from_vec3(Packed3& out, const Vec3Grid& in, bool topologyOnly);
+void to_vec3(Vec3Grid& out, const Packed3& in);
+
+struct World {
+    float dx;
+    Points particles;
+    Vec3Grid velocity, postAdvVelocity, viscousVelocity, solidVelocity, faceWeight;
+    FloatGrid liquidSDF, solidSDF, pressure, divergence, curvature;
+    bool hasSolidSDF = false, hasSolidVel = false;
+    // diagnostics
+    int pcgIterations = 0;
+    int pcgStatus = 0;
+    int mgLevels = 0;
+    int numDof = 0;
+    float pcgRelResidual = 0.f;
+    uint64_t droppedParticles = 0;
+    std::vector<float> residualHistory;
+    // optional pre-codec capture (SURVEY 8d "codec caveat"): fp32 particle
+    // position (index space) and velocity before the codecs, in source order.
+    bool capturePreCodec = false;
+    std::vector<float> preCodecPos, preCodecVel;
+    std::vector<uint8_t> preCodecAlive;
+    explicit World(float dx_);
+};
+
+// K1  projects/zenvdb/SetVDBPointDataGrid.cpp:17-72
+void bin_from_points(World& w, const float* pos, const float* vel, size_t n);
+// K3-K6  FF/nosys/P2G.cpp:11-42
+void node_FLIP_P2G(World& w, float dx, int velExtraLayer);
+// K5  FF/vdb_velocity_extrapolator.cpp:584-661
+void union_extrapolate(int nLayer, Packed3& v, const FloatGrid* targetTopo);
+// K2,K7,K8  FF/nosys/SheetG2PAdvector.cpp:15-54 / FF/FLIP_vdb.cpp:3237-3490
+void node_G2PAdvectorSheetty(World& w, float dt, float dx, int surfaceSize, int rkOrder,
+                             float picMin, float picMax);
+// K14 nodes
+void node_CutCellWeight(World& w);                          // FF/FLIP_vdb.cpp:2644-2718
+void node_PushOutLiquidSDF(World& w, float dx);             // FF/FLIP_vdb.cpp:2720-2803
+void node_FieldAddVector(World& w, float x, float y, float z);  // FF/FLIP_vdb.cpp:3145-3158
+float node_CFL_dt(World& w);                                // FF/FLIP_vdb.cpp:3160-3207
+// K9-K13  FF/nosys/SolvePoissonPressureEqn.cpp:23-64
+void node_AssembleSolvePPE(World& w, float dt, float dx);
+// FF/nosys/SubtractPressureGradient.cpp:25-66
+void node_SubtractPressureGradient(World& w, float dt, float dx, int velExtraLayer);
+
+float fraction_inside(float phi_left, float phi_right);  // FF/levelset_util.cpp:5-15
+float fraction_inside(float bl, float br, float tl, float tr);  // FF/levelset_util.cpp:26-99
+
+}  // namespace orc

@@ -1,0 +1,374 @@
+// libflipb200 -- particle-to-grid transfer (K3/K4), velocity extrapolation (K5).
+//
+// p2g_gather_kernel: one CTA per pool leaf, "collect style" like the reference
+// (FF/FLIP_vdb.cpp:1137-1263): every target voxel gathers the particles of its 27
+// neighbouring cells. The 10x10x10 cell shell around the leaf is streamed through shared
+// memory one x-plane at a time (decoded once per CTA), the per-voxel accumulators
+// (sum w*v, sum w per channel, min d^2, count) live in shared memory, and each voxel visits
+// its source cells in (x,y,z) order and the particles of a cell in store order. That is
+// exactly the order of the reference's all_particle_iterator (:1021-1132), so the fp32 sums
+// are reproducible and there are no float atomics anywhere.
+#include "world.cuh"
+
+namespace fb {
+void mark_alloc_from_mask(World* w, const uint64_t* mask, int n, uint8_t* alloc);
+namespace {
+
+constexpr int P2G_THREADS = 192;   // three x-slices of 64 target voxels are live per plane
+constexpr int PLANE_CELLS = 100;   // 10 x 10 cells (y,z in [-1,8])
+constexpr int PLANE_CAP = 1400;    // staged particles per batch (a plane at 8 ppc holds ~800)
+
+struct P2GParams {
+    TopoView t;
+    const uint32_t* voxelStart;
+    const uint32_t *w0, *w1, *w2;
+    float* vel[3];        // out: normalised velocity, 0 where the channel is off
+    uint64_t* chMask;     // out: [3][n][8]
+    float* sdf;           // out: liquid sdf values
+    uint64_t* topoMask;   // out: dilated-occupancy mask [n][8]
+    float dx, radius, sdfBg;
+    int* overflow;
+};
+
+__global__ void __launch_bounds__(P2G_THREADS) p2g_gather_kernel(P2GParams p) {
+    extern __shared__ float smem[];
+    float* sP = smem;                          // [PLANE_CAP][6] px,py,pz,vx,vy,vz
+    float* acc = sP + PLANE_CAP * 6;           // [8][512]: wv0..2, w0..2, mind2, count
+    __shared__ uint32_t cBeg[PLANE_CELLS];
+    __shared__ uint32_t cCnt[PLANE_CELLS];
+    __shared__ int cOff[PLANE_CELLS + 1];      // smem offset of the cell in the current batch (-1: not staged)
+    __shared__ int sBatchEnd;
+
+    const int leaf = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int* nbr = p.t.nbr27 + (size_t)leaf * 27;
+
+    for (int i = tid; i < 8 * LEAF; i += P2G_THREADS) acc[i] = (i >= 6 * LEAF && i < 7 * LEAF) ? 3.0e38f : 0.f;
+
+    for (int cx = -1; cx <= 8; cx++) {
+        __syncthreads();
+        // particle ranges of the plane's 100 cells
+        if (tid < PLANE_CELLS) {
+            int cy = tid / 10 - 1, cz = tid % 10 - 1;
+            int li = (cx < 0 ? 0 : (cx < 8 ? 1 : 2)) * 9 + (cy < 0 ? 0 : (cy < 8 ? 1 : 2)) * 3 + (cz < 0 ? 0 : (cz < 8 ? 1 : 2));
+            int nl = nbr[li];
+            uint32_t b = 0, c = 0;
+            if (nl >= 0) {
+                size_t v = (size_t)nl * LEAF + (((cx & 7) << 6) | ((cy & 7) << 3) | (cz & 7));
+                b = __ldg(&p.voxelStart[v]);
+                c = __ldg(&p.voxelStart[v + 1]) - b;
+            }
+            cBeg[tid] = b; cCnt[tid] = c;
+        }
+        __syncthreads();
+        int batchStart = 0;
+        while (batchStart < PLANE_CELLS) {
+            // warp 0: the maximal run of cells starting at batchStart whose particles fit PLANE_CAP
+            if (tid < 32) {
+                int run = 0, end = PLANE_CELLS;
+                for (int base = batchStart; base < PLANE_CELLS; base += 32) {
+                    int c = base + tid;
+                    int cnt = 0;
+                    if (c < PLANE_CELLS) {
+                        cnt = (int)cCnt[c];
+                        if (cnt > PLANE_CAP) { cnt = PLANE_CAP; atomicExch(p.overflow, 1); }
+                    }
+                    int incl = cnt;
+                    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += v; }
+                    int excl = run + incl - cnt;
+                    bool fits = excl + cnt <= PLANE_CAP;  // monotone in c: a prefix property
+                    unsigned fm = __ballot_sync(0xffffffffu, fits);
+                    int nfit = fm == 0xffffffffu ? 32 : __ffs(~fm) - 1;
+                    if (tid < nfit && c < PLANE_CELLS) cOff[c] = excl;
+                    run += __shfl_sync(0xffffffffu, incl, 31);
+                    if (nfit < 32) { end = base + nfit; break; }
+                }
+                if (end > PLANE_CELLS) end = PLANE_CELLS;
+                if (tid == 0) sBatchEnd = end;
+            }
+            __syncthreads();
+            const int batchEnd = sBatchEnd;
+            // stage + decode the batch's particles: one thread per cell
+            for (int c = batchStart + tid; c < batchEnd; c += P2G_THREADS) {
+                int cnt = min((int)cCnt[c], PLANE_CAP);
+                uint32_t b = cBeg[c];
+                float* dst = sP + (size_t)cOff[c] * 6;
+                for (int j = 0; j < cnt; j++) {
+                    uint32_t a0 = __ldg(&p.w0[b + j]), a1 = __ldg(&p.w1[b + j]), a2 = __ldg(&p.w2[b + j]);
+                    dst[6 * j + 0] = fx_decode(a0 & 0xffffu);
+                    dst[6 * j + 1] = fx_decode(a0 >> 16);
+                    dst[6 * j + 2] = fx_decode(a1 & 0xffffu);
+                    dst[6 * j + 3] = h_decode(a1 >> 16);
+                    dst[6 * j + 4] = h_decode(a2 & 0xffffu);
+                    dst[6 * j + 5] = h_decode(a2 >> 16);
+                }
+            }
+            __syncthreads();
+            // accumulate: slice si handles target x = cx + 1 - si... (ox = source - target)
+            {
+                int si = tid >> 6;                 // 0,1,2
+                int x = cx - 1 + si;               // si=0 -> ox=+1, si=1 -> ox=0, si=2 -> ox=-1
+                int ox = cx - x;
+                int y = (tid >> 3) & 7, z = tid & 7;
+                if (x >= 0 && x <= 7) {
+                    int vo = (x << 6) | (y << 3) | z;
+                    float a0 = acc[vo], a1 = acc[LEAF + vo], a2 = acc[2 * LEAF + vo];
+                    float g0 = acc[3 * LEAF + vo], g1 = acc[4 * LEAF + vo], g2 = acc[5 * LEAF + vo];
+                    float md = acc[6 * LEAF + vo], cn = acc[7 * LEAF + vo];
+                    const float fx = (float)(-ox);
+                    for (int oy = -1; oy <= 1; oy++) {
+                        const float fy = (float)(-oy);
+                        for (int oz = -1; oz <= 1; oz++) {
+                            const float fz = (float)(-oz);
+                            int c = (y + oy + 1) * 10 + (z + oz + 1);
+                            if (c < batchStart || c >= batchEnd) continue;
+                            int cnt = min((int)cCnt[c], PLANE_CAP);
+                            const float* src = sP + (size_t)cOff[c] * 6;
+                            for (int j = 0; j < cnt; j++) {
+                                float px = src[6 * j], py = src[6 * j + 1], pz = src[6 * j + 2];
+                                float tx = fabsf(__fsub_rn(fx, px)), ty = fabsf(__fsub_rn(fy, py)), tz = fabsf(__fsub_rn(fz, pz));
+                                float d2 = __fadd_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)), __fmul_rn(tz, tz));
+                                md = fminf(md, d2);
+                                cn += 1.f;
+                                float hx = fmaxf(0.f, __fsub_rn(1.0f, tx)), hy = fmaxf(0.f, __fsub_rn(1.0f, ty)), hz = fmaxf(0.f, __fsub_rn(1.0f, tz));
+                                if (ox != 1) {  // u sample at -0.5 in x; a source cell at +1 is always out of reach
+                                    float xs = fabsf(__fsub_rn(__fadd_rn(fx, -0.5f), px));
+                                    float wgt = __fmul_rn(__fmul_rn(fmaxf(0.f, __fsub_rn(1.0f, xs)), hy), hz);
+                                    a0 = __fadd_rn(__fmul_rn(src[6 * j + 3], wgt), a0);
+                                    g0 = __fadd_rn(wgt, g0);
+                                }
+                                if (oy != 1) {
+                                    float ys = fabsf(__fsub_rn(__fadd_rn(fy, -0.5f), py));
+                                    float wgt = __fmul_rn(__fmul_rn(hx, fmaxf(0.f, __fsub_rn(1.0f, ys))), hz);
+                                    a1 = __fadd_rn(__fmul_rn(src[6 * j + 4], wgt), a1);
+                                    g1 = __fadd_rn(wgt, g1);
+                                }
+                                if (oz != 1) {
+                                    float zs = fabsf(__fsub_rn(__fadd_rn(fz, -0.5f), pz));
+                                    float wgt = __fmul_rn(__fmul_rn(hx, hy), fmaxf(0.f, __fsub_rn(1.0f, zs)));
+                                    a2 = __fadd_rn(__fmul_rn(src[6 * j + 5], wgt), a2);
+                                    g2 = __fadd_rn(wgt, g2);
+                                }
+                            }
+                        }
+                    }
+                    acc[vo] = a0; acc[LEAF + vo] = a1; acc[2 * LEAF + vo] = a2;
+                    acc[3 * LEAF + vo] = g0; acc[4 * LEAF + vo] = g1; acc[5 * LEAF + vo] = g2;
+                    acc[6 * LEAF + vo] = md; acc[7 * LEAF + vo] = cn;
+                }
+            }
+            __syncthreads();
+            batchStart = batchEnd;
+        }
+    }
+    __syncthreads();
+    // normalize_p2g_velocity (FF/FLIP_vdb.cpp:120-165) + sdf transform (:1199-1204)
+    for (int base = 0; base < LEAF; base += 32 * (P2G_THREADS / 32)) {
+        int vo = base + tid;
+        bool valid = vo < LEAF;
+        bool on[3] = {false, false, false};
+        bool touched = false;
+        if (valid) {
+            touched = acc[7 * LEAF + vo] > 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float wsum = acc[(3 + c) * LEAF + vo];
+                float out = 0.f;
+                if (touched && wsum != 0.f) { out = __fdiv_rn(acc[c * LEAF + vo], __fadd_rn(wsum, 0.001f)); on[c] = true; }
+                p.vel[c][(size_t)leaf * LEAF + vo] = out;
+            }
+            float s = p.sdfBg;
+            if (touched) s = fminf(s, __fsub_rn(__fmul_rn(p.dx, sqrtf(acc[6 * LEAF + vo])), p.radius));
+            p.sdf[(size_t)leaf * LEAF + vo] = s;
+        }
+        unsigned bt = __ballot_sync(0xffffffffu, valid && touched);
+        unsigned b0 = __ballot_sync(0xffffffffu, on[0]), b1 = __ballot_sync(0xffffffffu, on[1]), b2 = __ballot_sync(0xffffffffu, on[2]);
+        if (valid && (tid & 31) == 0) {
+            size_t wi = (size_t)leaf * 16 + (vo >> 5);
+            reinterpret_cast<uint32_t*>(p.topoMask)[wi] = bt;
+            size_t nW = (size_t)p.t.n * 16;
+            reinterpret_cast<uint32_t*>(p.chMask)[wi] = b0;
+            reinterpret_cast<uint32_t*>(p.chMask)[nW + wi] = b1;
+            reinterpret_cast<uint32_t*>(p.chMask)[2 * nW + wi] = b2;
+        }
+    }
+}
+
+// air one-ring of the liquid sdf (FF/FLIP_vdb.cpp:1325-1382). ring = dilate26(topo) & ~topo.
+__global__ void __launch_bounds__(512) air_ring_kernel(TopoView t, const uint64_t* __restrict__ topoMask,
+                                                       const uint64_t* __restrict__ ringMask, float* __restrict__ sdf,
+                                                       uint64_t* __restrict__ sdfMask, float dx, float bg) {
+    int leaf = blockIdx.x, off = threadIdx.x;
+    bool inTopo = mask_get(topoMask, leaf, off);
+    bool inRing = mask_get(ringMask, leaf, off) && !inTopo;
+    bool on = inTopo;
+    float newSdf = 0.f;
+    if (inRing) {
+        int3 o = t.origin[leaf];
+        int x = o.x + (off >> 6), y = o.y + ((off >> 3) & 7), z = o.z + (off & 7);
+        bool hasLiquid = false;
+        newSdf = sdf[(size_t)leaf * LEAF + off];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            int comp = i >> 1;
+            int d = (i & 1) == 0 ? 1 : -1;
+            int nx = x + (comp == 0 ? d : 0), ny = y + (comp == 1 ? d : 0), nz = z + (comp == 2 ? d : 0);
+            // only voxels of the original topology can be negative; ring voxels hold bg or positive values
+            int nl = topo_find(t, nx, ny, nz);
+            float ns = bg;
+            if (nl >= 0 && mask_get(topoMask, nl, voxel_off(nx, ny, nz))) ns = sdf[(size_t)nl * LEAF + voxel_off(nx, ny, nz)];
+            if (ns < 0.f) { hasLiquid = true; newSdf = fminf(newSdf, __fadd_rn(dx, ns)); }
+        }
+        on = hasLiquid;
+    }
+    __syncthreads();  // all reads of neighbouring topo voxels in this leaf are done; ring writes touch ring voxels only
+    if (inRing && on) sdf[(size_t)leaf * LEAF + off] = newSdf;
+    unsigned b = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0) reinterpret_cast<uint32_t*>(sdfMask)[(size_t)leaf * 16 + (threadIdx.x >> 5)] = b;
+}
+
+// one layer of union_extrapolate for one channel (FF/vdb_velocity_extrapolator.cpp:618-657)
+__global__ void __launch_bounds__(512) extrapolate_layer_kernel(TopoView t, const uint64_t* __restrict__ target,
+                                                                const uint64_t* __restrict__ validIn,
+                                                                uint64_t* __restrict__ validOut, float* __restrict__ val) {
+    int leaf = blockIdx.x, off = threadIdx.x;
+    bool valid = mask_get(validIn, leaf, off);
+    bool tgt = mask_get(target, leaf, off);
+    bool newOn = valid;
+    if (tgt && !valid) {
+        int3 o = t.origin[leaf];
+        int x = o.x + (off >> 6), y = o.y + ((off >> 3) & 7), z = o.z + (off & 7);
+        int tw = 0;
+        float sum = 0.f;
+#pragma unroll
+        for (int d = 0; d < 6; d++) {
+            int dir = d >> 1, s = (d & 1) ? 1 : -1;
+            int nx = x + (dir == 0 ? s : 0), ny = y + (dir == 1 ? s : 0), nz = z + (dir == 2 ? s : 0);
+            int nl, no;
+            int lx = (off >> 6) + (dir == 0 ? s : 0), ly = ((off >> 3) & 7) + (dir == 1 ? s : 0), lz = (off & 7) + (dir == 2 ? s : 0);
+            if ((unsigned)lx < 8u && (unsigned)ly < 8u && (unsigned)lz < 8u) { nl = leaf; no = (lx << 6) | (ly << 3) | lz; }
+            else { nl = topo_find(t, nx, ny, nz); no = voxel_off(nx, ny, nz); }
+            if (nl >= 0 && mask_get(validIn, nl, no)) { tw++; sum = __fadd_rn(sum, val[(size_t)nl * LEAF + no]); }
+        }
+        if (tw != 0) { val[(size_t)leaf * LEAF + off] = __fdiv_rn(sum, (float)tw); newOn = true; }
+    }
+    unsigned b = __ballot_sync(0xffffffffu, newOn);
+    if ((threadIdx.x & 31) == 0) reinterpret_cast<uint32_t*>(validOut)[(size_t)leaf * 16 + (threadIdx.x >> 5)] = b;
+}
+// to_vec3 (packed3grids.cpp:49-83): union mask; a channel that is off contributes 0
+__global__ void __launch_bounds__(512) to_vec3_kernel(int n, const uint64_t* __restrict__ chMask, float* __restrict__ v0,
+                                                      float* __restrict__ v1, float* __restrict__ v2,
+                                                      uint64_t* __restrict__ outMask) {
+    int leaf = blockIdx.x, off = threadIdx.x;
+    size_t stride = (size_t)n * 8;
+    bool o0 = mask_get(chMask, leaf, off), o1 = mask_get(chMask + stride, leaf, off), o2 = mask_get(chMask + 2 * stride, leaf, off);
+    size_t i = (size_t)leaf * LEAF + off;
+    if (!o0) v0[i] = 0.f;
+    if (!o1) v1[i] = 0.f;
+    if (!o2) v2[i] = 0.f;
+    unsigned b = __ballot_sync(0xffffffffu, o0 | o1 | o2);
+    if ((threadIdx.x & 31) == 0) reinterpret_cast<uint32_t*>(outMask)[(size_t)leaf * 16 + (threadIdx.x >> 5)] = b;
+}
+__global__ void andnot_kernel(uint64_t* __restrict__ a, const uint64_t* __restrict__ b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] &= ~b[i];
+}
+}  // namespace
+
+void union_extrapolate(World* w, int nLayer, GridV& vel, uint64_t* chMask, const uint64_t* targetMask) {
+    const Topo& t = *vel.topo;
+    if (t.n == 0) return;
+    size_t stride = (size_t)t.n * 8;
+    DBuf<uint64_t> tmp(stride, w->stream);
+    for (int ch = 0; ch < 3; ch++) {
+        uint64_t* cur = chMask + ch * stride;
+        uint64_t* nxt = tmp.p;
+        for (int layer = 0; layer < nLayer; layer++) {
+            FB_LAUNCH(w, "extrapolate_layer", (size_t)t.n * (2048 + 192)) extrapolate_layer_kernel<<<t.n, 512, 0, w->stream>>>(t.view(), targetMask, cur, nxt, vel.val[ch].p);
+            check_launch("extrapolate_layer");
+            std::swap(cur, nxt);
+        }
+        if (cur != chMask + ch * stride)
+            FB_CUDA(cudaMemcpyAsync(chMask + ch * stride, cur, stride * 8, cudaMemcpyDeviceToDevice, w->stream));
+    }
+}
+
+void finish_vec3(World* w, GridV& vel, const uint64_t* chMask) {
+    int n = vel.topo->n;
+    if (!n) return;
+    FB_LAUNCH(w, "to_vec3", (size_t)n * (6144 + 256)) to_vec3_kernel<<<n, 512, 0, w->stream>>>(n, chMask, vel.val[0].p, vel.val[1].p, vel.val[2].p, vel.mask.p);
+    check_launch("to_vec3");
+}
+
+// FLIP_P2G::apply (FF/nosys/P2G.cpp:11-42)
+void p2g(World* w, float dx, int velExtraLayer) {
+    FB_REQUIRE(w->pts.topo != nullptr, FLIPB200_ERR_STATE, "FLIP_P2G: no particles");
+    ensure_pool(w, {}, /*includeParticles=*/true);
+    TopoPtr pool = w->pool;
+    const int n = pool->n;
+    GridV& vel = w->V(FLIPB200_VELOCITY);
+    GridV& post = w->V(FLIPB200_POSTADV_VELOCITY);
+    GridF& sdf = w->F(FLIPB200_LIQUID_SDF);
+    const float zero3[3] = {0.f, 0.f, 0.f};
+    // outputs are brand-new grids on the pool (the reference setTree()s new trees)
+    GridV nvel; nvel.topo = pool;
+    for (int c = 0; c < 3; c++) { nvel.bg[c] = 0.f; nvel.val[c].alloc((size_t)n * LEAF, w->stream); }
+    nvel.mask.alloc((size_t)n * 8, w->stream);
+    GridF nsdf; nsdf.topo = pool; nsdf.bg = sdf.bg;
+    nsdf.val.alloc((size_t)n * LEAF, w->stream);
+    nsdf.mask.alloc((size_t)n * 8, w->stream);
+    nsdf.alloc.alloc(n ? n : 1, w->stream);
+    nsdf.alloc.zero();
+    (void)zero3;
+    if (n == 0) { vel = std::move(nvel); grid_copy(w, post, vel); sdf = std::move(nsdf); return; }
+
+    DBuf<uint64_t> chMask((size_t)3 * n * 8, w->stream), topoMask((size_t)n * 8, w->stream), ring((size_t)n * 8, w->stream);
+    DBuf<int> overflow(1, w->stream);
+    overflow.zero();
+    P2GParams p;
+    p.t = pool->view();
+    p.voxelStart = w->pts.voxelStart.p;
+    p.w0 = w->pts.w0.p; p.w1 = w->pts.w1.p; p.w2 = w->pts.w2.p;
+    for (int c = 0; c < 3; c++) p.vel[c] = nvel.val[c].p;
+    p.chMask = chMask.p;
+    p.sdf = nsdf.val.p;
+    p.topoMask = topoMask.p;
+    p.dx = dx;
+    p.radius = dx * 0.8f * 1.01f;  // FF/FLIP_vdb.cpp:1287
+    p.sdfBg = sdf.bg;
+    p.overflow = overflow.p;
+    size_t smemBytes = (size_t)(PLANE_CAP * 6 + 8 * LEAF) * sizeof(float);
+    static bool attrSet = false;
+    if (!attrSet) {
+        FB_CUDA(cudaFuncSetAttribute(p2g_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+        attrSet = true;
+    }
+    // algorithmic bytes: 12 B/particle + 4 B/voxel offsets + 16 B/voxel outputs
+    FB_LAUNCH(w, "p2g_gather", w->pts.n * 12 + (size_t)n * LEAF * 20)
+        p2g_gather_kernel<<<n, P2G_THREADS, smemBytes, w->stream>>>(p);
+    check_launch("p2g_gather");
+
+    // air ring: airmask = dilate26(topo) \ topo ; final sdf mask = topo + ring voxels with a liquid face neighbour
+    mask_dilate(w, *pool, topoMask.p, ring.p, true);
+    FB_LAUNCH(w, "p2g_air_ring", (size_t)n * (2048 + 256)) air_ring_kernel<<<n, 512, 0, w->stream>>>(pool->view(), topoMask.p, ring.p, nsdf.val.p, nsdf.mask.p, dx, sdf.bg);
+    check_launch("air_ring");
+    // leaves of the reference's sdf tree: everything touched by the dilated topology (:1380)
+    mark_alloc_from_mask(w, ring.p, n, nsdf.alloc.p);
+
+    // post-P2G copy before extrapolation (FF/FLIP_vdb.cpp:1386), then extrapolate + to_vec3
+    GridV npost;
+    grid_copy(w, npost, nvel);
+    finish_vec3(w, npost, chMask.p);
+    union_extrapolate(w, velExtraLayer, nvel, chMask.p, nsdf.mask.p);
+    finish_vec3(w, nvel, chMask.p);
+
+    int ov = 0;
+    FB_CUDA(cudaMemcpyAsync(&ov, overflow.p, 4, cudaMemcpyDeviceToHost, w->stream));
+    sync(w);
+    FB_REQUIRE(ov == 0, FLIPB200_ERR_ARG, "FLIP_P2G: a voxel holds more than 1400 particles");
+    vel = std::move(nvel);
+    post = std::move(npost);
+    sdf = std::move(nsdf);
+}
+
+}  // namespace fb

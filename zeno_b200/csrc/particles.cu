@@ -1,0 +1,194 @@
+// libflipb200 -- particle store: initial binning (K1) and the stable counting sort by
+// (leaf slot, voxel offset) used by K1 and by the re-binning after advection (K2).
+//
+// The sort is bit-exact and deterministic: it produces exactly the order of a stable sort by
+// key of the source order (what openvdb's PointPartitioner and the reference's per-leaf
+// counting sort, FF/FLIP_vdb.cpp:3406-3476, produce for a sequential traversal).
+//   histogram (integer atomics)  ->  exclusive scan  ->  scatter source indices  ->
+//   per-voxel ascending fix-up of the (few) indices  ->  coalesced payload gather.
+#include "world.cuh"
+
+namespace fb {
+namespace {
+
+constexpr uint32_t KEY_DROPPED = 0xffffffffu;
+constexpr uint32_t VOXEL_CAP = 28;  // "existing_par > 27 -> drop" (FF/FLIP_vdb.cpp:711-714,742-745)
+
+// K1: particleArrayToGrid (projects/zenvdb/SetVDBPointDataGrid.cpp:17-72)
+//  index = double(pos) * (1.0/double(dx))       (openvdb/math/Maps.h:688,751-753)
+//  ijk   = floor(index + 0.5)                   (math/Coord.h:50-53, math/Math.h:822-823)
+//  P     = fxpt16(float(index - ijk))           (points/PointConversion.h:700-718)
+//  v     = half(vel)                            (TruncateCodec)
+__global__ void bin_encode_kernel(const float* __restrict__ pos, const float* __restrict__ vel, uint64_t n,
+                                  double inv, int3* __restrict__ ijkOut, uint32_t* __restrict__ w0,
+                                  uint32_t* __restrict__ w1, uint32_t* __restrict__ w2) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c[3];
+    uint32_t P[3], V[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        double idx = __dmul_rn((double)pos[3 * i + a], inv);
+        c[a] = (int)floor(__dadd_rn(idx, 0.5));
+        float local = (float)__dsub_rn(idx, (double)c[a]);
+        P[a] = fx_encode(local);
+        V[a] = h_encode(vel ? vel[3 * i + a] : 0.f);
+    }
+    ijkOut[i] = make_int3(c[0], c[1], c[2]);
+    w0[i] = P[0] | (P[1] << 16);
+    w1[i] = P[2] | (V[0] << 16);
+    w2[i] = V[1] | (V[2] << 16);
+}
+__global__ void ijk_to_origin_kernel(const int3* __restrict__ ijk, uint64_t n, int3* __restrict__ origins) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int3 c = ijk[i];
+    origins[i] = make_int3(c.x & ~7, c.y & ~7, c.z & ~7);
+}
+__global__ void ijk_to_key_kernel(TopoView t, const int3* __restrict__ ijk, const uint8_t* __restrict__ alive,
+                                  uint64_t n, uint32_t* __restrict__ keys) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (alive && !alive[i]) { keys[i] = KEY_DROPPED; return; }
+    int3 c = ijk[i];
+    int l = topo_find(t, c.x, c.y, c.z);
+    keys[i] = l < 0 ? KEY_DROPPED : (uint32_t)l * LEAF + (uint32_t)voxel_off(c.x, c.y, c.z);
+}
+__global__ void hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ count) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = keys[i];
+    if (k != KEY_DROPPED) atomicAdd(&count[k], 1u);
+}
+__global__ void cap_kernel(const uint32_t* __restrict__ count, uint32_t* __restrict__ capped, size_t nv, uint32_t cap) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nv) capped[i] = min(count[i], cap);
+}
+__global__ void scatter_kernel(const uint32_t* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ start,
+                               uint32_t* __restrict__ fill, uint32_t* __restrict__ perm) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = keys[i];
+    if (k == KEY_DROPPED) return;
+    uint32_t r = atomicAdd(&fill[k], 1u);
+    perm[start[k] + r] = (uint32_t)i;
+}
+// per voxel: ascending order of the source indices (= stable), then apply the per-voxel cap
+__global__ void fixup_kernel(const uint32_t* __restrict__ startU, const uint32_t* __restrict__ startC,
+                             size_t nv, uint32_t* __restrict__ perm, uint32_t* __restrict__ perm2) {
+    size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    uint32_t b = startU[v], e = startU[v + 1];
+    for (uint32_t i = b + 1; i < e; i++) {
+        uint32_t x = perm[i];
+        uint32_t j = i;
+        while (j > b && perm[j - 1] > x) { perm[j] = perm[j - 1]; j--; }
+        perm[j] = x;
+    }
+    uint32_t cb = startC[v], ce = startC[v + 1];
+    for (uint32_t j = 0; j < ce - cb; j++) perm2[cb + j] = perm[b + j];
+}
+__global__ void gather_kernel(const uint32_t* __restrict__ perm, uint64_t m, const uint32_t* __restrict__ i0,
+                              const uint32_t* __restrict__ i1, const uint32_t* __restrict__ i2,
+                              uint32_t* __restrict__ o0, uint32_t* __restrict__ o1, uint32_t* __restrict__ o2) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint32_t s = perm[i];
+    o0[i] = __ldg(&i0[s]);
+    o1[i] = __ldg(&i1[s]);
+    o2[i] = __ldg(&i2[s]);
+}
+inline unsigned nblk(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// keys -> sorted store on topo. cap = 0 disables the per-voxel cap.
+void sort_by_key(World* w, const TopoPtr& topo, const uint32_t* keys, uint64_t n, uint32_t cap,
+                 const uint32_t* i0, const uint32_t* i1, const uint32_t* i2, Particles& out, uint64_t* keptOut) {
+    size_t nv = (size_t)topo->n * LEAF;
+    DBuf<uint32_t> count(nv + 1, w->stream), startU(nv + 1, w->stream), fillc(nv + 1, w->stream);
+    count.zero();
+    fillc.zero();
+    if (n) {
+        FB_LAUNCH(w, "rebin_hist", n * 8) hist_kernel<<<nblk(n, 256), 256, 0, w->stream>>>(keys, n, count.p);
+        check_launch("hist");
+    }
+    uint64_t totalU = 0, totalC = 0;
+    exclusive_scan_u32(w, count.p, startU.p, nv + 1, cap ? nullptr : &totalU);
+    DBuf<uint32_t> startC;
+    if (cap) {
+        startC.alloc(nv + 1, w->stream);
+        FB_LAUNCH(w, "rebin_cap", nv * 8) cap_kernel<<<nblk(nv + 1, 256), 256, 0, w->stream>>>(count.p, startC.p, nv + 1, cap);
+        check_launch("cap");
+        exclusive_scan_u32(w, startC.p, startC.p, nv + 1, &totalC);
+    } else totalC = totalU;
+    const uint32_t* sC = cap ? startC.p : startU.p;
+    DBuf<uint32_t> perm(n ? n : 1, w->stream), perm2(totalC ? totalC : 1, w->stream);
+    if (n) {
+        FB_LAUNCH(w, "rebin_scatter", n * 12) scatter_kernel<<<nblk(n, 256), 256, 0, w->stream>>>(keys, n, startU.p, fillc.p, perm.p);
+        check_launch("scatter");
+        FB_LAUNCH(w, "rebin_fixup", nv * 8 + n * 12) fixup_kernel<<<nblk(nv, 256), 256, 0, w->stream>>>(startU.p, sC, nv, perm.p, perm2.p);
+        check_launch("fixup");
+    }
+    out.topo = topo;
+    out.n = totalC;
+    DBuf<uint32_t> o0(totalC ? totalC : 1, w->stream), o1(totalC ? totalC : 1, w->stream), o2(totalC ? totalC : 1, w->stream);
+    if (totalC) {
+        FB_LAUNCH(w, "rebin_gather", totalC * 28) gather_kernel<<<nblk(totalC, 256), 256, 0, w->stream>>>(perm2.p, totalC, i0, i1, i2, o0.p, o1.p, o2.p);
+        check_launch("gather");
+    }
+    out.w0 = std::move(o0); out.w1 = std::move(o1); out.w2 = std::move(o2);
+    if (cap) out.voxelStart = std::move(startC);
+    else out.voxelStart = std::move(startU);
+    if (keptOut) *keptOut = totalC;
+}
+}  // namespace
+
+void bin_from_points(World* w, const float* pos_host, const float* vel_host, uint64_t n) {
+    DBuf<float> pos(3 * n + 1, w->stream), vel;
+    FB_CUDA(cudaMemcpyAsync(pos.p, pos_host, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, w->stream));
+    if (vel_host) {
+        vel.alloc(3 * n + 1, w->stream);
+        FB_CUDA(cudaMemcpyAsync(vel.p, vel_host, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, w->stream));
+    }
+    DBuf<int3> ijk(n + 1, w->stream), origins(n + 1, w->stream);
+    DBuf<uint32_t> w0(n + 1, w->stream), w1(n + 1, w->stream), w2(n + 1, w->stream), keys(n + 1, w->stream);
+    const double inv = 1.0 / (double)w->dx;
+    if (n) {
+        FB_LAUNCH(w, "bin_encode", n * 48) bin_encode_kernel<<<nblk(n, 256), 256, 0, w->stream>>>(pos.p, vel.p, n, inv, ijk.p, w0.p, w1.p, w2.p);
+        check_launch("bin_encode");
+        FB_LAUNCH(w, "bin_origins", n * 24) ijk_to_origin_kernel<<<nblk(n, 256), 256, 0, w->stream>>>(ijk.p, n, origins.p);
+        check_launch("ijk_to_origin");
+    }
+    TopoPtr pool = topo_from_origins_dev(w, origins.p, (int)n, /*ring=*/true);
+    if (n) {
+        FB_LAUNCH(w, "bin_keys", n * 16) ijk_to_key_kernel<<<nblk(n, 256), 256, 0, w->stream>>>(pool->view(), ijk.p, nullptr, n, keys.p);
+        check_launch("ijk_to_key");
+    }
+    Particles out;
+    sort_by_key(w, pool, keys.p, n, /*cap=*/0, w0.p, w1.p, w2.p, out, nullptr);
+    w->pts = std::move(out);
+    w->pool = pool;
+    w->dropped = 0;
+}
+
+void rebin_particles(World* w, const TopoPtr& newPool, const uint32_t* keys_dev, uint64_t nOld,
+                     DBuf<uint32_t>& w0, DBuf<uint32_t>& w1, DBuf<uint32_t>& w2) {
+    Particles out;
+    uint64_t kept = 0;
+    sort_by_key(w, newPool, keys_dev, nOld, VOXEL_CAP, w0.p, w1.p, w2.p, out, &kept);
+    w->dropped = nOld - kept;
+    w->pts = std::move(out);
+}
+
+// helpers shared with g2p.cu
+void origins_from_ijk(World* w, const int3* ijk, uint64_t n, int3* origins) {
+    if (!n) return;
+    FB_LAUNCH(w, "bin_origins", n * 24) ijk_to_origin_kernel<<<nblk(n, 256), 256, 0, w->stream>>>(ijk, n, origins);
+    check_launch("ijk_to_origin");
+}
+void keys_from_ijk(World* w, const TopoPtr& t, const int3* ijk, const uint8_t* alive, uint64_t n, uint32_t* keys) {
+    if (!n) return;
+    FB_LAUNCH(w, "bin_keys", n * 17) ijk_to_key_kernel<<<nblk(n, 256), 256, 0, w->stream>>>(t->view(), ijk, alive, n, keys);
+    check_launch("ijk_to_key");
+}
+
+}  // namespace fb

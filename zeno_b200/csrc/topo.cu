@@ -1,0 +1,361 @@
+// libflipb200 -- leaf topology (dense directory), grid storage, pool management, mask morphology.
+// Replaces what the reference gets from openvdb::tree::Tree4 + tools::dilateActiveValues +
+// TopologyCopy/topologyUnion on this path.
+#include "world.cuh"
+
+namespace fb {
+namespace {
+
+__global__ void bbox_kernel(const int3* __restrict__ origins, int count, int* __restrict__ bb) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+    if (i < count) {
+        int3 o = origins[i];
+        lo[0] = hi[0] = o.x >> 3; lo[1] = hi[1] = o.y >> 3; lo[2] = hi[2] = o.z >> 3;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        for (int d = 16; d > 0; d >>= 1) {
+            lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
+            hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
+        }
+        if ((threadIdx.x & 31) == 0 && lo[a] != INT_MAX) {
+            atomicMin(&bb[a], lo[a]);
+            atomicMax(&bb[3 + a], hi[a]);
+        }
+    }
+}
+__global__ void mark_kernel(const int3* __restrict__ origins, int count, int3 dmin, int3 ddim, int ring,
+                            uint32_t* __restrict__ flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    int3 o = origins[i];
+    int lx = (o.x >> 3) - dmin.x, ly = (o.y >> 3) - dmin.y, lz = (o.z >> 3) - dmin.z;
+    for (int a = -ring; a <= ring; a++)
+        for (int b = -ring; b <= ring; b++)
+            for (int c = -ring; c <= ring; c++)
+                flags[((lx + a) * ddim.y + (ly + b)) * ddim.z + (lz + c)] = 1u;
+}
+__global__ void assign_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ slots,
+                              int3 dmin, int3 ddim, int* __restrict__ dir, int3* __restrict__ origin) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = ddim.x * ddim.y * ddim.z;
+    if (i >= total) return;
+    if (flags[i]) {
+        int s = (int)slots[i];
+        dir[i] = s;
+        int lz = i % ddim.z, ly = (i / ddim.z) % ddim.y, lx = i / (ddim.z * ddim.y);
+        origin[s] = make_int3((lx + dmin.x) * 8, (ly + dmin.y) * 8, (lz + dmin.z) * 8);
+    } else dir[i] = -1;
+}
+__global__ void nbr27_kernel(TopoView t, int* __restrict__ nbr) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= t.n * 27) return;
+    int l = i / 27, k = i % 27;
+    int3 o = t.origin[l];
+    int a = k / 9 - 1, b = (k / 3) % 3 - 1, c = k % 3 - 1;
+    nbr[i] = topo_find(t, o.x + 8 * a, o.y + 8 * b, o.z + 8 * c);
+}
+__global__ void fill_kernel(float* __restrict__ p, float v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// copy leaves of an old grid into the storage of a new topology
+__global__ void rebase_kernel(TopoView oldT, TopoView newT, const float* __restrict__ oldVal,
+                              float* __restrict__ newVal, const uint64_t* __restrict__ oldMask,
+                              uint64_t* __restrict__ newMask, const uint8_t* __restrict__ oldAlloc,
+                              uint8_t* __restrict__ newAlloc) {
+    int l = blockIdx.x;
+    int3 o = oldT.origin[l];
+    int nl = topo_find(newT, o.x, o.y, o.z);
+    if (nl < 0) return;
+    for (int i = threadIdx.x; i < LEAF; i += blockDim.x) newVal[(size_t)nl * LEAF + i] = oldVal[(size_t)l * LEAF + i];
+    if (oldMask && threadIdx.x < 8) newMask[(size_t)nl * 8 + threadIdx.x] = oldMask[(size_t)l * 8 + threadIdx.x];
+    if (oldAlloc && threadIdx.x == 0) newAlloc[nl] = oldAlloc[l];
+}
+__global__ void nonempty_origins_kernel(TopoView t, const uint64_t* __restrict__ mask, const uint8_t* __restrict__ alloc,
+                                        int3* __restrict__ out, uint32_t* __restrict__ counter) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= t.n) return;
+    uint64_t any = alloc ? alloc[l] : 0;
+    for (int k = 0; k < 8; k++) any |= mask[(size_t)l * 8 + k];
+    if (any) out[atomicAdd(counter, 1u)] = t.origin[l];
+}
+__global__ void particle_leaf_origins_kernel(TopoView t, const uint32_t* __restrict__ voxelStart,
+                                             int3* __restrict__ out, uint32_t* __restrict__ counter) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= t.n) return;
+    if (voxelStart[(size_t)(l + 1) * LEAF] > voxelStart[(size_t)l * LEAF]) out[atomicAdd(counter, 1u)] = t.origin[l];
+}
+__global__ void pts_counts_remap_kernel(TopoView oldT, TopoView newT, const uint32_t* __restrict__ oldStart,
+                                        uint32_t* __restrict__ newCount) {
+    int l = blockIdx.x;
+    int3 o = oldT.origin[l];
+    int nl = topo_find(newT, o.x, o.y, o.z);
+    if (nl < 0) return;
+    for (int i = threadIdx.x; i < LEAF; i += blockDim.x) {
+        size_t k = (size_t)l * LEAF + i;
+        newCount[(size_t)nl * LEAF + i] = oldStart[k + 1] - oldStart[k];
+    }
+}
+// dilation: one CTA of 512 threads per leaf, neighbour masks staged in shared memory
+__global__ void __launch_bounds__(512) dilate_kernel(TopoView t, const uint64_t* __restrict__ in,
+                                                     uint64_t* __restrict__ out, int nn26) {
+    __shared__ uint64_t sm[27 * 8];
+    int l = blockIdx.x;
+    for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) {
+        int nb = t.nbr27[l * 27 + i / 8];
+        sm[i] = nb >= 0 ? in[(size_t)nb * 8 + (i & 7)] : 0ull;
+    }
+    __syncthreads();
+    int off = threadIdx.x;
+    int x = off >> 6, y = (off >> 3) & 7, z = off & 7;
+    auto get = [&](int gx, int gy, int gz) -> bool {  // coordinates in [-1, 8]
+        int li = ((gx < 0 ? 0 : (gx < 8 ? 1 : 2)) * 9) + ((gy < 0 ? 0 : (gy < 8 ? 1 : 2)) * 3) +
+                 (gz < 0 ? 0 : (gz < 8 ? 1 : 2));
+        int o = ((gx & 7) << 6) | ((gy & 7) << 3) | (gz & 7);
+        return (sm[li * 8 + (o >> 6)] >> (o & 63)) & 1ull;
+    };
+    bool on = false;
+    if (nn26) {
+        for (int a = -1; a <= 1; a++)
+            for (int b = -1; b <= 1; b++)
+                for (int c = -1; c <= 1; c++) on |= get(x + a, y + b, z + c);
+    } else {
+        on = get(x, y, z) | get(x - 1, y, z) | get(x + 1, y, z) | get(x, y - 1, z) | get(x, y + 1, z) |
+             get(x, y, z - 1) | get(x, y, z + 1);
+    }
+    unsigned b = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0) reinterpret_cast<uint32_t*>(out)[(size_t)l * 16 + (threadIdx.x >> 5)] = b;
+}
+__global__ void popcount_kernel(const uint64_t* __restrict__ mask, size_t nWords, unsigned long long* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned c = i < nWords ? __popcll(mask[i]) : 0u;
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+__global__ void solid_view_kernel(TopoView pool, TopoView st, const float* __restrict__ sVal, float bg,
+                                  float* __restrict__ view, uint8_t* __restrict__ exists) {
+    int l = blockIdx.x;
+    int3 o = pool.origin[l];
+    int sl = st.n > 0 ? topo_find(st, o.x, o.y, o.z) : -1;
+    if (exists && threadIdx.x == 0) exists[l] = sl >= 0;
+    for (int i = threadIdx.x; i < LEAF; i += blockDim.x)
+        view[(size_t)l * LEAF + i] = sl >= 0 ? sVal[(size_t)sl * LEAF + i] : bg;
+}
+}  // namespace
+
+static inline unsigned nblk(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+TopoPtr topo_from_origins_dev(World* w, const int3* origins_dev, int count, bool ring) {
+    auto t = std::make_shared<Topo>();
+    t->epoch = ++w->epochCounter;
+    if (count == 0) {
+        t->n = 0; t->dmin = make_int3(0, 0, 0); t->ddim = make_int3(0, 0, 0);
+        return t;
+    }
+    DBuf<int> bb(6, w->stream);
+    int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+    FB_CUDA(cudaMemcpyAsync(bb.p, init, sizeof(init), cudaMemcpyHostToDevice, w->stream));
+    FB_LAUNCH(w, "topo_bbox", count * 12) bbox_kernel<<<nblk(count, 256), 256, 0, w->stream>>>(origins_dev, count, bb.p);
+    check_launch("bbox");
+    int h[6];
+    FB_CUDA(cudaMemcpyAsync(h, bb.p, sizeof(h), cudaMemcpyDeviceToHost, w->stream));
+    sync(w);
+    int r = ring ? 1 : 0;
+    t->dmin = make_int3(h[0] - r, h[1] - r, h[2] - r);
+    t->ddim = make_int3(h[3] - h[0] + 1 + 2 * r, h[4] - h[1] + 1 + 2 * r, h[5] - h[2] + 1 + 2 * r);
+    size_t vol = (size_t)t->ddim.x * t->ddim.y * t->ddim.z;
+    FB_REQUIRE(vol <= ((size_t)1 << 28), FLIPB200_ERR_DOMAIN,
+               "leaf bounding box exceeds the dense directory limit (2^28 leaves)");
+    DBuf<uint32_t> flags(vol, w->stream), slots(vol, w->stream);
+    flags.zero();
+    FB_LAUNCH(w, "topo_mark", count * 12) mark_kernel<<<nblk(count, 256), 256, 0, w->stream>>>(origins_dev, count, t->dmin, t->ddim, r, flags.p);
+    check_launch("mark");
+    uint64_t total = 0;
+    exclusive_scan_u32(w, flags.p, slots.p, vol, &total);
+    t->n = (int)total;
+    t->dir.alloc(vol, w->stream);
+    t->origin.alloc(t->n, w->stream);
+    FB_LAUNCH(w, "topo_assign", vol * 12) assign_kernel<<<nblk(vol, 256), 256, 0, w->stream>>>(flags.p, slots.p, t->dmin, t->ddim, t->dir.p, t->origin.p);
+    check_launch("assign");
+    t->nbr27.alloc((size_t)t->n * 27, w->stream);
+    FB_LAUNCH(w, "topo_nbr27", t->n * 27 * 8) nbr27_kernel<<<nblk((size_t)t->n * 27, 256), 256, 0, w->stream>>>(t->view(), t->nbr27.p);
+    check_launch("nbr27");
+    return t;
+}
+
+TopoPtr topo_from_origins_host(World* w, const int32_t* origins, int count, bool ring) {
+    DBuf<int3> d(count, w->stream);
+    if (count) FB_CUDA(cudaMemcpyAsync(d.p, origins, sizeof(int3) * (size_t)count, cudaMemcpyHostToDevice, w->stream));
+    return topo_from_origins_dev(w, d.p, count, ring);
+}
+
+static void fill(World* w, float* p, float v, size_t n) {
+    if (!n) return;
+    if (v == 0.f) { FB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(float), w->stream)); return; }
+    FB_LAUNCH(w, "fill", n * 4) fill_kernel<<<nblk(n, 256), 256, 0, w->stream>>>(p, v, n);
+    check_launch("fill");
+}
+
+void grid_alloc(World* w, GridF& g, const TopoPtr& t, float bg) {
+    g.topo = t; g.bg = bg;
+    size_t n = (size_t)t->n;
+    g.val.alloc(n * LEAF, w->stream);
+    g.mask.alloc(n * 8, w->stream);
+    g.alloc.alloc(n ? n : 1, w->stream);
+    fill(w, g.val.p, bg, n * LEAF);
+    g.mask.zero();
+    g.alloc.zero();
+}
+void grid_alloc(World* w, GridV& g, const TopoPtr& t, const float bg[3]) {
+    g.topo = t;
+    size_t n = (size_t)t->n;
+    for (int c = 0; c < 3; c++) {
+        g.bg[c] = bg[c];
+        g.val[c].alloc(n * LEAF, w->stream);
+        fill(w, g.val[c].p, bg[c], n * LEAF);
+    }
+    g.mask.alloc(n * 8, w->stream);
+    g.mask.zero();
+}
+void grid_rebase(World* w, GridF& g, const TopoPtr& t) {
+    if (g.topo == t) return;
+    GridF ng;
+    grid_alloc(w, ng, t, g.bg);
+    if (g.topo && g.topo->n > 0) {
+        FB_LAUNCH(w, "grid_rebase", (size_t)g.topo->n * 4096) rebase_kernel<<<g.topo->n, 256, 0, w->stream>>>(g.topo->view(), t->view(), g.val.p, ng.val.p, g.mask.p, ng.mask.p, g.alloc.p, ng.alloc.p);
+        check_launch("rebase");
+    }
+    g = std::move(ng);
+}
+void grid_rebase(World* w, GridV& g, const TopoPtr& t) {
+    if (g.topo == t) return;
+    GridV ng;
+    grid_alloc(w, ng, t, g.bg);
+    if (g.topo && g.topo->n > 0) {
+        for (int c = 0; c < 3; c++) {
+            FB_LAUNCH(w, "grid_rebase", (size_t)g.topo->n * 4096) rebase_kernel<<<g.topo->n, 256, 0, w->stream>>>(g.topo->view(), t->view(), g.val[c].p, ng.val[c].p, c == 0 ? g.mask.p : nullptr, ng.mask.p, nullptr, nullptr);
+            check_launch("rebase");
+        }
+    }
+    g = std::move(ng);
+}
+void grid_copy(World* w, GridF& dst, const GridF& src) {
+    dst.topo = src.topo; dst.bg = src.bg;
+    dst.val.alloc(src.val.n, w->stream);
+    dst.mask.alloc(src.mask.n, w->stream);
+    dst.alloc.alloc(src.alloc.n, w->stream);
+    if (src.alloc.n) FB_CUDA(cudaMemcpyAsync(dst.alloc.p, src.alloc.p, src.alloc.n, cudaMemcpyDeviceToDevice, w->stream));
+    if (src.val.n) FB_CUDA(cudaMemcpyAsync(dst.val.p, src.val.p, src.val.n * 4, cudaMemcpyDeviceToDevice, w->stream));
+    if (src.mask.n) FB_CUDA(cudaMemcpyAsync(dst.mask.p, src.mask.p, src.mask.n * 8, cudaMemcpyDeviceToDevice, w->stream));
+}
+void grid_copy(World* w, GridV& dst, const GridV& src) {
+    dst.topo = src.topo;
+    for (int c = 0; c < 3; c++) {
+        dst.bg[c] = src.bg[c];
+        dst.val[c].alloc(src.val[c].n, w->stream);
+        if (src.val[c].n) FB_CUDA(cudaMemcpyAsync(dst.val[c].p, src.val[c].p, src.val[c].n * 4, cudaMemcpyDeviceToDevice, w->stream));
+    }
+    dst.mask.alloc(src.mask.n, w->stream);
+    if (src.mask.n) FB_CUDA(cudaMemcpyAsync(dst.mask.p, src.mask.p, src.mask.n * 8, cudaMemcpyDeviceToDevice, w->stream));
+}
+
+void ensure_pool(World* w, std::initializer_list<int> gridIds, bool includeParticles) {
+    bool ok = (bool)w->pool;
+    auto topoOf = [&](int id) -> TopoPtr { return is_vec_grid(id) ? w->V(id).topo : w->F(id).topo; };
+    if (ok) {
+        for (int id : gridIds) { TopoPtr t = topoOf(id); if (t && t != w->pool) ok = false; }
+        if (includeParticles && w->pts.topo && w->pts.topo != w->pool) ok = false;
+    }
+    if (!ok) {
+        // candidate leaves: every non-empty leaf of the listed grids + every leaf holding particles
+        size_t cap = 0;
+        for (int id : gridIds) { TopoPtr t = topoOf(id); if (t) cap += t->n; }
+        if (w->pts.topo) cap += w->pts.topo->n;
+        DBuf<int3> cand(cap ? cap : 1, w->stream);
+        DBuf<uint32_t> counter(1, w->stream);
+        counter.zero();
+        for (int id : gridIds) {
+            TopoPtr t = topoOf(id);
+            if (!t || t->n == 0) continue;
+            const uint64_t* m = is_vec_grid(id) ? w->V(id).mask.p : w->F(id).mask.p;
+            const uint8_t* al = is_vec_grid(id) ? nullptr : w->F(id).alloc.p;
+            FB_LAUNCH(w, "pool_candidates", t->n * 76) nonempty_origins_kernel<<<nblk(t->n, 128), 128, 0, w->stream>>>(t->view(), m, al, cand.p, counter.p);
+            check_launch("nonempty_origins");
+        }
+        if (w->pts.topo && w->pts.topo->n > 0 && w->pts.n > 0) {
+            FB_LAUNCH(w, "pool_candidates", w->pts.topo->n * 20) particle_leaf_origins_kernel<<<nblk(w->pts.topo->n, 128), 128, 0, w->stream>>>(w->pts.topo->view(), w->pts.voxelStart.p, cand.p, counter.p);
+            check_launch("particle_leaf_origins");
+        }
+        uint32_t cnt = 0;
+        FB_CUDA(cudaMemcpyAsync(&cnt, counter.p, 4, cudaMemcpyDeviceToHost, w->stream));
+        sync(w);
+        w->pool = topo_from_origins_dev(w, cand.p, (int)cnt, /*ring=*/true);
+    }
+    for (int id : gridIds) {
+        if (is_vec_grid(id)) {
+            if (!w->V(id).topo) grid_alloc(w, w->V(id), w->pool, w->V(id).bg);
+            else grid_rebase(w, w->V(id), w->pool);
+        } else {
+            if (!w->F(id).topo) grid_alloc(w, w->F(id), w->pool, w->F(id).bg);
+            else grid_rebase(w, w->F(id), w->pool);
+        }
+    }
+    if (includeParticles && w->pts.topo != w->pool) {
+        // same lexicographic leaf order in both topologies: only the per-voxel offsets move
+        size_t nv = (size_t)w->pool->n * LEAF;
+        DBuf<uint32_t> ns(nv + 1, w->stream);
+        ns.zero();
+        if (w->pts.topo && w->pts.topo->n > 0 && w->pts.n > 0) {
+            FB_LAUNCH(w, "pts_remap", (size_t)w->pts.topo->n * 4096) pts_counts_remap_kernel<<<w->pts.topo->n, 256, 0, w->stream>>>(w->pts.topo->view(), w->pool->view(), w->pts.voxelStart.p, ns.p);
+            check_launch("pts_remap");
+        }
+        exclusive_scan_u32(w, ns.p, ns.p, nv + 1, nullptr);
+        w->pts.voxelStart = std::move(ns);
+        w->pts.topo = w->pool;
+    }
+}
+
+void refresh_solid_views(World* w) {
+    if (!w->pool) return;
+    if (w->solidViewEpoch == w->pool->epoch) return;
+    size_t n = (size_t)w->pool->n;
+    w->solidSdfView.alloc(n * LEAF, w->stream);
+    w->solidLeafExists.alloc(n ? n : 1, w->stream);
+    for (int c = 0; c < 3; c++) w->solidVelView[c].alloc(n * LEAF, w->stream);
+    if (n) {
+        GridF& s = w->F(FLIPB200_SOLID_SDF);
+        TopoView sv = s.topo ? s.topo->view() : TopoView{0, make_int3(0, 0, 0), make_int3(0, 0, 0), nullptr, nullptr, nullptr};
+        FB_LAUNCH(w, "solid_view", n * 4096) solid_view_kernel<<<(unsigned)n, 256, 0, w->stream>>>(w->pool->view(), sv, s.val.p, s.bg, w->solidSdfView.p, w->solidLeafExists.p);
+        check_launch("solid_view");
+        GridV& u = w->V(FLIPB200_SOLID_VELOCITY);
+        TopoView uv = u.topo ? u.topo->view() : TopoView{0, make_int3(0, 0, 0), make_int3(0, 0, 0), nullptr, nullptr, nullptr};
+        for (int c = 0; c < 3; c++) {
+            FB_LAUNCH(w, "solid_view", n * 4096) solid_view_kernel<<<(unsigned)n, 256, 0, w->stream>>>(w->pool->view(), uv, u.val[c].p, u.bg[c], w->solidVelView[c].p, nullptr);
+            check_launch("solid_view");
+        }
+    }
+    w->solidViewEpoch = w->pool->epoch;
+}
+
+void mask_dilate(World* w, const Topo& t, const uint64_t* in, uint64_t* out, bool nn26) {
+    if (t.n == 0) return;
+    FB_LAUNCH(w, "mask_dilate", (size_t)t.n * 128) dilate_kernel<<<t.n, 512, 0, w->stream>>>(t.view(), in, out, nn26 ? 1 : 0);
+    check_launch("dilate");
+}
+uint64_t mask_count(World* w, const uint64_t* mask, int nLeaves) {
+    DBuf<unsigned long long> c(1, w->stream);
+    c.zero();
+    size_t nw = (size_t)nLeaves * 8;
+    if (nw) {
+        FB_LAUNCH(w, "mask_count", nw * 8) popcount_kernel<<<nblk(nw, 256), 256, 0, w->stream>>>(mask, nw, c.p);
+        check_launch("popcount");
+    }
+    unsigned long long h = 0;
+    FB_CUDA(cudaMemcpyAsync(&h, c.p, 8, cudaMemcpyDeviceToHost, w->stream));
+    sync(w);
+    return h;
+}
+
+}  // namespace fb

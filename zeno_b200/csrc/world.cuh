@@ -1,0 +1,143 @@
+// libflipb200 -- world state + internal API shared between the .cu files.
+#pragma once
+#include "common.cuh"
+#include "../../include/flipb200.h"
+
+namespace fb {
+
+struct ProfEntry { double ms = 0; uint64_t launches = 0; uint64_t bytes = 0; };
+struct PendingEvt { cudaEvent_t a, b; std::string name; uint64_t bytes; };
+
+struct SolverStats {
+    int iterations = 0, status = 0, levels = 0, numDof = 0;
+    float relResidual = 0.f;
+    std::vector<float> history;
+};
+
+struct Comm;  // NCCL state (comm.cu)
+
+}  // namespace fb
+
+struct flipb200_world {
+    int device = 0;
+    float dx = 0.f;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    bool profiling = false;
+    std::map<std::string, fb::ProfEntry> prof;
+    std::vector<fb::PendingEvt> pending;
+    std::vector<cudaEvent_t> evtPool;
+
+    // the fluid-band pool: particle leaves + one ring of leaves; all band grids live on it
+    fb::TopoPtr pool;
+    uint64_t epochCounter = 0;
+
+    fb::GridV vgrid[5];   // ids 0..4
+    fb::GridF fgrid[10];  // ids 5..9 used
+    bool hasSolidSDF = false, hasSolidVel = false;
+    fb::Particles pts;
+
+    // views of the static solid grids resampled onto the pool (rebuilt when the pool changes)
+    uint64_t solidViewEpoch = ~0ull;
+    fb::DBuf<float> solidSdfView;        // [pool n][512]
+    fb::DBuf<float> solidVelView[3];     // [pool n][512]
+    fb::DBuf<uint8_t> solidLeafExists;   // [pool n]
+
+    uint64_t dropped = 0;
+    bool capturePreCodec = false;
+    fb::DBuf<float> preCodecPos, preCodecVel;
+    fb::DBuf<uint8_t> preCodecAlive;
+    uint64_t preCodecN = 0;
+
+    fb::SolverStats solver;
+    fb::Comm* comm = nullptr;
+    int rank = 0, nRanks = 1;
+
+    fb::GridV& V(int id) { return vgrid[id]; }
+    fb::GridF& F(int id) { return fgrid[id]; }
+};
+
+namespace fb {
+
+using World = flipb200_world;
+
+inline bool is_vec_grid(int id) { return id >= 0 && id <= FLIPB200_FACE_WEIGHT; }
+inline bool is_float_grid(int id) { return id >= FLIPB200_LIQUID_SDF && id < FLIPB200_NUM_GRIDS; }
+inline bool is_static_grid(int id) { return id == FLIPB200_SOLID_SDF || id == FLIPB200_SOLID_VELOCITY; }
+
+// ---- launch accounting -------------------------------------------------------------
+struct LaunchScope {
+    World* w; const char* name; uint64_t bytes; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(World* w_, const char* name_, uint64_t bytes_) : w(w_), name(name_), bytes(bytes_) {
+        w->launches++;
+        if (w->profiling) {
+            auto get = [&]() {
+                if (!w->evtPool.empty()) { cudaEvent_t e = w->evtPool.back(); w->evtPool.pop_back(); return e; }
+                cudaEvent_t e; cudaEventCreate(&e); return e;
+            };
+            a = get(); b = get();
+            cudaEventRecord(a, w->stream);
+        }
+    }
+    ~LaunchScope() {
+        if (a) {
+            cudaEventRecord(b, w->stream);
+            w->pending.push_back(PendingEvt{a, b, name, bytes});
+        }
+    }
+};
+// usage: FB_LAUNCH(w, "p2g_gather", bytes) kernel<<<grid, block, smem, w->stream>>>(...);
+#define FB_LAUNCH(w, name, bytes) if (fb::LaunchScope ls_{(w), (name), (uint64_t)(bytes)}; true)
+
+inline void check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw Error(2, std::string(what) + ": " + cudaGetErrorString(e));
+}
+inline void sync(World* w) { FB_CUDA(cudaStreamSynchronize(w->stream)); }
+
+// ---- topo.cu ------------------------------------------------------------------------
+// Build a topology from candidate leaf-origin voxel coordinates on the device (duplicates
+// allowed). ring: also add the 26 neighbour leaves of every candidate.
+TopoPtr topo_from_origins_dev(World* w, const int3* origins_dev, int count, bool ring);
+TopoPtr topo_from_origins_host(World* w, const int32_t* origins, int count, bool ring);
+void grid_alloc(World* w, GridF& g, const TopoPtr& t, float bg);              // values = bg, mask = 0
+void grid_alloc(World* w, GridV& g, const TopoPtr& t, const float bg[3]);
+void grid_rebase(World* w, GridF& g, const TopoPtr& t);                        // move onto t (lossless if t covers g)
+void grid_rebase(World* w, GridV& g, const TopoPtr& t);
+void grid_copy(World* w, GridF& dst, const GridF& src);
+void grid_copy(World* w, GridV& dst, const GridV& src);
+// makes sure w->pool exists, covers the particle leaves (+ring) and the listed band grids, and
+// that those grids live on it.
+void ensure_pool(World* w, std::initializer_list<int> gridIds, bool includeParticles);
+void refresh_solid_views(World* w);
+// mask morphology on the pool: out = dilate(in) (26- or 6-neighbourhood), in/out may not alias
+void mask_dilate(World* w, const Topo& t, const uint64_t* in, uint64_t* out, bool nn26);
+uint64_t mask_count(World* w, const uint64_t* mask, int nLeaves);
+
+// ---- scan.cu ------------------------------------------------------------------------
+// exclusive prefix sum of n uint32 (out may alias in); total (if non-null) receives the sum on the host
+void exclusive_scan_u32(World* w, const uint32_t* in, uint32_t* out, size_t n, uint64_t* total);
+
+// ---- particles.cu -------------------------------------------------------------------
+void bin_from_points(World* w, const float* pos_host, const float* vel_host, uint64_t n);
+// re-bin after advect: keys = target (pool slot*512 + off) or 0xffffffff for dropped particles
+void rebin_particles(World* w, const TopoPtr& newPool, const uint32_t* keys_dev, uint64_t nOld,
+                     DBuf<uint32_t>& w0, DBuf<uint32_t>& w1, DBuf<uint32_t>& w2);
+
+// ---- p2g.cu / g2p.cu / stencils.cu / poisson.cu --------------------------------------
+void p2g(World* w, float dx, int velExtraLayer);
+void g2p_advect_sheetty(World* w, float dt, float dx, int surfaceSize, int rkOrder, float picMin,
+                        float picMax, int flags);
+void face_weights(World* w);
+void pushout_sdf(World* w, float dx);
+void add_vector(World* w, float x, float y, float z);
+float cfl(World* w);
+void subtract_grad(World* w, float dt, float dx, int velExtraLayer);
+// per-channel masks are [3][n][8]; target topology mask = liquid SDF mask
+void union_extrapolate(World* w, int nLayer, GridV& vel, uint64_t* chMask, const uint64_t* targetMask);
+void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter);
+
+// ---- comm.cu ------------------------------------------------------------------------
+void comm_destroy(World* w);
+
+}  // namespace fb
