@@ -1,0 +1,176 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes driver of oracle/_build/liboracle.so (the CPU restatement of
+the reference's FastFLIP hot path). Imported only by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py, as the checker; the product (zeno_b200/) never
+imports it. Same method names and exchange formats as zeno_b200.abi.World."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "liboracle.so")
+GRID_IDS = {
+    "Velocity": 0, "PostAdvVelocity": 1, "ViscousVelocity": 2, "SolidVelocity": 3, "CellFWeight": 4,
+    "LiquidSDF": 5, "SolidSDF": 6, "Pressure": 7, "Divergence": 8, "Curvature": 9,
+}
+VEC_GRIDS = {"Velocity", "PostAdvVelocity", "ViscousVelocity", "SolidVelocity", "CellFWeight"}
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(_LIB):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-j8"])
+    else:
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-j8"])  # incremental, no-op when up to date
+    return _LIB
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        lib = C.CDLL(_LIB)
+        lib.orc_world_create.restype = C.c_void_p
+        lib.orc_cfl.restype = C.c_float
+        lib.orc_dropped.restype = C.c_uint64
+        lib.orc_fxpt16_encode.restype = C.c_uint16
+        lib.orc_fxpt16_decode.restype = C.c_float
+        lib.orc_half_encode.restype = C.c_uint16
+        lib.orc_half_decode.restype = C.c_float
+        lib.orc_fraction_inside2.restype = C.c_float
+        lib.orc_fraction_inside4.restype = C.c_float
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class OracleWorld:
+    def __init__(self, dx: float):
+        self.lib = load()
+        self.dx = float(dx)
+        self.h = C.c_void_p(self.lib.orc_world_create(C.c_float(dx)))
+
+    def close(self):
+        if self.h:
+            self.lib.orc_world_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_grid(self, name: str, g: Dict[str, np.ndarray]):
+        o = _c(g["origins"], np.int32).reshape(-1, 3)
+        m = _c(g["masks"], np.uint64).reshape(-1, 8)
+        v = _c(g["values"], np.float32)
+        bg = _c(g["bg"], np.float32)
+        rc = self.lib.orc_grid_set(self.h, C.c_int(GRID_IDS[name]), C.c_int(o.shape[0]), _p(o), _p(m), _p(v), _p(bg))
+        assert rc == 0
+
+    def get_grid(self, name: str) -> Dict[str, np.ndarray]:
+        gid = GRID_IDS[name]
+        nch = 3 if name in VEC_GRIDS else 1
+        n = self.lib.orc_grid_leaf_count(self.h, C.c_int(gid))
+        o = np.zeros((n, 3), np.int32)
+        m = np.zeros((n, 8), np.uint64)
+        v = np.zeros((n, nch, 512), np.float32)
+        bg = np.zeros(nch, np.float32)
+        assert self.lib.orc_grid_get(self.h, C.c_int(gid), _p(o), _p(m), _p(v), _p(bg)) == 0
+        return {"origins": o, "masks": m, "values": v, "bg": bg}
+
+    def set_particles(self, p: Dict[str, np.ndarray]):
+        o = _c(p["origins"], np.int32).reshape(-1, 3)
+        ve = _c(p["voxel_end"], np.uint32).reshape(-1, 512)
+        P = _c(p["P"], np.uint16).reshape(-1, 3)
+        v = _c(p["v"], np.uint16).reshape(-1, 3)
+        rc = self.lib.orc_particles_set(self.h, C.c_int(o.shape[0]), _p(o), _p(ve), C.c_uint64(P.shape[0]), _p(P), _p(v))
+        assert rc == 0, rc
+
+    def particles_info(self):
+        nl, n = C.c_int(0), C.c_uint64(0)
+        self.lib.orc_particles_info(self.h, C.byref(nl), C.byref(n))
+        return nl.value, n.value
+
+    def get_particles(self) -> Dict[str, np.ndarray]:
+        nl, n = self.particles_info()
+        o = np.zeros((nl, 3), np.int32)
+        ve = np.zeros((nl, 512), np.uint32)
+        P = np.zeros((n, 3), np.uint16)
+        v = np.zeros((n, 3), np.uint16)
+        self.lib.orc_particles_get(self.h, _p(o), _p(ve), _p(P), _p(v))
+        return {"origins": o, "voxel_end": ve, "P": P, "v": v}
+
+    def PrimToVDBPointDataGrid(self, pos, vel=None):
+        pos = _c(pos, np.float32).reshape(-1, 3)
+        vel = None if vel is None else _c(vel, np.float32).reshape(-1, 3)
+        self.lib.orc_bin_from_points(self.h, _p(pos), _p(vel), C.c_uint64(pos.shape[0]))
+
+    def FLIP_P2G(self, dx=None, VelExtraLayer=3):
+        self.lib.orc_p2g(self.h, C.c_float(self.dx if dx is None else dx), C.c_int(VelExtraLayer))
+
+    def G2PAdvectorSheetty(self, dt, dx=None, surface_size=4, RK_ORDER=1, pic_min=0.03, pic_max=0.05, viscous_is_velocity=True):
+        self.lib.orc_g2p_advect_sheetty(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.c_int(surface_size),
+                                        C.c_int(RK_ORDER), C.c_float(pic_min), C.c_float(pic_max), C.c_int(1 if viscous_is_velocity else 0))
+
+    def dropped(self) -> int:
+        return int(self.lib.orc_dropped(self.h))
+
+    def capture_precodec(self, on: bool):
+        self.lib.orc_capture_precodec(self.h, C.c_int(1 if on else 0))
+
+    def get_precodec(self, n: int):
+        pos = np.zeros((n, 3), np.float32)
+        vel = np.zeros((n, 3), np.float32)
+        alive = np.zeros(n, np.uint8)
+        self.lib.orc_get_precodec(self.h, _p(pos), _p(vel), _p(alive))
+        return pos, vel, alive
+
+    def CutCellWeight(self):
+        self.lib.orc_face_weights(self.h)
+
+    def PushOutLiquidSDF(self, dx=None):
+        self.lib.orc_pushout_sdf(self.h, C.c_float(self.dx if dx is None else dx))
+
+    def FieldAddVector(self, x, y, z):
+        self.lib.orc_add_vector(self.h, C.c_float(x), C.c_float(y), C.c_float(z))
+
+    def CFL_dt(self) -> float:
+        return float(self.lib.orc_cfl(self.h))
+
+    def AssembleSolvePPE(self, dt, dx=None, rel_tol=None, max_iter=100):
+        it, res, st = C.c_int(0), C.c_float(0), C.c_int(0)
+        self.lib.orc_solve_ppe(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.byref(it), C.byref(res), C.byref(st))
+        return {"iterations": it.value, "rel_residual": res.value, "status": st.value}
+
+    def solver_info(self):
+        lv, nd, nh = C.c_int(0), C.c_int(0), C.c_int(0)
+        self.lib.orc_solver_info(self.h, C.byref(lv), C.byref(nd), C.byref(nh))
+        hist = np.zeros(nh.value, np.float32)
+        if nh.value:
+            self.lib.orc_residual_history(self.h, _p(hist))
+        return {"levels": lv.value, "num_dof": nd.value, "history": hist}
+
+    def SubtractPressureGradient(self, dt, dx=None, VelExtraLayer=3):
+        self.lib.orc_subtract_grad(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.c_int(VelExtraLayer))
+
+    def substep(self, dt, dx=None, surface_size=4, RK_ORDER=3, pic_min=0.03, pic_max=0.05, gravity=(0.0, -9.8, 0.0),
+                VelExtraLayer=3, viscous_is_velocity=True, want_stage_ms=False):
+        secs = (C.c_double * 5)()
+        self.lib.orc_substep(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.c_int(surface_size), C.c_int(RK_ORDER),
+                             C.c_float(pic_min), C.c_float(pic_max), C.c_float(gravity[0]), C.c_float(gravity[1]), C.c_float(gravity[2]),
+                             C.c_int(VelExtraLayer), C.c_int(1 if viscous_is_velocity else 0), secs)
+        return [s * 1e3 for s in secs] if want_stage_ms else None
