@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- FLIP particle-substeps/s of the FastFLIP hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # our arm (libflipb200 through the C ABI)
+    python bench.py --impl reference --gpus N ...          # the reference's CPU algorithm on host cores
+
+A "step" is one substep of the packaged chain (projects/tools/FLIPtools/stub.cpp:5-17):
+CFL_dt -> G2PAdvectorSheetty(RK3) -> FLIP_P2G -> CutCellWeight -> PushOutLiquidSDF -> FieldAddVector(g dt)
+-> AssembleSolvePPE (MGPCG, 5e-5) -> SubtractPressureGradient, on BASELINE config[1]
+(dam-break 512^3, 16.8 M particles, 8 ppc, fp32) with the state resident in HBM (`value`), and the same
+step with the world state uploaded from / downloaded to pinned host buffers every step (`e2e`).
+Prints ONE JSON line. Inputs are synthetic (zeno_b200/scenes.py) and larger than L2 (>= 200 MB of
+particle state per step), so no L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GRAVITY = (0.0, -9.8, 0.0)
+STATE_GRIDS = ("Velocity", "PostAdvVelocity", "LiquidSDF")
+
+
+def substep_dt(w, dx):
+    # StepFLIPWorld: dt = min(dt_scale(3) * cfl_dt, frame time 1/24) (projects/tools/FLIPtools/stub.cpp:83)
+    return float(min(3.0 * w.CFL_dt(), 1.0 / 24.0))
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def start(self):
+        def run():
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            while not self._stop.is_set():
+                try:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([x.strip() for x in out.split(",")])
+                except Exception:
+                    pass
+                self._stop.wait(0.2)
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nme in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_arm(N: int, steps: int, warmup: int):
+    """The reference's CPU algorithm (oracle port; OpenMP over leaves) on a bounded sample."""
+    from oracle import pyoracle
+    from zeno_b200 import scenes
+    pyoracle.build()
+    pos, vel, dx = scenes.dam_break_points(N, seed=1)
+    w = pyoracle.OracleWorld(dx)
+    w.set_grid("SolidSDF", scenes.box_solid_sdf(N, dx))
+    w.PrimToVDBPointDataGrid(pos, vel)
+    w.FLIP_P2G(dx, 3)
+    n_particles = pos.shape[0]
+    for _ in range(warmup):
+        w.substep(substep_dt(w, dx), dx, 4, 3, 0.03, 0.05, GRAVITY, 3, True)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        w.substep(substep_dt(w, dx), dx, 4, 3, 0.03, 0.05, GRAVITY, 3, True)
+        done += w.particles_info()[1]
+    dtm = time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    return {"value": done / dtm, "seconds": dtm, "steps": steps, "cores": cores, "particles": n_particles,
+            "sample": f"dam-break {N}^3 tank, {n_particles} particles, 8 ppc, {steps} substeps (same chain, smaller tank)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=512, help="tank resolution N (BASELINE config[1]: 512)")
+    ap.add_argument("--ppc", type=int, default=8)
+    ap.add_argument("--cpu-grid", type=int, default=128, help="tank resolution of the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    metric = "FLIP particle-substeps/sec"
+    unit = "particle-substeps/s"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_arm(args.cpu_grid, args.steps, max(args.warmup, 1))
+        line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"FastFLIP dam-break substep chain, CPU port of the reference algorithm; {r['sample']}"},
+                "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from zeno_b200 import abi, scenes
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    N = args.grid
+    pos, vel, dx = scenes.dam_break_points(N, seed=1 + rank, ppc=args.ppc)
+    solid = scenes.box_solid_sdf(N, dx)
+    w = abi.World(dx, device=local_rank)
+    w.set_grid("SolidSDF", solid)
+    w.PrimToVDBPointDataGrid(pos, vel)
+    del pos, vel
+    w.FLIP_P2G(dx, 3)
+    stream = torch.cuda.ExternalStream(w.stream(), device=torch.device("cuda", local_rank))
+
+    def step():
+        dt = substep_dt(w, dx)
+        w.substep(dt, dx, 4, 3, 0.03, 0.05, GRAVITY, 3, True)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    launches0 = w.launch_count()
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    particle_steps = 0
+    iters = []
+    for _ in range(args.steps):
+        step()
+        particle_steps += w.particles_info()[1]
+        iters.append(w.solver_info()["history"].shape[0] - 1)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = w.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        c = torch.tensor([float(particle_steps)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        particle_steps = float(c.item())
+    value = particle_steps / (ms * 1e-3)
+
+    # ---- per-kernel device times (CUDA events on the library's stream), 2 further steps
+    w.profile_reset()
+    w.profile_enable(True)
+    stage_ms = np.zeros(5)
+    PROF_STEPS = 2
+    for _ in range(PROF_STEPS):
+        dt = substep_dt(w, dx)
+        stage_ms += np.array(w.substep(dt, dx, 4, 3, 0.03, 0.05, GRAVITY, 3, True, want_stage_ms=True))
+    w.profile_enable(False)
+    prof = w.profile_get()
+    stage_ms /= PROF_STEPS
+    peak, peak_src = measured_peak()
+    kern = {}
+    for k, v in prof.items():
+        if v["launches"] == 0:
+            continue
+        avg_ms = v["ms"] / v["launches"]
+        gbs = (v["bytes"] / v["launches"]) / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        kern[k] = {"ms_per_step": v["ms"] / PROF_STEPS, "launches_per_step": v["launches"] / PROF_STEPS,
+                   "avg_us": 1e3 * avg_ms, "algorithmic_GBps": gbs, "frac": gbs / peak}
+    dominant = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+    roofline = None
+    if dominant:
+        d = kern[dominant]
+        roofline = {"kernel": dominant, "bound": "hbm", "achieved": d["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": d["frac"], "traffic": None, "peak_source": peak_src, "avg_launch_us": d["avg_us"],
+                    "share_of_step": d["ms_per_step"] / max(sum(x["ms_per_step"] for x in kern.values()), 1e-9),
+                    "measured": f"CUDA events around every launch of the family over {PROF_STEPS} substeps following the timed region"}
+    top = sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])[:12]
+
+    # ---- e2e: the same step with the world state crossing PCIe both ways every step
+    e2e = None
+    if not args.no_e2e:
+        state = {g: w.get_grid(g) for g in STATE_GRIDS}
+        pts = w.get_particles()
+
+        def pin(a):
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            return t.numpy()
+        state = {g: {k: pin(v) for k, v in d.items()} for g, d in state.items()}
+        pts = {k: pin(v) for k, v in pts.items()}
+        h2d = sum(v.nbytes for d in state.values() for v in d.values()) + sum(v.nbytes for v in pts.values())
+        E_STEPS = max(1, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        psteps = 0
+        for _ in range(E_STEPS):
+            for g in STATE_GRIDS:
+                w.set_grid(g, state[g])
+            w.set_particles(pts)
+            step()
+            out_p = w.get_particles()
+            out_g = {g: w.get_grid(g) for g in STATE_GRIDS}
+            d2h = sum(v.nbytes for v in out_p.values()) + sum(v.nbytes for d in out_g.values() for v in d.values())
+            psteps += out_p["P"].shape[0]
+        barrier()
+        es = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([es], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            es = float(t.item())
+            c = torch.tensor([float(psteps)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            psteps = float(c.item())
+        e2e = {"value": psteps / es, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": E_STEPS, "ms_per_step": 1e3 * es / E_STEPS,
+               "what": "per step: upload particles + Velocity/PostAdvVelocity/LiquidSDF from host (VDB leaf layout), CFL + substep, download the same"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference_arm(args.cpu_grid, 3, 1)
+        cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        n_particles = w.particles_info()[1]
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"FastFLIP dam-break {N}^3 tank, {n_particles} particles/GPU, {args.ppc} ppc, one substep = CFL_dt + G2PAdvectorSheetty(RK3) + FLIP_P2G + CutCellWeight + PushOutLiquidSDF + FieldAddVector + AssembleSolvePPE(5e-5) + SubtractPressureGradient",
+                           "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one tank per GPU; brick decomposition not implemented yet)",
+                           "l2": "inputs larger than L2 (>=200 MB particle state per step), no flush",
+                           "pcg_iterations": iters},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu,
+                "stage_ms": {"g2p_advect_rebin": stage_ms[0], "p2g": stage_ms[1], "stencils": stage_ms[2], "mgpcg": stage_ms[3], "gradient": stage_ms[4]},
+                "kernels": {k: v for k, v in top}}
+        print(json.dumps(line))
+    w.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

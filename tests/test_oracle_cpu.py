@@ -1,0 +1,246 @@
+"""CPU tests (no GPU): the oracle against hand-computable cases, independent implementations
+(numpy float16, closed-form hat weights) and the committed golden fixtures."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from zeno_b200 import scenes
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_half_codec_matches_ieee_rne(oracle_lib):
+    # TruncateCodec -> half: every finite half decodes exactly and re-encodes to itself;
+    # float -> half equals numpy's IEEE round-to-nearest-even (openvdb/math/Half.h:430-490)
+    h = np.arange(65536, dtype=np.uint16)
+    f = h.view(np.float16).astype(np.float32)
+    finite = np.isfinite(f)
+    dec = np.array([oracle_lib.orc_half_decode(C.c_uint16(int(x))) for x in h[finite]], np.float32)
+    assert np.array_equal(dec.view(np.uint32), f[finite].view(np.uint32))
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.normal(0, 10, 20000), rng.uniform(-7e4, 7e4, 2000), rng.uniform(-1e-4, 1e-4, 5000),
+                        [0.0, -0.0, 65504.0, 65519.9, 65520.0, 1e9, 5.96e-8, 2.98e-8, 2.99e-8]]).astype(np.float32)
+    enc = np.array([oracle_lib.orc_half_encode(C.c_float(float(v))) for v in x], np.uint16)
+    with np.errstate(over="ignore"):
+        ref = x.astype(np.float16).view(np.uint16)
+    assert np.array_equal(enc, ref)
+
+
+def test_fixed_point_codec(oracle_lib):
+    # FixedPointCodec<false, PositionRange> (openvdb/points/AttributeArray.h:47-65)
+    u = np.arange(65536, dtype=np.uint16)
+    dec = np.array([oracle_lib.orc_fxpt16_decode(C.c_uint16(int(x))) for x in u[::17]], np.float32)
+    ref = (u[::17].astype(np.float32) / np.float32(65535.0)) - np.float32(0.5)
+    assert np.array_equal(dec, ref)
+    # encode: clamp to [0, 65535], truncation (not rounding)
+    assert oracle_lib.orc_fxpt16_encode(C.c_float(-0.51)) == 0
+    assert oracle_lib.orc_fxpt16_encode(C.c_float(0.5)) == 65535
+    assert oracle_lib.orc_fxpt16_encode(C.c_float(0.75)) == 65535
+    assert oracle_lib.orc_fxpt16_encode(C.c_float(0.0)) == int(np.float32(0.5) * np.float32(65535.0))
+    # decode(encode(p)) never exceeds p and is within one LSB
+    p = np.linspace(-0.5, 0.4999, 3001, dtype=np.float32)
+    e = np.array([oracle_lib.orc_fxpt16_encode(C.c_float(float(v))) for v in p], np.uint16)
+    d = e.astype(np.float32) / np.float32(65535.0) - np.float32(0.5)
+    assert (d <= p + 1e-7).all() and (p - d < 1.0 / 65535 + 1e-7).all()
+
+
+def test_codec_golden(oracle_lib):
+    g = np.load(os.path.join(GOLD, "codecs.npz"))
+    dec = np.array([oracle_lib.orc_fxpt16_decode(C.c_uint16(int(x))) for x in range(0, 65536, 13)], np.float32)
+    assert np.array_equal(dec, g["fx_dec"][::13])
+    enc = np.array([oracle_lib.orc_fxpt16_encode(C.c_float(float(x))) for x in g["fx_probe"]], np.uint16)
+    assert np.array_equal(enc, g["fx_enc"])
+    henc = np.array([oracle_lib.orc_half_encode(C.c_float(float(x))) for x in g["half_probe"]], np.uint16)
+    assert np.array_equal(henc, g["half_enc"])
+
+
+def test_fraction_inside(oracle_lib):
+    f2, f4 = oracle_lib.orc_fraction_inside2, oracle_lib.orc_fraction_inside4
+    c = lambda *a: [C.c_float(x) for x in a]
+    assert f2(*c(-1, -1)) == 1 and f2(*c(1, 1)) == 0
+    assert f2(*c(-1, 1)) == pytest.approx(0.5) and f2(*c(1, -3)) == pytest.approx(0.75)
+    assert f4(*c(-1, -1, -1, -1)) == 1 and f4(*c(1, 1, 1, 1)) == 0
+    # half plane through the middle, any orientation
+    assert f4(*c(-1, 1, -1, 1)) == pytest.approx(0.5)
+    assert f4(*c(-1, -1, 1, 1)) == pytest.approx(0.5)
+    # one corner inside: triangle of legs 1/2 x 1/2
+    assert f4(*c(-1, 1, 1, 1)) == pytest.approx(0.125)
+    # three inside: complement
+    assert f4(*c(1, -1, -1, -1)) == pytest.approx(0.875)
+    # symmetric under complement for generic values
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        v = rng.normal(0, 1, 4).astype(np.float32)
+        if (v < 0).sum() == 2 and (v[0] < 0) == (v[3] < 0):
+            continue  # diagonal case is resolved by the centre sign, not symmetric
+        a = f4(*c(*v))
+        b = f4(*c(*(-v)))
+        assert a + b == pytest.approx(1.0, abs=2e-6)
+
+
+def test_frand_matches_reference_hash():
+    # frand (FF/FLIP_vdb.h:10-17) evaluated by hand for a few arguments
+    def ref(i):
+        m = 0xFFFFFFFF
+        v = ((i ^ 61) ^ (i >> 16)) & m
+        v = (v * 9) & m
+        v = (v ^ (v << 4)) & m
+        v = (v * 0x27D4EB2D) & m
+        v = (v ^ (v >> 15)) & m
+        return np.float32(np.float32(v) / np.float32(4294967296.0))
+    xs = np.array([0, 1, 2, 61, 12345, 2 ** 31, 2 ** 32 - 1], np.uint64)
+    got = scenes.frand(xs.astype(np.uint32))
+    assert np.array_equal(got, np.array([ref(int(x)) for x in xs], np.float32))
+
+
+def test_single_voxel_dilation_topology(oracle_lib):
+    """One particle in voxel (7,7,7): the velocity topology is the 26-neighbour dilation -> 27 active
+    voxels in 8 leaves (the case the survey verified against the real OpenVDB headers)."""
+    from oracle.pyoracle import OracleWorld
+    dx = 0.1
+    w = OracleWorld(dx)
+    w.PrimToVDBPointDataGrid(np.float32([[0.7, 0.7, 0.7]]), np.float32([[0, 0, 0]]))
+    p = w.get_particles()
+    assert p["origins"].tolist() == [[0, 0, 0]] and p["voxel_end"][0, 511] == 1 and p["voxel_end"][0, 510] == 0
+    w.FLIP_P2G(dx, 0)
+    # the sdf inherits the dilated topology; the only liquid voxel (phi < 0) is the particle's own, whose
+    # face neighbours all lie inside the 27, so the air ring adds nothing: exactly 27 voxels in 8 leaves
+    sdf = scenes.canonical_grid(w.get_grid("LiquidSDF"))
+    assert sdf["origins"].shape[0] == 8
+    mb = scenes.mask_bits(sdf["masks"])
+    assert mb.sum() == 27
+    assert (sdf["values"][:, 0][mb] < 0).sum() == 1
+    # per-channel velocity masks keep only samples with non-zero weight: a subset of the 27
+    post = scenes.canonical_grid(w.get_grid("PostAdvVelocity"))
+    assert 0 < scenes.mask_bits(post["masks"]).sum() <= 27
+
+
+def test_single_particle_p2g_weights(oracle_lib):
+    """Hand-computed trilinear hat weights for one particle (FF/FLIP_vdb.cpp:863-884,1191-1239)."""
+    from oracle.pyoracle import OracleWorld
+    g = np.load(os.path.join(GOLD, "single_particle_p2g.npz"))
+    dx = float(g["dx"])
+    w = OracleWorld(dx)
+    w.PrimToVDBPointDataGrid(g["pos"], g["vel"])
+    part = w.get_particles()
+    P = part["P"][0].astype(np.float32) / np.float32(65535) - np.float32(0.5)
+    v = part["v"][0].view(np.float16).astype(np.float32)
+    ijk = np.floor(g["pos"][0].astype(np.float64) / dx + 0.5).astype(int)
+    w.FLIP_P2G(dx, 0)
+    post = scenes.canonical_grid(w.get_grid("PostAdvVelocity"))
+    lut = {tuple(o): i for i, o in enumerate(post["origins"].tolist())}
+    mb = scenes.mask_bits(post["masks"])
+    for c in range(3):
+        for off in np.ndindex(3, 3, 3):
+            b = np.array(off) - 1
+            vox = ijk + b
+            stag = b.astype(np.float32).copy()
+            stag[c] -= 0.5
+            wgt = np.prod(np.maximum(0, 1 - np.abs(stag - P)))
+            leaf = lut.get(tuple((vox // 8 * 8).tolist()))
+            o = ((vox[0] & 7) << 6) | ((vox[1] & 7) << 3) | (vox[2] & 7)
+            if wgt > 0:
+                assert leaf is not None and mb[leaf, o]
+                # v / (w + 1e-3) * w   (normalize_p2g_velocity, FF/FLIP_vdb.cpp:120-165)
+                assert post["values"][leaf, c, o] == pytest.approx(v[c] * wgt / (wgt + 1e-3), rel=1e-5)
+            elif leaf is not None:
+                assert post["values"][leaf, c, o] == 0
+    # sdf at the particle's own voxel: dx*|p| - 0.808 dx
+    sdf = scenes.canonical_grid(w.get_grid("LiquidSDF"))
+    lut = {tuple(o): i for i, o in enumerate(sdf["origins"].tolist())}
+    leaf = lut[tuple((ijk // 8 * 8).tolist())]
+    o = ((ijk[0] & 7) << 6) | ((ijk[1] & 7) << 3) | (ijk[2] & 7)
+    assert sdf["values"][leaf, 0, o] == pytest.approx(dx * np.linalg.norm(P) - dx * 0.8 * 1.01, rel=1e-5)
+    # golden
+    for name, key in (("Velocity", "vel"), ("PostAdvVelocity", "post"), ("LiquidSDF", "sdf")):
+        c = scenes.canonical_grid(w.get_grid(name)) if name != "Velocity" else None
+    w2 = OracleWorld(dx)
+    w2.PrimToVDBPointDataGrid(g["pos"], g["vel"])
+    w2.FLIP_P2G(dx, 3)
+    for name, key in (("Velocity", "vel"), ("PostAdvVelocity", "post"), ("LiquidSDF", "sdf")):
+        c = scenes.canonical_grid(w2.get_grid(name))
+        assert np.array_equal(c["origins"], g[f"{key}_origins"]) and np.array_equal(c["masks"], g[f"{key}_masks"])
+        assert np.array_equal(c["values"], g[f"{key}_values"])
+
+
+def test_two_leaf_migration(oracle_lib):
+    """Particles in a uniform +x velocity field cross the leaf boundary x=8 and are re-binned (K2)."""
+    from oracle.pyoracle import OracleWorld
+    dx = 0.125
+    w = OracleWorld(dx)
+    ii = np.arange(5, 8)
+    pos = np.float32([[(x + 0.1) * dx, (3 + 0.2) * dx, (4 - 0.3) * dx] for x in ii])
+    vel = np.float32([[1.0, 0, 0]] * len(ii))
+    w.PrimToVDBPointDataGrid(pos, vel)
+    # uniform velocity grid covering the neighbourhood: u = 1 everywhere
+    org = np.int32([[0, 0, 0], [8, 0, 0]])
+    vals = np.zeros((2, 3, 512), np.float32)
+    vals[:, 0, :] = 1.0
+    masks = np.full((2, 8), np.uint64(0xFFFFFFFFFFFFFFFF))
+    grid = {"origins": org, "masks": masks, "values": vals, "bg": np.zeros(3, np.float32)}
+    w.set_grid("Velocity", grid)
+    w.set_grid("PostAdvVelocity", grid)
+    w.set_grid("LiquidSDF", {"origins": org, "masks": masks, "values": np.full((2, 1, 512), -1.0, np.float32), "bg": np.float32([dx])})
+    dt = 3 * dx  # moves every particle exactly 3 voxels in +x
+    w.G2PAdvectorSheetty(dt, dx, 4, 1, 0.0, 0.0, True)
+    c = scenes.canonical_particles(w.get_particles())
+    assert c.shape[0] == 3 and w.dropped() == 0
+    assert sorted(c[:, 0].tolist()) == [8, 9, 10] and (c[:, 1] == 3).all() and (c[:, 2] == 4).all()
+    assert len({tuple(o) for o in w.get_particles()["origins"].tolist()}) == 1
+
+
+def test_dambreak_golden_and_invariants(oracle_lib):
+    from oracle.pyoracle import OracleWorld
+    g = np.load(os.path.join(GOLD, "dambreak16.npz"))
+    N, dx, dt = int(g["N"]), float(g["dx"]), float(g["dt"])
+    w = OracleWorld(dx)
+    w.set_grid("SolidSDF", scenes.box_solid_sdf(N, dx))
+    w.PrimToVDBPointDataGrid(g["pos"], g["vel"])
+    w.FLIP_P2G(dx, 3)
+    for step in range(2):
+        w.CutCellWeight()
+        w.PushOutLiquidSDF(dx)
+        w.FieldAddVector(0.0, -9.8 * dt, 0.0)
+        r = w.AssembleSolvePPE(dt, dx)
+        assert r["status"] == 0 and r["iterations"] == int(g["pcg_iterations"][step])
+        hist = w.solver_info()["history"]
+        assert hist[-1] <= 5e-5 and hist[0] == pytest.approx(1.0)
+        # Pressure mask == Divergence mask == DOF set; pressure is 0 off the DOFs
+        pr, dv = scenes.canonical_grid(w.get_grid("Pressure")), scenes.canonical_grid(w.get_grid("Divergence"))
+        assert np.array_equal(pr["masks"], dv["masks"])
+        assert (pr["values"][:, 0][~scenes.mask_bits(pr["masks"])] == 0).all()
+        w.SubtractPressureGradient(dt, dx, 3)
+        w.G2PAdvectorSheetty(dt, dx, 4, 3, 0.03, 0.05, True)
+        w.FLIP_P2G(dx, 3)
+        assert np.array_equal(scenes.canonical_particles(w.get_particles()), g[f"particles_{step}"])
+        v = scenes.canonical_grid(w.get_grid("Velocity"))
+        assert np.array_equal(v["masks"], g[f"vel_{step}_masks"]) and np.array_equal(v["values"], g[f"vel_{step}_values"])
+        s = scenes.canonical_grid(w.get_grid("LiquidSDF"))
+        assert np.array_equal(s["masks"], g[f"sdf_{step}_masks"]) and np.array_equal(s["values"], g[f"sdf_{step}_values"])
+
+
+def test_projection_removes_divergence(oracle_lib):
+    """After AssembleSolvePPE + SubtractPressureGradient the weighted divergence of interior DOFs
+    (all six neighbours liquid, full face weights) is ~1e-4 of what it was."""
+    from oracle.pyoracle import OracleWorld
+    N = 32
+    pos, vel, dx = scenes.dam_break_points(N, seed=5, random_velocity=True)
+    w = OracleWorld(dx)
+    w.set_grid("SolidSDF", scenes.box_solid_sdf(N, dx))
+    w.PrimToVDBPointDataGrid(pos, vel)
+    w.FLIP_P2G(dx, 3)
+    w.CutCellWeight()
+    w.PushOutLiquidSDF(dx)
+    dt = 0.01
+    w.AssembleSolvePPE(dt, dx)
+    rhs0 = scenes.canonical_grid(w.get_grid("Divergence"))
+    w.SubtractPressureGradient(dt, dx, 3)
+    w.AssembleSolvePPE(dt, dx)  # re-assemble the RHS of the projected field
+    rhs1 = scenes.canonical_grid(w.get_grid("Divergence"))
+    a, b = rhs0["values"].ravel(), rhs1["values"].ravel()
+    # a handful of free-surface voxels whose faces the gradient pass deactivates and the extrapolation
+    # refills keep a residual (reference behaviour); everywhere else the field is divergence free
+    assert np.linalg.norm(b) < 1e-2 * np.linalg.norm(a)
+    assert (np.abs(b) > 1e-2).sum() <= 3 < (np.abs(a) > 1e-2).sum()

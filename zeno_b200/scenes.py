@@ -57,22 +57,15 @@ def box_solid_sdf(N: int, dx: float, band: int = 3, inset: float = 0.02) -> Dict
     clamped to +-band*dx; only leaves intersecting the band are stored, background = 3dx."""
     lo, hi = -8, N + 8
     nl = (hi - lo) // 8
-    leaves = []
-    for lx in range(nl):
-        for ly in range(nl):
-            for lz in range(nl):
-                o = np.array([lo + 8 * lx, lo + 8 * ly, lo + 8 * lz])
-                # distance range of this leaf to the wall surfaces
-                c = [np.arange(o[a], o[a] + 8) for a in range(3)]
-                d = [np.minimum(c[a], N - c[a]).astype(np.float32) - inset for a in range(3)]
-                dmin = min(d[0].min(), d[1].min(), d[2].min())
-                # interior leaves far from every wall hold only background
-                if dmin >= band + 1:
-                    continue
-                if max(d[0].max(), d[1].max(), d[2].max()) < -(band + 9):
-                    continue
-                leaves.append(o)
-    origins = np.array(leaves, np.int32).reshape(-1, 3)
+    # per-axis min over the 8 voxels of a leaf of (min(i, N - i) - inset); a leaf is kept when it
+    # comes within band+1 voxels of a wall surface (interior leaves hold only background)
+    ax = lo + 8 * np.arange(nl)
+    vox = ax[:, None] + np.arange(8)[None, :]
+    dax = (np.minimum(vox, N - vox).astype(np.float32) - np.float32(inset)).min(axis=1)  # [nl]
+    near = dax < band + 1
+    keep = near[:, None, None] | near[None, :, None] | near[None, None, :]
+    lx, ly, lz = np.nonzero(keep)
+    origins = np.stack([ax[lx], ax[ly], ax[lz]], axis=1).astype(np.int32)
     n = origins.shape[0]
     r = np.arange(8)
     X = origins[:, 0, None] + r[None, :]
