@@ -56,9 +56,27 @@ def _c(a, dt):
     return np.ascontiguousarray(a, dtype=dt)
 
 
+class _Prefixed:
+    """lib.orc_foo -> getattr(raw, prefix + 'foo'): one harness for liboracle (orc_) and libflipref (ref_)"""
+
+    def __init__(self, raw, prefix):
+        self._raw, self._prefix = raw, prefix
+
+    def __getattr__(self, name):
+        if name.startswith("orc_"):
+            return getattr(self._raw, self._prefix + name[4:])
+        return getattr(self._raw, name)
+
+
 class OracleWorld:
+    PREFIX = "orc_"
+
+    @classmethod
+    def _load(cls):
+        return load()
+
     def __init__(self, dx: float):
-        self.lib = load()
+        self.lib = _Prefixed(self._load(), self.PREFIX)
         self.dx = float(dx)
         self.h = C.c_void_p(self.lib.orc_world_create(C.c_float(dx)))
 
@@ -174,3 +192,45 @@ class OracleWorld:
                              C.c_float(pic_min), C.c_float(pic_max), C.c_float(gravity[0]), C.c_float(gravity[1]), C.c_float(gravity[2]),
                              C.c_int(VelExtraLayer), C.c_int(1 if viscous_is_velocity else 0), secs)
         return [s * 1e3 for s in secs] if want_stage_ms else None
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref: the REAL reference sources (FLIP_vdb.cpp, simd_vdb_poisson_uaamg.cpp, ...) compiled by
+# oracle/ref/build_ref.sh behind the same flat API (prefix ref_). Used to pin the restatement and as the
+# `--impl reference` CPU arm of bench.py.
+_REF_LIB = os.path.join(_HERE, "_ref", "libflipref.so")
+_ref = None
+
+
+def ref_available() -> bool:
+    return os.path.exists(_REF_LIB)
+
+
+def load_ref() -> C.CDLL:
+    global _ref
+    if _ref is None:
+        if not os.path.exists(_REF_LIB):
+            raise FileNotFoundError(f"{_REF_LIB} not built (run oracle/ref/build_ref.sh where /root/reference exists)")
+        lib = C.CDLL(_REF_LIB)
+        lib.ref_world_create.restype = C.c_void_p
+        lib.ref_cfl.restype = C.c_float
+        lib.ref_dropped.restype = C.c_uint64
+        lib.ref_fraction_inside2.restype = C.c_float
+        lib.ref_fraction_inside4.restype = C.c_float
+        lib.ref_build_info.restype = C.c_char_p
+        lib.ref_set_threads.restype = C.c_int
+        _ref = lib
+    return _ref
+
+
+def ref_set_threads(n: int = 0) -> int:
+    return int(load_ref().ref_set_threads(C.c_int(n)))
+
+
+class RefWorld(OracleWorld):
+    """Same interface as OracleWorld, executed by the reference's own code."""
+    PREFIX = "ref_"
+
+    @classmethod
+    def _load(cls):
+        return load_ref()

@@ -17,7 +17,9 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 OUT="$HERE/../_ref"
 BUILD=${BUILD:-/tmp/flipref_build}
 JOBS=${JOBS:-8}
-CXX=${CXX:-$(test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)}
+# the image exports CXX=/opt/gcc/bin/g++, a wrapper that links libstdc++ statically (two libstdc++ copies in one
+# python process crash); use the distro g++ unless REF_CXX says otherwise
+CXX=${REF_CXX:-$(test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)}
 VDB="$REF/projects/zenvdb/openvdb/openvdb"
 FF="$REF/projects/FastFLIP"
 [ -d "$REF" ] || { echo "no $REF: keeping the prebuilt oracle/_ref"; exit 0; }
@@ -47,7 +49,7 @@ s = re.sub(r"#cmakedefine (\w+)", r"/* #undef \1 */", s)
 open(sys.argv[2], "w").write(s)
 EOF
 
-COMMON="-std=c++17 -O2 -fPIC -w -include cstring -I$HERE/shims -I$BUILD/gen -I$BUILD/gen/openvdb -I$VDB -I$VDB/openvdb -I$TBBINC -DOPENVDB_PRIVATE"
+COMMON="-std=c++17 -O2 -fPIC -w -include cstring -include $HERE/shims/boost_compat.h -I$HERE/shims -I$BUILD/gen -I$BUILD/gen/openvdb -I$VDB -I$VDB/openvdb -I$TBBINC -DOPENVDB_PRIVATE"
 
 # ---- 3. the OpenVDB library objects (23 of 26 .cc; io/{File,Stream,TempFile}.cc are file IO only)
 VDBSRC="Grid MetaMap Metadata Platform openvdb io/Archive io/Compression io/DelayedLoadMetadata io/GridDescriptor io/Queue math/Half math/Maps math/Proximity math/QuantizedUnitVec math/Transform points/AttributeArray points/AttributeArrayString points/AttributeGroup points/AttributeSet points/StreamCompression points/points util/Formats util/Util"
@@ -59,9 +61,9 @@ done
 xargs -P "$JOBS" -d '\n' -I{} bash -c {} < "$BUILD/cmds.txt" || { echo "openvdb compile failed"; exit 1; }
 
 # ---- 4. the reference FastFLIP sources, unmodified, with the reference's flags (FF/CMakeLists.txt:56: -mavx -mfma)
-FFFLAGS="$COMMON -mavx -mfma -I$HERE/shims/zeno_min -I$REF/projects/zenvdb/include -I$REF/zeno/include -I$FF"
+FFFLAGS="$COMMON -mavx -mfma -DZENO_APIFREE -I$HERE/shims/zeno_min -I$REF/projects/zenvdb/include -I$REF/zeno/include -I$FF"
 : > "$BUILD/cmds.txt"
-for s in "$FF/FLIP_vdb.cpp" "$FF/simd_vdb_poisson_uaamg.cpp" "$FF/vdb_velocity_extrapolator.cpp" "$FF/levelset_util.cpp" "$REF/projects/zenvdb/packed3grids.cpp" "$HERE/ref_driver.cpp"; do
+for s in "$FF/FLIP_vdb.cpp" "$FF/simd_vdb_poisson_uaamg.cpp" "$FF/vdb_velocity_extrapolator.cpp" "$FF/levelset_util.cpp" "$REF/projects/zenvdb/include/zeno/packed3grids.cpp" "$HERE/ref_driver.cpp" "$HERE/ref_stubs.cpp"; do
   o="$BUILD/ffobj/$(basename $s .cpp).o"
   if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ "$HERE/shims/Eigen/Eigen" -nt "$o" ]; then
     echo "$CXX $FFFLAGS -c $s -o $o 2> $o.log || { grep -m 30 -E 'error|Error' $o.log; exit 255; }" >> "$BUILD/cmds.txt"
