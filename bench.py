@@ -38,28 +38,72 @@ def substep_dt(w, dx):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe). Sampled through NVML
+    in-process: spawning nvidia-smi next to a ~100 ms timed region stalls the driver for tens of ms and was
+    measured to triple ms_per_step; nvidia-smi is only the fallback when NVML is unavailable."""
 
-    def __init__(self, index: int):
-        self.index = index
-        self.rows = []
+    def __init__(self, index: int, period: float = 0.02):
+        self.index, self.period = index, period
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
         self._stop = threading.Event()
         self._t = None
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: match by PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(hh).bus) == int(bus):
+                        h = hh
+                        break
+            self.h = h if h is not None else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _sample_nvml(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, name in ((nv.nvmlClocksThrottleReasonHwSlowdown, "hw_slowdown"),
+                          (nv.nvmlClocksThrottleReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                          (nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                          (nv.nvmlClocksThrottleReasonSwPowerCap, "sw_power_cap")):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return
+        r = [x.strip() for x in out.split(",")]
+        self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+        for k, nme in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                self.reasons.add(nme)
 
     def start(self):
         def run():
-            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap")
             while not self._stop.is_set():
                 try:
-                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                         capture_output=True, text=True, timeout=5).stdout.strip()
-                    if out:
-                        self.rows.append([x.strip() for x in out.split(",")])
+                    self._sample_nvml() if self.nv else self._sample_smi()
                 except Exception:
                     pass
-                self._stop.wait(0.2)
+                self._stop.wait(self.period if self.nv else 0.5)
         self._t = threading.Thread(target=run, daemon=True)
         self._t.start()
 
@@ -67,16 +111,9 @@ class ClockSampler:
         self._stop.set()
         if self._t:
             self._t.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nme in enumerate(names):
-                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "power_w_max": max(self.power) if self.power else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml" if self.nv else "nvidia-smi"}
 
 
 def measured_peak():

@@ -19,6 +19,12 @@ constexpr int NB_XM = 4, NB_XP = 22, NB_YM = 10, NB_YP = 16, NB_ZM = 12, NB_ZP =
 constexpr int MAX_COARSEST = 4000;  // uaamg.cpp:1965
 constexpr int RED_THREADS = 256;
 
+// everything a stencil CTA needs to know about its leaf, in one 32-byte record (one load instead of the
+// dependent mask -> nbr27 -> flags[nbr] chain): the six face-neighbour slots and
+// bit0 = leaf has a DOF, bit1 = all face coefficients this leaf reads are the default (-term)
+struct __align__(128) LeafInfo { int nb[6]; uint32_t flags; uint32_t pad; uint64_t mask[8]; uint64_t pad2[4]; };
+enum { LI_ANY = 1, LI_CONST = 2, LI_DIAG = 4 };  // LI_DIAG: diag / invdiag read as the default on the whole leaf
+
 struct Level {
     TopoPtr topo;
     int n = 0;
@@ -27,42 +33,22 @@ struct Level {
     DBuf<uint64_t> dof;
     DBuf<float> diag, invdiag, xe, ye, ze;
     DBuf<uint8_t> flags;   // bit0 diag, bit1 x, bit2 y, bit3 z read as the default
-    DBuf<float> x, b, tmp;
+    DBuf<LeafInfo> info;
+    DBuf<float> x, b;
 };
 struct LevelView {
     TopoView t;
     const uint64_t* dof;
     const float *diag, *invdiag, *xe, *ye, *ze;
     const uint8_t* flags;
+    const LeafInfo* info;
     float term;
 };
 LevelView view_of(const Level& L) {
-    return LevelView{L.topo->view(), L.dof.p, L.diag.p, L.invdiag.p, L.xe.p, L.ye.p, L.ze.p, L.flags.p, L.term};
+    return LevelView{L.topo->view(), L.dof.p, L.diag.p, L.invdiag.p, L.xe.p, L.ye.p, L.ze.p, L.flags.p, L.info.p, L.term};
 }
 
 // ---------------------------------------------------------------- reductions (deterministic)
-// per-leaf partials are written by the producing kernel; this folds them in a fixed order.
-template <bool IS_MAX>
-__global__ void __launch_bounds__(RED_THREADS) fold_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
-    __shared__ float sm[RED_THREADS];
-    float a = 0.f;
-    for (int i = threadIdx.x; i < n; i += RED_THREADS) {
-        float v = partial[i];
-        if (IS_MAX) a = (isfinite(a) ? (isfinite(v) ? fmaxf(a, v) : v) : a);
-        else a = __fadd_rn(a, v);
-    }
-    sm[threadIdx.x] = a;
-    __syncthreads();
-    for (int s = RED_THREADS / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            float u = sm[threadIdx.x], v = sm[threadIdx.x + s];
-            if (IS_MAX) sm[threadIdx.x] = (isfinite(u) ? (isfinite(v) ? fmaxf(u, v) : v) : u);
-            else sm[threadIdx.x] = __fadd_rn(u, v);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *out = sm[0];
-}
 // block-wide sum / max of one value per thread (512 threads), result valid in thread 0
 __device__ __forceinline__ float block_sum_512(float v, float* sm16) {
     for (int d = 16; d > 0; d >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, d));
@@ -282,108 +268,93 @@ __global__ void __launch_bounds__(512) rhs_kernel(TopoView t, const uint64_t* __
     rhs[i] = r;
 }
 
-// ---------------------------------------------------------------- stencil kernels
+// ---------------------------------------------------------------- stencil device functions
+// Written once as per-leaf device functions and used by two kinds of kernels: one CTA per leaf for the
+// large levels, and mg_bottom_kernel, a single resident CTA that runs the whole mu-cycle below a level
+// (every sweep / residual / restriction / prolongation / the coarsest CG) without returning to the host.
 struct Nbr { int xm, xp, ym, yp, zm, zp; };
-__device__ __forceinline__ Nbr load_nbr(const TopoView& t, int leaf) {
-    const int* nb = t.nbr27 + (size_t)leaf * 27;
-    return Nbr{nb[NB_XM], nb[NB_XP], nb[NB_YM], nb[NB_YP], nb[NB_ZM], nb[NB_ZP]};
+__device__ __forceinline__ LeafInfo load_info(const LevelView& L, int leaf) {
+    const int4* p = reinterpret_cast<const int4*>(L.info + leaf);
+    int4 a = __ldg(p), b = __ldg(p + 1);
+    LeafInfo li;
+    li.nb[0] = a.x; li.nb[1] = a.y; li.nb[2] = a.z; li.nb[3] = a.w; li.nb[4] = b.x; li.nb[5] = b.y;
+    li.flags = (uint32_t)b.z;
+    return li;
 }
+__device__ __forceinline__ Nbr nbr_of(const LeafInfo& li) { return Nbr{li.nb[0], li.nb[1], li.nb[2], li.nb[3], li.nb[4], li.nb[5]}; }
 // off-diagonal sum with the reference's association (uaamg.cpp:1044-1049):
 // ((x+ c_x+ + x- c_x-) + (y+ c_y+ + y- c_y-)) + (z+ c_z+ + z- c_z-)
 template <bool CONST_COEF>
-__device__ __forceinline__ float offdiag(const LevelView& L, const float* __restrict__ x, int leaf, int off, const Nbr& nb) {
+__device__ __forceinline__ float offdiag(const LevelView& L, const float* x, int leaf, int off, const Nbr& nb) {
     const int X = off >> 6, Y = (off >> 3) & 7, Z = off & 7;
     const size_t base = (size_t)leaf * LEAF;
     const float def = -L.term;
     float xp, xm, yp, ym, zp, zm, cxp, cxm, cyp, cym, czp, czm;
-    if (X < 7) { xp = x[base + off + 64]; cxp = CONST_COEF ? def : L.xe[base + off + 64]; }
-    else { xp = nb.xp >= 0 ? x[(size_t)nb.xp * LEAF + off - 448] : 0.f; cxp = (CONST_COEF || nb.xp < 0) ? def : L.xe[(size_t)nb.xp * LEAF + off - 448]; }
+    if (X < 7) { xp = x[base + off + 64]; cxp = CONST_COEF ? def : __ldg(&L.xe[base + off + 64]); }
+    else { xp = nb.xp >= 0 ? x[(size_t)nb.xp * LEAF + off - 448] : 0.f; cxp = (CONST_COEF || nb.xp < 0) ? def : __ldg(&L.xe[(size_t)nb.xp * LEAF + off - 448]); }
     xm = X > 0 ? x[base + off - 64] : (nb.xm >= 0 ? x[(size_t)nb.xm * LEAF + off + 448] : 0.f);
-    cxm = CONST_COEF ? def : L.xe[base + off];
-    if (Y < 7) { yp = x[base + off + 8]; cyp = CONST_COEF ? def : L.ye[base + off + 8]; }
-    else { yp = nb.yp >= 0 ? x[(size_t)nb.yp * LEAF + off - 56] : 0.f; cyp = (CONST_COEF || nb.yp < 0) ? def : L.ye[(size_t)nb.yp * LEAF + off - 56]; }
+    cxm = CONST_COEF ? def : __ldg(&L.xe[base + off]);
+    if (Y < 7) { yp = x[base + off + 8]; cyp = CONST_COEF ? def : __ldg(&L.ye[base + off + 8]); }
+    else { yp = nb.yp >= 0 ? x[(size_t)nb.yp * LEAF + off - 56] : 0.f; cyp = (CONST_COEF || nb.yp < 0) ? def : __ldg(&L.ye[(size_t)nb.yp * LEAF + off - 56]); }
     ym = Y > 0 ? x[base + off - 8] : (nb.ym >= 0 ? x[(size_t)nb.ym * LEAF + off + 56] : 0.f);
-    cym = CONST_COEF ? def : L.ye[base + off];
-    if (Z < 7) { zp = x[base + off + 1]; czp = CONST_COEF ? def : L.ze[base + off + 1]; }
-    else { zp = nb.zp >= 0 ? x[(size_t)nb.zp * LEAF + off - 7] : 0.f; czp = (CONST_COEF || nb.zp < 0) ? def : L.ze[(size_t)nb.zp * LEAF + off - 7]; }
+    cym = CONST_COEF ? def : __ldg(&L.ye[base + off]);
+    if (Z < 7) { zp = x[base + off + 1]; czp = CONST_COEF ? def : __ldg(&L.ze[base + off + 1]); }
+    else { zp = nb.zp >= 0 ? x[(size_t)nb.zp * LEAF + off - 7] : 0.f; czp = (CONST_COEF || nb.zp < 0) ? def : __ldg(&L.ze[(size_t)nb.zp * LEAF + off - 7]); }
     zm = Z > 0 ? x[base + off - 1] : (nb.zm >= 0 ? x[(size_t)nb.zm * LEAF + off + 7] : 0.f);
-    czm = CONST_COEF ? def : L.ze[base + off];
+    czm = CONST_COEF ? def : __ldg(&L.ze[base + off]);
     float fx = __fadd_rn(__fmul_rn(xp, cxp), __fmul_rn(xm, cxm));
     float fy = __fadd_rn(__fmul_rn(yp, cyp), __fmul_rn(ym, cym));
     float fz = __fadd_rn(__fmul_rn(zp, czp), __fmul_rn(zm, czm));
     return __fadd_rn(__fadd_rn(fx, fy), fz);
 }
-// a leaf takes the constant path when its own and its upper neighbours' face leaves read as default
-__device__ __forceinline__ bool leaf_const_faces(const LevelView& L, int leaf, const Nbr& nb) {
-    uint8_t f = L.flags[leaf];
-    if ((f & 14) != 14) return false;
-    if (nb.xp >= 0 && !(L.flags[nb.xp] & 2)) return false;
-    if (nb.yp >= 0 && !(L.flags[nb.yp] & 4)) return false;
-    if (nb.zp >= 0 && !(L.flags[nb.zp] & 8)) return false;
-    return true;
+__device__ __forceinline__ bool dof_bit(const LevelView& L, int leaf, int off) {
+    return (__ldg(&L.info[leaf].mask[off >> 6]) >> (off & 63)) & 1ull;
 }
-
-enum { MODE_LAPLACIAN = 0, MODE_RESIDUAL = 1 };
-// y = A x  or  y = b - A x  (uaamg.cpp:1085-1106); optional per-leaf partial of x.y (Laplacian) or
-// |y|_inf (Residual) for the fused reductions
-template <int MODE>
-__global__ void __launch_bounds__(512) apply_kernel(LevelView L, const float* __restrict__ x, const float* __restrict__ b,
-                                                    float* __restrict__ y, float* __restrict__ partial) {
-    __shared__ float sm16[16];
-    const int leaf = blockIdx.x, off = threadIdx.x;
-    const size_t i = (size_t)leaf * LEAF + off;
-    const uint64_t* m = L.dof + (size_t)leaf * 8;
-    uint64_t any = m[0] | m[1] | m[2] | m[3] | m[4] | m[5] | m[6] | m[7];
-    if (!any) {  // the reference skips empty rows; vectors stay zero there
-        if (partial && threadIdx.x == 0) partial[leaf] = 0.f;
-        return;
-    }
-    const bool on = (m[off >> 6] >> (off & 63)) & 1ull;
-    float out = 0.f, red = 0.f;
-    if (on) {
-        Nbr nb = load_nbr(L.t, leaf);
-        float od = leaf_const_faces(L, leaf, nb) ? offdiag<true>(L, x, leaf, off, nb) : offdiag<false>(L, x, leaf, off, nb);
-        float xi = x[i];
-        float ax = __fmaf_rn(xi, L.diag[i], od);
-        if (MODE == MODE_RESIDUAL) { out = __fsub_rn(b[i], ax); red = out; }
-        else { out = ax; red = __fmul_rn(xi, ax); }
-    }
-    y[i] = out;
-    if (partial) {
-        float r = MODE == MODE_RESIDUAL ? block_absmax_512(red, sm16) : block_sum_512(red, sm16);
-        if (threadIdx.x == 0) partial[leaf] = r;
-    }
-}
-// one colour of red-black SOR, in place (uaamg.cpp:1109-1150): x <- fma(x, 1-w, ((b - off) * invdiag) * w)
-// 256 threads: each owns one voxel of the colour. colour 0 = red = (x+y+z) even.
-__global__ void __launch_bounds__(256) rbgs_kernel(LevelView L, float* __restrict__ x, const float* __restrict__ b, int colour,
-                                                   float w, float oneMinusW) {
-    const int leaf = blockIdx.x;
-    const uint64_t* m = L.dof + (size_t)leaf * 8;
-    uint64_t any = m[0] | m[1] | m[2] | m[3] | m[4] | m[5] | m[6] | m[7];
-    if (!any) return;
-    const int t = threadIdx.x;
+// one colour of red-black SOR on one leaf, in place (uaamg.cpp:1109-1150):
+// x <- fma(x, 1-w, ((b - off) * invdiag) * w). t in [0,256) owns one voxel of the colour;
+// colour 0 = red = (x+y+z) even.
+template <bool B_READONLY>
+__device__ __forceinline__ void rbgs_leaf(const LevelView& L, float* x, const float* b, int leaf, int t, int colour,
+                                          float w, float oneMinusW) {
     const int X = t >> 5, Y = (t >> 2) & 7;
     const int Z = ((t & 3) << 1) | ((X + Y + colour) & 1);
     const int off = (X << 6) | (Y << 3) | Z;
-    if (!((m[X] >> (off & 63)) & 1ull)) return;
-    Nbr nb = load_nbr(L.t, leaf);
-    float od = leaf_const_faces(L, leaf, nb) ? offdiag<true>(L, x, leaf, off, nb) : offdiag<false>(L, x, leaf, off, nb);
     const size_t i = (size_t)leaf * LEAF + off;
-    float tt = __fmul_rn(__fmul_rn(__fsub_rn(b[i], od), L.invdiag[i]), w);
-    x[i] = __fmaf_rn(x[i], oneMinusW, tt);
+    // independent of the leaf record: in flight together with it (the arrays cover every leaf)
+    const float bi = B_READONLY ? __ldg(&b[i]) : b[i], inv = __ldg(&L.invdiag[i]), xi = x[i];
+    const bool on = dof_bit(L, leaf, off);
+    const LeafInfo li = load_info(L, leaf);
+    if (!(li.flags & LI_ANY) || !on) return;
+    const Nbr nb = nbr_of(li);
+    const float od = (li.flags & LI_CONST) ? offdiag<true>(L, x, leaf, off, nb) : offdiag<false>(L, x, leaf, off, nb);
+    const float tt = __fmul_rn(__fmul_rn(__fsub_rn(bi, od), inv), w);
+    x[i] = __fmaf_rn(xi, oneMinusW, tt);
 }
-// restriction (uaamg.cpp:1773-1833): coarse = 1/8 sum of the active fine 2^3
-__global__ void __launch_bounds__(512) restrict_kernel(LevelView F, LevelView C, const float* __restrict__ fine, float* __restrict__ coarse) {
-    int leaf = blockIdx.x, off = threadIdx.x;
-    size_t i = (size_t)leaf * LEAF + off;
-    if (!mask_get(C.dof, leaf, off)) return;
-    int3 o = C.t.origin[leaf];
-    int fx = 2 * (o.x + (off >> 6)), fy = 2 * (o.y + ((off >> 3) & 7)), fz = 2 * (o.z + (off & 7));
-    int fl = topo_find(F.t, fx, fy, fz);
-    if (fl < 0) return;
-    int fb = voxel_off(fx, fy, fz);
+// the first red pass of a sweep that starts from a zero guess (setGridToResultAfterFirstRBGS,
+// uaamg.cpp:1665-1731): every neighbour is 0, so off = ((0*c + 0*c) + ...) = 0 and
+// x_red = fma(0, 1-w, ((b - 0) * invdiag) * w); black voxels are set to 0. No neighbour traffic.
+__device__ __forceinline__ void zero_red_leaf(const LevelView& L, float* x, const float* b, int leaf, int off, float w) {
+    const size_t i = (size_t)leaf * LEAF + off;
+    float v = 0.f;
+    const int X = off >> 6, Y = (off >> 3) & 7, Z = off & 7;
+    if (((X + Y + Z) & 1) == 0 && dof_bit(L, leaf, off)) v = __fmul_rn(__fmul_rn(b[i], __ldg(&L.invdiag[i])), w);
+    x[i] = v;
+}
+// A x on one voxel (uaamg.cpp:1085-1106)
+__device__ __forceinline__ float ax_voxel(const LevelView& L, const LeafInfo& li, const float* x, int leaf, int off) {
+    const Nbr nb = nbr_of(li);
+    const float od = (li.flags & LI_CONST) ? offdiag<true>(L, x, leaf, off, nb) : offdiag<false>(L, x, leaf, off, nb);
+    const size_t i = (size_t)leaf * LEAF + off;
+    return __fmaf_rn(x[i], __ldg(&L.diag[i]), od);
+}
+// restriction of one fine leaf's residual held in shared memory (uaamg.cpp:1773-1833): coarse = 1/8 sum of
+// the active fine 2^3, same (ii,jj,kk) order. q in [0,64) is the coarse cell inside the fine leaf's octant.
+__device__ __forceinline__ void restrict_leaf(const LevelView& F, const LevelView& C, const float* sres, int fineLeaf, int q,
+                                              float* __restrict__ coarse) {
+    const int cx = q >> 4, cy = (q >> 2) & 3, cz = q & 3;
+    const int fb = (cx << 7) | (cy << 4) | (cz << 1);
     float sum = 0.f;
+    bool any = false;
 #pragma unroll
     for (int ii = 0; ii < 2; ii++)
 #pragma unroll
@@ -391,55 +362,156 @@ __global__ void __launch_bounds__(512) restrict_kernel(LevelView F, LevelView C,
 #pragma unroll
             for (int kk = 0; kk < 2; kk++) {
                 int fo = fb + 64 * ii + 8 * jj + kk;
-                if (mask_get(F.dof, fl, fo)) sum = __fadd_rn(sum, fine[(size_t)fl * LEAF + fo]);
+                if (dof_bit(F, fineLeaf, fo)) { sum = __fadd_rn(sum, sres[fo]); any = true; }
             }
-    coarse[i] = __fmul_rn(sum, 0.125f);
+    if (!any) return;
+    const int3 o = F.t.origin[fineLeaf];
+    const int gx = (o.x >> 1) + cx, gy = (o.y >> 1) + cy, gz = (o.z >> 1) + cz;
+    const int cl = topo_find(C.t, gx, gy, gz);
+    if (cl < 0) return;
+    coarse[(size_t)cl * LEAF + voxel_off(gx, gy, gz)] = __fmul_rn(sum, 0.125f);
 }
 // prolongation<inplace_add> (uaamg.cpp:1835-1903), gathered per fine voxel: fine += alpha * coarse(parent)
-__global__ void __launch_bounds__(512) prolong_kernel(LevelView F, LevelView C, float* __restrict__ fine, const float* __restrict__ coarse, float alpha) {
-    int leaf = blockIdx.x, off = threadIdx.x;
-    if (!mask_get(F.dof, leaf, off)) return;
-    int3 o = F.t.origin[leaf];
-    int gx = o.x + (off >> 6), gy = o.y + ((off >> 3) & 7), gz = o.z + (off & 7);
-    int cx = gx >> 1, cy = gy >> 1, cz = gz >> 1;
-    int cl = topo_find(C.t, cx, cy, cz);
+__device__ __forceinline__ void prolong_voxel(const LevelView& F, const LevelView& C, float* fine, const float* coarse, int leaf,
+                                              int off, float alpha) {
+    if (!dof_bit(F, leaf, off)) return;
+    const int3 o = F.t.origin[leaf];
+    const int cx = (o.x + (off >> 6)) >> 1, cy = (o.y + ((off >> 3) & 7)) >> 1, cz = (o.z + (off & 7)) >> 1;
+    const int cl = topo_find(C.t, cx, cy, cz);
     if (cl < 0) return;
-    int co = voxel_off(cx, cy, cz);
-    if (!mask_get(C.dof, cl, co)) return;
-    size_t i = (size_t)leaf * LEAF + off;
+    const int co = voxel_off(cx, cy, cz);
+    if (!dof_bit(C, cl, co)) return;
+    const size_t i = (size_t)leaf * LEAF + off;
     fine[i] = __fadd_rn(fine[i], __fmul_rn(alpha, coarse[(size_t)cl * LEAF + co]));
 }
 
-// ---------------------------------------------------------------- level-0 vector kernels
-// scalars live on the device: s[0]=rho s[1]=sigma s[2]=alpha s[3]=beta s[4]=nu s[5]=rho_new
-__global__ void alpha_kernel(float* s) { s[2] = __fdiv_rn(s[0], s[1]); }
-__global__ void beta_kernel(float* s) { s[3] = __fdiv_rn(s[5], s[0]); s[0] = s[5]; }
-// r -= alpha z ; per-leaf |r|_inf (levelAlphaXPlusY + levelAbsMax, uaamg.cpp:2447-2479)
-__global__ void __launch_bounds__(512) axpy_absmax_kernel(const uint64_t* __restrict__ dof, const float* __restrict__ s,
-                                                          const float* __restrict__ z, float* __restrict__ r, float* __restrict__ partial) {
-    __shared__ float sm16[16];
-    int leaf = blockIdx.x, off = threadIdx.x;
-    size_t i = (size_t)leaf * LEAF + off;
-    float v = 0.f;
-    if (mask_get(dof, leaf, off)) { v = __fadd_rn(r[i], __fmul_rn(-s[2], z[i])); r[i] = v; }
-    float m = block_absmax_512(v, sm16);
-    if (threadIdx.x == 0) partial[leaf] = m;
+// ---------------------------------------------------------------- per-leaf kernels (large levels)
+__global__ void leaf_info_kernel(TopoView t, const uint64_t* __restrict__ dof, const uint8_t* __restrict__ flags,
+                                 LeafInfo* __restrict__ info) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= t.n) return;
+    const int* nb = t.nbr27 + (size_t)l * 27;
+    LeafInfo li;
+    li.nb[0] = nb[NB_XM]; li.nb[1] = nb[NB_XP]; li.nb[2] = nb[NB_YM]; li.nb[3] = nb[NB_YP]; li.nb[4] = nb[NB_ZM]; li.nb[5] = nb[NB_ZP];
+    uint64_t any = 0;
+    for (int k = 0; k < 8; k++) any |= dof[(size_t)l * 8 + k];
+    // constant path: own and upper neighbours' face leaves all read as the default
+    bool c = (flags[l] & 14) == 14;
+    if (li.nb[1] >= 0 && !(flags[li.nb[1]] & 2)) c = false;
+    if (li.nb[3] >= 0 && !(flags[li.nb[3]] & 4)) c = false;
+    if (li.nb[5] >= 0 && !(flags[li.nb[5]] & 8)) c = false;
+    li.flags = (any ? LI_ANY : 0) | (c ? LI_CONST : 0) | ((flags[l] & 1) ? LI_DIAG : 0);
+    li.pad = 0;
+    for (int k = 0; k < 8; k++) li.mask[k] = dof[(size_t)l * 8 + k];
+    for (int k = 0; k < 4; k++) li.pad2[k] = 0;
+    info[l] = li;
 }
-__global__ void __launch_bounds__(512) dot_kernel(const uint64_t* __restrict__ dof, const float* __restrict__ a,
-                                                  const float* __restrict__ b, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256) rbgs_kernel(LevelView L, float* x, const float* __restrict__ b, int colour, float w, float oneMinusW) {
+    rbgs_leaf<true>(L, x, b, blockIdx.x, threadIdx.x, colour, w, oneMinusW);
+}
+__global__ void __launch_bounds__(512) zero_red_kernel(LevelView L, float* __restrict__ x, const float* __restrict__ b, float w) {
+    zero_red_leaf(L, x, b, blockIdx.x, threadIdx.x, w);
+}
+// r = b - A x on a fine leaf, restricted straight into the coarse right-hand side (no residual round trip)
+__global__ void __launch_bounds__(512) residual_restrict_kernel(LevelView F, LevelView C, const float* x, const float* __restrict__ b,
+                                                                float* __restrict__ coarse) {
+    __shared__ float sres[LEAF];
+    const int leaf = blockIdx.x, off = threadIdx.x;
+    const LeafInfo li = load_info(F, leaf);
+    if (!(li.flags & LI_ANY)) return;
+    float r = 0.f;
+    if (dof_bit(F, leaf, off)) r = __fsub_rn(b[(size_t)leaf * LEAF + off], ax_voxel(F, li, x, leaf, off));
+    sres[off] = r;
+    __syncthreads();
+    if (off < 64) restrict_leaf(F, C, sres, leaf, off, coarse);
+}
+__global__ void __launch_bounds__(512) prolong_kernel(LevelView F, LevelView C, float* fine, const float* __restrict__ coarse, float alpha) {
+    prolong_voxel(F, C, fine, coarse, blockIdx.x, threadIdx.x, alpha);
+}
+
+// ---------------------------------------------------------------- level-0 PCG kernels with fused reductions
+// scalars live on the device: s[0]=rho s[1]=sigma s[2]=alpha s[3]=beta s[4]=nu s[5]=rho_new.
+// Every producing kernel writes one partial per leaf; the LAST CTA to finish (threadfence + counter) folds the
+// partials in index order, so the result does not depend on which CTA that is, and applies the scalar update
+// that follows the reduction in solveMultigridPCG (uaamg.cpp:2332-2403). No separate fold / scalar launches.
+enum { FIN_NU = 0, FIN_SIGMA_ALPHA = 1, FIN_RHO_INIT = 2, FIN_RHO_BETA = 3 };
+template <bool IS_MAX>
+__device__ __forceinline__ void finish_reduction(float mine, float* partial, unsigned* counter, float* s, int fin, float* sm16) {
+    __shared__ bool sLast;
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = mine;
+        __threadfence();
+        sLast = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
+    float a = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+        float v = __ldcg(&partial[i]);
+        if (IS_MAX) a = (isfinite(a) ? (isfinite(v) ? fmaxf(a, v) : v) : a);
+        else a = __fadd_rn(a, v);
+    }
+    float r = IS_MAX ? block_absmax_512(a, sm16) : block_sum_512(a, sm16);
+    if (threadIdx.x == 0) {
+        if (fin == FIN_NU) s[4] = r;
+        else if (fin == FIN_SIGMA_ALPHA) { s[1] = r; s[2] = __fdiv_rn(s[0], r); }
+        else if (fin == FIN_RHO_INIT) s[0] = r;
+        else { s[5] = r; s[3] = __fdiv_rn(r, s[0]); s[0] = r; }
+        *counter = 0;
+    }
+}
+enum { MODE_LAPLACIAN = 0, MODE_RESIDUAL = 1 };
+// y = A x (+ sigma = x.y, alpha) or y = b - A x (+ nu = |y|_inf)   (uaamg.cpp:1085-1106)
+template <int MODE>
+__global__ void __launch_bounds__(512) apply_kernel(LevelView L, const float* x, const float* __restrict__ b, float* __restrict__ y,
+                                                    float* partial, unsigned* counter, float* s) {
     __shared__ float sm16[16];
-    int leaf = blockIdx.x, off = threadIdx.x;
-    size_t i = (size_t)leaf * LEAF + off;
-    float v = mask_get(dof, leaf, off) ? __fmul_rn(a[i], b[i]) : 0.f;
+    const int leaf = blockIdx.x, off = threadIdx.x;
+    const LeafInfo li = load_info(L, leaf);
+    float red = 0.f;
+    if (li.flags & LI_ANY) {  // the reference skips empty rows; vectors stay zero there
+        float out = 0.f;
+        if (dof_bit(L, leaf, off)) {
+            const size_t i = (size_t)leaf * LEAF + off;
+            float ax = ax_voxel(L, li, x, leaf, off);
+            if (MODE == MODE_RESIDUAL) { out = __fsub_rn(b[i], ax); red = out; }
+            else { out = ax; red = __fmul_rn(x[i], ax); }
+        }
+        y[(size_t)leaf * LEAF + off] = out;
+    }
+    float r = MODE == MODE_RESIDUAL ? block_absmax_512(red, sm16) : block_sum_512(red, sm16);
+    __syncthreads();
+    finish_reduction<MODE == MODE_RESIDUAL>(r, partial, counter, s, MODE == MODE_RESIDUAL ? FIN_NU : FIN_SIGMA_ALPHA, sm16);
+}
+// r -= alpha z ; nu = |r|_inf (levelAlphaXPlusY + levelAbsMax, uaamg.cpp:2447-2479)
+__global__ void __launch_bounds__(512) axpy_absmax_kernel(LevelView L, float* s, const float* __restrict__ z, float* __restrict__ r,
+                                                          float* partial, unsigned* counter) {
+    __shared__ float sm16[16];
+    const int leaf = blockIdx.x, off = threadIdx.x;
+    const size_t i = (size_t)leaf * LEAF + off;
+    float v = 0.f;
+    if (dof_bit(L, leaf, off)) { v = __fadd_rn(r[i], __fmul_rn(-s[2], z[i])); r[i] = v; }
+    float m = block_absmax_512(v, sm16);
+    __syncthreads();
+    finish_reduction<true>(m, partial, counter, s, FIN_NU, sm16);
+}
+__global__ void __launch_bounds__(512) dot_kernel(LevelView L, const float* __restrict__ a, const float* __restrict__ b, float* partial,
+                                                  unsigned* counter, float* s, int fin) {
+    __shared__ float sm16[16];
+    const int leaf = blockIdx.x, off = threadIdx.x;
+    const size_t i = (size_t)leaf * LEAF + off;
+    float v = dof_bit(L, leaf, off) ? __fmul_rn(a[i], b[i]) : 0.f;
     float m = block_sum_512(v, sm16);
-    if (threadIdx.x == 0) partial[leaf] = m;
+    __syncthreads();
+    finish_reduction<false>(m, partial, counter, s, fin, sm16);
 }
 // x += alpha p ; p = z + beta p   (uaamg.cpp:2396-2397); final=1: only the x update (:2375)
-__global__ void __launch_bounds__(512) update_kernel(const uint64_t* __restrict__ dof, const float* __restrict__ s,
-                                                     float* __restrict__ x, float* __restrict__ p, const float* __restrict__ z, int final) {
-    int leaf = blockIdx.x, off = threadIdx.x;
-    if (!mask_get(dof, leaf, off)) return;
-    size_t i = (size_t)leaf * LEAF + off;
+__global__ void __launch_bounds__(512) update_kernel(LevelView L, const float* __restrict__ s, float* __restrict__ x, float* __restrict__ p,
+                                                     const float* __restrict__ z, int final) {
+    const int leaf = blockIdx.x, off = threadIdx.x;
+    if (!dof_bit(L, leaf, off)) return;
+    const size_t i = (size_t)leaf * LEAF + off;
     float pv = p[i];
     x[i] = __fadd_rn(x[i], __fmul_rn(s[2], pv));
     if (!final) p[i] = __fadd_rn(z[i], __fmul_rn(s[3], pv));
@@ -449,7 +521,7 @@ __global__ void __launch_bounds__(512) update_kernel(const uint64_t* __restrict_
 // Compact ELL form of the coarsest matrix (getTriplets, uaamg.cpp:278-355) and a single-CTA
 // Jacobi-preconditioned CG, <= 10 iterations, tolerance float epsilon, zero initial guess
 // (Eigen::ConjugateGradient defaults, uaamg.cpp:2291-2303,2019-2023; Eigen itself is not in
-// the reference tree -> this follows Eigen's published algorithm, parity unpinned).
+// the reference tree -> this follows Eigen's published algorithm, parity unpinned at the bit level).
 __global__ void __launch_bounds__(512) ell_build_kernel(LevelView L, const uint32_t* __restrict__ leafStart,
                                                         int ndofPad, int* __restrict__ cols, float* __restrict__ vals,
                                                         int* __restrict__ rowOfVoxel) {
@@ -494,7 +566,7 @@ __global__ void ell_resolve_kernel(int* __restrict__ cols, int total, const int*
     int c = cols[i];
     if (c <= -2) cols[i] = rowOfVoxel[-2 - c];
 }
-constexpr int CG_THREADS = 1024;
+constexpr int BOT_THREADS = 1024;
 __device__ __forceinline__ float cg_block_sum(float v, float* sm33) {
     for (int d = 16; d > 0; d >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, d));
     __syncthreads();  // protect sm33 reuse
@@ -508,18 +580,20 @@ __device__ __forceinline__ float cg_block_sum(float v, float* sm33) {
     __syncthreads();
     return sm33[32];
 }
-__global__ void __launch_bounds__(CG_THREADS) coarse_cg_kernel(int ndof, int ndofPad, const int* __restrict__ cols,
-                                                               const float* __restrict__ vals, const int* __restrict__ rowOfVoxel,
-                                                               int nVoxels, const float* __restrict__ rhsGrid, float* __restrict__ lhsGrid) {
-    extern __shared__ float sm[];
+struct CoarseELL {
+    int ndof, ndofPad, nVoxels;
+    const int* cols; const float* vals; const int* rowOfVoxel;
+};
+// one CTA of BOT_THREADS threads; sm = 5*ndofPad floats of dynamic shared memory
+__device__ void coarse_cg(const CoarseELL& E, const float* rhsGrid, float* lhsGrid, float* sm, float* sm33) {
+    const int ndof = E.ndof, ndofPad = E.ndofPad;
     float* X = sm; float* R = X + ndofPad; float* P = R + ndofPad; float* T = P + ndofPad; float* DI = T + ndofPad;
-    __shared__ float sm33[33];
     const int tid = threadIdx.x;
-    for (int v = tid; v < nVoxels; v += CG_THREADS) { int r = rowOfVoxel[v]; if (r >= 0) R[r] = rhsGrid[v]; }
-    for (int r = tid; r < ndof; r += CG_THREADS) { X[r] = 0.f; float d = vals[r]; DI[r] = d != 0.f ? __fdiv_rn(1.0f, d) : 1.0f; }
+    for (int v = tid; v < E.nVoxels; v += BOT_THREADS) { int r = E.rowOfVoxel[v]; if (r >= 0) R[r] = rhsGrid[v]; }
+    for (int r = tid; r < ndof; r += BOT_THREADS) { X[r] = 0.f; float d = E.vals[r]; DI[r] = d != 0.f ? __fdiv_rn(1.0f, d) : 1.0f; }
     __syncthreads();
     float acc = 0.f;
-    for (int r = tid; r < ndof; r += CG_THREADS) acc = __fadd_rn(acc, __fmul_rn(R[r], R[r]));
+    for (int r = tid; r < ndof; r += BOT_THREADS) acc = __fadd_rn(acc, __fmul_rn(R[r], R[r]));
     float rhsNorm2 = cg_block_sum(acc, sm33);
     if (rhsNorm2 != 0.f) {
         const float tol = 1.1920929e-07f;
@@ -527,21 +601,21 @@ __global__ void __launch_bounds__(CG_THREADS) coarse_cg_kernel(int ndof, int ndo
         float residualNorm2 = rhsNorm2;
         if (!(residualNorm2 < threshold)) {
             acc = 0.f;
-            for (int r = tid; r < ndof; r += CG_THREADS) { float pv = __fmul_rn(DI[r], R[r]); P[r] = pv; acc = __fadd_rn(acc, __fmul_rn(R[r], pv)); }
+            for (int r = tid; r < ndof; r += BOT_THREADS) { float pv = __fmul_rn(DI[r], R[r]); P[r] = pv; acc = __fadd_rn(acc, __fmul_rn(R[r], pv)); }
             float absNew = cg_block_sum(acc, sm33);
             for (int it = 0; it < 10; it++) {
                 acc = 0.f;
-                for (int r = tid; r < ndof; r += CG_THREADS) {
+                for (int r = tid; r < ndof; r += BOT_THREADS) {
                     float s = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 7; k++) { int c = cols[k * ndofPad + r]; if (c >= 0) s = __fadd_rn(s, __fmul_rn(vals[k * ndofPad + r], P[c])); }
+                    for (int k = 0; k < 7; k++) { int c = E.cols[k * ndofPad + r]; if (c >= 0) s = __fadd_rn(s, __fmul_rn(E.vals[k * ndofPad + r], P[c])); }
                     T[r] = s;
                     acc = __fadd_rn(acc, __fmul_rn(P[r], s));
                 }
                 float pt = cg_block_sum(acc, sm33);
                 float alpha = __fdiv_rn(absNew, pt);
                 acc = 0.f;
-                for (int r = tid; r < ndof; r += CG_THREADS) {
+                for (int r = tid; r < ndof; r += BOT_THREADS) {
                     X[r] = __fadd_rn(X[r], __fmul_rn(alpha, P[r]));
                     float rv = __fsub_rn(R[r], __fmul_rn(alpha, T[r]));
                     R[r] = rv;
@@ -550,17 +624,89 @@ __global__ void __launch_bounds__(CG_THREADS) coarse_cg_kernel(int ndof, int ndo
                 residualNorm2 = cg_block_sum(acc, sm33);
                 if (residualNorm2 < threshold) break;
                 acc = 0.f;
-                for (int r = tid; r < ndof; r += CG_THREADS) { float zv = __fmul_rn(DI[r], R[r]); T[r] = zv; acc = __fadd_rn(acc, __fmul_rn(R[r], zv)); }
+                for (int r = tid; r < ndof; r += BOT_THREADS) { float zv = __fmul_rn(DI[r], R[r]); T[r] = zv; acc = __fadd_rn(acc, __fmul_rn(R[r], zv)); }
                 float absOld = absNew;
                 absNew = cg_block_sum(acc, sm33);
                 float beta = __fdiv_rn(absNew, absOld);
-                for (int r = tid; r < ndof; r += CG_THREADS) P[r] = __fadd_rn(T[r], __fmul_rn(beta, P[r]));
+                for (int r = tid; r < ndof; r += BOT_THREADS) P[r] = __fadd_rn(T[r], __fmul_rn(beta, P[r]));
                 __syncthreads();
             }
         }
     }
     __syncthreads();
-    for (int v = tid; v < nVoxels; v += CG_THREADS) { int r = rowOfVoxel[v]; if (r >= 0) lhsGrid[v] = X[r]; }
+    for (int v = tid; v < E.nVoxels; v += BOT_THREADS) { int r = E.rowOfVoxel[v]; if (r >= 0) lhsGrid[v] = X[r]; }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- the resident bottom of the mu-cycle
+// The W-like cycle (mu = 2) visits level l 2^l times; below the first few levels every visit is a handful of
+// leaves and the work is pure launch latency. mg_bottom_kernel executes the complete recursion below level
+// `first` as a flat op list on ONE resident CTA (1024 threads, block-level barriers between dependent passes,
+// data in L1/L2, the coarsest CG in shared memory) -- one launch per visit of level `first`.
+enum { OP_ZERO_RED = 0, OP_RED = 1, OP_BLACK = 2, OP_RESID_RESTRICT = 3, OP_PROLONG = 4, OP_COARSE = 5 };
+constexpr int BOT_MAX_LEVELS = 6;
+constexpr int BOT_MAX_OPS = 400;
+struct BottomLevel { LevelView v; float* x; float* b; int n; int xoff, boff; };  // offsets (floats) into dynamic smem, -1 = global
+struct BottomParams {
+    BottomLevel lv[BOT_MAX_LEVELS];
+    CoarseELL ell;
+    int nOps, nLevels;
+    int loadX;                    // the first level's x holds a guess that must be read (no ZERO_RED first)
+    float w, oneMinusW, prolongAlpha;
+    uint8_t op[BOT_MAX_OPS];      // low 3 bits: op, high bits: level index inside the bottom
+};
+__global__ void __launch_bounds__(BOT_THREADS) mg_bottom_kernel(const __grid_constant__ BottomParams P) {
+    extern __shared__ float dynsm[];
+    __shared__ float sm33[33];
+    __shared__ float sres[2 * LEAF];
+    const int tid = threadIdx.x;
+    // stage the first level's iterate in shared memory (x of every level and b of the lower levels live there
+    // for the whole cycle; only coefficients, masks and the first level's b are read from global memory)
+    if (P.lv[0].xoff >= 0 && P.loadX) {
+        float* xs = dynsm + P.lv[0].xoff;
+        for (int i = tid; i < P.lv[0].n * LEAF; i += BOT_THREADS) xs[i] = P.lv[0].x[i];
+        __syncthreads();
+    }
+    for (int k = 0; k < P.nOps; k++) {
+        const int code = P.op[k] & 7, li = P.op[k] >> 3;
+        const BottomLevel& B = P.lv[li];
+        float* x = B.xoff >= 0 ? dynsm + B.xoff : B.x;
+        const float* b = B.boff >= 0 ? dynsm + B.boff : B.b;
+        if (code == OP_ZERO_RED) {
+            for (int base = 0; base < B.n; base += 2) { int leaf = base + (tid >> 9); if (leaf < B.n) zero_red_leaf(B.v, x, b, leaf, tid & 511, P.w); }
+        } else if (code == OP_RED || code == OP_BLACK) {
+#pragma unroll 2
+            for (int base = 0; base < B.n; base += 4) { int leaf = base + (tid >> 8); if (leaf < B.n) rbgs_leaf<false>(B.v, x, b, leaf, tid & 255, code == OP_RED ? 0 : 1, P.w, P.oneMinusW); }
+        } else if (code == OP_RESID_RESTRICT) {
+            const BottomLevel& C = P.lv[li + 1];
+            float* cb = C.boff >= 0 ? dynsm + C.boff : C.b;
+            for (int base = 0; base < B.n; base += 2) {
+                int leaf = base + (tid >> 9), off = tid & 511;
+                bool live = false;
+                if (leaf < B.n) {
+                    const LeafInfo info = load_info(B.v, leaf);
+                    live = (info.flags & LI_ANY) != 0;
+                    float r = 0.f;
+                    if (live && dof_bit(B.v, leaf, off)) r = __fsub_rn(b[(size_t)leaf * LEAF + off], ax_voxel(B.v, info, x, leaf, off));
+                    sres[tid] = r;
+                }
+                __syncthreads();
+                if (live && off < 64) restrict_leaf(B.v, C.v, sres + (tid >> 9) * LEAF, leaf, off, cb);
+                __syncthreads();
+            }
+        } else if (code == OP_PROLONG) {
+            const BottomLevel& C = P.lv[li + 1];
+            const float* cx = C.xoff >= 0 ? dynsm + C.xoff : C.x;
+            for (int base = 0; base < B.n; base += 2) { int leaf = base + (tid >> 9); if (leaf < B.n) prolong_voxel(B.v, C.v, x, cx, leaf, tid & 511, P.prolongAlpha); }
+        } else {
+            coarse_cg(P.ell, b, x, dynsm, sm33);
+        }
+        __syncthreads();
+    }
+    if (P.lv[0].xoff >= 0) {
+        const float* xs = dynsm + P.lv[0].xoff;
+        for (int i = tid; i < P.lv[0].n * LEAF; i += BOT_THREADS) P.lv[0].x[i] = xs[i];
+    }
 }
 __global__ void leaf_popcount_kernel(const uint64_t* __restrict__ dof, int n, uint32_t* __restrict__ out) {
     int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -579,40 +725,64 @@ __global__ void warm_start_kernel(TopoView t, const uint64_t* __restrict__ dof, 
 }
 
 // ---------------------------------------------------------------- host-side solver
+// The bottom runs on ONE SM: its coefficient set (7 arrays x 2 KB per leaf) has to stay inside that SM's
+// L1 + shared memory (256 KB) or every pass turns into a serial chain of L2 round trips (measured: a 64-leaf
+// level inside the bottom cost 183 us per visit). 12 leaves = 168 KB.
+constexpr int BOTTOM_MAX_TOTAL_LEAVES = 12;
+constexpr size_t BOTTOM_SMEM_CAP = 96 * 1024;   // dynamic shared memory of mg_bottom_kernel (x, lower b, coarsest CG)
+
 struct Solver {
     World* w;
     std::vector<std::unique_ptr<Level>> levels;
+    float dt = 0.f;
     // coarsest ELL
     int ndof = 0, ndofPad = 0;
     DBuf<int> ellCols, rowOfVoxel;
     DBuf<float> ellVals;
     DBuf<float> partial, scal;  // [max leaves], [8]
+    DBuf<unsigned> counter;
+    int bottomFirst = 0;        // first level handled by mg_bottom_kernel
+    bool bottomInSmem = false;  // x (and the lower levels' b) of the bottom live in shared memory
+    size_t bottomSmem = 0;
+    int bottom_leaves(int first) const {
+        int t = 0;
+        for (int l = first; l < (int)levels.size(); l++) t += levels[l]->n;
+        return t;
+    }
+    size_t bottom_need(int first) const {
+        size_t need = (size_t)5 * ndofPad * sizeof(float);
+        for (int l = first; l < (int)levels.size(); l++) need += (size_t)levels[l]->n * LEAF * sizeof(float) * (l == first ? 1 : 2);
+        return need;
+    }
 
     void alloc_vectors(Level& L) {
         size_t n = (size_t)L.n * LEAF;
-        L.x.alloc(n, w->stream); L.b.alloc(n, w->stream); L.tmp.alloc(n, w->stream);
-        L.x.zero(); L.b.zero(); L.tmp.zero();
+        L.x.alloc(n, w->stream); L.b.alloc(n, w->stream);
+        L.x.zero(); L.b.zero();
     }
     void finish_level(Level& L) {
         L.invdiag.alloc((size_t)L.n * LEAF, w->stream);
         L.flags.alloc(L.n, w->stream);
+        L.info.alloc(L.n, w->stream);
         FB_LAUNCH(w, "mg_trim", (size_t)L.n * LEAF * 24) trim_kernel<<<L.n, 512, 0, w->stream>>>(L.dof.p, L.diag.p, L.xe.p, L.ye.p, L.ze.p, L.invdiag.p, L.flags.p, L.term);
         check_launch("trim");
+        FB_LAUNCH(w, "mg_leaf_info", (size_t)L.n * 140) leaf_info_kernel<<<(L.n + 127) / 128, 128, 0, w->stream>>>(L.topo->view(), L.dof.p, L.flags.p, L.info.p);
+        check_launch("leaf_info");
         L.numDof = (int)mask_count(w, L.dof.p, L.n);
     }
     void coarsen() {
         const Level& F = *levels.back();
         DBuf<int3> cand(F.n, w->stream);
-        DBuf<uint32_t> counter(1, w->stream);
-        counter.zero();
-        FB_LAUNCH(w, "mg_coarse_leaves", (size_t)F.n * 76) dof_leaf_origins_kernel<<<(F.n + 127) / 128, 128, 0, w->stream>>>(F.topo->view(), F.dof.p, cand.p, counter.p);
+        DBuf<uint32_t> cnt(1, w->stream);
+        cnt.zero();
+        FB_LAUNCH(w, "mg_coarse_leaves", (size_t)F.n * 76) dof_leaf_origins_kernel<<<(F.n + 127) / 128, 128, 0, w->stream>>>(F.topo->view(), F.dof.p, cand.p, cnt.p);
         check_launch("dof_leaf_origins");
-        uint32_t cnt = 0;
-        FB_CUDA(cudaMemcpyAsync(&cnt, counter.p, 4, cudaMemcpyDeviceToHost, w->stream));
+        uint32_t h = 0;
+        FB_CUDA(cudaMemcpyAsync(&h, cnt.p, 4, cudaMemcpyDeviceToHost, w->stream));
         sync(w);
         auto Lp = std::make_unique<Level>();
         Level& L = *Lp;
-        L.topo = topo_from_origins_dev(w, cand.p, (int)cnt, false);
+        L.topo = topo_from_origins_dev(w, cand.p, (int)h, false);
         L.n = L.topo->n;
         L.dx = 2.0f * F.dx;
         L.term = dt / (L.dx * L.dx);
@@ -625,8 +795,6 @@ struct Solver {
         alloc_vectors(L);
         levels.push_back(std::move(Lp));
     }
-    float dt = 0.f;
-
     void build_coarsest() {
         Level& L = *levels.back();
         ndof = L.numDof;
@@ -647,77 +815,144 @@ struct Solver {
         int total = 7 * ndofPad;
         FB_LAUNCH(w, "mg_ell_resolve", (size_t)total * 8) ell_resolve_kernel<<<(total + 255) / 256, 256, 0, w->stream>>>(ellCols.p, total, rowOfVoxel.p);
         check_launch("ell_resolve");
-        size_t smemBytes = (size_t)5 * ndofPad * sizeof(float);
-        FB_CUDA(cudaFuncSetAttribute(coarse_cg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smemBytes, 1024)));
+        // the bottom starts at the first level from which everything fits in shared memory and the op list fits
+        const int nl = (int)levels.size();
+        bottomFirst = nl - 1;
+        bottomInSmem = bottom_need(nl - 1) <= BOTTOM_SMEM_CAP;
+        if (bottomInSmem) {
+            while (bottomFirst > 0 && nl - (bottomFirst - 1) <= 5 && bottom_need(bottomFirst - 1) <= BOTTOM_SMEM_CAP &&
+                   bottom_leaves(bottomFirst - 1) <= BOTTOM_MAX_TOTAL_LEAVES) bottomFirst--;
+            bottomSmem = bottom_need(bottomFirst);
+        } else {
+            while (bottomFirst > 0 && bottom_leaves(bottomFirst - 1) <= BOTTOM_MAX_TOTAL_LEAVES && nl - (bottomFirst - 1) <= 5) bottomFirst--;
+            bottomSmem = (size_t)5 * ndofPad * sizeof(float);
+        }
+        bottomSmem = std::max<size_t>(bottomSmem, 1024);
+        FB_CUDA(cudaFuncSetAttribute(mg_bottom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bottomSmem));
     }
-    void coarsest_solve(float* lhs, const float* rhs) {
-        Level& L = *levels.back();
-        size_t smemBytes = (size_t)5 * ndofPad * sizeof(float);
-        FB_LAUNCH(w, "mg_coarse_cg", (size_t)ndof * 7 * 8 * 10) coarse_cg_kernel<<<1, CG_THREADS, smemBytes, w->stream>>>(ndof, ndofPad, ellCols.p, ellVals.p, rowOfVoxel.p, L.n * LEAF, rhs, lhs);
-        check_launch("coarse_cg");
+    // op list of one visit of bottom level li (index inside the bottom): muCyclePreconditioner<2,skip_first>
+    // (uaamg.cpp:1993-2126) when precond, muCycleIterative<2> (:2127-2288) otherwise
+    void emit(std::vector<uint8_t>& ops, int li, int nBottom, int n, bool skipFirst, bool precond, int postSmooth, bool isTop) {
+        auto put = [&](int code) { ops.push_back((uint8_t)(code | (li << 3))); };
+        const bool coarsest = li == nBottom - 1;
+        if (precond) {
+            if (coarsest) { put(OP_COARSE); return; }
+            if (skipFirst) { put(OP_ZERO_RED); put(OP_BLACK); }
+            for (int i = (skipFirst ? 1 : 0); i < n; i++) { put(OP_RED); put(OP_BLACK); }
+            put(OP_RESID_RESTRICT);
+            emit(ops, li + 1, nBottom, n, true, true, 0, false);
+            emit(ops, li + 1, nBottom, n, false, true, 0, false);
+            put(OP_PROLONG);
+            for (int i = 0; i < n; i++) { put(OP_BLACK); put(OP_RED); }
+        } else {
+            if (coarsest) { for (int i = 0; i < 10 * n; i++) { put(OP_RED); put(OP_BLACK); } return; }
+            for (int i = 0; i < n; i++) { put(OP_RED); put(OP_BLACK); }
+            put(OP_RESID_RESTRICT);
+            for (int mu = 0; mu < 2; mu++) emit(ops, li + 1, nBottom, n, false, false, 0, false);
+            put(OP_PROLONG);
+            for (int i = 0; i < n; i++) { put(OP_BLACK); put(OP_RED); }
+            for (int i = 0; i < postSmooth && isTop; i++) { put(OP_BLACK); put(OP_RED); }
+        }
+    }
+    void launch_bottom(float* x, const float* b, int n, bool skipFirst, bool precond, int postSmooth) {
+        const int nl = (int)levels.size();
+        const int nBottom = nl - bottomFirst;
+        BottomParams P;
+        std::vector<uint8_t> ops;
+        emit(ops, 0, nBottom, n, skipFirst, precond, postSmooth, bottomFirst == 0);
+        // a program that needs several launches keeps its state in global memory between them
+        const bool smem = bottomInSmem && ops.size() <= (size_t)BOT_MAX_OPS;
+        int cursor = 5 * ndofPad;
+        for (int i = 0; i < nBottom; i++) {
+            Level& L = *levels[bottomFirst + i];
+            P.lv[i].v = view_of(L);
+            P.lv[i].x = i == 0 ? x : L.x.p;
+            P.lv[i].b = i == 0 ? const_cast<float*>(b) : L.b.p;
+            P.lv[i].n = L.n;
+            P.lv[i].xoff = P.lv[i].boff = -1;
+            if (smem) {
+                P.lv[i].xoff = cursor; cursor += L.n * LEAF;
+                if (i > 0) { P.lv[i].boff = cursor; cursor += L.n * LEAF; }
+            }
+        }
+        P.nLevels = nBottom;
+        P.loadX = (ops.empty() || (ops[0] & 7) != OP_ZERO_RED) && (ops.empty() || (ops[0] & 7) != OP_COARSE) ? 1 : 0;
+        Level& C = *levels.back();
+        P.ell = CoarseELL{ndof, ndofPad, C.n * LEAF, ellCols.p, ellVals.p, rowOfVoxel.p};
+        P.w = precond ? 1.2f : 1.0f;
+        P.oneMinusW = 1.0f - P.w;
+        P.prolongAlpha = precond ? 1.0f : 0.5f;
+        // long programs (the pure-multigrid fallback smooths 10n times at the coarsest level) go out in pieces
+        uint64_t dofs = 0;
+        for (int i = 0; i < nBottom; i++) dofs += (uint64_t)levels[bottomFirst + i]->numDof << i;
+        for (size_t pos = 0; pos < ops.size(); pos += BOT_MAX_OPS) {
+            P.nOps = (int)std::min<size_t>(BOT_MAX_OPS, ops.size() - pos);
+            std::copy(ops.begin() + pos, ops.begin() + pos + P.nOps, P.op);
+            FB_LAUNCH(w, "mg_bottom", dofs * 121) mg_bottom_kernel<<<1, BOT_THREADS, bottomSmem, w->stream>>>(P);
+        }
+        check_launch("mg_bottom");
+    }
+    void rbgs_pass(Level& L, float* x, const float* b, int colour, float wSor) {
+        // one colour: read x (own + halo), b, invdiag, write half of x  -> ~14 B/DOF + coefficients
+        FB_LAUNCH(w, "mg_rbgs", (uint64_t)L.numDof * 14) rbgs_kernel<<<L.n, 256, 0, w->stream>>>(view_of(L), x, b, colour, wSor, 1.0f - wSor);
     }
     void rbgs(Level& L, float* x, const float* b, bool redFirst, float wSor) {
-        LevelView v = view_of(L);
-        float omw = 1.0f - wSor;
-        // one colour: read x (own + halo), b, invdiag, write half of x  -> ~14 B/DOF + coefficients
-        uint64_t bytes = (uint64_t)L.numDof * 14;
-        FB_LAUNCH(w, "mg_rbgs", bytes) rbgs_kernel<<<L.n, 256, 0, w->stream>>>(v, x, b, redFirst ? 0 : 1, wSor, omw);
-        FB_LAUNCH(w, "mg_rbgs", bytes) rbgs_kernel<<<L.n, 256, 0, w->stream>>>(v, x, b, redFirst ? 1 : 0, wSor, omw);
+        rbgs_pass(L, x, b, redFirst ? 0 : 1, wSor);
+        rbgs_pass(L, x, b, redFirst ? 1 : 0, wSor);
         check_launch("rbgs");
     }
-    void residual(Level& L, float* out, const float* x, const float* b, float* partialOut) {
-        FB_LAUNCH(w, "mg_residual", (uint64_t)L.numDof * 16) apply_kernel<MODE_RESIDUAL><<<L.n, 512, 0, w->stream>>>(view_of(L), x, b, out, partialOut);
-        check_launch("residual");
+    void residual_restrict(Level& L, Level& P, const float* x, const float* b) {
+        FB_LAUNCH(w, "mg_residual_restrict", (uint64_t)L.numDof * 8 + (uint64_t)P.numDof * 4)
+            residual_restrict_kernel<<<L.n, 512, 0, w->stream>>>(view_of(L), view_of(P), x, b, P.b.p);
+        check_launch("residual_restrict");
     }
-    void laplacian(Level& L, float* out, const float* x, float* partialOut) {
-        FB_LAUNCH(w, "mg_laplacian", (uint64_t)L.numDof * 12) apply_kernel<MODE_LAPLACIAN><<<L.n, 512, 0, w->stream>>>(view_of(L), x, nullptr, out, partialOut);
-        check_launch("laplacian");
+    void prolong(Level& L, Level& P, float* x, float alpha) {
+        FB_LAUNCH(w, "mg_prolong", (uint64_t)L.numDof * 8 + (uint64_t)P.numDof * 4) prolong_kernel<<<L.n, 512, 0, w->stream>>>(view_of(L), view_of(P), x, P.x.p, alpha);
+        check_launch("prolong");
     }
     // muCyclePreconditioner<2, skip_first> with the RBGS smoother (uaamg.cpp:1993-2126)
     void mu_cycle_precond(float* x, const float* b, int level, int n, bool skipFirst) {
-        const int nlevel = (int)levels.size();
+        if (level >= bottomFirst) { launch_bottom(x, b, n, skipFirst, true, 0); return; }
         Level& L = *levels[level];
-        if (level == nlevel - 1) { coarsest_solve(x, b); return; }
         const float wS = 1.2f;
         if (skipFirst) {
-            // setGridToResultAfterFirstRBGS == a red-first sweep from a zero guess (oracle/poisson.cpp)
-            FB_CUDA(cudaMemsetAsync(x, 0, (size_t)L.n * LEAF * 4, w->stream));
-            rbgs(L, x, b, true, wS);
+            // setGridToResultAfterFirstRBGS == the red pass of a sweep from a zero guess, then the black pass
+            FB_LAUNCH(w, "mg_zero_red", (uint64_t)L.numDof * 10) zero_red_kernel<<<L.n, 512, 0, w->stream>>>(view_of(L), x, b, wS);
+            rbgs_pass(L, x, b, 1, wS);
         }
         for (int i = (skipFirst ? 1 : 0); i < n; i++) rbgs(L, x, b, true, wS);
-        residual(L, L.tmp.p, x, b, nullptr);
         Level& P = *levels[level + 1];
-        FB_LAUNCH(w, "mg_restrict", (uint64_t)L.numDof * 4 + (uint64_t)P.numDof * 4) restrict_kernel<<<P.n, 512, 0, w->stream>>>(view_of(L), view_of(P), L.tmp.p, P.b.p);
-        check_launch("restrict");
+        residual_restrict(L, P, x, b);
         mu_cycle_precond(P.x.p, P.b.p, level + 1, n, true);
         mu_cycle_precond(P.x.p, P.b.p, level + 1, n, false);
-        FB_LAUNCH(w, "mg_prolong", (uint64_t)L.numDof * 8 + (uint64_t)P.numDof * 4) prolong_kernel<<<L.n, 512, 0, w->stream>>>(view_of(L), view_of(P), x, P.x.p, 1.0f);
-        check_launch("prolong");
+        prolong(L, P, x, 1.0f);
         for (int i = 0; i < n; i++) rbgs(L, x, b, false, wS);
     }
     // muCycleIterative<2> with RBGS, w = 1 (uaamg.cpp:2127-2288)
     void mu_cycle_iter(float* x, const float* b, int level, int n, int postSmooth) {
-        const int nlevel = (int)levels.size();
+        if (level >= bottomFirst) { launch_bottom(x, b, n, false, false, postSmooth); return; }
         Level& L = *levels[level];
         const float wS = 1.0f;
-        if (level == nlevel - 1) { for (int i = 0; i < 10 * n; i++) rbgs(L, x, b, true, wS); return; }
         for (int i = 0; i < n; i++) rbgs(L, x, b, true, wS);
-        residual(L, L.tmp.p, x, b, nullptr);
         Level& P = *levels[level + 1];
-        FB_LAUNCH(w, "mg_restrict", (uint64_t)L.numDof * 4 + (uint64_t)P.numDof * 4) restrict_kernel<<<P.n, 512, 0, w->stream>>>(view_of(L), view_of(P), L.tmp.p, P.b.p);
-        check_launch("restrict");
+        residual_restrict(L, P, x, b);
         for (int mu = 0; mu < 2; mu++) mu_cycle_iter(P.x.p, P.b.p, level + 1, n, 0);
-        FB_LAUNCH(w, "mg_prolong", (uint64_t)L.numDof * 8 + (uint64_t)P.numDof * 4) prolong_kernel<<<L.n, 512, 0, w->stream>>>(view_of(L), view_of(P), x, P.x.p, 0.5f);
-        check_launch("prolong");
+        prolong(L, P, x, 0.5f);
         for (int i = 0; i < n; i++) rbgs(L, x, b, false, wS);
         for (int i = 0; i < postSmooth && level == 0; i++) rbgs(L, x, b, false, wS);
     }
-    float fold(bool isMax, int n, int slot) {
-        if (isMax) fold_kernel<true><<<1, RED_THREADS, 0, w->stream>>>(partial.p, n, scal.p + slot);
-        else fold_kernel<false><<<1, RED_THREADS, 0, w->stream>>>(partial.p, n, scal.p + slot);
-        w->launches++;
-        check_launch("fold");
-        return 0.f;
+    // level-0 vector kernels
+    void residual0(Level& L0, float* out, const float* x, const float* b) {
+        FB_LAUNCH(w, "pcg_residual", (uint64_t)L0.numDof * 16) apply_kernel<MODE_RESIDUAL><<<L0.n, 512, 0, w->stream>>>(view_of(L0), x, b, out, partial.p, counter.p, scal.p);
+        check_launch("residual");
+    }
+    void laplacian0(Level& L0, float* out, const float* x) {
+        FB_LAUNCH(w, "pcg_laplacian_dot", (uint64_t)L0.numDof * 12) apply_kernel<MODE_LAPLACIAN><<<L0.n, 512, 0, w->stream>>>(view_of(L0), x, nullptr, out, partial.p, counter.p, scal.p);
+        check_launch("laplacian");
+    }
+    void dot0(Level& L0, const float* a, const float* b, int fin) {
+        FB_LAUNCH(w, "pcg_dot", (uint64_t)L0.numDof * 8) dot_kernel<<<L0.n, 512, 0, w->stream>>>(view_of(L0), a, b, partial.p, counter.p, scal.p, fin);
+        check_launch("dot");
     }
     float read_scalar(int slot) {
         float h = 0.f;
@@ -754,31 +989,29 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
         FB_LAUNCH(w, "mg_build_finest", nv * 36) build_finest_kernel<<<n, 512, 0, w->stream>>>(pool->view(), phi.val.p, phi.bg, phi.mask.p, fw.val[0].p, fw.val[1].p, fw.val[2].p, dt / (dx * dx), L.dof.p, L.diag.p, L.xe.p, L.ye.p, L.ze.p);
         check_launch("build_finest");
         S.finish_level(L);
-        S.alloc_vectors(L);
-        S.levels.push_back(std::move(Lp));
+        S.levels.push_back(std::move(Lp));  // level 0 iterates on the PCG vectors; it owns no x/b
     }
     while (S.levels.back()->numDof > MAX_COARSEST) S.coarsen();
     S.build_coarsest();
     Level& L0 = *S.levels[0];
     st.levels = (int)S.levels.size();
     st.numDof = L0.numDof;
-    int maxLeaves = 0;
-    for (auto& L : S.levels) maxLeaves = std::max(maxLeaves, L->n);
-    S.partial.alloc(maxLeaves, w->stream);
+    S.partial.alloc(n, w->stream);
     S.scal.alloc(8, w->stream);
     S.scal.zero();
+    S.counter.alloc(1, w->stream);
+    S.counter.zero();
 
     const size_t nv = (size_t)n * LEAF;
     DBuf<float> rhs(nv, w->stream), x(nv, w->stream), r(nv, w->stream), p(nv, w->stream), z(nv, w->stream);
-    x.zero(); p.zero(); z.zero();
+    x.zero(); p.zero(); z.zero(); r.zero();
     FB_LAUNCH(w, "mg_rhs", nv * 40) rhs_kernel<<<n, 512, 0, w->stream>>>(pool->view(), L0.dof.p, fw.val[0].p, fw.val[1].p, fw.val[2].p, vel.val[0].p, vel.val[1].p, vel.val[2].p,
                                                                         w->solidVelView[0].p, w->solidVelView[1].p, w->solidVelView[2].p, 1.0f / dx, rhs.p);
     check_launch("rhs");
 
     // solveMultigridPCG (uaamg.cpp:2332-2403)
     int status = 1, iter = 0;
-    S.residual(L0, r.p, x.p, rhs.p, S.partial.p);
-    S.fold(true, n, 4);
+    S.residual0(L0, r.p, x.p, rhs.p);
     float nu = S.read_scalar(4);
     const float initAbs = nu + 1e-16f;
     float numax = relTol * nu;
@@ -786,31 +1019,24 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
     if (nu <= numax) status = 0;
     else {
         S.mu_cycle_precond(p.p, r.p, 0, 4, true);
-        FB_LAUNCH(w, "pcg_dot", (uint64_t)L0.numDof * 8) dot_kernel<<<n, 512, 0, w->stream>>>(L0.dof.p, p.p, r.p, S.partial.p);
-        S.fold(false, n, 0);  // rho
+        S.dot0(L0, p.p, r.p, FIN_RHO_INIT);
         float nuOld = nu;
+        const LevelView v0 = view_of(L0);
         for (; iter < maxIter; iter++) {
-            S.laplacian(L0, z.p, p.p, S.partial.p);
-            S.fold(false, n, 1);  // sigma
-            alpha_kernel<<<1, 1, 0, w->stream>>>(S.scal.p);
-            w->launches++;
-            FB_LAUNCH(w, "pcg_axpy_absmax", (uint64_t)L0.numDof * 12) axpy_absmax_kernel<<<n, 512, 0, w->stream>>>(L0.dof.p, S.scal.p, z.p, r.p, S.partial.p);
-            S.fold(true, n, 4);
+            S.laplacian0(L0, z.p, p.p);  // z = A p, sigma = p.z, alpha = rho / sigma
+            FB_LAUNCH(w, "pcg_axpy_absmax", (uint64_t)L0.numDof * 12) axpy_absmax_kernel<<<n, 512, 0, w->stream>>>(v0, S.scal.p, z.p, r.p, S.partial.p, S.counter.p);
             nuOld = nu;
             nu = S.read_scalar(4);
             st.history.push_back(nu / initAbs);
             if (nu <= numax) {
-                FB_LAUNCH(w, "pcg_update", (uint64_t)L0.numDof * 12) update_kernel<<<n, 512, 0, w->stream>>>(L0.dof.p, S.scal.p, x.p, p.p, z.p, 1);
+                FB_LAUNCH(w, "pcg_update", (uint64_t)L0.numDof * 12) update_kernel<<<n, 512, 0, w->stream>>>(v0, S.scal.p, x.p, p.p, z.p, 1);
                 status = 0;
                 break;
             }
             if (nu > nuOld && iter > 3) { status = 1; break; }
             S.mu_cycle_precond(z.p, r.p, 0, 4, true);
-            FB_LAUNCH(w, "pcg_dot", (uint64_t)L0.numDof * 8) dot_kernel<<<n, 512, 0, w->stream>>>(L0.dof.p, z.p, r.p, S.partial.p);
-            S.fold(false, n, 5);  // rho_new
-            beta_kernel<<<1, 1, 0, w->stream>>>(S.scal.p);
-            w->launches++;
-            FB_LAUNCH(w, "pcg_update", (uint64_t)L0.numDof * 20) update_kernel<<<n, 512, 0, w->stream>>>(L0.dof.p, S.scal.p, x.p, p.p, z.p, 0);
+            S.dot0(L0, z.p, r.p, FIN_RHO_BETA);  // rho_new = z.r, beta = rho_new / rho, rho = rho_new
+            FB_LAUNCH(w, "pcg_update", (uint64_t)L0.numDof * 20) update_kernel<<<n, 512, 0, w->stream>>>(v0, S.scal.p, x.p, p.p, z.p, 0);
         }
         check_launch("pcg");
     }
@@ -821,15 +1047,13 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
         GridF& oldP = w->F(FLIPB200_PRESSURE);
         TopoView ot = oldP.topo ? oldP.topo->view() : TopoView{0, make_int3(0, 0, 0), make_int3(0, 0, 0), nullptr, nullptr, nullptr};
         FB_LAUNCH(w, "pcg_warm_start", nv * 8) warm_start_kernel<<<n, 512, 0, w->stream>>>(pool->view(), L0.dof.p, ot, oldP.val.p, oldP.bg, x.p);
-        S.residual(L0, r.p, x.p, rhs.p, S.partial.p);
-        S.fold(true, n, 4);
+        S.residual0(L0, r.p, x.p, rhs.p);
         nu = S.read_scalar(4);
         numax = relTol * nu;
         if (!(nu <= numax)) {
             for (int it2 = 0; it2 < 100; it2++) {
                 S.mu_cycle_iter(x.p, rhs.p, 0, 8, 8);
-                S.residual(L0, r.p, x.p, rhs.p, S.partial.p);
-                S.fold(true, n, 4);
+                S.residual0(L0, r.p, x.p, rhs.p);
                 nu = S.read_scalar(4);
                 if (nu <= numax) break;
             }

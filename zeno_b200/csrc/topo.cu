@@ -2,16 +2,24 @@
 // Replaces what the reference gets from openvdb::tree::Tree4 + tools::dilateActiveValues +
 // TopologyCopy/topologyUnion on this path.
 #include "world.cuh"
+#include <algorithm>
+#include <climits>
 
 namespace fb {
 namespace {
 
-__global__ void bbox_kernel(const int3* __restrict__ origins, int count, int* __restrict__ bb) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+// bounding box of the candidate leaves: grid-stride over a fixed number of CTAs, block-level reduction,
+// then six integer atomics per CTA (the first version issued them per warp over 16.8 M particles and
+// spent 2 ms per substep serialising on six addresses)
+constexpr int BBOX_THREADS = 256;
+__global__ void __launch_bounds__(BBOX_THREADS) bbox_kernel(const int3* __restrict__ origins, int count, int* __restrict__ bb) {
+    __shared__ int sLo[3][BBOX_THREADS / 32], sHi[3][BBOX_THREADS / 32];
     int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
-    if (i < count) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
         int3 o = origins[i];
-        lo[0] = hi[0] = o.x >> 3; lo[1] = hi[1] = o.y >> 3; lo[2] = hi[2] = o.z >> 3;
+        int c[3] = {o.x >> 3, o.y >> 3, o.z >> 3};
+#pragma unroll
+        for (int a = 0; a < 3; a++) { lo[a] = min(lo[a], c[a]); hi[a] = max(hi[a], c[a]); }
     }
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -19,22 +27,43 @@ __global__ void bbox_kernel(const int3* __restrict__ origins, int count, int* __
             lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], d));
             hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], d));
         }
-        if ((threadIdx.x & 31) == 0 && lo[a] != INT_MAX) {
-            atomicMin(&bb[a], lo[a]);
-            atomicMax(&bb[3 + a], hi[a]);
-        }
+        if ((threadIdx.x & 31) == 0) { sLo[a][threadIdx.x >> 5] = lo[a]; sHi[a][threadIdx.x >> 5] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        int a = threadIdx.x, l = INT_MAX, h = INT_MIN;
+        for (int k = 0; k < BBOX_THREADS / 32; k++) { l = min(l, sLo[a][k]); h = max(h, sHi[a][k]); }
+        if (l != INT_MAX) { atomicMin(&bb[a], l); atomicMax(&bb[3 + a], h); }
     }
 }
-__global__ void mark_kernel(const int3* __restrict__ origins, int count, int3 dmin, int3 ddim, int ring,
+// flags the directory cell of every candidate leaf; consecutive candidates usually share a leaf (the
+// particle store is leaf-sorted), so a lane only writes when its cell differs from the previous lane's
+__global__ void mark_kernel(const int3* __restrict__ origins, int count, int3 dmin, int3 ddim,
                             uint32_t* __restrict__ flags) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    int3 o = origins[i];
-    int lx = (o.x >> 3) - dmin.x, ly = (o.y >> 3) - dmin.y, lz = (o.z >> 3) - dmin.z;
-    for (int a = -ring; a <= ring; a++)
-        for (int b = -ring; b <= ring; b++)
-            for (int c = -ring; c <= ring; c++)
-                flags[((lx + a) * ddim.y + (ly + b)) * ddim.z + (lz + c)] = 1u;
+    int cell = -1;
+    if (i < count) {
+        int3 o = origins[i];
+        cell = (((o.x >> 3) - dmin.x) * ddim.y + ((o.y >> 3) - dmin.y)) * ddim.z + ((o.z >> 3) - dmin.z);
+    }
+    int prev = __shfl_up_sync(0xffffffffu, cell, 1);
+    if (cell >= 0 && ((threadIdx.x & 31) == 0 || prev != cell)) flags[cell] = 1u;
+}
+// ring = 1: also flag the 26 neighbour cells of every flagged cell (gather over the directory volume)
+__global__ void ring_kernel(const uint32_t* __restrict__ in, int3 ddim, uint32_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = ddim.x * ddim.y * ddim.z;
+    if (i >= total) return;
+    int lz = i % ddim.z, ly = (i / ddim.z) % ddim.y, lx = i / (ddim.z * ddim.y);
+    uint32_t on = 0;
+    for (int a = -1; a <= 1; a++)
+        for (int b = -1; b <= 1; b++)
+            for (int c = -1; c <= 1; c++) {
+                int x = lx + a, y = ly + b, z = lz + c;
+                if ((unsigned)x < (unsigned)ddim.x && (unsigned)y < (unsigned)ddim.y && (unsigned)z < (unsigned)ddim.z)
+                    on |= in[(x * ddim.y + y) * ddim.z + z];
+            }
+    out[i] = on ? 1u : 0u;
 }
 __global__ void assign_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ slots,
                               int3 dmin, int3 ddim, int* __restrict__ dir, int3* __restrict__ origin) {
@@ -157,7 +186,7 @@ TopoPtr topo_from_origins_dev(World* w, const int3* origins_dev, int count, bool
     DBuf<int> bb(6, w->stream);
     int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
     FB_CUDA(cudaMemcpyAsync(bb.p, init, sizeof(init), cudaMemcpyHostToDevice, w->stream));
-    FB_LAUNCH(w, "topo_bbox", count * 12) bbox_kernel<<<nblk(count, 256), 256, 0, w->stream>>>(origins_dev, count, bb.p);
+    FB_LAUNCH(w, "topo_bbox", count * 12) bbox_kernel<<<std::min<unsigned>(nblk(count, BBOX_THREADS), 148 * 8), BBOX_THREADS, 0, w->stream>>>(origins_dev, count, bb.p);
     check_launch("bbox");
     int h[6];
     FB_CUDA(cudaMemcpyAsync(h, bb.p, sizeof(h), cudaMemcpyDeviceToHost, w->stream));
@@ -170,8 +199,14 @@ TopoPtr topo_from_origins_dev(World* w, const int3* origins_dev, int count, bool
                "leaf bounding box exceeds the dense directory limit (2^28 leaves)");
     DBuf<uint32_t> flags(vol, w->stream), slots(vol, w->stream);
     flags.zero();
-    FB_LAUNCH(w, "topo_mark", count * 12) mark_kernel<<<nblk(count, 256), 256, 0, w->stream>>>(origins_dev, count, t->dmin, t->ddim, r, flags.p);
+    FB_LAUNCH(w, "topo_mark", count * 12) mark_kernel<<<nblk(count, 256), 256, 0, w->stream>>>(origins_dev, count, t->dmin, t->ddim, flags.p);
     check_launch("mark");
+    if (ring) {
+        DBuf<uint32_t> ringed(vol, w->stream);
+        FB_LAUNCH(w, "topo_ring", vol * 8) ring_kernel<<<nblk(vol, 256), 256, 0, w->stream>>>(flags.p, t->ddim, ringed.p);
+        check_launch("ring");
+        flags = std::move(ringed);
+    }
     uint64_t total = 0;
     exclusive_scan_u32(w, flags.p, slots.p, vol, &total);
     t->n = (int)total;
