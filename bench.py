@@ -219,8 +219,11 @@ def main():
     e0.record(stream)
     particle_steps = 0
     iters = []
+    step_ms = []
     for _ in range(args.steps):
+        t_s = time.perf_counter()
         step()
+        step_ms.append(round(1e3 * (time.perf_counter() - t_s), 3))  # host wall time; every substep ends synchronised
         particle_steps += w.particles_info()[1]
         iters.append(w.solver_info()["history"].shape[0] - 1)
     e1.record(stream)
@@ -319,7 +322,7 @@ def main():
                 "config": {"workload": f"FastFLIP dam-break {N}^3 tank, {n_particles} particles/GPU, {args.ppc} ppc, one substep = CFL_dt + G2PAdvectorSheetty(RK3) + FLIP_P2G + CutCellWeight + PushOutLiquidSDF + FieldAddVector + AssembleSolvePPE(5e-5) + SubtractPressureGradient",
                            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one tank per GPU; brick decomposition not implemented yet)",
                            "l2": "inputs larger than L2 (>=200 MB particle state per step), no flush",
-                           "pcg_iterations": iters},
+                           "pcg_iterations": iters, "step_ms_host": step_ms},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu,
                 "stage_ms": {"g2p_advect_rebin": stage_ms[0], "p2g": stage_ms[1], "stencils": stage_ms[2], "mgpcg": stage_ms[3], "gradient": stage_ms[4]},

@@ -273,6 +273,20 @@ __global__ void __launch_bounds__(512) rhs_kernel(TopoView t, const uint64_t* __
 // large levels, and mg_bottom_kernel, a single resident CTA that runs the whole mu-cycle below a level
 // (every sweep / residual / restriction / prolongation / the coarsest CG) without returning to the host.
 struct Nbr { int xm, xp, ym, yp, zm, zp; };
+// how the iterate x and the right-hand side b are read:
+//   M_LEAF  one CTA per leaf, one kernel per pass: x plain, b through the read-only path
+//   M_GRID  mg_cycle_kernel, many CTAs in one launch separated by grid barriers: x and b were written by other
+//           SMs inside this launch, so they are read from L2 (ld.global.cg), never from this SM's L1
+//   M_LOCAL one CTA owns the data for the whole launch (shared memory or its own L1): plain loads
+enum { M_LEAF = 0, M_GRID = 1, M_LOCAL = 2 };
+// L2-coherent load (LDG.E.STRONG.GPU): never served from this SM's L1
+__device__ __forceinline__ float ld_l2(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+template <int M> __device__ __forceinline__ float ldx(const float* p) { return M == M_GRID ? ld_l2(p) : *p; }
+template <int M> __device__ __forceinline__ float ldb(const float* p) { return M == M_GRID ? ld_l2(p) : (M == M_LEAF ? __ldg(p) : *p); }
 __device__ __forceinline__ LeafInfo load_info(const LevelView& L, int leaf) {
     const int4* p = reinterpret_cast<const int4*>(L.info + leaf);
     int4 a = __ldg(p), b = __ldg(p + 1);
@@ -284,24 +298,33 @@ __device__ __forceinline__ LeafInfo load_info(const LevelView& L, int leaf) {
 __device__ __forceinline__ Nbr nbr_of(const LeafInfo& li) { return Nbr{li.nb[0], li.nb[1], li.nb[2], li.nb[3], li.nb[4], li.nb[5]}; }
 // off-diagonal sum with the reference's association (uaamg.cpp:1044-1049):
 // ((x+ c_x+ + x- c_x-) + (y+ c_y+ + y- c_y-)) + (z+ c_z+ + z- c_z-)
-template <bool CONST_COEF>
+template <bool CONST_COEF, int M>
 __device__ __forceinline__ float offdiag(const LevelView& L, const float* x, int leaf, int off, const Nbr& nb) {
+    // branch-free: every neighbour is (leaf slot, offset) picked with selects, a missing neighbour leaf reads
+    // slot 0 and is masked afterwards, so the twelve loads issue back to back (the first version branched per
+    // face and the loads sat behind reconvergence points)
     const int X = off >> 6, Y = (off >> 3) & 7, Z = off & 7;
-    const size_t base = (size_t)leaf * LEAF;
     const float def = -L.term;
-    float xp, xm, yp, ym, zp, zm, cxp, cxm, cyp, cym, czp, czm;
-    if (X < 7) { xp = x[base + off + 64]; cxp = CONST_COEF ? def : __ldg(&L.xe[base + off + 64]); }
-    else { xp = nb.xp >= 0 ? x[(size_t)nb.xp * LEAF + off - 448] : 0.f; cxp = (CONST_COEF || nb.xp < 0) ? def : __ldg(&L.xe[(size_t)nb.xp * LEAF + off - 448]); }
-    xm = X > 0 ? x[base + off - 64] : (nb.xm >= 0 ? x[(size_t)nb.xm * LEAF + off + 448] : 0.f);
-    cxm = CONST_COEF ? def : __ldg(&L.xe[base + off]);
-    if (Y < 7) { yp = x[base + off + 8]; cyp = CONST_COEF ? def : __ldg(&L.ye[base + off + 8]); }
-    else { yp = nb.yp >= 0 ? x[(size_t)nb.yp * LEAF + off - 56] : 0.f; cyp = (CONST_COEF || nb.yp < 0) ? def : __ldg(&L.ye[(size_t)nb.yp * LEAF + off - 56]); }
-    ym = Y > 0 ? x[base + off - 8] : (nb.ym >= 0 ? x[(size_t)nb.ym * LEAF + off + 56] : 0.f);
-    cym = CONST_COEF ? def : __ldg(&L.ye[base + off]);
-    if (Z < 7) { zp = x[base + off + 1]; czp = CONST_COEF ? def : __ldg(&L.ze[base + off + 1]); }
-    else { zp = nb.zp >= 0 ? x[(size_t)nb.zp * LEAF + off - 7] : 0.f; czp = (CONST_COEF || nb.zp < 0) ? def : __ldg(&L.ze[(size_t)nb.zp * LEAF + off - 7]); }
-    zm = Z > 0 ? x[base + off - 1] : (nb.zm >= 0 ? x[(size_t)nb.zm * LEAF + off + 7] : 0.f);
-    czm = CONST_COEF ? def : __ldg(&L.ze[base + off]);
+    const int lxp = X < 7 ? leaf : nb.xp, oxp = X < 7 ? off + 64 : off - 448;
+    const int lxm = X > 0 ? leaf : nb.xm, oxm = X > 0 ? off - 64 : off + 448;
+    const int lyp = Y < 7 ? leaf : nb.yp, oyp = Y < 7 ? off + 8 : off - 56;
+    const int lym = Y > 0 ? leaf : nb.ym, oym = Y > 0 ? off - 8 : off + 56;
+    const int lzp = Z < 7 ? leaf : nb.zp, ozp = Z < 7 ? off + 1 : off - 7;
+    const int lzm = Z > 0 ? leaf : nb.zm, ozm = Z > 0 ? off - 1 : off + 7;
+    const size_t ixp = (size_t)max(lxp, 0) * LEAF + oxp, ixm = (size_t)max(lxm, 0) * LEAF + oxm;
+    const size_t iyp = (size_t)max(lyp, 0) * LEAF + oyp, iym = (size_t)max(lym, 0) * LEAF + oym;
+    const size_t izp = (size_t)max(lzp, 0) * LEAF + ozp, izm = (size_t)max(lzm, 0) * LEAF + ozm;
+    float xp = ldx<M>(&x[ixp]), xm = ldx<M>(&x[ixm]), yp = ldx<M>(&x[iyp]), ym = ldx<M>(&x[iym]), zp = ldx<M>(&x[izp]), zm = ldx<M>(&x[izm]);
+    float cxp = def, cxm = def, cyp = def, cym = def, czp = def, czm = def;
+    if (!CONST_COEF) {
+        const size_t i = (size_t)leaf * LEAF + off;
+        const float a = __ldg(&L.xe[ixp]), b2 = __ldg(&L.ye[iyp]), c2 = __ldg(&L.ze[izp]);
+        cxm = __ldg(&L.xe[i]); cym = __ldg(&L.ye[i]); czm = __ldg(&L.ze[i]);
+        cxp = lxp < 0 ? def : a; cyp = lyp < 0 ? def : b2; czp = lzp < 0 ? def : c2;
+    }
+    xp = lxp < 0 ? 0.f : xp; xm = lxm < 0 ? 0.f : xm;
+    yp = lyp < 0 ? 0.f : yp; ym = lym < 0 ? 0.f : ym;
+    zp = lzp < 0 ? 0.f : zp; zm = lzm < 0 ? 0.f : zm;
     float fx = __fadd_rn(__fmul_rn(xp, cxp), __fmul_rn(xm, cxm));
     float fy = __fadd_rn(__fmul_rn(yp, cyp), __fmul_rn(ym, cym));
     float fz = __fadd_rn(__fmul_rn(zp, czp), __fmul_rn(zm, czm));
@@ -313,39 +336,42 @@ __device__ __forceinline__ bool dof_bit(const LevelView& L, int leaf, int off) {
 // one colour of red-black SOR on one leaf, in place (uaamg.cpp:1109-1150):
 // x <- fma(x, 1-w, ((b - off) * invdiag) * w). t in [0,256) owns one voxel of the colour;
 // colour 0 = red = (x+y+z) even.
-template <bool B_READONLY>
+template <int M>
 __device__ __forceinline__ void rbgs_leaf(const LevelView& L, float* x, const float* b, int leaf, int t, int colour,
                                           float w, float oneMinusW) {
     const int X = t >> 5, Y = (t >> 2) & 7;
     const int Z = ((t & 3) << 1) | ((X + Y + colour) & 1);
     const int off = (X << 6) | (Y << 3) | Z;
     const size_t i = (size_t)leaf * LEAF + off;
-    // independent of the leaf record: in flight together with it (the arrays cover every leaf)
-    const float bi = B_READONLY ? __ldg(&b[i]) : b[i], inv = __ldg(&L.invdiag[i]), xi = x[i];
-    const bool on = dof_bit(L, leaf, off);
     const LeafInfo li = load_info(L, leaf);
-    if (!(li.flags & LI_ANY) || !on) return;
+    if (!(li.flags & LI_ANY)) return;   // uniform over the 256 threads of the leaf
+    // everything below is issued unconditionally (the arrays cover every voxel of every leaf); only the store
+    // is predicated on the DOF bit, so no load waits behind a branch
+    const float bi = ldb<M>(&b[i]), inv = __ldg(&L.invdiag[i]), xi = ldx<M>(&x[i]);
+    const bool on = dof_bit(L, leaf, off);
     const Nbr nb = nbr_of(li);
-    const float od = (li.flags & LI_CONST) ? offdiag<true>(L, x, leaf, off, nb) : offdiag<false>(L, x, leaf, off, nb);
+    const float od = (li.flags & LI_CONST) ? offdiag<true, M>(L, x, leaf, off, nb) : offdiag<false, M>(L, x, leaf, off, nb);
     const float tt = __fmul_rn(__fmul_rn(__fsub_rn(bi, od), inv), w);
-    x[i] = __fmaf_rn(xi, oneMinusW, tt);
+    if (on) x[i] = __fmaf_rn(xi, oneMinusW, tt);
 }
 // the first red pass of a sweep that starts from a zero guess (setGridToResultAfterFirstRBGS,
 // uaamg.cpp:1665-1731): every neighbour is 0, so off = ((0*c + 0*c) + ...) = 0 and
 // x_red = fma(0, 1-w, ((b - 0) * invdiag) * w); black voxels are set to 0. No neighbour traffic.
+template <int M>
 __device__ __forceinline__ void zero_red_leaf(const LevelView& L, float* x, const float* b, int leaf, int off, float w) {
     const size_t i = (size_t)leaf * LEAF + off;
     float v = 0.f;
     const int X = off >> 6, Y = (off >> 3) & 7, Z = off & 7;
-    if (((X + Y + Z) & 1) == 0 && dof_bit(L, leaf, off)) v = __fmul_rn(__fmul_rn(b[i], __ldg(&L.invdiag[i])), w);
+    if (((X + Y + Z) & 1) == 0 && dof_bit(L, leaf, off)) v = __fmul_rn(__fmul_rn(ldb<M>(&b[i]), __ldg(&L.invdiag[i])), w);
     x[i] = v;
 }
 // A x on one voxel (uaamg.cpp:1085-1106)
+template <int M>
 __device__ __forceinline__ float ax_voxel(const LevelView& L, const LeafInfo& li, const float* x, int leaf, int off) {
     const Nbr nb = nbr_of(li);
-    const float od = (li.flags & LI_CONST) ? offdiag<true>(L, x, leaf, off, nb) : offdiag<false>(L, x, leaf, off, nb);
+    const float od = (li.flags & LI_CONST) ? offdiag<true, M>(L, x, leaf, off, nb) : offdiag<false, M>(L, x, leaf, off, nb);
     const size_t i = (size_t)leaf * LEAF + off;
-    return __fmaf_rn(x[i], __ldg(&L.diag[i]), od);
+    return __fmaf_rn(ldx<M>(&x[i]), __ldg(&L.diag[i]), od);
 }
 // restriction of one fine leaf's residual held in shared memory (uaamg.cpp:1773-1833): coarse = 1/8 sum of
 // the active fine 2^3, same (ii,jj,kk) order. q in [0,64) is the coarse cell inside the fine leaf's octant.
@@ -372,6 +398,7 @@ __device__ __forceinline__ void restrict_leaf(const LevelView& F, const LevelVie
     coarse[(size_t)cl * LEAF + voxel_off(gx, gy, gz)] = __fmul_rn(sum, 0.125f);
 }
 // prolongation<inplace_add> (uaamg.cpp:1835-1903), gathered per fine voxel: fine += alpha * coarse(parent)
+template <int M>
 __device__ __forceinline__ void prolong_voxel(const LevelView& F, const LevelView& C, float* fine, const float* coarse, int leaf,
                                               int off, float alpha) {
     if (!dof_bit(F, leaf, off)) return;
@@ -382,7 +409,7 @@ __device__ __forceinline__ void prolong_voxel(const LevelView& F, const LevelVie
     const int co = voxel_off(cx, cy, cz);
     if (!dof_bit(C, cl, co)) return;
     const size_t i = (size_t)leaf * LEAF + off;
-    fine[i] = __fadd_rn(fine[i], __fmul_rn(alpha, coarse[(size_t)cl * LEAF + co]));
+    fine[i] = __fadd_rn(ldx<M>(&fine[i]), __fmul_rn(alpha, ldx<M>(&coarse[(size_t)cl * LEAF + co])));
 }
 
 // ---------------------------------------------------------------- per-leaf kernels (large levels)
@@ -407,10 +434,10 @@ __global__ void leaf_info_kernel(TopoView t, const uint64_t* __restrict__ dof, c
     info[l] = li;
 }
 __global__ void __launch_bounds__(256) rbgs_kernel(LevelView L, float* x, const float* __restrict__ b, int colour, float w, float oneMinusW) {
-    rbgs_leaf<true>(L, x, b, blockIdx.x, threadIdx.x, colour, w, oneMinusW);
+    rbgs_leaf<M_LEAF>(L, x, b, blockIdx.x, threadIdx.x, colour, w, oneMinusW);
 }
 __global__ void __launch_bounds__(512) zero_red_kernel(LevelView L, float* __restrict__ x, const float* __restrict__ b, float w) {
-    zero_red_leaf(L, x, b, blockIdx.x, threadIdx.x, w);
+    zero_red_leaf<M_LEAF>(L, x, b, blockIdx.x, threadIdx.x, w);
 }
 // r = b - A x on a fine leaf, restricted straight into the coarse right-hand side (no residual round trip)
 __global__ void __launch_bounds__(512) residual_restrict_kernel(LevelView F, LevelView C, const float* x, const float* __restrict__ b,
@@ -420,13 +447,13 @@ __global__ void __launch_bounds__(512) residual_restrict_kernel(LevelView F, Lev
     const LeafInfo li = load_info(F, leaf);
     if (!(li.flags & LI_ANY)) return;
     float r = 0.f;
-    if (dof_bit(F, leaf, off)) r = __fsub_rn(b[(size_t)leaf * LEAF + off], ax_voxel(F, li, x, leaf, off));
+    if (dof_bit(F, leaf, off)) r = __fsub_rn(b[(size_t)leaf * LEAF + off], ax_voxel<M_LEAF>(F, li, x, leaf, off));
     sres[off] = r;
     __syncthreads();
     if (off < 64) restrict_leaf(F, C, sres, leaf, off, coarse);
 }
 __global__ void __launch_bounds__(512) prolong_kernel(LevelView F, LevelView C, float* fine, const float* __restrict__ coarse, float alpha) {
-    prolong_voxel(F, C, fine, coarse, blockIdx.x, threadIdx.x, alpha);
+    prolong_voxel<M_LEAF>(F, C, fine, coarse, blockIdx.x, threadIdx.x, alpha);
 }
 
 // ---------------------------------------------------------------- level-0 PCG kernels with fused reductions
@@ -474,7 +501,7 @@ __global__ void __launch_bounds__(512) apply_kernel(LevelView L, const float* x,
         float out = 0.f;
         if (dof_bit(L, leaf, off)) {
             const size_t i = (size_t)leaf * LEAF + off;
-            float ax = ax_voxel(L, li, x, leaf, off);
+            float ax = ax_voxel<M_LEAF>(L, li, x, leaf, off);
             if (MODE == MODE_RESIDUAL) { out = __fsub_rn(b[i], ax); red = out; }
             else { out = ax; red = __fmul_rn(x[i], ax); }
         }
@@ -582,6 +609,7 @@ __device__ __forceinline__ float cg_block_sum(float v, float* sm33) {
 }
 struct CoarseELL {
     int ndof, ndofPad, nVoxels;
+    int inSmem;   // mg_cycle_kernel: the matrix is staged in CTA 0's shared memory (coarse_cg_smem)
     const int* cols; const float* vals; const int* rowOfVoxel;
 };
 // one CTA of BOT_THREADS threads; sm = 5*ndofPad floats of dynamic shared memory
@@ -638,6 +666,88 @@ __device__ void coarse_cg(const CoarseELL& E, const float* rhsGrid, float* lhsGr
     __syncthreads();
 }
 
+// The same CG with the coarsest matrix resident in shared memory in a compact symmetric form: per row the
+// diagonal, the three "minus" face coefficients and six 16-bit neighbour rows (28 B/row instead of 56 B/row of ELL
+// in L2); the coefficient towards a "plus" neighbour is that neighbour's "minus" coefficient. Same summation
+// order as coarse_cg (diag, x-, x+, y-, y+, z-, z+). sm: X,R,P,T [4N] then diag [N], minus [3N], cols [6N u16].
+__device__ void coarse_matrix_to_smem(const CoarseELL& E, float* sm) {
+    const int N = E.ndofPad;
+    float* diag = sm + 4 * N;
+    float* minus = diag + N;
+    unsigned short* cols = reinterpret_cast<unsigned short*>(minus + 3 * N);
+    for (int r = threadIdx.x; r < E.ndof; r += BOT_THREADS) {
+        diag[r] = E.vals[r];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            minus[ch * N + r] = E.vals[(1 + 2 * ch) * N + r];
+            int cm = E.cols[(1 + 2 * ch) * N + r], cp = E.cols[(2 + 2 * ch) * N + r];
+            cols[(2 * ch) * N + r] = cm >= 0 ? (unsigned short)cm : (unsigned short)0xffff;
+            cols[(2 * ch + 1) * N + r] = cp >= 0 ? (unsigned short)cp : (unsigned short)0xffff;
+        }
+    }
+    __syncthreads();
+}
+__device__ void coarse_cg_smem(const CoarseELL& E, const float* rhsGrid, float* lhsGrid, float* sm, float* sm33) {
+    const int ndof = E.ndof, N = E.ndofPad;
+    float* X = sm; float* R = X + N; float* P = R + N; float* T = P + N;
+    const float* diag = sm + 4 * N;
+    const float* minus = diag + N;
+    const unsigned short* cols = reinterpret_cast<const unsigned short*>(minus + 3 * N);
+    const int tid = threadIdx.x;
+    auto dinv = [&](int r) { float d = diag[r]; return d != 0.f ? __fdiv_rn(1.0f, d) : 1.0f; };
+    for (int v = tid; v < E.nVoxels; v += BOT_THREADS) { int r = __ldg(&E.rowOfVoxel[v]); if (r >= 0) R[r] = rhsGrid[v]; }
+    for (int r = tid; r < ndof; r += BOT_THREADS) X[r] = 0.f;
+    __syncthreads();
+    float acc = 0.f;
+    for (int r = tid; r < ndof; r += BOT_THREADS) acc = __fadd_rn(acc, __fmul_rn(R[r], R[r]));
+    float rhsNorm2 = cg_block_sum(acc, sm33);
+    if (rhsNorm2 != 0.f) {
+        const float tol = 1.1920929e-07f;
+        float threshold = fmaxf(__fmul_rn(__fmul_rn(tol, tol), rhsNorm2), 1.17549435e-38f);
+        float residualNorm2 = rhsNorm2;
+        if (!(residualNorm2 < threshold)) {
+            acc = 0.f;
+            for (int r = tid; r < ndof; r += BOT_THREADS) { float pv = __fmul_rn(dinv(r), R[r]); P[r] = pv; acc = __fadd_rn(acc, __fmul_rn(R[r], pv)); }
+            float absNew = cg_block_sum(acc, sm33);
+            for (int it = 0; it < 10; it++) {
+                acc = 0.f;
+                for (int r = tid; r < ndof; r += BOT_THREADS) {
+                    float s = __fadd_rn(0.f, __fmul_rn(diag[r], P[r]));
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) {
+                        unsigned cm = cols[(2 * ch) * N + r], cp = cols[(2 * ch + 1) * N + r];
+                        if (cm != 0xffffu) s = __fadd_rn(s, __fmul_rn(minus[ch * N + r], P[cm]));
+                        if (cp != 0xffffu) s = __fadd_rn(s, __fmul_rn(minus[ch * N + cp], P[cp]));
+                    }
+                    T[r] = s;
+                    acc = __fadd_rn(acc, __fmul_rn(P[r], s));
+                }
+                float pt = cg_block_sum(acc, sm33);
+                float alpha = __fdiv_rn(absNew, pt);
+                acc = 0.f;
+                for (int r = tid; r < ndof; r += BOT_THREADS) {
+                    X[r] = __fadd_rn(X[r], __fmul_rn(alpha, P[r]));
+                    float rv = __fsub_rn(R[r], __fmul_rn(alpha, T[r]));
+                    R[r] = rv;
+                    acc = __fadd_rn(acc, __fmul_rn(rv, rv));
+                }
+                residualNorm2 = cg_block_sum(acc, sm33);
+                if (residualNorm2 < threshold) break;
+                acc = 0.f;
+                for (int r = tid; r < ndof; r += BOT_THREADS) { float zv = __fmul_rn(dinv(r), R[r]); T[r] = zv; acc = __fadd_rn(acc, __fmul_rn(R[r], zv)); }
+                float absOld = absNew;
+                absNew = cg_block_sum(acc, sm33);
+                float beta = __fdiv_rn(absNew, absOld);
+                for (int r = tid; r < ndof; r += BOT_THREADS) P[r] = __fadd_rn(T[r], __fmul_rn(beta, P[r]));
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+    for (int v = tid; v < E.nVoxels; v += BOT_THREADS) { int r = __ldg(&E.rowOfVoxel[v]); if (r >= 0) lhsGrid[v] = X[r]; }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------- the resident bottom of the mu-cycle
 // The W-like cycle (mu = 2) visits level l 2^l times; below the first few levels every visit is a handful of
 // leaves and the work is pure launch latency. mg_bottom_kernel executes the complete recursion below level
@@ -646,7 +756,7 @@ __device__ void coarse_cg(const CoarseELL& E, const float* rhsGrid, float* lhsGr
 enum { OP_ZERO_RED = 0, OP_RED = 1, OP_BLACK = 2, OP_RESID_RESTRICT = 3, OP_PROLONG = 4, OP_COARSE = 5 };
 constexpr int BOT_MAX_LEVELS = 6;
 constexpr int BOT_MAX_OPS = 400;
-struct BottomLevel { LevelView v; float* x; float* b; int n; int xoff, boff; };  // offsets (floats) into dynamic smem, -1 = global
+struct BottomLevel { LevelView v; float* x; float* b; int n; int xoff, boff; int bReadOnly; };  // offsets (floats) into dynamic smem, -1 = global
 struct BottomParams {
     BottomLevel lv[BOT_MAX_LEVELS];
     CoarseELL ell;
@@ -673,10 +783,10 @@ __global__ void __launch_bounds__(BOT_THREADS) mg_bottom_kernel(const __grid_con
         float* x = B.xoff >= 0 ? dynsm + B.xoff : B.x;
         const float* b = B.boff >= 0 ? dynsm + B.boff : B.b;
         if (code == OP_ZERO_RED) {
-            for (int base = 0; base < B.n; base += 2) { int leaf = base + (tid >> 9); if (leaf < B.n) zero_red_leaf(B.v, x, b, leaf, tid & 511, P.w); }
+            for (int base = 0; base < B.n; base += 2) { int leaf = base + (tid >> 9); if (leaf < B.n) zero_red_leaf<M_LOCAL>(B.v, x, b, leaf, tid & 511, P.w); }
         } else if (code == OP_RED || code == OP_BLACK) {
 #pragma unroll 2
-            for (int base = 0; base < B.n; base += 4) { int leaf = base + (tid >> 8); if (leaf < B.n) rbgs_leaf<false>(B.v, x, b, leaf, tid & 255, code == OP_RED ? 0 : 1, P.w, P.oneMinusW); }
+            for (int base = 0; base < B.n; base += 4) { int leaf = base + (tid >> 8); if (leaf < B.n) rbgs_leaf<M_LOCAL>(B.v, x, b, leaf, tid & 255, code == OP_RED ? 0 : 1, P.w, P.oneMinusW); }
         } else if (code == OP_RESID_RESTRICT) {
             const BottomLevel& C = P.lv[li + 1];
             float* cb = C.boff >= 0 ? dynsm + C.boff : C.b;
@@ -687,7 +797,7 @@ __global__ void __launch_bounds__(BOT_THREADS) mg_bottom_kernel(const __grid_con
                     const LeafInfo info = load_info(B.v, leaf);
                     live = (info.flags & LI_ANY) != 0;
                     float r = 0.f;
-                    if (live && dof_bit(B.v, leaf, off)) r = __fsub_rn(b[(size_t)leaf * LEAF + off], ax_voxel(B.v, info, x, leaf, off));
+                    if (live && dof_bit(B.v, leaf, off)) r = __fsub_rn(b[(size_t)leaf * LEAF + off], ax_voxel<M_LOCAL>(B.v, info, x, leaf, off));
                     sres[tid] = r;
                 }
                 __syncthreads();
@@ -697,7 +807,7 @@ __global__ void __launch_bounds__(BOT_THREADS) mg_bottom_kernel(const __grid_con
         } else if (code == OP_PROLONG) {
             const BottomLevel& C = P.lv[li + 1];
             const float* cx = C.xoff >= 0 ? dynsm + C.xoff : C.x;
-            for (int base = 0; base < B.n; base += 2) { int leaf = base + (tid >> 9); if (leaf < B.n) prolong_voxel(B.v, C.v, x, cx, leaf, tid & 511, P.prolongAlpha); }
+            for (int base = 0; base < B.n; base += 2) { int leaf = base + (tid >> 9); if (leaf < B.n) prolong_voxel<M_LOCAL>(B.v, C.v, x, cx, leaf, tid & 511, P.prolongAlpha); }
         } else {
             coarse_cg(P.ell, b, x, dynsm, sm33);
         }
@@ -707,6 +817,232 @@ __global__ void __launch_bounds__(BOT_THREADS) mg_bottom_kernel(const __grid_con
         const float* xs = dynsm + P.lv[0].xoff;
         for (int i = tid; i < P.lv[0].n * LEAF; i += BOT_THREADS) P.lv[0].x[i] = xs[i];
     }
+}
+// ---------------------------------------------------------------- shared-memory leaf tiles (mg_cycle_kernel)
+// In the one-launch cycle the iterate is written by other SMs between passes, so it cannot be read through L1.
+// Reading the 7-point stencil straight from L2 fetches every line six times (measured: 1.4 us per 4-leaf chunk,
+// SM<->L2 bandwidth bound). Instead each group of 256 threads stages its leaf plus the six neighbour faces once,
+// coalesced, in a padded 10x10x10 tile, and the stencil reads shared memory.
+constexpr int TILE = 1000;
+__device__ __forceinline__ int tidx(int x, int y, int z) { return (x + 1) * 100 + (y + 1) * 10 + (z + 1); }
+__device__ __forceinline__ float2 ld_l2_f2(const float* p) {
+    float2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
+// t in [0,256): loads the leaf (two z-adjacent values per thread) and 6 x 64 face values (1.5 per thread)
+__device__ __forceinline__ void tile_load(const float* x, int leaf, const LeafInfo& li, float* T, int t) {
+    {
+        const float2 v = ld_l2_f2(x + (size_t)leaf * LEAF + 2 * t);
+        const int X = t >> 5, Y = (t >> 2) & 7, Z = (t & 3) << 1;
+        T[tidx(X, Y, Z)] = v.x; T[tidx(X, Y, Z + 1)] = v.y;
+    }
+    const int f = t >> 6, q = t & 63, a = q >> 3, b = q & 7;   // face f, cell (a,b) of the face
+    // round 1: faces x-, x+, y-, y+ ; round 2 (threads 0..127): z-, z+
+    {
+        int nb, off, ti;
+        if (f == 0) { nb = li.nb[0]; off = 448 + q; ti = tidx(-1, a, b); }
+        else if (f == 1) { nb = li.nb[1]; off = q; ti = tidx(8, a, b); }
+        else if (f == 2) { nb = li.nb[2]; off = (a << 6) + 56 + b; ti = tidx(a, -1, b); }
+        else { nb = li.nb[3]; off = (a << 6) + b; ti = tidx(a, 8, b); }
+        T[ti] = nb >= 0 ? ld_l2(x + (size_t)nb * LEAF + off) : 0.f;
+    }
+    if (f < 2) {
+        int nb, off, ti;
+        if (f == 0) { nb = li.nb[4]; off = (a << 6) + (b << 3) + 7; ti = tidx(a, b, -1); }
+        else { nb = li.nb[5]; off = (a << 6) + (b << 3); ti = tidx(a, b, 8); }
+        T[ti] = nb >= 0 ? ld_l2(x + (size_t)nb * LEAF + off) : 0.f;
+    }
+}
+// off-diagonal sum from a tile, same association as offdiag()
+template <bool CONST_COEF>
+__device__ __forceinline__ float offdiag_tile(const LevelView& L, const float* T, int leaf, int X, int Y, int Z, const LeafInfo& li) {
+    const int off = (X << 6) | (Y << 3) | Z;
+    const size_t base = (size_t)leaf * LEAF;
+    const float def = -L.term;
+    float cxp, cxm, cyp, cym, czp, czm;
+    if (CONST_COEF) { cxp = cxm = cyp = cym = czp = czm = def; }
+    else {
+        cxp = X < 7 ? __ldg(&L.xe[base + off + 64]) : (li.nb[1] < 0 ? def : __ldg(&L.xe[(size_t)li.nb[1] * LEAF + off - 448]));
+        cxm = __ldg(&L.xe[base + off]);
+        cyp = Y < 7 ? __ldg(&L.ye[base + off + 8]) : (li.nb[3] < 0 ? def : __ldg(&L.ye[(size_t)li.nb[3] * LEAF + off - 56]));
+        cym = __ldg(&L.ye[base + off]);
+        czp = Z < 7 ? __ldg(&L.ze[base + off + 1]) : (li.nb[5] < 0 ? def : __ldg(&L.ze[(size_t)li.nb[5] * LEAF + off - 7]));
+        czm = __ldg(&L.ze[base + off]);
+    }
+    const int c = tidx(X, Y, Z);
+    float fx = __fadd_rn(__fmul_rn(T[c + 100], cxp), __fmul_rn(T[c - 100], cxm));
+    float fy = __fadd_rn(__fmul_rn(T[c + 10], cyp), __fmul_rn(T[c - 10], cym));
+    float fz = __fadd_rn(__fmul_rn(T[c + 1], czp), __fmul_rn(T[c - 1], czm));
+    return __fadd_rn(__fadd_rn(fx, fy), fz);
+}
+
+// ---------------------------------------------------------------- the whole preconditioner in one launch
+// mg_cycle_kernel: a persistent cooperative kernel, one CTA of 1024 threads per SM, that executes the COMPLETE
+// mu-cycle (every level) as a flat op list. Ops on the large levels are spread over all CTAs (leaf chunks
+// strided by the grid) and separated by a device-wide barrier; runs of ops on the bottom levels are executed by
+// CTA 0 alone out of its shared memory (as in mg_bottom_kernel) while the others wait at the next barrier.
+// One launch replaces ~370 kernel launches per preconditioner application at 512^3 -- the host could not
+// issue those faster than ~4.5 us each, which was the solver's real bound.
+constexpr int CYC_MAX_LEVELS = 10;
+struct CycleParams {
+    BottomLevel lv[CYC_MAX_LEVELS];   // xoff/boff >= 0 only on bottom levels (CTA 0's shared memory)
+    CoarseELL ell;
+    const uint8_t* prog;              // op | level << 3
+    int nOps, nLevels, bottomFirst;
+    float w, oneMinusW, prolongAlpha;
+    unsigned* barrier;                // arrival counter, zero at launch
+    unsigned long long* trace;        // optional: %globaltimer at the start of every op (CTA 0), nOps + 1 entries
+};
+__device__ __forceinline__ unsigned long long globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Device-wide barrier for the co-resident grid: one arrival counter, release by fence + atomic, acquire by polling.
+// Measured on B200 with 148 CTAs x 1024 threads (tools/micro/barrier_bench.cu), us per barrier, no work / with work:
+//   this (atomic counter, acquire poll)          1.41 / 2.03      cooperative_groups grid.sync   1.26 / 2.02
+//   one flag per CTA, every CTA polls all flags   3.54 / 3.83      master gather + private release 3.28 / 3.64
+// (the flag variants win only below ~32 CTAs: 0.97 us). The barrier, not bandwidth, bounds every op on the small
+// levels of the cycle.
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& passed) {
+    __syncthreads();
+    passed++;
+    if (threadIdx.x == 0) {
+        const unsigned target = passed * gridDim.x;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        while (ld_acquire(ctr) < target) { }
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(BOT_THREADS) mg_cycle_kernel(const __grid_constant__ CycleParams P) {
+    extern __shared__ float dynsm[];
+    __shared__ float sm33[33];
+    __shared__ float sres[2 * LEAF];
+    __shared__ float tiles[4 * TILE];
+    __shared__ float sresGrid[4 * LEAF];
+    const int tid = threadIdx.x, G = gridDim.x, c = blockIdx.x;
+    unsigned passed = 0;
+    int k = 0;
+    if (c == 0 && P.ell.inSmem) coarse_matrix_to_smem(P.ell, dynsm);
+    while (k < P.nOps) {
+        const int code = P.prog[k] & 7, li = P.prog[k] >> 3;
+        if (P.trace && c == 0 && tid == 0) P.trace[k] = globaltimer();
+        if (li < P.bottomFirst) {
+            const BottomLevel& B = P.lv[li];
+            if (code == OP_ZERO_RED) {
+                for (int base = c * 2; base < B.n; base += G * 2) { int leaf = base + (tid >> 9); if (leaf < B.n) zero_red_leaf<M_GRID>(B.v, B.x, B.b, leaf, tid & 511, P.w); }
+            } else if (code == OP_RED || code == OP_BLACK) {
+                // no block barrier inside a pass: warps run ahead into the next chunk, which is what keeps loads in
+                // flight (a shared-memory tile version with two bar.sync per chunk measured 25 us vs 15 us at level 0)
+                for (int base = c * 4; base < B.n; base += G * 4) { int leaf = base + (tid >> 8); if (leaf < B.n) rbgs_leaf<M_GRID>(B.v, B.x, B.b, leaf, tid & 255, code == OP_RED ? 0 : 1, P.w, P.oneMinusW); }
+            } else if (code == OP_RESID_RESTRICT) {
+                // 256 threads per leaf, two z-adjacent voxels each; residual into shared memory, then restrict
+                const BottomLevel& C = P.lv[li + 1];
+                const int g = tid >> 8, t = tid & 255;
+                float* T = tiles + g * TILE;
+                float* R = sresGrid + g * LEAF;
+                for (int base = c * 4; base < B.n; base += G * 4) {
+                    const int leaf = base + g;
+                    LeafInfo info;
+                    bool live = false;
+                    float2 bv = make_float2(0.f, 0.f);
+                    if (leaf < B.n) {
+                        info = load_info(B.v, leaf);
+                        live = (info.flags & LI_ANY) != 0;
+                        if (live) {
+                            tile_load(B.x, leaf, info, T, t);
+                            bv = B.bReadOnly ? __ldg(reinterpret_cast<const float2*>(B.b + (size_t)leaf * LEAF + 2 * t)) : ld_l2_f2(B.b + (size_t)leaf * LEAF + 2 * t);
+                        }
+                    }
+                    __syncthreads();
+                    if (live) {
+                        const int X = t >> 5, Y = (t >> 2) & 7;
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int Z = ((t & 3) << 1) | h;
+                            const int off = (X << 6) | (Y << 3) | Z;
+                            float r = 0.f;
+                            if (dof_bit(B.v, leaf, off)) {
+                                const float od = (info.flags & LI_CONST) ? offdiag_tile<true>(B.v, T, leaf, X, Y, Z, info) : offdiag_tile<false>(B.v, T, leaf, X, Y, Z, info);
+                                const float dg = (info.flags & LI_DIAG) ? __fmul_rn(6.0f, B.v.term) : __ldg(&B.v.diag[(size_t)leaf * LEAF + off]);
+                                r = __fsub_rn(h == 0 ? bv.x : bv.y, __fmaf_rn(T[tidx(X, Y, Z)], dg, od));
+                            }
+                            R[off] = r;
+                        }
+                    }
+                    __syncthreads();
+                    if (live && t < 64) restrict_leaf(B.v, C.v, R, leaf, t, C.b);
+                    __syncthreads();
+                }
+            } else if (code == OP_PROLONG) {
+                const BottomLevel& C = P.lv[li + 1];
+                for (int base = c * 2; base < B.n; base += G * 2) { int leaf = base + (tid >> 9); if (leaf < B.n) prolong_voxel<M_GRID>(B.v, C.v, B.x, C.x, leaf, tid & 511, P.prolongAlpha); }
+            }
+            k++;
+            grid_barrier(P.barrier, passed);
+            continue;
+        }
+        // a run of bottom ops [k, kEnd): CTA 0 alone, shared-memory resident
+        int kEnd = k;
+        while (kEnd < P.nOps && (P.prog[kEnd] >> 3) >= P.bottomFirst) kEnd++;
+        if (c == 0) {
+            const BottomLevel& T = P.lv[P.bottomFirst];
+            float* tx = dynsm + T.xoff;
+            float* tb = dynsm + T.boff;
+            const int first = P.prog[k] & 7;
+            const bool needX = first != OP_ZERO_RED && first != OP_COARSE;
+            for (int i = tid; i < T.n * LEAF; i += BOT_THREADS) { tb[i] = ld_l2(&T.b[i]); if (needX) tx[i] = ld_l2(&T.x[i]); }
+            __syncthreads();
+            for (int q = k; q < kEnd; q++) {
+                const int cd = P.prog[q] & 7, l2 = P.prog[q] >> 3;
+                if (P.trace && tid == 0) P.trace[q] = globaltimer();
+                const BottomLevel& B = P.lv[l2];
+                float* x = dynsm + B.xoff;
+                const float* b = dynsm + B.boff;
+                if (cd == OP_ZERO_RED) {
+                    for (int base = 0; base < B.n; base += 2) { int leaf = base + (tid >> 9); if (leaf < B.n) zero_red_leaf<M_LOCAL>(B.v, x, b, leaf, tid & 511, P.w); }
+                } else if (cd == OP_RED || cd == OP_BLACK) {
+                    for (int base = 0; base < B.n; base += 4) { int leaf = base + (tid >> 8); if (leaf < B.n) rbgs_leaf<M_LOCAL>(B.v, x, b, leaf, tid & 255, cd == OP_RED ? 0 : 1, P.w, P.oneMinusW); }
+                } else if (cd == OP_RESID_RESTRICT) {
+                    const BottomLevel& C = P.lv[l2 + 1];
+                    float* cb = dynsm + C.boff;
+                    for (int base = 0; base < B.n; base += 2) {
+                        int leaf = base + (tid >> 9), off = tid & 511;
+                        bool live = false;
+                        if (leaf < B.n) {
+                            const LeafInfo info = load_info(B.v, leaf);
+                            live = (info.flags & LI_ANY) != 0;
+                            float r = 0.f;
+                            if (live && dof_bit(B.v, leaf, off)) r = __fsub_rn(b[(size_t)leaf * LEAF + off], ax_voxel<M_LOCAL>(B.v, info, x, leaf, off));
+                            sres[tid] = r;
+                        }
+                        __syncthreads();
+                        if (live && off < 64) restrict_leaf(B.v, C.v, sres + (tid >> 9) * LEAF, leaf, off, cb);
+                        __syncthreads();
+                    }
+                } else if (cd == OP_PROLONG) {
+                    const BottomLevel& C = P.lv[l2 + 1];
+                    const float* cx = dynsm + C.xoff;
+                    for (int base = 0; base < B.n; base += 2) { int leaf = base + (tid >> 9); if (leaf < B.n) prolong_voxel<M_LOCAL>(B.v, C.v, x, cx, leaf, tid & 511, P.prolongAlpha); }
+                } else {
+                    if (P.ell.inSmem) coarse_cg_smem(P.ell, b, x, dynsm, sm33);
+                    else coarse_cg(P.ell, b, x, dynsm, sm33);
+                }
+                __syncthreads();
+            }
+            for (int i = tid; i < T.n * LEAF; i += BOT_THREADS) T.x[i] = tx[i];
+        }
+        k = kEnd;
+        if (k < P.nOps) grid_barrier(P.barrier, passed);
+    }
+    if (P.trace && c == 0 && tid == 0) P.trace[P.nOps] = globaltimer();
 }
 __global__ void leaf_popcount_kernel(const uint64_t* __restrict__ dof, int n, uint32_t* __restrict__ out) {
     int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -729,7 +1065,7 @@ __global__ void warm_start_kernel(TopoView t, const uint64_t* __restrict__ dof, 
 // L1 + shared memory (256 KB) or every pass turns into a serial chain of L2 round trips (measured: a 64-leaf
 // level inside the bottom cost 183 us per visit). 12 leaves = 168 KB.
 constexpr int BOTTOM_MAX_TOTAL_LEAVES = 12;
-constexpr size_t BOTTOM_SMEM_CAP = 96 * 1024;   // dynamic shared memory of mg_bottom_kernel (x, lower b, coarsest CG)
+constexpr size_t BOTTOM_SMEM_CAP = 190 * 1024;   // dynamic shared memory of mg_bottom_kernel (x, lower b, coarsest CG)
 
 struct Solver {
     World* w;
@@ -741,6 +1077,13 @@ struct Solver {
     DBuf<float> ellVals;
     DBuf<float> partial, scal;  // [max leaves], [8]
     DBuf<unsigned> counter;
+    // mg_cycle_kernel (the whole preconditioner in one cooperative launch)
+    bool cycleReady = false, cycleMatrixInSmem = false;
+    DBuf<uint8_t> cycleProg;
+    int cycleOps = 0, cycleGrid = 1;
+    static constexpr int cycleGridMax = 192;
+    size_t cycleSmem = 0;
+    DBuf<unsigned> cycleBarrier;
     int bottomFirst = 0;        // first level handled by mg_bottom_kernel
     bool bottomInSmem = false;  // x (and the lower levels' b) of the bottom live in shared memory
     size_t bottomSmem = 0;
@@ -751,7 +1094,7 @@ struct Solver {
     }
     size_t bottom_need(int first) const {
         size_t need = (size_t)5 * ndofPad * sizeof(float);
-        for (int l = first; l < (int)levels.size(); l++) need += (size_t)levels[l]->n * LEAF * sizeof(float) * (l == first ? 1 : 2);
+        for (int l = first; l < (int)levels.size(); l++) need += (size_t)levels[l]->n * LEAF * sizeof(float) * 2;
         return need;
     }
 
@@ -854,6 +1197,96 @@ struct Solver {
             for (int i = 0; i < postSmooth && isTop; i++) { put(OP_BLACK); put(OP_RED); }
         }
     }
+    // op list of muCyclePreconditioner<2, true>(level 0, n) over ALL levels (level index = absolute level)
+    void emit_cycle(std::vector<uint8_t>& ops, int level, int n, bool skipFirst) {
+        const int nl = (int)levels.size();
+        auto put = [&](int code) { ops.push_back((uint8_t)(code | (level << 3))); };
+        if (level == nl - 1) { put(OP_COARSE); return; }
+        if (skipFirst) { put(OP_ZERO_RED); put(OP_BLACK); }
+        for (int i = (skipFirst ? 1 : 0); i < n; i++) { put(OP_RED); put(OP_BLACK); }
+        put(OP_RESID_RESTRICT);
+        emit_cycle(ops, level + 1, n, true);
+        emit_cycle(ops, level + 1, n, false);
+        put(OP_PROLONG);
+        for (int i = 0; i < n; i++) { put(OP_BLACK); put(OP_RED); }
+    }
+    void prepare_cycle(int n) {
+        const int nl = (int)levels.size();
+        cycleReady = false;
+        if (!bottomInSmem || nl > CYC_MAX_LEVELS || nl > 31) return;
+        std::vector<uint8_t> ops;
+        emit_cycle(ops, 0, n, true);
+        cycleOps = (int)ops.size();
+        cycleProg.alloc(ops.size(), w->stream);
+        FB_CUDA(cudaMemcpyAsync(cycleProg.p, ops.data(), ops.size(), cudaMemcpyHostToDevice, w->stream));
+        sync(w);  // ops is a host temporary
+        cycleBarrier.alloc(1, w->stream);
+        // shared memory of CTA 0: coarsest CG + x and b of every bottom level
+        size_t bottomBytes = 0;
+        for (int l = bottomFirst; l < nl; l++) bottomBytes += (size_t)levels[l]->n * LEAF * sizeof(float) * 2;
+        // 227 KB per CTA minus the kernel's static shared memory (tiles, residual staging: ~29 KB)
+        const size_t cap = 196 * 1024;
+        cycleMatrixInSmem = ndofPad < 65535 && (size_t)11 * ndofPad * sizeof(float) + bottomBytes <= cap;
+        cycleSmem = (size_t)(cycleMatrixInSmem ? 11 : 5) * ndofPad * sizeof(float) + bottomBytes;
+        cycleSmem = std::max<size_t>(cycleSmem, 1024);
+        if (cycleSmem > cap) return;
+        FB_CUDA(cudaFuncSetAttribute(mg_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cycleSmem));
+        int dev = 0, sms = 0, perSm = 0, coop = 0;
+        FB_CUDA(cudaGetDevice(&dev));
+        FB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        FB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, mg_cycle_kernel, BOT_THREADS, cycleSmem));
+        if (!coop || perSm < 1) return;
+        cycleGrid = bottomFirst == 0 ? 1 : std::min(sms, (int)cycleGridMax);
+        cycleReady = true;
+    }
+    void launch_cycle(float* x, const float* b) {
+        const int nl = (int)levels.size();
+        CycleParams P;
+        int cursor = (cycleMatrixInSmem ? 11 : 5) * ndofPad;
+        for (int i = 0; i < nl; i++) {
+            Level& L = *levels[i];
+            P.lv[i].v = view_of(L);
+            P.lv[i].x = i == 0 ? x : L.x.p;
+            P.lv[i].b = i == 0 ? const_cast<float*>(b) : L.b.p;
+            P.lv[i].n = L.n;
+            P.lv[i].xoff = P.lv[i].boff = -1;
+            P.lv[i].bReadOnly = i == 0 ? 1 : 0;  // level 0 iterates on the caller's residual, never written in the launch
+            if (i >= bottomFirst) {
+                P.lv[i].xoff = cursor; cursor += L.n * LEAF;
+                P.lv[i].boff = cursor; cursor += L.n * LEAF;
+            }
+        }
+        Level& C = *levels.back();
+        P.ell = CoarseELL{ndof, ndofPad, C.n * LEAF, cycleMatrixInSmem ? 1 : 0, ellCols.p, ellVals.p, rowOfVoxel.p};
+        P.prog = cycleProg.p; P.nOps = cycleOps; P.nLevels = nl; P.bottomFirst = bottomFirst;
+        P.w = 1.2f; P.oneMinusW = 1.0f - 1.2f; P.prolongAlpha = 1.0f;
+        P.barrier = cycleBarrier.p;
+        // FLIPB200_TRACE_CYCLE=<file>: per-op device timestamps of the next application, written as CSV (debug aid)
+        static const char* tracePath = getenv("FLIPB200_TRACE_CYCLE");
+        DBuf<unsigned long long> trace;
+        P.trace = nullptr;
+        if (tracePath) { trace.alloc(cycleOps + 1, w->stream); trace.zero(); P.trace = trace.p; }
+        FB_CUDA(cudaMemsetAsync(cycleBarrier.p, 0, sizeof(unsigned), w->stream));
+        uint64_t bytes = 0;  // 121 B/DOF per level visit, level l is visited 2^l times
+        for (int i = 0; i < nl; i++) bytes += ((uint64_t)levels[i]->numDof * 121) << i;
+        void* args[] = {(void*)&P};
+        FB_LAUNCH(w, "mg_cycle", bytes)
+            FB_CUDA(cudaLaunchCooperativeKernel((const void*)mg_cycle_kernel, dim3(cycleGrid), dim3(BOT_THREADS), args, cycleSmem, w->stream));
+        check_launch("mg_cycle");
+        if (tracePath) {
+            std::vector<unsigned long long> t(cycleOps + 1);
+            std::vector<uint8_t> ops(cycleOps);
+            FB_CUDA(cudaMemcpyAsync(t.data(), trace.p, t.size() * 8, cudaMemcpyDeviceToHost, w->stream));
+            FB_CUDA(cudaMemcpyAsync(ops.data(), cycleProg.p, ops.size(), cudaMemcpyDeviceToHost, w->stream));
+            sync(w);
+            if (FILE* f = fopen(tracePath, "w")) {
+                fprintf(f, "k,op,level,leaves,ns\n");
+                for (int k = 0; k < cycleOps; k++) fprintf(f, "%d,%d,%d,%d,%llu\n", k, ops[k] & 7, ops[k] >> 3, levels[ops[k] >> 3]->n, t[k + 1] - t[k]);
+                fclose(f);
+            }
+        }
+    }
     void launch_bottom(float* x, const float* b, int n, bool skipFirst, bool precond, int postSmooth) {
         const int nl = (int)levels.size();
         const int nBottom = nl - bottomFirst;
@@ -878,7 +1311,7 @@ struct Solver {
         P.nLevels = nBottom;
         P.loadX = (ops.empty() || (ops[0] & 7) != OP_ZERO_RED) && (ops.empty() || (ops[0] & 7) != OP_COARSE) ? 1 : 0;
         Level& C = *levels.back();
-        P.ell = CoarseELL{ndof, ndofPad, C.n * LEAF, ellCols.p, ellVals.p, rowOfVoxel.p};
+        P.ell = CoarseELL{ndof, ndofPad, C.n * LEAF, 0, ellCols.p, ellVals.p, rowOfVoxel.p};
         P.w = precond ? 1.2f : 1.0f;
         P.oneMinusW = 1.0f - P.w;
         P.prolongAlpha = precond ? 1.0f : 0.5f;
@@ -912,6 +1345,7 @@ struct Solver {
     }
     // muCyclePreconditioner<2, skip_first> with the RBGS smoother (uaamg.cpp:1993-2126)
     void mu_cycle_precond(float* x, const float* b, int level, int n, bool skipFirst) {
+        if (level == 0 && skipFirst && n == 4 && cycleReady) { launch_cycle(x, b); return; }
         if (level >= bottomFirst) { launch_bottom(x, b, n, skipFirst, true, 0); return; }
         Level& L = *levels[level];
         const float wS = 1.2f;
@@ -993,6 +1427,7 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
     }
     while (S.levels.back()->numDof > MAX_COARSEST) S.coarsen();
     S.build_coarsest();
+    if (!getenv("FLIPB200_NO_CYCLE_KERNEL")) S.prepare_cycle(4);
     Level& L0 = *S.levels[0];
     st.levels = (int)S.levels.size();
     st.numDof = L0.numDof;
