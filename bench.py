@@ -125,12 +125,24 @@ def measured_peak():
 
 
 def cpu_reference_arm(N: int, steps: int, warmup: int):
-    """The reference's CPU algorithm (oracle port; OpenMP over leaves) on a bounded sample."""
+    """The reference's own CPU implementation of the path on the host cores, on a bounded sample of the workload:
+    oracle/_ref (FLIP_vdb.cpp + simd_vdb_poisson_uaamg.cpp + OpenVDB + TBB, all hardware threads) when it was
+    built (kind "reference"), else the oracle port (kind "port", OpenMP over leaves)."""
     from oracle import pyoracle
     from zeno_b200 import scenes
-    pyoracle.build()
+    cores = os.cpu_count() or 1
+    if pyoracle.ref_available():
+        try:
+            cores = pyoracle.ref_set_threads(0)
+            cls, kind = pyoracle.RefWorld, "reference"
+        except OSError:
+            pyoracle.build()
+            cls, kind = pyoracle.OracleWorld, "port"
+    else:
+        pyoracle.build()
+        cls, kind = pyoracle.OracleWorld, "port"
     pos, vel, dx = scenes.dam_break_points(N, seed=1)
-    w = pyoracle.OracleWorld(dx)
+    w = cls(dx)
     w.set_grid("SolidSDF", scenes.box_solid_sdf(N, dx))
     w.PrimToVDBPointDataGrid(pos, vel)
     w.FLIP_P2G(dx, 3)
@@ -143,9 +155,10 @@ def cpu_reference_arm(N: int, steps: int, warmup: int):
         w.substep(substep_dt(w, dx), dx, 4, 3, 0.03, 0.05, GRAVITY, 3, True)
         done += w.particles_info()[1]
     dtm = time.perf_counter() - t0
-    cores = os.cpu_count() or 1
-    return {"value": done / dtm, "seconds": dtm, "steps": steps, "cores": cores, "particles": n_particles,
-            "sample": f"dam-break {N}^3 tank, {n_particles} particles, 8 ppc, {steps} substeps (same chain, smaller tank)"}
+    what = ("the reference's own sources (oracle/_ref: FLIP_vdb.cpp, simd_vdb_poisson_uaamg.cpp, OpenVDB 9.0.1, TBB)"
+            if kind == "reference" else "CPU port of the reference algorithm (oracle/*.cpp)")
+    return {"value": done / dtm, "seconds": dtm, "steps": steps, "cores": cores, "particles": n_particles, "kind": kind,
+            "sample": f"dam-break {N}^3 tank, {n_particles} particles, 8 ppc, {steps} substeps of the same node chain, {what}"}
 
 
 def main():
@@ -156,7 +169,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=512, help="tank resolution N (BASELINE config[1]: 512)")
     ap.add_argument("--ppc", type=int, default=8)
-    ap.add_argument("--cpu-grid", type=int, default=128, help="tank resolution of the bounded CPU sample")
+    ap.add_argument("--cpu-grid", type=int, default=256, help="tank resolution of the bounded CPU sample (256 = BASELINE config[0], 2.1 M particles)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -174,8 +187,8 @@ def main():
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"FastFLIP dam-break substep chain, CPU port of the reference algorithm; {r['sample']}"},
-                "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+                "config": {"workload": f"FastFLIP dam-break substep chain on the host CPU; {r['sample']}"},
+                "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -264,8 +277,17 @@ def main():
     roofline = None
     if dominant:
         d = kern[dominant]
+        traffic = None
+        try:  # measured DRAM bytes per launch of this kernel from the committed ncu --set full capture (same workload)
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                t = json.load(f).get(dominant)
+            if t and N == 512 and args.ppc == 8:
+                traffic = t["bytes"]
+        except Exception:
+            traffic = None
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": d["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
-                    "frac": d["frac"], "traffic": None, "peak_source": peak_src, "avg_launch_us": d["avg_us"],
+                    "frac": d["frac"], "traffic": traffic, "algorithmic_bytes_per_launch": prof[dominant]["bytes"] / max(prof[dominant]["launches"], 1),
+                    "peak_source": peak_src, "avg_launch_us": d["avg_us"],
                     "share_of_step": d["ms_per_step"] / max(sum(x["ms_per_step"] for x in kern.values()), 1e-9),
                     "measured": f"CUDA events around every launch of the family over {PROF_STEPS} substeps following the timed region"}
     top = sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])[:12]
@@ -273,14 +295,12 @@ def main():
     # ---- e2e: the same step with the world state crossing PCIe both ways every step
     e2e = None
     if not args.no_e2e:
-        state = {g: w.get_grid(g) for g in STATE_GRIDS}
-        pts = w.get_particles()
-
-        def pin(a):
-            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-            return t.numpy()
-        state = {g: {k: pin(v) for k, v in d.items()} for g, d in state.items()}
-        pts = {k: pin(v) for k, v in pts.items()}
+        arena = abi.PinnedArena()
+        state = {g: {k: (arena.like(v) if k != "bg" else v) for k, v in w.get_grid(g).items()} for g in STATE_GRIDS}
+        pts = {k: arena.like(v) for k, v in w.get_particles().items()}
+        # pinned result buffers with head-room (the fluid spreads: leaf counts grow a little every step)
+        out_state = {g: {k: (arena.like(v, 1.5) if k != "bg" else v) for k, v in state[g].items()} for g in STATE_GRIDS}
+        out_pts = {k: arena.like(v, 1.5 if k in ("origins", "voxel_end") else 1.0) for k, v in pts.items()}
         h2d = sum(v.nbytes for d in state.values() for v in d.values()) + sum(v.nbytes for v in pts.values())
         E_STEPS = max(1, min(args.steps, 5))
         barrier()
@@ -292,8 +312,8 @@ def main():
                 w.set_grid(g, state[g])
             w.set_particles(pts)
             step()
-            out_p = w.get_particles()
-            out_g = {g: w.get_grid(g) for g in STATE_GRIDS}
+            out_p = w.get_particles(out=out_pts)
+            out_g = {g: w.get_grid(g, out=out_state[g]) for g in STATE_GRIDS}
             d2h = sum(v.nbytes for v in out_p.values()) + sum(v.nbytes for d in out_g.values() for v in d.values())
             psteps += out_p["P"].shape[0]
         barrier()
@@ -311,8 +331,8 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_reference_arm(args.cpu_grid, 3, 1)
-        cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        r = cpu_reference_arm(args.cpu_grid, 5, 1)
+        cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
     if rank == 0:
         n_particles = w.particles_info()[1]

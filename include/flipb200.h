@@ -88,6 +88,11 @@ int flipb200_particles_info(flipb200_world* w, int* nLeaves, uint64_t* nParticle
 int flipb200_particles_download(flipb200_world* w, int32_t* origins, uint32_t* voxelEnd, uint16_t* P,
                                 uint16_t* v);
 
+/* Page-locked host staging buffers for the marshalling calls above (what the node shims use to hand VDB leaf
+ * buffers to the device at PCIe speed; pageable memory works too, at a third of the bandwidth). */
+int flipb200_host_alloc(size_t bytes, void** out);
+int flipb200_host_free(void* p);
+
 /* K1: PrimToVDBPointDataGrid / particleArrayToGrid (projects/zenvdb/SetVDBPointDataGrid.cpp:17-72):
  * world positions + velocities -> voxel-sorted quantised particle store. vel may be NULL (zeros). */
 int flipb200_bin_from_points(flipb200_world* w, const float* pos, const float* vel, uint64_t n);

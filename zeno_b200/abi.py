@@ -29,7 +29,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libflipb20
 # every symbol include/flipb200.h declares (the CPU-side loader test checks this list against the header)
 EXPORTS = [
     "flipb200_last_error", "flipb200_build_info", "flipb200_abi_version", "flipb200_device_count",
-    "flipb200_world_create", "flipb200_world_destroy", "flipb200_grid_upload", "flipb200_grid_leaf_count",
+    "flipb200_world_create", "flipb200_world_destroy", "flipb200_host_alloc", "flipb200_host_free", "flipb200_grid_upload", "flipb200_grid_leaf_count",
     "flipb200_grid_download", "flipb200_particles_upload", "flipb200_particles_info",
     "flipb200_particles_download", "flipb200_bin_from_points", "flipb200_p2g",
     "flipb200_g2p_advect_sheetty", "flipb200_dropped", "flipb200_capture_precodec", "flipb200_get_precodec",
@@ -76,6 +76,44 @@ def _c(a, dtype) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=dtype)
 
 
+class PinnedArena:
+    """Page-locked host arrays (flipb200_host_alloc) for staging grids / particles across PCIe."""
+
+    def __init__(self, lib: Optional[C.CDLL] = None):
+        self.lib = lib or load_library()
+        self._ptrs = []
+
+    def empty(self, shape, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ptr = C.c_void_p()
+        rc = self.lib.flipb200_host_alloc(C.c_size_t(max(n, 1)), C.byref(ptr))
+        if rc != 0:
+            raise FlipB200Error(rc, (self.lib.flipb200_last_error() or b"").decode())
+        self._ptrs.append(ptr)
+        buf = (C.c_byte * max(n, 1)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def like(self, a: np.ndarray, slack: float = 1.0) -> np.ndarray:
+        """pinned copy of a; slack > 1 reserves extra leading-dimension capacity"""
+        shape = list(a.shape)
+        cap = int(np.ceil(shape[0] * slack)) if shape else 0
+        out = self.empty([cap] + shape[1:], a.dtype)
+        out[:shape[0]] = a
+        return out
+
+    def close(self):
+        for p in self._ptrs:
+            self.lib.flipb200_host_free(p)
+        self._ptrs = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class World:
     """One FLIP world on one GPU (SetFLIPWorld, FF/nosys/FLIP_Creator.cpp)."""
 
@@ -111,15 +149,19 @@ class World:
         n = o.shape[0]
         self._ck(self.lib.flipb200_grid_upload(self.h, C.c_int(gid), C.c_int(n), _p(o), _p(m), _p(v), C.c_int(layout), _p(bg)))
 
-    def get_grid(self, name: str, layout: int = SOA) -> Dict[str, np.ndarray]:
+    def get_grid(self, name: str, layout: int = SOA, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+        """out: optional pre-allocated (e.g. pinned) arrays with leading capacity >= the leaf count; views are returned"""
         gid = GRID_IDS[name]
         nch = 3 if name in VEC_GRIDS else 1
         n = C.c_int(0)
         self._ck(self.lib.flipb200_grid_leaf_count(self.h, C.c_int(gid), C.byref(n)))
         n = n.value
-        o = np.zeros((n, 3), np.int32)
-        m = np.zeros((n, 8), np.uint64)
-        v = np.zeros((n, nch, 512) if layout == SOA else (n, 512, nch), np.float32)
+        if out is not None and out["origins"].shape[0] >= n:
+            o, m, v = out["origins"][:n], out["masks"][:n], out["values"][:n]
+        else:
+            o = np.zeros((n, 3), np.int32)
+            m = np.zeros((n, 8), np.uint64)
+            v = np.zeros((n, nch, 512) if layout == SOA else (n, 512, nch), np.float32)
         bg = np.zeros(nch, np.float32)
         self._ck(self.lib.flipb200_grid_download(self.h, C.c_int(gid), _p(o), _p(m), _p(v), C.c_int(layout), _p(bg)))
         return {"origins": o, "masks": m, "values": v, "bg": bg}
@@ -136,12 +178,15 @@ class World:
         self._ck(self.lib.flipb200_particles_info(self.h, C.byref(nl), C.byref(n)))
         return nl.value, n.value
 
-    def get_particles(self) -> Dict[str, np.ndarray]:
+    def get_particles(self, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
         nl, n = self.particles_info()
-        o = np.zeros((nl, 3), np.int32)
-        ve = np.zeros((nl, 512), np.uint32)
-        P = np.zeros((n, 3), np.uint16)
-        v = np.zeros((n, 3), np.uint16)
+        if out is not None and out["origins"].shape[0] >= nl and out["P"].shape[0] >= n:
+            o, ve, P, v = out["origins"][:nl], out["voxel_end"][:nl], out["P"][:n], out["v"][:n]
+        else:
+            o = np.zeros((nl, 3), np.int32)
+            ve = np.zeros((nl, 512), np.uint32)
+            P = np.zeros((n, 3), np.uint16)
+            v = np.zeros((n, 3), np.uint16)
         self._ck(self.lib.flipb200_particles_download(self.h, _p(o), _p(ve), _p(P), _p(v)))
         return {"origins": o, "voxel_end": ve, "P": P, "v": v}
 

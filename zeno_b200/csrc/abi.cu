@@ -201,6 +201,17 @@ int flipb200_world_destroy(flipb200_world* w) {
     });
 }
 
+int flipb200_host_alloc(size_t bytes, void** out) {
+    return guarded([&] {
+        FB_REQUIRE(out != nullptr, FLIPB200_ERR_ARG, "host_alloc: null out");
+        *out = nullptr;
+        if (bytes) FB_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    });
+}
+int flipb200_host_free(void* p) {
+    return guarded([&] { if (p) FB_CUDA(cudaFreeHost(p)); });
+}
+
 int flipb200_grid_upload(flipb200_world* w, int grid, int nLeaves, const int32_t* origins, const uint64_t* masks,
                          const float* values, int layout, const float* background) {
     return guarded([&] {
