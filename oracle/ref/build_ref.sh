@@ -75,3 +75,12 @@ xargs -P "$JOBS" -d '\n' -I{} bash -c {} < "$BUILD/cmds.txt" || { echo "FastFLIP
 cp "$BUILD/libtbb.so.2" "$OUT/libtbb.so.2"
 $CXX -shared -o "$OUT/libflipref.so" "$BUILD"/ffobj/*.o "$BUILD"/vdbobj/*.o -L"$BUILD" -ltbb -lpthread -Wl,-rpath,'$ORIGIN' -Wl,-z,defs 2> "$BUILD/link.log" || { head -40 "$BUILD/link.log"; exit 1; }
 echo "built $OUT/libflipref.so"
+
+# ---- 6. compile check of the Zeno-side drop-in (zeno_b200/plugin/flipb200_nodes.cpp) against the reference's own
+#         headers (zeno core, zenvdb VDBGrid.h, OpenVDB): it is built into the zeno target, so here only -fsyntax-only
+PLUGIN="$HERE/../../zeno_b200/plugin/flipb200_nodes.cpp"
+if [ -f "$PLUGIN" ]; then
+  $CXX -std=c++17 -O1 -fPIC -w -fsyntax-only -fopenmp -include cstring -include $HERE/shims/boost_compat.h -I$HERE/shims -I$BUILD/gen -I$BUILD/gen/openvdb \
+      -I$VDB -I$VDB/openvdb -I$TBBINC -I$REF/projects/zenvdb/include -I$REF/zeno/include -I$HERE/../../include "$PLUGIN" \
+      && echo "plugin compile check ok" > "$OUT/plugin_check.txt" || { echo "plugin compile check FAILED"; exit 1; }
+fi
