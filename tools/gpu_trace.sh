@@ -8,9 +8,9 @@ rows=list(csv.DictReader(open("gpurun_out/cycle_trace.csv")))
 names={0:"zero_red",1:"red",2:"black",3:"resid_restrict",4:"prolong",5:"coarse_cg"}
 agg=collections.OrderedDict()
 for r in rows:
-    key=(int(r["level"]), names[int(r["op"])], int(r["leaves"]))
+    key=(int(r["level"]), names[int(r["op"])], int(r["leaves"]), int(r.get("dofs",0)), int(r.get("compact",0)))
     a=agg.setdefault(key,[0,0]); a[0]+=1; a[1]+=int(r["ns"])
 tot=sum(int(r["ns"]) for r in rows)
 print("total us", tot/1e3, "ops", len(rows))
-for (lv,op,n),(c,ns) in sorted(agg.items()): print(f"level {lv} ({n} leaves) {op:15s} x{c:4d}  avg {ns/c/1e3:8.2f} us  total {ns/1e3:9.1f} us")
+for (lv,op,n,nd,cp),(c,ns) in sorted(agg.items()): print(f"level {lv} ({n} leaves, {nd} dofs, compact={cp}) {op:15s} x{c:4d}  avg {ns/c/1e3:8.2f} us  total {ns/1e3:9.1f} us")
 PY

@@ -11,6 +11,8 @@
 // traffic). The stencil arithmetic keeps the reference's association and its explicit FMAs.
 #include "world.cuh"
 #include "levelset.cuh"
+#include <algorithm>
+#include <cstring>
 
 namespace fb {
 namespace {
@@ -666,88 +668,6 @@ __device__ void coarse_cg(const CoarseELL& E, const float* rhsGrid, float* lhsGr
     __syncthreads();
 }
 
-// The same CG with the coarsest matrix resident in shared memory in a compact symmetric form: per row the
-// diagonal, the three "minus" face coefficients and six 16-bit neighbour rows (28 B/row instead of 56 B/row of ELL
-// in L2); the coefficient towards a "plus" neighbour is that neighbour's "minus" coefficient. Same summation
-// order as coarse_cg (diag, x-, x+, y-, y+, z-, z+). sm: X,R,P,T [4N] then diag [N], minus [3N], cols [6N u16].
-__device__ void coarse_matrix_to_smem(const CoarseELL& E, float* sm) {
-    const int N = E.ndofPad;
-    float* diag = sm + 4 * N;
-    float* minus = diag + N;
-    unsigned short* cols = reinterpret_cast<unsigned short*>(minus + 3 * N);
-    for (int r = threadIdx.x; r < E.ndof; r += BOT_THREADS) {
-        diag[r] = E.vals[r];
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            minus[ch * N + r] = E.vals[(1 + 2 * ch) * N + r];
-            int cm = E.cols[(1 + 2 * ch) * N + r], cp = E.cols[(2 + 2 * ch) * N + r];
-            cols[(2 * ch) * N + r] = cm >= 0 ? (unsigned short)cm : (unsigned short)0xffff;
-            cols[(2 * ch + 1) * N + r] = cp >= 0 ? (unsigned short)cp : (unsigned short)0xffff;
-        }
-    }
-    __syncthreads();
-}
-__device__ void coarse_cg_smem(const CoarseELL& E, const float* rhsGrid, float* lhsGrid, float* sm, float* sm33) {
-    const int ndof = E.ndof, N = E.ndofPad;
-    float* X = sm; float* R = X + N; float* P = R + N; float* T = P + N;
-    const float* diag = sm + 4 * N;
-    const float* minus = diag + N;
-    const unsigned short* cols = reinterpret_cast<const unsigned short*>(minus + 3 * N);
-    const int tid = threadIdx.x;
-    auto dinv = [&](int r) { float d = diag[r]; return d != 0.f ? __fdiv_rn(1.0f, d) : 1.0f; };
-    for (int v = tid; v < E.nVoxels; v += BOT_THREADS) { int r = __ldg(&E.rowOfVoxel[v]); if (r >= 0) R[r] = rhsGrid[v]; }
-    for (int r = tid; r < ndof; r += BOT_THREADS) X[r] = 0.f;
-    __syncthreads();
-    float acc = 0.f;
-    for (int r = tid; r < ndof; r += BOT_THREADS) acc = __fadd_rn(acc, __fmul_rn(R[r], R[r]));
-    float rhsNorm2 = cg_block_sum(acc, sm33);
-    if (rhsNorm2 != 0.f) {
-        const float tol = 1.1920929e-07f;
-        float threshold = fmaxf(__fmul_rn(__fmul_rn(tol, tol), rhsNorm2), 1.17549435e-38f);
-        float residualNorm2 = rhsNorm2;
-        if (!(residualNorm2 < threshold)) {
-            acc = 0.f;
-            for (int r = tid; r < ndof; r += BOT_THREADS) { float pv = __fmul_rn(dinv(r), R[r]); P[r] = pv; acc = __fadd_rn(acc, __fmul_rn(R[r], pv)); }
-            float absNew = cg_block_sum(acc, sm33);
-            for (int it = 0; it < 10; it++) {
-                acc = 0.f;
-                for (int r = tid; r < ndof; r += BOT_THREADS) {
-                    float s = __fadd_rn(0.f, __fmul_rn(diag[r], P[r]));
-#pragma unroll
-                    for (int ch = 0; ch < 3; ch++) {
-                        unsigned cm = cols[(2 * ch) * N + r], cp = cols[(2 * ch + 1) * N + r];
-                        if (cm != 0xffffu) s = __fadd_rn(s, __fmul_rn(minus[ch * N + r], P[cm]));
-                        if (cp != 0xffffu) s = __fadd_rn(s, __fmul_rn(minus[ch * N + cp], P[cp]));
-                    }
-                    T[r] = s;
-                    acc = __fadd_rn(acc, __fmul_rn(P[r], s));
-                }
-                float pt = cg_block_sum(acc, sm33);
-                float alpha = __fdiv_rn(absNew, pt);
-                acc = 0.f;
-                for (int r = tid; r < ndof; r += BOT_THREADS) {
-                    X[r] = __fadd_rn(X[r], __fmul_rn(alpha, P[r]));
-                    float rv = __fsub_rn(R[r], __fmul_rn(alpha, T[r]));
-                    R[r] = rv;
-                    acc = __fadd_rn(acc, __fmul_rn(rv, rv));
-                }
-                residualNorm2 = cg_block_sum(acc, sm33);
-                if (residualNorm2 < threshold) break;
-                acc = 0.f;
-                for (int r = tid; r < ndof; r += BOT_THREADS) { float zv = __fmul_rn(dinv(r), R[r]); T[r] = zv; acc = __fadd_rn(acc, __fmul_rn(R[r], zv)); }
-                float absOld = absNew;
-                absNew = cg_block_sum(acc, sm33);
-                float beta = __fdiv_rn(absNew, absOld);
-                for (int r = tid; r < ndof; r += BOT_THREADS) P[r] = __fadd_rn(T[r], __fmul_rn(beta, P[r]));
-                __syncthreads();
-            }
-        }
-    }
-    __syncthreads();
-    for (int v = tid; v < E.nVoxels; v += BOT_THREADS) { int r = __ldg(&E.rowOfVoxel[v]); if (r >= 0) lhsGrid[v] = X[r]; }
-    __syncthreads();
-}
-
 // ---------------------------------------------------------------- the resident bottom of the mu-cycle
 // The W-like cycle (mu = 2) visits level l 2^l times; below the first few levels every visit is a handful of
 // leaves and the work is pure launch latency. mg_bottom_kernel executes the complete recursion below level
@@ -877,6 +797,225 @@ __device__ __forceinline__ float offdiag_tile(const LevelView& L, const float* T
     return __fadd_rn(__fadd_rn(fx, fy), fz);
 }
 
+// ---------------------------------------------------------------- compact rows for the bottom of the cycle
+// Below the first few levels a leaf holds a few hundred DOFs at most, and the mu = 2 cycle visits those levels
+// 8-16 times per application. They are stored as COMPACT ROWS (one row per DOF, 16-bit neighbour rows, the three
+// "minus" face coefficients; the coefficient towards a "plus" neighbour is that neighbour's "minus" coefficient)
+// that stay in CTA 0's shared memory for the whole launch: a colour pass is one shared-memory sweep + one
+// bar.sync instead of an L2 round trip + a device-wide barrier. Row n (the first padding row) is a zero dummy:
+// x = 0 and every coefficient 0, so a missing / non-DOF neighbour contributes 0 * 0 where the leaf form
+// contributes 0 * c -- the same value in the same place of the reference's association.
+struct BlobLayout { int diag, inv, minus, cols, parent, child, bytes; };
+__host__ __device__ inline BlobLayout blob_layout(int np, bool hasChild) {
+    BlobLayout b;
+    int o = 0;
+    b.diag = o; o += 4 * np;
+    b.inv = o; o += 4 * np;
+    b.minus = o; o += 12 * np;
+    b.cols = o; o += 12 * np;     // u16 [6][np]: x-, x+, y-, y+, z-, z+
+    b.parent = o; o += 2 * np;    // u16 [np]: row in the next coarser compact level
+    b.child = o; if (hasChild) o += 16 * np;  // u16 [8][np]: rows of the 2^3 children in the finer compact level
+    b.bytes = o;
+    return b;
+}
+inline int compact_np(int n) { return (n + 1 + 31) & ~31; }
+// Rows are numbered red first: a red DOF's row = (red DOFs in earlier leaves) + (red DOF bits below it in its
+// leaf), a black DOF's row = nRed + the same over black bits. A colour pass is then a contiguous row range.
+// red = (x+y+z) even; bit (y<<3|z) of mask word x
+__device__ __forceinline__ uint64_t colour_mask(int word, int colour) {
+    const uint64_t red = (word & 1) ? 0x55AA55AA55AA55AAull : 0xAA55AA55AA55AA55ull;
+    return colour == 0 ? red : ~red;
+}
+__global__ void leaf_colour_count_kernel(const uint64_t* __restrict__ dof, int n, uint32_t* __restrict__ red, uint32_t* __restrict__ black) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n) return;
+    uint32_t r = 0, b = 0;
+    for (int k = 0; k < 8; k++) { const uint64_t m = dof[(size_t)l * 8 + k]; r += __popcll(m & colour_mask(k, 0)); b += __popcll(m & colour_mask(k, 1)); }
+    red[l] = r; black[l] = b;
+}
+struct RowMap { const uint64_t* dof; const uint32_t* redStart; const uint32_t* blackStart; int nRed; };
+__device__ __forceinline__ int dof_row(const RowMap& R, int leaf, int off) {   // -1 if not a DOF
+    const uint64_t* m = R.dof + (size_t)leaf * 8;
+    const int X = off >> 6, bit = off & 63;
+    const uint64_t w = m[X];
+    if (!((w >> bit) & 1ull)) return -1;
+    const int colour = (X + (bit >> 3) + (bit & 7)) & 1;
+    int below = __popcll(w & colour_mask(X, colour) & ((1ull << bit) - 1ull));
+    for (int k = 0; k < X; k++) below += __popcll(m[k] & colour_mask(k, colour));
+    return colour == 0 ? (int)R.redStart[leaf] + below : R.nRed + (int)R.blackStart[leaf] + below;
+}
+__device__ __forceinline__ int dof_row_at(const TopoView& t, const RowMap& R, int gx, int gy, int gz) {
+    const int l = topo_find(t, gx, gy, gz);
+    return l < 0 ? -1 : dof_row(R, l, voxel_off(gx, gy, gz));
+}
+// one CTA per leaf of level L. F (finer) / C (coarser) compact neighbours are optional (RowMap.dof == null).
+__global__ void __launch_bounds__(512) compact_build_kernel(LevelView L, RowMap R, int n, int np,
+                                                            TopoView ft, RowMap FR, int fn, TopoView ct, RowMap CR,
+                                                            uint8_t* __restrict__ blob, uint32_t* __restrict__ voxelOfRow) {
+    const bool hasF = FR.dof != nullptr, hasC = CR.dof != nullptr;
+    const BlobLayout B = blob_layout(np, hasF);
+    float* diag = reinterpret_cast<float*>(blob + B.diag);
+    float* inv = reinterpret_cast<float*>(blob + B.inv);
+    float* minus = reinterpret_cast<float*>(blob + B.minus);
+    uint16_t* cols = reinterpret_cast<uint16_t*>(blob + B.cols);
+    uint16_t* parent = reinterpret_cast<uint16_t*>(blob + B.parent);
+    uint16_t* child = reinterpret_cast<uint16_t*>(blob + B.child);
+    const int leaf = blockIdx.x, off = threadIdx.x;
+    if (leaf == 0 && off < np - n) {   // padding rows, the first of them is the zero dummy
+        const int r = n + off;
+        diag[r] = 1.f; inv[r] = 0.f;
+        for (int ch = 0; ch < 3; ch++) minus[ch * np + r] = 0.f;
+        for (int k = 0; k < 6; k++) cols[k * np + r] = (uint16_t)n;
+        parent[r] = 0;
+        if (hasF) for (int k = 0; k < 8; k++) child[k * np + r] = (uint16_t)fn;
+        voxelOfRow[r] = 0;
+    }
+    const int row = dof_row(R, leaf, off);
+    if (row < 0) return;
+    const size_t i = (size_t)leaf * LEAF + off;
+    const int3 o = L.t.origin[leaf];
+    const int gx = o.x + (off >> 6), gy = o.y + ((off >> 3) & 7), gz = o.z + (off & 7);
+    diag[row] = L.diag[i];
+    inv[row] = L.invdiag[i];
+    minus[row] = L.xe[i]; minus[np + row] = L.ye[i]; minus[2 * np + row] = L.ze[i];
+    voxelOfRow[row] = (uint32_t)i;
+    const int d[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int r = dof_row_at(L.t, R, gx + d[k][0], gy + d[k][1], gz + d[k][2]);
+        cols[k * np + row] = (uint16_t)(r < 0 ? n : r);
+    }
+    int pr = 0;
+    if (hasC) { pr = dof_row_at(ct, CR, gx >> 1, gy >> 1, gz >> 1); if (pr < 0) pr = 0; }
+    parent[row] = (uint16_t)pr;
+    if (hasF) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int r = dof_row_at(ft, FR, 2 * gx + (k >> 2), 2 * gy + ((k >> 1) & 1), 2 * gz + (k & 1));
+            child[k * np + row] = (uint16_t)(r < 0 ? fn : r);
+        }
+    }
+}
+struct CompactDev {        // one compact level, as the cycle kernel sees it
+    int n, np, nRed, hasChild;
+    int oInv, oMinus, oCols;      // byte offsets into dynamic shared memory, always resident
+    int oDiag, oParent, oChild;   // byte offset into dynamic shared memory, or -1: read from the global blob
+    int xOff, bOff;               // scratch
+    const uint8_t* blob;          // global blob (blob_layout)
+    const uint32_t* voxelOfRow;
+};
+struct CompactSm {
+    int n, np, nRed;
+    float *x, *b;
+    const float *diag, *inv, *minus;
+    const uint16_t *cols, *parent, *child;
+};
+__device__ __forceinline__ CompactSm compact_sm(const CompactDev& c, unsigned char* sm) {
+    const BlobLayout B = blob_layout(c.np, c.hasChild != 0);
+    CompactSm S;
+    S.n = c.n; S.np = c.np; S.nRed = c.nRed;
+    S.x = reinterpret_cast<float*>(sm + c.xOff);
+    S.b = reinterpret_cast<float*>(sm + c.bOff);
+    S.inv = reinterpret_cast<const float*>(sm + c.oInv);
+    S.minus = reinterpret_cast<const float*>(sm + c.oMinus);
+    S.cols = reinterpret_cast<const uint16_t*>(sm + c.oCols);
+    S.diag = reinterpret_cast<const float*>(c.oDiag >= 0 ? sm + c.oDiag : c.blob + B.diag);
+    S.parent = reinterpret_cast<const uint16_t*>(c.oParent >= 0 ? sm + c.oParent : c.blob + B.parent);
+    S.child = reinterpret_cast<const uint16_t*>(c.oChild >= 0 ? sm + c.oChild : c.blob + B.child);
+    return S;
+}
+// off-diagonal sum of row r, same association as offdiag()
+__device__ __forceinline__ float compact_offdiag(const CompactSm& S, const float* x, int r) {
+    const int np = S.np;
+    const unsigned xm = S.cols[r], xp = S.cols[np + r], ym = S.cols[2 * np + r], yp = S.cols[3 * np + r],
+                   zm = S.cols[4 * np + r], zp = S.cols[5 * np + r];
+    const float fx = __fadd_rn(__fmul_rn(x[xp], S.minus[xp]), __fmul_rn(x[xm], S.minus[r]));
+    const float fy = __fadd_rn(__fmul_rn(x[yp], S.minus[np + yp]), __fmul_rn(x[ym], S.minus[np + r]));
+    const float fz = __fadd_rn(__fmul_rn(x[zp], S.minus[2 * np + zp]), __fmul_rn(x[zm], S.minus[2 * np + r]));
+    return __fadd_rn(__fadd_rn(fx, fy), fz);
+}
+// sum over the CTA (1024 threads), same tree as cg_block_sum but one bar.sync: every warp folds the 32 warp
+// partials itself; red = 2 x 32 floats used alternately
+__device__ __forceinline__ float cta_sum_1024(float v, float* red, unsigned& phase) {
+    for (int d = 16; d > 0; d >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, d));
+    float* buf = red + (phase & 1u) * 32;
+    phase++;
+    if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = buf[threadIdx.x & 31];
+    for (int d = 16; d > 0; d >>= 1) r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, d));
+    return r;
+}
+// Jacobi-preconditioned CG on the compact coarsest level (same arithmetic as coarse_cg_smem); x = S.x, the
+// residual lives in S.b, P and T in `pt` (2 x np floats)
+__device__ __forceinline__ float2 cta_sum2_1024(float a, float b, float2* red2, unsigned& phase) {
+    for (int d = 16; d > 0; d >>= 1) { a = __fadd_rn(a, __shfl_xor_sync(0xffffffffu, a, d)); b = __fadd_rn(b, __shfl_xor_sync(0xffffffffu, b, d)); }
+    float2* buf = red2 + (phase & 1u) * 32;
+    phase++;
+    if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5] = make_float2(a, b);
+    __syncthreads();
+    float2 r = buf[threadIdx.x & 31];
+    for (int d = 16; d > 0; d >>= 1) { r.x = __fadd_rn(r.x, __shfl_xor_sync(0xffffffffu, r.x, d)); r.y = __fadd_rn(r.y, __shfl_xor_sync(0xffffffffu, r.y, d)); }
+    return r;
+}
+__device__ void compact_cg(const CompactSm& S, float* pt, float* red, float2* red2, unsigned& phase) {
+    const int n = S.n, tid = threadIdx.x;
+    float* X = S.x; float* R = S.b; float* P = pt; float* T = pt + S.np;
+    auto dinv = [&](int r) { float d = S.diag[r]; return d != 0.f ? __fdiv_rn(1.0f, d) : 1.0f; };
+    for (int r = tid; r < S.np; r += BOT_THREADS) { X[r] = 0.f; P[r] = 0.f; if (r >= n) R[r] = 0.f; }
+    float acc = 0.f;
+    for (int r = tid; r < n; r += BOT_THREADS) acc = __fadd_rn(acc, __fmul_rn(R[r], R[r]));
+    const float rhsNorm2 = cta_sum_1024(acc, red, phase);
+    if (rhsNorm2 != 0.f) {
+        const float tol = 1.1920929e-07f;
+        const float threshold = fmaxf(__fmul_rn(__fmul_rn(tol, tol), rhsNorm2), 1.17549435e-38f);
+        float residualNorm2 = rhsNorm2;
+        if (!(residualNorm2 < threshold)) {
+            acc = 0.f;
+            for (int r = tid; r < n; r += BOT_THREADS) { float pv = __fmul_rn(dinv(r), R[r]); P[r] = pv; acc = __fadd_rn(acc, __fmul_rn(R[r], pv)); }
+            float absNew = cta_sum_1024(acc, red, phase);   // the bar.sync inside also publishes P
+            const int np = S.np;
+            for (int it = 0; it < 10; it++) {
+                acc = 0.f;
+                for (int r = tid; r < n; r += BOT_THREADS) {
+                    float s = __fadd_rn(0.f, __fmul_rn(S.diag[r], P[r]));
+#pragma unroll
+                    for (int ch = 0; ch < 3; ch++) {
+                        const unsigned cm = S.cols[(2 * ch) * np + r], cp = S.cols[(2 * ch + 1) * np + r];
+                        if (cm != (unsigned)n) s = __fadd_rn(s, __fmul_rn(S.minus[ch * np + r], P[cm]));
+                        if (cp != (unsigned)n) s = __fadd_rn(s, __fmul_rn(S.minus[ch * np + cp], P[cp]));
+                    }
+                    T[r] = s;
+                    acc = __fadd_rn(acc, __fmul_rn(P[r], s));
+                }
+                const float pt2 = cta_sum_1024(acc, red, phase);
+                const float alpha = __fdiv_rn(absNew, pt2);
+                acc = 0.f;
+                float acc2 = 0.f;
+                for (int r = tid; r < n; r += BOT_THREADS) {
+                    X[r] = __fadd_rn(X[r], __fmul_rn(alpha, P[r]));
+                    const float rv = __fsub_rn(R[r], __fmul_rn(alpha, T[r]));
+                    R[r] = rv;
+                    acc = __fadd_rn(acc, __fmul_rn(rv, rv));
+                    // |r|^2 and r.z (z = D^-1 r) go through one reduction: both only need the new r
+                    const float zv = __fmul_rn(dinv(r), rv);
+                    T[r] = zv;
+                    acc2 = __fadd_rn(acc2, __fmul_rn(rv, zv));
+                }
+                const float2 both = cta_sum2_1024(acc, acc2, red2, phase);   // all SpMV reads of P are behind this bar.sync
+                residualNorm2 = both.x;
+                if (residualNorm2 < threshold) break;
+                const float absOld = absNew;
+                absNew = both.y;
+                const float beta = __fdiv_rn(absNew, absOld);
+                for (int r = tid; r < n; r += BOT_THREADS) P[r] = __fadd_rn(T[r], __fmul_rn(beta, P[r]));
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------- the whole preconditioner in one launch
 // mg_cycle_kernel: a persistent cooperative kernel, one CTA of 1024 threads per SM, that executes the COMPLETE
 // mu-cycle (every level) as a flat op list. Ops on the large levels are spread over all CTAs (leaf chunks
@@ -885,11 +1024,13 @@ __device__ __forceinline__ float offdiag_tile(const LevelView& L, const float* T
 // One launch replaces ~370 kernel launches per preconditioner application at 512^3 -- the host could not
 // issue those faster than ~4.5 us each, which was the solver's real bound.
 constexpr int CYC_MAX_LEVELS = 10;
+constexpr int CYC_GRID_SCRATCH = (4 * TILE + 4 * LEAF) * 4;   // bytes: four 10^3 tiles + four leaf residuals
 struct CycleParams {
-    BottomLevel lv[CYC_MAX_LEVELS];   // xoff/boff >= 0 only on bottom levels (CTA 0's shared memory)
-    CoarseELL ell;
+    BottomLevel lv[CYC_MAX_LEVELS];   // leaf form (global memory), used on levels < compactFirst
+    CompactDev cl[CYC_MAX_LEVELS];    // compact rows (CTA 0's shared memory), levels >= compactFirst
     const uint8_t* prog;              // op | level << 3
-    int nOps, nLevels, bottomFirst;
+    int nOps, nLevels, compactFirst;
+    int scratchOff, cgOff;            // byte offsets into dynamic shared memory
     float w, oneMinusW, prolongAlpha;
     unsigned* barrier;                // arrival counter, zero at launch
     unsigned long long* trace;        // optional: %globaltimer at the start of every op (CTA 0), nOps + 1 entries
@@ -921,20 +1062,116 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& passed) {
     }
     __syncthreads();
 }
+// ops of the compact bottom, executed by CTA 0 between two device-wide barriers
+__device__ void compact_run(const CycleParams& P, unsigned char* sm, int k, int kEnd, float* red, float2* red2, unsigned& phase) {
+    const int tid = threadIdx.x;
+    const CompactDev& TD = P.cl[P.compactFirst];
+    const BottomLevel& TG = P.lv[P.compactFirst];
+    // every x starts as zero (row n of each level must read 0 for the whole run; the scratch region is shared
+    // with the leaf-tile staging of the grid ops and holds garbage here)
+    for (int l = P.compactFirst; l < P.nLevels; l++) {
+        const CompactSm S = compact_sm(P.cl[l], sm);
+        for (int r = tid; r < S.np; r += BOT_THREADS) { S.x[r] = 0.f; S.b[r] = 0.f; }
+    }
+    __syncthreads();
+    {
+        const CompactSm S = compact_sm(TD, sm);
+        const int first = P.prog[k] & 7;
+        const bool needX = first != OP_ZERO_RED && first != OP_COARSE;
+        for (int r = tid; r < S.n; r += BOT_THREADS) {
+            const uint32_t v = __ldg(&TD.voxelOfRow[r]);
+            S.b[r] = ld_l2(&TG.b[v]);
+            if (needX) S.x[r] = ld_l2(&TG.x[v]);
+        }
+    }
+    __syncthreads();
+    for (int q = k; q < kEnd; q++) {
+        const int cd = P.prog[q] & 7, l = P.prog[q] >> 3;
+        if (P.trace && tid == 0) P.trace[q] = globaltimer();
+        const CompactSm S = compact_sm(P.cl[l], sm);
+        if (cd == OP_ZERO_RED) {
+            for (int r = tid; r < S.n; r += BOT_THREADS)
+                S.x[r] = r < S.nRed ? __fmul_rn(__fmul_rn(S.b[r], S.inv[r]), P.w) : 0.f;
+        } else if (cd == OP_RED || cd == OP_BLACK) {
+            const int r0 = cd == OP_RED ? 0 : S.nRed, r1 = cd == OP_RED ? S.nRed : S.n;
+            for (int r = r0 + tid; r < r1; r += BOT_THREADS) {
+                const float od = compact_offdiag(S, S.x, r);
+                const float tt = __fmul_rn(__fmul_rn(__fsub_rn(S.b[r], od), S.inv[r]), P.w);
+                S.x[r] = __fmaf_rn(S.x[r], P.oneMinusW, tt);
+            }
+        } else if (cd == OP_RESID_RESTRICT) {
+            // item = coarse row * 8 + child slot; the eight residuals of a coarse row sit in eight adjacent lanes
+            // and are added in the reference's (ii,jj,kk) order (uaamg.cpp:1773-1833)
+            const CompactSm C = compact_sm(P.cl[l + 1], sm);
+            const int items = (C.n * 8 + 31) & ~31;
+            // child row and its diagonal are fetched one iteration ahead (either may live in global memory)
+            auto child_of = [&](int w) { const int crow = w >> 3; return (w < items && crow < C.n) ? (int)C.child[(w & 7) * C.np + crow] : S.n; };
+            int w = tid;
+            int f = child_of(w);
+            float dg = f < S.n ? S.diag[f] : 0.f;
+            while (w < items) {
+                const int wn = w + BOT_THREADS;
+                const int fn = child_of(wn);
+                const float dgn = fn < S.n ? S.diag[fn] : 0.f;
+                const int crow = w >> 3, slot = w & 7;
+                const bool present = f < S.n;
+                float res = 0.f;
+                if (present) res = __fsub_rn(S.b[f], __fmaf_rn(S.x[f], dg, compact_offdiag(S, S.x, f)));
+                const unsigned pm = __ballot_sync(0xffffffffu, present);
+                const int base = (tid & 31) & ~7;
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float v = __shfl_sync(0xffffffffu, res, base + j);
+                    if ((pm >> (base + j)) & 1u) sum = __fadd_rn(sum, v);
+                }
+                if (slot == 0 && crow < C.n) C.b[crow] = __fmul_rn(sum, 0.125f);
+                w = wn; f = fn; dg = dgn;
+            }
+        } else if (cd == OP_PROLONG) {
+            const CompactSm C = compact_sm(P.cl[l + 1], sm);
+            for (int r = tid; r < S.n; r += BOT_THREADS)
+                S.x[r] = __fadd_rn(S.x[r], __fmul_rn(P.prolongAlpha, C.x[S.parent[r]]));
+        } else {
+            compact_cg(S, reinterpret_cast<float*>(sm + P.cgOff), red, red2, phase);
+        }
+        __syncthreads();
+    }
+    {
+        const CompactSm S = compact_sm(TD, sm);
+        for (int r = tid; r < S.n; r += BOT_THREADS) TG.x[__ldg(&TD.voxelOfRow[r])] = S.x[r];
+    }
+}
 __global__ void __launch_bounds__(BOT_THREADS) mg_cycle_kernel(const __grid_constant__ CycleParams P) {
-    extern __shared__ float dynsm[];
-    __shared__ float sm33[33];
-    __shared__ float sres[2 * LEAF];
-    __shared__ float tiles[4 * TILE];
-    __shared__ float sresGrid[4 * LEAF];
+    extern __shared__ __align__(16) unsigned char cycsm[];
+    unsigned char* dynsm = cycsm;
+    __shared__ float red[64];
+    __shared__ float2 red2[64];
+    float* tiles = reinterpret_cast<float*>(dynsm + P.scratchOff);
+    float* sresGrid = tiles + 4 * TILE;
     const int tid = threadIdx.x, G = gridDim.x, c = blockIdx.x;
-    unsigned passed = 0;
+    unsigned passed = 0, phase = 0;
     int k = 0;
-    if (c == 0 && P.ell.inSmem) coarse_matrix_to_smem(P.ell, dynsm);
+    if (c == 0) {   // stage the compact matrices once
+        for (int l = P.compactFirst; l < P.nLevels; l++) {
+            const CompactDev& D = P.cl[l];
+            const BlobLayout B = blob_layout(D.np, D.hasChild != 0);
+            const int src[6] = {B.inv, B.minus, B.cols, B.diag, B.parent, B.child};
+            const int dst[6] = {D.oInv, D.oMinus, D.oCols, D.oDiag, D.oParent, D.hasChild ? D.oChild : -1};
+            const int len[6] = {4 * D.np, 12 * D.np, 12 * D.np, 4 * D.np, 2 * D.np, 16 * D.np};
+            for (int q = 0; q < 6; q++) {
+                if (dst[q] < 0) continue;
+                const uint4* sp = reinterpret_cast<const uint4*>(D.blob + src[q]);
+                uint4* dp = reinterpret_cast<uint4*>(dynsm + dst[q]);
+                for (int i = tid; i < (len[q] >> 4); i += BOT_THREADS) dp[i] = __ldg(&sp[i]);
+            }
+        }
+        __syncthreads();
+    }
     while (k < P.nOps) {
         const int code = P.prog[k] & 7, li = P.prog[k] >> 3;
-        if (P.trace && c == 0 && tid == 0) P.trace[k] = globaltimer();
-        if (li < P.bottomFirst) {
+        if (li < P.compactFirst) {
+            if (P.trace && c == 0 && tid == 0) P.trace[k] = globaltimer();
             const BottomLevel& B = P.lv[li];
             if (code == OP_ZERO_RED) {
                 for (int base = c * 2; base < B.n; base += G * 2) { int leaf = base + (tid >> 9); if (leaf < B.n) zero_red_leaf<M_GRID>(B.v, B.x, B.b, leaf, tid & 511, P.w); }
@@ -989,56 +1226,10 @@ __global__ void __launch_bounds__(BOT_THREADS) mg_cycle_kernel(const __grid_cons
             grid_barrier(P.barrier, passed);
             continue;
         }
-        // a run of bottom ops [k, kEnd): CTA 0 alone, shared-memory resident
+        // a run of compact ops [k, kEnd): CTA 0 alone, shared-memory resident
         int kEnd = k;
-        while (kEnd < P.nOps && (P.prog[kEnd] >> 3) >= P.bottomFirst) kEnd++;
-        if (c == 0) {
-            const BottomLevel& T = P.lv[P.bottomFirst];
-            float* tx = dynsm + T.xoff;
-            float* tb = dynsm + T.boff;
-            const int first = P.prog[k] & 7;
-            const bool needX = first != OP_ZERO_RED && first != OP_COARSE;
-            for (int i = tid; i < T.n * LEAF; i += BOT_THREADS) { tb[i] = ld_l2(&T.b[i]); if (needX) tx[i] = ld_l2(&T.x[i]); }
-            __syncthreads();
-            for (int q = k; q < kEnd; q++) {
-                const int cd = P.prog[q] & 7, l2 = P.prog[q] >> 3;
-                if (P.trace && tid == 0) P.trace[q] = globaltimer();
-                const BottomLevel& B = P.lv[l2];
-                float* x = dynsm + B.xoff;
-                const float* b = dynsm + B.boff;
-                if (cd == OP_ZERO_RED) {
-                    for (int base = 0; base < B.n; base += 2) { int leaf = base + (tid >> 9); if (leaf < B.n) zero_red_leaf<M_LOCAL>(B.v, x, b, leaf, tid & 511, P.w); }
-                } else if (cd == OP_RED || cd == OP_BLACK) {
-                    for (int base = 0; base < B.n; base += 4) { int leaf = base + (tid >> 8); if (leaf < B.n) rbgs_leaf<M_LOCAL>(B.v, x, b, leaf, tid & 255, cd == OP_RED ? 0 : 1, P.w, P.oneMinusW); }
-                } else if (cd == OP_RESID_RESTRICT) {
-                    const BottomLevel& C = P.lv[l2 + 1];
-                    float* cb = dynsm + C.boff;
-                    for (int base = 0; base < B.n; base += 2) {
-                        int leaf = base + (tid >> 9), off = tid & 511;
-                        bool live = false;
-                        if (leaf < B.n) {
-                            const LeafInfo info = load_info(B.v, leaf);
-                            live = (info.flags & LI_ANY) != 0;
-                            float r = 0.f;
-                            if (live && dof_bit(B.v, leaf, off)) r = __fsub_rn(b[(size_t)leaf * LEAF + off], ax_voxel<M_LOCAL>(B.v, info, x, leaf, off));
-                            sres[tid] = r;
-                        }
-                        __syncthreads();
-                        if (live && off < 64) restrict_leaf(B.v, C.v, sres + (tid >> 9) * LEAF, leaf, off, cb);
-                        __syncthreads();
-                    }
-                } else if (cd == OP_PROLONG) {
-                    const BottomLevel& C = P.lv[l2 + 1];
-                    const float* cx = dynsm + C.xoff;
-                    for (int base = 0; base < B.n; base += 2) { int leaf = base + (tid >> 9); if (leaf < B.n) prolong_voxel<M_LOCAL>(B.v, C.v, x, cx, leaf, tid & 511, P.prolongAlpha); }
-                } else {
-                    if (P.ell.inSmem) coarse_cg_smem(P.ell, b, x, dynsm, sm33);
-                    else coarse_cg(P.ell, b, x, dynsm, sm33);
-                }
-                __syncthreads();
-            }
-            for (int i = tid; i < T.n * LEAF; i += BOT_THREADS) T.x[i] = tx[i];
-        }
+        while (kEnd < P.nOps && (P.prog[kEnd] >> 3) >= P.compactFirst) kEnd++;
+        if (c == 0) compact_run(P, dynsm, k, kEnd, red, red2, phase);
         k = kEnd;
         if (k < P.nOps) grid_barrier(P.barrier, passed);
     }
@@ -1078,7 +1269,17 @@ struct Solver {
     DBuf<float> partial, scal;  // [max leaves], [8]
     DBuf<unsigned> counter;
     // mg_cycle_kernel (the whole preconditioner in one cooperative launch)
-    bool cycleReady = false, cycleMatrixInSmem = false;
+    struct CompactHost {
+        int n = 0, np = 0;
+        bool hasChild = false;
+        int nRed = 0;
+        DBuf<uint32_t> redStart, blackStart, voxelOfRow;
+        DBuf<uint8_t> blob;
+        int oInv = 0, oMinus = 0, oCols = 0, oDiag = -1, oParent = -1, oChild = -1, xOff = 0, bOff = 0;
+    };
+    std::vector<CompactHost> compact;   // index = level - compactFirst
+    int compactFirst = 0, scratchOff = 0, cgOff = 0;
+    bool cycleReady = false;
     DBuf<uint8_t> cycleProg;
     int cycleOps = 0, cycleGrid = 1;
     static constexpr int cycleGridMax = 192;
@@ -1201,7 +1402,9 @@ struct Solver {
     void emit_cycle(std::vector<uint8_t>& ops, int level, int n, bool skipFirst) {
         const int nl = (int)levels.size();
         auto put = [&](int code) { ops.push_back((uint8_t)(code | (level << 3))); };
-        if (level == nl - 1) { put(OP_COARSE); return; }
+        // the second visit of the coarsest level solves the same right-hand side from a zero guess again
+        // (uaamg.cpp:2019-2023: Eigen solve(), not solveWithGuess) -- same bits, so it is issued once
+        if (level == nl - 1) { if (skipFirst) put(OP_COARSE); return; }
         if (skipFirst) { put(OP_ZERO_RED); put(OP_BLACK); }
         for (int i = (skipFirst ? 1 : 0); i < n; i++) { put(OP_RED); put(OP_BLACK); }
         put(OP_RESID_RESTRICT);
@@ -1210,10 +1413,97 @@ struct Solver {
         put(OP_PROLONG);
         for (int i = 0; i < n; i++) { put(OP_BLACK); put(OP_RED); }
     }
+    // ---- mg_cycle_kernel: decide which levels run as compact rows in CTA 0's shared memory and build them
+    // mandatory shared memory with levels >= first compact: inv, minus, cols, x, b per row (36 B), the coarsest
+    // level's diag and the CG's P and T; diag / parent / child of the other levels are resident only if they fit
+    size_t compact_need(int first) const {
+        const int nl = (int)levels.size();
+        size_t persistent = 0, scratch = 0;
+        for (int l = first; l < nl; l++) {
+            const int np = compact_np(levels[l]->numDof);
+            persistent += (size_t)28 * np;
+            scratch += (size_t)8 * np;
+        }
+        const int npc = compact_np(levels[nl - 1]->numDof);
+        persistent += (size_t)4 * npc;
+        scratch += (size_t)8 * npc;
+        return persistent + std::max<size_t>(scratch, CYC_GRID_SCRATCH);
+    }
     void prepare_cycle(int n) {
         const int nl = (int)levels.size();
         cycleReady = false;
-        if (!bottomInSmem || nl > CYC_MAX_LEVELS || nl > 31) return;
+        if (nl > CYC_MAX_LEVELS || nl > 31) return;
+        int dev = 0, sms = 0, perSm = 0, coop = 0, optin = 0;
+        FB_CUDA(cudaGetDevice(&dev));
+        FB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        FB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        FB_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        cudaFuncAttributes fa;
+        FB_CUDA(cudaFuncGetAttributes(&fa, mg_cycle_kernel));
+        const size_t cap = (size_t)optin - fa.sharedSizeBytes - 256;
+        const int maxRows = 65000;   // 16-bit row indices
+        if (levels[nl - 1]->numDof > maxRows || compact_need(nl - 1) > cap) return;
+        compactFirst = nl - 1;
+        while (compactFirst > 0 && levels[compactFirst - 1]->numDof <= maxRows && compact_need(compactFirst - 1) <= cap) compactFirst--;
+        if (const char* e = getenv("FLIPB200_COMPACT_FIRST")) compactFirst = std::max(compactFirst, std::min(nl - 1, atoi(e)));
+        // rows: per-leaf red / black DOF prefixes of every compact level, then the blobs
+        compact.clear();
+        compact.resize(nl - compactFirst);
+        for (int l = compactFirst; l < nl; l++) {
+            Level& L = *levels[l];
+            CompactHost& H = compact[l - compactFirst];
+            H.n = L.numDof; H.np = compact_np(H.n); H.hasChild = l > compactFirst;
+            H.redStart.alloc(L.n + 1, w->stream); H.blackStart.alloc(L.n + 1, w->stream);
+            H.redStart.zero(); H.blackStart.zero();
+            FB_LAUNCH(w, "mg_leaf_popcount", (size_t)L.n * 72) leaf_colour_count_kernel<<<(L.n + 127) / 128, 128, 0, w->stream>>>(L.dof.p, L.n, H.redStart.p, H.blackStart.p);
+            uint64_t nRed = 0;
+            exclusive_scan_u32(w, H.redStart.p, H.redStart.p, L.n + 1, &nRed);
+            exclusive_scan_u32(w, H.blackStart.p, H.blackStart.p, L.n + 1, nullptr);
+            H.nRed = (int)nRed;
+            H.blob.alloc(blob_layout(H.np, H.hasChild).bytes, w->stream);
+            H.blob.zero();
+            H.voxelOfRow.alloc(H.np, w->stream);
+        }
+        auto rowmap = [&](int l) {
+            const CompactHost& H = compact[l - compactFirst];
+            return RowMap{levels[l]->dof.p, H.redStart.p, H.blackStart.p, H.nRed};
+        };
+        const RowMap none{nullptr, nullptr, nullptr, 0};
+        for (int l = compactFirst; l < nl; l++) {
+            Level& L = *levels[l];
+            CompactHost& H = compact[l - compactFirst];
+            const bool hasF = l > compactFirst, hasC = l + 1 < nl;
+            const LevelView lv = view_of(L);
+            FB_LAUNCH(w, "mg_compact_build", (size_t)L.n * LEAF * 24)
+                compact_build_kernel<<<L.n, 512, 0, w->stream>>>(lv, rowmap(l), H.n, H.np,
+                    hasF ? levels[l - 1]->topo->view() : lv.t, hasF ? rowmap(l - 1) : none, hasF ? compact[l - 1 - compactFirst].n : 0,
+                    hasC ? levels[l + 1]->topo->view() : lv.t, hasC ? rowmap(l + 1) : none,
+                    H.blob.p, H.voxelOfRow.p);
+        }
+        check_launch("compact_build");
+        // shared-memory map: [resident sections][scratch: x, b of every compact level, CG P/T | leaf tiles of the grid ops]
+        size_t cursor = 0;
+        for (auto& H : compact) {
+            H.oInv = (int)cursor; cursor += (size_t)4 * H.np;
+            H.oMinus = (int)cursor; cursor += (size_t)12 * H.np;
+            H.oCols = (int)cursor; cursor += (size_t)12 * H.np;
+            H.oDiag = H.oParent = H.oChild = -1;
+        }
+        { CompactHost& C = compact.back(); C.oDiag = (int)cursor; cursor += (size_t)4 * C.np; }
+        size_t scratch = 0;
+        for (auto& H : compact) scratch += (size_t)8 * H.np;
+        scratch += (size_t)8 * compact.back().np;
+        scratch = std::max<size_t>(scratch, CYC_GRID_SCRATCH);
+        // optional sections, most frequently read first
+        auto fits = [&](size_t bytes) { return cursor + bytes + scratch <= cap; };
+        for (auto& H : compact) if (H.hasChild && fits((size_t)16 * H.np)) { H.oChild = (int)cursor; cursor += (size_t)16 * H.np; }
+        for (size_t i = 0; i + 1 < compact.size(); i++) { auto& H = compact[i]; if (fits((size_t)2 * H.np)) { H.oParent = (int)cursor; cursor += (size_t)2 * H.np; } }
+        for (auto& H : compact) if (H.oDiag < 0 && fits((size_t)4 * H.np)) { H.oDiag = (int)cursor; cursor += (size_t)4 * H.np; }
+        scratchOff = (int)cursor;
+        for (auto& H : compact) { H.xOff = (int)cursor; cursor += (size_t)4 * H.np; H.bOff = (int)cursor; cursor += (size_t)4 * H.np; }
+        cgOff = (int)cursor; cursor += (size_t)8 * compact.back().np;
+        cycleSmem = std::max<size_t>(cursor, (size_t)scratchOff + CYC_GRID_SCRATCH);
+        if (cycleSmem > cap) return;
         std::vector<uint8_t> ops;
         emit_cycle(ops, 0, n, true);
         cycleOps = (int)ops.size();
@@ -1221,29 +1511,16 @@ struct Solver {
         FB_CUDA(cudaMemcpyAsync(cycleProg.p, ops.data(), ops.size(), cudaMemcpyHostToDevice, w->stream));
         sync(w);  // ops is a host temporary
         cycleBarrier.alloc(1, w->stream);
-        // shared memory of CTA 0: coarsest CG + x and b of every bottom level
-        size_t bottomBytes = 0;
-        for (int l = bottomFirst; l < nl; l++) bottomBytes += (size_t)levels[l]->n * LEAF * sizeof(float) * 2;
-        // 227 KB per CTA minus the kernel's static shared memory (tiles, residual staging: ~29 KB)
-        const size_t cap = 196 * 1024;
-        cycleMatrixInSmem = ndofPad < 65535 && (size_t)11 * ndofPad * sizeof(float) + bottomBytes <= cap;
-        cycleSmem = (size_t)(cycleMatrixInSmem ? 11 : 5) * ndofPad * sizeof(float) + bottomBytes;
-        cycleSmem = std::max<size_t>(cycleSmem, 1024);
-        if (cycleSmem > cap) return;
         FB_CUDA(cudaFuncSetAttribute(mg_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cycleSmem));
-        int dev = 0, sms = 0, perSm = 0, coop = 0;
-        FB_CUDA(cudaGetDevice(&dev));
-        FB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        FB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
         FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, mg_cycle_kernel, BOT_THREADS, cycleSmem));
         if (!coop || perSm < 1) return;
-        cycleGrid = bottomFirst == 0 ? 1 : std::min(sms, (int)cycleGridMax);
+        cycleGrid = compactFirst == 0 ? 1 : std::min(sms, (int)cycleGridMax);
         cycleReady = true;
     }
     void launch_cycle(float* x, const float* b) {
         const int nl = (int)levels.size();
         CycleParams P;
-        int cursor = (cycleMatrixInSmem ? 11 : 5) * ndofPad;
+        memset(&P, 0, sizeof(P));
         for (int i = 0; i < nl; i++) {
             Level& L = *levels[i];
             P.lv[i].v = view_of(L);
@@ -1252,14 +1529,14 @@ struct Solver {
             P.lv[i].n = L.n;
             P.lv[i].xoff = P.lv[i].boff = -1;
             P.lv[i].bReadOnly = i == 0 ? 1 : 0;  // level 0 iterates on the caller's residual, never written in the launch
-            if (i >= bottomFirst) {
-                P.lv[i].xoff = cursor; cursor += L.n * LEAF;
-                P.lv[i].boff = cursor; cursor += L.n * LEAF;
+            if (i >= compactFirst) {
+                const CompactHost& H = compact[i - compactFirst];
+                P.cl[i] = CompactDev{H.n, H.np, H.nRed, H.hasChild ? 1 : 0, H.oInv, H.oMinus, H.oCols, H.oDiag, H.oParent, H.oChild,
+                                     H.xOff, H.bOff, H.blob.p, H.voxelOfRow.p};
             }
         }
-        Level& C = *levels.back();
-        P.ell = CoarseELL{ndof, ndofPad, C.n * LEAF, cycleMatrixInSmem ? 1 : 0, ellCols.p, ellVals.p, rowOfVoxel.p};
-        P.prog = cycleProg.p; P.nOps = cycleOps; P.nLevels = nl; P.bottomFirst = bottomFirst;
+        P.prog = cycleProg.p; P.nOps = cycleOps; P.nLevels = nl; P.compactFirst = compactFirst;
+        P.scratchOff = scratchOff; P.cgOff = cgOff;
         P.w = 1.2f; P.oneMinusW = 1.0f - 1.2f; P.prolongAlpha = 1.0f;
         P.barrier = cycleBarrier.p;
         // FLIPB200_TRACE_CYCLE=<file>: per-op device timestamps of the next application, written as CSV (debug aid)
@@ -1281,8 +1558,10 @@ struct Solver {
             FB_CUDA(cudaMemcpyAsync(ops.data(), cycleProg.p, ops.size(), cudaMemcpyDeviceToHost, w->stream));
             sync(w);
             if (FILE* f = fopen(tracePath, "w")) {
-                fprintf(f, "k,op,level,leaves,ns\n");
-                for (int k = 0; k < cycleOps; k++) fprintf(f, "%d,%d,%d,%d,%llu\n", k, ops[k] & 7, ops[k] >> 3, levels[ops[k] >> 3]->n, t[k + 1] - t[k]);
+                fprintf(f, "k,op,level,leaves,dofs,compact,ns\n");
+                for (int k = 0; k < cycleOps; k++)
+                    fprintf(f, "%d,%d,%d,%d,%d,%d,%llu\n", k, ops[k] & 7, ops[k] >> 3, levels[ops[k] >> 3]->n, levels[ops[k] >> 3]->numDof,
+                            (ops[k] >> 3) >= compactFirst ? 1 : 0, t[k + 1] - t[k]);
                 fclose(f);
             }
         }
