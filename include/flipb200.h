@@ -164,6 +164,20 @@ int flipb200_stream(flipb200_world* w, void** stream);
 /* 128-byte NCCL unique id created on rank 0 and distributed by the host (torch.distributed / MPI) */
 int flipb200_comm_unique_id(uint8_t id[128]);
 int flipb200_comm_init(flipb200_world* w, int rank, int nRanks, const uint8_t id[128]);
+/* in-process communicator: rank r = worlds[r], all in this process, each driven by its own host thread. Carries the
+ * same message sequence as the NCCL one; lets the decomposition run (and be tested) on a single GPU. */
+int flipb200_comm_init_local(flipb200_world** worlds, int n);
+/* wake the ranks of an in-process communicator that are blocked in a collective after a peer failed */
+int flipb200_comm_abort(flipb200_world* w);
+/* Slab decomposition (no reference counterpart: the reference runs one TBB process).
+ * This rank owns the leaf layers [leafLo, leafHi) along x (leaf coordinate = voxel >> 3); the first rank's lower and
+ * the last rank's upper bound are open. Slabs must be at least two layers thick and cover the axis without gaps.
+ * From here on every node call is COLLECTIVE (all ranks issue the same sequence): flipb200_bin_from_points routes
+ * points to their owners and fills the ghost layers, flipb200_g2p_advect_sheetty migrates particles,
+ * P2G / solve / gradient exchange ghost leaves, CFL and the PCG scalars are all-reduced. Grids and particles
+ * downloaded from a rank include its ghost layers; flipb200_dd_owned tells which leaves are authoritative. */
+int flipb200_dd_set_slab(flipb200_world* w, int leafLo, int leafHi);
+int flipb200_dd_owned(flipb200_world* w, int* leafLo, int* leafHi);
 
 #ifdef __cplusplus
 }

@@ -37,7 +37,7 @@ EXPORTS = [
     "flipb200_solve_ppe", "flipb200_solve_ppe_ex", "flipb200_solver_info", "flipb200_residual_history",
     "flipb200_subtract_grad", "flipb200_substep", "flipb200_launch_count", "flipb200_profile_enable",
     "flipb200_profile_reset", "flipb200_profile_get", "flipb200_stream", "flipb200_comm_unique_id",
-    "flipb200_comm_init",
+    "flipb200_comm_init", "flipb200_comm_init_local", "flipb200_comm_abort", "flipb200_dd_set_slab", "flipb200_dd_owned",
 ]
 
 
@@ -265,6 +265,23 @@ class World:
                                            C.c_int(1 if viscous_is_velocity else 0), ms if want_stage_ms else None))
         return list(ms) if want_stage_ms else None
 
+    # -- multi-GPU: slab decomposition along x (include/flipb200.h "multi-GPU") --------------
+    def comm_init_nccl(self, rank: int, world: int, unique_id: bytes):
+        """one process per GPU; unique_id = the 128 bytes rank 0 got from comm_unique_id()"""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self.lib.flipb200_comm_init(self.h, C.c_int(rank), C.c_int(world), buf))
+
+    def comm_abort(self):
+        self.lib.flipb200_comm_abort(self.h)
+
+    def dd_set_slab(self, leaf_lo: int, leaf_hi: int):
+        self._ck(self.lib.flipb200_dd_set_slab(self.h, C.c_int(leaf_lo), C.c_int(leaf_hi)))
+
+    def dd_owned(self):
+        lo, hi = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.flipb200_dd_owned(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     # -- measurement hooks -----------------------------------------------------------
     def launch_count(self) -> int:
         n = C.c_uint64(0)
@@ -292,3 +309,46 @@ class World:
         s = C.c_void_p()
         self._ck(self.lib.flipb200_stream(self.h, C.byref(s)))
         return s.value or 0
+
+
+def comm_unique_id(lib: Optional[C.CDLL] = None) -> bytes:
+    lib = lib or load_library()
+    buf = (C.c_uint8 * 128)()
+    rc = lib.flipb200_comm_unique_id(buf)
+    if rc != 0:
+        raise FlipB200Error(rc, "ncclGetUniqueId failed (is libnccl.so.2 loadable? import torch first)")
+    return bytes(buf)
+
+
+def comm_init_local(worlds) -> None:
+    """Connect several worlds of THIS process (one host thread each) with the in-process communicator."""
+    lib = worlds[0].lib
+    arr = (C.c_void_p * len(worlds))(*[w.h for w in worlds])
+    rc = lib.flipb200_comm_init_local(arr, C.c_int(len(worlds)))
+    if rc != 0:
+        raise FlipB200Error(rc, "comm_init_local failed")
+
+
+def run_ranks(worlds, fn):
+    """Run fn(rank, world) for every world on its own host thread (ctypes releases the GIL inside library calls);
+    a failing rank aborts the in-process communicator so its peers do not wait forever. Returns the results by rank."""
+    import threading
+    res, err = [None] * len(worlds), [None] * len(worlds)
+
+    def body(r):
+        try:
+            res[r] = fn(r, worlds[r])
+        except BaseException as e:  # noqa: BLE001
+            err[r] = e
+            for w in worlds:
+                w.comm_abort()
+
+    th = [threading.Thread(target=body, args=(r,)) for r in range(len(worlds))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return res

@@ -23,6 +23,9 @@ int guarded(F&& f) {
     }
 }
 void use_device(flipb200_world* w) { FB_CUDA(cudaSetDevice(w->device)); }
+}  // namespace
+namespace fb { void set_last_error(const std::string& m) { g_lastError = m; } }
+namespace {
 
 __global__ void aos_to_soa_kernel(const float* __restrict__ in, float* __restrict__ c0, float* __restrict__ c1,
                                   float* __restrict__ c2, size_t nVox) {
@@ -192,6 +195,7 @@ int flipb200_world_destroy(flipb200_world* w) {
         cudaSetDevice(w->device);
         cudaStreamSynchronize(w->stream);
         comm_destroy(w);
+        dd_destroy(w);
         resolve_profile(w);
         for (auto e : w->evtPool) cudaEventDestroy(e);
         cudaStream_t s = w->stream;

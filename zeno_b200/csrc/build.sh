@@ -9,7 +9,7 @@ OUT=../libflipb200.so
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xcompiler -O2 --expt-relaxed-constexpr -Xptxas -v"
 mkdir -p _build
 pids=()
-for f in scan topo particles p2g g2p stencils poisson abi comm; do
+for f in scan topo particles p2g g2p stencils poisson abi comm dd; do
   if [ ! -f _build/$f.o ] || [ $f.cu -nt _build/$f.o ] || [ common.cuh -nt _build/$f.o ] || [ world.cuh -nt _build/$f.o ] || [ levelset.cuh -nt _build/$f.o ] || [ ../../include/flipb200.h -nt _build/$f.o ]; then
     ( $NVCC $FLAGS -c $f.cu -o _build/$f.o > _build/$f.log 2>&1 || { cat _build/$f.log; exit 1; } ) &
     pids+=($!)

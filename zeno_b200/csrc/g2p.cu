@@ -27,6 +27,7 @@ struct G2PParams {
     float dx, dt, picMin, picMax, surfacedist;
     int rkOrder, sameField;
     int3* ijkOut; uint8_t* alive;
+    int leaf0;                        // first leaf of the launch (slab decomposition: owned leaves only)
     float *prePos, *preVel; uint8_t* preAlive;
 };
 
@@ -189,7 +190,7 @@ __device__ bool solid_normal_at(const G2PParams& p, int qx, int qy, int qz, floa
 
 __global__ void __launch_bounds__(G2P_THREADS) g2p_advect_kernel(G2PParams p) {
     __shared__ uint32_t sStart[LEAF + 1];
-    const int leaf = blockIdx.x;
+    const int leaf = blockIdx.x + p.leaf0;
     const size_t vbase = (size_t)leaf * LEAF;
     const uint32_t leafBeg = __ldg(&p.voxelStart[vbase]), leafEnd = __ldg(&p.voxelStart[vbase + LEAF]);
     if (leafEnd == leafBeg) return;
@@ -341,18 +342,44 @@ void g2p_advect_sheetty(World* w, float dt, float dx, int surfaceSize, int rkOrd
     p.prePos = w->capturePreCodec ? w->preCodecPos.p : nullptr;
     p.preVel = w->capturePreCodec ? w->preCodecVel.p : nullptr;
     p.preAlive = w->capturePreCodec ? w->preCodecAlive.p : nullptr;
-    if (nl && n) {
+    // slab decomposition: only the owned leaves are advected (ghost particles are re-imported below)
+    int leafLo = 0, leafHi = nl;
+    const bool dd = dd_on(w);
+    if (dd) dd_owned_slots(w, &leafLo, &leafHi);
+    p.leaf0 = leafLo;
+    if (leafHi > leafLo && n) {
         // compulsory traffic: 12 B read + 12 B write per particle + the band grids once
         FB_LAUNCH(w, "g2p_advect", n * 24 + (size_t)nl * LEAF * 28 + (size_t)nl * LEAF * 4)
-            g2p_advect_kernel<<<nl, G2P_THREADS, 0, w->stream>>>(p);
+            g2p_advect_kernel<<<leafHi - leafLo, G2P_THREADS, 0, w->stream>>>(p);
         check_launch("g2p_advect");
+    }
+    DBuf<uint32_t> i0 = std::move(w->pts.w0), i1 = std::move(w->pts.w1), i2 = std::move(w->pts.w2);
+    if (dd) {
+        // migrants and ghost copies cross the slab faces; the merged set replaces the local one
+        uint32_t range[2] = {0, 0};
+        if (nl) {
+            FB_CUDA(cudaMemcpyAsync(&range[0], w->pts.voxelStart.p + (size_t)leafLo * LEAF, 4, cudaMemcpyDeviceToHost, w->stream));
+            FB_CUDA(cudaMemcpyAsync(&range[1], w->pts.voxelStart.p + (size_t)leafHi * LEAF, 4, cudaMemcpyDeviceToHost, w->stream));
+            sync(w);
+        }
+        DBuf<uint32_t> m0, m1, m2;
+        DBuf<int3> mijk;
+        uint64_t nm = 0;
+        dd_migrate(w, range[0], range[1], i0.p, i1.p, i2.p, ijk.p, alive.p, m0, m1, m2, mijk, &nm);
+        DBuf<int3> morig(nm + 1, w->stream);
+        origins_from_ijk(w, mijk.p, nm, morig.p);
+        TopoPtr newPool = topo_from_origins_dev(w, morig.p, (int)nm, true);
+        DBuf<uint32_t> keys(nm + 1, w->stream);
+        keys_from_ijk(w, newPool, mijk.p, nullptr, nm, keys.p);
+        rebin_particles(w, newPool, keys.p, nm, m0, m1, m2);
+        w->pool = newPool;
+        return;
     }
     // K2: new pool from the target leaves (+ring), keys, stable counting sort with the voxel cap
     origins_from_ijk(w, ijk.p, n, origins.p);
     TopoPtr newPool = topo_from_origins_dev(w, origins.p, (int)n, true);
     DBuf<uint32_t> keys(n + 1, w->stream);
     keys_from_ijk(w, newPool, ijk.p, alive.p, n, keys.p);
-    DBuf<uint32_t> i0 = std::move(w->pts.w0), i1 = std::move(w->pts.w1), i2 = std::move(w->pts.w2);
     rebin_particles(w, newPool, keys.p, n, i0, i1, i2);
     w->pool = newPool;
 }

@@ -320,7 +320,11 @@ void p2g(World* w, float dx, int velExtraLayer) {
     nsdf.alloc.alloc(n ? n : 1, w->stream);
     nsdf.alloc.zero();
     (void)zero3;
-    if (n == 0) { vel = std::move(nvel); grid_copy(w, post, vel); sdf = std::move(nsdf); return; }
+    if (n == 0) {
+        vel = std::move(nvel); grid_copy(w, post, vel); sdf = std::move(nsdf);
+        if (dd_on(w)) { dd_refresh(w, vel, 2); dd_refresh(w, post, 2); dd_refresh(w, sdf, 2); }
+        return;
+    }
 
     DBuf<uint64_t> chMask((size_t)3 * n * 8, w->stream), topoMask((size_t)n * 8, w->stream), ring((size_t)n * 8, w->stream);
     DBuf<int> overflow(1, w->stream);
@@ -369,6 +373,12 @@ void p2g(World* w, float dx, int velExtraLayer) {
     vel = std::move(nvel);
     post = std::move(npost);
     sdf = std::move(nsdf);
+    if (dd_on(w)) {
+        // the two leaf layers beyond each slab face were computed from an incomplete particle set: take the owner's
+        dd_refresh(w, vel, 2);
+        dd_refresh(w, post, 2);
+        dd_refresh(w, sdf, 2);
+    }
 }
 
 }  // namespace fb

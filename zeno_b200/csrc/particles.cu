@@ -142,6 +142,8 @@ void sort_by_key(World* w, const TopoPtr& topo, const uint32_t* keys, uint64_t n
 }
 }  // namespace
 
+void origins_from_ijk(World* w, const int3* ijk, uint64_t n, int3* origins);
+
 void bin_from_points(World* w, const float* pos_host, const float* vel_host, uint64_t n) {
     DBuf<float> pos(3 * n + 1, w->stream), vel;
     FB_CUDA(cudaMemcpyAsync(pos.p, pos_host, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, w->stream));
@@ -157,6 +159,19 @@ void bin_from_points(World* w, const float* pos_host, const float* vel_host, uin
         check_launch("bin_encode");
         FB_LAUNCH(w, "bin_origins", n * 24) ijk_to_origin_kernel<<<nblk(n, 256), 256, 0, w->stream>>>(ijk.p, n, origins.p);
         check_launch("ijk_to_origin");
+    }
+    if (dd_on(w)) {
+        // slab decomposition: the caller hands each rank (at least) its own points; whatever lies in a neighbour's
+        // slab moves there and the ghost layers are filled before the store is sorted
+        DBuf<uint32_t> m0, m1, m2;
+        DBuf<int3> mijk;
+        uint64_t nm = 0;
+        dd_migrate(w, 0, n, w0.p, w1.p, w2.p, ijk.p, nullptr, m0, m1, m2, mijk, &nm);
+        n = nm;
+        w0 = std::move(m0); w1 = std::move(m1); w2 = std::move(m2); ijk = std::move(mijk);
+        origins.alloc(n + 1, w->stream);
+        keys.alloc(n + 1, w->stream);
+        origins_from_ijk(w, ijk.p, n, origins.p);
     }
     TopoPtr pool = topo_from_origins_dev(w, origins.p, (int)n, /*ring=*/true);
     if (n) {

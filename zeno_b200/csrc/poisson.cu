@@ -10,6 +10,7 @@
 // and the stencil kernels take a constant-coefficient path on flagged leaves (no coefficient
 // traffic). The stencil arithmetic keeps the reference's association and its explicit FMAs.
 #include "world.cuh"
+#include <climits>
 #include "levelset.cuh"
 #include <algorithm>
 #include <cstring>
@@ -37,6 +38,7 @@ struct Level {
     DBuf<uint8_t> flags;   // bit0 diag, bit1 x, bit2 y, bit3 z read as the default
     DBuf<LeafInfo> info;
     DBuf<float> x, b;
+    int ownLo = 0, ownHi = -1;   // slab decomposition: leaves whose DOFs this rank owns (reductions); -1 = all
 };
 struct LevelView {
     TopoView t;
@@ -45,10 +47,13 @@ struct LevelView {
     const uint8_t* flags;
     const LeafInfo* info;
     float term;
+    int ownLo, ownHi;   // leaves that contribute to dot products / norms (everything on a single GPU)
 };
 LevelView view_of(const Level& L) {
-    return LevelView{L.topo->view(), L.dof.p, L.diag.p, L.invdiag.p, L.xe.p, L.ye.p, L.ze.p, L.flags.p, L.info.p, L.term};
+    return LevelView{L.topo->view(), L.dof.p, L.diag.p, L.invdiag.p, L.xe.p, L.ye.p, L.ze.p, L.flags.p, L.info.p, L.term,
+                     L.ownLo, L.ownHi < 0 ? L.n : L.ownHi};
 }
+__device__ __forceinline__ bool owned_leaf(const LevelView& L, int leaf) { return leaf >= L.ownLo && leaf < L.ownHi; }
 
 // ---------------------------------------------------------------- reductions (deterministic)
 // block-wide sum / max of one value per thread (512 threads), result valid in thread 0
@@ -443,9 +448,9 @@ __global__ void __launch_bounds__(512) zero_red_kernel(LevelView L, float* __res
 }
 // r = b - A x on a fine leaf, restricted straight into the coarse right-hand side (no residual round trip)
 __global__ void __launch_bounds__(512) residual_restrict_kernel(LevelView F, LevelView C, const float* x, const float* __restrict__ b,
-                                                                float* __restrict__ coarse) {
+                                                                float* __restrict__ coarse, int leaf0) {
     __shared__ float sres[LEAF];
-    const int leaf = blockIdx.x, off = threadIdx.x;
+    const int leaf = blockIdx.x + leaf0, off = threadIdx.x;
     const LeafInfo li = load_info(F, leaf);
     if (!(li.flags & LI_ANY)) return;
     float r = 0.f;
@@ -463,7 +468,16 @@ __global__ void __launch_bounds__(512) prolong_kernel(LevelView F, LevelView C, 
 // Every producing kernel writes one partial per leaf; the LAST CTA to finish (threadfence + counter) folds the
 // partials in index order, so the result does not depend on which CTA that is, and applies the scalar update
 // that follows the reduction in solveMultigridPCG (uaamg.cpp:2332-2403). No separate fold / scalar launches.
-enum { FIN_NU = 0, FIN_SIGMA_ALPHA = 1, FIN_RHO_INIT = 2, FIN_RHO_BETA = 3 };
+// FIN_DEFER (slab decomposition): the fold only stores this rank's partial in s[6]; after the all-reduce of s[6]
+// scalar_fin_kernel applies the same update.
+enum { FIN_NU = 0, FIN_SIGMA_ALPHA = 1, FIN_RHO_INIT = 2, FIN_RHO_BETA = 3, FIN_DEFER = 8 };
+__device__ __forceinline__ void apply_fin(float* s, int fin, float r) {
+    if (fin == FIN_NU) s[4] = r;
+    else if (fin == FIN_SIGMA_ALPHA) { s[1] = r; s[2] = __fdiv_rn(s[0], r); }
+    else if (fin == FIN_RHO_INIT) s[0] = r;
+    else { s[5] = r; s[3] = __fdiv_rn(r, s[0]); s[0] = r; }
+}
+__global__ void scalar_fin_kernel(float* s, int fin) { apply_fin(s, fin, s[6]); }
 template <bool IS_MAX>
 __device__ __forceinline__ void finish_reduction(float mine, float* partial, unsigned* counter, float* s, int fin, float* sm16) {
     __shared__ bool sLast;
@@ -483,10 +497,8 @@ __device__ __forceinline__ void finish_reduction(float mine, float* partial, uns
     }
     float r = IS_MAX ? block_absmax_512(a, sm16) : block_sum_512(a, sm16);
     if (threadIdx.x == 0) {
-        if (fin == FIN_NU) s[4] = r;
-        else if (fin == FIN_SIGMA_ALPHA) { s[1] = r; s[2] = __fdiv_rn(s[0], r); }
-        else if (fin == FIN_RHO_INIT) s[0] = r;
-        else { s[5] = r; s[3] = __fdiv_rn(r, s[0]); s[0] = r; }
+        if (fin & FIN_DEFER) s[6] = r;
+        else apply_fin(s, fin, r);
         *counter = 0;
     }
 }
@@ -494,7 +506,7 @@ enum { MODE_LAPLACIAN = 0, MODE_RESIDUAL = 1 };
 // y = A x (+ sigma = x.y, alpha) or y = b - A x (+ nu = |y|_inf)   (uaamg.cpp:1085-1106)
 template <int MODE>
 __global__ void __launch_bounds__(512) apply_kernel(LevelView L, const float* x, const float* __restrict__ b, float* __restrict__ y,
-                                                    float* partial, unsigned* counter, float* s) {
+                                                    float* partial, unsigned* counter, float* s, int defer) {
     __shared__ float sm16[16];
     const int leaf = blockIdx.x, off = threadIdx.x;
     const LeafInfo li = load_info(L, leaf);
@@ -509,28 +521,30 @@ __global__ void __launch_bounds__(512) apply_kernel(LevelView L, const float* x,
         }
         y[(size_t)leaf * LEAF + off] = out;
     }
+    if (!owned_leaf(L, leaf)) red = 0.f;
     float r = MODE == MODE_RESIDUAL ? block_absmax_512(red, sm16) : block_sum_512(red, sm16);
     __syncthreads();
-    finish_reduction<MODE == MODE_RESIDUAL>(r, partial, counter, s, MODE == MODE_RESIDUAL ? FIN_NU : FIN_SIGMA_ALPHA, sm16);
+    finish_reduction<MODE == MODE_RESIDUAL>(r, partial, counter, s, (MODE == MODE_RESIDUAL ? FIN_NU : FIN_SIGMA_ALPHA) | defer, sm16);
 }
 // r -= alpha z ; nu = |r|_inf (levelAlphaXPlusY + levelAbsMax, uaamg.cpp:2447-2479)
 __global__ void __launch_bounds__(512) axpy_absmax_kernel(LevelView L, float* s, const float* __restrict__ z, float* __restrict__ r,
-                                                          float* partial, unsigned* counter) {
+                                                          float* partial, unsigned* counter, int defer) {
     __shared__ float sm16[16];
     const int leaf = blockIdx.x, off = threadIdx.x;
     const size_t i = (size_t)leaf * LEAF + off;
     float v = 0.f;
     if (dof_bit(L, leaf, off)) { v = __fadd_rn(r[i], __fmul_rn(-s[2], z[i])); r[i] = v; }
+    if (!owned_leaf(L, leaf)) v = 0.f;
     float m = block_absmax_512(v, sm16);
     __syncthreads();
-    finish_reduction<true>(m, partial, counter, s, FIN_NU, sm16);
+    finish_reduction<true>(m, partial, counter, s, FIN_NU | defer, sm16);
 }
 __global__ void __launch_bounds__(512) dot_kernel(LevelView L, const float* __restrict__ a, const float* __restrict__ b, float* partial,
                                                   unsigned* counter, float* s, int fin) {
     __shared__ float sm16[16];
     const int leaf = blockIdx.x, off = threadIdx.x;
     const size_t i = (size_t)leaf * LEAF + off;
-    float v = dof_bit(L, leaf, off) ? __fmul_rn(a[i], b[i]) : 0.f;
+    float v = (dof_bit(L, leaf, off) && owned_leaf(L, leaf)) ? __fmul_rn(a[i], b[i]) : 0.f;
     float m = block_sum_512(v, sm16);
     __syncthreads();
     finish_reduction<false>(m, partial, counter, s, fin, sm16);
@@ -1251,6 +1265,38 @@ __global__ void warm_start_kernel(TopoView t, const uint64_t* __restrict__ dof, 
     if (isfinite(v)) x[(size_t)leaf * LEAF + off] = v;
 }
 
+// ---------------------------------------------------------------- slab decomposition: global level 1
+// Every rank coarsens its own pool; a level-1 cell whose eight children it owns is exact there (the coefficients read
+// the children and the DOF bits one fine voxel below them, which the ghost layer holds). This kernel writes the
+// owned cells of the GLOBAL level-1 leaves (defaults where the rank has no such leaf, zero for cells of other ranks);
+// an all-reduce (sum) then gives every rank the complete level.
+__global__ void __launch_bounds__(512) dd_scatter_coarse_kernel(TopoView gt, TopoView lt, const uint64_t* __restrict__ ldof,
+                                                                const float* __restrict__ ldiag, const float* __restrict__ lx,
+                                                                const float* __restrict__ ly, const float* __restrict__ lz,
+                                                                int xlo, int xhi, float cterm, uint64_t* __restrict__ gdof,
+                                                                float* __restrict__ gdiag, float* __restrict__ gx,
+                                                                float* __restrict__ gy, float* __restrict__ gz) {
+    const int leaf = blockIdx.x, off = threadIdx.x;
+    const int3 o = gt.origin[leaf];
+    const int X = o.x + (off >> 6), Y = o.y + ((off >> 3) & 7), Z = o.z + (off & 7);
+    float d = 0.f, a = 0.f, b = 0.f, c = 0.f;
+    bool on = false;
+    if (X >= xlo && X < xhi) {
+        const int l = topo_find(lt, X, Y, Z);
+        if (l >= 0) {
+            const size_t i = (size_t)l * LEAF + off;
+            d = ldiag[i]; a = lx[i]; b = ly[i]; c = lz[i];
+            on = mask_get(ldof, l, off);
+        } else {
+            d = __fmul_rn(6.0f, cterm); a = -cterm; b = -cterm; c = -cterm;
+        }
+    }
+    const size_t i = (size_t)leaf * LEAF + off;
+    gdiag[i] = d; gx[i] = a; gy[i] = b; gz[i] = c;
+    const unsigned bal = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0) reinterpret_cast<uint32_t*>(gdof)[(size_t)leaf * 16 + (threadIdx.x >> 5)] = bal;
+}
+
 // ---------------------------------------------------------------- host-side solver
 // The bottom runs on ONE SM: its coefficient set (7 arrays x 2 KB per leaf) has to stay inside that SM's
 // L1 + shared memory (256 KB) or every pass turns into a serial chain of L2 round trips (measured: a 64-leaf
@@ -1280,8 +1326,13 @@ struct Solver {
     std::vector<CompactHost> compact;   // index = level - compactFirst
     int compactFirst = 0, scratchOff = 0, cgOff = 0;
     bool cycleReady = false;
-    DBuf<uint8_t> cycleProg;
-    int cycleOps = 0, cycleGrid = 1;
+    DBuf<uint8_t> cycleProg, cycleProg2;   // visit from a zero guess / from the current iterate
+    int cycleOps = 0, cycleOps2 = 0, cycleGrid = 1;
+    // slab decomposition (dd.cu): level 0 lives on this rank's pool, levels >= 1 are assembled globally and
+    // replicated on every rank inside `coarse`
+    bool dd = false;
+    bool coarseOnly = false;   // this object is the replicated coarse part of a decomposed solve
+    std::unique_ptr<Solver> coarse;
     static constexpr int cycleGridMax = 192;
     size_t cycleSmem = 0;
     DBuf<unsigned> cycleBarrier;
@@ -1314,7 +1365,7 @@ struct Solver {
         check_launch("leaf_info");
         L.numDof = (int)mask_count(w, L.dof.p, L.n);
     }
-    void coarsen() {
+    std::unique_ptr<Level> coarsen_raw() {
         const Level& F = *levels.back();
         DBuf<int3> cand(F.n, w->stream);
         DBuf<uint32_t> cnt(1, w->stream);
@@ -1335,9 +1386,65 @@ struct Solver {
         L.diag.alloc(n, w->stream); L.xe.alloc(n, w->stream); L.ye.alloc(n, w->stream); L.ze.alloc(n, w->stream);
         FB_LAUNCH(w, "mg_coarsen", (size_t)L.n * LEAF * 16 + (size_t)F.n * LEAF * 16) coarsen_kernel<<<L.n, 512, 0, w->stream>>>(view_of(F), L.topo->view(), L.term, L.dof.p, L.diag.p, L.xe.p, L.ye.p, L.ze.p);
         check_launch("coarsen");
-        finish_level(L);
-        alloc_vectors(L);
+        return Lp;
+    }
+    void coarsen() {
+        std::unique_ptr<Level> Lp = coarsen_raw();
+        finish_level(*Lp);
+        alloc_vectors(*Lp);
         levels.push_back(std::move(Lp));
+    }
+    // slab decomposition: assemble level 1 globally, then build and keep the rest of the hierarchy replicated
+    void dd_build_coarse() {
+        FB_REQUIRE(levels[0]->numDof > MAX_COARSEST, FLIPB200_ERR_DOMAIN,
+                   "slab decomposition needs at least two multigrid levels (more than 4000 pressure DOFs)");
+        std::unique_ptr<Level> loc = coarsen_raw();
+        const int R = w->nRanks, me = w->rank;
+        DBuf<int> cnt(R, w->stream);
+        cnt.zero();
+        const int mine = loc->n;
+        FB_CUDA(cudaMemcpyAsync(cnt.p + me, &mine, 4, cudaMemcpyHostToDevice, w->stream));
+        comm_allreduce(w, cnt.p, R, CT_I32, false);
+        std::vector<int> counts(R);
+        FB_CUDA(cudaMemcpyAsync(counts.data(), cnt.p, 4 * R, cudaMemcpyDeviceToHost, w->stream));
+        sync(w);
+        int maxCnt = 1, total = 0;
+        for (int c : counts) { maxCnt = std::max(maxCnt, c); total += c; }
+        DBuf<int> gath((size_t)R * maxCnt * 3, w->stream);
+        gath.zero();
+        if (mine) FB_CUDA(cudaMemcpyAsync(gath.p + (size_t)me * maxCnt * 3, loc->topo->origin.p, (size_t)mine * 12, cudaMemcpyDeviceToDevice, w->stream));
+        comm_allreduce(w, gath.p, (size_t)R * maxCnt * 3, CT_I32, false);
+        DBuf<int3> cand(total + 1, w->stream);
+        for (int r = 0, at = 0; r < R; at += counts[r], r++)
+            if (counts[r]) FB_CUDA(cudaMemcpyAsync(cand.p + at, gath.p + (size_t)r * maxCnt * 3, (size_t)counts[r] * 12, cudaMemcpyDeviceToDevice, w->stream));
+        auto Gp = std::make_unique<Level>();
+        Level& G = *Gp;
+        G.topo = topo_from_origins_dev(w, cand.p, total, false);
+        G.n = G.topo->n;
+        G.dx = loc->dx; G.term = loc->term;
+        const size_t nv = (size_t)G.n * LEAF;
+        G.dof.alloc((size_t)G.n * 8, w->stream);
+        G.diag.alloc(nv, w->stream); G.xe.alloc(nv, w->stream); G.ye.alloc(nv, w->stream); G.ze.alloc(nv, w->stream);
+        int lo, hi;
+        dd_owned_coords(w, &lo, &hi);
+        const int xlo = me > 0 ? 4 * lo : INT_MIN, xhi = me < R - 1 ? 4 * hi : INT_MAX;   // level-1 cells: fine voxel / 2
+        TopoView lt = loc->topo->view();
+        FB_LAUNCH(w, "dd_scatter_coarse", nv * 40) dd_scatter_coarse_kernel<<<G.n, 512, 0, w->stream>>>(G.topo->view(), lt, loc->dof.p, loc->diag.p, loc->xe.p, loc->ye.p, loc->ze.p,
+                                                                                                       xlo, xhi, G.term, G.dof.p, G.diag.p, G.xe.p, G.ye.p, G.ze.p);
+        check_launch("dd_scatter_coarse");
+        comm_allreduce(w, G.diag.p, nv, CT_F32, false);
+        comm_allreduce(w, G.xe.p, nv, CT_F32, false);
+        comm_allreduce(w, G.ye.p, nv, CT_F32, false);
+        comm_allreduce(w, G.ze.p, nv, CT_F32, false);
+        comm_allreduce(w, G.dof.p, (size_t)G.n * 16, CT_U32, false);   // disjoint bits: sum == or
+        coarse = std::make_unique<Solver>();
+        coarse->w = w; coarse->dt = dt; coarse->coarseOnly = true;
+        coarse->finish_level(G);
+        coarse->alloc_vectors(G);
+        coarse->levels.push_back(std::move(Gp));
+        while (coarse->levels.back()->numDof > MAX_COARSEST) coarse->coarsen();
+        coarse->build_coarsest();
+        if (!getenv("FLIPB200_NO_CYCLE_KERNEL")) coarse->prepare_cycle(4);
     }
     void build_coarsest() {
         Level& L = *levels.back();
@@ -1509,7 +1616,12 @@ struct Solver {
         cycleOps = (int)ops.size();
         cycleProg.alloc(ops.size(), w->stream);
         FB_CUDA(cudaMemcpyAsync(cycleProg.p, ops.data(), ops.size(), cudaMemcpyHostToDevice, w->stream));
-        sync(w);  // ops is a host temporary
+        std::vector<uint8_t> ops2;
+        emit_cycle(ops2, 0, n, false);
+        cycleOps2 = (int)ops2.size();
+        cycleProg2.alloc(ops2.size() + 1, w->stream);
+        if (cycleOps2) FB_CUDA(cudaMemcpyAsync(cycleProg2.p, ops2.data(), ops2.size(), cudaMemcpyHostToDevice, w->stream));
+        sync(w);  // ops, ops2 are host temporaries
         cycleBarrier.alloc(1, w->stream);
         FB_CUDA(cudaFuncSetAttribute(mg_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cycleSmem));
         FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, mg_cycle_kernel, BOT_THREADS, cycleSmem));
@@ -1517,8 +1629,9 @@ struct Solver {
         cycleGrid = compactFirst == 0 ? 1 : std::min(sms, (int)cycleGridMax);
         cycleReady = true;
     }
-    void launch_cycle(float* x, const float* b) {
+    void launch_cycle(float* x, const float* b, bool second = false) {
         const int nl = (int)levels.size();
+        if (second && cycleOps2 == 0) return;
         CycleParams P;
         memset(&P, 0, sizeof(P));
         for (int i = 0; i < nl; i++) {
@@ -1535,14 +1648,16 @@ struct Solver {
                                      H.xOff, H.bOff, H.blob.p, H.voxelOfRow.p};
             }
         }
-        P.prog = cycleProg.p; P.nOps = cycleOps; P.nLevels = nl; P.compactFirst = compactFirst;
+        P.prog = second ? cycleProg2.p : cycleProg.p; P.nOps = second ? cycleOps2 : cycleOps; P.nLevels = nl; P.compactFirst = compactFirst;
         P.scratchOff = scratchOff; P.cgOff = cgOff;
         P.w = 1.2f; P.oneMinusW = 1.0f - 1.2f; P.prolongAlpha = 1.0f;
         P.barrier = cycleBarrier.p;
         // FLIPB200_TRACE_CYCLE=<file>: per-op device timestamps of the next application, written as CSV (debug aid)
-        static const char* tracePath = getenv("FLIPB200_TRACE_CYCLE");
+        static const char* tracePathEnv = getenv("FLIPB200_TRACE_CYCLE");
+        const char* tracePath = tracePathEnv;
         DBuf<unsigned long long> trace;
         P.trace = nullptr;
+        if (second) tracePath = nullptr;
         if (tracePath) { trace.alloc(cycleOps + 1, w->stream); trace.zero(); P.trace = trace.p; }
         FB_CUDA(cudaMemsetAsync(cycleBarrier.p, 0, sizeof(unsigned), w->stream));
         uint64_t bytes = 0;  // 121 B/DOF per level visit, level l is visited 2^l times
@@ -1613,9 +1728,11 @@ struct Solver {
         rbgs_pass(L, x, b, redFirst ? 1 : 0, wSor);
         check_launch("rbgs");
     }
-    void residual_restrict(Level& L, Level& P, const float* x, const float* b) {
+    void residual_restrict(Level& L, Level& P, const float* x, const float* b, int leafLo = 0, int leafHi = -1) {
+        if (leafHi < 0) leafHi = L.n;
+        if (leafHi <= leafLo) return;
         FB_LAUNCH(w, "mg_residual_restrict", (uint64_t)L.numDof * 8 + (uint64_t)P.numDof * 4)
-            residual_restrict_kernel<<<L.n, 512, 0, w->stream>>>(view_of(L), view_of(P), x, b, P.b.p);
+            residual_restrict_kernel<<<leafHi - leafLo, 512, 0, w->stream>>>(view_of(L), view_of(P), x, b, P.b.p, leafLo);
         check_launch("residual_restrict");
     }
     void prolong(Level& L, Level& P, float* x, float alpha) {
@@ -1623,8 +1740,30 @@ struct Solver {
         check_launch("prolong");
     }
     // muCyclePreconditioner<2, skip_first> with the RBGS smoother (uaamg.cpp:1993-2126)
+    // slab decomposition, level 0. Whole ghost LEAVES are exchanged, so eight colour passes fit between two exchanges:
+    // what pass k computes in the ghost layer is wrong only within k voxels of its far face, and the owned DOFs read
+    // just the nearest ghost plane. Per application: r in, the iterate after pre-smoothing, the coarse right-hand side.
+    void dd_cycle0(float* x, const float* b, int n) {
+        Level& L = *levels[0];
+        Solver& G = *coarse;
+        Level& P = *G.levels[0];
+        const float wS = 1.2f;
+        dd_refresh(w, {DDArray{const_cast<float*>(b), LEAF * 4}}, 1);
+        FB_LAUNCH(w, "mg_zero_red", (uint64_t)L.numDof * 10) zero_red_kernel<<<L.n, 512, 0, w->stream>>>(view_of(L), x, b, wS);
+        rbgs_pass(L, x, b, 1, wS);
+        for (int i = 1; i < n; i++) rbgs(L, x, b, true, wS);
+        dd_refresh(w, {DDArray{x, LEAF * 4}}, 1);
+        P.b.zero();
+        residual_restrict(L, P, x, b, L.ownLo, L.ownHi);
+        comm_allreduce(w, P.b.p, (size_t)P.n * LEAF, CT_F32, false);   // every coarse cell has exactly one non-zero contributor
+        G.mu_cycle_precond(P.x.p, P.b.p, 0, n, true);
+        G.mu_cycle_precond(P.x.p, P.b.p, 0, n, false);
+        prolong(L, P, x, 1.0f);
+        for (int i = 0; i < n; i++) rbgs(L, x, b, false, wS);
+    }
     void mu_cycle_precond(float* x, const float* b, int level, int n, bool skipFirst) {
-        if (level == 0 && skipFirst && n == 4 && cycleReady) { launch_cycle(x, b); return; }
+        if (level == 0 && dd) { dd_cycle0(x, b, n); return; }
+        if (level == 0 && n == 4 && cycleReady && (skipFirst || coarseOnly)) { launch_cycle(x, b, !skipFirst); return; }
         if (level >= bottomFirst) { launch_bottom(x, b, n, skipFirst, true, 0); return; }
         Level& L = *levels[level];
         const float wS = 1.2f;
@@ -1655,17 +1794,33 @@ struct Solver {
         for (int i = 0; i < postSmooth && level == 0; i++) rbgs(L, x, b, false, wS);
     }
     // level-0 vector kernels
+    int defer() const { return dd ? FIN_DEFER : 0; }
+    // slab decomposition: s[6] holds this rank's partial; all-reduce it, then apply the scalar update
+    void finish(int fin, bool isMax) {
+        if (!dd) return;
+        comm_allreduce(w, scal.p + 6, 1, CT_F32, isMax);
+        FB_LAUNCH(w, "pcg_scalar", 32) scalar_fin_kernel<<<1, 1, 0, w->stream>>>(scal.p, fin);
+        check_launch("scalar_fin");
+    }
     void residual0(Level& L0, float* out, const float* x, const float* b) {
-        FB_LAUNCH(w, "pcg_residual", (uint64_t)L0.numDof * 16) apply_kernel<MODE_RESIDUAL><<<L0.n, 512, 0, w->stream>>>(view_of(L0), x, b, out, partial.p, counter.p, scal.p);
+        FB_LAUNCH(w, "pcg_residual", (uint64_t)L0.numDof * 16) apply_kernel<MODE_RESIDUAL><<<L0.n, 512, 0, w->stream>>>(view_of(L0), x, b, out, partial.p, counter.p, scal.p, defer());
         check_launch("residual");
+        finish(FIN_NU, true);
     }
     void laplacian0(Level& L0, float* out, const float* x) {
-        FB_LAUNCH(w, "pcg_laplacian_dot", (uint64_t)L0.numDof * 12) apply_kernel<MODE_LAPLACIAN><<<L0.n, 512, 0, w->stream>>>(view_of(L0), x, nullptr, out, partial.p, counter.p, scal.p);
+        FB_LAUNCH(w, "pcg_laplacian_dot", (uint64_t)L0.numDof * 12) apply_kernel<MODE_LAPLACIAN><<<L0.n, 512, 0, w->stream>>>(view_of(L0), x, nullptr, out, partial.p, counter.p, scal.p, defer());
         check_launch("laplacian");
+        finish(FIN_SIGMA_ALPHA, false);
     }
     void dot0(Level& L0, const float* a, const float* b, int fin) {
-        FB_LAUNCH(w, "pcg_dot", (uint64_t)L0.numDof * 8) dot_kernel<<<L0.n, 512, 0, w->stream>>>(view_of(L0), a, b, partial.p, counter.p, scal.p, fin);
+        FB_LAUNCH(w, "pcg_dot", (uint64_t)L0.numDof * 8) dot_kernel<<<L0.n, 512, 0, w->stream>>>(view_of(L0), a, b, partial.p, counter.p, scal.p, fin | defer());
         check_launch("dot");
+        finish(fin, false);
+    }
+    void axpy_absmax0(Level& L0, const float* z, float* r) {
+        FB_LAUNCH(w, "pcg_axpy_absmax", (uint64_t)L0.numDof * 12) axpy_absmax_kernel<<<L0.n, 512, 0, w->stream>>>(view_of(L0), scal.p, z, r, partial.p, counter.p, defer());
+        check_launch("axpy_absmax");
+        finish(FIN_NU, true);
     }
     float read_scalar(int slot) {
         float h = 0.f;
@@ -1687,11 +1842,16 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
     GridV& fw = w->V(FLIPB200_FACE_WEIGHT);
     GridV& vel = w->V(FLIPB200_VELOCITY);
     const int n = pool->n;
+    const bool dd = dd_on(w);
+    FB_REQUIRE(!dd || n > 0, FLIPB200_ERR_DOMAIN, "slab decomposition: a rank without fluid cannot take part in the solve");
     if (n == 0) return;  // "skip if there is no dof to solve" (FF/FLIP_vdb.cpp:3044-3047)
+    int ownLo = 0, ownHi = n;
+    if (dd) dd_owned_slots(w, &ownLo, &ownHi);
 
     Solver S;
     S.w = w;
     S.dt = dt;
+    S.dd = dd;
     {
         auto Lp = std::make_unique<Level>();
         Level& L = *Lp;
@@ -1702,13 +1862,26 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
         FB_LAUNCH(w, "mg_build_finest", nv * 36) build_finest_kernel<<<n, 512, 0, w->stream>>>(pool->view(), phi.val.p, phi.bg, phi.mask.p, fw.val[0].p, fw.val[1].p, fw.val[2].p, dt / (dx * dx), L.dof.p, L.diag.p, L.xe.p, L.ye.p, L.ze.p);
         check_launch("build_finest");
         S.finish_level(L);
+        if (dd) {
+            // reductions and the DOF count cover the owned leaves only; the count is global
+            L.ownLo = ownLo; L.ownHi = ownHi;
+            DBuf<int> c(1, w->stream);
+            const int mine = ownHi > ownLo ? (int)mask_count(w, L.dof.p + (size_t)ownLo * 8, ownHi - ownLo) : 0;
+            FB_CUDA(cudaMemcpyAsync(c.p, &mine, 4, cudaMemcpyHostToDevice, w->stream));
+            comm_allreduce(w, c.p, 1, CT_I32, false);
+            FB_CUDA(cudaMemcpyAsync(&L.numDof, c.p, 4, cudaMemcpyDeviceToHost, w->stream));
+            sync(w);
+        }
         S.levels.push_back(std::move(Lp));  // level 0 iterates on the PCG vectors; it owns no x/b
     }
-    while (S.levels.back()->numDof > MAX_COARSEST) S.coarsen();
-    S.build_coarsest();
-    if (!getenv("FLIPB200_NO_CYCLE_KERNEL")) S.prepare_cycle(4);
+    if (dd) S.dd_build_coarse();
+    else {
+        while (S.levels.back()->numDof > MAX_COARSEST) S.coarsen();
+        S.build_coarsest();
+        if (!getenv("FLIPB200_NO_CYCLE_KERNEL")) S.prepare_cycle(4);
+    }
     Level& L0 = *S.levels[0];
-    st.levels = (int)S.levels.size();
+    st.levels = dd ? 1 + (int)S.coarse->levels.size() : (int)S.levels.size();
     st.numDof = L0.numDof;
     S.partial.alloc(n, w->stream);
     S.scal.alloc(8, w->stream);
@@ -1737,8 +1910,9 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
         float nuOld = nu;
         const LevelView v0 = view_of(L0);
         for (; iter < maxIter; iter++) {
+            if (dd) dd_refresh(w, {DDArray{p.p, LEAF * 4}}, 1);   // A p reads the nearest ghost plane of p
             S.laplacian0(L0, z.p, p.p);  // z = A p, sigma = p.z, alpha = rho / sigma
-            FB_LAUNCH(w, "pcg_axpy_absmax", (uint64_t)L0.numDof * 12) axpy_absmax_kernel<<<n, 512, 0, w->stream>>>(v0, S.scal.p, z.p, r.p, S.partial.p, S.counter.p);
+            S.axpy_absmax0(L0, z.p, r.p);
             nuOld = nu;
             nu = S.read_scalar(4);
             st.history.push_back(nu / initAbs);
@@ -1756,7 +1930,7 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
     }
     st.iterations = iter;
     st.status = status;
-    if (status != 0) {
+    if (status != 0 && !dd) {   // (not available under slab decomposition: the status is reported instead)
         // MGPCG failed: warm start from the previous pressure + pure multigrid (FF/FLIP_vdb.cpp:3089-3097)
         GridF& oldP = w->F(FLIPB200_PRESSURE);
         TopoView ot = oldP.topo ? oldP.topo->view() : TopoView{0, make_int3(0, 0, 0), make_int3(0, 0, 0), nullptr, nullptr, nullptr};
@@ -1787,6 +1961,7 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
     FB_CUDA(cudaMemcpyAsync(nd.mask.p, L0.dof.p, (size_t)n * 64, cudaMemcpyDeviceToDevice, w->stream));
     w->F(FLIPB200_PRESSURE) = std::move(np);
     w->F(FLIPB200_DIVERGENCE) = std::move(nd);
+    if (dd) { dd_refresh(w, w->F(FLIPB200_PRESSURE), 2); dd_refresh(w, w->F(FLIPB200_DIVERGENCE), 2); }
     sync(w);
 }
 

@@ -237,12 +237,16 @@ void add_vector(World* w, float x, float y, float z) {
 
 float cfl(World* w) {
     GridV& v = w->V(FLIPB200_VELOCITY);
-    if (!v.topo || v.topo->n == 0) return 3.402823466e+38f / 2;
-    int n = v.topo->n;
+    const bool empty = !v.topo || v.topo->n == 0;
+    if (empty && !dd_on(w)) return 3.402823466e+38f / 2;
+    int n = empty ? 0 : v.topo->n;
     DBuf<unsigned> m(1, w->stream);
     m.zero();
-    FB_LAUNCH(w, "cfl_absmax", (size_t)n * LEAF * 12) absmax3_kernel<<<n, 512, 0, w->stream>>>(v.mask.p, v.val[0].p, v.val[1].p, v.val[2].p, m.p);
-    check_launch("absmax3");
+    if (n) {
+        FB_LAUNCH(w, "cfl_absmax", (size_t)n * LEAF * 12) absmax3_kernel<<<n, 512, 0, w->stream>>>(v.mask.p, v.val[0].p, v.val[1].p, v.val[2].p, m.p);
+        check_launch("absmax3");
+    }
+    if (dd_on(w)) comm_allreduce(w, m.p, 1, CT_U32, true);   // bit patterns of non-negative floats order like the floats
     unsigned h = 0;
     FB_CUDA(cudaMemcpyAsync(&h, m.p, 4, cudaMemcpyDeviceToHost, w->stream));
     sync(w);
@@ -257,7 +261,7 @@ void subtract_grad(World* w, float dt, float dx, int velExtraLayer) {
     refresh_solid_views(w);
     TopoPtr pool = w->pool;
     const int n = pool->n;
-    if (!n) return;
+    if (!n) { if (dd_on(w)) dd_refresh(w, w->V(FLIPB200_VELOCITY), 2); return; }
     GridV& vel = w->V(FLIPB200_VELOCITY);
     GridV& fw = w->V(FLIPB200_FACE_WEIGHT);
     GridF& phi = w->F(FLIPB200_LIQUID_SDF);
@@ -271,6 +275,7 @@ void subtract_grad(World* w, float dt, float dx, int velExtraLayer) {
     }
     union_extrapolate(w, velExtraLayer, vel, chMask.p, phi.mask.p);
     finish_vec3(w, vel, chMask.p);
+    if (dd_on(w)) dd_refresh(w, vel, 2);
 }
 
 }  // namespace fb

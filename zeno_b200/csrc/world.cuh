@@ -14,7 +14,8 @@ struct SolverStats {
     std::vector<float> history;
 };
 
-struct Comm;  // NCCL state (comm.cu)
+struct Comm;     // NCCL / in-process communicator (comm.cu)
+struct DDState;  // slab decomposition state (dd.cu)
 
 }  // namespace fb
 
@@ -52,6 +53,7 @@ struct flipb200_world {
     fb::SolverStats solver;
     fb::Comm* comm = nullptr;
     int rank = 0, nRanks = 1;
+    fb::DDState* dd = nullptr;   // non-null once flipb200_dd_set_slab was called
 
     fb::GridV& V(int id) { return vgrid[id]; }
     fb::GridF& F(int id) { return fgrid[id]; }
@@ -93,6 +95,7 @@ inline void check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw Error(2, std::string(what) + ": " + cudaGetErrorString(e));
 }
+void set_last_error(const std::string& m);   // abi.cu: what flipb200_last_error() returns on this thread
 inline void sync(World* w) { FB_CUDA(cudaStreamSynchronize(w->stream)); }
 
 // ---- topo.cu ------------------------------------------------------------------------
@@ -138,6 +141,32 @@ void union_extrapolate(World* w, int nLayer, GridV& vel, uint64_t* chMask, const
 void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter);
 
 // ---- comm.cu ------------------------------------------------------------------------
+// Point-to-point messages are issued in groups (ncclGroupStart/End semantics): every send/recv between
+// begin and end is matched with the peer's in issue order; buffers are device memory, sizes in bytes.
+enum { CT_F32 = 0, CT_U32 = 1, CT_I32 = 2 };
 void comm_destroy(World* w);
+bool comm_active(World* w);
+void comm_group_begin(World* w);
+void comm_send(World* w, int peer, const void* buf, size_t bytes);
+void comm_recv(World* w, int peer, void* buf, size_t bytes);
+void comm_group_end(World* w);
+void comm_allreduce(World* w, void* buf, size_t n, int type, bool isMax);   // in place, sum or max
+
+// ---- dd.cu --------------------------------------------------------------------------
+// Slab decomposition along x: rank r owns the leaf layers [lo, hi) (leaf coordinate = voxel >> 3),
+// keeps one ghost layer of particles on each side and a pool that reaches one further ring layer.
+struct DDArray { void* base; int bytesPerLeaf; };
+bool dd_on(World* w);
+void dd_destroy(World* w);
+void dd_set_slab(World* w, int lo, int hi);
+void dd_owned_slots(World* w, int* ownLo, int* ownHi);          // slot range of the owned leaves in w->pool (collective)
+void dd_owned_coords(World* w, int* lo, int* hi);               // owned leaf-layer range; +-2^29 at the open ends
+void dd_refresh(World* w, const std::vector<DDArray>& arrays, int layers);   // ghost (+ring) leaves <- owner (collective)
+void dd_refresh(World* w, GridF& g, int layers);
+void dd_refresh(World* w, GridV& g, int layers);
+// exchange after a move: particles [pLo,pHi) of the arrays (alive may be null = all alive) are kept, sent to the left /
+// right neighbour (migrants + ghost copies), and the merged set [from left | kept | from right] is returned.
+void dd_migrate(World* w, uint64_t pLo, uint64_t pHi, const uint32_t* w0, const uint32_t* w1, const uint32_t* w2, const int3* ijk,
+                const uint8_t* alive, DBuf<uint32_t>& o0, DBuf<uint32_t>& o1, DBuf<uint32_t>& o2, DBuf<int3>& oijk, uint64_t* nOut);
 
 }  // namespace fb
