@@ -198,16 +198,48 @@ def main():
     import torch.distributed as dist
     from zeno_b200 import abi, scenes
 
+    # stdout carries exactly one JSON line: NCCL / torch banners ("NCCL version ...") go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
 
     N = args.grid
-    pos, vel, dx = scenes.dam_break_points(N, seed=1 + rank, ppc=args.ppc)
-    solid = scenes.box_solid_sdf(N, dx)
-    w = abi.World(dx, device=local_rank)
-    w.set_grid("SolidSDF", solid)
-    w.PrimToVDBPointDataGrid(pos, vel)
+    if world == 1:
+        pos, vel, dx = scenes.dam_break_points(N, seed=1 + rank, ppc=args.ppc)
+        solid = scenes.box_solid_sdf(N, dx)
+        w = abi.World(dx, device=local_rank)
+        w.set_grid("SolidSDF", solid)
+        w.PrimToVDBPointDataGrid(pos, vel)
+        block = (N // 4,) * 3
+        parallelism = "single GPU"
+    else:
+        # BASELINE config[4]: ONE tank (2N)^3 shared by all ranks, the water block grows with the rank count so that
+        # every rank owns ~(N/4)^3 voxels x ppc particles (weak scaling); slabs of whole leaf layers along x.
+        # The NCCL communicator of the library is created from an id rank 0 broadcasts through torch.distributed.
+        from zeno_b200 import dist_util
+        q = N // 4
+        block = {2: (2 * q, q, q), 4: (2 * q, 2 * q, q), 8: (2 * q, 2 * q, 2 * q)}.get(world, (q * world, q, q))
+        N = 2 * N if max(block) <= 2 * N - 16 else max(block) + 16
+        bounds = dist_util.slab_bounds(block[0] // 8, world)
+        lo, hi = bounds[rank]
+        pos, vel, dx = scenes.dam_break_points(N, seed=1 + rank, ppc=args.ppc, box=((8 * lo, 8 * hi), (0, block[1]), (0, block[2])))
+        solid = scenes.box_solid_sdf(N, dx)
+        w = abi.World(dx, device=local_rank)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(abi.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        w.comm_init_nccl(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        w.dd_set_slab(lo, hi)
+        w.set_grid("SolidSDF", solid)
+        w.PrimToVDBPointDataGrid(pos, vel)
+        parallelism = (f"slab decomposition along x over {world} ranks ({hi - lo} leaf layers each + 1 ghost layer per face), "
+                       "particle migration / ghost-leaf exchange / sharded MGPCG over NCCL")
+    owned_particles = (lambda: w.particles_info()[1]) if world == 1 else w.dd_owned_particles
     del pos, vel
     w.FLIP_P2G(dx, 3)
     stream = torch.cuda.ExternalStream(w.stream(), device=torch.device("cuda", local_rank))
@@ -237,7 +269,7 @@ def main():
         t_s = time.perf_counter()
         step()
         step_ms.append(round(1e3 * (time.perf_counter() - t_s), 3))  # host wall time; every substep ends synchronised
-        particle_steps += w.particles_info()[1]
+        particle_steps += owned_particles()
         iters.append(w.solver_info()["history"].shape[0] - 1)
     e1.record(stream)
     barrier()
@@ -315,7 +347,7 @@ def main():
             out_p = w.get_particles(out=out_pts)
             out_g = {g: w.get_grid(g, out=out_state[g]) for g in STATE_GRIDS}
             d2h = sum(v.nbytes for v in out_p.values()) + sum(v.nbytes for d in out_g.values() for v in d.values())
-            psteps += out_p["P"].shape[0]
+            psteps += out_p["P"].shape[0] if world == 1 else owned_particles()
         barrier()
         es = time.perf_counter() - t0
         if world > 1:
@@ -334,20 +366,21 @@ def main():
         r = cpu_reference_arm(args.cpu_grid, 5, 1)
         cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
+    n_particles = owned_particles()   # collective under the decomposition
     if rank == 0:
-        n_particles = w.particles_info()[1]
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"FastFLIP dam-break {N}^3 tank, {n_particles} particles/GPU, {args.ppc} ppc, one substep = CFL_dt + G2PAdvectorSheetty(RK3) + FLIP_P2G + CutCellWeight + PushOutLiquidSDF + FieldAddVector + AssembleSolvePPE(5e-5) + SubtractPressureGradient",
-                           "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (one tank per GPU; brick decomposition not implemented yet)",
+                "config": {"workload": f"FastFLIP dam-break {N}^3 tank, water block {block[0]}x{block[1]}x{block[2]} voxels, {n_particles} particles/GPU, {args.ppc} ppc, one substep = CFL_dt + G2PAdvectorSheetty(RK3) + FLIP_P2G + CutCellWeight + PushOutLiquidSDF + FieldAddVector + AssembleSolvePPE(5e-5) + SubtractPressureGradient",
+                           "parallelism": parallelism,
                            "l2": "inputs larger than L2 (>=200 MB particle state per step), no flush",
                            "pcg_iterations": iters, "step_ms_host": step_ms},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
                 "roofline": roofline, "cpu_baseline": cpu,
                 "stage_ms": {"g2p_advect_rebin": stage_ms[0], "p2g": stage_ms[1], "stencils": stage_ms[2], "mgpcg": stage_ms[3], "gradient": stage_ms[4]},
                 "kernels": {k: v for k, v in top}}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     w.close()
     if world > 1:
         dist.destroy_process_group()

@@ -178,6 +178,8 @@ int flipb200_comm_abort(flipb200_world* w);
  * downloaded from a rank include its ghost layers; flipb200_dd_owned tells which leaves are authoritative. */
 int flipb200_dd_set_slab(flipb200_world* w, int leafLo, int leafHi);
 int flipb200_dd_owned(flipb200_world* w, int* leafLo, int* leafHi);
+/* particles in the owned leaves (flipb200_particles_info counts the ghost copies as well); collective */
+int flipb200_dd_owned_particles(flipb200_world* w, uint64_t* n);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,7 @@ EXPORTS = [
     "flipb200_subtract_grad", "flipb200_substep", "flipb200_launch_count", "flipb200_profile_enable",
     "flipb200_profile_reset", "flipb200_profile_get", "flipb200_stream", "flipb200_comm_unique_id",
     "flipb200_comm_init", "flipb200_comm_init_local", "flipb200_comm_abort", "flipb200_dd_set_slab", "flipb200_dd_owned",
+    "flipb200_dd_owned_particles",
 ]
 
 
@@ -281,6 +282,11 @@ class World:
         lo, hi = C.c_int(0), C.c_int(0)
         self._ck(self.lib.flipb200_dd_owned(self.h, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
+
+    def dd_owned_particles(self) -> int:
+        n = C.c_uint64(0)
+        self._ck(self.lib.flipb200_dd_owned_particles(self.h, C.byref(n)))
+        return n.value
 
     # -- measurement hooks -----------------------------------------------------------
     def launch_count(self) -> int:

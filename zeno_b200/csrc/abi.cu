@@ -194,6 +194,10 @@ int flipb200_world_destroy(flipb200_world* w) {
         if (!w) return;
         cudaSetDevice(w->device);
         cudaStreamSynchronize(w->stream);
+        if (!w->phase.empty()) {
+            fprintf(stderr, "[flipb200 rank %d] host phases (wall ms total / calls):\n", w->rank);
+            for (auto& kv : w->phase) fprintf(stderr, "  %-28s %10.3f ms  %6llu calls  %8.3f ms/call\n", kv.first.c_str(), kv.second.ms, (unsigned long long)kv.second.launches, kv.second.ms / kv.second.launches);
+        }
         comm_destroy(w);
         dd_destroy(w);
         resolve_profile(w);
@@ -530,17 +534,18 @@ int flipb200_substep(flipb200_world* w, float dt, float dx, int surfaceSize, int
         if (stageMs) for (auto& e : ev) FB_CUDA(cudaEventCreate(&e));
         auto mark = [&](int i) { if (stageMs) FB_CUDA(cudaEventRecord(ev[i], w->stream)); };
         mark(0);
-        g2p_advect_sheetty(w, dt, dx, surfaceSize, rkOrder, picMin, picMax, flags);
+        { FB_PHASE(w, "S1 g2p_advect_rebin"); g2p_advect_sheetty(w, dt, dx, surfaceSize, rkOrder, picMin, picMax, flags); }
         mark(1);
-        p2g(w, dx, velExtraLayer);
+        { FB_PHASE(w, "S2 p2g"); p2g(w, dx, velExtraLayer); }
         mark(2);
-        face_weights(w);
-        pushout_sdf(w, dx);
-        add_vector(w, gx * dt, gy * dt, gz * dt);
+        { FB_PHASE(w, "S3 stencils");
+          face_weights(w);
+          pushout_sdf(w, dx);
+          add_vector(w, gx * dt, gy * dt, gz * dt); }
         mark(3);
-        solve_ppe(w, dt, dx, 5e-5f, 100);
+        { FB_PHASE(w, "S4 solve_ppe"); solve_ppe(w, dt, dx, 5e-5f, 100); }
         mark(4);
-        subtract_grad(w, dt, dx, velExtraLayer);
+        { FB_PHASE(w, "S5 subtract_grad"); subtract_grad(w, dt, dx, velExtraLayer); }
         mark(5);
         sync(w);
         if (stageMs) {

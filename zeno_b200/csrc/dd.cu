@@ -117,6 +117,7 @@ DDMaps& dd_maps(World* w) {
     DDMaps& M = D.maps;
     FB_REQUIRE(w->pool != nullptr, FLIPB200_ERR_STATE, "slab decomposition: no pool yet");
     if (M.epoch == w->pool->epoch) return M;
+    FB_PHASE(w, "dd_maps rebuild");
     const Topo& t = *w->pool;
     const bool hasL = w->rank > 0, hasR = w->rank < w->nRanks - 1;
     const int lo = hasL ? D.lo : -DD_OPEN, hi = hasR ? D.hi : DD_OPEN;
@@ -185,6 +186,7 @@ void dd_refresh(World* w, const std::vector<DDArray>& arrays, int layers) {
     if (!dd_on(w) || arrays.empty()) return;
     FB_REQUIRE((int)arrays.size() <= DD_MAX_ARRAYS && (layers == 1 || layers == 2), FLIPB200_ERR_ARG, "dd_refresh: bad argument");
     DDMaps& M = dd_maps(w);
+    FB_PHASE(w, layers == 1 ? "dd_refresh 1 layer" : "dd_refresh 2 layers");
     const bool has[2] = {w->rank > 0, w->rank < w->nRanks - 1};
     const int peer[2] = {w->rank - 1, w->rank + 1};
     // what I send: to the left the first layers of my slab, to the right the last ones
@@ -244,6 +246,7 @@ void dd_migrate(World* w, uint64_t pLo, uint64_t pHi, const uint32_t* w0, const 
         check_launch("migrate_flags");
     }
     uint64_t cL = 0, cR = 0, cK = 0;
+    FB_PHASE(w, "dd_migrate after flags");
     exclusive_scan_u32(w, fL.p, pL.p, m + 1, &cL);
     exclusive_scan_u32(w, fR.p, pR.p, m + 1, &cR);
     exclusive_scan_u32(w, fK.p, pK.p, m + 1, &cK);
@@ -283,6 +286,23 @@ int flipb200_dd_set_slab(flipb200_world* w, int leafLo, int leafHi) {
         if (!w) return FLIPB200_ERR_ARG;
         cudaSetDevice(w->device);
         fb::dd_set_slab(w, leafLo, leafHi);
+        return FLIPB200_OK;
+    } catch (const fb::Error& e) { fb::set_last_error(e.what()); return e.code; } catch (...) { return FLIPB200_ERR_ARG; }
+}
+int flipb200_dd_owned_particles(flipb200_world* w, uint64_t* n) {
+    try {
+        if (!w || !n || !fb::dd_on(w)) return FLIPB200_ERR_STATE;
+        cudaSetDevice(w->device);
+        *n = 0;
+        if (!w->pts.topo || w->pts.topo != w->pool) return FLIPB200_ERR_STATE;
+        int a = 0, b = 0;
+        fb::dd_owned_slots(w, &a, &b);
+        uint32_t r[2] = {0, 0};
+        if (w->pool->n == 0) return FLIPB200_OK;
+        FB_CUDA(cudaMemcpyAsync(&r[0], w->pts.voxelStart.p + (size_t)a * fb::LEAF, 4, cudaMemcpyDeviceToHost, w->stream));
+        FB_CUDA(cudaMemcpyAsync(&r[1], w->pts.voxelStart.p + (size_t)b * fb::LEAF, 4, cudaMemcpyDeviceToHost, w->stream));
+        fb::sync(w);
+        *n = r[1] - r[0];
         return FLIPB200_OK;
     } catch (const fb::Error& e) { fb::set_last_error(e.what()); return e.code; } catch (...) { return FLIPB200_ERR_ARG; }
 }

@@ -308,6 +308,7 @@ void g2p_advect_sheetty(World* w, float dt, float dx, int surfaceSize, int rkOrd
     GridV& carr = same ? vel : w->V(FLIPB200_VISCOUS_VELOCITY);
     GridF& lsdf = w->F(FLIPB200_LIQUID_SDF);
 
+    FB_PHASE(w, "g2p total");
     // K8 support: dilate5(liquid sdf topology), 26-neighbourhood (FF/FLIP_vdb.cpp:3277-3279)
     DBuf<uint64_t> nm((size_t)nl * 8 + 1, w->stream), nm2((size_t)nl * 8 + 1, w->stream);
     if (w->hasSolidSDF && nl) {
@@ -348,6 +349,7 @@ void g2p_advect_sheetty(World* w, float dt, float dx, int surfaceSize, int rkOrd
     if (dd) dd_owned_slots(w, &leafLo, &leafHi);
     p.leaf0 = leafLo;
     if (leafHi > leafLo && n) {
+        FB_PHASE(w, "g2p kernel");
         // compulsory traffic: 12 B read + 12 B write per particle + the band grids once
         FB_LAUNCH(w, "g2p_advect", n * 24 + (size_t)nl * LEAF * 28 + (size_t)nl * LEAF * 4)
             g2p_advect_kernel<<<leafHi - leafLo, G2P_THREADS, 0, w->stream>>>(p);
@@ -365,19 +367,25 @@ void g2p_advect_sheetty(World* w, float dt, float dx, int surfaceSize, int rkOrd
         DBuf<uint32_t> m0, m1, m2;
         DBuf<int3> mijk;
         uint64_t nm = 0;
-        dd_migrate(w, range[0], range[1], i0.p, i1.p, i2.p, ijk.p, alive.p, m0, m1, m2, mijk, &nm);
+        { FB_PHASE(w, "g2p dd_migrate"); dd_migrate(w, range[0], range[1], i0.p, i1.p, i2.p, ijk.p, alive.p, m0, m1, m2, mijk, &nm); }
         DBuf<int3> morig(nm + 1, w->stream);
-        origins_from_ijk(w, mijk.p, nm, morig.p);
-        TopoPtr newPool = topo_from_origins_dev(w, morig.p, (int)nm, true);
+        TopoPtr newPool;
+        { FB_PHASE(w, "g2p topo");
+          origins_from_ijk(w, mijk.p, nm, morig.p);
+          newPool = topo_from_origins_dev(w, morig.p, (int)nm, true); }
         DBuf<uint32_t> keys(nm + 1, w->stream);
+        FB_PHASE(w, "g2p rebin");
         keys_from_ijk(w, newPool, mijk.p, nullptr, nm, keys.p);
         rebin_particles(w, newPool, keys.p, nm, m0, m1, m2);
         w->pool = newPool;
         return;
     }
     // K2: new pool from the target leaves (+ring), keys, stable counting sort with the voxel cap
-    origins_from_ijk(w, ijk.p, n, origins.p);
-    TopoPtr newPool = topo_from_origins_dev(w, origins.p, (int)n, true);
+    TopoPtr newPool;
+    { FB_PHASE(w, "g2p topo");
+      origins_from_ijk(w, ijk.p, n, origins.p);
+      newPool = topo_from_origins_dev(w, origins.p, (int)n, true); }
+    FB_PHASE(w, "g2p rebin");
     DBuf<uint32_t> keys(n + 1, w->stream);
     keys_from_ijk(w, newPool, ijk.p, alive.p, n, keys.p);
     rebin_particles(w, newPool, keys.p, n, i0, i1, i2);

@@ -1396,6 +1396,7 @@ struct Solver {
     }
     // slab decomposition: assemble level 1 globally, then build and keep the rest of the hierarchy replicated
     void dd_build_coarse() {
+        FB_PHASE(w, "ppe dd_build_coarse");
         FB_REQUIRE(levels[0]->numDof > MAX_COARSEST, FLIPB200_ERR_DOMAIN,
                    "slab decomposition needs at least two multigrid levels (more than 4000 pressure DOFs)");
         std::unique_ptr<Level> loc = coarsen_raw();
@@ -1755,9 +1756,10 @@ struct Solver {
         dd_refresh(w, {DDArray{x, LEAF * 4}}, 1);
         P.b.zero();
         residual_restrict(L, P, x, b, L.ownLo, L.ownHi);
-        comm_allreduce(w, P.b.p, (size_t)P.n * LEAF, CT_F32, false);   // every coarse cell has exactly one non-zero contributor
-        G.mu_cycle_precond(P.x.p, P.b.p, 0, n, true);
-        G.mu_cycle_precond(P.x.p, P.b.p, 0, n, false);
+        { FB_PHASE(w, "ppe allreduce coarse rhs"); comm_allreduce(w, P.b.p, (size_t)P.n * LEAF, CT_F32, false); }   // every coarse cell has exactly one non-zero contributor
+        { FB_PHASE(w, "ppe coarse cycles (2 visits)");
+          G.mu_cycle_precond(P.x.p, P.b.p, 0, n, true);
+          G.mu_cycle_precond(P.x.p, P.b.p, 0, n, false); }
         prolong(L, P, x, 1.0f);
         for (int i = 0; i < n; i++) rbgs(L, x, b, false, wS);
     }
@@ -1897,6 +1899,7 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
     check_launch("rhs");
 
     // solveMultigridPCG (uaamg.cpp:2332-2403)
+    FB_PHASE(w, "ppe pcg loop");
     int status = 1, iter = 0;
     S.residual0(L0, r.p, x.p, rhs.p);
     float nu = S.read_scalar(4);

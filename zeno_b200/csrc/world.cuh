@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 #include "../../include/flipb200.h"
+#include <ctime>
+#include <cstdlib>
 
 namespace fb {
 
@@ -26,6 +28,7 @@ struct flipb200_world {
     uint64_t launches = 0;
     bool profiling = false;
     std::map<std::string, fb::ProfEntry> prof;
+    std::map<std::string, fb::ProfEntry> phase;   // FLIPB200_PHASE_TRACE
     std::vector<fb::PendingEvt> pending;
     std::vector<cudaEvent_t> evtPool;
 
@@ -97,6 +100,19 @@ inline void check_launch(const char* what) {
 }
 void set_last_error(const std::string& m);   // abi.cu: what flipb200_last_error() returns on this thread
 inline void sync(World* w) { FB_CUDA(cudaStreamSynchronize(w->stream)); }
+
+// ---- host-phase trace (FLIPB200_PHASE_TRACE=1): wall clock of named host phases, stream-synchronised on both
+// sides, accumulated per world and printed when the world is destroyed. A diagnosis aid, off by default.
+struct PhaseTimer {
+    World* w; const char* name; double t0 = 0; bool on;
+    static bool enabled() { static const bool e = getenv("FLIPB200_PHASE_TRACE") != nullptr; return e; }
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    PhaseTimer(World* w_, const char* n) : w(w_), name(n), on(enabled()) { if (on) { cudaStreamSynchronize(w->stream); t0 = now(); } }
+    ~PhaseTimer() { if (on) { cudaStreamSynchronize(w->stream); auto& e = w->phase[name]; e.ms += now() - t0; e.launches++; } }
+};
+#define FB_PHASE_CAT2(a, b) a##b
+#define FB_PHASE_CAT(a, b) FB_PHASE_CAT2(a, b)
+#define FB_PHASE(w, name) fb::PhaseTimer FB_PHASE_CAT(phase_, __LINE__)((w), (name))
 
 // ---- topo.cu ------------------------------------------------------------------------
 // Build a topology from candidate leaf-origin voxel coordinates on the device (duplicates

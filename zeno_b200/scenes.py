@@ -21,13 +21,17 @@ def frand(i: np.ndarray) -> np.ndarray:
 
 
 def dam_break_points(N: int, seed: int = 1, ppc: int = 8, W: int = 0, side: int | None = None,
-                     random_velocity: bool = False) -> Tuple[np.ndarray, np.ndarray, float]:
+                     random_velocity: bool = False, box=None) -> Tuple[np.ndarray, np.ndarray, float]:
     """Water cube [W, W+side)^3 voxels in an N^3 tank, dx = 1/N, `ppc` particles per cell placed per
-    octant: p_local = +-0.25 + 0.25*(frand(seed + 3*pid + c) - 0.5). Returns world pos, vel, dx."""
+    octant: p_local = +-0.25 + 0.25*(frand(seed + 3*pid + c) - 0.5). Returns world pos, vel, dx.
+    box = ((x0, x1), (y0, y1), (z0, z1)) voxel ranges replaces the cube (one rank's part of a larger block)."""
     dx = np.float32(1.0 / N)
     side = N // 4 if side is None else side
     ii = np.arange(W, W + side, dtype=np.int64)
-    gx, gy, gz = np.meshgrid(ii, ii, ii, indexing="ij")
+    if box is None:
+        gx, gy, gz = np.meshgrid(ii, ii, ii, indexing="ij")
+    else:
+        gx, gy, gz = np.meshgrid(*[np.arange(a, b, dtype=np.int64) for a, b in box], indexing="ij")
     cells = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], axis=1)  # [V,3]
     V = cells.shape[0]
     reps = (ppc + 7) // 8
