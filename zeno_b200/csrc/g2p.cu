@@ -31,10 +31,26 @@ struct G2PParams {
     float *prePos, *preVel; uint8_t* preAlive;
 };
 
+// The particle's own leaf: most samples fall into it, and then the slot is known without the (dependent) directory load.
+#ifndef FB_G2P_HOME
+#define FB_G2P_HOME 0   // measured on B200: the shortcut branch costs more (4.1 ms) than the directory load it saves (2.4 ms)
+#endif
+struct Home { int leaf; int ox, oy, oz; };
+__device__ __forceinline__ int find_leaf(const TopoView& t, const Home& h, int x, int y, int z) {
+#if FB_G2P_HOME
+    if ((((x ^ h.ox) | (y ^ h.oy) | (z ^ h.oz)) & ~7) == 0) return h.leaf;
+#endif
+    return topo_find(t, x, y, z);
+}
+__device__ __forceinline__ float grid_get_h(const TopoView& t, const Home& h, const float* val, float bg, int vx, int vy, int vz) {
+    int l = find_leaf(t, h, vx, vy, vz);
+    if (l < 0) return bg;
+    return __ldg(&val[(size_t)l * LEAF + voxel_off(vx, vy, vz)]);
+}
 // eight corner values of the cell with base (bx,by,bz); index i*4+j*2+k
-__device__ __forceinline__ void fetch8(const TopoView& t, const float* __restrict__ val, float bg, int bx, int by, int bz, float d[8]) {
+__device__ __forceinline__ void fetch8(const TopoView& t, const Home& h, const float* __restrict__ val, float bg, int bx, int by, int bz, float d[8]) {
     if (((bx & 7) != 7) && ((by & 7) != 7) && ((bz & 7) != 7)) {
-        int l = topo_find(t, bx, by, bz);
+        int l = find_leaf(t, h, bx, by, bz);
         if (l < 0) {
 #pragma unroll
             for (int q = 0; q < 8; q++) d[q] = bg;
@@ -50,17 +66,17 @@ __device__ __forceinline__ void fetch8(const TopoView& t, const float* __restric
 #pragma unroll
         for (int j = 0; j < 2; j++)
 #pragma unroll
-            for (int k = 0; k < 2; k++) d[i * 4 + j * 2 + k] = grid_get(t, val, bg, bx + i, by + j, bz + k);
+            for (int k = 0; k < 2; k++) d[i * 4 + j * 2 + k] = grid_get_h(t, h, val, bg, bx + i, by + j, bz + k);
 }
-__device__ __forceinline__ float solid_get(const G2PParams& p, int x, int y, int z) {
-    int l = topo_find(p.t, x, y, z);
+__device__ __forceinline__ float solid_get(const G2PParams& p, const Home& h, int x, int y, int z) {
+    int l = find_leaf(p.t, h, x, y, z);
     if (l >= 0) return __ldg(&p.solidView[(size_t)l * LEAF + voxel_off(x, y, z)]);
     if (p.st.n > 0) return grid_get(p.st, p.solidStatic, p.solidBg, x, y, z);
     return p.solidBg;
 }
-__device__ __forceinline__ void fetch8_solid(const G2PParams& p, int bx, int by, int bz, float d[8]) {
+__device__ __forceinline__ void fetch8_solid(const G2PParams& p, const Home& h, int bx, int by, int bz, float d[8]) {
     if (((bx & 7) != 7) && ((by & 7) != 7) && ((bz & 7) != 7)) {
-        int l = topo_find(p.t, bx, by, bz);
+        int l = find_leaf(p.t, h, bx, by, bz);
         if (l >= 0) {
             const float* q = p.solidView + (size_t)l * LEAF + voxel_off(bx, by, bz);
             d[0] = __ldg(q); d[1] = __ldg(q + 1); d[2] = __ldg(q + 8); d[3] = __ldg(q + 9);
@@ -73,21 +89,21 @@ __device__ __forceinline__ void fetch8_solid(const G2PParams& p, int bx, int by,
 #pragma unroll
         for (int j = 0; j < 2; j++)
 #pragma unroll
-            for (int k = 0; k < 2; k++) d[i * 4 + j * 2 + k] = solid_get(p, bx + i, by + j, bz + k);
+            for (int k = 0; k < 2; k++) d[i * 4 + j * 2 + k] = solid_get(p, h, bx + i, by + j, bz + k);
 }
 __device__ __forceinline__ float mixf(float a, float b, float w) { return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), w)); }
 // local fp32 sampler (FF/FLIP_vdb.cpp:25-110)
-__device__ __forceinline__ float samplec_f32(const TopoView& t, const float* val, float bg, float x, float y, float z) {
+__device__ __forceinline__ float samplec_f32(const TopoView& t, const Home& h, const float* val, float bg, float x, float y, float z) {
     int bx = (int)floor((double)x), by = (int)floor((double)y), bz = (int)floor((double)z);
     float d[8];
-    fetch8(t, val, bg, bx, by, bz, d);
+    fetch8(t, h, val, bg, bx, by, bz, d);
     float wx = __fsub_rn(x, (float)bx), wy = __fsub_rn(y, (float)by), wz = __fsub_rn(z, (float)bz);
     return mixf(mixf(mixf(d[0], d[1], wz), mixf(d[2], d[3], wz), wy), mixf(mixf(d[4], d[5], wz), mixf(d[6], d[7], wz), wy), wx);
 }
-__device__ __forceinline__ void staggered_f32(const TopoView& t, const float* const v[3], const float q[3], float out[3]) {
-    out[0] = samplec_f32(t, v[0], 0.f, __fadd_rn(q[0], 0.5f), q[1], q[2]);
-    out[1] = samplec_f32(t, v[1], 0.f, q[0], __fadd_rn(q[1], 0.5f), q[2]);
-    out[2] = samplec_f32(t, v[2], 0.f, q[0], q[1], __fadd_rn(q[2], 0.5f));
+__device__ __forceinline__ void staggered_f32(const TopoView& t, const Home& h, const float* const v[3], const float q[3], float out[3]) {
+    out[0] = samplec_f32(t, h, v[0], 0.f, __fadd_rn(q[0], 0.5f), q[1], q[2]);
+    out[1] = samplec_f32(t, h, v[1], 0.f, q[0], __fadd_rn(q[1], 0.5f), q[2]);
+    out[2] = samplec_f32(t, h, v[2], 0.f, q[0], q[1], __fadd_rn(q[2], 0.5f));
 }
 // openvdb BoxSampler, double weights (openvdb/tools/Interpolation.h:712-737)
 __device__ __forceinline__ float ip64(float a, float b, double w) {
@@ -96,52 +112,52 @@ __device__ __forceinline__ float ip64(float a, float b, double w) {
 __device__ __forceinline__ float tri64(const float d[8], double u, double v, double w) {
     return ip64(ip64(ip64(d[0], d[1], w), ip64(d[2], d[3], w), v), ip64(ip64(d[4], d[5], w), ip64(d[6], d[7], w), v), u);
 }
-__device__ __forceinline__ float box_f64(const TopoView& t, const float* val, float bg, double x, double y, double z) {
+__device__ __forceinline__ float box_f64(const TopoView& t, const Home& h, const float* val, float bg, double x, double y, double z) {
     int bx = (int)floor(x), by = (int)floor(y), bz = (int)floor(z);
     float d[8];
-    fetch8(t, val, bg, bx, by, bz, d);
+    fetch8(t, h, val, bg, bx, by, bz, d);
     return tri64(d, __dsub_rn(x, (double)bx), __dsub_rn(y, (double)by), __dsub_rn(z, (double)bz));
 }
-__device__ __forceinline__ float box_f64_solid(const G2PParams& p, double x, double y, double z) {
+__device__ __forceinline__ float box_f64_solid(const G2PParams& p, const Home& h, double x, double y, double z) {
     int bx = (int)floor(x), by = (int)floor(y), bz = (int)floor(z);
     float d[8];
-    fetch8_solid(p, bx, by, bz, d);
+    fetch8_solid(p, h, bx, by, bz, d);
     return tri64(d, __dsub_rn(x, (double)bx), __dsub_rn(y, (double)by), __dsub_rn(z, (double)bz));
 }
-__device__ __forceinline__ void staggered_f64(const TopoView& t, const float* const v[3], const float q[3], float out[3]) {
-    out[0] = box_f64(t, v[0], 0.f, __dadd_rn((double)q[0], 0.5), (double)q[1], (double)q[2]);
-    out[1] = box_f64(t, v[1], 0.f, (double)q[0], __dadd_rn((double)q[1], 0.5), (double)q[2]);
-    out[2] = box_f64(t, v[2], 0.f, (double)q[0], (double)q[1], __dadd_rn((double)q[2], 0.5));
+__device__ __forceinline__ void staggered_f64(const TopoView& t, const Home& h, const float* const v[3], const float q[3], float out[3]) {
+    out[0] = box_f64(t, h, v[0], 0.f, __dadd_rn((double)q[0], 0.5), (double)q[1], (double)q[2]);
+    out[1] = box_f64(t, h, v[1], 0.f, (double)q[0], __dadd_rn((double)q[1], 0.5), (double)q[2]);
+    out[2] = box_f64(t, h, v[2], 0.f, (double)q[0], (double)q[1], __dadd_rn((double)q[2], 0.5));
 }
 // custom_integrator (FF/FLIP_vdb.cpp:169-214)
-__device__ __forceinline__ void integrate(int order, const G2PParams& p, float dtinvx, float ipos[3], const float V0[3]) {
+__device__ __forceinline__ void integrate(int order, const G2PParams& p, const Home& h, float dtinvx, float ipos[3], const float V0[3]) {
     float q[3], V1[3], V2[3], V3[3];
     if (order == 2) {
 #pragma unroll
         for (int a = 0; a < 3; a++) q[a] = __fadd_rn(ipos[a], __fmul_rn(__fmul_rn(0.5f, V0[a]), dtinvx));
-        staggered_f64(p.t, p.vel, q, V1);
+        staggered_f64(p.t, h, p.vel, q, V1);
 #pragma unroll
         for (int a = 0; a < 3; a++) ipos[a] = __fadd_rn(ipos[a], __fmul_rn(V1[a], dtinvx));
     } else if (order == 3) {
 #pragma unroll
         for (int a = 0; a < 3; a++) q[a] = __fadd_rn(ipos[a], __fmul_rn(__fmul_rn(0.5f, V0[a]), dtinvx));
-        staggered_f64(p.t, p.vel, q, V1);
+        staggered_f64(p.t, h, p.vel, q, V1);
 #pragma unroll
         for (int a = 0; a < 3; a++) q[a] = __fadd_rn(ipos[a], __fmul_rn(dtinvx, __fsub_rn(__fmul_rn(2.0f, V1[a]), V0[a])));
-        staggered_f64(p.t, p.vel, q, V2);
+        staggered_f64(p.t, h, p.vel, q, V2);
 #pragma unroll
         for (int a = 0; a < 3; a++)
             ipos[a] = __fadd_rn(ipos[a], __fmul_rn(__fmul_rn(dtinvx, __fadd_rn(__fadd_rn(V0[a], __fmul_rn(4.0f, V1[a])), V2[a])), (1.0f / 6.0f)));
     } else if (order == 4) {
 #pragma unroll
         for (int a = 0; a < 3; a++) q[a] = __fadd_rn(ipos[a], __fmul_rn(__fmul_rn(0.5f, V0[a]), dtinvx));
-        staggered_f64(p.t, p.vel, q, V1);
+        staggered_f64(p.t, h, p.vel, q, V1);
 #pragma unroll
         for (int a = 0; a < 3; a++) q[a] = __fadd_rn(ipos[a], __fmul_rn(__fmul_rn(0.5f, V1[a]), dtinvx));
-        staggered_f64(p.t, p.vel, q, V2);
+        staggered_f64(p.t, h, p.vel, q, V2);
 #pragma unroll
         for (int a = 0; a < 3; a++) q[a] = __fadd_rn(ipos[a], __fmul_rn(V2[a], dtinvx));
-        staggered_f64(p.t, p.vel, q, V3);
+        staggered_f64(p.t, h, p.vel, q, V3);
 #pragma unroll
         for (int a = 0; a < 3; a++)
             ipos[a] = __fadd_rn(ipos[a], __fmul_rn(__fmul_rn(dtinvx, __fadd_rn(__fadd_rn(V0[a], __fmul_rn(2.0f, __fadd_rn(V1[a], V2[a]))), V3[a])), (1.0f / 6.0f)));
@@ -151,9 +167,9 @@ __device__ __forceinline__ void integrate(int order, const G2PParams& p, float d
     }
 }
 // K8 on the fly: normal / on-state of voxel q of the "solidnormal" grid (FF/FLIP_vdb.cpp:3270-3367)
-__device__ bool solid_normal_at(const G2PParams& p, int qx, int qy, int qz, float n[3]) {
+__device__ bool solid_normal_at(const G2PParams& p, const Home& h, int qx, int qy, int qz, float n[3]) {
     n[0] = n[1] = n[2] = 0.f;
-    int l = topo_find(p.t, qx, qy, qz);
+    int l = find_leaf(p.t, h, qx, qy, qz);
     if (l < 0 || !mask_get(p.nmask, l, voxel_off(qx, qy, qz))) return false;
     float data[8];
 #pragma unroll
@@ -161,7 +177,7 @@ __device__ bool solid_normal_at(const G2PParams& p, int qx, int qy, int qz, floa
 #pragma unroll
         for (int b = 0; b < 2; b++)
 #pragma unroll
-            for (int c = 0; c < 2; c++) data[a * 4 + b * 2 + c] = solid_get(p, qx + a, qy + b, qz + c);
+            for (int c = 0; c < 2; c++) data[a * 4 + b * 2 + c] = solid_get(p, h, qx + a, qy + b, qz + c);
     const float dx = p.dx;
     const float s = __fdiv_rn(1.0f, __fmul_rn(dx, dx));
     const float invATA[4] = {__fmul_rn(0.5f, s), __fmul_rn(0.5f, s), __fmul_rn(0.5f, s), __fmul_rn(0.125f, s)};
@@ -188,7 +204,8 @@ __device__ bool solid_normal_at(const G2PParams& p, int qx, int qy, int qz, floa
     return true;
 }
 
-__global__ void __launch_bounds__(G2P_THREADS) g2p_advect_kernel(G2PParams p) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_advect_kernel(G2PParams p) {
     __shared__ uint32_t sStart[LEAF + 1];
     const int leaf = blockIdx.x + p.leaf0;
     const size_t vbase = (size_t)leaf * LEAF;
@@ -197,6 +214,7 @@ __global__ void __launch_bounds__(G2P_THREADS) g2p_advect_kernel(G2PParams p) {
     for (int i = threadIdx.x; i <= LEAF; i += G2P_THREADS) sStart[i] = __ldg(&p.voxelStart[vbase + i]);
     __syncthreads();
     const int3 o = p.t.origin[leaf];
+    const Home h{leaf, o.x, o.y, o.z};
     const float dx = p.dx;
     const float deep_threshold = (float)(-4.0 * (double)dx);
     const float invdx = __fdiv_rn(1.0f, dx);
@@ -212,10 +230,10 @@ __global__ void __launch_bounds__(G2P_THREADS) g2p_advect_kernel(G2PParams p) {
                         __fadd_rn((float)vz, fx_decode(a1 & 0xffffu))};
         float pvel[3] = {h_decode(a1 >> 16), h_decode(a2 & 0xffffu), h_decode(a2 >> 16)};
         float adv[3], old[3], carried[3];
-        staggered_f32(p.t, p.vel, pIs, adv);
-        staggered_f32(p.t, p.oldv, pIs, old);
+        staggered_f32(p.t, h, p.vel, pIs, adv);
+        staggered_f32(p.t, h, p.oldv, pIs, old);
         float flip = __fsub_rn(1.0f, p.picMin);
-        float pls = p.hasLiquid ? box_f64(p.t, p.lsdf, p.lsdfBg, (double)pIs[0], (double)pIs[1], (double)pIs[2]) : p.lsdfBg;
+        float pls = p.hasLiquid ? box_f64(p.t, h, p.lsdf, p.lsdfBg, (double)pIs[0], (double)pIs[1], (double)pIs[2]) : p.lsdfBg;
         float t_coef = 1.f;
         if (pls < 0.f && pls >= -p.surfacedist) {
             t_coef = __fdiv_rn(pls, -p.surfacedist);
@@ -224,28 +242,28 @@ __global__ void __launch_bounds__(G2P_THREADS) g2p_advect_kernel(G2PParams p) {
         if (pls >= 0.f) t_coef = 0.f;
         if (p.surfacedist > 0.f)
             flip = __fadd_rn(__fmul_rn(t_coef, flip), __fmul_rn(__fsub_rn(1.0f, t_coef), fminf(__fsub_rn(1.0f, p.picMax), flip)));
-        float pss = box_f64_solid(p, (double)__fadd_rn(pIs[0], 0.5f), (double)__fadd_rn(pIs[1], 0.5f), (double)__fadd_rn(pIs[2], 0.5f));
+        float pss = box_f64_solid(p, h, (double)__fadd_rn(pIs[0], 0.5f), (double)__fadd_rn(pIs[1], 0.5f), (double)__fadd_rn(pIs[2], 0.5f));
         if (pss >= 0.f && (double)pss <= 2.0 * (double)dx) {
             float scoef = __fdiv_rn(pss, __fmul_rn(2.0f, dx));
             flip = __fadd_rn(__fmul_rn(scoef, flip), __fmul_rn(__fsub_rn(1.0f, scoef), 1.0f));
         }
         if (p.sameField) { carried[0] = adv[0]; carried[1] = adv[1]; carried[2] = adv[2]; }
-        else staggered_f32(p.t, p.carr, pIs, carried);
+        else staggered_f32(p.t, h, p.carr, pIs, carried);
 #pragma unroll
         for (int a = 0; a < 3; a++) pvel[a] = __fadd_rn(carried[a], __fmul_rn(flip, __fadd_rn(-old[a], pvel[a])));
         float pIt[3] = {pIs[0], pIs[1], pIs[2]};
-        if (pls >= -p.surfacedist) integrate(1, p, dtinvx, pIt, adv);
-        else integrate(p.rkOrder, p, dtinvx, pIt, adv);
+        if (pls >= -p.surfacedist) integrate(1, p, h, dtinvx, pIt, adv);
+        else integrate(p.rkOrder, p, h, dtinvx, pIt, adv);
         int pt[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) pt[a] = (int)floor((double)__fadd_rn(pIt[a], 0.5f));
-        float nps = box_f64_solid(p, (double)__fadd_rn(pIt[0], 0.5f), (double)__fadd_rn(pIt[1], 0.5f), (double)__fadd_rn(pIt[2], 0.5f));
+        float nps = box_f64_solid(p, h, (double)__fadd_rn(pIt[0], 0.5f), (double)__fadd_rn(pIt[1], 0.5f), (double)__fadd_rn(pIt[2], 0.5f));
         bool dropped = false;
         if (nps < 0.f) {
             if (nps < deep_threshold) dropped = true;
             else {
                 float sn[3];
-                solid_normal_at(p, pt[0], pt[1], pt[2], sn);
+                solid_normal_at(p, h, pt[0], pt[1], pt[2], sn);
 #pragma unroll
                 for (int a = 0; a < 3; a++) pIt[a] = __fsub_rn(pIt[a], __fmul_rn(__fmul_rn(__fmul_rn(nps, sn[a]), invdx), 1.0f));
 #pragma unroll
@@ -253,8 +271,8 @@ __global__ void __launch_bounds__(G2P_THREADS) g2p_advect_kernel(G2PParams p) {
                 float vnv = 0.f;
                 if (p.hasSolidVel) {
                     float n2[3];
-                    if (solid_normal_at(p, pt[0], pt[1], pt[2], n2)) {
-                        int l = topo_find(p.t, pt[0], pt[1], pt[2]);  // on => inside the pool
+                    if (solid_normal_at(p, h, pt[0], pt[1], pt[2], n2)) {
+                        int l = find_leaf(p.t, h, pt[0], pt[1], pt[2]);  // on => inside the pool
                         size_t k = (size_t)l * LEAF + voxel_off(pt[0], pt[1], pt[2]);
                         vnv = __fadd_rn(__fadd_rn(__fmul_rn(p.svelView[0][k], n2[0]), __fmul_rn(p.svelView[1][k], n2[1])), __fmul_rn(p.svelView[2][k], n2[2]));
                     }
@@ -352,7 +370,12 @@ void g2p_advect_sheetty(World* w, float dt, float dx, int surfaceSize, int rkOrd
         FB_PHASE(w, "g2p kernel");
         // compulsory traffic: 12 B read + 12 B write per particle + the band grids once
         FB_LAUNCH(w, "g2p_advect", n * 24 + (size_t)nl * LEAF * 28 + (size_t)nl * LEAF * 4)
-            g2p_advect_kernel<<<leafHi - leafLo, G2P_THREADS, 0, w->stream>>>(p);
+            {
+                static const int occ = getenv("FLIPB200_G2P_OCC") ? atoi(getenv("FLIPB200_G2P_OCC")) : 5;   // 48 registers, 5 CTAs/SM: 2.23 ms against 2.37 ms at 80 registers / 3 CTAs (B200, 16.8 M particles)
+                if (occ >= 5) g2p_advect_kernel<5><<<leafHi - leafLo, G2P_THREADS, 0, w->stream>>>(p);
+                else if (occ == 4) g2p_advect_kernel<4><<<leafHi - leafLo, G2P_THREADS, 0, w->stream>>>(p);
+                else g2p_advect_kernel<3><<<leafHi - leafLo, G2P_THREADS, 0, w->stream>>>(p);
+            }
         check_launch("g2p_advect");
     }
     DBuf<uint32_t> i0 = std::move(w->pts.w0), i1 = std::move(w->pts.w1), i2 = std::move(w->pts.w2);
