@@ -85,6 +85,17 @@ int flipb200_particles_upload(flipb200_world* w, int nLeaves, const int32_t* ori
                               const uint32_t* voxelEnd, uint64_t nParticles, const uint16_t* P,
                               const uint16_t* v);
 int flipb200_particles_info(flipb200_world* w, int* nLeaves, uint64_t* nParticles);
+/* Asynchronous downloads: *_begin stages the data as of this point of the node sequence and returns the counts; the
+ * device->host copies run on a second stream and overlap the node calls that follow (e.g. particles are final after
+ * G2PAdvectorSheetty and cross PCIe while P2G and the pressure solve run). The host buffers (page-locked, e.g. from
+ * flipb200_host_alloc; their capacities are passed in and FLIPB200_ERR_ARG is returned, before anything is written, if the
+ * data does not fit) are valid after flipb200_download_wait.
+ * This is the lazy write-back a node shim uses when a downstream un-accelerated node needs the OpenVDB object. */
+int flipb200_particles_download_begin(flipb200_world* w, int capLeaves, uint64_t capParticles, int32_t* origins,
+                                      uint32_t* voxelEnd, uint16_t* P, uint16_t* v, int* nLeaves, uint64_t* nParticles);
+int flipb200_grid_download_begin(flipb200_world* w, int grid, int capLeaves, int32_t* origins, uint64_t* masks,
+                                 float* values, int layout, float* background, int* nLeaves);
+int flipb200_download_wait(flipb200_world* w);
 int flipb200_particles_download(flipb200_world* w, int32_t* origins, uint32_t* voxelEnd, uint16_t* P,
                                 uint16_t* v);
 

@@ -95,6 +95,30 @@ def test_particles_roundtrip(gw, traj):
     util.compare_particles(gw.get_particles(), traj["binned"], "upload/download")
 
 
+def test_async_download_matches_blocking(gw, traj):
+    """flipb200_*_download_begin / flipb200_download_wait deliver what the blocking calls deliver, and a begin issued
+    before later nodes returns the state as of the begin"""
+    from zeno_b200 import abi
+    st = traj["steps"][0]
+    restore(gw, st["pre_p2g"])
+    arena = abi.PinnedArena()
+    p_ref = gw.get_particles()
+    bufs = {k: arena.empty([int(v.shape[0] * 1.2) + 4] + list(v.shape[1:]), v.dtype) for k, v in p_ref.items()}
+    p_async = gw.get_particles_begin(bufs)
+    gw.FLIP_P2G(traj["dx"], 3)                      # runs while the particles cross PCIe
+    g_ref = gw.get_grid("Velocity")
+    gb = {k: arena.empty([g_ref["origins"].shape[0] + 3] + list(v.shape[1:]), v.dtype) for k, v in g_ref.items() if k != "bg"}
+    g_async = gw.get_grid_begin("Velocity", gb)
+    gw.CutCellWeight()
+    gw.download_wait()
+    util.compare_particles(p_async, p_ref, "async particle download")
+    util.compare_grids(g_async, g_ref, "async grid download")
+    small = {k: arena.empty([1] + list(v.shape[1:]), v.dtype) for k, v in p_ref.items()}
+    with pytest.raises(abi.FlipB200Error):
+        gw.get_particles_begin(small)
+    gw.download_wait()
+
+
 def test_grid_roundtrip_soa_aos(gw, traj):
     from zeno_b200 import abi
     g = traj["steps"][0]["pre_ppe"]["Velocity"]

@@ -39,6 +39,7 @@ EXPORTS = [
     "flipb200_profile_reset", "flipb200_profile_get", "flipb200_stream", "flipb200_comm_unique_id",
     "flipb200_comm_init", "flipb200_comm_init_local", "flipb200_comm_abort", "flipb200_dd_set_slab", "flipb200_dd_owned",
     "flipb200_dd_owned_particles",
+    "flipb200_particles_download_begin", "flipb200_grid_download_begin", "flipb200_download_wait",
 ]
 
 
@@ -190,6 +191,26 @@ class World:
             v = np.zeros((n, 3), np.uint16)
         self._ck(self.lib.flipb200_particles_download(self.h, _p(o), _p(ve), _p(P), _p(v)))
         return {"origins": o, "voxel_end": ve, "P": P, "v": v}
+
+    # -- asynchronous downloads into caller-provided (pinned) buffers; valid after download_wait() -------------
+    def get_particles_begin(self, out: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+        nl, n = C.c_int(0), C.c_uint64(0)
+        self._ck(self.lib.flipb200_particles_download_begin(self.h, C.c_int(out["origins"].shape[0]), C.c_uint64(out["P"].shape[0]),
+                                                            _p(out["origins"]), _p(out["voxel_end"]), _p(out["P"]), _p(out["v"]),
+                                                            C.byref(nl), C.byref(n)))
+        return {"origins": out["origins"][:nl.value], "voxel_end": out["voxel_end"][:nl.value], "P": out["P"][:n.value], "v": out["v"][:n.value]}
+
+    def get_grid_begin(self, name: str, out: Dict[str, np.ndarray], layout: int = SOA) -> Dict[str, np.ndarray]:
+        gid = GRID_IDS[name]
+        nch = 3 if name in VEC_GRIDS else 1
+        n = C.c_int(0)
+        bg = np.zeros(nch, np.float32)
+        self._ck(self.lib.flipb200_grid_download_begin(self.h, C.c_int(gid), C.c_int(out["origins"].shape[0]), _p(out["origins"]), _p(out["masks"]), _p(out["values"]),
+                                                       C.c_int(layout), _p(bg), C.byref(n)))
+        return {"origins": out["origins"][:n.value], "masks": out["masks"][:n.value], "values": out["values"][:n.value], "bg": bg}
+
+    def download_wait(self):
+        self._ck(self.lib.flipb200_download_wait(self.h))
 
     # -- nodes (names follow the reference's ZENDEFNODE names) ------------------------
     def PrimToVDBPointDataGrid(self, pos: np.ndarray, vel: Optional[np.ndarray] = None):

@@ -135,6 +135,34 @@ __global__ void pts_leaf_flag_kernel(int n, const uint32_t* __restrict__ voxelSt
 }
 inline unsigned nblk(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
+// Where the device->host copies of a download go: the world's stream followed by a sync (blocking calls), or the
+// copy stream behind an event recorded after the staging kernels (the *_begin calls).
+struct Copier {
+    flipb200_world* w; bool async; bool armed = false;
+    template <typename T> T* hold(DBuf<T>&& b) {
+        auto sp = std::make_shared<DBuf<T>>(std::move(b));
+        T* p = sp->p;
+        w->held.push_back(sp);
+        return p;
+    }
+    void arm() {
+        if (!async || armed) return;
+        if (!w->copyStream) {
+            FB_CUDA(cudaStreamCreateWithFlags(&w->copyStream, cudaStreamNonBlocking));
+            FB_CUDA(cudaEventCreateWithFlags(&w->copyEvt, cudaEventDisableTiming));
+        }
+        FB_CUDA(cudaEventRecord(w->copyEvt, w->stream));
+        FB_CUDA(cudaStreamWaitEvent(w->copyStream, w->copyEvt, 0));
+        armed = true;
+    }
+    void d2h(void* dst, const void* src, size_t bytes) {
+        if (!bytes) return;
+        arm();
+        FB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, async ? w->copyStream : w->stream));
+    }
+    void finish() { if (!async) sync(w); }
+};
+
 void resolve_profile(flipb200_world* w) {
     if (w->pending.empty()) return;
     cudaStreamSynchronize(w->stream);
@@ -202,6 +230,7 @@ int flipb200_world_destroy(flipb200_world* w) {
         dd_destroy(w);
         resolve_profile(w);
         for (auto e : w->evtPool) cudaEventDestroy(e);
+        if (w->copyStream) { cudaStreamSynchronize(w->copyStream); w->held.clear(); cudaStreamDestroy(w->copyStream); cudaEventDestroy(w->copyEvt); }
         cudaStream_t s = w->stream;
         delete w;
         cudaStreamSynchronize(s);
@@ -301,46 +330,72 @@ int flipb200_grid_leaf_count(flipb200_world* w, int grid, int* nLeaves) {
         select_leaves(w, grid, flag, pos, nLeaves);
     });
 }
+static void grid_download_impl(flipb200_world* w, int grid, int32_t* origins, uint64_t* masks, float* values, int layout,
+                               float* background, bool async, int* nLeavesOut, int capLeaves = -1) {
+    FB_REQUIRE(w && (is_vec_grid(grid) || is_float_grid(grid)), FLIPB200_ERR_ARG, "grid_download: bad argument");
+    use_device(w);
+    Copier cp{w, async};
+    const int nch = is_vec_grid(grid) ? 3 : 1;
+    if (background) {
+        if (nch == 1) background[0] = w->F(grid).bg;
+        else for (int c = 0; c < 3; c++) background[c] = w->V(grid).bg[c];
+    }
+    DBuf<uint32_t> flag, pos;
+    int cnt = 0;
+    select_leaves(w, grid, flag, pos, &cnt);
+    if (nLeavesOut) *nLeavesOut = cnt;
+    FB_REQUIRE(capLeaves < 0 || cnt <= capLeaves, FLIPB200_ERR_ARG, "grid_download_begin: " + std::to_string(cnt) + " leaves do not fit the caller's buffers");
+    if (cnt == 0) return;
+    TopoPtr t = nch == 3 ? w->V(grid).topo : w->F(grid).topo;
+    DBuf<int3> o(cnt, w->stream);
+    DBuf<uint64_t> m((size_t)cnt * 8, w->stream);
+    DBuf<float> v((size_t)cnt * nch * LEAF, w->stream);
+    const float *c0, *c1 = nullptr, *c2 = nullptr;
+    const uint64_t* mk;
+    if (nch == 3) { c0 = w->V(grid).val[0].p; c1 = w->V(grid).val[1].p; c2 = w->V(grid).val[2].p; mk = w->V(grid).mask.p; }
+    else { c0 = w->F(grid).val.p; mk = w->F(grid).mask.p; }
+    FB_LAUNCH(w, "download_compact", (size_t)cnt * nch * 4096) compact_leaves_kernel<<<t->n, 256, 0, w->stream>>>(t->view(), flag.p, pos.p, c0, c1, c2, nch, mk, o.p, m.p, v.p);
+    check_launch("compact_leaves");
+    const float* vsrc = v.p;
+    if (nch == 3 && layout == FLIPB200_AOS) {
+        // [leaf][3][512] -> [leaf][512][3]: per leaf transposition on the device
+        size_t nVox = (size_t)cnt * LEAF;
+        DBuf<float> planar(3 * nVox, w->stream), aos(3 * nVox, w->stream);
+        for (int c = 0; c < 3; c++)
+            FB_CUDA(cudaMemcpy2DAsync(planar.p + c * nVox, LEAF * 4, v.p + c * LEAF, 3 * LEAF * 4, LEAF * 4, cnt, cudaMemcpyDeviceToDevice, w->stream));
+        FB_LAUNCH(w, "download_soa_to_aos", nVox * 24) soa_to_aos_kernel<<<nblk(nVox, 256), 256, 0, w->stream>>>(planar.p, planar.p + nVox, planar.p + 2 * nVox, aos.p, nVox);
+        check_launch("soa_to_aos");
+        vsrc = async ? cp.hold(std::move(aos)) : aos.p;
+        if (!async) {   // aos dies at the end of this scope: copy + sync here
+            cp.d2h(values, vsrc, sizeof(float) * 3 * nVox);
+            cp.d2h(origins, o.p, sizeof(int3) * (size_t)cnt);
+            cp.d2h(masks, m.p, 64 * (size_t)cnt);
+            cp.finish();
+            return;
+        }
+    }
+    const int3* op = async ? cp.hold(std::move(o)) : o.p;
+    const uint64_t* mp = async ? cp.hold(std::move(m)) : m.p;
+    if (async && vsrc == v.p) vsrc = cp.hold(std::move(v));
+    cp.d2h(origins, op, sizeof(int3) * (size_t)cnt);
+    cp.d2h(masks, mp, 64 * (size_t)cnt);
+    cp.d2h(values, vsrc, sizeof(float) * (size_t)cnt * nch * LEAF);
+    cp.finish();
+}
 int flipb200_grid_download(flipb200_world* w, int grid, int32_t* origins, uint64_t* masks, float* values, int layout,
                            float* background) {
+    return guarded([&] { grid_download_impl(w, grid, origins, masks, values, layout, background, false, nullptr); });
+}
+int flipb200_grid_download_begin(flipb200_world* w, int grid, int capLeaves, int32_t* origins, uint64_t* masks, float* values,
+                                 int layout, float* background, int* nLeaves) {
+    return guarded([&] { grid_download_impl(w, grid, origins, masks, values, layout, background, true, nLeaves, capLeaves < 0 ? 0 : capLeaves); });
+}
+int flipb200_download_wait(flipb200_world* w) {
     return guarded([&] {
-        FB_REQUIRE(w && (is_vec_grid(grid) || is_float_grid(grid)), FLIPB200_ERR_ARG, "grid_download: bad argument");
+        FB_REQUIRE(w, FLIPB200_ERR_ARG, "download_wait: null world");
         use_device(w);
-        const int nch = is_vec_grid(grid) ? 3 : 1;
-        if (background) {
-            if (nch == 1) background[0] = w->F(grid).bg;
-            else for (int c = 0; c < 3; c++) background[c] = w->V(grid).bg[c];
-        }
-        DBuf<uint32_t> flag, pos;
-        int cnt = 0;
-        select_leaves(w, grid, flag, pos, &cnt);
-        if (cnt == 0) return;
-        TopoPtr t = nch == 3 ? w->V(grid).topo : w->F(grid).topo;
-        DBuf<int3> o(cnt, w->stream);
-        DBuf<uint64_t> m((size_t)cnt * 8, w->stream);
-        DBuf<float> v((size_t)cnt * nch * LEAF, w->stream);
-        const float *c0, *c1 = nullptr, *c2 = nullptr;
-        const uint64_t* mk;
-        if (nch == 3) { c0 = w->V(grid).val[0].p; c1 = w->V(grid).val[1].p; c2 = w->V(grid).val[2].p; mk = w->V(grid).mask.p; }
-        else { c0 = w->F(grid).val.p; mk = w->F(grid).mask.p; }
-        FB_LAUNCH(w, "download_compact", (size_t)cnt * nch * 4096) compact_leaves_kernel<<<t->n, 256, 0, w->stream>>>(t->view(), flag.p, pos.p, c0, c1, c2, nch, mk, o.p, m.p, v.p);
-        check_launch("compact_leaves");
-        FB_CUDA(cudaMemcpyAsync(origins, o.p, sizeof(int3) * (size_t)cnt, cudaMemcpyDeviceToHost, w->stream));
-        FB_CUDA(cudaMemcpyAsync(masks, m.p, 64 * (size_t)cnt, cudaMemcpyDeviceToHost, w->stream));
-        if (nch == 3 && layout == FLIPB200_AOS) {
-            // [leaf][3][512] -> [leaf][512][3]: per leaf transposition on the device
-            size_t nVox = (size_t)cnt * LEAF;
-            DBuf<float> planar(3 * nVox, w->stream), aos(3 * nVox, w->stream);
-            for (int c = 0; c < 3; c++)
-                FB_CUDA(cudaMemcpy2DAsync(planar.p + c * nVox, LEAF * 4, v.p + c * LEAF, 3 * LEAF * 4, LEAF * 4, cnt, cudaMemcpyDeviceToDevice, w->stream));
-            FB_LAUNCH(w, "download_soa_to_aos", nVox * 24) soa_to_aos_kernel<<<nblk(nVox, 256), 256, 0, w->stream>>>(planar.p, planar.p + nVox, planar.p + 2 * nVox, aos.p, nVox);
-            check_launch("soa_to_aos");
-            FB_CUDA(cudaMemcpyAsync(values, aos.p, sizeof(float) * 3 * nVox, cudaMemcpyDeviceToHost, w->stream));
-            sync(w);
-        } else {
-            FB_CUDA(cudaMemcpyAsync(values, v.p, sizeof(float) * (size_t)cnt * nch * LEAF, cudaMemcpyDeviceToHost, w->stream));
-            sync(w);
-        }
+        if (w->copyStream) FB_CUDA(cudaStreamSynchronize(w->copyStream));
+        w->held.clear();   // staging buffers go back to the pool in stream order of the world's stream
     });
 }
 
@@ -409,37 +464,55 @@ int flipb200_particles_info(flipb200_world* w, int* nLeaves, uint64_t* nParticle
         }
     });
 }
+static void particles_download_impl(flipb200_world* w, int32_t* origins, uint32_t* voxelEnd, uint16_t* P, uint16_t* v, bool async,
+                                    int* nLeavesOut, uint64_t* nParticlesOut, int64_t capLeaves = -1, int64_t capParticles = -1) {
+    FB_REQUIRE(w, FLIPB200_ERR_ARG, "particles_download: bad argument");
+    use_device(w);
+    Copier cp{w, async};
+    if (nLeavesOut) *nLeavesOut = 0;
+    if (nParticlesOut) *nParticlesOut = 0;
+    if (!w->pts.topo || w->pts.topo->n == 0) return;
+    int n = w->pts.topo->n;
+    uint64_t np = w->pts.n;
+    DBuf<uint32_t> flag(n + 1, w->stream), pos(n + 1, w->stream);
+    flag.zero();
+    pts_leaf_flag_kernel<<<nblk(n, 128), 128, 0, w->stream>>>(n, w->pts.voxelStart.p, flag.p);
+    w->launches++;
+    uint64_t total = 0;
+    exclusive_scan_u32(w, flag.p, pos.p, n + 1, &total);
+    if (nLeavesOut) *nLeavesOut = (int)total;
+    if (nParticlesOut) *nParticlesOut = np;
+    FB_REQUIRE(capLeaves < 0 || ((int64_t)total <= capLeaves && (int64_t)np <= capParticles), FLIPB200_ERR_ARG,
+               "particles_download_begin: " + std::to_string(total) + " leaves / " + std::to_string(np) + " particles do not fit the caller's buffers");
+    if (total) {
+        DBuf<int3> o(total, w->stream);
+        DBuf<uint32_t> ve((size_t)total * LEAF, w->stream);
+        FB_LAUNCH(w, "pts_export", total * 4096) pts_export_kernel<<<n, 256, 0, w->stream>>>(w->pts.topo->view(), flag.p, pos.p, w->pts.voxelStart.p, o.p, ve.p);
+        check_launch("pts_export");
+        const int3* op = async ? cp.hold(std::move(o)) : o.p;
+        const uint32_t* vp = async ? cp.hold(std::move(ve)) : ve.p;
+        cp.d2h(origins, op, sizeof(int3) * total);
+        cp.d2h(voxelEnd, vp, 4 * (size_t)total * LEAF);
+        cp.finish();
+    }
+    if (np) {
+        DBuf<uint16_t> dP(3 * np, w->stream), dv(3 * np, w->stream);
+        FB_LAUNCH(w, "pts_unpack", np * 24) pts_unpack_kernel<<<nblk(np, 256), 256, 0, w->stream>>>(w->pts.w0.p, w->pts.w1.p, w->pts.w2.p, np, dP.p, dv.p);
+        check_launch("pts_unpack");
+        cp.armed = false;   // the copies below must follow the unpack kernel
+        const uint16_t* pp = async ? cp.hold(std::move(dP)) : dP.p;
+        const uint16_t* vp = async ? cp.hold(std::move(dv)) : dv.p;
+        cp.d2h(P, pp, 6 * np);
+        cp.d2h(v, vp, 6 * np);
+        cp.finish();
+    }
+}
 int flipb200_particles_download(flipb200_world* w, int32_t* origins, uint32_t* voxelEnd, uint16_t* P, uint16_t* v) {
-    return guarded([&] {
-        FB_REQUIRE(w, FLIPB200_ERR_ARG, "particles_download: bad argument");
-        use_device(w);
-        if (!w->pts.topo || w->pts.topo->n == 0) return;
-        int n = w->pts.topo->n;
-        uint64_t np = w->pts.n;
-        DBuf<uint32_t> flag(n + 1, w->stream), pos(n + 1, w->stream);
-        flag.zero();
-        pts_leaf_flag_kernel<<<nblk(n, 128), 128, 0, w->stream>>>(n, w->pts.voxelStart.p, flag.p);
-        w->launches++;
-        uint64_t total = 0;
-        exclusive_scan_u32(w, flag.p, pos.p, n + 1, &total);
-        if (total) {
-            DBuf<int3> o(total, w->stream);
-            DBuf<uint32_t> ve((size_t)total * LEAF, w->stream);
-            FB_LAUNCH(w, "pts_export", total * 4096) pts_export_kernel<<<n, 256, 0, w->stream>>>(w->pts.topo->view(), flag.p, pos.p, w->pts.voxelStart.p, o.p, ve.p);
-            check_launch("pts_export");
-            FB_CUDA(cudaMemcpyAsync(origins, o.p, sizeof(int3) * total, cudaMemcpyDeviceToHost, w->stream));
-            FB_CUDA(cudaMemcpyAsync(voxelEnd, ve.p, 4 * (size_t)total * LEAF, cudaMemcpyDeviceToHost, w->stream));
-            sync(w);
-        }
-        if (np) {
-            DBuf<uint16_t> dP(3 * np, w->stream), dv(3 * np, w->stream);
-            FB_LAUNCH(w, "pts_unpack", np * 24) pts_unpack_kernel<<<nblk(np, 256), 256, 0, w->stream>>>(w->pts.w0.p, w->pts.w1.p, w->pts.w2.p, np, dP.p, dv.p);
-            check_launch("pts_unpack");
-            FB_CUDA(cudaMemcpyAsync(P, dP.p, 6 * np, cudaMemcpyDeviceToHost, w->stream));
-            FB_CUDA(cudaMemcpyAsync(v, dv.p, 6 * np, cudaMemcpyDeviceToHost, w->stream));
-            sync(w);
-        }
-    });
+    return guarded([&] { particles_download_impl(w, origins, voxelEnd, P, v, false, nullptr, nullptr); });
+}
+int flipb200_particles_download_begin(flipb200_world* w, int capLeaves, uint64_t capParticles, int32_t* origins, uint32_t* voxelEnd,
+                                      uint16_t* P, uint16_t* v, int* nLeaves, uint64_t* nParticles) {
+    return guarded([&] { particles_download_impl(w, origins, voxelEnd, P, v, true, nLeaves, nParticles, capLeaves < 0 ? 0 : capLeaves, (int64_t)capParticles); });
 }
 
 int flipb200_bin_from_points(flipb200_world* w, const float* pos, const float* vel, uint64_t n) {

@@ -54,6 +54,12 @@ struct flipb200_world {
     uint64_t preCodecN = 0;
 
     fb::SolverStats solver;
+    // asynchronous downloads (flipb200_*_download_begin / flipb200_download_wait): device->host copies run on a
+    // second stream behind an event, so they overlap the nodes that follow; staging buffers are held until the wait
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t copyEvt = nullptr;
+    std::vector<std::shared_ptr<void>> held;
+
     fb::Comm* comm = nullptr;
     int rank = 0, nRanks = 1;
     fb::DDState* dd = nullptr;   // non-null once flipb200_dd_set_slab was called
