@@ -256,8 +256,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, period=float(os.environ.get("FLIPB200_CLOCK_PERIOD", "0.02")))
     launches0 = w.launch_count()
+    syncs0 = w.sync_count()
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -276,6 +277,7 @@ def main():
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = w.launch_count() - launches0
+    host_syncs = w.sync_count() - syncs0
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -387,6 +389,7 @@ def main():
                            "l2": "inputs larger than L2 (>=200 MB particle state per step), no flush",
                            "pcg_iterations": iters, "step_ms_host": step_ms},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "host_syncs_per_step": host_syncs / max(args.steps, 1), "kernel_ms_sum_per_step": sum(x["ms_per_step"] for x in kern.values()),
                 "roofline": roofline, "cpu_baseline": cpu,
                 "stage_ms": {"g2p_advect_rebin": stage_ms[0], "p2g": stage_ms[1], "stencils": stage_ms[2], "mgpcg": stage_ms[3], "gradient": stage_ms[4]},
                 "kernels": {k: v for k, v in top}}

@@ -162,6 +162,8 @@ int flipb200_substep(flipb200_world* w, float dt, float dx, int surfaceSize, int
 /* ---- measurement hooks used by bench.py (device timing on the world's stream) ---- */
 /* number of kernels this library launched since the world was created */
 int flipb200_launch_count(flipb200_world* w, uint64_t* n);
+/* host waits on the world's stream so far (every one is an idle gap on the device) */
+int flipb200_sync_count(flipb200_world* w, uint64_t* n);
 /* per-kernel-family accumulated device time and launch counts since the last reset;
  * names is a ';'-separated list written into buf */
 int flipb200_profile_enable(flipb200_world* w, int on);

@@ -39,7 +39,7 @@ EXPORTS = [
     "flipb200_profile_reset", "flipb200_profile_get", "flipb200_stream", "flipb200_comm_unique_id",
     "flipb200_comm_init", "flipb200_comm_init_local", "flipb200_comm_abort", "flipb200_dd_set_slab", "flipb200_dd_owned",
     "flipb200_dd_owned_particles",
-    "flipb200_particles_download_begin", "flipb200_grid_download_begin", "flipb200_download_wait",
+    "flipb200_sync_count", "flipb200_particles_download_begin", "flipb200_grid_download_begin", "flipb200_download_wait",
 ]
 
 
@@ -313,6 +313,11 @@ class World:
     def launch_count(self) -> int:
         n = C.c_uint64(0)
         self._ck(self.lib.flipb200_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def sync_count(self) -> int:
+        n = C.c_uint64(0)
+        self._ck(self.lib.flipb200_sync_count(self.h, C.byref(n)))
         return n.value
 
     def profile_enable(self, on: bool):

@@ -206,6 +206,7 @@ int flipb200_world_create(int device, float dx, flipb200_world** out) {
         w->device = device;
         w->dx = dx;
         FB_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+        FB_CUDA(cudaHostAlloc((void**)&w->hostScratch, 1024, cudaHostAllocDefault));
         // keep freed blocks in the stream-ordered pool: per-substep temporaries are recycled
         cudaMemPool_t pool;
         FB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -230,6 +231,8 @@ int flipb200_world_destroy(flipb200_world* w) {
         dd_destroy(w);
         resolve_profile(w);
         for (auto e : w->evtPool) cudaEventDestroy(e);
+        if (w->p2gOverflowHost) cudaFreeHost(w->p2gOverflowHost);
+        if (w->hostScratch) cudaFreeHost(w->hostScratch);
         if (w->copyStream) { cudaStreamSynchronize(w->copyStream); w->held.clear(); cudaStreamDestroy(w->copyStream); cudaEventDestroy(w->copyEvt); }
         cudaStream_t s = w->stream;
         delete w;
@@ -404,6 +407,7 @@ int flipb200_particles_upload(flipb200_world* w, int nLeaves, const int32_t* ori
     return guarded([&] {
         FB_REQUIRE(w && nLeaves >= 0, FLIPB200_ERR_ARG, "particles_upload: bad argument");
         use_device(w);
+        reserve_pool(w, ((uint64_t)1 << 30) + 512 * nParticles);
         TopoPtr pool = topo_from_origins_host(w, origins, nLeaves, true);
         const uint64_t n = nParticles;
         DBuf<int3> o(nLeaves + 1, w->stream);
@@ -524,7 +528,7 @@ int flipb200_bin_from_points(flipb200_world* w, const float* pos, const float* v
     });
 }
 int flipb200_p2g(flipb200_world* w, float dx, int velExtraLayer) {
-    return guarded([&] { FB_REQUIRE(w, FLIPB200_ERR_ARG, "p2g: null world"); use_device(w); p2g(w, dx, velExtraLayer); sync(w); });
+    return guarded([&] { FB_REQUIRE(w, FLIPB200_ERR_ARG, "p2g: null world"); use_device(w); p2g(w, dx, velExtraLayer); sync(w); check_p2g_overflow(w); });
 }
 int flipb200_g2p_advect_sheetty(flipb200_world* w, float dt, float dx, int surfaceSize, int rkOrder, float picMin,
                                 float picMax, int flags) {
@@ -621,6 +625,7 @@ int flipb200_substep(flipb200_world* w, float dt, float dx, int surfaceSize, int
         { FB_PHASE(w, "S5 subtract_grad"); subtract_grad(w, dt, dx, velExtraLayer); }
         mark(5);
         sync(w);
+        check_p2g_overflow(w);
         if (stageMs) {
             for (int i = 0; i < 5; i++) FB_CUDA(cudaEventElapsedTime(&stageMs[i], ev[i], ev[i + 1]));
             for (auto& e : ev) cudaEventDestroy(e);
@@ -630,6 +635,9 @@ int flipb200_substep(flipb200_world* w, float dt, float dx, int surfaceSize, int
 
 int flipb200_launch_count(flipb200_world* w, uint64_t* n) {
     return guarded([&] { FB_REQUIRE(w && n, FLIPB200_ERR_ARG, "launch_count: bad argument"); *n = w->launches; });
+}
+int flipb200_sync_count(flipb200_world* w, uint64_t* n) {
+    return guarded([&] { FB_REQUIRE(w && n, FLIPB200_ERR_ARG, "sync_count: bad argument"); *n = w->syncs; });
 }
 int flipb200_profile_enable(flipb200_world* w, int on) {
     return guarded([&] { FB_REQUIRE(w, FLIPB200_ERR_ARG, "profile_enable: null world"); use_device(w); resolve_profile(w); w->profiling = on != 0; });

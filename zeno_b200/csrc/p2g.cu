@@ -300,6 +300,13 @@ void finish_vec3(World* w, GridV& vel, const uint64_t* chMask) {
     check_launch("to_vec3");
 }
 
+void check_p2g_overflow(World* w) {   // call right after a host wait on the stream
+    if (w->p2gOverflowHost && *w->p2gOverflowHost) {
+        *w->p2gOverflowHost = 0;
+        throw Error(FLIPB200_ERR_ARG, "FLIP_P2G: a voxel holds more than 1400 particles");
+    }
+}
+
 // FLIP_P2G::apply (FF/nosys/P2G.cpp:11-42)
 void p2g(World* w, float dx, int velExtraLayer) {
     FB_REQUIRE(w->pts.topo != nullptr, FLIPB200_ERR_STATE, "FLIP_P2G: no particles");
@@ -327,7 +334,12 @@ void p2g(World* w, float dx, int velExtraLayer) {
     }
 
     DBuf<uint64_t> chMask((size_t)3 * n * 8, w->stream), topoMask((size_t)n * 8, w->stream), ring((size_t)n * 8, w->stream);
-    DBuf<int> overflow(1, w->stream);
+    if (!w->p2gOverflowHost) {
+        FB_CUDA(cudaHostAlloc((void**)&w->p2gOverflowHost, sizeof(int), cudaHostAllocDefault));
+        *w->p2gOverflowHost = 0;
+        w->p2gOverflow.alloc(1, w->stream);
+    }
+    DBuf<int>& overflow = w->p2gOverflow;
     overflow.zero();
     P2GParams p;
     p.t = pool->view();
@@ -366,10 +378,7 @@ void p2g(World* w, float dx, int velExtraLayer) {
     union_extrapolate(w, velExtraLayer, nvel, chMask.p, nsdf.mask.p);
     finish_vec3(w, nvel, chMask.p);
 
-    int ov = 0;
-    FB_CUDA(cudaMemcpyAsync(&ov, overflow.p, 4, cudaMemcpyDeviceToHost, w->stream));
-    sync(w);
-    FB_REQUIRE(ov == 0, FLIPB200_ERR_ARG, "FLIP_P2G: a voxel holds more than 1400 particles");
+    FB_CUDA(cudaMemcpyAsync(w->p2gOverflowHost, overflow.p, 4, cudaMemcpyDeviceToHost, w->stream));   // checked by check_p2g_overflow
     vel = std::move(nvel);
     post = std::move(npost);
     sdf = std::move(nsdf);

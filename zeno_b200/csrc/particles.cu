@@ -145,6 +145,7 @@ void sort_by_key(World* w, const TopoPtr& topo, const uint32_t* keys, uint64_t n
 void origins_from_ijk(World* w, const int3* ijk, uint64_t n, int3* origins);
 
 void bin_from_points(World* w, const float* pos_host, const float* vel_host, uint64_t n) {
+    reserve_pool(w, ((uint64_t)1 << 30) + 512 * n);
     DBuf<float> pos(3 * n + 1, w->stream), vel;
     FB_CUDA(cudaMemcpyAsync(pos.p, pos_host, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, w->stream));
     if (vel_host) {

@@ -38,6 +38,10 @@ struct Level {
     DBuf<uint8_t> flags;   // bit0 diag, bit1 x, bit2 y, bit3 z read as the default
     DBuf<LeafInfo> info;
     DBuf<float> x, b;
+    // candidate leaves of the next coarser level, listed speculatively while the DOF count is being read back
+    // (one host wait per level instead of two)
+    DBuf<int3> cand;
+    int candCount = 0;
     int ownLo = 0, ownHi = -1;   // slab decomposition: leaves whose DOFs this rank owns (reductions); -1 = all
 };
 struct LevelView {
@@ -1327,6 +1331,7 @@ struct Solver {
     int compactFirst = 0, scratchOff = 0, cgOff = 0;
     bool cycleReady = false;
     DBuf<uint8_t> cycleProg, cycleProg2;   // visit from a zero guess / from the current iterate
+    std::vector<uint8_t> hostOps, hostOps2;
     int cycleOps = 0, cycleOps2 = 0, cycleGrid = 1;
     // slab decomposition (dd.cu): level 0 lives on this rank's pool, levels >= 1 are assembled globally and
     // replicated on every rank inside `coarse`
@@ -1363,21 +1368,27 @@ struct Solver {
         check_launch("trim");
         FB_LAUNCH(w, "mg_leaf_info", (size_t)L.n * 140) leaf_info_kernel<<<(L.n + 127) / 128, 128, 0, w->stream>>>(L.topo->view(), L.dof.p, L.flags.p, L.info.p);
         check_launch("leaf_info");
-        L.numDof = (int)mask_count(w, L.dof.p, L.n);
+        // DOF count and the coarser level's candidate leaves in one read-back
+        DBuf<unsigned long long> c(2, w->stream);
+        c.zero();
+        mask_count_async(w, L.dof.p, L.n, c.p);
+        L.cand.alloc(L.n + 1, w->stream);
+        FB_LAUNCH(w, "mg_coarse_leaves", (size_t)L.n * 76) dof_leaf_origins_kernel<<<(L.n + 127) / 128, 128, 0, w->stream>>>(L.topo->view(), L.dof.p, L.cand.p, reinterpret_cast<uint32_t*>(c.p + 1));
+        check_launch("dof_leaf_origins");
+        unsigned long long h[2] = {0, 0};
+        read_back(w, h, c.p, 16);
+        L.numDof = (int)h[0];
+        L.candCount = (int)(h[1] & 0xffffffffull);
     }
     std::unique_ptr<Level> coarsen_raw() {
         const Level& F = *levels.back();
-        DBuf<int3> cand(F.n, w->stream);
-        DBuf<uint32_t> cnt(1, w->stream);
-        cnt.zero();
-        FB_LAUNCH(w, "mg_coarse_leaves", (size_t)F.n * 76) dof_leaf_origins_kernel<<<(F.n + 127) / 128, 128, 0, w->stream>>>(F.topo->view(), F.dof.p, cand.p, cnt.p);
-        check_launch("dof_leaf_origins");
-        uint32_t h = 0;
-        FB_CUDA(cudaMemcpyAsync(&h, cnt.p, 4, cudaMemcpyDeviceToHost, w->stream));
-        sync(w);
         auto Lp = std::make_unique<Level>();
         Level& L = *Lp;
-        L.topo = topo_from_origins_dev(w, cand.p, (int)h, false);
+        // coarse leaf coordinate = floor(fine leaf coordinate / 2): the fine directory bounds give the coarse ones
+        const Topo& ft = *F.topo;
+        const int bb[6] = {ft.dmin.x >> 1, ft.dmin.y >> 1, ft.dmin.z >> 1,
+                           (ft.dmin.x + ft.ddim.x - 1) >> 1, (ft.dmin.y + ft.ddim.y - 1) >> 1, (ft.dmin.z + ft.ddim.z - 1) >> 1};
+        L.topo = topo_from_origins_dev(w, F.cand.p, F.candCount, false, bb);
         L.n = L.topo->n;
         L.dx = 2.0f * F.dx;
         L.term = dt / (L.dx * L.dx);
@@ -1564,13 +1575,18 @@ struct Solver {
             H.redStart.alloc(L.n + 1, w->stream); H.blackStart.alloc(L.n + 1, w->stream);
             H.redStart.zero(); H.blackStart.zero();
             FB_LAUNCH(w, "mg_leaf_popcount", (size_t)L.n * 72) leaf_colour_count_kernel<<<(L.n + 127) / 128, 128, 0, w->stream>>>(L.dof.p, L.n, H.redStart.p, H.blackStart.p);
-            uint64_t nRed = 0;
-            exclusive_scan_u32(w, H.redStart.p, H.redStart.p, L.n + 1, &nRed);
+            exclusive_scan_u32(w, H.redStart.p, H.redStart.p, L.n + 1, nullptr);
             exclusive_scan_u32(w, H.blackStart.p, H.blackStart.p, L.n + 1, nullptr);
-            H.nRed = (int)nRed;
             H.blob.alloc(blob_layout(H.np, H.hasChild).bytes, w->stream);
             H.blob.zero();
             H.voxelOfRow.alloc(H.np, w->stream);
+        }
+        {   // red row counts of all compact levels (= the last entry of each exclusive scan) in one host wait
+            uint32_t* nr = reinterpret_cast<uint32_t*>(w->hostScratch);
+            for (size_t i = 0; i < compact.size(); i++)
+                FB_CUDA(cudaMemcpyAsync(&nr[i], compact[i].redStart.p + levels[compactFirst + i]->n, 4, cudaMemcpyDeviceToHost, w->stream));
+            sync(w);
+            for (size_t i = 0; i < compact.size(); i++) compact[i].nRed = (int)nr[i];
         }
         auto rowmap = [&](int l) {
             const CompactHost& H = compact[l - compactFirst];
@@ -1612,17 +1628,17 @@ struct Solver {
         cgOff = (int)cursor; cursor += (size_t)8 * compact.back().np;
         cycleSmem = std::max<size_t>(cursor, (size_t)scratchOff + CYC_GRID_SCRATCH);
         if (cycleSmem > cap) return;
-        std::vector<uint8_t> ops;
+        std::vector<uint8_t>& ops = hostOps;    // members: the asynchronous copies below read them after this returns
+        std::vector<uint8_t>& ops2 = hostOps2;
+        ops.clear(); ops2.clear();
         emit_cycle(ops, 0, n, true);
         cycleOps = (int)ops.size();
         cycleProg.alloc(ops.size(), w->stream);
         FB_CUDA(cudaMemcpyAsync(cycleProg.p, ops.data(), ops.size(), cudaMemcpyHostToDevice, w->stream));
-        std::vector<uint8_t> ops2;
         emit_cycle(ops2, 0, n, false);
         cycleOps2 = (int)ops2.size();
         cycleProg2.alloc(ops2.size() + 1, w->stream);
         if (cycleOps2) FB_CUDA(cudaMemcpyAsync(cycleProg2.p, ops2.data(), ops2.size(), cudaMemcpyHostToDevice, w->stream));
-        sync(w);  // ops, ops2 are host temporaries
         cycleBarrier.alloc(1, w->stream);
         FB_CUDA(cudaFuncSetAttribute(mg_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cycleSmem));
         FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, mg_cycle_kernel, BOT_THREADS, cycleSmem));
@@ -1826,8 +1842,7 @@ struct Solver {
     }
     float read_scalar(int slot) {
         float h = 0.f;
-        FB_CUDA(cudaMemcpyAsync(&h, scal.p + slot, 4, cudaMemcpyDeviceToHost, w->stream));
-        sync(w);
+        read_back(w, &h, scal.p + slot, 4);
         return h;
     }
 };

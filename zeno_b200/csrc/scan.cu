@@ -81,8 +81,7 @@ void exclusive_scan_u32(World* w, const uint32_t* in, uint32_t* out, size_t n, u
     scan_rec(w, in, out, n, tot.p);
     if (total) {
         uint32_t h = 0;
-        FB_CUDA(cudaMemcpyAsync(&h, tot.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
-        sync(w);
+        read_back(w, &h, tot.p, sizeof(uint32_t));
         *total = h;
     }
 }

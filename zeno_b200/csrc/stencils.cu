@@ -248,8 +248,7 @@ float cfl(World* w) {
     }
     if (dd_on(w)) comm_allreduce(w, m.p, 1, CT_U32, true);   // bit patterns of non-negative floats order like the floats
     unsigned h = 0;
-    FB_CUDA(cudaMemcpyAsync(&h, m.p, 4, cudaMemcpyDeviceToHost, w->stream));
-    sync(w);
+    read_back(w, &h, m.p, 4);
     float mv;
     memcpy(&mv, &h, 4);
     // see oracle/stencils.cpp node_CFL_dt: the value the reference reads is the global maximum

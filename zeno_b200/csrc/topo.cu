@@ -176,21 +176,24 @@ __global__ void solid_view_kernel(TopoView pool, TopoView st, const float* __res
 
 static inline unsigned nblk(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
-TopoPtr topo_from_origins_dev(World* w, const int3* origins_dev, int count, bool ring) {
+TopoPtr topo_from_origins_dev(World* w, const int3* origins_dev, int count, bool ring, const int* bbox) {
     auto t = std::make_shared<Topo>();
     t->epoch = ++w->epochCounter;
     if (count == 0) {
         t->n = 0; t->dmin = make_int3(0, 0, 0); t->ddim = make_int3(0, 0, 0);
         return t;
     }
-    DBuf<int> bb(6, w->stream);
-    int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
-    FB_CUDA(cudaMemcpyAsync(bb.p, init, sizeof(init), cudaMemcpyHostToDevice, w->stream));
-    FB_LAUNCH(w, "topo_bbox", count * 12) bbox_kernel<<<std::min<unsigned>(nblk(count, BBOX_THREADS), 148 * 8), BBOX_THREADS, 0, w->stream>>>(origins_dev, count, bb.p);
-    check_launch("bbox");
     int h[6];
-    FB_CUDA(cudaMemcpyAsync(h, bb.p, sizeof(h), cudaMemcpyDeviceToHost, w->stream));
-    sync(w);
+    if (bbox) {
+        for (int k = 0; k < 6; k++) h[k] = bbox[k];
+    } else {
+        DBuf<int> bb(6, w->stream);
+        int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+        FB_CUDA(cudaMemcpyAsync(bb.p, init, sizeof(init), cudaMemcpyHostToDevice, w->stream));
+        FB_LAUNCH(w, "topo_bbox", count * 12) bbox_kernel<<<std::min<unsigned>(nblk(count, BBOX_THREADS), 148 * 8), BBOX_THREADS, 0, w->stream>>>(origins_dev, count, bb.p);
+        check_launch("bbox");
+        read_back(w, h, bb.p, sizeof(h));
+    }
     int r = ring ? 1 : 0;
     t->dmin = make_int3(h[0] - r, h[1] - r, h[2] - r);
     t->ddim = make_int3(h[3] - h[0] + 1 + 2 * r, h[4] - h[1] + 1 + 2 * r, h[5] - h[2] + 1 + 2 * r);
@@ -324,8 +327,7 @@ void ensure_pool(World* w, std::initializer_list<int> gridIds, bool includeParti
             check_launch("particle_leaf_origins");
         }
         uint32_t cnt = 0;
-        FB_CUDA(cudaMemcpyAsync(&cnt, counter.p, 4, cudaMemcpyDeviceToHost, w->stream));
-        sync(w);
+        read_back(w, &cnt, counter.p, 4);
         w->pool = topo_from_origins_dev(w, cand.p, (int)cnt, /*ring=*/true);
     }
     for (int id : gridIds) {
@@ -379,6 +381,12 @@ void mask_dilate(World* w, const Topo& t, const uint64_t* in, uint64_t* out, boo
     FB_LAUNCH(w, "mask_dilate", (size_t)t.n * 128) dilate_kernel<<<t.n, 512, 0, w->stream>>>(t.view(), in, out, nn26 ? 1 : 0);
     check_launch("dilate");
 }
+void mask_count_async(World* w, const uint64_t* mask, int nLeaves, unsigned long long* out) {
+    size_t nw = (size_t)nLeaves * 8;
+    if (!nw) return;
+    FB_LAUNCH(w, "mask_count", nw * 8) popcount_kernel<<<nblk(nw, 256), 256, 0, w->stream>>>(mask, nw, out);
+    check_launch("popcount");
+}
 uint64_t mask_count(World* w, const uint64_t* mask, int nLeaves) {
     DBuf<unsigned long long> c(1, w->stream);
     c.zero();
@@ -388,8 +396,7 @@ uint64_t mask_count(World* w, const uint64_t* mask, int nLeaves) {
         check_launch("popcount");
     }
     unsigned long long h = 0;
-    FB_CUDA(cudaMemcpyAsync(&h, c.p, 8, cudaMemcpyDeviceToHost, w->stream));
-    sync(w);
+    read_back(w, &h, c.p, 8);
     return h;
 }
 

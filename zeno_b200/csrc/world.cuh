@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "../../include/flipb200.h"
 #include <ctime>
+#include <cstring>
 #include <cstdlib>
 
 namespace fb {
@@ -26,6 +27,7 @@ struct flipb200_world {
     float dx = 0.f;
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
+    uint64_t syncs = 0;      // host waits on the stream (each one is a bubble on the device)
     bool profiling = false;
     std::map<std::string, fb::ProfEntry> prof;
     std::map<std::string, fb::ProfEntry> phase;   // FLIPB200_PHASE_TRACE
@@ -46,6 +48,16 @@ struct flipb200_world {
     fb::DBuf<float> solidSdfView;        // [pool n][512]
     fb::DBuf<float> solidVelView[3];     // [pool n][512]
     fb::DBuf<uint8_t> solidLeafExists;   // [pool n]
+
+    // FLIP_P2G's staging-overflow flag: written by the kernel, copied to page-locked host memory in stream order and
+    // checked at the next host wait that happens anyway (flipb200_p2g / flipb200_substep), not with a wait of its own
+    fb::DBuf<int> p2gOverflow;
+    int* p2gOverflowHost = nullptr;
+
+    // page-locked scratch for the few-byte read-backs (a pageable destination makes the driver stage the copy)
+    unsigned char* hostScratch = nullptr;   // 1 KB, allocated by flipb200_world_create
+
+    uint64_t reservedBytes = 0;   // device memory parked in the stream-ordered pool (reserve_pool)
 
     uint64_t dropped = 0;
     bool capturePreCodec = false;
@@ -104,8 +116,28 @@ inline void check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw Error(2, std::string(what) + ": " + cudaGetErrorString(e));
 }
+// Read a few bytes back and wait for them (the data-dependent sizes of the path: leaf counts, totals, the PCG norm).
+// part k of a multi-part read-back goes to scratch offset `at`; the last part waits and the caller copies out.
+inline void read_back(World* w, void* dst, const void* src, size_t bytes) {
+    FB_CUDA(cudaMemcpyAsync(w->hostScratch, src, bytes, cudaMemcpyDeviceToHost, w->stream));
+    w->syncs++;
+    FB_CUDA(cudaStreamSynchronize(w->stream));
+    memcpy(dst, w->hostScratch, bytes);
+}
+// Park `bytes` of device memory in the stream-ordered pool (allocate once, free: the release threshold keeps it), so
+// that the per-substep temporaries -- whose sizes creep up as the fluid spreads -- never make the pool map new physical
+// memory in the middle of a step (measured: occasional 20-500 ms substeps at 16.8 M particles without it).
+inline void reserve_pool(World* w, uint64_t bytes) {
+    if (bytes <= w->reservedBytes) return;
+    size_t freeB = 0, totalB = 0;
+    if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess && bytes > freeB / 2) bytes = freeB / 2;
+    if (bytes <= w->reservedBytes) return;
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, bytes, w->stream) == cudaSuccess) { cudaFreeAsync(p, w->stream); w->reservedBytes = bytes; }
+    else cudaGetLastError();
+}
 void set_last_error(const std::string& m);   // abi.cu: what flipb200_last_error() returns on this thread
-inline void sync(World* w) { FB_CUDA(cudaStreamSynchronize(w->stream)); }
+inline void sync(World* w) { w->syncs++; FB_CUDA(cudaStreamSynchronize(w->stream)); }
 
 // ---- host-phase trace (FLIPB200_PHASE_TRACE=1): wall clock of named host phases, stream-synchronised on both
 // sides, accumulated per world and printed when the world is destroyed. A diagnosis aid, off by default.
@@ -123,7 +155,9 @@ struct PhaseTimer {
 // ---- topo.cu ------------------------------------------------------------------------
 // Build a topology from candidate leaf-origin voxel coordinates on the device (duplicates
 // allowed). ring: also add the 26 neighbour leaves of every candidate.
-TopoPtr topo_from_origins_dev(World* w, const int3* origins_dev, int count, bool ring);
+// bbox (optional): leaf-coordinate bounds {xmin,ymin,zmin,xmax,ymax,zmax} known to contain every candidate; saves the
+// bounding-box kernel and its host read-back (the directory may then be larger than tight, slot order is unaffected).
+TopoPtr topo_from_origins_dev(World* w, const int3* origins_dev, int count, bool ring, const int* bbox = nullptr);
 TopoPtr topo_from_origins_host(World* w, const int32_t* origins, int count, bool ring);
 void grid_alloc(World* w, GridF& g, const TopoPtr& t, float bg);              // values = bg, mask = 0
 void grid_alloc(World* w, GridV& g, const TopoPtr& t, const float bg[3]);
@@ -138,6 +172,8 @@ void refresh_solid_views(World* w);
 // mask morphology on the pool: out = dilate(in) (26- or 6-neighbourhood), in/out may not alias
 void mask_dilate(World* w, const Topo& t, const uint64_t* in, uint64_t* out, bool nn26);
 uint64_t mask_count(World* w, const uint64_t* mask, int nLeaves);
+// asynchronous form: adds the popcount to *out (device, zeroed by the caller); no host wait
+void mask_count_async(World* w, const uint64_t* mask, int nLeaves, unsigned long long* out);
 
 // ---- scan.cu ------------------------------------------------------------------------
 // exclusive prefix sum of n uint32 (out may alias in); total (if non-null) receives the sum on the host
@@ -151,6 +187,7 @@ void rebin_particles(World* w, const TopoPtr& newPool, const uint32_t* keys_dev,
 
 // ---- p2g.cu / g2p.cu / stencils.cu / poisson.cu --------------------------------------
 void p2g(World* w, float dx, int velExtraLayer);
+void check_p2g_overflow(World* w);
 void g2p_advect_sheetty(World* w, float dt, float dx, int surfaceSize, int rkOrder, float picMin,
                         float picMax, int flags);
 void face_weights(World* w);
