@@ -334,7 +334,23 @@ def main():
         pts = {k: arena.like(v) for k, v in w.get_particles().items()}
         # pinned result buffers with head-room (the fluid spreads: leaf counts grow a little every step)
         out_state = {g: {k: (arena.like(v, 1.5) if k != "bg" else v) for k, v in state[g].items()} for g in STATE_GRIDS}
-        out_pts = {k: arena.like(v, 1.5 if k in ("origins", "voxel_end") else 1.0) for k, v in pts.items()}
+        # (under the decomposition a rank's particle count includes its ghost layers and moves both ways)
+        out_pts = {k: arena.like(v, 1.5 if k in ("origins", "voxel_end") else (1.0 if world == 1 else 1.3)) for k, v in pts.items()}
+
+        # a result that outgrows its pinned buffer falls back to the blocking download: no rank may raise on its own
+        # here, its peers would wait for it in the next collective
+        def particles_begin():
+            try:
+                return w.get_particles_begin(out_pts)
+            except abi.FlipB200Error:
+                return w.get_particles()
+
+        def grid_begin(g):
+            try:
+                return w.get_grid_begin(g, out_state[g])
+            except abi.FlipB200Error:
+                return w.get_grid(g)
+
         h2d = sum(v.nbytes for d in state.values() for v in d.values()) + sum(v.nbytes for v in pts.values())
         E_STEPS = max(1, min(args.steps, 5))
         barrier()
@@ -349,15 +365,15 @@ def main():
             # final (particles after the advection, PostAdvVelocity / LiquidSDF after the push-out) and overlaps the solve
             dt = substep_dt(w, dx)
             w.G2PAdvectorSheetty(dt, dx, 4, 3, 0.03, 0.05, True)
-            out_p = w.get_particles_begin(out_pts)
+            out_p = particles_begin()
             w.FLIP_P2G(dx, 3)
             w.CutCellWeight()
             w.PushOutLiquidSDF(dx)
-            out_g = {g: w.get_grid_begin(g, out_state[g]) for g in ("PostAdvVelocity", "LiquidSDF")}
+            out_g = {g: grid_begin(g) for g in ("PostAdvVelocity", "LiquidSDF")}
             w.FieldAddVector(GRAVITY[0] * dt, GRAVITY[1] * dt, GRAVITY[2] * dt)
             w.AssembleSolvePPE(dt, dx)
             w.SubtractPressureGradient(dt, dx, 3)
-            out_g["Velocity"] = w.get_grid_begin("Velocity", out_state["Velocity"])
+            out_g["Velocity"] = grid_begin("Velocity")
             w.download_wait()
             d2h = sum(v.nbytes for v in out_p.values()) + sum(v.nbytes for d in out_g.values() for v in d.values())
             psteps += out_p["P"].shape[0] if world == 1 else owned_particles()
@@ -401,4 +417,18 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # A rank that fails must take the whole job down at once: its peers are (or will be) waiting for it inside a
+    # collective, and a normal interpreter shutdown would itself wait in the communicator's destructor. The watchdog
+    # bounds any other hang (FLIPB200_BENCH_TIMEOUT seconds, default 900).
+    import traceback
+    _wd = threading.Timer(float(os.environ.get("FLIPB200_BENCH_TIMEOUT", "900")), lambda: (sys.stderr.write("bench.py: watchdog timeout\n"), sys.stderr.flush(), os._exit(3)))
+    _wd.daemon = True
+    _wd.start()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
