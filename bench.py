@@ -320,7 +320,9 @@ def main():
         except Exception:
             traffic = None
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": d["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
-                    "frac": d["frac"], "traffic": traffic, "algorithmic_bytes_per_launch": prof[dominant]["bytes"] / max(prof[dominant]["launches"], 1),
+                    "frac": d["frac"], "traffic": traffic,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch (profiles/r01f_ncu_full_*; the mg_cycle capture predates the compact-row bottom of the cycle kernel)" if traffic is not None else None,
+                    "algorithmic_bytes_per_launch": prof[dominant]["bytes"] / max(prof[dominant]["launches"], 1),
                     "peak_source": peak_src, "avg_launch_us": d["avg_us"],
                     "share_of_step": d["ms_per_step"] / max(sum(x["ms_per_step"] for x in kern.values()), 1e-9),
                     "measured": f"CUDA events around every launch of the family over {PROF_STEPS} substeps following the timed region"}
