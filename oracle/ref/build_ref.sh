@@ -23,7 +23,8 @@ CXX=${REF_CXX:-$(test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)}
 VDB="$REF/projects/zenvdb/openvdb/openvdb"
 FF="$REF/projects/FastFLIP"
 [ -d "$REF" ] || { echo "no $REF: keeping the prebuilt oracle/_ref"; exit 0; }
-if [ -f "$OUT/libflipref.so" ] && [ "$OUT/libflipref.so" -nt "$HERE/ref_driver.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/shims/Eigen/Eigen" ] && [ -z "$FORCE" ]; then
+PLUGIN_SRC="$HERE/../../zeno_b200/plugin/flipb200_nodes.cpp"
+if [ -f "$OUT/libflipref.so" ] && [ "$OUT/libflipref.so" -nt "$HERE/ref_driver.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/shims/Eigen/Eigen" ] && [ "$OUT/libflipref.so" -nt "$PLUGIN_SRC" ] && [ -z "$FORCE" ]; then
   echo "oracle/_ref/libflipref.so is up to date"; exit 0
 fi
 mkdir -p "$OUT" "$BUILD/gen/openvdb" "$BUILD/vdbobj" "$BUILD/ffobj"
@@ -61,11 +62,11 @@ done
 xargs -P "$JOBS" -d '\n' -I{} bash -c {} < "$BUILD/cmds.txt" || { echo "openvdb compile failed"; exit 1; }
 
 # ---- 4. the reference FastFLIP sources, unmodified, with the reference's flags (FF/CMakeLists.txt:56: -mavx -mfma)
-FFFLAGS="$COMMON -mavx -mfma -DZENO_APIFREE -I$HERE/shims/zeno_min -I$REF/projects/zenvdb/include -I$REF/zeno/include -I$FF"
+FFFLAGS="$COMMON -mavx -mfma -DZENO_APIFREE -I$HERE/shims/zeno_min -I$REF/projects/zenvdb/include -I$REF/zeno/include -I$FF -I$HERE/../../include"
 : > "$BUILD/cmds.txt"
 for s in "$FF/FLIP_vdb.cpp" "$FF/simd_vdb_poisson_uaamg.cpp" "$FF/vdb_velocity_extrapolator.cpp" "$FF/levelset_util.cpp" "$REF/projects/zenvdb/include/zeno/packed3grids.cpp" "$HERE/ref_driver.cpp" "$HERE/ref_stubs.cpp"; do
   o="$BUILD/ffobj/$(basename $s .cpp).o"
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ "$HERE/shims/Eigen/Eigen" -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ "$HERE/shims/Eigen/Eigen" -nt "$o" ] || { [ "$(basename $s)" = "ref_driver.cpp" ] && [ "$HERE/../../zeno_b200/plugin/flipb200_nodes.cpp" -nt "$o" ]; }; then
     echo "$CXX $FFFLAGS -c $s -o $o 2> $o.log || { grep -m 30 -E 'error|Error' $o.log; exit 255; }" >> "$BUILD/cmds.txt"
   fi
 done

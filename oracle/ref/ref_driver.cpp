@@ -227,13 +227,15 @@ int ref_particles_set(void* wp, int nLeaves, const int32_t* origins, const uint3
                       const uint16_t* P, const uint16_t* v) {
     RefWorld* w = static_cast<RefWorld*>(wp);
     auto descr = particleDescriptor();
+    auto pdescr = openvdb::points::AttributeSet::Descriptor::create(FLIP_vdb::position_attribute::attributeType());
     auto tree = std::make_shared<openvdb::points::PointDataTree>();
     uint64_t begin = 0;
     for (int l = 0; l < nLeaves; l++) {
         auto* leaf = tree->touchLeaf(Coord(origins[3 * l], origins[3 * l + 1], origins[3 * l + 2]));
         const uint32_t* ve = voxelEnd + size_t(l) * 512;
         const uint32_t cnt = ve[511];
-        leaf->initializeAttributes(descr, cnt);
+        leaf->initializeAttributes(pdescr, cnt);   // only the position descriptor is accepted here; "v" is appended (FF/FLIP_vdb.cpp:3455-3460)
+        leaf->appendAttribute(leaf->attributeSet().descriptor(), descr, 1);
         std::vector<openvdb::PointDataIndex32> offs(512);
         for (int i = 0; i < 512; i++) offs[i] = openvdb::PointDataIndex32(ve[i]);
         leaf->setOffsets(offs, /*updateValueMask=*/true);
@@ -451,3 +453,159 @@ int ref_substep(void* wp, float dt, float dx, int surfaceSize, int rkOrder, floa
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// Marshalling test of the Zeno-side drop-in (zeno_b200/plugin/flipb200_nodes.cpp): its upload()/download() /
+// upload_particles()/download_particles() are compiled here against a LOOPBACK C ABI (the flipb200_* entry points it
+// calls are renamed to lb_* and implemented below: they keep the flat leaf arrays and hand them back with the leaves
+// in REVERSE order, as a device library is free to reorder them), and REAL reference objects -- the grids and the
+// particle tree this world holds after reference nodes ran -- are round-tripped through them.
+#define FLIPB200_PLUGIN_MARSHAL_ONLY
+#define FLIPB200_HAVE_TEST_ATTRIBUTE_ARRAY
+#define flipb200_last_error lb_last_error
+#define flipb200_world_create lb_world_create
+#define flipb200_world_destroy lb_world_destroy
+#define flipb200_grid_upload lb_grid_upload
+#define flipb200_grid_leaf_count lb_grid_leaf_count
+#define flipb200_grid_download lb_grid_download
+#define flipb200_particles_upload lb_particles_upload
+#define flipb200_particles_info lb_particles_info
+#define flipb200_particles_download lb_particles_download
+#include <map>
+#include "../../zeno_b200/plugin/flipb200_nodes.cpp"
+
+struct flipb200_world {
+    struct G { int n = 0, nch = 1, layout = 0; std::vector<int32_t> o; std::vector<uint64_t> m; std::vector<float> v; float bg[3] = {0, 0, 0}; };
+    std::map<int, G> grids;
+    int nl = 0;
+    uint64_t np = 0;
+    std::vector<int32_t> po;
+    std::vector<uint32_t> ve;
+    std::vector<uint16_t> P, V;
+};
+extern "C" {
+const char* lb_last_error(void) { return "loopback"; }
+int lb_world_create(int, float, flipb200_world** out) { *out = new flipb200_world(); return 0; }
+int lb_world_destroy(flipb200_world* w) { delete w; return 0; }
+int lb_grid_upload(flipb200_world* w, int grid, int n, const int32_t* o, const uint64_t* m, const float* v, int layout, const float* bg) {
+    auto& g = w->grids[grid];
+    g.n = n; g.nch = grid <= FLIPB200_FACE_WEIGHT ? 3 : 1; g.layout = layout;
+    g.o.assign(o, o + 3 * size_t(n)); g.m.assign(m, m + 8 * size_t(n)); g.v.assign(v, v + size_t(512) * g.nch * n);
+    for (int c = 0; c < g.nch; c++) g.bg[c] = bg[c];
+    return 0;
+}
+int lb_grid_leaf_count(flipb200_world* w, int grid, int* n) { *n = w->grids[grid].n; return 0; }
+int lb_grid_download(flipb200_world* w, int grid, int32_t* o, uint64_t* m, float* v, int layout, float* bg) {
+    auto& g = w->grids[grid];
+    if (layout != g.layout) return 1;
+    const size_t per = size_t(512) * g.nch;
+    for (int i = 0; i < g.n; i++) {   // reversed leaf order
+        const int s = g.n - 1 - i;
+        std::memcpy(o + 3 * size_t(i), &g.o[3 * size_t(s)], 12);
+        std::memcpy(m + 8 * size_t(i), &g.m[8 * size_t(s)], 64);
+        std::memcpy(v + per * i, &g.v[per * s], per * 4);
+    }
+    for (int c = 0; c < g.nch; c++) bg[c] = g.bg[c];
+    return 0;
+}
+int lb_particles_upload(flipb200_world* w, int nl, const int32_t* o, const uint32_t* ve, uint64_t np, const uint16_t* P, const uint16_t* V) {
+    w->nl = nl; w->np = np;
+    w->po.assign(o, o + 3 * size_t(nl)); w->ve.assign(ve, ve + 512 * size_t(nl));
+    w->P.assign(P, P + 3 * np); w->V.assign(V, V + 3 * np);
+    return 0;
+}
+int lb_particles_info(flipb200_world* w, int* nl, uint64_t* np) { *nl = w->nl; *np = w->np; return 0; }
+int lb_particles_download(flipb200_world* w, int32_t* o, uint32_t* ve, uint16_t* P, uint16_t* V) {
+    // reversed leaf order; the attribute arrays follow the leaves
+    std::vector<uint64_t> begin(size_t(w->nl) + 1, 0);
+    for (int i = 0; i < w->nl; i++) begin[i + 1] = begin[i] + w->ve[512 * size_t(i) + 511];
+    uint64_t at = 0;
+    for (int i = 0; i < w->nl; i++) {
+        const int s = w->nl - 1 - i;
+        std::memcpy(o + 3 * size_t(i), &w->po[3 * size_t(s)], 12);
+        std::memcpy(ve + 512 * size_t(i), &w->ve[512 * size_t(s)], 2048);
+        const uint64_t cnt = begin[s + 1] - begin[s];
+        std::memcpy(P + 3 * at, &w->P[3 * begin[s]], cnt * 6);
+        std::memcpy(V + 3 * at, &w->V[3 * begin[s]], cnt * 6);
+        at += cnt;
+    }
+    return 0;
+}
+}  // extern "C"
+
+namespace {
+template <typename GridT>
+bool sameGrid(const GridT& a, const GridT& b, std::string& why, const char* name) {
+    using Leaf = typename GridT::TreeType::LeafNodeType;
+    if (!(a.background() == b.background())) { why = std::string(name) + ": background differs"; return false; }
+    if (a.tree().leafCount() != b.tree().leafCount()) { why = std::string(name) + ": leaf count differs"; return false; }
+    if (a.activeVoxelCount() != b.activeVoxelCount()) { why = std::string(name) + ": active voxel count differs"; return false; }
+    for (auto it = a.tree().cbeginLeaf(); it; ++it) {
+        const Leaf* lb = b.tree().probeConstLeaf(it->origin());
+        if (!lb) { why = std::string(name) + ": a leaf is missing"; return false; }
+        if (!(it->getValueMask() == lb->getValueMask())) { why = std::string(name) + ": a value mask differs"; return false; }
+        if (std::memcmp(it->buffer().data(), lb->buffer().data(), sizeof(typename GridT::ValueType) * 512) != 0) { why = std::string(name) + ": leaf values differ"; return false; }
+    }
+    return true;
+}
+bool sameParticles(const PointDataGrid& a, const PointDataGrid& b, std::string& why) {
+    if (a.tree().leafCount() != b.tree().leafCount()) { why = "particles: leaf count differs"; return false; }
+    if (openvdb::points::pointCount(a.tree()) != openvdb::points::pointCount(b.tree())) { why = "particles: point count differs"; return false; }
+    for (auto it = a.tree().cbeginLeaf(); it; ++it) {
+        const auto* lb = b.tree().probeConstLeaf(it->origin());
+        if (!lb) { why = "particles: a leaf is missing"; return false; }
+        for (openvdb::Index k = 0; k < 512; k++)
+            if (it->getValue(k) != lb->getValue(k)) { why = "particles: voxel offsets differ"; return false; }
+        if (!(it->getValueMask() == lb->getValueMask())) { why = "particles: value mask differs"; return false; }
+        const openvdb::Index cnt = it->getLastValue();
+        if (!cnt) continue;
+        for (const char* attr : {"P", "v"}) {
+            const auto& xa = it->constAttributeArray(attr);
+            const auto& xb = lb->constAttributeArray(attr);
+            if (xa.type() != xb.type()) { why = std::string("particles: attribute type of ") + attr + " differs"; return false; }
+            const uint16_t* pa = reinterpret_cast<const uint16_t*>(TestAttributeArray::bytes(xa));
+            const uint16_t* pb = reinterpret_cast<const uint16_t*>(TestAttributeArray::bytes(xb));
+            for (openvdb::Index j = 0; j < cnt; j++)
+                for (int c = 0; c < 3; c++)
+                    if (pa[xa.isUniform() ? c : 3 * j + c] != pb[xb.isUniform() ? c : 3 * j + c]) { why = std::string("particles: codes of ") + attr + " differ"; return false; }
+        }
+    }
+    return true;
+}
+}  // namespace
+
+extern "C" int ref_plugin_roundtrip(void* h, char* msg, int cap) {
+    // 0 = every grid and the particle tree of this world survive upload() -> loopback ABI -> download() unchanged
+    RefWorld& w = *static_cast<RefWorld*>(h);
+    std::string why;
+    bool ok = true;
+    try {
+        zeno::flipb200::WorldHolder holder;
+        holder.dx = w.dx;
+        lb_world_create(0, w.dx, &holder.w);
+        const char* vnames[5] = {"Velocity", "PostAdvVelocity", "ViscousVelocity", "SolidVelocity", "CellFWeight"};
+        for (int i = 0; i < 5 && ok; i++) {
+            if (!w.vec[i]) continue;
+            zeno::flipb200::upload<Vec3fGrid>(holder, i, w.vec[i]);
+            Vec3fGrid::Ptr back = Vec3fGrid::create(openvdb::Vec3f(-7.f));
+            zeno::flipb200::download<Vec3fGrid>(holder, i, back);
+            ok = sameGrid(*w.vec[i], *back, why, vnames[i]);
+        }
+        const char* fnames[10] = {"", "", "", "", "", "LiquidSDF", "SolidSDF", "Pressure", "Divergence", "Curvature"};
+        for (int i = 5; i < 10 && ok; i++) {
+            if (!w.flt[i]) continue;
+            zeno::flipb200::upload<FloatGrid>(holder, i, w.flt[i]);
+            FloatGrid::Ptr back = FloatGrid::create(-7.f);
+            zeno::flipb200::download<FloatGrid>(holder, i, back);
+            ok = sameGrid(*w.flt[i], *back, why, fnames[i]);
+        }
+        if (ok) {
+            zeno::flipb200::upload_particles(holder, w.particles);
+            PointDataGrid::Ptr back = PointDataGrid::create();
+            zeno::flipb200::download_particles(holder, back);
+            ok = sameParticles(*w.particles, *back, why);
+        }
+    } catch (const std::exception& e) { ok = false; why = std::string("exception: ") + e.what(); }
+    if (msg && cap > 0) { std::strncpy(msg, why.c_str(), size_t(cap) - 1); msg[cap - 1] = 0; }
+    return ok ? 0 : 1;
+}

@@ -82,3 +82,33 @@ def test_plugin_calls_only_the_c_abi():
     hdr = open(os.path.join(ROOT, "include", "flipb200.h")).read()
     for call in set(re.findall(r"\b(flipb200_\w+)\(", src)):
         assert re.search(r"\b" + call + r"\(", hdr), f"{call} is not declared in include/flipb200.h"
+
+
+def test_plugin_marshalling_roundtrips_real_reference_objects():
+    """The plugin's OpenVDB <-> flat-array marshalling (upload / download / upload_particles / download_particles), compiled
+    unchanged into oracle/_ref with a loopback C ABI that hands the leaves back in reverse order, must return every grid and the
+    particle tree of a world the REAL reference nodes produced -- same leaves, masks, values, per-voxel offsets and raw codec words
+    (oracle/ref/ref_driver.cpp: ref_plugin_roundtrip)."""
+    import ctypes as C
+
+    import pytest
+
+    from oracle import pyoracle
+    from zeno_b200 import scenes
+    if not pyoracle.ref_available():
+        pytest.skip("oracle/_ref was not built (no /root/reference here)")
+    lib = pyoracle.load_ref()
+    if not hasattr(lib, "ref_plugin_roundtrip"):
+        pytest.skip("oracle/_ref predates the marshalling harness")
+    N = 32
+    pos, vel, dx = scenes.dam_break_points(N, seed=4, random_velocity=True)
+    w = pyoracle.RefWorld(dx)
+    w.set_grid("SolidSDF", scenes.box_solid_sdf(N, dx))
+    w.PrimToVDBPointDataGrid(pos, vel * 0.2)
+    w.FLIP_P2G(dx, 3)
+    dt = 0.01
+    for _ in range(2):
+        w.substep(dt, dx, 4, 3, 0.03, 0.05, (0.0, -9.8, 0.0), 3, True)
+    msg = C.create_string_buffer(256)
+    rc = lib.ref_plugin_roundtrip(w.h, msg, C.c_int(256))
+    assert rc == 0, msg.value.decode()

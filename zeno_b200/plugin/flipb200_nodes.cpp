@@ -16,9 +16,19 @@
 // conservative mode whose cost bench.py reports as `e2e`. Setting FLIPB200_RESIDENT=1 keeps grids on the device
 // between accelerated nodes: an object is uploaded only when its tree pointer or leaf count changed since we
 // last wrote it, and a node's outputs are still written back (the substep chain itself then never re-uploads).
+// FLIPB200_PLUGIN_MARSHAL_ONLY: only the OpenVDB <-> flat-array marshalling below is compiled (no Zeno headers, no
+// node registration). oracle/ref/ref_driver.cpp includes this file that way to round-trip REAL reference grids and
+// particle trees through upload()/download() against a loopback C ABI (tests/test_plugin_cpu.py).
+#ifndef FLIPB200_PLUGIN_MARSHAL_ONLY
 #include <zeno/zeno.h>
 #include <zeno/VDBGrid.h>
 #include <zeno/types/NumericObject.h>
+#else
+#include <stdexcept>
+#include <string>
+#include <memory>
+#include <tbb/parallel_for.h>
+#endif
 
 #include <openvdb/openvdb.h>
 #include <openvdb/points/PointDataGrid.h>
@@ -33,11 +43,13 @@
 #include "flipb200.h"
 
 // OpenVDB's own test hook (openvdb/points/AttributeArray.h:353,756): raw codec words without a decode/encode trip
+#ifndef FLIPB200_HAVE_TEST_ATTRIBUTE_ARRAY
 class TestAttributeArray {
 public:
     static char* bytes(openvdb::points::AttributeArray& a) { return a.dataAsByteArray(); }
     static const char* bytes(const openvdb::points::AttributeArray& a) { return a.constDataAsByteArray(); }
 };
+#endif
 
 namespace zeno {
 namespace flipb200 {
@@ -48,7 +60,13 @@ using position_attribute = openvdb::points::TypedAttributeArray<openvdb::Vec3f, 
 using velocity_attribute = openvdb::points::TypedAttributeArray<openvdb::Vec3f, openvdb::points::TruncateCodec>;
 
 inline void check(int rc, const char* what) {
-    if (rc != FLIPB200_OK) throw makeError(std::string(what) + ": libflipb200 error " + std::to_string(rc) + ": " + flipb200_last_error());
+    if (rc == FLIPB200_OK) return;
+    const std::string msg = std::string(what) + ": libflipb200 error " + std::to_string(rc) + ": " + flipb200_last_error();
+#ifdef FLIPB200_PLUGIN_MARSHAL_ONLY
+    throw std::runtime_error(msg);
+#else
+    throw makeError(msg);   // -> GraphException with the node name (zeno/src/core/Graph.cpp:88-90)
+#endif
 }
 
 struct WorldHolder {
@@ -175,8 +193,9 @@ void download_particles(WorldHolder& h, openvdb::points::PointDataGrid::Ptr& g) 
     std::vector<uint16_t> P(3 * np), V(3 * np);
     check(flipb200_particles_download(h.w, o.data(), ve.data(), P.data(), V.data()), "particles_download");
     // the descriptor the reference builds for a new particle tree (FF/FLIP_vdb.cpp:3398-3404)
-    auto descr = openvdb::points::AttributeSet::Descriptor::create(position_attribute::attributeType());
-    descr = descr->duplicateAppend("v", velocity_attribute::attributeType());
+    // (initializeAttributes accepts only the one-attribute position descriptor; "v" is appended per leaf, as the reference does)
+    auto pdescr = openvdb::points::AttributeSet::Descriptor::create(position_attribute::attributeType());
+    auto pvdescr = pdescr->duplicateAppend("v", velocity_attribute::attributeType());
     auto tree = std::make_shared<openvdb::points::PointDataTree>();
     std::vector<openvdb::points::PointDataTree::LeafNodeType*> leaves(nl);
     std::vector<uint64_t> begin(size_t(nl) + 1, 0);
@@ -186,7 +205,8 @@ void download_particles(WorldHolder& h, openvdb::points::PointDataGrid::Ptr& g) 
     }
     tbb::parallel_for(0, nl, [&](int i) {
         const uint32_t cnt = ve[512 * size_t(i) + 511];
-        leaves[i]->initializeAttributes(descr, cnt);
+        leaves[i]->initializeAttributes(pdescr, cnt);
+        leaves[i]->appendAttribute(leaves[i]->attributeSet().descriptor(), pvdescr, 1);
         std::vector<openvdb::PointDataIndex32> offs(512);
         for (int k = 0; k < 512; k++) offs[k] = openvdb::PointDataIndex32(ve[512 * size_t(i) + k]);
         leaves[i]->setOffsets(offs, /*updateValueMask=*/true);
@@ -200,14 +220,18 @@ void download_particles(WorldHolder& h, openvdb::points::PointDataGrid::Ptr& g) 
     h.lastTree[FLIPB200_NUM_GRIDS] = &g->tree(); h.lastLeaves[FLIPB200_NUM_GRIDS] = g->tree().leafCount();
 }
 
+#ifndef FLIPB200_PLUGIN_MARSHAL_ONLY
 inline float dx_of(INode* node) {
     float dx = node->get_param<float>("dx");
     if (node->has_input("Dx")) dx = node->get_input("Dx")->as<NumericObject>()->get<float>();
     return dx;
 }
 
+#endif  // !FLIPB200_PLUGIN_MARSHAL_ONLY
+
 }  // namespace flipb200
 
+#ifndef FLIPB200_PLUGIN_MARSHAL_ONLY
 using namespace flipb200;
 
 // ---- FLIP_P2G (FF/nosys/P2G.cpp:11-62)
@@ -395,4 +419,5 @@ static int defSubtractPressureGradient = zeno::defNodeClass<SubtractPressureGrad
                     "CellFWeight", "Velocity", "SolidVelocity", "Curvature"},
      /* outputs: */ {}, /* params: */ {{"float", "dx", "0.0"}, {"int", "VelExtraLayer", "3"}}, /* category: */ {"FLIPSolver"}});
 
+#endif  // !FLIPB200_PLUGIN_MARSHAL_ONLY
 }  // namespace zeno
