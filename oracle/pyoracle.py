@@ -234,3 +234,51 @@ class RefWorld(OracleWorld):
     @classmethod
     def _load(cls):
         return load_ref()
+
+
+class PluginWorld(OracleWorld):
+    """Same interface again, executed by the NODES of the Zeno-side drop-in (zeno_b200/plugin/flipb200_nodes.cpp) on real
+    OpenVDB objects, with the CPU oracle behind the C ABI they call (oracle/ref/plugin_nodes_test.cpp, prefix pn_)."""
+    PREFIX = "pn_"
+
+    @classmethod
+    def _load(cls):
+        lib = load_ref()
+        if not getattr(lib, "_pn_ready", False):
+            build()
+            lib.pn_world_create.restype = C.c_void_p
+            lib.pn_cfl.restype = C.c_float
+            lib.pn_dropped.restype = C.c_uint64
+            lib.pn_last_error.restype = C.c_char_p
+            if lib.pn_backend(_LIB.encode()) != 0:
+                raise RuntimeError("pn_backend: " + (lib.pn_last_error() or b"").decode())
+            lib._pn_ready = True
+        return lib
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError("plugin node failed: " + (self.lib.pn_last_error() or b"").decode())
+
+    def FLIP_P2G(self, dx=None, VelExtraLayer=3):
+        self._ck(self.lib.orc_p2g(self.h, C.c_float(self.dx if dx is None else dx), C.c_int(VelExtraLayer)))
+
+    def G2PAdvectorSheetty(self, dt, dx=None, surface_size=4, RK_ORDER=1, pic_min=0.03, pic_max=0.05, viscous_is_velocity=True):
+        self._ck(self.lib.orc_g2p_advect_sheetty(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.c_int(surface_size),
+                                                 C.c_int(RK_ORDER), C.c_float(pic_min), C.c_float(pic_max), C.c_int(1 if viscous_is_velocity else 0)))
+
+    def CutCellWeight(self):
+        self._ck(self.lib.orc_face_weights(self.h))
+
+    def PushOutLiquidSDF(self, dx=None):
+        self._ck(self.lib.orc_pushout_sdf(self.h, C.c_float(self.dx if dx is None else dx)))
+
+    def FieldAddVector(self, x, y, z):
+        self._ck(self.lib.orc_add_vector(self.h, C.c_float(x), C.c_float(y), C.c_float(z)))
+
+    def AssembleSolvePPE(self, dt, dx=None, rel_tol=None, max_iter=100):
+        it, res, st = C.c_int(0), C.c_float(0), C.c_int(0)
+        self._ck(self.lib.orc_solve_ppe(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.byref(it), C.byref(res), C.byref(st)))
+        return {"iterations": it.value, "rel_residual": res.value, "status": st.value}
+
+    def SubtractPressureGradient(self, dt, dx=None, VelExtraLayer=3):
+        self._ck(self.lib.orc_subtract_grad(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.c_int(VelExtraLayer)))

@@ -24,7 +24,7 @@ VDB="$REF/projects/zenvdb/openvdb/openvdb"
 FF="$REF/projects/FastFLIP"
 [ -d "$REF" ] || { echo "no $REF: keeping the prebuilt oracle/_ref"; exit 0; }
 PLUGIN_SRC="$HERE/../../zeno_b200/plugin/flipb200_nodes.cpp"
-if [ -f "$OUT/libflipref.so" ] && [ "$OUT/libflipref.so" -nt "$HERE/ref_driver.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/shims/Eigen/Eigen" ] && [ "$OUT/libflipref.so" -nt "$PLUGIN_SRC" ] && [ -z "$FORCE" ]; then
+if [ -f "$OUT/libflipref.so" ] && [ "$OUT/libflipref.so" -nt "$HERE/ref_driver.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/shims/Eigen/Eigen" ] && [ "$OUT/libflipref.so" -nt "$PLUGIN_SRC" ] && [ "$OUT/libflipref.so" -nt "$HERE/plugin_nodes_test.cpp" ] && [ -z "$FORCE" ]; then
   echo "oracle/_ref/libflipref.so is up to date"; exit 0
 fi
 mkdir -p "$OUT" "$BUILD/gen/openvdb" "$BUILD/vdbobj" "$BUILD/ffobj"
@@ -64,17 +64,26 @@ xargs -P "$JOBS" -d '\n' -I{} bash -c {} < "$BUILD/cmds.txt" || { echo "openvdb 
 # ---- 4. the reference FastFLIP sources, unmodified, with the reference's flags (FF/CMakeLists.txt:56: -mavx -mfma)
 FFFLAGS="$COMMON -mavx -mfma -DZENO_APIFREE -I$HERE/shims/zeno_min -I$REF/projects/zenvdb/include -I$REF/zeno/include -I$FF -I$HERE/../../include"
 : > "$BUILD/cmds.txt"
-for s in "$FF/FLIP_vdb.cpp" "$FF/simd_vdb_poisson_uaamg.cpp" "$FF/vdb_velocity_extrapolator.cpp" "$FF/levelset_util.cpp" "$REF/projects/zenvdb/include/zeno/packed3grids.cpp" "$HERE/ref_driver.cpp" "$HERE/ref_stubs.cpp"; do
+# plugin_nodes_test.cpp compiles the drop-in's NODES against a minimal stand-in of the Zeno node runtime (shims/zeno_nodes,
+# searched before the real zeno headers) and without FLIP_vdb.h
+NODEFLAGS="$COMMON -I$HERE/shims/zeno_nodes -I$HERE/../../include"
+for s in "$FF/FLIP_vdb.cpp" "$FF/simd_vdb_poisson_uaamg.cpp" "$FF/vdb_velocity_extrapolator.cpp" "$FF/levelset_util.cpp" "$REF/projects/zenvdb/include/zeno/packed3grids.cpp" "$HERE/ref_driver.cpp" "$HERE/ref_stubs.cpp" "$HERE/plugin_nodes_test.cpp"; do
   o="$BUILD/ffobj/$(basename $s .cpp).o"
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ "$HERE/shims/Eigen/Eigen" -nt "$o" ] || { [ "$(basename $s)" = "ref_driver.cpp" ] && [ "$HERE/../../zeno_b200/plugin/flipb200_nodes.cpp" -nt "$o" ]; }; then
-    echo "$CXX $FFFLAGS -c $s -o $o 2> $o.log || { grep -m 30 -E 'error|Error' $o.log; exit 255; }" >> "$BUILD/cmds.txt"
+  FL="$FFFLAGS"
+  USES_PLUGIN=""
+  case "$(basename $s)" in
+    plugin_nodes_test.cpp) FL="$NODEFLAGS"; USES_PLUGIN=1 ;;
+    ref_driver.cpp) USES_PLUGIN=1 ;;
+  esac
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ "$HERE/shims/Eigen/Eigen" -nt "$o" ] || { [ -n "$USES_PLUGIN" ] && [ "$PLUGIN_SRC" -nt "$o" ]; } || { [ "$(basename $s)" = "plugin_nodes_test.cpp" ] && [ "$HERE/shims/zeno_nodes/zeno/zeno.h" -nt "$o" ]; }; then
+    echo "$CXX $FL -c $s -o $o 2> $o.log || { grep -m 30 -E 'error|Error' $o.log; exit 255; }" >> "$BUILD/cmds.txt"
   fi
 done
 xargs -P "$JOBS" -d '\n' -I{} bash -c {} < "$BUILD/cmds.txt" || { echo "FastFLIP compile failed"; exit 1; }
 
 # ---- 5. link
 cp "$BUILD/libtbb.so.2" "$OUT/libtbb.so.2"
-$CXX -shared -o "$OUT/libflipref.so" "$BUILD"/ffobj/*.o "$BUILD"/vdbobj/*.o -L"$BUILD" -ltbb -lpthread -Wl,-rpath,'$ORIGIN' -Wl,-z,defs 2> "$BUILD/link.log" || { head -40 "$BUILD/link.log"; exit 1; }
+$CXX -shared -o "$OUT/libflipref.so" "$BUILD"/ffobj/*.o "$BUILD"/vdbobj/*.o -L"$BUILD" -ltbb -lpthread -ldl -Wl,-rpath,'$ORIGIN' -Wl,-z,defs 2> "$BUILD/link.log" || { head -40 "$BUILD/link.log"; exit 1; }
 echo "built $OUT/libflipref.so"
 
 # ---- 6. compile check of the Zeno-side drop-in (zeno_b200/plugin/flipb200_nodes.cpp) against the reference's own

@@ -1,0 +1,265 @@
+// TEST INFRASTRUCTURE ONLY -- runs the NODES of the Zeno-side drop-in (zeno_b200/plugin/flipb200_nodes.cpp) on the CPU.
+//
+// The plugin source is compiled here unchanged against (a) a minimal stand-in for the Zeno node runtime
+// (oracle/ref/shims/zeno_nodes: INode sockets/params, defNodeClass, NumericObject, VDBGridWrapper) and (b) a C ABI whose
+// flipb200_* entry points are renamed to ob_* and implemented below by the CPU oracle (liboracle.so, dlopen'ed; the same
+// flat leaf layout). A "pn world" holds REAL OpenVDB objects (a RefWorld of ref_driver.cpp); every pn_<node> call wires those
+// objects to the sockets of the plugin's node class, exactly as the packaged graph does (projects/tools/FLIPtools/stub.cpp),
+// and runs its apply(). tests/test_plugin_cpu.py drives the reference nodes (ref_*) and the plugin nodes (pn_*) from the
+// same state and compares: together with the GPU parity tests (CUDA library == oracle through the same ABI) this closes
+// the drop-in chain  reference node == plugin node o ABI(oracle) == plugin node o ABI(CUDA).
+#define flipb200_last_error ob_last_error
+#define flipb200_world_create ob_world_create
+#define flipb200_world_destroy ob_world_destroy
+#define flipb200_grid_upload ob_grid_upload
+#define flipb200_grid_leaf_count ob_grid_leaf_count
+#define flipb200_grid_download ob_grid_download
+#define flipb200_particles_upload ob_particles_upload
+#define flipb200_particles_info ob_particles_info
+#define flipb200_particles_download ob_particles_download
+#define flipb200_p2g ob_p2g
+#define flipb200_g2p_advect_sheetty ob_g2p_advect_sheetty
+#define flipb200_face_weights ob_face_weights
+#define flipb200_pushout_sdf ob_pushout_sdf
+#define flipb200_add_vector ob_add_vector
+#define flipb200_cfl ob_cfl
+#define flipb200_solve_ppe ob_solve_ppe
+#define flipb200_subtract_grad ob_subtract_grad
+#include <tbb/parallel_for.h>
+#include "../../zeno_b200/plugin/flipb200_nodes.cpp"
+
+#include <dlfcn.h>
+
+// ---------------------------------------------------------------- the oracle behind the C ABI
+namespace {
+struct OracleApi {
+    void* handle = nullptr;
+    void* (*world_create)(float) = nullptr;
+    void (*world_destroy)(void*) = nullptr;
+    int (*grid_set)(void*, int, int, const int32_t*, const uint64_t*, const float*, const float*) = nullptr;
+    int (*grid_leaf_count)(void*, int) = nullptr;
+    int (*grid_get)(void*, int, int32_t*, uint64_t*, float*, float*) = nullptr;
+    int (*particles_set)(void*, int, const int32_t*, const uint32_t*, uint64_t, const uint16_t*, const uint16_t*) = nullptr;
+    int (*particles_info)(void*, int*, uint64_t*) = nullptr;
+    int (*particles_get)(void*, int32_t*, uint32_t*, uint16_t*, uint16_t*) = nullptr;
+    int (*p2g)(void*, float, int) = nullptr;
+    int (*g2p)(void*, float, float, int, int, float, float, int) = nullptr;
+    int (*face_weights)(void*) = nullptr;
+    int (*pushout)(void*, float) = nullptr;
+    int (*add_vector)(void*, float, float, float) = nullptr;
+    float (*cfl)(void*) = nullptr;
+    int (*solve)(void*, float, float, int*, float*, int*) = nullptr;
+    int (*subtract)(void*, float, float, int) = nullptr;
+};
+OracleApi g_orc;
+std::string g_err;
+template <typename F> void bind(F& f, const char* name) {
+    f = reinterpret_cast<F>(dlsym(g_orc.handle, name));
+    if (!f) throw std::runtime_error(std::string("liboracle has no ") + name);
+}
+}  // namespace
+
+struct flipb200_world { void* orc = nullptr; };
+
+extern "C" {
+const char* ob_last_error(void) { return g_err.c_str(); }
+int ob_world_create(int, float dx, flipb200_world** out) {
+    if (!g_orc.handle) { g_err = "pn_backend was not called"; return FLIPB200_ERR_STATE; }
+    *out = new flipb200_world{g_orc.world_create(dx)};
+    return 0;
+}
+int ob_world_destroy(flipb200_world* w) { if (w) { g_orc.world_destroy(w->orc); delete w; } return 0; }
+int ob_grid_upload(flipb200_world* w, int grid, int n, const int32_t* o, const uint64_t* m, const float* v, int layout, const float* bg) {
+    const int nch = grid <= FLIPB200_FACE_WEIGHT ? 3 : 1;
+    if (nch == 3 && layout == FLIPB200_AOS) {   // [leaf][512][3] -> the oracle's [leaf][3][512]
+        std::vector<float> soa(size_t(n) * 1536);
+        for (size_t l = 0; l < size_t(n); l++)
+            for (int i = 0; i < 512; i++)
+                for (int c = 0; c < 3; c++) soa[l * 1536 + size_t(c) * 512 + i] = v[l * 1536 + size_t(i) * 3 + c];
+        return g_orc.grid_set(w->orc, grid, n, o, m, soa.data(), bg);
+    }
+    return g_orc.grid_set(w->orc, grid, n, o, m, v, bg);
+}
+int ob_grid_leaf_count(flipb200_world* w, int grid, int* n) { *n = g_orc.grid_leaf_count(w->orc, grid); return *n < 0 ? FLIPB200_ERR_ARG : 0; }
+int ob_grid_download(flipb200_world* w, int grid, int32_t* o, uint64_t* m, float* v, int layout, float* bg) {
+    const int nch = grid <= FLIPB200_FACE_WEIGHT ? 3 : 1;
+    if (nch == 3 && layout == FLIPB200_AOS) {
+        const int n = g_orc.grid_leaf_count(w->orc, grid);
+        std::vector<float> soa(size_t(n) * 1536);
+        int rc = g_orc.grid_get(w->orc, grid, o, m, soa.data(), bg);
+        for (size_t l = 0; l < size_t(n); l++)
+            for (int i = 0; i < 512; i++)
+                for (int c = 0; c < 3; c++) v[l * 1536 + size_t(i) * 3 + c] = soa[l * 1536 + size_t(c) * 512 + i];
+        return rc;
+    }
+    return g_orc.grid_get(w->orc, grid, o, m, v, bg);
+}
+int ob_particles_upload(flipb200_world* w, int nl, const int32_t* o, const uint32_t* ve, uint64_t np, const uint16_t* P, const uint16_t* V) {
+    return g_orc.particles_set(w->orc, nl, o, ve, np, P, V);
+}
+int ob_particles_info(flipb200_world* w, int* nl, uint64_t* np) { return g_orc.particles_info(w->orc, nl, np); }
+int ob_particles_download(flipb200_world* w, int32_t* o, uint32_t* ve, uint16_t* P, uint16_t* V) { return g_orc.particles_get(w->orc, o, ve, P, V); }
+int ob_p2g(flipb200_world* w, float dx, int n) { return g_orc.p2g(w->orc, dx, n); }
+int ob_g2p_advect_sheetty(flipb200_world* w, float dt, float dx, int ss, int rk, float pmin, float pmax, int flags) {
+    return g_orc.g2p(w->orc, dt, dx, ss, rk, pmin, pmax, flags);
+}
+int ob_face_weights(flipb200_world* w) { return g_orc.face_weights(w->orc); }
+int ob_pushout_sdf(flipb200_world* w, float dx) { return g_orc.pushout(w->orc, dx); }
+int ob_add_vector(flipb200_world* w, float x, float y, float z) { return g_orc.add_vector(w->orc, x, y, z); }
+int ob_cfl(flipb200_world* w, float* dt) { *dt = g_orc.cfl(w->orc); return 0; }
+int ob_solve_ppe(flipb200_world* w, float dt, float dx, int* it, float* res, int* st) { return g_orc.solve(w->orc, dt, dx, it, res, st); }
+int ob_subtract_grad(flipb200_world* w, float dt, float dx, int n) { return g_orc.subtract(w->orc, dt, dx, n); }
+
+// ---- RefWorld access (ref_driver.cpp)
+void* ref_world_create(float dx);
+void ref_world_destroy(void* w);
+void* ref_internal_vec(void* w, int id);        // openvdb::Vec3fGrid::Ptr*
+void* ref_internal_flt(void* w, int id);        // openvdb::FloatGrid::Ptr*
+void* ref_internal_particles(void* w);          // openvdb::points::PointDataGrid::Ptr*
+int ref_grid_set(void*, int, int, const int32_t*, const uint64_t*, const float*, const float*);
+int ref_grid_leaf_count(void*, int);
+int ref_grid_get(void*, int, int32_t*, uint64_t*, float*, float*);
+int ref_particles_set(void*, int, const int32_t*, const uint32_t*, uint64_t, const uint16_t*, const uint16_t*);
+int ref_particles_info(void*, int*, uint64_t*);
+int ref_particles_get(void*, int32_t*, uint32_t*, uint16_t*, uint16_t*);
+int ref_bin_from_points(void*, const float*, const float*, uint64_t);
+}  // extern "C"
+
+// ---------------------------------------------------------------- the pn world: real OpenVDB objects + plugin nodes
+namespace {
+using namespace zeno;
+struct PnWorld {
+    void* ref;
+    float dx;
+    int iterations = 0, status = 0;
+    float relResidual = 0.f;
+    std::shared_ptr<VDBFloat3Grid> vec(int id) { return std::make_shared<VDBFloat3Grid>(*static_cast<openvdb::Vec3fGrid::Ptr*>(ref_internal_vec(ref, id))); }
+    std::shared_ptr<VDBFloatGrid> flt(int id) { return std::make_shared<VDBFloatGrid>(*static_cast<openvdb::FloatGrid::Ptr*>(ref_internal_flt(ref, id))); }
+    std::shared_ptr<VDBPointsGrid> pts() { return std::make_shared<VDBPointsGrid>(*static_cast<openvdb::points::PointDataGrid::Ptr*>(ref_internal_particles(ref))); }
+};
+std::shared_ptr<IObject> num(float v) { return std::make_shared<NumericObject>(v); }
+
+// runs node `name` with the given sockets / params; returns its outputs
+std::map<std::string, std::shared_ptr<IObject>> run(const char* name, std::map<std::string, std::shared_ptr<IObject>> in,
+                                                    std::map<std::string, ParamValue> params) {
+    auto it = nodeRegistry().find(name);
+    if (it == nodeRegistry().end()) throw std::runtime_error(std::string("the plugin does not register node ") + name);
+    // defaults of the descriptor's params, as the graph loader supplies them (zeno/src/core/Graph.cpp)
+    for (auto& p : it->second.desc.params) {
+        if (params.count(p.name)) continue;
+        const std::string first = p.defl.substr(0, p.defl.find(' '));
+        if (p.type == "int") params[p.name] = std::atoi(first.c_str());
+        else if (p.type == "float") params[p.name] = float(std::atof(first.c_str()));
+        else params[p.name] = p.defl;
+    }
+    // every wired socket must exist in the descriptor (the editor could not connect it otherwise)
+    for (auto& kv : in) {
+        bool known = false;
+        for (auto& s : it->second.desc.inputs) known = known || s.name == kv.first;
+        if (!known) throw std::runtime_error(std::string(name) + " has no input socket " + kv.first);
+    }
+    auto node = it->second.make();
+    node->inputs = std::move(in);
+    node->params = std::move(params);
+    node->apply();
+    return node->outputs;
+}
+template <typename F> int guarded(F&& f) {
+    try { f(); return 0; } catch (const std::exception& e) { g_err = e.what(); fprintf(stderr, "plugin node test: %s\n", e.what()); return 1; }
+}
+}  // namespace
+
+extern "C" {
+int pn_backend(const char* liboracle) {
+    return guarded([&] {
+        if (g_orc.handle) return;
+        g_orc.handle = dlopen(liboracle, RTLD_NOW | RTLD_LOCAL);
+        if (!g_orc.handle) throw std::runtime_error(std::string("cannot load ") + liboracle + ": " + dlerror());
+        bind(g_orc.world_create, "orc_world_create"); bind(g_orc.world_destroy, "orc_world_destroy");
+        bind(g_orc.grid_set, "orc_grid_set"); bind(g_orc.grid_leaf_count, "orc_grid_leaf_count"); bind(g_orc.grid_get, "orc_grid_get");
+        bind(g_orc.particles_set, "orc_particles_set"); bind(g_orc.particles_info, "orc_particles_info"); bind(g_orc.particles_get, "orc_particles_get");
+        bind(g_orc.p2g, "orc_p2g"); bind(g_orc.g2p, "orc_g2p_advect_sheetty"); bind(g_orc.face_weights, "orc_face_weights");
+        bind(g_orc.pushout, "orc_pushout_sdf"); bind(g_orc.add_vector, "orc_add_vector"); bind(g_orc.cfl, "orc_cfl");
+        bind(g_orc.solve, "orc_solve_ppe"); bind(g_orc.subtract, "orc_subtract_grad");
+    });
+}
+const char* pn_last_error(void) { return g_err.c_str(); }
+void* pn_world_create(float dx) { return new PnWorld{ref_world_create(dx), dx}; }
+void pn_world_destroy(void* w) { auto* p = static_cast<PnWorld*>(w); ref_world_destroy(p->ref); delete p; }
+// data access: straight to the OpenVDB objects
+int pn_grid_set(void* w, int id, int n, const int32_t* o, const uint64_t* m, const float* v, const float* bg) { return ref_grid_set(static_cast<PnWorld*>(w)->ref, id, n, o, m, v, bg); }
+int pn_grid_leaf_count(void* w, int id) { return ref_grid_leaf_count(static_cast<PnWorld*>(w)->ref, id); }
+int pn_grid_get(void* w, int id, int32_t* o, uint64_t* m, float* v, float* bg) { return ref_grid_get(static_cast<PnWorld*>(w)->ref, id, o, m, v, bg); }
+int pn_particles_set(void* w, int nl, const int32_t* o, const uint32_t* ve, uint64_t n, const uint16_t* P, const uint16_t* v) { return ref_particles_set(static_cast<PnWorld*>(w)->ref, nl, o, ve, n, P, v); }
+int pn_particles_info(void* w, int* nl, uint64_t* n) { return ref_particles_info(static_cast<PnWorld*>(w)->ref, nl, n); }
+int pn_particles_get(void* w, int32_t* o, uint32_t* ve, uint16_t* P, uint16_t* v) { return ref_particles_get(static_cast<PnWorld*>(w)->ref, o, ve, P, v); }
+int pn_bin_from_points(void* w, const float* pos, const float* vel, uint64_t n) { return ref_bin_from_points(static_cast<PnWorld*>(w)->ref, pos, vel, n); }
+uint64_t pn_dropped(void*) { return 0; }
+
+// nodes, wired like the packaged sub-graphs (projects/tools/FLIPtools/stub.cpp:5-17); grid ids = include/flipb200.h
+int pn_p2g(void* wp, float dx, int velExtraLayer) {
+    auto& w = *static_cast<PnWorld*>(wp);
+    return guarded([&] {
+        run("FLIP_P2G", {{"Dx", num(dx)}, {"Particles", w.pts()}, {"Velocity", w.vec(FLIPB200_VELOCITY)},
+                         {"PostP2GVelocity", w.vec(FLIPB200_POSTADV_VELOCITY)}, {"LiquidSDF", w.flt(FLIPB200_LIQUID_SDF)}},
+            {{"VelExtraLayer", velExtraLayer}});
+    });
+}
+int pn_g2p_advect_sheetty(void* wp, float dt, float dx, int surfaceSize, int rkOrder, float picMin, float picMax, int flags) {
+    auto& w = *static_cast<PnWorld*>(wp);
+    return guarded([&] {
+        auto vel = w.vec(FLIPB200_VELOCITY);
+        std::shared_ptr<IObject> visc = (flags & 1) ? std::static_pointer_cast<IObject>(vel) : std::static_pointer_cast<IObject>(w.vec(FLIPB200_VISCOUS_VELOCITY));
+        // (flags & 1: the ViscousVelocity socket carries the Velocity OBJECT; the wrapper differs here but m_grid is the same pointer)
+        run("G2PAdvectorSheetty", {{"dt", num(dt)}, {"Dx", num(dx)}, {"pic_min", num(picMin)}, {"pic_max", num(picMax)}, {"Particles", w.pts()},
+                                   {"Velocity", vel}, {"ViscousVelocity", visc}, {"LiquidSDF", w.flt(FLIPB200_LIQUID_SDF)},
+                                   {"PostAdvVelocity", w.vec(FLIPB200_POSTADV_VELOCITY)}, {"SolidSDF", w.flt(FLIPB200_SOLID_SDF)},
+                                   {"SolidVelocity", w.vec(FLIPB200_SOLID_VELOCITY)}},
+            {{"RK_ORDER", rkOrder}, {"surface_size", surfaceSize}});
+    });
+}
+int pn_face_weights(void* wp) {
+    auto& w = *static_cast<PnWorld*>(wp);
+    return guarded([&] { run("CutCellWeight", {{"LiquidSDF", w.flt(FLIPB200_LIQUID_SDF)}, {"SolidSDF", w.flt(FLIPB200_SOLID_SDF)}, {"FaceWeight", w.vec(FLIPB200_FACE_WEIGHT)}}, {}); });
+}
+int pn_pushout_sdf(void* wp, float dx) {
+    auto& w = *static_cast<PnWorld*>(wp);
+    return guarded([&] { run("PushOutLiquidSDF", {{"Dx", num(dx)}, {"LiquidSDF", w.flt(FLIPB200_LIQUID_SDF)}, {"SolidSDF", w.flt(FLIPB200_SOLID_SDF)}}, {}); });
+}
+int pn_add_vector(void* wp, float x, float y, float z) {
+    auto& w = *static_cast<PnWorld*>(wp);
+    return guarded([&] { run("FieldAddVector", {{"invec3", std::make_shared<NumericObject>(vec3f(x, y, z))}, {"Velocity", w.vec(FLIPB200_VELOCITY)}}, {}); });
+}
+float pn_cfl(void* wp) {
+    auto& w = *static_cast<PnWorld*>(wp);
+    float out = -1.f;
+    guarded([&] {
+        auto res = run("CFL_dt", {{"Velocity", w.vec(FLIPB200_VELOCITY)}, {"Dx", num(w.dx)}}, {});
+        out = res.at("cfl_dt")->as<NumericObject>()->get<float>();
+    });
+    return out;
+}
+int pn_solve_ppe(void* wp, float dt, float dx, int* iters, float* relResidual, int* status) {
+    auto& w = *static_cast<PnWorld*>(wp);
+    int rc = guarded([&] {
+        run("AssembleSolvePPE", {{"dt", num(dt)}, {"Dx", num(dx)}, {"Density", num(1000.f)}, {"SurfaceTension", num(0.f)},
+                                 {"LiquidSDF", w.flt(FLIPB200_LIQUID_SDF)}, {"Divergence", w.flt(FLIPB200_DIVERGENCE)}, {"Pressure", w.flt(FLIPB200_PRESSURE)},
+                                 {"CellFWeight", w.vec(FLIPB200_FACE_WEIGHT)}, {"Velocity", w.vec(FLIPB200_VELOCITY)},
+                                 {"SolidVelocity", w.vec(FLIPB200_SOLID_VELOCITY)}, {"Curvature", w.flt(FLIPB200_CURVATURE)}}, {});
+    });
+    if (iters) *iters = -1;          // the node reports them on stdout only, like the reference's
+    if (relResidual) *relResidual = 0.f;
+    if (status) *status = rc;
+    return rc;
+}
+int pn_subtract_grad(void* wp, float dt, float dx, int velExtraLayer) {
+    auto& w = *static_cast<PnWorld*>(wp);
+    return guarded([&] {
+        run("SubtractPressureGradient", {{"dt", num(dt)}, {"Dx", num(dx)}, {"Density", num(1000.f)}, {"SurfaceTension", num(0.f)},
+                                         {"LiquidSDF", w.flt(FLIPB200_LIQUID_SDF)}, {"SolidSDF", w.flt(FLIPB200_SOLID_SDF)}, {"Pressure", w.flt(FLIPB200_PRESSURE)},
+                                         {"CellFWeight", w.vec(FLIPB200_FACE_WEIGHT)}, {"Velocity", w.vec(FLIPB200_VELOCITY)},
+                                         {"SolidVelocity", w.vec(FLIPB200_SOLID_VELOCITY)}, {"Curvature", w.flt(FLIPB200_CURVATURE)}},
+            {{"VelExtraLayer", velExtraLayer}});
+    });
+}
+}  // extern "C"

@@ -214,6 +214,10 @@ int ref_grid_leaf_count(void* wp, int id) {
     if (id < 10 && w->flt[id]) return leafCountOf(*w->flt[id]);
     return -1;
 }
+// the OpenVDB objects themselves, for oracle/ref/plugin_nodes_test.cpp (pointers to the world's grid Ptrs)
+void* ref_internal_vec(void* wp, int id) { return (id >= 0 && id <= G_FACEWEIGHT) ? &static_cast<RefWorld*>(wp)->vec[id] : nullptr; }
+void* ref_internal_flt(void* wp, int id) { return (id > G_FACEWEIGHT && id < 10) ? &static_cast<RefWorld*>(wp)->flt[id] : nullptr; }
+void* ref_internal_particles(void* wp) { return &static_cast<RefWorld*>(wp)->particles; }
 int ref_grid_get(void* wp, int id, int32_t* origins, uint64_t* masks, float* values, float* bg) {
     RefWorld* w = static_cast<RefWorld*>(wp);
     if (id >= 0 && id <= G_FACEWEIGHT) getVecGrid(*w->vec[id], origins, masks, values, bg);
@@ -472,7 +476,11 @@ int ref_substep(void* wp, float dt, float dx, int surfaceSize, int rkOrder, floa
 #define flipb200_particles_info lb_particles_info
 #define flipb200_particles_download lb_particles_download
 #include <map>
+// (the plugin's namespace zeno::flipb200 is renamed in this translation unit: plugin_nodes_test.cpp compiles the same
+// inline functions against a different ABI, and the two sets must not be merged by the linker)
+#define flipb200 flipb200_loopback
 #include "../../zeno_b200/plugin/flipb200_nodes.cpp"
+#undef flipb200
 
 struct flipb200_world {
     struct G { int n = 0, nch = 1, layout = 0; std::vector<int32_t> o; std::vector<uint64_t> m; std::vector<float> v; float bg[3] = {0, 0, 0}; };
@@ -580,29 +588,29 @@ extern "C" int ref_plugin_roundtrip(void* h, char* msg, int cap) {
     std::string why;
     bool ok = true;
     try {
-        zeno::flipb200::WorldHolder holder;
+        zeno::flipb200_loopback::WorldHolder holder;
         holder.dx = w.dx;
         lb_world_create(0, w.dx, &holder.w);
         const char* vnames[5] = {"Velocity", "PostAdvVelocity", "ViscousVelocity", "SolidVelocity", "CellFWeight"};
         for (int i = 0; i < 5 && ok; i++) {
             if (!w.vec[i]) continue;
-            zeno::flipb200::upload<Vec3fGrid>(holder, i, w.vec[i]);
+            zeno::flipb200_loopback::upload<Vec3fGrid>(holder, i, w.vec[i]);
             Vec3fGrid::Ptr back = Vec3fGrid::create(openvdb::Vec3f(-7.f));
-            zeno::flipb200::download<Vec3fGrid>(holder, i, back);
+            zeno::flipb200_loopback::download<Vec3fGrid>(holder, i, back);
             ok = sameGrid(*w.vec[i], *back, why, vnames[i]);
         }
         const char* fnames[10] = {"", "", "", "", "", "LiquidSDF", "SolidSDF", "Pressure", "Divergence", "Curvature"};
         for (int i = 5; i < 10 && ok; i++) {
             if (!w.flt[i]) continue;
-            zeno::flipb200::upload<FloatGrid>(holder, i, w.flt[i]);
+            zeno::flipb200_loopback::upload<FloatGrid>(holder, i, w.flt[i]);
             FloatGrid::Ptr back = FloatGrid::create(-7.f);
-            zeno::flipb200::download<FloatGrid>(holder, i, back);
+            zeno::flipb200_loopback::download<FloatGrid>(holder, i, back);
             ok = sameGrid(*w.flt[i], *back, why, fnames[i]);
         }
         if (ok) {
-            zeno::flipb200::upload_particles(holder, w.particles);
+            zeno::flipb200_loopback::upload_particles(holder, w.particles);
             PointDataGrid::Ptr back = PointDataGrid::create();
-            zeno::flipb200::download_particles(holder, back);
+            zeno::flipb200_loopback::download_particles(holder, back);
             ok = sameParticles(*w.particles, *back, why);
         }
     } catch (const std::exception& e) { ok = false; why = std::string("exception: ") + e.what(); }

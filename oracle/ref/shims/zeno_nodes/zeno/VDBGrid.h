@@ -1,0 +1,17 @@
+// TEST INFRASTRUCTURE ONLY. The socket object types of projects/zenvdb/include/zeno/VDBGrid.h:80-86,316-320
+// (VDBGridWrapper<GridT>{ GridT::Ptr m_grid; }) over the minimal IObject of this shim.
+#pragma once
+#include <zeno/zeno.h>
+#include <openvdb/openvdb.h>
+#include <openvdb/points/PointDataGrid.h>
+namespace zeno {
+template <typename GridT>
+struct VDBGridWrapper : IObject {
+    typename GridT::Ptr m_grid;
+    VDBGridWrapper() = default;
+    explicit VDBGridWrapper(typename GridT::Ptr g) : m_grid(std::move(g)) {}
+};
+using VDBFloatGrid = VDBGridWrapper<openvdb::FloatGrid>;
+using VDBFloat3Grid = VDBGridWrapper<openvdb::Vec3fGrid>;
+using VDBPointsGrid = VDBGridWrapper<openvdb::points::PointDataGrid>;
+}  // namespace zeno

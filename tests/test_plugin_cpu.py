@@ -112,3 +112,48 @@ def test_plugin_marshalling_roundtrips_real_reference_objects():
     msg = C.create_string_buffer(256)
     rc = lib.ref_plugin_roundtrip(w.h, msg, C.c_int(256))
     assert rc == 0, msg.value.decode()
+
+
+def test_plugin_nodes_reproduce_the_reference_nodes():
+    """The drop-in's NODE classes (same names, sockets, params), instantiated through a minimal stand-in of the Zeno node
+    runtime and wired to real OpenVDB objects the way the packaged graph wires them, with the CPU oracle behind the C ABI they
+    call (oracle/ref/plugin_nodes_test.cpp). Stage by stage from the reference's state:
+      * against the oracle driven directly (no plugin, no OpenVDB): bit-identical -> sockets, params, upload/download sets and
+        the marshalling add nothing;
+      * against the REAL reference nodes: within the oracle's own pinned tolerances (tests/test_ref_pin_cpu.py).
+    With the GPU parity tests (CUDA library == oracle through the same ABI) this closes the drop-in chain."""
+    import numpy as np
+    import pytest
+
+    from oracle import pyoracle
+    from tests import util
+    from zeno_b200 import scenes
+    if not pyoracle.ref_available():
+        pytest.skip("oracle/_ref was not built (no /root/reference here)")
+    if not hasattr(pyoracle.load_ref(), "pn_backend"):
+        pytest.skip("oracle/_ref predates the node harness")
+    from oracle.pyoracle import OracleWorld, PluginWorld, RefWorld
+    pyoracle.ref_set_threads(0)
+    N, dt = 40, 0.006
+    pos, vel, dx = scenes.dam_break_points(N, seed=11, random_velocity=True)
+    vel *= np.float32(0.25)
+    solid = scenes.box_solid_sdf(N, dx)
+    pw, ow, rw = PluginWorld(dx), OracleWorld(dx), RefWorld(dx)
+    for w in (pw, ow, rw):
+        w.set_grid("SolidSDF", solid)
+        w.PrimToVDBPointDataGrid(pos, vel)
+    for name, grids in util.REF_STAGES:
+        util.sync_state(ow, rw)
+        util.sync_state(pw, rw)
+        res = [util.run_ref_stage(w, name, dx, dt) for w in (pw, ow, rw)]
+        for g in grids:
+            util.compare_grids(pw.get_grid(g), ow.get_grid(g), f"plugin node vs oracle: {name}.{g}", tol=0.0, check_inactive=False)
+            util.compare_grids(pw.get_grid(g), rw.get_grid(g), f"plugin node vs reference node: {name}.{g}", tol=util.REF_TOL[name], check_inactive=False)
+        if name == "g2p":
+            a, b, c = (scenes.canonical_particles(w.get_particles()) for w in (pw, ow, rw))
+            assert np.array_equal(a, b), "plugin G2PAdvectorSheetty differs from the oracle driven directly"
+            m = util.particle_code_report(a, c)
+            assert a.shape == c.shape and m["same_voxel"] >= 0.999 and m["P_within_1lsb"] >= 0.999 and m["v_within_1ulp"] >= 0.999, m
+        if name == "grad":
+            cp, co, cr = pw.CFL_dt(), ow.CFL_dt(), rw.CFL_dt()
+            assert cp == co and abs(cp - cr) <= 1e-5 * cr, (cp, co, cr)

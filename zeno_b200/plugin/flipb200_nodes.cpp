@@ -151,7 +151,7 @@ void download(WorldHolder& h, int id, typename GridT::Ptr& g) {
     h.lastTree[id] = &g->tree(); h.lastLeaves[id] = g->tree().leafCount();
 }
 
-void upload_particles(WorldHolder& h, const openvdb::points::PointDataGrid::Ptr& g) {
+inline void upload_particles(WorldHolder& h, const openvdb::points::PointDataGrid::Ptr& g) {
     using Leaf = openvdb::points::PointDataTree::LeafNodeType;
     const void* treeKey = &g->tree();
     const size_t nLeaves = g->tree().leafCount();
@@ -184,7 +184,7 @@ void upload_particles(WorldHolder& h, const openvdb::points::PointDataGrid::Ptr&
     h.lastTree[FLIPB200_NUM_GRIDS] = treeKey; h.lastLeaves[FLIPB200_NUM_GRIDS] = nLeaves;
 }
 
-void download_particles(WorldHolder& h, openvdb::points::PointDataGrid::Ptr& g) {
+inline void download_particles(WorldHolder& h, openvdb::points::PointDataGrid::Ptr& g) {
     int nl = 0;
     uint64_t np = 0;
     check(flipb200_particles_info(h.w, &nl, &np), "particles_info");
