@@ -157,3 +157,32 @@ def test_plugin_nodes_reproduce_the_reference_nodes():
         if name == "grad":
             cp, co, cr = pw.CFL_dt(), ow.CFL_dt(), rw.CFL_dt()
             assert cp == co and abs(cp - cr) <= 1e-5 * cr, (cp, co, cr)
+
+
+def test_plugin_resident_mode():
+    """FLIPB200_RESIDENT=1 (grids stay on the device between accelerated nodes; an object is re-uploaded only when its
+    tree pointer or leaf count changed) must not change any result: two free-running substeps through the plugin nodes give
+    the same digest with and without it, and the same as the oracle driven directly."""
+    import subprocess
+    import sys
+
+    import pytest
+
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "pn_backend"):
+        pytest.skip("oracle/_ref with the node harness is not available here")
+    worker = os.path.join(ROOT, "tests", "plugin_resident_worker.py")
+
+    def digest(args, env_extra):
+        env = dict(os.environ)
+        env.pop("FLIPB200_RESIDENT", None)
+        env.update(env_extra)
+        r = subprocess.run([sys.executable, worker] + args, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return [ln.split()[1] for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
+
+    plain = digest([], {})
+    resident = digest([], {"FLIPB200_RESIDENT": "1"})
+    direct = digest(["oracle"], {})
+    assert plain == direct, "plugin nodes (upload-everything mode) differ from the oracle driven directly"
+    assert resident == plain, "FLIPB200_RESIDENT=1 changes the results"
