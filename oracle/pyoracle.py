@@ -257,7 +257,7 @@ class PluginWorld(OracleWorld):
 
     def _ck(self, rc):
         if rc != 0:
-            raise RuntimeError("plugin node failed: " + (self.lib.pn_last_error() or b"").decode())
+            raise RuntimeError("plugin node failed: " + (self.lib.orc_last_error() or b"").decode())
 
     def FLIP_P2G(self, dx=None, VelExtraLayer=3):
         self._ck(self.lib.orc_p2g(self.h, C.c_float(self.dx if dx is None else dx), C.c_int(VelExtraLayer)))
@@ -282,3 +282,24 @@ class PluginWorld(OracleWorld):
 
     def SubtractPressureGradient(self, dt, dx=None, VelExtraLayer=3):
         self._ck(self.lib.orc_subtract_grad(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.c_int(VelExtraLayer)))
+
+
+class RefNodeWorld(PluginWorld):
+    """Same interface, executed by the REFERENCE's own node classes (projects/FastFLIP/nosys/*.cpp compiled unmodified into
+    oracle/_ref, oracle/ref/ref_nodes_test.cpp, prefix rn_) on real OpenVDB objects."""
+    PREFIX = "rn_"
+
+    @classmethod
+    def _load(cls):
+        lib = load_ref()
+        if not getattr(lib, "_rn_ready", False):
+            lib.rn_world_create.restype = C.c_void_p
+            lib.rn_cfl.restype = C.c_float
+            lib.rn_dropped.restype = C.c_uint64
+            lib.rn_last_error.restype = C.c_char_p
+            lib._rn_ready = True
+        return lib
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError("reference node failed: " + (self.lib.orc_last_error() or b"").decode())

@@ -24,7 +24,7 @@ VDB="$REF/projects/zenvdb/openvdb/openvdb"
 FF="$REF/projects/FastFLIP"
 [ -d "$REF" ] || { echo "no $REF: keeping the prebuilt oracle/_ref"; exit 0; }
 PLUGIN_SRC="$HERE/../../zeno_b200/plugin/flipb200_nodes.cpp"
-if [ -f "$OUT/libflipref.so" ] && [ "$OUT/libflipref.so" -nt "$HERE/ref_driver.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/shims/Eigen/Eigen" ] && [ "$OUT/libflipref.so" -nt "$PLUGIN_SRC" ] && [ "$OUT/libflipref.so" -nt "$HERE/plugin_nodes_test.cpp" ] && [ -z "$FORCE" ]; then
+if [ -f "$OUT/libflipref.so" ] && [ "$OUT/libflipref.so" -nt "$HERE/ref_driver.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/shims/Eigen/Eigen" ] && [ "$OUT/libflipref.so" -nt "$PLUGIN_SRC" ] && [ "$OUT/libflipref.so" -nt "$HERE/plugin_nodes_test.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/ref_nodes_test.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/node_harness.inc" ] && [ -z "$FORCE" ]; then
   echo "oracle/_ref/libflipref.so is up to date"; exit 0
 fi
 mkdir -p "$OUT" "$BUILD/gen/openvdb" "$BUILD/vdbobj" "$BUILD/ffobj"
@@ -66,16 +66,17 @@ FFFLAGS="$COMMON -mavx -mfma -DZENO_APIFREE -I$HERE/shims/zeno_min -I$REF/projec
 : > "$BUILD/cmds.txt"
 # plugin_nodes_test.cpp compiles the drop-in's NODES against a minimal stand-in of the Zeno node runtime (shims/zeno_nodes,
 # searched before the real zeno headers) and without FLIP_vdb.h
-NODEFLAGS="$COMMON -I$HERE/shims/zeno_nodes -I$HERE/../../include"
-for s in "$FF/FLIP_vdb.cpp" "$FF/simd_vdb_poisson_uaamg.cpp" "$FF/vdb_velocity_extrapolator.cpp" "$FF/levelset_util.cpp" "$REF/projects/zenvdb/include/zeno/packed3grids.cpp" "$HERE/ref_driver.cpp" "$HERE/ref_stubs.cpp" "$HERE/plugin_nodes_test.cpp"; do
+NODEFLAGS="$COMMON -DZENO_APIFREE -I$HERE/shims/zeno_nodes -I$REF/zeno/include -I$HERE/../../include"
+for s in "$FF/FLIP_vdb.cpp" "$FF/simd_vdb_poisson_uaamg.cpp" "$FF/vdb_velocity_extrapolator.cpp" "$FF/levelset_util.cpp" "$REF/projects/zenvdb/include/zeno/packed3grids.cpp" "$HERE/ref_driver.cpp" "$HERE/ref_stubs.cpp" "$HERE/plugin_nodes_test.cpp" "$HERE/ref_nodes_test.cpp" "$HERE/zeno_error_impl.cpp"; do
   o="$BUILD/ffobj/$(basename $s .cpp).o"
   FL="$FFFLAGS"
   USES_PLUGIN=""
   case "$(basename $s)" in
     plugin_nodes_test.cpp) FL="$NODEFLAGS"; USES_PLUGIN=1 ;;
+    ref_nodes_test.cpp) FL="$COMMON -mavx -mfma -DZENO_APIFREE -I$HERE/shims/zeno_nodes -I$REF/projects/zenvdb/include -I$REF/zeno/include -I$FF -I$HERE/../../include" ;;
     ref_driver.cpp) USES_PLUGIN=1 ;;
   esac
-  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ "$HERE/shims/Eigen/Eigen" -nt "$o" ] || { [ -n "$USES_PLUGIN" ] && [ "$PLUGIN_SRC" -nt "$o" ]; } || { [ "$(basename $s)" = "plugin_nodes_test.cpp" ] && [ "$HERE/shims/zeno_nodes/zeno/zeno.h" -nt "$o" ]; }; then
+  if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ "$HERE/shims/Eigen/Eigen" -nt "$o" ] || { [ -n "$USES_PLUGIN" ] && [ "$PLUGIN_SRC" -nt "$o" ]; } || { case "$(basename $s)" in plugin_nodes_test.cpp|ref_nodes_test.cpp) [ "$HERE/shims/zeno_nodes/zeno/zeno.h" -nt "$o" ] || [ "$HERE/node_harness.inc" -nt "$o" ] ;; *) false ;; esac; }; then
     echo "$CXX $FL -c $s -o $o 2> $o.log || { grep -m 30 -E 'error|Error' $o.log; exit 255; }" >> "$BUILD/cmds.txt"
   fi
 done

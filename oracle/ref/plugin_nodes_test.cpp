@@ -109,65 +109,11 @@ int ob_add_vector(flipb200_world* w, float x, float y, float z) { return g_orc.a
 int ob_cfl(flipb200_world* w, float* dt) { *dt = g_orc.cfl(w->orc); return 0; }
 int ob_solve_ppe(flipb200_world* w, float dt, float dx, int* it, float* res, int* st) { return g_orc.solve(w->orc, dt, dx, it, res, st); }
 int ob_subtract_grad(flipb200_world* w, float dt, float dx, int n) { return g_orc.subtract(w->orc, dt, dx, n); }
-
-// ---- RefWorld access (ref_driver.cpp)
-void* ref_world_create(float dx);
-void ref_world_destroy(void* w);
-void* ref_internal_vec(void* w, int id);        // openvdb::Vec3fGrid::Ptr*
-void* ref_internal_flt(void* w, int id);        // openvdb::FloatGrid::Ptr*
-void* ref_internal_particles(void* w);          // openvdb::points::PointDataGrid::Ptr*
-int ref_grid_set(void*, int, int, const int32_t*, const uint64_t*, const float*, const float*);
-int ref_grid_leaf_count(void*, int);
-int ref_grid_get(void*, int, int32_t*, uint64_t*, float*, float*);
-int ref_particles_set(void*, int, const int32_t*, const uint32_t*, uint64_t, const uint16_t*, const uint16_t*);
-int ref_particles_info(void*, int*, uint64_t*);
-int ref_particles_get(void*, int32_t*, uint32_t*, uint16_t*, uint16_t*);
-int ref_bin_from_points(void*, const float*, const float*, uint64_t);
 }  // extern "C"
 
-// ---------------------------------------------------------------- the pn world: real OpenVDB objects + plugin nodes
-namespace {
-using namespace zeno;
-struct PnWorld {
-    void* ref;
-    float dx;
-    int iterations = 0, status = 0;
-    float relResidual = 0.f;
-    std::shared_ptr<VDBFloat3Grid> vec(int id) { return std::make_shared<VDBFloat3Grid>(*static_cast<openvdb::Vec3fGrid::Ptr*>(ref_internal_vec(ref, id))); }
-    std::shared_ptr<VDBFloatGrid> flt(int id) { return std::make_shared<VDBFloatGrid>(*static_cast<openvdb::FloatGrid::Ptr*>(ref_internal_flt(ref, id))); }
-    std::shared_ptr<VDBPointsGrid> pts() { return std::make_shared<VDBPointsGrid>(*static_cast<openvdb::points::PointDataGrid::Ptr*>(ref_internal_particles(ref))); }
-};
-std::shared_ptr<IObject> num(float v) { return std::make_shared<NumericObject>(v); }
-
-// runs node `name` with the given sockets / params; returns its outputs
-std::map<std::string, std::shared_ptr<IObject>> run(const char* name, std::map<std::string, std::shared_ptr<IObject>> in,
-                                                    std::map<std::string, ParamValue> params) {
-    auto it = nodeRegistry().find(name);
-    if (it == nodeRegistry().end()) throw std::runtime_error(std::string("the plugin does not register node ") + name);
-    // defaults of the descriptor's params, as the graph loader supplies them (zeno/src/core/Graph.cpp)
-    for (auto& p : it->second.desc.params) {
-        if (params.count(p.name)) continue;
-        const std::string first = p.defl.substr(0, p.defl.find(' '));
-        if (p.type == "int") params[p.name] = std::atoi(first.c_str());
-        else if (p.type == "float") params[p.name] = float(std::atof(first.c_str()));
-        else params[p.name] = p.defl;
-    }
-    // every wired socket must exist in the descriptor (the editor could not connect it otherwise)
-    for (auto& kv : in) {
-        bool known = false;
-        for (auto& s : it->second.desc.inputs) known = known || s.name == kv.first;
-        if (!known) throw std::runtime_error(std::string(name) + " has no input socket " + kv.first);
-    }
-    auto node = it->second.make();
-    node->inputs = std::move(in);
-    node->params = std::move(params);
-    node->apply();
-    return node->outputs;
-}
-template <typename F> int guarded(F&& f) {
-    try { f(); return 0; } catch (const std::exception& e) { g_err = e.what(); fprintf(stderr, "plugin node test: %s\n", e.what()); return 1; }
-}
-}  // namespace
+#define NH_FN(name) pn_##name
+#define NH_REGISTRY ::zeno::nodeRegistry()
+#include "node_harness.inc"
 
 extern "C" {
 int pn_backend(const char* liboracle) {
@@ -181,85 +127,6 @@ int pn_backend(const char* liboracle) {
         bind(g_orc.p2g, "orc_p2g"); bind(g_orc.g2p, "orc_g2p_advect_sheetty"); bind(g_orc.face_weights, "orc_face_weights");
         bind(g_orc.pushout, "orc_pushout_sdf"); bind(g_orc.add_vector, "orc_add_vector"); bind(g_orc.cfl, "orc_cfl");
         bind(g_orc.solve, "orc_solve_ppe"); bind(g_orc.subtract, "orc_subtract_grad");
-    });
-}
-const char* pn_last_error(void) { return g_err.c_str(); }
-void* pn_world_create(float dx) { return new PnWorld{ref_world_create(dx), dx}; }
-void pn_world_destroy(void* w) { auto* p = static_cast<PnWorld*>(w); ref_world_destroy(p->ref); delete p; }
-// data access: straight to the OpenVDB objects
-int pn_grid_set(void* w, int id, int n, const int32_t* o, const uint64_t* m, const float* v, const float* bg) { return ref_grid_set(static_cast<PnWorld*>(w)->ref, id, n, o, m, v, bg); }
-int pn_grid_leaf_count(void* w, int id) { return ref_grid_leaf_count(static_cast<PnWorld*>(w)->ref, id); }
-int pn_grid_get(void* w, int id, int32_t* o, uint64_t* m, float* v, float* bg) { return ref_grid_get(static_cast<PnWorld*>(w)->ref, id, o, m, v, bg); }
-int pn_particles_set(void* w, int nl, const int32_t* o, const uint32_t* ve, uint64_t n, const uint16_t* P, const uint16_t* v) { return ref_particles_set(static_cast<PnWorld*>(w)->ref, nl, o, ve, n, P, v); }
-int pn_particles_info(void* w, int* nl, uint64_t* n) { return ref_particles_info(static_cast<PnWorld*>(w)->ref, nl, n); }
-int pn_particles_get(void* w, int32_t* o, uint32_t* ve, uint16_t* P, uint16_t* v) { return ref_particles_get(static_cast<PnWorld*>(w)->ref, o, ve, P, v); }
-int pn_bin_from_points(void* w, const float* pos, const float* vel, uint64_t n) { return ref_bin_from_points(static_cast<PnWorld*>(w)->ref, pos, vel, n); }
-uint64_t pn_dropped(void*) { return 0; }
-
-// nodes, wired like the packaged sub-graphs (projects/tools/FLIPtools/stub.cpp:5-17); grid ids = include/flipb200.h
-int pn_p2g(void* wp, float dx, int velExtraLayer) {
-    auto& w = *static_cast<PnWorld*>(wp);
-    return guarded([&] {
-        run("FLIP_P2G", {{"Dx", num(dx)}, {"Particles", w.pts()}, {"Velocity", w.vec(FLIPB200_VELOCITY)},
-                         {"PostP2GVelocity", w.vec(FLIPB200_POSTADV_VELOCITY)}, {"LiquidSDF", w.flt(FLIPB200_LIQUID_SDF)}},
-            {{"VelExtraLayer", velExtraLayer}});
-    });
-}
-int pn_g2p_advect_sheetty(void* wp, float dt, float dx, int surfaceSize, int rkOrder, float picMin, float picMax, int flags) {
-    auto& w = *static_cast<PnWorld*>(wp);
-    return guarded([&] {
-        auto vel = w.vec(FLIPB200_VELOCITY);
-        std::shared_ptr<IObject> visc = (flags & 1) ? std::static_pointer_cast<IObject>(vel) : std::static_pointer_cast<IObject>(w.vec(FLIPB200_VISCOUS_VELOCITY));
-        // (flags & 1: the ViscousVelocity socket carries the Velocity OBJECT; the wrapper differs here but m_grid is the same pointer)
-        run("G2PAdvectorSheetty", {{"dt", num(dt)}, {"Dx", num(dx)}, {"pic_min", num(picMin)}, {"pic_max", num(picMax)}, {"Particles", w.pts()},
-                                   {"Velocity", vel}, {"ViscousVelocity", visc}, {"LiquidSDF", w.flt(FLIPB200_LIQUID_SDF)},
-                                   {"PostAdvVelocity", w.vec(FLIPB200_POSTADV_VELOCITY)}, {"SolidSDF", w.flt(FLIPB200_SOLID_SDF)},
-                                   {"SolidVelocity", w.vec(FLIPB200_SOLID_VELOCITY)}},
-            {{"RK_ORDER", rkOrder}, {"surface_size", surfaceSize}});
-    });
-}
-int pn_face_weights(void* wp) {
-    auto& w = *static_cast<PnWorld*>(wp);
-    return guarded([&] { run("CutCellWeight", {{"LiquidSDF", w.flt(FLIPB200_LIQUID_SDF)}, {"SolidSDF", w.flt(FLIPB200_SOLID_SDF)}, {"FaceWeight", w.vec(FLIPB200_FACE_WEIGHT)}}, {}); });
-}
-int pn_pushout_sdf(void* wp, float dx) {
-    auto& w = *static_cast<PnWorld*>(wp);
-    return guarded([&] { run("PushOutLiquidSDF", {{"Dx", num(dx)}, {"LiquidSDF", w.flt(FLIPB200_LIQUID_SDF)}, {"SolidSDF", w.flt(FLIPB200_SOLID_SDF)}}, {}); });
-}
-int pn_add_vector(void* wp, float x, float y, float z) {
-    auto& w = *static_cast<PnWorld*>(wp);
-    return guarded([&] { run("FieldAddVector", {{"invec3", std::make_shared<NumericObject>(vec3f(x, y, z))}, {"Velocity", w.vec(FLIPB200_VELOCITY)}}, {}); });
-}
-float pn_cfl(void* wp) {
-    auto& w = *static_cast<PnWorld*>(wp);
-    float out = -1.f;
-    guarded([&] {
-        auto res = run("CFL_dt", {{"Velocity", w.vec(FLIPB200_VELOCITY)}, {"Dx", num(w.dx)}}, {});
-        out = res.at("cfl_dt")->as<NumericObject>()->get<float>();
-    });
-    return out;
-}
-int pn_solve_ppe(void* wp, float dt, float dx, int* iters, float* relResidual, int* status) {
-    auto& w = *static_cast<PnWorld*>(wp);
-    int rc = guarded([&] {
-        run("AssembleSolvePPE", {{"dt", num(dt)}, {"Dx", num(dx)}, {"Density", num(1000.f)}, {"SurfaceTension", num(0.f)},
-                                 {"LiquidSDF", w.flt(FLIPB200_LIQUID_SDF)}, {"Divergence", w.flt(FLIPB200_DIVERGENCE)}, {"Pressure", w.flt(FLIPB200_PRESSURE)},
-                                 {"CellFWeight", w.vec(FLIPB200_FACE_WEIGHT)}, {"Velocity", w.vec(FLIPB200_VELOCITY)},
-                                 {"SolidVelocity", w.vec(FLIPB200_SOLID_VELOCITY)}, {"Curvature", w.flt(FLIPB200_CURVATURE)}}, {});
-    });
-    if (iters) *iters = -1;          // the node reports them on stdout only, like the reference's
-    if (relResidual) *relResidual = 0.f;
-    if (status) *status = rc;
-    return rc;
-}
-int pn_subtract_grad(void* wp, float dt, float dx, int velExtraLayer) {
-    auto& w = *static_cast<PnWorld*>(wp);
-    return guarded([&] {
-        run("SubtractPressureGradient", {{"dt", num(dt)}, {"Dx", num(dx)}, {"Density", num(1000.f)}, {"SurfaceTension", num(0.f)},
-                                         {"LiquidSDF", w.flt(FLIPB200_LIQUID_SDF)}, {"SolidSDF", w.flt(FLIPB200_SOLID_SDF)}, {"Pressure", w.flt(FLIPB200_PRESSURE)},
-                                         {"CellFWeight", w.vec(FLIPB200_FACE_WEIGHT)}, {"Velocity", w.vec(FLIPB200_VELOCITY)},
-                                         {"SolidVelocity", w.vec(FLIPB200_SOLID_VELOCITY)}, {"Curvature", w.flt(FLIPB200_CURVATURE)}},
-            {{"VelExtraLayer", velExtraLayer}});
     });
 }
 }  // extern "C"

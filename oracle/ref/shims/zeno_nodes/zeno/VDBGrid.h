@@ -4,6 +4,16 @@
 #include <zeno/zeno.h>
 #include <openvdb/openvdb.h>
 #include <openvdb/points/PointDataGrid.h>
+#if __has_include(<zeno/packed3grids.h>)
+#include <optional>
+#include <iostream>
+#include <openvdb/points/PointCount.h>
+#include <openvdb/tree/LeafManager.h>
+#include <openvdb/points/PointAdvect.h>
+#include <openvdb/tools/Morphology.h>
+#include <openvdb/tools/MeshToVolume.h>
+#include <zeno/packed3grids.h>   // FF/FLIP_vdb.h gets packed_FloatGrid3 through this header
+#endif
 namespace zeno {
 template <typename GridT>
 struct VDBGridWrapper : IObject {

@@ -13,4 +13,8 @@ struct NumericObject : IObject {
     }
     template <class T> void set(T v) { value = v; }
 };
+template <class T> T INode::get_input2(std::string const& id) const {
+    if (is_param(id)) return get_param<T>(id.substr(0, id.size() - 1));
+    return get_input<NumericObject>(id)->template get<T>();
+}
 }  // namespace zeno

@@ -14,22 +14,18 @@
 #include <vector>
 #include <array>
 #include <cstdio>
+// IObject is the reference's own (header-only under ZENO_APIFREE): packed_FloatGrid3 derives from it and crosses into the
+// FLIP_vdb statics compiled in other translation units, so its layout must be the real one
+#ifndef ZENO_APIFREE
+#define ZENO_APIFREE
+#endif
+#include <zeno/core/IObject.h>
 
 namespace zeno {
 
 struct vec3f : std::array<float, 3> {
     vec3f() : std::array<float, 3>{0.f, 0.f, 0.f} {}
     vec3f(float a, float b, float c) : std::array<float, 3>{a, b, c} {}
-};
-
-struct IObject : std::enable_shared_from_this<IObject> {
-    virtual ~IObject() = default;
-    template <class T> T* as() {
-        T* p = dynamic_cast<T*>(this);
-        if (!p) throw std::runtime_error("IObject::as: wrong object type on a socket");
-        return p;
-    }
-    template <class T, class... Ts> static std::shared_ptr<T> make(Ts&&... ts) { return std::make_shared<T>(std::forward<Ts>(ts)...); }
 };
 
 inline std::runtime_error makeError(const std::string& what) { return std::runtime_error(what); }
@@ -59,11 +55,20 @@ struct INode {
     std::map<std::string, ParamValue> params;
     virtual ~INode() = default;
     virtual void apply() = 0;
-    bool has_input(std::string const& id) const { return inputs.count(id) != 0; }
+    // a param is the input socket "<name>:" (zeno/include/zeno/core/INode.h:107-111)
+    static bool is_param(std::string const& id) { return !id.empty() && id.back() == ':'; }
+    bool has_input(std::string const& id) const {
+        return is_param(id) ? params.count(id.substr(0, id.size() - 1)) != 0 : inputs.count(id) != 0;
+    }
     std::shared_ptr<IObject> get_input(std::string const& id) const {
         auto it = inputs.find(id);
         if (it == inputs.end() || !it->second) throw std::runtime_error("INode::get_input: socket `" + id + "` is not connected");
         return it->second;
+    }
+    template <class T> std::shared_ptr<T> get_input(std::string const& id) const {
+        auto p = std::dynamic_pointer_cast<T>(get_input(id));
+        if (!p) throw std::runtime_error("INode::get_input<T>: socket `" + id + "` holds another object type");
+        return p;
     }
     template <class T> T get_param(std::string const& id) const {
         auto it = params.find(id);
@@ -72,6 +77,7 @@ struct INode {
         if constexpr (std::is_same_v<T, float>) { if (auto q = std::get_if<int>(&it->second)) return float(*q); }
         throw std::runtime_error("INode::get_param: param `" + id + "` has another type");
     }
+    template <class T> T get_input2(std::string const& id) const;   // literal of a NumericObject socket or of a param (NumericObject.h)
     void set_output(std::string const& id, std::shared_ptr<IObject> obj) { outputs[id] = std::move(obj); }
 };
 

@@ -70,3 +70,38 @@ def test_reference_fraction_inside_matches_oracle(oracle_lib):
         x = oracle_lib.orc_fraction_inside4(C.c_float(a), C.c_float(b), C.c_float(c), C.c_float(d))
         y = ref.ref_fraction_inside4(C.c_float(a), C.c_float(b), C.c_float(c), C.c_float(d))
         assert abs(x - y) <= 1e-6, (a, b, c, d, x, y)
+
+
+def test_ref_driver_equals_reference_nodes(oracle_lib):
+    """oracle/ref/ref_driver.cpp (ours) claims that every ref_<node> entry point performs exactly the calls of the node shim it
+    stands for. Here the reference's node classes themselves (FF/nosys/*.cpp, compiled unmodified and run through a minimal
+    stand-in of the Zeno node runtime, oracle/ref/ref_nodes_test.cpp) execute the same substep from the same state: every
+    grid, mask and particle must be bit-identical (single-threaded TBB, so the reference's own reductions are reproducible).
+    This anchors the fixtures, the oracle pinning and bench.py's CPU arm at the reference's nodes, not at our reading of them."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "rn_world_create"):
+        pytest.skip("oracle/_ref with the reference-node harness is not available here")
+    from oracle.pyoracle import RefNodeWorld, RefWorld
+    from zeno_b200 import scenes
+    pyoracle.ref_set_threads(1)
+    try:
+        N, dt = 40, 0.006
+        pos, vel, dx = scenes.dam_break_points(N, seed=11, random_velocity=True)
+        vel *= np.float32(0.25)
+        solid = scenes.box_solid_sdf(N, dx)
+        nw, rw = RefNodeWorld(dx), RefWorld(dx)
+        for w in (nw, rw):
+            w.set_grid("SolidSDF", solid)
+            w.PrimToVDBPointDataGrid(pos, vel)
+        for name, grids in util.REF_STAGES:
+            util.sync_state(nw, rw)
+            for w in (nw, rw):
+                util.run_ref_stage(w, name, dx, dt)
+            for g in grids:
+                util.compare_grids(nw.get_grid(g), rw.get_grid(g), f"reference node vs ref_driver: {name}.{g}", tol=0.0, check_inactive=False)
+            if name == "g2p":
+                util.compare_particles(nw.get_particles(), rw.get_particles(), "reference node vs ref_driver: advected particles")
+            if name == "grad":
+                assert nw.CFL_dt() == rw.CFL_dt()
+    finally:
+        pyoracle.ref_set_threads(0)
