@@ -76,7 +76,9 @@ def test_ref_driver_equals_reference_nodes(oracle_lib):
     """oracle/ref/ref_driver.cpp (ours) claims that every ref_<node> entry point performs exactly the calls of the node shim it
     stands for. Here the reference's node classes themselves (FF/nosys/*.cpp, compiled unmodified and run through a minimal
     stand-in of the Zeno node runtime, oracle/ref/ref_nodes_test.cpp) execute the same substep from the same state: every
-    grid, mask and particle must be bit-identical (single-threaded TBB, so the reference's own reductions are reproducible).
+    grid, mask and particle must be bit-identical -- except the pressure and the velocity projected with it, where the
+    reference's own TBB reductions associate differently from run to run (1e-6 relative L2 there; bit-identical too whenever
+    the TBB pool really is single-threaded, which a process that already ran multi-threaded reference code cannot guarantee).
     This anchors the fixtures, the oracle pinning and bench.py's CPU arm at the reference's nodes, not at our reading of them."""
     from oracle import pyoracle
     if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "rn_world_create"):
@@ -98,7 +100,8 @@ def test_ref_driver_equals_reference_nodes(oracle_lib):
             for w in (nw, rw):
                 util.run_ref_stage(w, name, dx, dt)
             for g in grids:
-                util.compare_grids(nw.get_grid(g), rw.get_grid(g), f"reference node vs ref_driver: {name}.{g}", tol=0.0, check_inactive=False)
+                tol = 1e-6 if (name, g) in (("ppe", "Pressure"), ("grad", "Velocity")) else 0.0
+                util.compare_grids(nw.get_grid(g), rw.get_grid(g), f"reference node vs ref_driver: {name}.{g}", tol=tol, check_inactive=False)
             if name == "g2p":
                 util.compare_particles(nw.get_particles(), rw.get_particles(), "reference node vs ref_driver: advected particles")
             if name == "grad":
