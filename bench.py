@@ -320,7 +320,7 @@ def main():
         except Exception:
             traffic = None
         roofline = {"kernel": dominant, "bound": "hbm", "achieved": d["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
-                    "frac": d["frac"], "traffic": traffic,
+                    "frac": d["frac"], "frac_of_nominal_8TBps": d["algorithmic_GBps"] / 8000.0, "traffic": traffic,
                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch (profiles/r01f_ncu_full_*; the mg_cycle capture predates the compact-row bottom of the cycle kernel)" if traffic is not None else None,
                     "algorithmic_bytes_per_launch": prof[dominant]["bytes"] / max(prof[dominant]["launches"], 1),
                     "peak_source": peak_src, "avg_launch_us": d["avg_us"],
