@@ -58,7 +58,8 @@ enum {
     FLIPB200_PRESSURE = 7,        /* "Pressure"          float */
     FLIPB200_DIVERGENCE = 8,      /* "Divergence"        float (the PPE right-hand side) */
     FLIPB200_CURVATURE = 9,       /* "Curvature"         float (unused: tension path is out of scope) */
-    FLIPB200_NUM_GRIDS = 10
+    FLIPB200_KILLER_SDF = 10,     /* "KillerSDF" socket of KillParticlesInSDF: any float grid, sampled in ITS index space */
+    FLIPB200_NUM_GRIDS = 11
 };
 enum { FLIPB200_SOA = 0, FLIPB200_AOS = 1 };
 
@@ -120,6 +121,11 @@ int flipb200_g2p_advect_sheetty(flipb200_world* w, float dt, float dx, int surfa
                                 float picMin, float picMax, int flags);
 /* particles dropped by the last advect (deep in solid, FF/FLIP_vdb.cpp:682-685, or voxel cap :711-714) */
 int flipb200_dropped(flipb200_world* w, uint64_t* n);
+/* KillParticlesInSDF (FF/nosys/KillParticles.cpp:13-165; SURVEY 8f-1, the first node beyond the substep chain): every particle
+ * samples float grid `sdfGrid` (normally FLIPB200_KILLER_SDF) with OpenVDB's BoxSampler at voxel + position IN THAT GRID'S INDEX
+ * SPACE and survives when the sample is <= 0 (keep != 0, OpType KEEP) or >= 0 (OpType DEL); survivors' positions go through the
+ * codec once more, as the reference's write-back does. */
+int flipb200_kill_particles_in_sdf(flipb200_world* w, int sdfGrid, int keep);
 /* debug: keep / fetch the fp32 position (index space) and velocity before the codecs, in the
  * order of the particle store the advect call started from (codec caveat). */
 int flipb200_capture_precodec(flipb200_world* w, int on);

@@ -304,4 +304,43 @@ void node_G2PAdvectorSheetty(World& w, float dt, float dx, int surfaceSize, int 
                                         float(surfaceSize) * dx, rkOrder);
 }
 
+// kill_particles_inside (FF/nosys/KillParticles.cpp:13-149): per leaf, per voxel, per particle in store order: the killer SDF is
+// sampled with openvdb's BoxSampler at voxel + decoded position -- a float sum (Coord + Vec3f, math/Coord.h) handed to the
+// sampler as doubles, in the SDF grid's OWN index space (no transform is applied) -- and the particle survives when the sample
+// is <= 0 (keep) / >= 0 (delete). Survivors are written back through the attribute write handles (:138-141), i.e. the
+// position goes decode -> encode once more (not the identity for 5461 of the 65536 fixed-point codes); the half velocity
+// round-trips exactly. Leaves stay in the tree even when they end up empty (clearAttributes, :117-118).
+void node_KillParticlesInSDF(World& w, const FloatGrid& sdf, bool keep) {
+    const Points& in = w.particles;
+    Points out;
+    out.dir = in.dir;
+    out.origins = in.origins;
+    out.voxelEnd.resize(in.leafCount());
+    out.P.reserve(in.P.size());
+    out.v.reserve(in.v.size());
+    for (int l = 0; l < in.leafCount(); l++) {
+        out.leafBegin.push_back(out.P.size() / 3);
+        const Coord o = in.origins[l];
+        uint32_t count = 0;
+        for (int off = 0; off < 512; off++) {
+            const uint32_t b = off ? in.voxelEnd[l][off - 1] : 0u, e = in.voxelEnd[l][off];
+            const int vx = o.x + (off >> 6), vy = o.y + ((off >> 3) & 7), vz = o.z + (off & 7);
+            for (uint32_t i = b; i < e; i++) {
+                const size_t gi = in.leafBegin[l] + i;
+                const float px = fxpt16_decode(in.P[3 * gi]), py = fxpt16_decode(in.P[3 * gi + 1]), pz = fxpt16_decode(in.P[3 * gi + 2]);
+                const float x = float(vx) + px, y = float(vy) + py, z = float(vz) + pz;
+                const float s = box_sample_f64(sdf, 0, double(x), double(y), double(z));
+                if (keep ? (s <= 0.f) : (s >= 0.f)) {
+                    out.P.push_back(fxpt16_encode(px)); out.P.push_back(fxpt16_encode(py)); out.P.push_back(fxpt16_encode(pz));
+                    for (int a = 0; a < 3; a++) out.v.push_back(half_encode(half_decode(in.v[3 * gi + a])));
+                    count++;
+                }
+            }
+            out.voxelEnd[l][off] = count;
+        }
+    }
+    out.leafBegin.push_back(out.P.size() / 3);
+    w.particles = std::move(out);
+}
+
 }  // namespace orc

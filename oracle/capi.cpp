@@ -9,7 +9,7 @@ using namespace orc;
 
 namespace {
 enum GridId { G_VELOCITY = 0, G_POSTADV = 1, G_VISCOUS = 2, G_SOLIDVEL = 3, G_FACEWEIGHT = 4,
-              G_LIQUIDSDF = 5, G_SOLIDSDF = 6, G_PRESSURE = 7, G_DIVERGENCE = 8, G_CURVATURE = 9 };
+              G_LIQUIDSDF = 5, G_SOLIDSDF = 6, G_PRESSURE = 7, G_DIVERGENCE = 8, G_CURVATURE = 9, G_KILLERSDF = 10 };
 Vec3Grid* vec3Of(World* w, int id) {
     switch (id) {
     case G_VELOCITY: return &w->velocity;
@@ -27,6 +27,7 @@ FloatGrid* floatOf(World* w, int id) {
     case G_PRESSURE: return &w->pressure;
     case G_DIVERGENCE: return &w->divergence;
     case G_CURVATURE: return &w->curvature;
+    case G_KILLERSDF: return &w->killerSDF;
     }
     return nullptr;
 }
@@ -137,6 +138,13 @@ int orc_g2p_advect_sheetty(void* wp, float dt, float dx, int surfaceSize, int rk
     World* w = static_cast<World*>(wp);
     if (flags & 1) w->viscousVelocity = w->velocity;
     node_G2PAdvectorSheetty(*w, dt, dx, surfaceSize, rkOrder, picMin, picMax);
+    return 0;
+}
+int orc_kill_particles(void* wp, int sdfGrid, int keep) {
+    World* w = static_cast<World*>(wp);
+    FloatGrid* g = floatOf(w, sdfGrid);
+    if (!g) return 1;
+    node_KillParticlesInSDF(*w, *g, keep != 0);
     return 0;
 }
 int orc_face_weights(void* wp) { node_CutCellWeight(*static_cast<World*>(wp)); return 0; }

@@ -28,7 +28,7 @@ struct World {
     float dx;
     Points particles;
     Vec3Grid velocity, postAdvVelocity, viscousVelocity, solidVelocity, faceWeight;
-    FloatGrid liquidSDF, solidSDF, pressure, divergence, curvature;
+    FloatGrid liquidSDF, solidSDF, pressure, divergence, curvature, killerSDF;
     bool hasSolidSDF = false, hasSolidVel = false;
     // diagnostics
     int pcgIterations = 0;
@@ -64,6 +64,9 @@ float node_CFL_dt(World& w);                                // FF/FLIP_vdb.cpp:3
 void node_AssembleSolvePPE(World& w, float dt, float dx);
 // FF/nosys/SubtractPressureGradient.cpp:25-66
 void node_SubtractPressureGradient(World& w, float dt, float dx, int velExtraLayer);
+
+// FF/nosys/KillParticles.cpp:13-158: keep the particles whose KillerSDF sample is <= 0 (keep) / >= 0 (delete)
+void node_KillParticlesInSDF(World& w, const FloatGrid& sdf, bool keep);
 
 float fraction_inside(float phi_left, float phi_right);  // FF/levelset_util.cpp:5-15
 float fraction_inside(float bl, float br, float tl, float tr);  // FF/levelset_util.cpp:26-99

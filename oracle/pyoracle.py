@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "_build", "liboracle.so")
 GRID_IDS = {
     "Velocity": 0, "PostAdvVelocity": 1, "ViscousVelocity": 2, "SolidVelocity": 3, "CellFWeight": 4,
-    "LiquidSDF": 5, "SolidSDF": 6, "Pressure": 7, "Divergence": 8, "Curvature": 9,
+    "LiquidSDF": 5, "SolidSDF": 6, "Pressure": 7, "Divergence": 8, "Curvature": 9, "KillerSDF": 10,
 }
 VEC_GRIDS = {"Velocity", "PostAdvVelocity", "ViscousVelocity", "SolidVelocity", "CellFWeight"}
 _lib = None
@@ -143,6 +143,11 @@ class OracleWorld:
     def G2PAdvectorSheetty(self, dt, dx=None, surface_size=4, RK_ORDER=1, pic_min=0.03, pic_max=0.05, viscous_is_velocity=True):
         self.lib.orc_g2p_advect_sheetty(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.c_int(surface_size),
                                         C.c_int(RK_ORDER), C.c_float(pic_min), C.c_float(pic_max), C.c_int(1 if viscous_is_velocity else 0))
+
+    def KillParticlesInSDF(self, sdf_grid: str = "KillerSDF", keep: bool = True):
+        rc = self.lib.orc_kill_particles(self.h, C.c_int(GRID_IDS[sdf_grid]), C.c_int(1 if keep else 0))
+        if rc != 0:
+            raise RuntimeError("KillParticlesInSDF failed")
 
     def dropped(self) -> int:
         return int(self.lib.orc_dropped(self.h))
@@ -282,6 +287,9 @@ class PluginWorld(OracleWorld):
 
     def SubtractPressureGradient(self, dt, dx=None, VelExtraLayer=3):
         self._ck(self.lib.orc_subtract_grad(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.c_int(VelExtraLayer)))
+
+    def KillParticlesInSDF(self, sdf_grid: str = "KillerSDF", keep: bool = True):
+        self._ck(self.lib.orc_kill_particles(self.h, C.c_int(GRID_IDS[sdf_grid]), C.c_int(1 if keep else 0)))
 
 
 class RefNodeWorld(PluginWorld):

@@ -48,14 +48,14 @@ using openvdb::Vec3fGrid;
 using openvdb::points::PointDataGrid;
 
 enum GridId { G_VELOCITY = 0, G_POSTADV = 1, G_VISCOUS = 2, G_SOLIDVEL = 3, G_FACEWEIGHT = 4,
-              G_LIQUIDSDF = 5, G_SOLIDSDF = 6, G_PRESSURE = 7, G_DIVERGENCE = 8, G_CURVATURE = 9 };
+              G_LIQUIDSDF = 5, G_SOLIDSDF = 6, G_PRESSURE = 7, G_DIVERGENCE = 8, G_CURVATURE = 9, G_KILLERSDF = 10, G_NUM = 11 };
 
 struct RefWorld {
     float dx;
     openvdb::math::Transform::Ptr centre, vertex;
     PointDataGrid::Ptr particles;
     Vec3fGrid::Ptr vec[5];
-    FloatGrid::Ptr flt[10];
+    FloatGrid::Ptr flt[G_NUM];
     bool hasSolidSDF = false, hasSolidVel = false, hasCurvature = false;
     int iterations = 0, status = 0, levels = 0, numDof = 0;
     float relResidual = 0.f;
@@ -75,7 +75,7 @@ struct RefWorld {
             vec[i]->setTransform(centre);
             vec[i]->setGridClass(openvdb::GridClass::GRID_STAGGERED);
         }
-        for (int i = 0; i < 10; i++) flt[i] = nullptr;
+        for (int i = 0; i < G_NUM; i++) flt[i] = nullptr;
         flt[G_PRESSURE] = FloatGrid::create(0.f);
         flt[G_PRESSURE]->setTransform(centre);
         flt[G_PRESSURE]->setGridClass(openvdb::GridClass::GRID_FOG_VOLUME);
@@ -87,6 +87,8 @@ struct RefWorld {
         flt[G_SOLIDSDF]->setTransform(vertex);
         flt[G_SOLIDSDF]->setGridClass(openvdb::GridClass::GRID_LEVEL_SET);
         flt[G_CURVATURE] = FloatGrid::create();
+        flt[G_KILLERSDF] = FloatGrid::create(3.0f * dx);   // the "KillerSDF" socket object of KillParticlesInSDF
+        flt[G_KILLERSDF]->setTransform(centre);
     }
 };
 
@@ -201,7 +203,7 @@ void ref_world_destroy(void* w) { delete static_cast<RefWorld*>(w); }
 int ref_grid_set(void* wp, int id, int nLeaves, const int32_t* origins, const uint64_t* masks, const float* values, const float* bg) {
     RefWorld* w = static_cast<RefWorld*>(wp);
     if (id >= 0 && id <= G_FACEWEIGHT) setVecGrid(*w->vec[id], nLeaves, origins, masks, values, bg);
-    else if (id < 10 && w->flt[id]) setFloatGrid(*w->flt[id], nLeaves, origins, masks, values, bg[0]);
+    else if (id < G_NUM && w->flt[id]) setFloatGrid(*w->flt[id], nLeaves, origins, masks, values, bg[0]);
     else return 1;
     if (id == G_SOLIDSDF) w->hasSolidSDF = true;
     if (id == G_SOLIDVEL) w->hasSolidVel = true;
@@ -211,17 +213,17 @@ int ref_grid_set(void* wp, int id, int nLeaves, const int32_t* origins, const ui
 int ref_grid_leaf_count(void* wp, int id) {
     RefWorld* w = static_cast<RefWorld*>(wp);
     if (id >= 0 && id <= G_FACEWEIGHT) return leafCountOf(*w->vec[id]);
-    if (id < 10 && w->flt[id]) return leafCountOf(*w->flt[id]);
+    if (id < G_NUM && w->flt[id]) return leafCountOf(*w->flt[id]);
     return -1;
 }
 // the OpenVDB objects themselves, for oracle/ref/plugin_nodes_test.cpp (pointers to the world's grid Ptrs)
 void* ref_internal_vec(void* wp, int id) { return (id >= 0 && id <= G_FACEWEIGHT) ? &static_cast<RefWorld*>(wp)->vec[id] : nullptr; }
-void* ref_internal_flt(void* wp, int id) { return (id > G_FACEWEIGHT && id < 10) ? &static_cast<RefWorld*>(wp)->flt[id] : nullptr; }
+void* ref_internal_flt(void* wp, int id) { return (id > G_FACEWEIGHT && id < G_NUM) ? &static_cast<RefWorld*>(wp)->flt[id] : nullptr; }
 void* ref_internal_particles(void* wp) { return &static_cast<RefWorld*>(wp)->particles; }
 int ref_grid_get(void* wp, int id, int32_t* origins, uint64_t* masks, float* values, float* bg) {
     RefWorld* w = static_cast<RefWorld*>(wp);
     if (id >= 0 && id <= G_FACEWEIGHT) getVecGrid(*w->vec[id], origins, masks, values, bg);
-    else if (id < 10 && w->flt[id]) getFloatGrid(*w->flt[id], origins, masks, values, bg);
+    else if (id < G_NUM && w->flt[id]) getFloatGrid(*w->flt[id], origins, masks, values, bg);
     else return 1;
     return 0;
 }

@@ -17,6 +17,10 @@
 #include <zeno/VDBGrid.h>
 #include <omp.h>
 #include <limits>
+#include <openvdb/points/PointCount.h>
+#include <openvdb/points/PointAdvect.h>
+#include <openvdb/tree/LeafManager.h>
+#include "levelset_util.h"
 #include "FLIP_vdb.h"
 #include "vdb_velocity_extrapolator.h"
 
@@ -40,6 +44,7 @@ namespace zeno { using namespace ::zeno; }
 #include "nosys/CFL.cpp"
 #include "nosys/SolvePoissonPressureEqn.cpp"
 #include "nosys/SubtractPressureGradient.cpp"
+#include "nosys/KillParticles.cpp"
 }  // namespace refnodes
 #undef defNodeClass
 

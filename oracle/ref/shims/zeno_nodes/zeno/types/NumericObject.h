@@ -15,6 +15,7 @@ struct NumericObject : IObject {
 };
 template <class T> T INode::get_input2(std::string const& id) const {
     if (is_param(id)) return get_param<T>(id.substr(0, id.size() - 1));
-    return get_input<NumericObject>(id)->template get<T>();
+    if constexpr (std::is_same_v<T, std::string>) throw std::runtime_error("INode::get_input2<string>: `" + id + "` is not a param");
+    else return get_input<NumericObject>(id)->template get<T>();
 }
 }  // namespace zeno

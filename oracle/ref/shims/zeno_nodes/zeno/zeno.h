@@ -91,3 +91,6 @@ int defNodeClass(std::string const& name, Descriptor const& desc = {}) {
 }
 
 }  // namespace zeno
+
+// zeno/include/zeno/core/defNode.h:28-34
+#define ZENDEFNODE(Class, ...) static int def##Class = zeno::defNodeClass<Class>(#Class, __VA_ARGS__)

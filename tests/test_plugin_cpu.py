@@ -9,7 +9,8 @@ PLUGIN = os.path.join(ROOT, "zeno_b200", "plugin", "flipb200_nodes.cpp")
 REF = "/root/reference/projects/FastFLIP/nosys"
 REF_FILES = {"FLIP_P2G": "P2G.cpp", "G2PAdvectorSheetty": "SheetG2PAdvector.cpp", "AssembleSolvePPE": "SolvePoissonPressureEqn.cpp",
              "SubtractPressureGradient": "SubtractPressureGradient.cpp", "CutCellWeight": "EvalFaceWeight.cpp",
-             "PushOutLiquidSDF": "FixLiquidSDF.cpp", "FieldAddVector": "FieldAddVector.cpp", "CFL_dt": "CFL.cpp"}
+             "PushOutLiquidSDF": "FixLiquidSDF.cpp", "FieldAddVector": "FieldAddVector.cpp", "CFL_dt": "CFL.cpp",
+             "KillParticlesInSDF": "KillParticles.cpp"}
 # (inputs, outputs, params) by name only, recorded from the reference files above
 EXPECTED = {
     "FLIP_P2G": (["Dx", "Particles", "Velocity", "PostP2GVelocity", "LiquidSDF"], [], ["dx", "VelExtraLayer"]),
@@ -23,6 +24,7 @@ EXPECTED = {
     "PushOutLiquidSDF": (["Dx", "LiquidSDF", "SolidSDF"], [], ["dx"]),
     "FieldAddVector": (["invec3", "Velocity", "FieldWeight"], [], []),
     "CFL_dt": (["Velocity", "Dx"], ["cfl_dt"], ["dx"]),
+    "KillParticlesInSDF": (["Particles", "KillerSDF"], ["Particles"], ["OpType"]),
 }
 
 
@@ -31,7 +33,8 @@ def descriptors(text):
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     text = re.sub(r"//[^\n]*", "", text)
     out = {}
-    for m in re.finditer(r'defNodeClass<\w+>\(\s*"(\w+)"\s*,', text):
+    # both registration forms: defNodeClass<T>("name", {...}) and ZENDEFNODE(name, {...}) (zeno/core/defNode.h:28-34)
+    for m in list(re.finditer(r'defNodeClass<\w+>\(\s*"(\w+)"\s*,', text)) + list(re.finditer(r'ZENDEFNODE\(\s*(\w+)\s*,', text)):
         i = text.index("{", m.end())
         depth, j = 0, i
         while True:

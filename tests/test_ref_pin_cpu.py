@@ -108,3 +108,31 @@ def test_ref_driver_equals_reference_nodes(oracle_lib):
                 assert nw.CFL_dt() == rw.CFL_dt()
     finally:
         pyoracle.ref_set_threads(0)
+
+
+@pytest.mark.parametrize("keep", [True, False], ids=["KEEP", "DEL"])
+def test_kill_particles_in_sdf_oracle_plugin_and_reference_node(oracle_lib, keep):
+    """SURVEY 8f-1, the first node beyond the substep chain. The REAL reference node class (FF/nosys/KillParticles.cpp, unmodified,
+    through the node-runtime stand-in), the oracle restatement and the drop-in's node (oracle behind the C ABI) filter the same
+    particle set with the same killer SDF: survivors identical code for code (the reference re-encodes positions on write-back)."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "rn_kill_particles"):
+        pytest.skip("oracle/_ref with the reference-node harness is not available here")
+    from oracle.pyoracle import OracleWorld, PluginWorld, RefNodeWorld
+    from zeno_b200 import scenes
+    N = 32
+    pos, vel, dx = scenes.dam_break_points(N, seed=9, random_velocity=True)
+    killer = scenes.sphere_sdf(centre=(3.3, 4.1, 2.7), radius=4.6, lo=(-8, -8, -8), hi=(16, 16, 16), bg=3.0)
+    worlds = [cls(dx) for cls in (RefNodeWorld, OracleWorld, PluginWorld)]
+    for w in worlds:
+        w.PrimToVDBPointDataGrid(pos, vel)
+        w.set_grid("KillerSDF", killer)
+    n0 = worlds[0].particles_info()[1]
+    for w in worlds:
+        w.KillParticlesInSDF("KillerSDF", keep)
+    ref = scenes.canonical_particles(worlds[0].get_particles())
+    assert 0 < ref.shape[0] < n0, "the test shape must cut the particle set"
+    for w, what in zip(worlds[1:], ("oracle", "plugin node")):
+        got = scenes.canonical_particles(w.get_particles())
+        assert got.shape == ref.shape, f"{what}: {got.shape[0]} survivors vs {ref.shape[0]} in the reference node"
+        assert np.array_equal(got, ref), f"{what}: surviving particles differ from the reference node"

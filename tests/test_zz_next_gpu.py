@@ -1,0 +1,44 @@
+"""GPU parity of the first node beyond the substep chain: KillParticlesInSDF.
+
+The CPU side of this node is pinned in tests/test_ref_pin_cpu.py (the reference's own node class == oracle == the drop-in's node).
+This file compares the CUDA implementation with the oracle through the C ABI. It was written after the round's GPU budget was
+spent, so its first execution is the driver's round-end run: the expected-failure marker is non-strict and says so.
+"""
+import numpy as np
+import pytest
+
+from tests import util
+from zeno_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+FIRST_RUN = pytest.mark.xfail(strict=False, reason="written after the round-1 GPU budget was spent: the first GPU run is the driver's round-end run")
+
+
+@FIRST_RUN
+@pytest.mark.parametrize("keep", [True, False], ids=["KEEP", "DEL"])
+def test_kill_particles_in_sdf_matches_oracle(gpu_lib, oracle_lib, keep):
+    from oracle.pyoracle import OracleWorld
+    from zeno_b200 import abi
+    N = 32
+    pos, vel, dx = scenes.dam_break_points(N, seed=9, random_velocity=True)
+    killer = scenes.sphere_sdf(centre=(3.3, 4.1, 2.7), radius=4.6, lo=(-8, -8, -8), hi=(16, 16, 16), bg=3.0)
+    gw, ow = abi.World(dx), OracleWorld(dx)
+    for w in (gw, ow):
+        w.PrimToVDBPointDataGrid(pos, vel)
+        w.set_grid("KillerSDF", killer)
+    n0 = gw.particles_info()[1]
+    for w in (gw, ow):
+        w.KillParticlesInSDF("KillerSDF", keep)
+    a = scenes.canonical_particles(gw.get_particles())
+    b = scenes.canonical_particles(ow.get_particles())
+    assert 0 < b.shape[0] < n0
+    assert a.shape == b.shape, f"{a.shape[0]} survivors on the GPU vs {b.shape[0]} in the oracle"
+    assert np.array_equal(a, b), "surviving particles differ from the oracle"
+    util.check_store_invariants(gw.get_particles())
+    # the filtered store is a valid input of the next node
+    for w in (gw, ow):
+        w.FLIP_P2G(dx, 3)
+    for name in ("Velocity", "LiquidSDF"):
+        util.compare_grids(gw.get_grid(name), ow.get_grid(name), f"P2G after KillParticlesInSDF: {name}", tol=0.0, check_inactive=False)
+    gw.close()

@@ -19,7 +19,7 @@ import numpy as np
 
 GRID_IDS = {
     "Velocity": 0, "PostAdvVelocity": 1, "ViscousVelocity": 2, "SolidVelocity": 3, "CellFWeight": 4,
-    "LiquidSDF": 5, "SolidSDF": 6, "Pressure": 7, "Divergence": 8, "Curvature": 9,
+    "LiquidSDF": 5, "SolidSDF": 6, "Pressure": 7, "Divergence": 8, "Curvature": 9, "KillerSDF": 10,
 }
 VEC_GRIDS = {"Velocity", "PostAdvVelocity", "ViscousVelocity", "SolidVelocity", "CellFWeight"}
 SOA, AOS = 0, 1
@@ -39,7 +39,7 @@ EXPORTS = [
     "flipb200_profile_reset", "flipb200_profile_get", "flipb200_stream", "flipb200_comm_unique_id",
     "flipb200_comm_init", "flipb200_comm_init_local", "flipb200_comm_abort", "flipb200_dd_set_slab", "flipb200_dd_owned",
     "flipb200_dd_owned_particles",
-    "flipb200_sync_count", "flipb200_particles_download_begin", "flipb200_grid_download_begin", "flipb200_download_wait",
+    "flipb200_sync_count", "flipb200_kill_particles_in_sdf", "flipb200_particles_download_begin", "flipb200_grid_download_begin", "flipb200_download_wait",
 ]
 
 
@@ -226,6 +226,9 @@ class World:
         self._ck(self.lib.flipb200_g2p_advect_sheetty(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx),
                                                       C.c_int(surface_size), C.c_int(RK_ORDER), C.c_float(pic_min),
                                                       C.c_float(pic_max), C.c_int(1 if viscous_is_velocity else 0)))
+
+    def KillParticlesInSDF(self, sdf_grid: str = "KillerSDF", keep: bool = True):
+        self._ck(self.lib.flipb200_kill_particles_in_sdf(self.h, C.c_int(GRID_IDS[sdf_grid]), C.c_int(1 if keep else 0)))
 
     def dropped(self) -> int:
         n = C.c_uint64(0)

@@ -539,6 +539,14 @@ int flipb200_g2p_advect_sheetty(flipb200_world* w, float dt, float dx, int surfa
         sync(w);
     });
 }
+int flipb200_kill_particles_in_sdf(flipb200_world* w, int sdfGrid, int keep) {
+    return guarded([&] {
+        FB_REQUIRE(w, FLIPB200_ERR_ARG, "kill_particles_in_sdf: null world");
+        use_device(w);
+        kill_particles_in_sdf(w, sdfGrid, keep != 0);
+        sync(w);
+    });
+}
 int flipb200_dropped(flipb200_world* w, uint64_t* n) {
     return guarded([&] { FB_REQUIRE(w && n, FLIPB200_ERR_ARG, "dropped: bad argument"); *n = w->dropped; });
 }

@@ -39,7 +39,7 @@ struct flipb200_world {
     uint64_t epochCounter = 0;
 
     fb::GridV vgrid[5];   // ids 0..4
-    fb::GridF fgrid[10];  // ids 5..9 used
+    fb::GridF fgrid[FLIPB200_NUM_GRIDS];  // ids 5..10 used
     bool hasSolidSDF = false, hasSolidVel = false;
     fb::Particles pts;
 
@@ -182,6 +182,8 @@ void exclusive_scan_u32(World* w, const uint32_t* in, uint32_t* out, size_t n, u
 // ---- particles.cu -------------------------------------------------------------------
 void bin_from_points(World* w, const float* pos_host, const float* vel_host, uint64_t n);
 // re-bin after advect: keys = target (pool slot*512 + off) or 0xffffffff for dropped particles
+// KillParticlesInSDF (FF/nosys/KillParticles.cpp): drop the particles the killer SDF (float grid sdfGrid) rejects
+void kill_particles_in_sdf(World* w, int sdfGrid, bool keep);
 void rebin_particles(World* w, const TopoPtr& newPool, const uint32_t* keys_dev, uint64_t nOld,
                      DBuf<uint32_t>& w0, DBuf<uint32_t>& w1, DBuf<uint32_t>& w2);
 

@@ -291,6 +291,24 @@ static int defG2PAdvectorSheet = zeno::defNodeClass<G2PAdvectorSheet>("G2PAdvect
      /* params: */ {{"float", "dx", "0.01 0.0"}, {"int", "RK_ORDER", "1 1 4"}, {"float", "pic_smoothness", "0.1 0.0 1.0"}, {"int", "surface_size", "4 0 8"}},
      /* category: */ {"FLIPSolver"}});
 
+// ---- KillParticlesInSDF (FF/nosys/KillParticles.cpp:150-165)
+struct KillParticlesInSDF : zeno::INode {
+    virtual void apply() override {
+        auto points = get_input("Particles")->as<VDBPointsGrid>();
+        auto sdf = get_input("KillerSDF")->as<VDBFloatGrid>();
+        const std::string op = has_input("OpType:") ? get_param<std::string>("OpType") : std::string("KEEP");
+        WorldHolder& h = world_for(float(points->m_grid->voxelSize()[0]));
+        upload_particles(h, points->m_grid);
+        upload<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, sdf->m_grid);
+        check(flipb200_kill_particles_in_sdf(h.w, FLIPB200_KILLER_SDF, op == "KEEP" ? 1 : 0), "KillParticlesInSDF");
+        download_particles(h, points->m_grid);
+        set_output("Particles", get_input("Particles"));
+    }
+};
+static int defKillParticlesInSDF = zeno::defNodeClass<KillParticlesInSDF>("KillParticlesInSDF",
+    {/* inputs: */ {"Particles", "KillerSDF"}, /* outputs: */ {"Particles"}, /* params: */ {{"enum KEEP DEL", "OpType", "KEEP"}},
+     /* category: */ {"FLIPSolver"}});
+
 // ---- CutCellWeight (FF/nosys/EvalFaceWeight.cpp:17-41)
 struct CutCellWeightEval : zeno::INode {
     virtual void apply() override {

@@ -129,3 +129,22 @@ def canonical_particles(p: Dict[str, np.ndarray]) -> np.ndarray:
     full = np.concatenate([rows, p["P"].astype(np.int64), p["v"].astype(np.int64)], axis=1)
     order = np.lexsort(tuple(full[:, k] for k in range(8, -1, -1)))
     return full[order]
+
+
+def sphere_sdf(centre, radius: float, lo, hi, bg: float = 3.0) -> Dict[str, np.ndarray]:
+    """A float grid in flat leaf layout holding (|ijk - centre| - radius) on every leaf that overlaps the voxel box [lo, hi)
+    (index space, unit = voxels), clamped to +-bg, all voxels active. A generic "killer" / sink shape for tests."""
+    lo = (np.asarray(lo) // 8) * 8
+    hi = -((-np.asarray(hi)) // 8) * 8
+    ax = [np.arange(lo[a], hi[a], 8) for a in range(3)]
+    ox, oy, oz = np.meshgrid(*ax, indexing="ij")
+    origins = np.stack([ox.ravel(), oy.ravel(), oz.ravel()], axis=1).astype(np.int32)
+    n = origins.shape[0]
+    r = np.arange(8)
+    X = (origins[:, 0, None] + r[None, :]).astype(np.float32) - np.float32(centre[0])
+    Y = (origins[:, 1, None] + r[None, :]).astype(np.float32) - np.float32(centre[1])
+    Z = (origins[:, 2, None] + r[None, :]).astype(np.float32) - np.float32(centre[2])
+    d = np.sqrt(X[:, :, None, None] ** 2 + Y[:, None, :, None] ** 2 + Z[:, None, None, :] ** 2) - np.float32(radius)
+    values = np.clip(d, -bg, bg).astype(np.float32).reshape(n, 1, 512)
+    masks = np.full((n, 8), np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64)
+    return {"origins": origins, "masks": masks, "values": values, "bg": np.array([bg], np.float32)}
