@@ -121,6 +121,10 @@ int flipb200_g2p_advect_sheetty(flipb200_world* w, float dt, float dx, int surfa
                                 float picMin, float picMax, int flags);
 /* particles dropped by the last advect (deep in solid, FF/FLIP_vdb.cpp:682-685, or voxel cap :711-714) */
 int flipb200_dropped(flipb200_world* w, uint64_t* n);
+/* ParticleAddDV (FF/nosys/ParticleAddGravity.cpp:9-19 -> FLIP_vdb::point_integrate_vector, FF/FLIP_vdb.cpp:3492-3535; SURVEY 8b
+ * last row / 8f-1): adds dv to the stored velocity of every particle -- read as double from the half codec, summed in double,
+ * written back float -> half. Positions are untouched. */
+int flipb200_particles_add_dv(flipb200_world* w, float dvx, float dvy, float dvz);
 /* KillParticlesInSDF (FF/nosys/KillParticles.cpp:13-165; SURVEY 8f-1, the first node beyond the substep chain): every particle
  * samples float grid `sdfGrid` (normally FLIPB200_KILLER_SDF) with OpenVDB's BoxSampler at voxel + position IN THAT GRID'S INDEX
  * SPACE and survives when the sample is <= 0 (keep != 0, OpType KEEP) or >= 0 (OpType DEL); survivors' positions go through the

@@ -343,4 +343,17 @@ void node_KillParticlesInSDF(World& w, const FloatGrid& sdf, bool keep) {
     w.particles = std::move(out);
 }
 
+// FLIP_vdb::point_integrate_vector, channel "vel" (FF/FLIP_vdb.cpp:3492-3535): v is read as Vec3R (half -> float -> double),
+// dv (a Vec3R built from the node's float vec3) is added in double, and the sum goes back through the Vec3f write handle:
+// double -> float (round to nearest) -> half (TruncateCodec, round to nearest even). Positions are untouched.
+void node_ParticleAddDV(World& w, float dvx, float dvy, float dvz) {
+    const double dv[3] = {double(dvx), double(dvy), double(dvz)};
+    Points& p = w.particles;
+    for (size_t i = 0; i < p.size(); i++)
+        for (int a = 0; a < 3; a++) {
+            const double v = double(half_decode(p.v[3 * i + a])) + dv[a];
+            p.v[3 * i + a] = half_encode(float(v));
+        }
+}
+
 }  // namespace orc

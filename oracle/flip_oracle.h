@@ -68,6 +68,9 @@ void node_SubtractPressureGradient(World& w, float dt, float dx, int velExtraLay
 // FF/nosys/KillParticles.cpp:13-158: keep the particles whose KillerSDF sample is <= 0 (keep) / >= 0 (delete)
 void node_KillParticlesInSDF(World& w, const FloatGrid& sdf, bool keep);
 
+// FF/nosys/ParticleAddGravity.cpp:9-19 -> FLIP_vdb::point_integrate_vector (FF/FLIP_vdb.cpp:3492-3535)
+void node_ParticleAddDV(World& w, float dvx, float dvy, float dvz);
+
 float fraction_inside(float phi_left, float phi_right);  // FF/levelset_util.cpp:5-15
 float fraction_inside(float bl, float br, float tl, float tr);  // FF/levelset_util.cpp:26-99
 

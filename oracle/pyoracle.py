@@ -149,6 +149,11 @@ class OracleWorld:
         if rc != 0:
             raise RuntimeError("KillParticlesInSDF failed")
 
+    def ParticleAddDV(self, x, y, z):
+        rc = self.lib.orc_particles_add_dv(self.h, C.c_float(x), C.c_float(y), C.c_float(z))
+        if rc != 0:
+            raise RuntimeError("ParticleAddDV failed")
+
     def dropped(self) -> int:
         return int(self.lib.orc_dropped(self.h))
 
@@ -290,6 +295,9 @@ class PluginWorld(OracleWorld):
 
     def KillParticlesInSDF(self, sdf_grid: str = "KillerSDF", keep: bool = True):
         self._ck(self.lib.orc_kill_particles(self.h, C.c_int(GRID_IDS[sdf_grid]), C.c_int(1 if keep else 0)))
+
+    def ParticleAddDV(self, x, y, z):
+        self._ck(self.lib.orc_particles_add_dv(self.h, C.c_float(x), C.c_float(y), C.c_float(z)))
 
 
 class RefNodeWorld(PluginWorld):

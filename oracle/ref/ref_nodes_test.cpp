@@ -45,6 +45,7 @@ namespace zeno { using namespace ::zeno; }
 #include "nosys/SolvePoissonPressureEqn.cpp"
 #include "nosys/SubtractPressureGradient.cpp"
 #include "nosys/KillParticles.cpp"
+#include "nosys/ParticleAddGravity.cpp"     // ParticleAddDV
 }  // namespace refnodes
 #undef defNodeClass
 

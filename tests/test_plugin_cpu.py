@@ -10,7 +10,7 @@ REF = "/root/reference/projects/FastFLIP/nosys"
 REF_FILES = {"FLIP_P2G": "P2G.cpp", "G2PAdvectorSheetty": "SheetG2PAdvector.cpp", "AssembleSolvePPE": "SolvePoissonPressureEqn.cpp",
              "SubtractPressureGradient": "SubtractPressureGradient.cpp", "CutCellWeight": "EvalFaceWeight.cpp",
              "PushOutLiquidSDF": "FixLiquidSDF.cpp", "FieldAddVector": "FieldAddVector.cpp", "CFL_dt": "CFL.cpp",
-             "KillParticlesInSDF": "KillParticles.cpp"}
+             "KillParticlesInSDF": "KillParticles.cpp", "ParticleAddDV": "ParticleAddGravity.cpp"}
 # (inputs, outputs, params) by name only, recorded from the reference files above
 EXPECTED = {
     "FLIP_P2G": (["Dx", "Particles", "Velocity", "PostP2GVelocity", "LiquidSDF"], [], ["dx", "VelExtraLayer"]),
@@ -25,6 +25,7 @@ EXPECTED = {
     "FieldAddVector": (["invec3", "Velocity", "FieldWeight"], [], []),
     "CFL_dt": (["Velocity", "Dx"], ["cfl_dt"], ["dx"]),
     "KillParticlesInSDF": (["Particles", "KillerSDF"], ["Particles"], ["OpType"]),
+    "ParticleAddDV": (["Particles", "dv"], [], ["channel", "vx", "vy", "vz"]),
 }
 
 

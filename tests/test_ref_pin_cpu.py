@@ -136,3 +136,25 @@ def test_kill_particles_in_sdf_oracle_plugin_and_reference_node(oracle_lib, keep
         got = scenes.canonical_particles(w.get_particles())
         assert got.shape == ref.shape, f"{what}: {got.shape[0]} survivors vs {ref.shape[0]} in the reference node"
         assert np.array_equal(got, ref), f"{what}: surviving particles differ from the reference node"
+
+
+def test_particle_add_dv_oracle_plugin_and_reference_node(oracle_lib):
+    """ParticleAddDV (FF/nosys/ParticleAddGravity.cpp -> FLIP_vdb::point_integrate_vector): the reference's node class, the oracle
+    and the drop-in's node give the same half-precision velocities, bit for bit; positions and binning untouched."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "rn_particles_add_dv"):
+        pytest.skip("oracle/_ref with the reference-node harness is not available here")
+    from oracle.pyoracle import OracleWorld, PluginWorld, RefNodeWorld
+    from zeno_b200 import scenes
+    pos, vel, dx = scenes.dam_break_points(32, seed=2, random_velocity=True)
+    worlds = [cls(dx) for cls in (RefNodeWorld, OracleWorld, PluginWorld)]
+    for w in worlds:
+        w.PrimToVDBPointDataGrid(pos, vel)
+    before = scenes.canonical_particles(worlds[0].get_particles())
+    for w in worlds:
+        w.ParticleAddDV(0.013, -0.1633333, 1.0e-4)
+    ref = worlds[0].get_particles()
+    after = scenes.canonical_particles(ref)
+    assert np.array_equal(after[:, :6], before[:, :6]) and not np.array_equal(after[:, 6:], before[:, 6:])
+    for w, what in zip(worlds[1:], ("oracle", "plugin node")):
+        util.compare_particles(w.get_particles(), ref, f"ParticleAddDV: {what} vs the reference node")

@@ -42,3 +42,16 @@ def test_kill_particles_in_sdf_matches_oracle(gpu_lib, oracle_lib, keep):
     for name in ("Velocity", "LiquidSDF"):
         util.compare_grids(gw.get_grid(name), ow.get_grid(name), f"P2G after KillParticlesInSDF: {name}", tol=0.0, check_inactive=False)
     gw.close()
+
+
+@FIRST_RUN
+def test_particle_add_dv_matches_oracle(gpu_lib, oracle_lib):
+    from oracle.pyoracle import OracleWorld
+    from zeno_b200 import abi
+    pos, vel, dx = scenes.dam_break_points(32, seed=2, random_velocity=True)
+    gw, ow = abi.World(dx), OracleWorld(dx)
+    for w in (gw, ow):
+        w.PrimToVDBPointDataGrid(pos, vel)
+        w.ParticleAddDV(0.013, -0.1633333, 1.0e-4)
+    util.compare_particles(gw.get_particles(), ow.get_particles(), "ParticleAddDV vs oracle")
+    gw.close()

@@ -547,6 +547,14 @@ int flipb200_kill_particles_in_sdf(flipb200_world* w, int sdfGrid, int keep) {
         sync(w);
     });
 }
+int flipb200_particles_add_dv(flipb200_world* w, float dvx, float dvy, float dvz) {
+    return guarded([&] {
+        FB_REQUIRE(w, FLIPB200_ERR_ARG, "particles_add_dv: null world");
+        use_device(w);
+        particles_add_dv(w, dvx, dvy, dvz);
+        sync(w);
+    });
+}
 int flipb200_dropped(flipb200_world* w, uint64_t* n) {
     return guarded([&] { FB_REQUIRE(w && n, FLIPB200_ERR_ARG, "dropped: bad argument"); *n = w->dropped; });
 }

@@ -245,6 +245,28 @@ __global__ void __launch_bounds__(256) kill_keys_kernel(TopoView pt, const uint3
 }
 }  // namespace
 
+namespace {
+// FLIP_vdb::point_integrate_vector, channel "vel" (FF/FLIP_vdb.cpp:3526-3532): half -> double, + dv, -> float -> half
+__global__ void add_dv_kernel(uint32_t* __restrict__ w1, uint32_t* __restrict__ w2, uint64_t n, double dx, double dy, double dz) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t b = w1[i], c = w2[i];
+    const float vx = __double2float_rn(__dadd_rn((double)h_decode(b >> 16), dx));
+    const float vy = __double2float_rn(__dadd_rn((double)h_decode(c & 0xffffu), dy));
+    const float vz = __double2float_rn(__dadd_rn((double)h_decode(c >> 16), dz));
+    w1[i] = (b & 0xffffu) | (h_encode(vx) << 16);
+    w2[i] = h_encode(vy) | (h_encode(vz) << 16);
+}
+}  // namespace
+
+void particles_add_dv(World* w, float dvx, float dvy, float dvz) {
+    FB_REQUIRE(w->pts.topo != nullptr, FLIPB200_ERR_STATE, "ParticleAddDV: no particles");
+    const uint64_t n = w->pts.n;
+    if (!n) return;
+    FB_LAUNCH(w, "particles_add_dv", n * 16) add_dv_kernel<<<nblk(n, 256), 256, 0, w->stream>>>(w->pts.w1.p, w->pts.w2.p, n, (double)dvx, (double)dvy, (double)dvz);
+    check_launch("add_dv");
+}
+
 void kill_particles_in_sdf(World* w, int sdfGrid, bool keep) {
     FB_REQUIRE(w->pts.topo != nullptr, FLIPB200_ERR_STATE, "KillParticlesInSDF: no particles");
     FB_REQUIRE(is_float_grid(sdfGrid) && w->F(sdfGrid).topo != nullptr, FLIPB200_ERR_STATE, "KillParticlesInSDF: the killer SDF grid was not uploaded");

@@ -184,6 +184,8 @@ void bin_from_points(World* w, const float* pos_host, const float* vel_host, uin
 // re-bin after advect: keys = target (pool slot*512 + off) or 0xffffffff for dropped particles
 // KillParticlesInSDF (FF/nosys/KillParticles.cpp): drop the particles the killer SDF (float grid sdfGrid) rejects
 void kill_particles_in_sdf(World* w, int sdfGrid, bool keep);
+// ParticleAddDV (FF/nosys/ParticleAddGravity.cpp): v += dv on every stored particle, through the half codec
+void particles_add_dv(World* w, float dvx, float dvy, float dvz);
 void rebin_particles(World* w, const TopoPtr& newPool, const uint32_t* keys_dev, uint64_t nOld,
                      DBuf<uint32_t>& w0, DBuf<uint32_t>& w1, DBuf<uint32_t>& w2);
 

@@ -309,6 +309,22 @@ static int defKillParticlesInSDF = zeno::defNodeClass<KillParticlesInSDF>("KillP
     {/* inputs: */ {"Particles", "KillerSDF"}, /* outputs: */ {"Particles"}, /* params: */ {{"enum KEEP DEL", "OpType", "KEEP"}},
      /* category: */ {"FLIPSolver"}});
 
+// ---- ParticleAddDV (FF/nosys/ParticleAddGravity.cpp:9-41)
+struct ParticleAddDV : zeno::INode {
+    virtual void apply() override {
+        auto particles = get_input("Particles")->as<VDBPointsGrid>();
+        auto dv = get_input("dv")->as<zeno::NumericObject>()->get<zeno::vec3f>();
+        WorldHolder& h = world_for(float(particles->m_grid->voxelSize()[0]));
+        upload_particles(h, particles->m_grid);
+        check(flipb200_particles_add_dv(h.w, dv[0], dv[1], dv[2]), "ParticleAddDV");   // the node's channel is always "vel"
+        download_particles(h, particles->m_grid);
+    }
+};
+static int defParticleAddDV = zeno::defNodeClass<ParticleAddDV>("ParticleAddDV",
+    {/* inputs: */ {"Particles", "dv"}, /* outputs: */ {},
+     /* params: */ {{"string", "channel", "vel"}, {"float", "vx", "0.0"}, {"float", "vy", "0.0"}, {"float", "vz", "0.0"}},
+     /* category: */ {"FLIPSolver"}});
+
 // ---- CutCellWeight (FF/nosys/EvalFaceWeight.cpp:17-41)
 struct CutCellWeightEval : zeno::INode {
     virtual void apply() override {
