@@ -120,6 +120,11 @@ int flipb200_p2g(flipb200_world* w, float dx, int velExtraLayer);
 int flipb200_g2p_advect_sheetty(flipb200_world* w, float dt, float dx, int surfaceSize, int rkOrder,
                                 float picMin, float picMax, int flags);
 /* particles dropped by the last advect (deep in solid, FF/FLIP_vdb.cpp:682-685, or voxel cap :711-714) */
+/* G2P_Advector (FF/nosys/G2P_Advector.cpp:16-47 -> FLIP_vdb::Advect, FF/FLIP_vdb.cpp:3209-3219): the plain node. It passes no liquid
+ * SDF and surfacedist 0, so every particle takes one Euler step (RK_ORDER is accepted and has no effect, as in the reference) with
+ * the FLIP factor 1 - pic_smoothness, and it is only usable without solids: with a SolidSDF connected the reference dereferences
+ * the null liquid SDF. Particles + Velocity + PostAdvVelocity in, re-binned particles out. */
+int flipb200_g2p_advect(flipb200_world* w, float dt, float dx, int rkOrder, float picSmoothness);
 int flipb200_dropped(flipb200_world* w, uint64_t* n);
 /* ParticleAddDV (FF/nosys/ParticleAddGravity.cpp:9-19 -> FLIP_vdb::point_integrate_vector, FF/FLIP_vdb.cpp:3492-3535; SURVEY 8b
  * last row / 8f-1): adds dv to the stored velocity of every particle -- read as double from the half codec, summed in double,

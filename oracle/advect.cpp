@@ -304,6 +304,14 @@ void node_G2PAdvectorSheetty(World& w, float dt, float dx, int surfaceSize, int 
                                         float(surfaceSize) * dx, rkOrder);
 }
 
+// G2P_Advector::apply (FF/nosys/G2P_Advector.cpp:16-47) -> FLIP_vdb::Advect (:3209-3219): liquid sdf = nullptr, the advected and
+// the carried field are both `velocity`, pic_min = pic_smoothness, pic_max = 0.05, surfacedist = 0; no solid (with one connected the
+// reference dereferences the null liquid sdf, :3251-3278)
+void node_G2P_Advector(World& w, float dt, float dx, int rkOrder, float picSmoothness) {
+    (void)dx;
+    custom_move_points_and_set_flip_vel(w, nullptr, w.velocity, w.velocity, true, w.postAdvVelocity, false, picSmoothness, 0.05f, dt, 0.f, rkOrder);
+}
+
 // kill_particles_inside (FF/nosys/KillParticles.cpp:13-149): per leaf, per voxel, per particle in store order: the killer SDF is
 // sampled with openvdb's BoxSampler at voxel + decoded position -- a float sum (Coord + Vec3f, math/Coord.h) handed to the
 // sampler as doubles, in the SDF grid's OWN index space (no transform is applied) -- and the particle survives when the sample

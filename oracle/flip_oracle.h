@@ -55,6 +55,8 @@ void union_extrapolate(int nLayer, Packed3& v, const FloatGrid* targetTopo);
 // K2,K7,K8  FF/nosys/SheetG2PAdvector.cpp:15-54 / FF/FLIP_vdb.cpp:3237-3490
 void node_G2PAdvectorSheetty(World& w, float dt, float dx, int surfaceSize, int rkOrder,
                              float picMin, float picMax);
+// the plain node: FF/nosys/G2P_Advector.cpp:16-47 -> FLIP_vdb::Advect (FF/FLIP_vdb.cpp:3209-3219)
+void node_G2P_Advector(World& w, float dt, float dx, int rkOrder, float picSmoothness);
 // K14 nodes
 void node_CutCellWeight(World& w);                          // FF/FLIP_vdb.cpp:2644-2718
 void node_PushOutLiquidSDF(World& w, float dx);             // FF/FLIP_vdb.cpp:2720-2803

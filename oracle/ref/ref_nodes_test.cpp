@@ -46,6 +46,7 @@ namespace zeno { using namespace ::zeno; }
 #include "nosys/SubtractPressureGradient.cpp"
 #include "nosys/KillParticles.cpp"
 #include "nosys/ParticleAddGravity.cpp"     // ParticleAddDV
+#include "nosys/G2P_Advector.cpp"           // the plain advector
 }  // namespace refnodes
 #undef defNodeClass
 

@@ -158,3 +158,34 @@ def test_particle_add_dv_oracle_plugin_and_reference_node(oracle_lib):
     assert np.array_equal(after[:, :6], before[:, :6]) and not np.array_equal(after[:, 6:], before[:, 6:])
     for w, what in zip(worlds[1:], ("oracle", "plugin node")):
         util.compare_particles(w.get_particles(), ref, f"ParticleAddDV: {what} vs the reference node")
+
+
+def test_plain_g2p_advector_oracle_plugin_and_reference_node(oracle_lib):
+    """G2P_Advector, the plain node (FF/nosys/G2P_Advector.cpp -> FLIP_vdb::Advect): no liquid SDF, no solids, every particle takes
+    an Euler step whatever RK_ORDER says, FLIP factor 1 - pic_smoothness with NO clamp to 0.05 (0.3 is used here). The reference's
+    node class, the oracle and the drop-in's node from the same post-P2G state."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "rn_g2p_advect"):
+        pytest.skip("oracle/_ref with the reference-node harness is not available here")
+    from oracle.pyoracle import OracleWorld, PluginWorld, RefNodeWorld
+    from zeno_b200 import scenes
+    N, dt = 32, 0.01
+    pos, vel, dx = scenes.dam_break_points(N, seed=6, random_velocity=True)
+    vel *= np.float32(0.3)
+    worlds = [cls(dx) for cls in (RefNodeWorld, OracleWorld, PluginWorld)]
+    for w in worlds:
+        w.PrimToVDBPointDataGrid(pos, vel)
+    worlds[0].FLIP_P2G(dx, 3)
+    worlds[0].FieldAddVector(0.0, -9.8 * dt, 0.0)      # Velocity != PostAdvVelocity, so the FLIP part is exercised
+    for w in worlds[1:]:
+        util.sync_state(w, worlds[0], grids=("Velocity", "PostAdvVelocity"))
+    for w in worlds:
+        w.G2P_Advector(dt, dx, 3, 0.3)
+    ref = scenes.canonical_particles(worlds[0].get_particles())
+    for w, what in zip(worlds[1:], ("oracle", "plugin node")):
+        got = scenes.canonical_particles(w.get_particles())
+        assert got.shape == ref.shape, (what, got.shape, ref.shape)
+        m = util.particle_code_report(got, ref)
+        assert m["same_voxel"] >= 0.999 and m["P_within_1lsb"] >= 0.999 and m["v_within_1ulp"] >= 0.999, (what, m)
+    a, b = (scenes.canonical_particles(w.get_particles()) for w in worlds[1:])
+    assert np.array_equal(a, b), "plugin node differs from the oracle driven directly"

@@ -55,3 +55,24 @@ def test_particle_add_dv_matches_oracle(gpu_lib, oracle_lib):
         w.ParticleAddDV(0.013, -0.1633333, 1.0e-4)
     util.compare_particles(gw.get_particles(), ow.get_particles(), "ParticleAddDV vs oracle")
     gw.close()
+
+
+@FIRST_RUN
+def test_plain_g2p_advector_matches_oracle(gpu_lib, oracle_lib):
+    from oracle.pyoracle import OracleWorld
+    from zeno_b200 import abi
+    N, dt = 32, 0.01
+    pos, vel, dx = scenes.dam_break_points(N, seed=6, random_velocity=True)
+    vel *= np.float32(0.3)
+    gw, ow = abi.World(dx), OracleWorld(dx)
+    for w in (gw, ow):
+        w.PrimToVDBPointDataGrid(pos, vel)
+        w.FLIP_P2G(dx, 3)
+        w.FieldAddVector(0.0, -9.8 * dt, 0.0)
+        w.G2P_Advector(dt, dx, 3, 0.3)
+    a = scenes.canonical_particles(gw.get_particles())
+    b = scenes.canonical_particles(ow.get_particles())
+    assert a.shape == b.shape
+    assert (a[:, :3] == b[:, :3]).all(axis=1).mean() > 0.999
+    assert np.array_equal(a, b), "plain G2P_Advector: quantised particle state differs from the oracle"
+    gw.close()

@@ -555,6 +555,14 @@ int flipb200_particles_add_dv(flipb200_world* w, float dvx, float dvy, float dvz
         sync(w);
     });
 }
+int flipb200_g2p_advect(flipb200_world* w, float dt, float dx, int rkOrder, float picSmoothness) {
+    return guarded([&] {
+        FB_REQUIRE(w, FLIPB200_ERR_ARG, "g2p_advect: null world");
+        use_device(w);
+        g2p_advect_sheetty(w, dt, dx, /*surfaceSize=*/0, rkOrder, picSmoothness, 0.05f, /*flags: same field | plain*/ 3);
+        sync(w);
+    });
+}
 int flipb200_dropped(flipb200_world* w, uint64_t* n) {
     return guarded([&] { FB_REQUIRE(w && n, FLIPB200_ERR_ARG, "dropped: bad argument"); *n = w->dropped; });
 }

@@ -310,11 +310,27 @@ __global__ void __launch_bounds__(G2P_THREADS, MIN_BLOCKS) g2p_advect_kernel(G2P
 }
 }  // namespace
 
+namespace {
+__global__ void fill_const_kernel(float* __restrict__ p, float v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+void fill_const(World* w, float* p, float v, size_t n) {
+    if (!n) return;
+    FB_LAUNCH(w, "fill", n * 4) fill_const_kernel<<<(unsigned)((n + 255) / 256), 256, 0, w->stream>>>(p, v, n);
+    check_launch("fill_const");
+}
+}  // namespace
+
 // G2PAdvectorSheet::apply (FF/nosys/SheetG2PAdvector.cpp:15-54)
 void g2p_advect_sheetty(World* w, float dt, float dx, int surfaceSize, int rkOrder, float picMin, float picMax, int flags) {
     FB_REQUIRE(w->pts.topo != nullptr, FLIPB200_ERR_STATE, "G2PAdvectorSheetty: no particles");
-    picMin = picMin > picMax ? picMax : picMin;
-    const bool same = (flags & 1) != 0;
+    // flags & 2: the plain G2P_Advector (FF/nosys/G2P_Advector.cpp -> FLIP_vdb::Advect, FF/FLIP_vdb.cpp:3209-3219): no liquid SDF
+    // (the sampled value is the background dx >= 0, so every particle takes the Euler step and the FLIP factor is 1 - pic_smoothness),
+    // no solids, velocity carried = velocity advected. The Sheetty node clamps pic_min to pic_max (SheetG2PAdvector.cpp:49-52), Advect does not.
+    const bool plain = (flags & 2) != 0;
+    if (!plain) picMin = picMin > picMax ? picMax : picMin;
+    const bool same = (flags & 1) != 0 || plain;
     if (same) ensure_pool(w, {FLIPB200_VELOCITY, FLIPB200_POSTADV_VELOCITY, FLIPB200_LIQUID_SDF}, true);
     else ensure_pool(w, {FLIPB200_VELOCITY, FLIPB200_POSTADV_VELOCITY, FLIPB200_VISCOUS_VELOCITY, FLIPB200_LIQUID_SDF}, true);
     refresh_solid_views(w);
@@ -329,7 +345,7 @@ void g2p_advect_sheetty(World* w, float dt, float dx, int surfaceSize, int rkOrd
     FB_PHASE(w, "g2p total");
     // K8 support: dilate5(liquid sdf topology), 26-neighbourhood (FF/FLIP_vdb.cpp:3277-3279)
     DBuf<uint64_t> nm((size_t)nl * 8 + 1, w->stream), nm2((size_t)nl * 8 + 1, w->stream);
-    if (w->hasSolidSDF && nl) {
+    if (w->hasSolidSDF && nl && !plain) {
         mask_dilate(w, *pool, lsdf.mask.p, nm.p, true);
         for (int i = 1; i < 5; i++) { mask_dilate(w, *pool, nm.p, nm2.p, true); std::swap(nm, nm2); }
     }
@@ -355,6 +371,16 @@ void g2p_advect_sheetty(World* w, float dt, float dx, int surfaceSize, int rkOrd
     p.solidStatic = ss.val.p;
     p.hasSolidVel = (w->hasSolidVel && w->V(FLIPB200_SOLID_VELOCITY).leaves() > 0) ? 1 : 0;
     p.nmask = nm.p;
+    DBuf<float> noSolid;
+    if (plain) {
+        // everything the kernel can read about liquid depth and solids is the background
+        p.hasLiquid = 0; p.lsdfBg = dx;
+        noSolid.alloc((size_t)nl * LEAF + 1, w->stream);
+        const float bg3 = 3.0f * dx;
+        fill_const(w, noSolid.p, bg3, (size_t)nl * LEAF);
+        p.solidView = noSolid.p; p.solidBg = bg3; p.hasSolid = 0; p.hasSolidVel = 0;
+        p.st = TopoView{0, make_int3(0, 0, 0), make_int3(0, 0, 0), nullptr, nullptr, nullptr};
+    }
     p.dx = dx; p.dt = dt; p.picMin = picMin; p.picMax = picMax; p.surfacedist = (float)surfaceSize * dx;
     p.rkOrder = rkOrder; p.sameField = same ? 1 : 0;
     p.ijkOut = ijk.p; p.alive = alive.p;

@@ -291,6 +291,32 @@ static int defG2PAdvectorSheet = zeno::defNodeClass<G2PAdvectorSheet>("G2PAdvect
      /* params: */ {{"float", "dx", "0.01 0.0"}, {"int", "RK_ORDER", "1 1 4"}, {"float", "pic_smoothness", "0.1 0.0 1.0"}, {"int", "surface_size", "4 0 8"}},
      /* category: */ {"FLIPSolver"}});
 
+// ---- G2P_Advector (FF/nosys/G2P_Advector.cpp:16-69): the plain node
+struct G2P_Advector : zeno::INode {
+    virtual void apply() override {
+        const float dt = get_input("dt")->as<NumericObject>()->get<float>();
+        const float dx = dx_of(this);
+        const float smoothness = get_param<float>("pic_smoothness");
+        const int RK_ORDER = get_param<int>("RK_ORDER");
+        auto particles = get_input("Particles")->as<VDBPointsGrid>();
+        auto velocity = get_input("Velocity")->as<VDBFloat3Grid>();
+        auto velocity_after_p2g = get_input("PostAdvVelocity")->as<VDBFloat3Grid>();
+        if (has_input("SolidSDF"))
+            throw makeError("G2P_Advector (libflipb200): with a SolidSDF connected the reference node dereferences a null liquid SDF "
+                            "(FF/FLIP_vdb.cpp:3251-3278); use G2PAdvectorSheetty");
+        WorldHolder& h = world_for(dx);
+        upload_particles(h, particles->m_grid);
+        upload<openvdb::Vec3fGrid>(h, FLIPB200_VELOCITY, velocity->m_grid);
+        upload<openvdb::Vec3fGrid>(h, FLIPB200_POSTADV_VELOCITY, velocity_after_p2g->m_grid);
+        check(flipb200_g2p_advect(h.w, dt, dx, RK_ORDER, smoothness), "G2P_Advector");
+        download_particles(h, particles->m_grid);
+    }
+};
+static int defG2P_Advector = zeno::defNodeClass<G2P_Advector>("G2P_Advector",
+    {/* inputs: */ {"dt", "Dx", "Particles", "Velocity", "PostAdvVelocity", "SolidSDF", "SolidVelocity"}, /* outputs: */ {},
+     /* params: */ {{"float", "dx", "0.01 0.0"}, {"int", "RK_ORDER", "1 1 4"}, {"float", "pic_smoothness", "0.02 0.0 1.0"}},
+     /* category: */ {"FLIPSolver"}});
+
 // ---- KillParticlesInSDF (FF/nosys/KillParticles.cpp:150-165)
 struct KillParticlesInSDF : zeno::INode {
     virtual void apply() override {
