@@ -125,6 +125,11 @@ int flipb200_g2p_advect_sheetty(flipb200_world* w, float dt, float dx, int surfa
  * the FLIP factor 1 - pic_smoothness, and it is only usable without solids: with a SolidSDF connected the reference dereferences
  * the null liquid SDF. Particles + Velocity + PostAdvVelocity in, re-binned particles out. */
 int flipb200_g2p_advect(flipb200_world* w, float dt, float dx, int rkOrder, float picSmoothness);
+/* VDBRenormalizeSDF (projects/zenvdb/VDBRenormalize.cpp:18-52): openvdb::tools::LevelSetTracker::normalize()
+ * `iterations` times with {FIRST_BIAS, TVD_RK3}, trimming off -- three Euler stages of the first-order upwind (Godunov)
+ * re-distancing per call -- on the ACTIVE voxels of float grid `grid` (its topology and inactive values do not change).
+ * dilateIters must be 0 (the tracker's dilate / erode is not accelerated: FLIPB200_ERR_ARG). */
+int flipb200_renormalize_sdf(flipb200_world* w, int grid, int iterations, int dilateIters);
 int flipb200_dropped(flipb200_world* w, uint64_t* n);
 /* ParticleAddDV (FF/nosys/ParticleAddGravity.cpp:9-19 -> FLIP_vdb::point_integrate_vector, FF/FLIP_vdb.cpp:3492-3535; SURVEY 8b
  * last row / 8f-1): adds dv to the stored velocity of every particle -- read as double from the half codec, summed in double,

@@ -149,6 +149,13 @@ int orc_kill_particles(void* wp, int sdfGrid, int keep) {
 }
 int orc_particles_add_dv(void* wp, float x, float y, float z) { node_ParticleAddDV(*static_cast<World*>(wp), x, y, z); return 0; }
 int orc_g2p_advect(void* wp, float dt, float dx, int rkOrder, float picSmoothness) { node_G2P_Advector(*static_cast<World*>(wp), dt, dx, rkOrder, picSmoothness); return 0; }
+int orc_renormalize_sdf(void* wp, int grid, int iterations, int dilateIters) {
+    World* w = static_cast<World*>(wp);
+    FloatGrid* g = floatOf(w, grid);
+    if (!g || dilateIters != 0) return 1;
+    node_VDBRenormalizeSDF(*g, w->dx, iterations);
+    return 0;
+}
 int orc_face_weights(void* wp) { node_CutCellWeight(*static_cast<World*>(wp)); return 0; }
 int orc_pushout_sdf(void* wp, float dx) { node_PushOutLiquidSDF(*static_cast<World*>(wp), dx); return 0; }
 int orc_add_vector(void* wp, float x, float y, float z) { node_FieldAddVector(*static_cast<World*>(wp), x, y, z); return 0; }

@@ -73,6 +73,10 @@ void node_KillParticlesInSDF(World& w, const FloatGrid& sdf, bool keep);
 // FF/nosys/ParticleAddGravity.cpp:9-19 -> FLIP_vdb::point_integrate_vector (FF/FLIP_vdb.cpp:3492-3535)
 void node_ParticleAddDV(World& w, float dvx, float dvy, float dvz);
 
+// VDBRenormalizeSDF (projects/zenvdb/VDBRenormalize.cpp:18-37) = openvdb::tools::LevelSetTracker::normalize x iterations with
+// {FIRST_BIAS, TVD_RK3, 1, 1}, trimming off, no dilation (tools/LevelSetTracker.h:510-655)
+void node_VDBRenormalizeSDF(FloatGrid& g, float voxelSize, int iterations);
+
 float fraction_inside(float phi_left, float phi_right);  // FF/levelset_util.cpp:5-15
 float fraction_inside(float bl, float br, float tl, float tr);  // FF/levelset_util.cpp:26-99
 

@@ -73,7 +73,7 @@ for s in "$FF/FLIP_vdb.cpp" "$FF/simd_vdb_poisson_uaamg.cpp" "$FF/vdb_velocity_e
   USES_PLUGIN=""
   case "$(basename $s)" in
     plugin_nodes_test.cpp) FL="$NODEFLAGS"; USES_PLUGIN=1 ;;
-    ref_nodes_test.cpp) FL="$COMMON -mavx -mfma -DZENO_APIFREE -I$HERE/shims/zeno_nodes -I$REF/projects/zenvdb/include -I$REF/zeno/include -I$FF -I$HERE/../../include" ;;
+    ref_nodes_test.cpp) FL="$COMMON -mavx -mfma -DZENO_APIFREE -I$HERE/shims/zeno_nodes -I$REF/projects/zenvdb/include -I$REF/zeno/include -I$FF -I$REF/projects/zenvdb -I$HERE/../../include" ;;
     ref_driver.cpp) USES_PLUGIN=1 ;;
   esac
   if [ ! -f "$o" ] || [ "$s" -nt "$o" ] || [ "$HERE/shims/Eigen/Eigen" -nt "$o" ] || { [ -n "$USES_PLUGIN" ] && [ "$PLUGIN_SRC" -nt "$o" ]; } || { case "$(basename $s)" in plugin_nodes_test.cpp|ref_nodes_test.cpp) [ "$HERE/shims/zeno_nodes/zeno/zeno.h" -nt "$o" ] || [ "$HERE/node_harness.inc" -nt "$o" ] ;; *) false ;; esac; }; then

@@ -21,6 +21,14 @@
 #include <openvdb/points/PointAdvect.h>
 #include <openvdb/tree/LeafManager.h>
 #include "levelset_util.h"
+#include <zeno/StringObject.h>
+#include <vector>
+#include <openvdb/tools/Morphology.h>
+#include <openvdb/tools/MeshToVolume.h>
+#include <openvdb/tools/LevelSetTracker.h>
+#include <openvdb/tools/Filter.h>
+#include <openvdb/tools/LevelSetSphere.h>
+#include <openvdb/tools/ChangeBackground.h>
 #include "FLIP_vdb.h"
 #include "vdb_velocity_extrapolator.h"
 
@@ -47,6 +55,7 @@ namespace zeno { using namespace ::zeno; }
 #include "nosys/KillParticles.cpp"
 #include "nosys/ParticleAddGravity.cpp"     // ParticleAddDV
 #include "nosys/G2P_Advector.cpp"           // the plain advector
+#include "VDBRenormalize.cpp"               // projects/zenvdb: VDBRenormalizeSDF
 }  // namespace refnodes
 #undef defNodeClass
 

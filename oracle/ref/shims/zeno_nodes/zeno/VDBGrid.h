@@ -15,11 +15,21 @@
 #include <zeno/packed3grids.h>   // FF/FLIP_vdb.h gets packed_FloatGrid3 through this header
 #endif
 namespace zeno {
+// the type-erased base some zenvdb nodes ask for (VDBGrid.h:52-78); only what projects/zenvdb/VDBRenormalize.cpp touches
+struct VDBGrid : IObject {
+    virtual std::string getType() const { return {}; }
+    virtual void dilateTopo(int) {}
+};
 template <typename GridT>
-struct VDBGridWrapper : IObject {
+struct VDBGridWrapper : VDBGrid {
     typename GridT::Ptr m_grid;
     VDBGridWrapper() = default;
     explicit VDBGridWrapper(typename GridT::Ptr g) : m_grid(std::move(g)) {}
+    std::string getType() const override {
+        if (std::is_same<GridT, openvdb::FloatGrid>::value) return "FloatGrid";
+        if (std::is_same<GridT, openvdb::Vec3fGrid>::value) return "Vec3fGrid";
+        return "PointDataGrid";
+    }
 };
 using VDBFloatGrid = VDBGridWrapper<openvdb::FloatGrid>;
 using VDBFloat3Grid = VDBGridWrapper<openvdb::Vec3fGrid>;

@@ -94,3 +94,5 @@ int defNodeClass(std::string const& name, Descriptor const& desc = {}) {
 
 // zeno/include/zeno/core/defNode.h:28-34
 #define ZENDEFNODE(Class, ...) static int def##Class = zeno::defNodeClass<Class>(#Class, __VA_ARGS__)
+#define ZENO_DEFNODE(Class) \
+    static struct _Def##Class { _Def##Class(::zeno::Descriptor const& desc) { zeno::defNodeClass<Class>(#Class, desc); } } _def##Class

@@ -242,4 +242,56 @@ void node_SubtractPressureGradient(World& w, float dt, float dx, int velExtraLay
     to_vec3(w.velocity, p);
 }
 
+// ---------------------------------------------------------------- VDBRenormalizeSDF
+namespace {
+// math::GodunovsNormSqrd (openvdb/math/FiniteDifference.h:326-347) of the first-order one-sided differences
+// (ISGradientNormSqrd<FIRST_BIAS>, math/Operators.h:249-260: up = forward, down = backward differences, index space)
+inline float godunov_norm_sqrd(bool outside, const float m[3], const float p[3]) {
+    auto pow2 = [](float x) { return x * x; };
+    float s;
+    if (outside) {
+        s = std::max(pow2(std::max(m[0], 0.f)), pow2(std::min(p[0], 0.f)));
+        s += std::max(pow2(std::max(m[1], 0.f)), pow2(std::min(p[1], 0.f)));
+        s += std::max(pow2(std::max(m[2], 0.f)), pow2(std::min(p[2], 0.f)));
+    } else {
+        s = std::max(pow2(std::min(m[0], 0.f)), pow2(std::max(p[0], 0.f)));
+        s += std::max(pow2(std::min(m[1], 0.f)), pow2(std::max(p[1], 0.f)));
+        s += std::max(pow2(std::min(m[2], 0.f)), pow2(std::max(p[2], 0.f)));
+    }
+    return s;
+}
+// one Euler stage of Normalizer::euler<N,D> (LevelSetTracker.h:631-675): every ACTIVE voxel of `cur` gets
+// alpha*phi0 + beta*v (v alone when N == 0); the stencil reads `cur` wherever it lands (inactive voxels and the background
+// included); inactive voxels keep their value
+void renorm_stage(const FloatGrid& cur, const std::vector<float>& phi0, int N, int D, float dt, float invDx, std::vector<float>& out) {
+    out = cur.vals;
+    const float alpha = D ? float(N) / float(D) : 0.f, beta = 1.0f - alpha;
+    for (int l = 0; l < cur.leafCount(); l++) {
+        const Coord o = cur.origins[l];
+        for (int off = 0; off < 512; off++) {
+            if (!maskGet(cur.masks[l], off)) continue;
+            const int x = o.x + (off >> 6), y = o.y + ((off >> 3) & 7), z = o.z + (off & 7);
+            const float c = cur.vals[size_t(l) * 512 + off];
+            const float up[3] = {cur.get(0, x + 1, y, z) - c, cur.get(0, x, y + 1, z) - c, cur.get(0, x, y, z + 1) - c};
+            const float dn[3] = {c - cur.get(0, x - 1, y, z), c - cur.get(0, x, y - 1, z), c - cur.get(0, x, y, z - 1)};
+            const float n2 = godunov_norm_sqrd(c > 0.f, dn, up);
+            float v = c / (std::sqrt(c * c + n2) + 1e-8f);          // math::Tolerance<float>::value() = 1e-8
+            v = c - dt * v * (std::sqrt(n2) * invDx - 1.0f);
+            out[size_t(l) * 512 + off] = N ? alpha * phi0[size_t(l) * 512 + off] + beta * v : v;
+        }
+    }
+}
+}  // namespace
+
+void node_VDBRenormalizeSDF(FloatGrid& g, float voxelSize, int iterations) {
+    const float dt = voxelSize * 1.0f, invDx = 1.0f / voxelSize;   // Normalizer ctor (:519-523): TVD_RK3 -> dt = dx
+    std::vector<float> next;
+    for (int it = 0; it < iterations; it++) {
+        const std::vector<float> phi0 = g.vals;                    // aux buffer 1 after the first swap
+        renorm_stage(g, phi0, 0, 1, dt, invDx, next); g.vals.swap(next);   // euler01: Phi_t1
+        renorm_stage(g, phi0, 3, 4, dt, invDx, next); g.vals.swap(next);   // euler34: 3/4 Phi_t0 + 1/4 (Phi_t1 - dt V.G)
+        renorm_stage(g, phi0, 1, 3, dt, invDx, next); g.vals.swap(next);   // euler13: 1/3 Phi_t0 + 2/3 (Phi_t2 - dt V.G)
+    }
+}
+
 }  // namespace orc

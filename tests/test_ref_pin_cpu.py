@@ -189,3 +189,36 @@ def test_plain_g2p_advector_oracle_plugin_and_reference_node(oracle_lib):
         assert m["same_voxel"] >= 0.999 and m["P_within_1lsb"] >= 0.999 and m["v_within_1ulp"] >= 0.999, (what, m)
     a, b = (scenes.canonical_particles(w.get_particles()) for w in worlds[1:])
     assert np.array_equal(a, b), "plugin node differs from the oracle driven directly"
+
+
+@pytest.mark.parametrize("iterations", [1, 4])
+def test_renormalize_sdf_oracle_plugin_and_reference_node(oracle_lib, iterations):
+    """VDBRenormalizeSDF (projects/zenvdb/VDBRenormalize.cpp -> openvdb::tools::LevelSetTracker::normalize, FIRST_BIAS / TVD_RK3,
+    no trimming) on the liquid SDF that FLIP_P2G produced: the real node class (compiled unmodified), the oracle
+    restatement and the drop-in's node. Topology and inactive values must not change; active values agree to fp32 rounding with the
+    reference (its binary contracts a*b+c into FMAs, the oracle does not), and the plugin node equals the oracle bit for bit."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "rn_renormalize_sdf"):
+        pytest.skip("oracle/_ref with the reference-node harness is not available here")
+    from oracle.pyoracle import OracleWorld, PluginWorld, RefNodeWorld
+    from zeno_b200 import scenes
+    N = 32
+    pos, vel, dx = scenes.dam_break_points(N, seed=8, random_velocity=True)
+    worlds = [cls(dx) for cls in (RefNodeWorld, OracleWorld, PluginWorld)]
+    for w in worlds:
+        w.PrimToVDBPointDataGrid(pos, vel)
+    worlds[0].FLIP_P2G(dx, 3)
+    before = worlds[0].get_grid("LiquidSDF")
+    for w in worlds[1:]:
+        w.set_grid("LiquidSDF", before)
+    for w in worlds:
+        w.VDBRenormalizeSDF("LiquidSDF", iterations, 0)
+    ref, orc, plg = (w.get_grid("LiquidSDF") for w in worlds)
+    e = util.compare_grids(orc, ref, "VDBRenormalizeSDF: oracle vs the reference node", tol=2e-6, check_inactive=False)
+    util.compare_grids(plg, orc, "VDBRenormalizeSDF: plugin node vs oracle", tol=0.0)
+    # it did something, and only to active voxels
+    a, b = scenes.canonical_grid(before, drop_empty=False), scenes.canonical_grid(ref, drop_empty=False)
+    mb = scenes.mask_bits(a["masks"])
+    assert np.array_equal(a["masks"], b["masks"]) and np.array_equal(a["values"][:, 0][~mb], b["values"][:, 0][~mb])
+    assert not np.array_equal(a["values"][:, 0][mb], b["values"][:, 0][mb])
+    print(f"renormalize x{iterations}: oracle vs reference node rel L2 {e:.2e}")

@@ -76,3 +76,19 @@ def test_plain_g2p_advector_matches_oracle(gpu_lib, oracle_lib):
     assert (a[:, :3] == b[:, :3]).all(axis=1).mean() > 0.999
     assert np.array_equal(a, b), "plain G2P_Advector: quantised particle state differs from the oracle"
     gw.close()
+
+
+@FIRST_RUN
+def test_renormalize_sdf_matches_oracle(gpu_lib, oracle_lib):
+    from oracle.pyoracle import OracleWorld
+    from zeno_b200 import abi
+    pos, vel, dx = scenes.dam_break_points(32, seed=8, random_velocity=True)
+    gw, ow = abi.World(dx), OracleWorld(dx)
+    for w in (gw, ow):
+        w.PrimToVDBPointDataGrid(pos, vel)
+        w.FLIP_P2G(dx, 3)
+        w.VDBRenormalizeSDF("LiquidSDF", 4, 0)
+    util.compare_grids(gw.get_grid("LiquidSDF"), ow.get_grid("LiquidSDF"), "VDBRenormalizeSDF vs oracle", tol=0.0, check_inactive=False)
+    with pytest.raises(abi.FlipB200Error):
+        gw.VDBRenormalizeSDF("LiquidSDF", 1, 2)      # the tracker's dilate is not accelerated
+    gw.close()

@@ -39,7 +39,7 @@ EXPORTS = [
     "flipb200_profile_reset", "flipb200_profile_get", "flipb200_stream", "flipb200_comm_unique_id",
     "flipb200_comm_init", "flipb200_comm_init_local", "flipb200_comm_abort", "flipb200_dd_set_slab", "flipb200_dd_owned",
     "flipb200_dd_owned_particles",
-    "flipb200_sync_count", "flipb200_g2p_advect", "flipb200_kill_particles_in_sdf", "flipb200_particles_add_dv", "flipb200_particles_download_begin", "flipb200_grid_download_begin", "flipb200_download_wait",
+    "flipb200_sync_count", "flipb200_renormalize_sdf", "flipb200_g2p_advect", "flipb200_kill_particles_in_sdf", "flipb200_particles_add_dv", "flipb200_particles_download_begin", "flipb200_grid_download_begin", "flipb200_download_wait",
 ]
 
 
@@ -235,6 +235,9 @@ class World:
 
     def G2P_Advector(self, dt: float, dx: Optional[float] = None, RK_ORDER: int = 1, pic_smoothness: float = 0.02):
         self._ck(self.lib.flipb200_g2p_advect(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.c_int(RK_ORDER), C.c_float(pic_smoothness)))
+
+    def VDBRenormalizeSDF(self, grid: str = "LiquidSDF", iterations: int = 4, dilateIters: int = 0):
+        self._ck(self.lib.flipb200_renormalize_sdf(self.h, C.c_int(GRID_IDS[grid]), C.c_int(iterations), C.c_int(dilateIters)))
 
     def dropped(self) -> int:
         n = C.c_uint64(0)

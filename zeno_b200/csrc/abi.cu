@@ -563,6 +563,15 @@ int flipb200_g2p_advect(flipb200_world* w, float dt, float dx, int rkOrder, floa
         sync(w);
     });
 }
+int flipb200_renormalize_sdf(flipb200_world* w, int grid, int iterations, int dilateIters) {
+    return guarded([&] {
+        FB_REQUIRE(w, FLIPB200_ERR_ARG, "renormalize_sdf: null world");
+        FB_REQUIRE(dilateIters == 0, FLIPB200_ERR_ARG, "renormalize_sdf: the tracker's dilate / erode (dilateIters != 0) is not accelerated");
+        use_device(w);
+        renormalize_sdf(w, grid, iterations);
+        sync(w);
+    });
+}
 int flipb200_dropped(flipb200_world* w, uint64_t* n) {
     return guarded([&] { FB_REQUIRE(w && n, FLIPB200_ERR_ARG, "dropped: bad argument"); *n = w->dropped; });
 }

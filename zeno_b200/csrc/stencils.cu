@@ -255,6 +255,74 @@ float cfl(World* w) {
     return w->dx / (fabsf(mv) + 1e-6f);
 }
 
+// ---------------------------------------------------------------- VDBRenormalizeSDF
+namespace {
+// One Euler stage of openvdb::tools::LevelSetTracker's Normalizer (tools/LevelSetTracker.h:631-675) with the first-order
+// upwind Godunov norm (math/Operators.h:249-260, math/FiniteDifference.h:326-347): every ACTIVE voxel of `cur` gets
+// alpha*phi0 + beta*v (v alone when useAlpha == 0); inactive voxels keep their value; the stencil reads `cur` wherever it lands.
+__global__ void __launch_bounds__(512) renorm_stage_kernel(TopoView t, const uint64_t* __restrict__ mask, const float* __restrict__ cur,
+                                                           const float* __restrict__ phi0, float* __restrict__ out, float bg, float dt,
+                                                           float invDx, float alpha, float beta, int useAlpha) {
+    const int leaf = blockIdx.x, off = threadIdx.x;
+    const size_t i = (size_t)leaf * LEAF + off;
+    const float c = cur[i];
+    float r = c;
+    if (mask_get(mask, leaf, off)) {
+        const int3 o = t.origin[leaf];
+        const int x = o.x + (off >> 6), y = o.y + ((off >> 3) & 7), z = o.z + (off & 7);
+        const float ux = __fsub_rn(grid_get(t, cur, bg, x + 1, y, z), c), uy = __fsub_rn(grid_get(t, cur, bg, x, y + 1, z), c),
+                    uz = __fsub_rn(grid_get(t, cur, bg, x, y, z + 1), c);
+        const float dxm = __fsub_rn(c, grid_get(t, cur, bg, x - 1, y, z)), dym = __fsub_rn(c, grid_get(t, cur, bg, x, y - 1, z)),
+                    dzm = __fsub_rn(c, grid_get(t, cur, bg, x, y, z - 1));
+        float n2;
+        if (c > 0.f) {
+            float a = fmaxf(dxm, 0.f), b = fminf(ux, 0.f);
+            n2 = fmaxf(__fmul_rn(a, a), __fmul_rn(b, b));
+            a = fmaxf(dym, 0.f); b = fminf(uy, 0.f);
+            n2 = __fadd_rn(n2, fmaxf(__fmul_rn(a, a), __fmul_rn(b, b)));
+            a = fmaxf(dzm, 0.f); b = fminf(uz, 0.f);
+            n2 = __fadd_rn(n2, fmaxf(__fmul_rn(a, a), __fmul_rn(b, b)));
+        } else {
+            float a = fminf(dxm, 0.f), b = fmaxf(ux, 0.f);
+            n2 = fmaxf(__fmul_rn(a, a), __fmul_rn(b, b));
+            a = fminf(dym, 0.f); b = fmaxf(uy, 0.f);
+            n2 = __fadd_rn(n2, fmaxf(__fmul_rn(a, a), __fmul_rn(b, b)));
+            a = fminf(dzm, 0.f); b = fmaxf(uz, 0.f);
+            n2 = __fadd_rn(n2, fmaxf(__fmul_rn(a, a), __fmul_rn(b, b)));
+        }
+        float v = __fdiv_rn(c, __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(c, c), n2)), 1e-8f));
+        v = __fsub_rn(c, __fmul_rn(__fmul_rn(dt, v), __fsub_rn(__fmul_rn(__fsqrt_rn(n2), invDx), 1.0f)));
+        r = useAlpha ? __fadd_rn(__fmul_rn(alpha, phi0[i]), __fmul_rn(beta, v)) : v;
+    }
+    out[i] = r;
+}
+}  // namespace
+
+// VDBRenormalizeSDF::apply (projects/zenvdb/VDBRenormalize.cpp:18-37): LevelSetTracker {FIRST_BIAS, TVD_RK3, 1, 1}, no trimming,
+// `iterations` x normalize(); each normalize = three Euler stages (Normalizer::normalize, LevelSetTracker.h:535-604)
+void renormalize_sdf(World* w, int grid, int iterations) {
+    FB_REQUIRE(is_float_grid(grid) && w->F(grid).topo != nullptr, FLIPB200_ERR_STATE, "VDBRenormalizeSDF: the grid does not exist");
+    GridF& g = w->F(grid);
+    const int n = g.topo->n;
+    if (!n || iterations <= 0) return;
+    const size_t nv = (size_t)n * LEAF;
+    const float h = w->dx, dt = h * 1.0f, invDx = 1.0f / h;
+    DBuf<float> phi0(nv, w->stream), a(nv, w->stream);
+    const TopoView t = g.topo->view();
+    auto stage = [&](const float* cur, float* out, int N, int D) {
+        const float alpha = D ? (float)N / (float)D : 0.f;
+        FB_LAUNCH(w, "renorm_stage", nv * 12) renorm_stage_kernel<<<n, 512, 0, w->stream>>>(t, g.mask.p, cur, phi0.p, out, g.bg, dt, invDx, alpha, 1.0f - alpha, N ? 1 : 0);
+        check_launch("renorm_stage");
+    };
+    for (int it = 0; it < iterations; it++) {
+        FB_CUDA(cudaMemcpyAsync(phi0.p, g.val.p, nv * 4, cudaMemcpyDeviceToDevice, w->stream));
+        stage(g.val.p, a.p, 0, 1);      // Phi_t1
+        stage(a.p, g.val.p, 3, 4);      // Phi_t2
+        stage(g.val.p, a.p, 1, 3);      // Phi_t3
+        std::swap(g.val, a);
+    }
+}
+
 void subtract_grad(World* w, float dt, float dx, int velExtraLayer) {
     ensure_pool(w, {FLIPB200_VELOCITY, FLIPB200_LIQUID_SDF, FLIPB200_PRESSURE, FLIPB200_FACE_WEIGHT}, false);
     refresh_solid_views(w);

@@ -199,6 +199,8 @@ void pushout_sdf(World* w, float dx);
 void add_vector(World* w, float x, float y, float z);
 float cfl(World* w);
 void subtract_grad(World* w, float dt, float dx, int velExtraLayer);
+// VDBRenormalizeSDF (projects/zenvdb/VDBRenormalize.cpp): LevelSetTracker::normalize x iterations on a float grid
+void renormalize_sdf(World* w, int grid, int iterations);
 // per-channel masks are [3][n][8]; target topology mask = liquid SDF mask
 void union_extrapolate(World* w, int nLayer, GridV& vel, uint64_t* chMask, const uint64_t* targetMask);
 void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter);

@@ -291,6 +291,25 @@ static int defG2PAdvectorSheet = zeno::defNodeClass<G2PAdvectorSheet>("G2PAdvect
      /* params: */ {{"float", "dx", "0.01 0.0"}, {"int", "RK_ORDER", "1 1 4"}, {"float", "pic_smoothness", "0.1 0.0 1.0"}, {"int", "surface_size", "4 0 8"}},
      /* category: */ {"FLIPSolver"}});
 
+// ---- VDBRenormalizeSDF (projects/zenvdb/VDBRenormalize.cpp:18-52)
+struct VDBRenormalizeSDF : zeno::INode {
+    virtual void apply() override {
+        auto inoutSDF = get_input("inoutSDF")->as<VDBFloatGrid>();
+        const int normIter = get_param<int>("iterations");
+        const int dilateIter = get_param<int>("dilateIters");
+        WorldHolder& h = world_for(float(inoutSDF->m_grid->voxelSize()[0]));
+        // the socket can carry any level set: it travels in the generic float slot, not in the world's LiquidSDF
+        upload<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, inoutSDF->m_grid);
+        check(flipb200_renormalize_sdf(h.w, FLIPB200_KILLER_SDF, normIter, dilateIter), "VDBRenormalizeSDF");
+        download<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, inoutSDF->m_grid);
+        set_output("inoutSDF", get_input("inoutSDF"));
+    }
+};
+static int defVDBRenormalizeSDF = zeno::defNodeClass<VDBRenormalizeSDF>("VDBRenormalizeSDF",
+    {/* inputs: */ {"inoutSDF"}, /* outputs: */ {"inoutSDF"},
+     /* params: */ {{"enum 1oUpwind", "method", "1oUpwind"}, {"int", "iterations", "4"}, {"int", "dilateIters", "0"}},
+     /* category: */ {"openvdb"}});
+
 // ---- G2P_Advector (FF/nosys/G2P_Advector.cpp:16-69): the plain node
 struct G2P_Advector : zeno::INode {
     virtual void apply() override {
