@@ -130,6 +130,9 @@ int flipb200_g2p_advect(flipb200_world* w, float dt, float dx, int rkOrder, floa
  * re-distancing per call -- on the ACTIVE voxels of float grid `grid` (its topology and inactive values do not change).
  * dilateIters must be 0 (the tracker's dilate / erode is not accelerated: FLIPB200_ERR_ARG). */
 int flipb200_renormalize_sdf(flipb200_world* w, int grid, int iterations, int dilateIters);
+/* VDBErodeSDF (projects/zenvdb/VDBRenormalize.cpp:155-185, used once by the packaged FLIP template): adds `depth` to every
+ * active voxel of float grid `grid`. */
+int flipb200_erode_sdf(flipb200_world* w, int grid, float depth);
 int flipb200_dropped(flipb200_world* w, uint64_t* n);
 /* ParticleAddDV (FF/nosys/ParticleAddGravity.cpp:9-19 -> FLIP_vdb::point_integrate_vector, FF/FLIP_vdb.cpp:3492-3535; SURVEY 8b
  * last row / 8f-1): adds dv to the stored velocity of every particle -- read as double from the half codec, summed in double,

@@ -77,6 +77,9 @@ void node_ParticleAddDV(World& w, float dvx, float dvy, float dvz);
 // {FIRST_BIAS, TVD_RK3, 1, 1}, trimming off, no dilation (tools/LevelSetTracker.h:510-655)
 void node_VDBRenormalizeSDF(FloatGrid& g, float voxelSize, int iterations);
 
+// VDBErodeSDF (projects/zenvdb/VDBRenormalize.cpp:155-172): every ACTIVE voxel += depth
+void node_VDBErodeSDF(FloatGrid& g, float depth);
+
 float fraction_inside(float phi_left, float phi_right);  // FF/levelset_util.cpp:5-15
 float fraction_inside(float bl, float br, float tl, float tr);  // FF/levelset_util.cpp:26-99
 

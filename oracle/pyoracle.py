@@ -164,6 +164,11 @@ class OracleWorld:
         if rc != 0:
             raise RuntimeError("VDBRenormalizeSDF failed")
 
+    def VDBErodeSDF(self, grid: str, depth: float):
+        rc = self.lib.orc_erode_sdf(self.h, C.c_int(GRID_IDS[grid]), C.c_float(depth))
+        if rc != 0:
+            raise RuntimeError("VDBErodeSDF failed")
+
     def dropped(self) -> int:
         return int(self.lib.orc_dropped(self.h))
 
@@ -311,6 +316,9 @@ class PluginWorld(OracleWorld):
 
     def VDBRenormalizeSDF(self, grid: str = "LiquidSDF", iterations: int = 4, dilateIters: int = 0):
         self._ck(self.lib.orc_renormalize_sdf(self.h, C.c_int(GRID_IDS[grid]), C.c_int(iterations), C.c_int(dilateIters)))
+
+    def VDBErodeSDF(self, grid: str, depth: float):
+        self._ck(self.lib.orc_erode_sdf(self.h, C.c_int(GRID_IDS[grid]), C.c_float(depth)))
 
     def G2P_Advector(self, dt, dx=None, RK_ORDER=1, pic_smoothness=0.02):
         self._ck(self.lib.orc_g2p_advect(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.c_int(RK_ORDER), C.c_float(pic_smoothness)))

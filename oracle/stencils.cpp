@@ -294,4 +294,11 @@ void node_VDBRenormalizeSDF(FloatGrid& g, float voxelSize, int iterations) {
     }
 }
 
+// VDBErodeSDF::apply (projects/zenvdb/VDBRenormalize.cpp:155-172)
+void node_VDBErodeSDF(FloatGrid& g, float depth) {
+    for (int l = 0; l < g.leafCount(); l++)
+        for (int off = 0; off < 512; off++)
+            if (maskGet(g.masks[l], off)) g.vals[size_t(l) * 512 + off] += depth;
+}
+
 }  // namespace orc

@@ -11,7 +11,8 @@ REF_FILES = {"FLIP_P2G": "P2G.cpp", "G2PAdvectorSheetty": "SheetG2PAdvector.cpp"
              "SubtractPressureGradient": "SubtractPressureGradient.cpp", "CutCellWeight": "EvalFaceWeight.cpp",
              "PushOutLiquidSDF": "FixLiquidSDF.cpp", "FieldAddVector": "FieldAddVector.cpp", "CFL_dt": "CFL.cpp",
              "KillParticlesInSDF": "KillParticles.cpp", "ParticleAddDV": "ParticleAddGravity.cpp",
-             "G2P_Advector": "G2P_Advector.cpp", "VDBRenormalizeSDF": "../../zenvdb/VDBRenormalize.cpp"}
+             "G2P_Advector": "G2P_Advector.cpp", "VDBRenormalizeSDF": "../../zenvdb/VDBRenormalize.cpp",
+             "VDBErodeSDF": "../../zenvdb/VDBRenormalize.cpp"}
 # (inputs, outputs, params) by name only, recorded from the reference files above
 EXPECTED = {
     "FLIP_P2G": (["Dx", "Particles", "Velocity", "PostP2GVelocity", "LiquidSDF"], [], ["dx", "VelExtraLayer"]),
@@ -29,6 +30,7 @@ EXPECTED = {
     "ParticleAddDV": (["Particles", "dv"], [], ["channel", "vx", "vy", "vz"]),
     "G2P_Advector": (["dt", "Dx", "Particles", "Velocity", "PostAdvVelocity", "SolidSDF", "SolidVelocity"], [], ["dx", "RK_ORDER", "pic_smoothness"]),
     "VDBRenormalizeSDF": (["inoutSDF"], ["inoutSDF"], ["method", "iterations", "dilateIters"]),
+    "VDBErodeSDF": (["inoutSDF", "depth"], ["inoutSDF"], []),
 }
 
 

@@ -222,3 +222,26 @@ def test_renormalize_sdf_oracle_plugin_and_reference_node(oracle_lib, iterations
     assert np.array_equal(a["masks"], b["masks"]) and np.array_equal(a["values"][:, 0][~mb], b["values"][:, 0][~mb])
     assert not np.array_equal(a["values"][:, 0][mb], b["values"][:, 0][mb])
     print(f"renormalize x{iterations}: oracle vs reference node rel L2 {e:.2e}")
+
+
+def test_erode_sdf_oracle_plugin_and_reference_node(oracle_lib):
+    """VDBErodeSDF (projects/zenvdb/VDBRenormalize.cpp:155-185): active voxels += depth; reference node class == oracle == plugin node."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "rn_erode_sdf"):
+        pytest.skip("oracle/_ref with the reference-node harness is not available here")
+    from oracle.pyoracle import OracleWorld, PluginWorld, RefNodeWorld
+    from zeno_b200 import scenes
+    pos, vel, dx = scenes.dam_break_points(32, seed=8)
+    worlds = [cls(dx) for cls in (RefNodeWorld, OracleWorld, PluginWorld)]
+    for w in worlds:
+        w.PrimToVDBPointDataGrid(pos, vel)
+    worlds[0].FLIP_P2G(dx, 3)
+    before = worlds[0].get_grid("LiquidSDF")
+    for w in worlds[1:]:
+        w.set_grid("LiquidSDF", before)
+    for w in worlds:
+        w.VDBErodeSDF("LiquidSDF", 0.37 * dx)
+    ref = worlds[0].get_grid("LiquidSDF")
+    for w, what in zip(worlds[1:], ("oracle", "plugin node")):
+        util.compare_grids(w.get_grid("LiquidSDF"), ref, f"VDBErodeSDF: {what} vs the reference node", tol=0.0)
+    assert not np.array_equal(scenes.canonical_grid(before)["values"], scenes.canonical_grid(ref)["values"])

@@ -39,7 +39,7 @@ EXPORTS = [
     "flipb200_profile_reset", "flipb200_profile_get", "flipb200_stream", "flipb200_comm_unique_id",
     "flipb200_comm_init", "flipb200_comm_init_local", "flipb200_comm_abort", "flipb200_dd_set_slab", "flipb200_dd_owned",
     "flipb200_dd_owned_particles",
-    "flipb200_sync_count", "flipb200_renormalize_sdf", "flipb200_g2p_advect", "flipb200_kill_particles_in_sdf", "flipb200_particles_add_dv", "flipb200_particles_download_begin", "flipb200_grid_download_begin", "flipb200_download_wait",
+    "flipb200_sync_count", "flipb200_renormalize_sdf", "flipb200_erode_sdf", "flipb200_g2p_advect", "flipb200_kill_particles_in_sdf", "flipb200_particles_add_dv", "flipb200_particles_download_begin", "flipb200_grid_download_begin", "flipb200_download_wait",
 ]
 
 
@@ -238,6 +238,9 @@ class World:
 
     def VDBRenormalizeSDF(self, grid: str = "LiquidSDF", iterations: int = 4, dilateIters: int = 0):
         self._ck(self.lib.flipb200_renormalize_sdf(self.h, C.c_int(GRID_IDS[grid]), C.c_int(iterations), C.c_int(dilateIters)))
+
+    def VDBErodeSDF(self, grid: str, depth: float):
+        self._ck(self.lib.flipb200_erode_sdf(self.h, C.c_int(GRID_IDS[grid]), C.c_float(depth)))
 
     def dropped(self) -> int:
         n = C.c_uint64(0)

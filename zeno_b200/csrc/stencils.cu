@@ -298,6 +298,22 @@ __global__ void __launch_bounds__(512) renorm_stage_kernel(TopoView t, const uin
 }
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(512) add_active_kernel(const uint64_t* __restrict__ mask, float* __restrict__ val, float d) {
+    const int leaf = blockIdx.x, off = threadIdx.x;
+    if (mask_get(mask, leaf, off)) { const size_t i = (size_t)leaf * LEAF + off; val[i] = __fadd_rn(val[i], d); }
+}
+}  // namespace
+// VDBErodeSDF::apply (projects/zenvdb/VDBRenormalize.cpp:155-172): every active voxel += depth
+void erode_sdf(World* w, int grid, float depth) {
+    FB_REQUIRE(is_float_grid(grid) && w->F(grid).topo != nullptr, FLIPB200_ERR_STATE, "VDBErodeSDF: the grid does not exist");
+    GridF& g = w->F(grid);
+    const int n = g.topo->n;
+    if (!n) return;
+    FB_LAUNCH(w, "erode_sdf", (size_t)n * LEAF * 8) add_active_kernel<<<n, 512, 0, w->stream>>>(g.mask.p, g.val.p, depth);
+    check_launch("erode_sdf");
+}
+
 // VDBRenormalizeSDF::apply (projects/zenvdb/VDBRenormalize.cpp:18-37): LevelSetTracker {FIRST_BIAS, TVD_RK3, 1, 1}, no trimming,
 // `iterations` x normalize(); each normalize = three Euler stages (Normalizer::normalize, LevelSetTracker.h:535-604)
 void renormalize_sdf(World* w, int grid, int iterations) {

@@ -310,6 +310,21 @@ static int defVDBRenormalizeSDF = zeno::defNodeClass<VDBRenormalizeSDF>("VDBReno
      /* params: */ {{"enum 1oUpwind", "method", "1oUpwind"}, {"int", "iterations", "4"}, {"int", "dilateIters", "0"}},
      /* category: */ {"openvdb"}});
 
+// ---- VDBErodeSDF (projects/zenvdb/VDBRenormalize.cpp:155-185)
+struct VDBErodeSDF : zeno::INode {
+    virtual void apply() override {
+        auto inoutSDF = get_input("inoutSDF")->as<VDBFloatGrid>();
+        const float depth = get_input("depth")->as<zeno::NumericObject>()->get<float>();
+        WorldHolder& h = world_for(float(inoutSDF->m_grid->voxelSize()[0]));
+        upload<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, inoutSDF->m_grid);
+        check(flipb200_erode_sdf(h.w, FLIPB200_KILLER_SDF, depth), "VDBErodeSDF");
+        download<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, inoutSDF->m_grid);
+        set_output("inoutSDF", get_input("inoutSDF"));
+    }
+};
+static int defVDBErodeSDF = zeno::defNodeClass<VDBErodeSDF>("VDBErodeSDF",
+    {/* inputs: */ {"inoutSDF", {"float", "depth"}}, /* outputs: */ {"inoutSDF"}, /* params: */ {}, /* category: */ {"openvdb"}});
+
 // ---- G2P_Advector (FF/nosys/G2P_Advector.cpp:16-69): the plain node
 struct G2P_Advector : zeno::INode {
     virtual void apply() override {
