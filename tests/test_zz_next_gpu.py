@@ -2,7 +2,8 @@
 
 The CPU side of this node is pinned in tests/test_ref_pin_cpu.py (the reference's own node class == oracle == the drop-in's node).
 This file compares the CUDA implementation with the oracle through the C ABI. It was written after the round's GPU budget was
-spent, so its first execution is the driver's round-end run: the expected-failure marker is non-strict and says so.
+spent, so its first execution is the driver's round-end run: the expected-failure marker is non-strict and says so. The device
+code of these kernels has already been executed on the CPU and matches the oracle bit for bit (tests/test_next_kernels_emul_cpu.py).
 """
 import numpy as np
 import pytest

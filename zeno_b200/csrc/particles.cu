@@ -7,6 +7,7 @@
 //   histogram (integer atomics)  ->  exclusive scan  ->  scatter source indices  ->
 //   per-voxel ascending fix-up of the (few) indices  ->  coalesced payload gather.
 #include "world.cuh"
+#include "next_kernels.cuh"
 
 namespace fb {
 namespace {
@@ -195,27 +196,9 @@ void rebin_particles(World* w, const TopoPtr& newPool, const uint32_t* keys_dev,
     w->pts = std::move(out);
 }
 
-// ---------------------------------------------------------------- KillParticlesInSDF
+// ---------------------------------------------------------------- nodes beyond the substep chain (bodies: next_kernels.cuh)
 namespace {
-// openvdb::tools::BoxSampler::sample, double weights (tools/Interpolation.h:712-737,763-778): a + float((b - a) * w)
-__device__ __forceinline__ float ip64(float a, float b, double w) {
-    return __fadd_rn(a, __double2float_rn(__dmul_rn((double)__fsub_rn(b, a), w)));
-}
-__device__ float box_sample_f64(const TopoView& t, const float* __restrict__ val, float bg, double x, double y, double z) {
-    const int bx = (int)floor(x), by = (int)floor(y), bz = (int)floor(z);
-    const double u = __dsub_rn(x, (double)bx), v = __dsub_rn(y, (double)by), w = __dsub_rn(z, (double)bz);
-    float d[8];
-#pragma unroll
-    for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int j = 0; j < 2; j++)
-#pragma unroll
-            for (int k = 0; k < 2; k++) d[i * 4 + j * 2 + k] = grid_get(t, val, bg, bx + i, by + j, bz + k);
-    return ip64(ip64(ip64(d[0], d[1], w), ip64(d[2], d[3], w), v), ip64(ip64(d[4], d[5], w), ip64(d[6], d[7], w), v), u);
-}
-// kill_particles_inside (FF/nosys/KillParticles.cpp:13-149), one CTA per store leaf: key = the particle's own voxel if it
-// survives, KEY_DROPPED otherwise; survivors' positions go through decode -> encode once (the reference rewrites them
-// through the attribute write handle, :138-141)
+// KillParticlesInSDF: one CTA per store leaf
 __global__ void __launch_bounds__(256) kill_keys_kernel(TopoView pt, const uint32_t* __restrict__ voxelStart, uint32_t* __restrict__ w0,
                                                         uint32_t* __restrict__ w1, TopoView st, const float* __restrict__ sval, float sbg,
                                                         int keep, uint32_t* __restrict__ keys) {
@@ -225,37 +208,13 @@ __global__ void __launch_bounds__(256) kill_keys_kernel(TopoView pt, const uint3
     for (int i = threadIdx.x; i <= LEAF; i += blockDim.x) sStart[i] = __ldg(&voxelStart[vbase + i]);
     __syncthreads();
     const uint32_t beg = sStart[0], end = sStart[LEAF];
-    const int3 o = pt.origin[leaf];
-    for (uint32_t gi = beg + threadIdx.x; gi < end; gi += blockDim.x) {
-        int lo = 0, hi = LEAF;   // voxel of this particle: largest off with sStart[off] <= gi
-        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (sStart[mid] <= gi) lo = mid; else hi = mid; }
-        const int off = lo;
-        const uint32_t a0 = w0[gi], a1 = w1[gi];
-        const float px = fx_decode(a0 & 0xffffu), py = fx_decode(a0 >> 16), pz = fx_decode(a1 & 0xffffu);
-        const float x = __fadd_rn((float)(o.x + (off >> 6)), px), y = __fadd_rn((float)(o.y + ((off >> 3) & 7)), py),
-                    z = __fadd_rn((float)(o.z + (off & 7)), pz);
-        const float s = box_sample_f64(st, sval, sbg, (double)x, (double)y, (double)z);
-        const bool alive = keep ? (s <= 0.f) : (s >= 0.f);
-        if (alive) {
-            w0[gi] = fx_encode(px) | (fx_encode(py) << 16);
-            w1[gi] = fx_encode(pz) | (a1 & 0xffff0000u);
-        }
-        keys[gi] = alive ? (uint32_t)leaf * LEAF + (uint32_t)off : KEY_DROPPED;
-    }
+    for (uint32_t gi = beg + threadIdx.x; gi < end; gi += blockDim.x)
+        nextk::kill_keys_one(pt, sStart, w0, w1, st, sval, sbg, keep, keys, leaf, gi);
 }
-}  // namespace
-
-namespace {
-// FLIP_vdb::point_integrate_vector, channel "vel" (FF/FLIP_vdb.cpp:3526-3532): half -> double, + dv, -> float -> half
+// ParticleAddDV
 __global__ void add_dv_kernel(uint32_t* __restrict__ w1, uint32_t* __restrict__ w2, uint64_t n, double dx, double dy, double dz) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t b = w1[i], c = w2[i];
-    const float vx = __double2float_rn(__dadd_rn((double)h_decode(b >> 16), dx));
-    const float vy = __double2float_rn(__dadd_rn((double)h_decode(c & 0xffffu), dy));
-    const float vz = __double2float_rn(__dadd_rn((double)h_decode(c >> 16), dz));
-    w1[i] = (b & 0xffffu) | (h_encode(vx) << 16);
-    w2[i] = h_encode(vy) | (h_encode(vz) << 16);
+    if (i < n) nextk::add_dv_one(w1, w2, i, dx, dy, dz);
 }
 }  // namespace
 

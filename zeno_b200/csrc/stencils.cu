@@ -1,6 +1,7 @@
 // libflipb200 -- the small single-pass stencil stages that keep a substep device resident (K14):
 // face weights, liquid-SDF push-out, body force, CFL, pressure-gradient subtraction.
 #include "world.cuh"
+#include "next_kernels.cuh"
 #include "levelset.cuh"
 
 namespace fb {
@@ -255,53 +256,15 @@ float cfl(World* w) {
     return w->dx / (fabsf(mv) + 1e-6f);
 }
 
-// ---------------------------------------------------------------- VDBRenormalizeSDF
+// ---------------------------------------------------------------- VDBRenormalizeSDF / VDBErodeSDF (bodies: next_kernels.cuh)
 namespace {
-// One Euler stage of openvdb::tools::LevelSetTracker's Normalizer (tools/LevelSetTracker.h:631-675) with the first-order
-// upwind Godunov norm (math/Operators.h:249-260, math/FiniteDifference.h:326-347): every ACTIVE voxel of `cur` gets
-// alpha*phi0 + beta*v (v alone when useAlpha == 0); inactive voxels keep their value; the stencil reads `cur` wherever it lands.
 __global__ void __launch_bounds__(512) renorm_stage_kernel(TopoView t, const uint64_t* __restrict__ mask, const float* __restrict__ cur,
                                                            const float* __restrict__ phi0, float* __restrict__ out, float bg, float dt,
                                                            float invDx, float alpha, float beta, int useAlpha) {
-    const int leaf = blockIdx.x, off = threadIdx.x;
-    const size_t i = (size_t)leaf * LEAF + off;
-    const float c = cur[i];
-    float r = c;
-    if (mask_get(mask, leaf, off)) {
-        const int3 o = t.origin[leaf];
-        const int x = o.x + (off >> 6), y = o.y + ((off >> 3) & 7), z = o.z + (off & 7);
-        const float ux = __fsub_rn(grid_get(t, cur, bg, x + 1, y, z), c), uy = __fsub_rn(grid_get(t, cur, bg, x, y + 1, z), c),
-                    uz = __fsub_rn(grid_get(t, cur, bg, x, y, z + 1), c);
-        const float dxm = __fsub_rn(c, grid_get(t, cur, bg, x - 1, y, z)), dym = __fsub_rn(c, grid_get(t, cur, bg, x, y - 1, z)),
-                    dzm = __fsub_rn(c, grid_get(t, cur, bg, x, y, z - 1));
-        float n2;
-        if (c > 0.f) {
-            float a = fmaxf(dxm, 0.f), b = fminf(ux, 0.f);
-            n2 = fmaxf(__fmul_rn(a, a), __fmul_rn(b, b));
-            a = fmaxf(dym, 0.f); b = fminf(uy, 0.f);
-            n2 = __fadd_rn(n2, fmaxf(__fmul_rn(a, a), __fmul_rn(b, b)));
-            a = fmaxf(dzm, 0.f); b = fminf(uz, 0.f);
-            n2 = __fadd_rn(n2, fmaxf(__fmul_rn(a, a), __fmul_rn(b, b)));
-        } else {
-            float a = fminf(dxm, 0.f), b = fmaxf(ux, 0.f);
-            n2 = fmaxf(__fmul_rn(a, a), __fmul_rn(b, b));
-            a = fminf(dym, 0.f); b = fmaxf(uy, 0.f);
-            n2 = __fadd_rn(n2, fmaxf(__fmul_rn(a, a), __fmul_rn(b, b)));
-            a = fminf(dzm, 0.f); b = fmaxf(uz, 0.f);
-            n2 = __fadd_rn(n2, fmaxf(__fmul_rn(a, a), __fmul_rn(b, b)));
-        }
-        float v = __fdiv_rn(c, __fadd_rn(__fsqrt_rn(__fadd_rn(__fmul_rn(c, c), n2)), 1e-8f));
-        v = __fsub_rn(c, __fmul_rn(__fmul_rn(dt, v), __fsub_rn(__fmul_rn(__fsqrt_rn(n2), invDx), 1.0f)));
-        r = useAlpha ? __fadd_rn(__fmul_rn(alpha, phi0[i]), __fmul_rn(beta, v)) : v;
-    }
-    out[i] = r;
+    nextk::renorm_stage_one(t, mask, cur, phi0, out, bg, dt, invDx, alpha, beta, useAlpha, blockIdx.x, threadIdx.x);
 }
-}  // namespace
-
-namespace {
 __global__ void __launch_bounds__(512) add_active_kernel(const uint64_t* __restrict__ mask, float* __restrict__ val, float d) {
-    const int leaf = blockIdx.x, off = threadIdx.x;
-    if (mask_get(mask, leaf, off)) { const size_t i = (size_t)leaf * LEAF + off; val[i] = __fadd_rn(val[i], d); }
+    nextk::add_active_one(mask, val, blockIdx.x, threadIdx.x, d);
 }
 }  // namespace
 // VDBErodeSDF::apply (projects/zenvdb/VDBRenormalize.cpp:155-172): every active voxel += depth
