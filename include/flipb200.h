@@ -133,6 +133,10 @@ int flipb200_renormalize_sdf(flipb200_world* w, int grid, int iterations, int di
 /* VDBErodeSDF (projects/zenvdb/VDBRenormalize.cpp:155-185, used once by the packaged FLIP template): adds `depth` to every
  * active voxel of float grid `grid`. */
 int flipb200_erode_sdf(flipb200_world* w, int grid, float depth);
+/* VDBSmoothSDF (projects/zenvdb/VDBRenormalize.cpp:108-133, used once by the packaged FLIP template) =
+ * openvdb::tools::Filter::gaussian(width, iterations) without mask or tiles: per iteration four separable box filters
+ * (passes X, Z, Y of 2*width+1 taps) on the active voxels of float grid `grid`. */
+int flipb200_smooth_sdf(flipb200_world* w, int grid, int width, int iterations);
 int flipb200_dropped(flipb200_world* w, uint64_t* n);
 /* ParticleAddDV (FF/nosys/ParticleAddGravity.cpp:9-19 -> FLIP_vdb::point_integrate_vector, FF/FLIP_vdb.cpp:3492-3535; SURVEY 8b
  * last row / 8f-1): adds dv to the stored velocity of every particle -- read as double from the half codec, summed in double,

@@ -163,6 +163,13 @@ int orc_erode_sdf(void* wp, int grid, float depth) {
     node_VDBErodeSDF(*g, depth);
     return 0;
 }
+int orc_smooth_sdf(void* wp, int grid, int width, int iterations) {
+    World* w = static_cast<World*>(wp);
+    FloatGrid* g = floatOf(w, grid);
+    if (!g) return 1;
+    node_VDBSmoothSDF(*g, width, iterations);
+    return 0;
+}
 int orc_face_weights(void* wp) { node_CutCellWeight(*static_cast<World*>(wp)); return 0; }
 int orc_pushout_sdf(void* wp, float dx) { node_PushOutLiquidSDF(*static_cast<World*>(wp), dx); return 0; }
 int orc_add_vector(void* wp, float x, float y, float z) { node_FieldAddVector(*static_cast<World*>(wp), x, y, z); return 0; }

@@ -80,6 +80,9 @@ void node_VDBRenormalizeSDF(FloatGrid& g, float voxelSize, int iterations);
 // VDBErodeSDF (projects/zenvdb/VDBRenormalize.cpp:155-172): every ACTIVE voxel += depth
 void node_VDBErodeSDF(FloatGrid& g, float depth);
 
+// VDBSmoothSDF (projects/zenvdb/VDBRenormalize.cpp:108-120) = openvdb::tools::Filter::gaussian (tools/Filter.h:503-514,574-630,744-768)
+void node_VDBSmoothSDF(FloatGrid& g, int width, int iterations);
+
 float fraction_inside(float phi_left, float phi_right);  // FF/levelset_util.cpp:5-15
 float fraction_inside(float bl, float br, float tl, float tr);  // FF/levelset_util.cpp:26-99
 

@@ -169,6 +169,11 @@ class OracleWorld:
         if rc != 0:
             raise RuntimeError("VDBErodeSDF failed")
 
+    def VDBSmoothSDF(self, grid: str, width: int = 1, iterations: int = 1):
+        rc = self.lib.orc_smooth_sdf(self.h, C.c_int(GRID_IDS[grid]), C.c_int(width), C.c_int(iterations))
+        if rc != 0:
+            raise RuntimeError("VDBSmoothSDF failed")
+
     def dropped(self) -> int:
         return int(self.lib.orc_dropped(self.h))
 
@@ -319,6 +324,9 @@ class PluginWorld(OracleWorld):
 
     def VDBErodeSDF(self, grid: str, depth: float):
         self._ck(self.lib.orc_erode_sdf(self.h, C.c_int(GRID_IDS[grid]), C.c_float(depth)))
+
+    def VDBSmoothSDF(self, grid: str, width: int = 1, iterations: int = 1):
+        self._ck(self.lib.orc_smooth_sdf(self.h, C.c_int(GRID_IDS[grid]), C.c_int(width), C.c_int(iterations)))
 
     def G2P_Advector(self, dt, dx=None, RK_ORDER=1, pic_smoothness=0.02):
         self._ck(self.lib.orc_g2p_advect(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.c_int(RK_ORDER), C.c_float(pic_smoothness)))

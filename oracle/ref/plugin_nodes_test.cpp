@@ -30,6 +30,7 @@
 #define flipb200_g2p_advect ob_g2p_advect
 #define flipb200_renormalize_sdf ob_renormalize_sdf
 #define flipb200_erode_sdf ob_erode_sdf
+#define flipb200_smooth_sdf ob_smooth_sdf
 #include <tbb/parallel_for.h>
 #include "../../zeno_b200/plugin/flipb200_nodes.cpp"
 
@@ -60,6 +61,7 @@ struct OracleApi {
     int (*g2p_plain)(void*, float, float, int, float) = nullptr;
     int (*renorm)(void*, int, int, int) = nullptr;
     int (*erode)(void*, int, float) = nullptr;
+    int (*smooth)(void*, int, int, int) = nullptr;
 };
 OracleApi g_orc;
 std::string g_err;
@@ -124,6 +126,7 @@ int ob_particles_add_dv(flipb200_world* w, float x, float y, float z) { return g
 int ob_g2p_advect(flipb200_world* w, float dt, float dx, int rk, float s) { return g_orc.g2p_plain(w->orc, dt, dx, rk, s); }
 int ob_renormalize_sdf(flipb200_world* w, int grid, int it, int dil) { return g_orc.renorm(w->orc, grid, it, dil); }
 int ob_erode_sdf(flipb200_world* w, int grid, float d) { return g_orc.erode(w->orc, grid, d); }
+int ob_smooth_sdf(flipb200_world* w, int grid, int wd, int it) { return g_orc.smooth(w->orc, grid, wd, it); }
 }  // extern "C"
 
 #define NH_FN(name) pn_##name
@@ -141,7 +144,7 @@ int pn_backend(const char* liboracle) {
         bind(g_orc.particles_set, "orc_particles_set"); bind(g_orc.particles_info, "orc_particles_info"); bind(g_orc.particles_get, "orc_particles_get");
         bind(g_orc.p2g, "orc_p2g"); bind(g_orc.g2p, "orc_g2p_advect_sheetty"); bind(g_orc.face_weights, "orc_face_weights");
         bind(g_orc.pushout, "orc_pushout_sdf"); bind(g_orc.add_vector, "orc_add_vector"); bind(g_orc.cfl, "orc_cfl");
-        bind(g_orc.solve, "orc_solve_ppe"); bind(g_orc.subtract, "orc_subtract_grad"); bind(g_orc.kill, "orc_kill_particles"); bind(g_orc.add_dv, "orc_particles_add_dv"); bind(g_orc.g2p_plain, "orc_g2p_advect"); bind(g_orc.renorm, "orc_renormalize_sdf"); bind(g_orc.erode, "orc_erode_sdf");
+        bind(g_orc.solve, "orc_solve_ppe"); bind(g_orc.subtract, "orc_subtract_grad"); bind(g_orc.kill, "orc_kill_particles"); bind(g_orc.add_dv, "orc_particles_add_dv"); bind(g_orc.g2p_plain, "orc_g2p_advect"); bind(g_orc.renorm, "orc_renormalize_sdf"); bind(g_orc.erode, "orc_erode_sdf"); bind(g_orc.smooth, "orc_smooth_sdf");
     });
 }
 }  // extern "C"

@@ -301,4 +301,32 @@ void node_VDBErodeSDF(FloatGrid& g, float depth) {
             if (maskGet(g.masks[l], off)) g.vals[size_t(l) * 512 + off] += depth;
 }
 
+// VDBSmoothSDF::apply -> Filter::gaussian(width, iterations, nullptr), tiles off: per iteration 4 x (box X, box Z, box Y); each pass
+// writes (sum_{k=-w..w} value shifted by k along the axis, float adds in that order) * (1.f / float(2w+1)) to the ACTIVE voxels
+void node_VDBSmoothSDF(FloatGrid& g, int width, int iterations) {
+    if (iterations <= 0) return;
+    const int w = std::max(1, width);
+    const float frac = 1.f / float(2 * w + 1);
+    static const int order[3] = {0, 2, 1};
+    std::vector<float> next;
+    for (int it = 0; it < iterations; it++)
+        for (int rep = 0; rep < 4; rep++)
+            for (int a = 0; a < 3; a++) {
+                const int axis = order[a];
+                next = g.vals;
+                for (int l = 0; l < g.leafCount(); l++) {
+                    const Coord o = g.origins[l];
+                    for (int off = 0; off < 512; off++) {
+                        if (!maskGet(g.masks[l], off)) continue;
+                        int c[3] = {o.x + (off >> 6), o.y + ((off >> 3) & 7), o.z + (off & 7)};
+                        const int centre = c[axis];
+                        float sum = 0.f;
+                        for (int k = -w; k <= w; k++) { c[axis] = centre + k; sum += g.get(0, c[0], c[1], c[2]); }
+                        next[size_t(l) * 512 + off] = sum * frac;
+                    }
+                }
+                g.vals.swap(next);
+            }
+}
+
 }  // namespace orc

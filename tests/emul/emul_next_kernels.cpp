@@ -39,6 +39,12 @@ void emul_renorm_stage(int n, const int* dmin, const int* ddim, const int* dir, 
     for (int leaf = 0; leaf < n; leaf++)
         for (int off = 0; off < LEAF; off++) nextk::renorm_stage_one(t, mask, cur, phi0, out, bg, dt, invDx, alpha, beta, useAlpha, leaf, off);
 }
+void emul_box_avg(int n, const int* dmin, const int* ddim, const int* dir, const int* origins, const uint64_t* mask, const float* cur,
+                  float* out, float bg, int axis, int w, float frac) {
+    const TopoView t = view(n, dmin, ddim, dir, origins);
+    for (int leaf = 0; leaf < n; leaf++)
+        for (int off = 0; off < LEAF; off++) nextk::box_avg_one(t, mask, cur, out, bg, axis, w, frac, leaf, off);
+}
 void emul_add_active(int n, const uint64_t* mask, float* val, float d) {
     for (int leaf = 0; leaf < n; leaf++)
         for (int off = 0; off < LEAF; off++) nextk::add_active_one(mask, val, leaf, off, d);

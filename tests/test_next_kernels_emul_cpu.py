@@ -171,3 +171,21 @@ def test_kill_keys_device_code(emul, scene, oracle_lib, keep):
     new_start = np.concatenate([[0], np.cumsum(counts)]).astype(np.uint32)
     got = particles_from_device(t, new_start, w0[alive], w1[alive], w2[alive])
     util.compare_particles(got, ow.get_particles(), "device code of kill_keys vs oracle")
+
+
+def test_box_avg_device_code(emul, scene, oracle_lib):
+    from oracle.pyoracle import OracleWorld
+    ow = OracleWorld(scene["dx"])
+    ow.set_grid("LiquidSDF", scene["sdf"])
+    ow.VDBSmoothSDF("LiquidSDF", 2, 2)
+    # host sequence of smooth_sdf (stencils.cu): per iteration 4 x (X, Z, Y), ping-pong
+    t, val, mask = grid_to_device(scene["sdf"])
+    bg = np.float32(scene["sdf"]["bg"][0])
+    a = np.empty_like(val)
+    w, frac = 2, np.float32(1.0) / np.float32(5.0)
+    for _ in range(2):
+        for _rep in range(4):
+            for axis in (0, 2, 1):
+                emul.emul_box_avg(*t.args(), _p(mask), _p(val), _p(a), C.c_float(bg), C.c_int(axis), C.c_int(w), C.c_float(frac))
+                val, a = a, val
+    util.compare_grids(grid_from_device(t, val, mask, [bg]), ow.get_grid("LiquidSDF"), "device code of box_avg vs oracle", tol=0.0)

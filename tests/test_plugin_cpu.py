@@ -12,7 +12,7 @@ REF_FILES = {"FLIP_P2G": "P2G.cpp", "G2PAdvectorSheetty": "SheetG2PAdvector.cpp"
              "PushOutLiquidSDF": "FixLiquidSDF.cpp", "FieldAddVector": "FieldAddVector.cpp", "CFL_dt": "CFL.cpp",
              "KillParticlesInSDF": "KillParticles.cpp", "ParticleAddDV": "ParticleAddGravity.cpp",
              "G2P_Advector": "G2P_Advector.cpp", "VDBRenormalizeSDF": "../../zenvdb/VDBRenormalize.cpp",
-             "VDBErodeSDF": "../../zenvdb/VDBRenormalize.cpp"}
+             "VDBErodeSDF": "../../zenvdb/VDBRenormalize.cpp", "VDBSmoothSDF": "../../zenvdb/VDBRenormalize.cpp"}
 # (inputs, outputs, params) by name only, recorded from the reference files above
 EXPECTED = {
     "FLIP_P2G": (["Dx", "Particles", "Velocity", "PostP2GVelocity", "LiquidSDF"], [], ["dx", "VelExtraLayer"]),
@@ -31,6 +31,7 @@ EXPECTED = {
     "G2P_Advector": (["dt", "Dx", "Particles", "Velocity", "PostAdvVelocity", "SolidSDF", "SolidVelocity"], [], ["dx", "RK_ORDER", "pic_smoothness"]),
     "VDBRenormalizeSDF": (["inoutSDF"], ["inoutSDF"], ["method", "iterations", "dilateIters"]),
     "VDBErodeSDF": (["inoutSDF", "depth"], ["inoutSDF"], []),
+    "VDBSmoothSDF": (["inoutSDF"], ["inoutSDF"], ["width", "iterations", "DEPRECATED"]),
 }
 
 

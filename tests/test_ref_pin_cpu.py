@@ -245,3 +245,28 @@ def test_erode_sdf_oracle_plugin_and_reference_node(oracle_lib):
     for w, what in zip(worlds[1:], ("oracle", "plugin node")):
         util.compare_grids(w.get_grid("LiquidSDF"), ref, f"VDBErodeSDF: {what} vs the reference node", tol=0.0)
     assert not np.array_equal(scenes.canonical_grid(before)["values"], scenes.canonical_grid(ref)["values"])
+
+
+@pytest.mark.parametrize("width,iterations", [(1, 1), (2, 2)])
+def test_smooth_sdf_oracle_plugin_and_reference_node(oracle_lib, width, iterations):
+    """VDBSmoothSDF (projects/zenvdb/VDBRenormalize.cpp:108-133 -> openvdb::tools::Filter::gaussian): the real node class with the
+    vendored OpenVDB filter, the oracle restatement (four X/Z/Y box-filter rounds per iteration) and the drop-in's node."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "rn_smooth_sdf"):
+        pytest.skip("oracle/_ref with the reference-node harness is not available here")
+    from oracle.pyoracle import OracleWorld, PluginWorld, RefNodeWorld
+    from zeno_b200 import scenes
+    pos, vel, dx = scenes.dam_break_points(32, seed=8)
+    worlds = [cls(dx) for cls in (RefNodeWorld, OracleWorld, PluginWorld)]
+    for w in worlds:
+        w.PrimToVDBPointDataGrid(pos, vel)
+    worlds[0].FLIP_P2G(dx, 3)
+    before = worlds[0].get_grid("LiquidSDF")
+    for w in worlds[1:]:
+        w.set_grid("LiquidSDF", before)
+    for w in worlds:
+        w.VDBSmoothSDF("LiquidSDF", width, iterations)
+    ref, orc, plg = (w.get_grid("LiquidSDF") for w in worlds)
+    util.compare_grids(orc, ref, "VDBSmoothSDF: oracle vs the reference node", tol=0.0)
+    util.compare_grids(plg, orc, "VDBSmoothSDF: plugin node vs oracle", tol=0.0)
+    assert not np.array_equal(scenes.canonical_grid(before)["values"], scenes.canonical_grid(ref)["values"])

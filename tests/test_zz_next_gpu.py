@@ -107,3 +107,17 @@ def test_erode_sdf_matches_oracle(gpu_lib, oracle_lib):
         w.VDBErodeSDF("LiquidSDF", 0.37 * dx)
     util.compare_grids(gw.get_grid("LiquidSDF"), ow.get_grid("LiquidSDF"), "VDBErodeSDF vs oracle", tol=0.0, check_inactive=False)
     gw.close()
+
+
+@FIRST_RUN
+def test_smooth_sdf_matches_oracle(gpu_lib, oracle_lib):
+    from oracle.pyoracle import OracleWorld
+    from zeno_b200 import abi
+    pos, vel, dx = scenes.dam_break_points(32, seed=8)
+    gw, ow = abi.World(dx), OracleWorld(dx)
+    for w in (gw, ow):
+        w.PrimToVDBPointDataGrid(pos, vel)
+        w.FLIP_P2G(dx, 3)
+        w.VDBSmoothSDF("LiquidSDF", 2, 2)
+    util.compare_grids(gw.get_grid("LiquidSDF"), ow.get_grid("LiquidSDF"), "VDBSmoothSDF vs oracle", tol=0.0, check_inactive=False)
+    gw.close()

@@ -39,7 +39,7 @@ EXPORTS = [
     "flipb200_profile_reset", "flipb200_profile_get", "flipb200_stream", "flipb200_comm_unique_id",
     "flipb200_comm_init", "flipb200_comm_init_local", "flipb200_comm_abort", "flipb200_dd_set_slab", "flipb200_dd_owned",
     "flipb200_dd_owned_particles",
-    "flipb200_sync_count", "flipb200_renormalize_sdf", "flipb200_erode_sdf", "flipb200_g2p_advect", "flipb200_kill_particles_in_sdf", "flipb200_particles_add_dv", "flipb200_particles_download_begin", "flipb200_grid_download_begin", "flipb200_download_wait",
+    "flipb200_sync_count", "flipb200_smooth_sdf", "flipb200_renormalize_sdf", "flipb200_erode_sdf", "flipb200_g2p_advect", "flipb200_kill_particles_in_sdf", "flipb200_particles_add_dv", "flipb200_particles_download_begin", "flipb200_grid_download_begin", "flipb200_download_wait",
 ]
 
 
@@ -241,6 +241,9 @@ class World:
 
     def VDBErodeSDF(self, grid: str, depth: float):
         self._ck(self.lib.flipb200_erode_sdf(self.h, C.c_int(GRID_IDS[grid]), C.c_float(depth)))
+
+    def VDBSmoothSDF(self, grid: str, width: int = 1, iterations: int = 1):
+        self._ck(self.lib.flipb200_smooth_sdf(self.h, C.c_int(GRID_IDS[grid]), C.c_int(width), C.c_int(iterations)))
 
     def dropped(self) -> int:
         n = C.c_uint64(0)

@@ -575,6 +575,9 @@ int flipb200_renormalize_sdf(flipb200_world* w, int grid, int iterations, int di
 int flipb200_erode_sdf(flipb200_world* w, int grid, float depth) {
     return guarded([&] { FB_REQUIRE(w, FLIPB200_ERR_ARG, "erode_sdf: null world"); use_device(w); erode_sdf(w, grid, depth); sync(w); });
 }
+int flipb200_smooth_sdf(flipb200_world* w, int grid, int width, int iterations) {
+    return guarded([&] { FB_REQUIRE(w, FLIPB200_ERR_ARG, "smooth_sdf: null world"); use_device(w); smooth_sdf(w, grid, width, iterations); sync(w); });
+}
 int flipb200_dropped(flipb200_world* w, uint64_t* n) {
     return guarded([&] { FB_REQUIRE(w && n, FLIPB200_ERR_ARG, "dropped: bad argument"); *n = w->dropped; });
 }

@@ -103,5 +103,26 @@ __device__ __forceinline__ void renorm_stage_one(const TopoView& t, const uint64
     out[i] = r;
 }
 
+// One pass of openvdb::tools::Filter's separable box filter (tools/Filter.h:503-514,744-768, no alpha mask): an ACTIVE voxel of `cur`
+// gets (sum over k = -w..w of cur at the voxel shifted by k along `axis`, added in that order) * frac; the taps read `cur` wherever
+// they land (inactive voxels and the background included); an inactive voxel keeps its value.
+__device__ __forceinline__ void box_avg_one(const TopoView& t, const uint64_t* __restrict__ mask, const float* __restrict__ cur,
+                                            float* __restrict__ out, float bg, int axis, int w, float frac, int leaf, int off) {
+    const size_t i = (size_t)leaf * LEAF + off;
+    float r = cur[i];
+    if (mask_get(mask, leaf, off)) {
+        const int3 o = t.origin[leaf];
+        int c[3] = {o.x + (off >> 6), o.y + ((off >> 3) & 7), o.z + (off & 7)};
+        const int centre = c[axis];
+        float sum = 0.f;
+        for (int k = -w; k <= w; k++) {
+            c[axis] = centre + k;
+            sum = __fadd_rn(sum, grid_get(t, cur, bg, c[0], c[1], c[2]));
+        }
+        r = __fmul_rn(sum, frac);
+    }
+    out[i] = r;
+}
+
 }  // namespace nextk
 }  // namespace fb

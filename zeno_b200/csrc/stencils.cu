@@ -263,10 +263,35 @@ __global__ void __launch_bounds__(512) renorm_stage_kernel(TopoView t, const uin
                                                            float invDx, float alpha, float beta, int useAlpha) {
     nextk::renorm_stage_one(t, mask, cur, phi0, out, bg, dt, invDx, alpha, beta, useAlpha, blockIdx.x, threadIdx.x);
 }
+__global__ void __launch_bounds__(512) box_avg_kernel(TopoView t, const uint64_t* __restrict__ mask, const float* __restrict__ cur,
+                                                      float* __restrict__ out, float bg, int axis, int w, float frac) {
+    nextk::box_avg_one(t, mask, cur, out, bg, axis, w, frac, blockIdx.x, threadIdx.x);
+}
 __global__ void __launch_bounds__(512) add_active_kernel(const uint64_t* __restrict__ mask, float* __restrict__ val, float d) {
     nextk::add_active_one(mask, val, blockIdx.x, threadIdx.x, d);
 }
 }  // namespace
+// VDBSmoothSDF::apply (projects/zenvdb/VDBRenormalize.cpp:108-120) = openvdb::tools::Filter::gaussian(width, iterations), tiles off
+// (tools/Filter.h:574-630): per iteration four box filters, each as three one-dimensional passes in the order X, Z, Y
+void smooth_sdf(World* w, int grid, int width, int iterations) {
+    FB_REQUIRE(is_float_grid(grid) && w->F(grid).topo != nullptr, FLIPB200_ERR_STATE, "VDBSmoothSDF: the grid does not exist");
+    GridF& g = w->F(grid);
+    const int n = g.topo->n;
+    if (!n || iterations <= 0) return;
+    const int wd = width < 1 ? 1 : width;
+    const float frac = 1.f / (float)(2 * wd + 1);
+    DBuf<float> a((size_t)n * LEAF, w->stream);
+    const TopoView t = g.topo->view();
+    static const int order[3] = {0, 2, 1};
+    for (int it = 0; it < iterations; it++)
+        for (int rep = 0; rep < 4; rep++)
+            for (int k = 0; k < 3; k++) {
+                FB_LAUNCH(w, "box_avg", (size_t)n * LEAF * 8) box_avg_kernel<<<n, 512, 0, w->stream>>>(t, g.mask.p, g.val.p, a.p, g.bg, order[k], wd, frac);
+                check_launch("box_avg");
+                std::swap(g.val, a);
+            }
+}
+
 // VDBErodeSDF::apply (projects/zenvdb/VDBRenormalize.cpp:155-172): every active voxel += depth
 void erode_sdf(World* w, int grid, float depth) {
     FB_REQUIRE(is_float_grid(grid) && w->F(grid).topo != nullptr, FLIPB200_ERR_STATE, "VDBErodeSDF: the grid does not exist");

@@ -201,7 +201,8 @@ float cfl(World* w);
 void subtract_grad(World* w, float dt, float dx, int velExtraLayer);
 // VDBRenormalizeSDF (projects/zenvdb/VDBRenormalize.cpp): LevelSetTracker::normalize x iterations on a float grid
 void renormalize_sdf(World* w, int grid, int iterations);
-void erode_sdf(World* w, int grid, float depth);   // VDBErodeSDF: active voxels += depth
+void erode_sdf(World* w, int grid, float depth);
+void smooth_sdf(World* w, int grid, int width, int iterations);   // VDBSmoothSDF: openvdb Filter::gaussian   // VDBErodeSDF: active voxels += depth
 // per-channel masks are [3][n][8]; target topology mask = liquid SDF mask
 void union_extrapolate(World* w, int nLayer, GridV& vel, uint64_t* chMask, const uint64_t* targetMask);
 void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter);

@@ -310,6 +310,24 @@ static int defVDBRenormalizeSDF = zeno::defNodeClass<VDBRenormalizeSDF>("VDBReno
      /* params: */ {{"enum 1oUpwind", "method", "1oUpwind"}, {"int", "iterations", "4"}, {"int", "dilateIters", "0"}},
      /* category: */ {"openvdb"}});
 
+// ---- VDBSmoothSDF (projects/zenvdb/VDBRenormalize.cpp:108-133; "deprecated" category, still wired in the packaged FLIP template)
+struct VDBSmoothSDF : zeno::INode {
+    virtual void apply() override {
+        auto inoutSDF = get_input("inoutSDF")->as<VDBFloatGrid>();
+        const int width = get_param<int>("width");
+        const int iterations = get_param<int>("iterations");
+        WorldHolder& h = world_for(float(inoutSDF->m_grid->voxelSize()[0]));
+        upload<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, inoutSDF->m_grid);
+        check(flipb200_smooth_sdf(h.w, FLIPB200_KILLER_SDF, width, iterations), "VDBSmoothSDF");
+        download<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, inoutSDF->m_grid);
+        set_output("inoutSDF", get_input("inoutSDF"));
+    }
+};
+static int defVDBSmoothSDF = zeno::defNodeClass<VDBSmoothSDF>("VDBSmoothSDF",
+    {/* inputs: */ {"inoutSDF"}, /* outputs: */ {"inoutSDF"},
+     /* params: */ {{"int", "width", "1"}, {"int", "iterations", "1"}, {"string", "DEPRECATED", "Use VDBSmooth Instead"}},
+     /* category: */ {"deprecated"}});
+
 // ---- VDBErodeSDF (projects/zenvdb/VDBRenormalize.cpp:155-185)
 struct VDBErodeSDF : zeno::INode {
     virtual void apply() override {
