@@ -212,6 +212,8 @@ int flipb200_comm_abort(flipb200_world* w);
 /* Slab decomposition (no reference counterpart: the reference runs one TBB process).
  * This rank owns the leaf layers [leafLo, leafHi) along x (leaf coordinate = voxel >> 3); the first rank's lower and
  * the last rank's upper bound are open. Slabs must be at least two layers thick and cover the axis without gaps.
+ * (VDBRenormalizeSDF and VDBSmoothSDF are refused in this mode for now: FLIPB200_ERR_STATE; the particle-local nodes
+ * KillParticlesInSDF / ParticleAddDV / VDBErodeSDF need no exchange.)
  * From here on every node call is COLLECTIVE (all ranks issue the same sequence): flipb200_bin_from_points routes
  * points to their owners and fills the ghost layers, flipb200_g2p_advect_sheetty migrates particles,
  * P2G / solve / gradient exchange ghost leaves, CFL and the PCG scalars are all-reduced. Grids and particles

@@ -275,6 +275,8 @@ __global__ void __launch_bounds__(512) add_active_kernel(const uint64_t* __restr
 // (tools/Filter.h:574-630): per iteration four box filters, each as three one-dimensional passes in the order X, Z, Y
 void smooth_sdf(World* w, int grid, int width, int iterations) {
     FB_REQUIRE(is_float_grid(grid) && w->F(grid).topo != nullptr, FLIPB200_ERR_STATE, "VDBSmoothSDF: the grid does not exist");
+    // every pass reads `width` voxels across a slab face; the ghost-leaf refresh between passes is not wired up yet
+    FB_REQUIRE(!dd_on(w), FLIPB200_ERR_STATE, "VDBSmoothSDF is not available under slab decomposition yet");
     GridF& g = w->F(grid);
     const int n = g.topo->n;
     if (!n || iterations <= 0) return;
@@ -306,6 +308,8 @@ void erode_sdf(World* w, int grid, float depth) {
 // `iterations` x normalize(); each normalize = three Euler stages (Normalizer::normalize, LevelSetTracker.h:535-604)
 void renormalize_sdf(World* w, int grid, int iterations) {
     FB_REQUIRE(is_float_grid(grid) && w->F(grid).topo != nullptr, FLIPB200_ERR_STATE, "VDBRenormalizeSDF: the grid does not exist");
+    // twelve stencil passes read across a slab face; the ghost-leaf refresh between them is not wired up yet
+    FB_REQUIRE(!dd_on(w), FLIPB200_ERR_STATE, "VDBRenormalizeSDF is not available under slab decomposition yet");
     GridF& g = w->F(grid);
     const int n = g.topo->n;
     if (!n || iterations <= 0) return;
