@@ -10,7 +10,10 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=fa
 mkdir -p _build
 pids=()
 for f in scan topo particles p2g g2p stencils poisson abi comm dd; do
-  if [ ! -f _build/$f.o ] || [ $f.cu -nt _build/$f.o ] || [ common.cuh -nt _build/$f.o ] || [ world.cuh -nt _build/$f.o ] || [ levelset.cuh -nt _build/$f.o ] || [ next_kernels.cuh -nt _build/$f.o ] || [ ../../include/flipb200.h -nt _build/$f.o ]; then
+  stale=0
+  [ -f _build/$f.o ] || stale=1
+  for dep in $f.cu *.cuh ../../include/flipb200.h build.sh; do [ $dep -nt _build/$f.o ] && stale=1; done
+  if [ $stale = 1 ]; then
     ( $NVCC $FLAGS -c $f.cu -o _build/$f.o > _build/$f.log 2>&1 || { cat _build/$f.log; exit 1; } ) &
     pids+=($!)
   fi

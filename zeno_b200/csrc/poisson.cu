@@ -1301,6 +1301,8 @@ __global__ void __launch_bounds__(512) dd_scatter_coarse_kernel(TopoView gt, Top
     if ((threadIdx.x & 31) == 0) reinterpret_cast<uint32_t*>(gdof)[(size_t)leaf * 16 + (threadIdx.x >> 5)] = bal;
 }
 
+#include "mg_cluster.cuh"
+
 // ---------------------------------------------------------------- host-side solver
 // The bottom runs on ONE SM: its coefficient set (7 arrays x 2 KB per leaf) has to stay inside that SM's
 // L1 + shared memory (256 KB) or every pass turns into a serial chain of L2 round trips (measured: a 64-leaf
@@ -1341,6 +1343,18 @@ struct Solver {
     static constexpr int cycleGridMax = 192;
     size_t cycleSmem = 0;
     DBuf<unsigned> cycleBarrier;
+    // mg_cluster_kernel (mg_cluster.cuh): levels >= clFirst run inside one thread-block cluster
+    struct ClusterHost { DBuf<uint32_t> assign; DBuf<ClMeta> meta; int nN = 0, nC = 0, xbPer = 0, coefPer = 0, xbOff = 0, coefOff = 0, metaOff = 0; };
+    std::vector<ClusterHost> clHost;   // index = level
+    DBuf<int> clCounts;
+    bool tiles = true;                 // FLIPB200_MG_PATH=cycle selects the round-1 one-launch cycle kernel instead
+    bool clusterReady = false;
+    int clFirst = 0, clSize = 0, clCandFirst = 0;
+    size_t clSmem = 0;
+    int clXbBytes = 0, clCgOff = 0, clSresOff = 0, clProgOff = 0, clDumpOff = 0;
+    DBuf<uint8_t> clProg[3];           // one visit from a zero guess / one visit from the current iterate / both in a row
+    std::vector<uint8_t> clHostOps[3];
+    int clOps[3] = {0, 0, 0};
     int bottomFirst = 0;        // first level handled by mg_bottom_kernel
     bool bottomInSmem = false;  // x (and the lower levels' b) of the bottom live in shared memory
     size_t bottomSmem = 0;
@@ -1450,7 +1464,7 @@ struct Solver {
         comm_allreduce(w, G.ze.p, nv, CT_F32, false);
         comm_allreduce(w, G.dof.p, (size_t)G.n * 16, CT_U32, false);   // disjoint bits: sum == or
         coarse = std::make_unique<Solver>();
-        coarse->w = w; coarse->dt = dt; coarse->coarseOnly = true;
+        coarse->w = w; coarse->dt = dt; coarse->coarseOnly = true; coarse->tiles = tiles;
         coarse->finish_level(G);
         coarse->alloc_vectors(G);
         coarse->levels.push_back(std::move(Gp));
@@ -1581,6 +1595,7 @@ struct Solver {
             H.blob.zero();
             H.voxelOfRow.alloc(H.np, w->stream);
         }
+        cluster_rank_leaves();   // its counts come back with the same host wait
         {   // red row counts of all compact levels (= the last entry of each exclusive scan) in one host wait
             uint32_t* nr = reinterpret_cast<uint32_t*>(w->hostScratch);
             for (size_t i = 0; i < compact.size(); i++)
@@ -1642,9 +1657,192 @@ struct Solver {
         cycleBarrier.alloc(1, w->stream);
         FB_CUDA(cudaFuncSetAttribute(mg_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cycleSmem));
         FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, mg_cycle_kernel, BOT_THREADS, cycleSmem));
+        if (tiles) cluster_prepare(n);
         if (!coop || perSm < 1) return;
         cycleGrid = compactFirst == 0 ? 1 : std::min(sms, (int)cycleGridMax);
         cycleReady = true;
+    }
+    // ---- mg_cluster_kernel: which cluster size the part gives us (16 is the non-portable maximum)
+    static int cluster_size(size_t smem) {
+        static int cached = -1;
+        if (cached >= 0) return cached;
+        cached = 0;
+        if (const char* e = getenv("FLIPB200_CLUSTER")) { const int v = atoi(e); if (v == 0) return cached; }
+        if (cudaFuncSetAttribute(mg_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); }
+        if (cudaFuncSetAttribute(mg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return cached; }
+        int want = 16;
+        if (const char* e = getenv("FLIPB200_CLUSTER")) want = atoi(e);
+        for (int c = want; c >= 2; c >>= 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(c); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = c; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, mg_cluster_kernel, &cfg) == cudaSuccess && nc >= 1) { cached = c; break; }
+            cudaGetLastError();
+        }
+        return cached;
+    }
+    size_t cluster_cap() const {
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, mg_cluster_kernel) != cudaSuccess) { cudaGetLastError(); return 0; }
+        return (size_t)optin - fa.sharedSizeBytes - 256;
+    }
+    // step 1 (before the host wait of prepare_cycle): rank the leaves of every candidate level
+    void cluster_rank_leaves() {
+        clusterReady = false;
+        const int nl = (int)levels.size();
+        clHost.clear();
+        clHost.resize(nl);
+        clSize = cluster_size(cluster_cap());
+        if (clSize < 2) return;
+        clCandFirst = nl;
+        clCounts.alloc((size_t)2 * nl, w->stream);
+        clCounts.zero();
+        for (int l = nl - 1; l >= 0 && nl - l <= CL_MAX_LEVELS && levels[l]->n <= 1024; l--) {
+            clCandFirst = l;
+            clHost[l].assign.alloc(levels[l]->n, w->stream);
+            FB_LAUNCH(w, "mg_cluster_assign", (size_t)levels[l]->n * 132)
+                cl_assign_kernel<<<1, 1024, 0, w->stream>>>(levels[l]->info.p, levels[l]->n, clSize - 1, clHost[l].assign.p, clCounts.p + 2 * l);
+        }
+        check_launch("cl_assign");
+        if (clCandFirst < nl) FB_CUDA(cudaMemcpyAsync(w->hostScratch + 256, clCounts.p, (size_t)8 * nl, cudaMemcpyDeviceToHost, w->stream));
+    }
+    void emit_cl(std::vector<uint8_t>& ops, int li, int nb, int n, bool skipFirst) {
+        auto put = [&](int code) { ops.push_back((uint8_t)(code | (li << 3))); };
+        if (li == nb - 1) { if (skipFirst) put(OP_COARSE); return; }
+        if (skipFirst) { put(OP_ZERO_RED); put(OP_BLACK); }
+        for (int i = (skipFirst ? 1 : 0); i < n; i++) { put(OP_RED); put(OP_BLACK); }
+        put(OP_RESID_RESTRICT);
+        emit_cl(ops, li + 1, nb, n, true);
+        emit_cl(ops, li + 1, nb, n, false);
+        put(OP_PROLONG);
+        for (int i = 0; i < n; i++) { put(OP_BLACK); put(OP_RED); }
+    }
+    // step 2 (after the host wait): how many levels fit, shared-memory map, op lists
+    void cluster_prepare(int n) {
+        const int nl = (int)levels.size();
+        if (clSize < 2 || clCandFirst >= nl || compact.empty()) return;
+        const int* cnt = reinterpret_cast<const int*>(w->hostScratch + 256);
+        for (int l = clCandFirst; l < nl; l++) { clHost[l].nN = cnt[2 * l]; clHost[l].nC = cnt[2 * l + 1]; }
+        const size_t cap = cluster_cap();
+        const int ranks = clSize - 1;
+        const int npc = compact.back().np;
+        const size_t cgBytes = (size_t)48 * npc;
+        const size_t sresBytes = (size_t)CL_GROUPS * LEAF * 4 + CL_XB_BYTES + CL_MAX_OPS;
+        if (cgBytes + CL_MAX_OPS > cap) return;
+        auto need = [&](int first) {
+            size_t b = sresBytes;
+            for (int l = first; l < nl; l++) {
+                const ClusterHost& H = clHost[l];
+                const size_t per = (H.nN + ranks - 1) / ranks, perC = (H.nC + ranks - 1) / ranks;
+                b += (per + perC) * (CL_XB_BYTES + sizeof(ClSlot)) + per * CL_COEF_BYTES;
+            }
+            return b;
+        };
+        if (need(nl - 1) > cap) return;
+        clFirst = nl - 1;
+        while (clFirst > clCandFirst && need(clFirst - 1) <= cap) clFirst--;
+        if (const char* e = getenv("FLIPB200_CLUSTER_FIRST")) clFirst = std::max(clFirst, std::min(nl - 1, atoi(e)));
+        size_t cursor = 0;
+        for (int l = clFirst; l < nl; l++) {
+            ClusterHost& H = clHost[l];
+            H.coefPer = (H.nN + ranks - 1) / ranks;
+            H.xbPer = H.coefPer + (H.nC + ranks - 1) / ranks;
+            H.xbOff = (int)cursor; cursor += (size_t)H.xbPer * CL_XB_BYTES;
+        }
+        clXbBytes = (int)cursor;
+        for (int l = clFirst; l < nl; l++) { ClusterHost& H = clHost[l]; H.coefOff = (int)cursor; cursor += (size_t)H.coefPer * CL_COEF_BYTES; }
+        for (int l = clFirst; l < nl; l++) { ClusterHost& H = clHost[l]; H.metaOff = (int)cursor; cursor += (size_t)H.xbPer * sizeof(ClSlot); }
+        clSresOff = (int)cursor; cursor += (size_t)CL_GROUPS * LEAF * 4;
+        clDumpOff = (int)cursor; cursor += CL_XB_BYTES;
+        clCgOff = 0;
+        cursor = std::max(cursor, (cgBytes + 15) & ~(size_t)15);
+        clProgOff = (int)cursor; cursor += CL_MAX_OPS;
+        clSmem = cursor;
+        if (clSmem > cap) return;
+        for (int v = 0; v < 3; v++) {
+            std::vector<uint8_t>& ops = clHostOps[v];
+            ops.clear();
+            if (v != 1) emit_cl(ops, 0, nl - clFirst, n, true);
+            if (v != 0) emit_cl(ops, 0, nl - clFirst, n, false);
+            clOps[v] = (int)ops.size();
+            if (clOps[v] > CL_MAX_OPS) return;
+            clProg[v].alloc(ops.size() + 1, w->stream);
+            if (!ops.empty()) FB_CUDA(cudaMemcpyAsync(clProg[v].p, ops.data(), ops.size(), cudaMemcpyHostToDevice, w->stream));
+        }
+        for (int l = clFirst; l < nl; l++) {   // the per-slot records (neighbours, parent, masks), once per solve
+            ClusterHost& H = clHost[l];
+            H.meta.alloc((size_t)clSize * H.xbPer, w->stream);
+            H.meta.fill_bytes(0xff);
+            const bool hasC = l + 1 < nl;
+            FB_LAUNCH(w, "mg_cluster_meta", (size_t)levels[l]->n * 400)
+                cl_meta_kernel<<<(levels[l]->n + 127) / 128, 128, 0, w->stream>>>(view_of(*levels[l]), H.assign.p, levels[l]->n, H.xbPer, H.meta.p,
+                                                                                   view_of(*levels[hasC ? l + 1 : l]), hasC ? clHost[l + 1].assign.p : nullptr);
+        }
+        check_launch("cl_meta");
+        FB_CUDA(cudaFuncSetAttribute(mg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_cap()));
+        clusterReady = true;
+    }
+    // variant 0: one visit of level clFirst from a zero guess, 1: one visit from the iterate in x, 2: both in a row
+    void launch_cluster(float* x, const float* b, int variant) {
+        if (clOps[variant] == 0) return;
+        const int nl = (int)levels.size();
+        ClusterParams P;
+        memset(&P, 0, sizeof(P));
+        for (int l = clFirst; l < nl; l++) {
+            ClLevel& D = P.lv[l - clFirst];
+            const ClusterHost& H = clHost[l];
+            D.v = view_of(*levels[l]);
+            D.assign = H.assign.p; D.meta = H.meta.p;
+            D.n = levels[l]->n; D.xbPer = H.xbPer; D.coefPer = H.coefPer; D.nN = H.nN; D.nC = H.nC;
+            D.xbOff = H.xbOff; D.coefOff = H.coefOff; D.metaOff = H.metaOff;
+        }
+        P.nLevels = nl - clFirst; P.nOps = clOps[variant]; P.prog = clProg[variant].p;
+        P.topX = x; P.topB = b; P.loadX = variant == 1 ? 1 : 0;
+        P.xbBytes = clXbBytes;
+        P.w = 1.2f; P.oneMinusW = 1.0f - 1.2f; P.prolongAlpha = 1.0f;
+        const CompactHost& H = compact.back();
+        P.cg = CompactDev{H.n, H.np, H.nRed, H.hasChild ? 1 : 0, 0, 0, 0, 0, 0, 0, 0, 0, H.blob.p, H.voxelOfRow.p};
+        P.cgOff = clCgOff; P.sresOff = clSresOff; P.progOff = clProgOff; P.dumpOff = clDumpOff;
+        P.cgCompat = getenv("FLIPB200_CG_COMPAT") ? atoi(getenv("FLIPB200_CG_COMPAT")) : 0;
+        static const char* tracePathEnv = getenv("FLIPB200_TRACE_CLUSTER");
+        static int traced = 0;
+        DBuf<unsigned long long> trace;
+        const bool doTrace = tracePathEnv && variant == 2 && traced++ == 8;
+        if (doTrace) { trace.alloc(5 * P.nOps + 4, w->stream); trace.zero(); P.trace = trace.p; }
+        static const int dbg = getenv("FLIPB200_CLUSTER_DBG") ? atoi(getenv("FLIPB200_CLUSTER_DBG")) : 0;
+        P.dbg = dbg;
+        uint64_t bytes = 0;
+        for (int l = clFirst; l < nl; l++) bytes += (((uint64_t)levels[l]->numDof * 121) << (l - clFirst)) * (variant == 2 ? 2 : 1);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(clSize); cfg.blockDim = dim3(CL_THREADS); cfg.dynamicSmemBytes = clSmem; cfg.stream = w->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = clSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        FB_LAUNCH(w, "mg_cluster", bytes) FB_CUDA(cudaLaunchKernelEx(&cfg, mg_cluster_kernel, P));
+        check_launch("mg_cluster");
+        if (doTrace) {
+            std::vector<unsigned long long> t(5 * P.nOps + 4);
+            FB_CUDA(cudaMemcpyAsync(t.data(), trace.p, t.size() * 8, cudaMemcpyDeviceToHost, w->stream));
+            sync(w);
+            if (FILE* f = fopen(tracePathEnv, "w")) {
+                fprintf(f, "# staging %llu ns, ops %llu ns\n", t[2 * P.nOps + 3] - t[2 * P.nOps + 2], t[P.nOps] - t[0]);
+                fprintf(f, "k,op,level,leaves,dofs,ns,work_ns,cyc_dispatch,cyc_work,cyc_barrier\n");
+                for (int k = 0; k < P.nOps; k++) {
+                    const int l = clFirst + (clHostOps[variant][k] >> 3);
+                    fprintf(f, "%d,%d,%d,%d,%d,%llu,%lld,%llu,%llu,%llu\n", k, clHostOps[variant][k] & 7, l, levels[l]->n, levels[l]->numDof, t[k + 1] - t[k],
+                            (long long)(t[P.nOps + 1 + k] - t[k]), t[2 * P.nOps + 4 + 3 * k], t[2 * P.nOps + 4 + 3 * k + 1], t[2 * P.nOps + 4 + 3 * k + 2]);
+                }
+                fclose(f);
+            }
+        }
     }
     void launch_cycle(float* x, const float* b, bool second = false) {
         const int nl = (int)levels.size();
@@ -1781,8 +1979,10 @@ struct Solver {
     }
     void mu_cycle_precond(float* x, const float* b, int level, int n, bool skipFirst) {
         if (level == 0 && dd) { dd_cycle0(x, b, n); return; }
-        if (level == 0 && n == 4 && cycleReady && (skipFirst || coarseOnly)) { launch_cycle(x, b, !skipFirst); return; }
-        if (level >= bottomFirst) { launch_bottom(x, b, n, skipFirst, true, 0); return; }
+        const bool cl = tiles && clusterReady && n == 4;
+        if (cl && level == clFirst) { launch_cluster(x, b, skipFirst ? 0 : 1); return; }
+        if (!cl && level == 0 && n == 4 && cycleReady && (skipFirst || coarseOnly)) { launch_cycle(x, b, !skipFirst); return; }
+        if (!(cl && level < clFirst) && level >= bottomFirst) { launch_bottom(x, b, n, skipFirst, true, 0); return; }
         Level& L = *levels[level];
         const float wS = 1.2f;
         if (skipFirst) {
@@ -1793,8 +1993,11 @@ struct Solver {
         for (int i = (skipFirst ? 1 : 0); i < n; i++) rbgs(L, x, b, true, wS);
         Level& P = *levels[level + 1];
         residual_restrict(L, P, x, b);
-        mu_cycle_precond(P.x.p, P.b.p, level + 1, n, true);
-        mu_cycle_precond(P.x.p, P.b.p, level + 1, n, false);
+        if (cl && level + 1 == clFirst) launch_cluster(P.x.p, P.b.p, 2);   // both visits of the cluster's top level in one launch
+        else {
+            mu_cycle_precond(P.x.p, P.b.p, level + 1, n, true);
+            mu_cycle_precond(P.x.p, P.b.p, level + 1, n, false);
+        }
         prolong(L, P, x, 1.0f);
         for (int i = 0; i < n; i++) rbgs(L, x, b, false, wS);
     }
@@ -1869,6 +2072,7 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
     S.w = w;
     S.dt = dt;
     S.dd = dd;
+    if (const char* e = getenv("FLIPB200_MG_PATH")) S.tiles = strcmp(e, "cycle") != 0;
     {
         auto Lp = std::make_unique<Level>();
         Level& L = *Lp;
