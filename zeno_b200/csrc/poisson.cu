@@ -447,6 +447,83 @@ __global__ void leaf_info_kernel(TopoView t, const uint64_t* __restrict__ dof, c
 __global__ void __launch_bounds__(256) rbgs_kernel(LevelView L, float* x, const float* __restrict__ b, int colour, float w, float oneMinusW) {
     rbgs_leaf<M_LEAF>(L, x, b, blockIdx.x, threadIdx.x, colour, w, oneMinusW);
 }
+// ---- one colour pass with a Z-ROW PER THREAD (the large levels of the tiled path)
+// rbgs_kernel spends ~100 issued instructions on one update (six neighbour index selects, 64-bit address arithmetic, one 4-byte
+// load each). Here a thread owns the row (X, Y) of its leaf: the row, its four x / y neighbour rows, b, invdiag and the
+// coefficient rows arrive as 128-bit loads and feed the row's four updates of the colour. The 64 threads of a leaf are arranged
+// so that a warp holds the rows of ONE parity of X + Y: which half of a row is being updated (P = first z) is then warp-uniform
+// and selected by a branch, not by per-element selects. Same arithmetic and association as rbgs_leaf / offdiag.
+struct Row8 { float v[8]; };
+__device__ __forceinline__ Row8 row_ld(const float* p) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    return Row8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ Row8 row_ldg(const float* p) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+    return Row8{{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w}};
+}
+__device__ __forceinline__ Row8 row_const(float c) { return Row8{{c, c, c, c, c, c, c, c}}; }
+template <int P, bool CONST_COEF>
+__device__ __forceinline__ void rbgs_row(const LevelView& L, float* x, const float* __restrict__ b, int leaf, int X, int Y, const LeafInfo& li,
+                                         float w, float oneMinusW) {
+    const int off = (X << 6) | (Y << 3);
+    const size_t base = (size_t)leaf * LEAF + off;
+    const float def = -L.term;
+    const int lxp = X < 7 ? leaf : li.nb[1], lxm = X > 0 ? leaf : li.nb[0], lyp = Y < 7 ? leaf : li.nb[3], lym = Y > 0 ? leaf : li.nb[2];
+    const int oxp = X < 7 ? off + 64 : off - 448, oxm = X > 0 ? off - 64 : off + 448, oyp = Y < 7 ? off + 8 : off - 56, oym = Y > 0 ? off - 8 : off + 56;
+    // (a missing neighbour leaf reads slot 0 and is masked afterwards: every load is issued unconditionally)
+    Row8 own = row_ld(x + base);
+    Row8 xp = row_ld(x + (size_t)max(lxp, 0) * LEAF + oxp), xm = row_ld(x + (size_t)max(lxm, 0) * LEAF + oxm);
+    Row8 yp = row_ld(x + (size_t)max(lyp, 0) * LEAF + oyp), ym = row_ld(x + (size_t)max(lym, 0) * LEAF + oym);
+    const int lz = P == 0 ? li.nb[4] : li.nb[5];
+    float zh = x[(size_t)max(lz, 0) * LEAF + off + (P == 0 ? 7 : 0)];   // the one z neighbour outside the row
+    const Row8 bb = row_ldg(b + base);
+    const uint32_t dof = (uint32_t)(__ldg(&L.info[leaf].mask[X]) >> (Y << 3)) & 0xffu;
+    Row8 inv, cxp, cxm, cyp, cym, cz;
+    float cz8 = def;
+    if (CONST_COEF) { cxp = cxm = cyp = cym = cz = row_const(def); }
+    else {
+        cxm = row_ldg(L.xe + base); cym = row_ldg(L.ye + base); cz = row_ldg(L.ze + base);
+        cxp = row_ldg(L.xe + (size_t)max(lxp, 0) * LEAF + oxp); cyp = row_ldg(L.ye + (size_t)max(lyp, 0) * LEAF + oyp);
+        if (P == 1) cz8 = __ldg(&L.ze[(size_t)max(lz, 0) * LEAF + off]);
+        if (lxp < 0) cxp = row_const(def);
+        if (lyp < 0) cyp = row_const(def);
+        if (lz < 0) cz8 = def;
+    }
+    if (li.flags & LI_DIAG) inv = row_const(__fdiv_rn(1.0f, __fmul_rn(6.0f, L.term)));
+    else inv = row_ldg(L.invdiag + base);
+    if (lxp < 0) xp = row_const(0.f);
+    if (lxm < 0) xm = row_const(0.f);
+    if (lyp < 0) yp = row_const(0.f);
+    if (lym < 0) ym = row_const(0.f);
+    if (lz < 0) zh = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int Z = 2 * k + P;
+        const float zpv = Z < 7 ? own.v[Z < 7 ? Z + 1 : 7] : zh, zmv = Z > 0 ? own.v[Z > 0 ? Z - 1 : 0] : zh;
+        const float czp = Z < 7 ? cz.v[Z < 7 ? Z + 1 : 7] : cz8, czm = cz.v[Z];
+        const float fx = __fadd_rn(__fmul_rn(xp.v[Z], cxp.v[Z]), __fmul_rn(xm.v[Z], cxm.v[Z]));
+        const float fy = __fadd_rn(__fmul_rn(yp.v[Z], cyp.v[Z]), __fmul_rn(ym.v[Z], cym.v[Z]));
+        const float fz = __fadd_rn(__fmul_rn(zpv, czp), __fmul_rn(zmv, czm));
+        const float od = __fadd_rn(__fadd_rn(fx, fy), fz);
+        const float tt = __fmul_rn(__fmul_rn(__fsub_rn(bb.v[Z], od), inv.v[Z]), w);
+        if ((dof >> Z) & 1u) x[base + Z] = __fmaf_rn(own.v[Z], oneMinusW, tt);
+    }
+}
+__global__ void __launch_bounds__(256) rbgs_rows_kernel(LevelView L, float* x, const float* __restrict__ b, int colour, float w, float oneMinusW) {
+    const int leaf = blockIdx.x * 4 + (threadIdx.x >> 6);
+    if (leaf >= L.t.n) return;
+    const LeafInfo li = load_info(L, leaf);
+    if (!(li.flags & LI_ANY)) return;
+    const int l = threadIdx.x & 31, parity = (threadIdx.x >> 5) & 1;
+    const int X = l >> 2, Y = ((l & 3) << 1) | ((X + parity) & 1);
+    const bool cc = (li.flags & LI_CONST) != 0;
+    if ((parity ^ colour) == 0) {
+        if (cc) rbgs_row<0, true>(L, x, b, leaf, X, Y, li, w, oneMinusW); else rbgs_row<0, false>(L, x, b, leaf, X, Y, li, w, oneMinusW);
+    } else {
+        if (cc) rbgs_row<1, true>(L, x, b, leaf, X, Y, li, w, oneMinusW); else rbgs_row<1, false>(L, x, b, leaf, X, Y, li, w, oneMinusW);
+    }
+}
 __global__ void __launch_bounds__(512) zero_red_kernel(LevelView L, float* __restrict__ x, const float* __restrict__ b, float w) {
     zero_red_leaf<M_LEAF>(L, x, b, blockIdx.x, threadIdx.x, w);
 }
@@ -1052,6 +1129,7 @@ struct CycleParams {
     float w, oneMinusW, prolongAlpha;
     unsigned* barrier;                // arrival counter, zero at launch
     unsigned long long* trace;        // optional: %globaltimer at the start of every op (CTA 0), nOps + 1 entries
+    int gridOnly;                     // the program holds ops of levels < compactFirst only (hybrid path): no compact staging
 };
 __device__ __forceinline__ unsigned long long globaltimer() {
     unsigned long long t;
@@ -1170,7 +1248,7 @@ __global__ void __launch_bounds__(BOT_THREADS) mg_cycle_kernel(const __grid_cons
     const int tid = threadIdx.x, G = gridDim.x, c = blockIdx.x;
     unsigned passed = 0, phase = 0;
     int k = 0;
-    if (c == 0) {   // stage the compact matrices once
+    if (c == 0 && !P.gridOnly) {   // stage the compact matrices once
         for (int l = P.compactFirst; l < P.nLevels; l++) {
             const CompactDev& D = P.cl[l];
             const BlobLayout B = blob_layout(D.np, D.hasChild != 0);
@@ -1352,6 +1430,11 @@ struct Solver {
     int clFirst = 0, clSize = 0, clCandFirst = 0;
     size_t clSmem = 0;
     int clXbBytes = 0, clCgOff = 0, clSresOff = 0, clProgOff = 0, clDumpOff = 0;
+    // hybrid: levels < clFirst as segments of the one-launch cycle kernel, the cluster kernel between them
+    bool hybridReady = false;
+    DBuf<uint8_t> hybridProg;
+    std::vector<uint8_t> hybridHost;
+    std::vector<std::pair<int, int>> hybridSeg, hybridSeg2;   // (offset, ops): visit from a zero guess / from the current iterate
     DBuf<uint8_t> clProg[3];           // one visit from a zero guess / one visit from the current iterate / both in a row
     std::vector<uint8_t> clHostOps[3];
     int clOps[3] = {0, 0, 0};
@@ -1661,6 +1744,7 @@ struct Solver {
         if (!coop || perSm < 1) return;
         cycleGrid = compactFirst == 0 ? 1 : std::min(sms, (int)cycleGridMax);
         cycleReady = true;
+        if (tiles) hybrid_prepare(n);
     }
     // ---- mg_cluster_kernel: which cluster size the part gives us (16 is the non-portable maximum)
     static int cluster_size(size_t smem) {
@@ -1723,6 +1807,37 @@ struct Solver {
         emit_cl(ops, li + 1, nb, n, false);
         put(OP_PROLONG);
         for (int i = 0; i < n; i++) { put(OP_BLACK); put(OP_RED); }
+    }
+    void emit_hybrid(std::vector<std::vector<uint8_t>>& segs, int level, int n, bool skipFirst) {
+        auto put = [&](int code) { segs.back().push_back((uint8_t)(code | (level << 3))); };
+        if (skipFirst) { put(OP_ZERO_RED); put(OP_BLACK); }
+        for (int i = (skipFirst ? 1 : 0); i < n; i++) { put(OP_RED); put(OP_BLACK); }
+        put(OP_RESID_RESTRICT);
+        if (level + 1 == clFirst) segs.emplace_back();   // both visits of level clFirst run in the cluster kernel, between two segments
+        else { emit_hybrid(segs, level + 1, n, true); emit_hybrid(segs, level + 1, n, false); }
+        put(OP_PROLONG);
+        for (int i = 0; i < n; i++) { put(OP_BLACK); put(OP_RED); }
+    }
+    void hybrid_prepare(int n) {
+        hybridReady = false;
+        if (!cycleReady || !clusterReady || clFirst <= 0 || clFirst > compactFirst) return;
+        hybridHost.clear(); hybridSeg.clear(); hybridSeg2.clear();
+        for (int v = 0; v < 2; v++) {
+            std::vector<std::vector<uint8_t>> segs(1);
+            emit_hybrid(segs, 0, n, v == 0);
+            auto& dst = v == 0 ? hybridSeg : hybridSeg2;
+            for (auto& sg : segs) { dst.emplace_back((int)hybridHost.size(), (int)sg.size()); hybridHost.insert(hybridHost.end(), sg.begin(), sg.end()); }
+        }
+        hybridProg.alloc(hybridHost.size() + 1, w->stream);
+        FB_CUDA(cudaMemcpyAsync(hybridProg.p, hybridHost.data(), hybridHost.size(), cudaMemcpyHostToDevice, w->stream));
+        hybridReady = true;
+    }
+    void launch_hybrid(float* x, const float* b, bool skipFirst) {
+        const auto& seg = skipFirst ? hybridSeg : hybridSeg2;
+        for (size_t sgi = 0; sgi < seg.size(); sgi++) {
+            if (seg[sgi].second) launch_cycle(x, b, false, hybridProg.p + seg[sgi].first, seg[sgi].second);
+            if (sgi + 1 < seg.size()) launch_cluster(levels[clFirst]->x.p, levels[clFirst]->b.p, 2);
+        }
     }
     // step 2 (after the host wait): how many levels fit, shared-memory map, op lists
     void cluster_prepare(int n) {
@@ -1844,9 +1959,9 @@ struct Solver {
             }
         }
     }
-    void launch_cycle(float* x, const float* b, bool second = false) {
+    void launch_cycle(float* x, const float* b, bool second = false, const uint8_t* segProg = nullptr, int segOps = 0) {
         const int nl = (int)levels.size();
-        if (second && cycleOps2 == 0) return;
+        if (!segProg && second && cycleOps2 == 0) return;
         CycleParams P;
         memset(&P, 0, sizeof(P));
         for (int i = 0; i < nl; i++) {
@@ -1864,6 +1979,7 @@ struct Solver {
             }
         }
         P.prog = second ? cycleProg2.p : cycleProg.p; P.nOps = second ? cycleOps2 : cycleOps; P.nLevels = nl; P.compactFirst = compactFirst;
+        if (segProg) { P.prog = segProg; P.nOps = segOps; P.gridOnly = 1; }
         P.scratchOff = scratchOff; P.cgOff = cgOff;
         P.w = 1.2f; P.oneMinusW = 1.0f - 1.2f; P.prolongAlpha = 1.0f;
         P.barrier = cycleBarrier.p;
@@ -1872,13 +1988,20 @@ struct Solver {
         const char* tracePath = tracePathEnv;
         DBuf<unsigned long long> trace;
         P.trace = nullptr;
-        if (second) tracePath = nullptr;
+        if (second || segProg) tracePath = nullptr;
         if (tracePath) { trace.alloc(cycleOps + 1, w->stream); trace.zero(); P.trace = trace.p; }
         FB_CUDA(cudaMemsetAsync(cycleBarrier.p, 0, sizeof(unsigned), w->stream));
         uint64_t bytes = 0;  // 121 B/DOF per level visit, level l is visited 2^l times
         for (int i = 0; i < nl; i++) bytes += ((uint64_t)levels[i]->numDof * 121) << i;
+        if (segProg) {   // a segment's share: the colour passes it holds, 6 B/DOF each (12 B per sweep), + 12 / 4.5 / 8.5 B for the transfers
+            bytes = 0;
+            for (int k = 0; k < segOps; k++) {
+                const int code = hybridHost[(segProg - hybridProg.p) + k] & 7, l = hybridHost[(segProg - hybridProg.p) + k] >> 3;
+                bytes += (uint64_t)levels[l]->numDof * (code == OP_RESID_RESTRICT ? 16 : (code == OP_PROLONG ? 9 : 6));
+            }
+        }
         void* args[] = {(void*)&P};
-        FB_LAUNCH(w, "mg_cycle", bytes)
+        FB_LAUNCH(w, segProg ? "mg_cycle_upper" : "mg_cycle", bytes)
             FB_CUDA(cudaLaunchCooperativeKernel((const void*)mg_cycle_kernel, dim3(cycleGrid), dim3(BOT_THREADS), args, cycleSmem, w->stream));
         check_launch("mg_cycle");
         if (tracePath) {
@@ -1936,7 +2059,8 @@ struct Solver {
     }
     void rbgs_pass(Level& L, float* x, const float* b, int colour, float wSor) {
         // one colour: read x (own + halo), b, invdiag, write half of x  -> ~14 B/DOF + coefficients
-        FB_LAUNCH(w, "mg_rbgs", (uint64_t)L.numDof * 14) rbgs_kernel<<<L.n, 256, 0, w->stream>>>(view_of(L), x, b, colour, wSor, 1.0f - wSor);
+        if (tiles) { FB_LAUNCH(w, "mg_rbgs_rows", (uint64_t)L.numDof * 14) rbgs_rows_kernel<<<(L.n + 3) / 4, 256, 0, w->stream>>>(view_of(L), x, b, colour, wSor, 1.0f - wSor); }
+        else { FB_LAUNCH(w, "mg_rbgs", (uint64_t)L.numDof * 14) rbgs_kernel<<<L.n, 256, 0, w->stream>>>(view_of(L), x, b, colour, wSor, 1.0f - wSor); }
     }
     void rbgs(Level& L, float* x, const float* b, bool redFirst, float wSor) {
         rbgs_pass(L, x, b, redFirst ? 0 : 1, wSor);
@@ -1980,6 +2104,7 @@ struct Solver {
     void mu_cycle_precond(float* x, const float* b, int level, int n, bool skipFirst) {
         if (level == 0 && dd) { dd_cycle0(x, b, n); return; }
         const bool cl = tiles && clusterReady && n == 4;
+        if (cl && level == 0 && hybridReady && !getenv("FLIPB200_NO_HYBRID")) { launch_hybrid(x, b, skipFirst); return; }
         if (cl && level == clFirst) { launch_cluster(x, b, skipFirst ? 0 : 1); return; }
         if (!cl && level == 0 && n == 4 && cycleReady && (skipFirst || coarseOnly)) { launch_cycle(x, b, !skipFirst); return; }
         if (!(cl && level < clFirst) && level >= bottomFirst) { launch_bottom(x, b, n, skipFirst, true, 0); return; }
