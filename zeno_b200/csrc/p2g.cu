@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(P2G_THREADS) p2g_gather_kernel(P2GParams p) {
     __shared__ uint32_t cBeg[PLANE_CELLS];
     __shared__ uint32_t cCnt[PLANE_CELLS];
     __shared__ int cOff[PLANE_CELLS + 1];      // smem offset of the cell in the current batch (-1: not staged)
-    __shared__ int sBatchEnd;
+    __shared__ int sBatchEnd, sBatchTotal;
 
     const int leaf = blockIdx.x;
     const int tid = threadIdx.x;
@@ -80,28 +80,30 @@ __global__ void __launch_bounds__(P2G_THREADS) p2g_gather_kernel(P2GParams p) {
                     unsigned fm = __ballot_sync(0xffffffffu, fits);
                     int nfit = fm == 0xffffffffu ? 32 : __ffs(~fm) - 1;
                     if (tid < nfit && c < PLANE_CELLS) cOff[c] = excl;
+                    if (nfit < 32) { run = __shfl_sync(0xffffffffu, excl, nfit); end = base + nfit; break; }   // run = particles of the cells that fit
                     run += __shfl_sync(0xffffffffu, incl, 31);
-                    if (nfit < 32) { end = base + nfit; break; }
                 }
                 if (end > PLANE_CELLS) end = PLANE_CELLS;
-                if (tid == 0) sBatchEnd = end;
+                if (tid == 0) { sBatchEnd = end; sBatchTotal = run; }
             }
             __syncthreads();
             const int batchEnd = sBatchEnd;
-            // stage + decode the batch's particles: one thread per cell
-            for (int c = batchStart + tid; c < batchEnd; c += P2G_THREADS) {
-                int cnt = min((int)cCnt[c], PLANE_CAP);
-                uint32_t b = cBeg[c];
-                float* dst = sP + (size_t)cOff[c] * 6;
-                for (int j = 0; j < cnt; j++) {
-                    uint32_t a0 = __ldg(&p.w0[b + j]), a1 = __ldg(&p.w1[b + j]), a2 = __ldg(&p.w2[b + j]);
-                    dst[6 * j + 0] = fx_decode(a0 & 0xffffu);
-                    dst[6 * j + 1] = fx_decode(a0 >> 16);
-                    dst[6 * j + 2] = fx_decode(a1 & 0xffffu);
-                    dst[6 * j + 3] = h_decode(a1 >> 16);
-                    dst[6 * j + 4] = h_decode(a2 & 0xffffu);
-                    dst[6 * j + 5] = h_decode(a2 >> 16);
-                }
+            const int total = sBatchTotal;
+            // stage + decode the batch's particles, one thread per staged slot (round 1 used one thread per cell with a serial loop over
+            // its particles: 100 of 192 threads busy, strided loads; ncu showed a third of all warp samples waiting at the barriers).
+            // The slot's cell is the last staged cell c with cOff[c] <= slot; consecutive threads read consecutive particles of a cell.
+            for (int sl = tid; sl < total; sl += P2G_THREADS) {
+                int lo = batchStart, hi = batchEnd;
+                while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (cOff[mid] <= sl) lo = mid; else hi = mid; }
+                const uint32_t gi = cBeg[lo] + (uint32_t)(sl - cOff[lo]);
+                const uint32_t a0 = __ldg(&p.w0[gi]), a1 = __ldg(&p.w1[gi]), a2 = __ldg(&p.w2[gi]);
+                float* dst = sP + (size_t)sl * 6;
+                dst[0] = fx_decode(a0 & 0xffffu);
+                dst[1] = fx_decode(a0 >> 16);
+                dst[2] = fx_decode(a1 & 0xffffu);
+                dst[3] = h_decode(a1 >> 16);
+                dst[4] = h_decode(a2 & 0xffffu);
+                dst[5] = h_decode(a2 >> 16);
             }
             __syncthreads();
             // accumulate: slice si handles target x = cx + 1 - si... (ox = source - target)

@@ -559,11 +559,14 @@ __device__ __forceinline__ void apply_fin(float* s, int fin, float r) {
     else { s[5] = r; s[3] = __fdiv_rn(r, s[0]); s[0] = r; }
 }
 __global__ void scalar_fin_kernel(float* s, int fin) { apply_fin(s, fin, s[6]); }
+// The per-leaf partials are already in partial[0, nPartials); the last CTA to get here folds them in index order.
+// (One arrival per CTA on ONE counter: with a CTA per leaf that was ~5800 same-address atomics, ~25 us of every
+// reduction kernel at 16.8 M particles; the kernels now stride over the leaves with a few hundred CTAs.)
 template <bool IS_MAX>
-__device__ __forceinline__ void finish_reduction(float mine, float* partial, unsigned* counter, float* s, int fin, float* sm16) {
+__device__ __forceinline__ void finish_reduction(float* partial, int nPartials, unsigned* counter, float* s, int fin, float* sm16) {
     __shared__ bool sLast;
+    __syncthreads();
     if (threadIdx.x == 0) {
-        partial[blockIdx.x] = mine;
         __threadfence();
         sLast = atomicAdd(counter, 1u) == gridDim.x - 1;
     }
@@ -571,7 +574,7 @@ __device__ __forceinline__ void finish_reduction(float mine, float* partial, uns
     if (!sLast) return;
     __threadfence();
     float a = 0.f;
-    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    for (int i = threadIdx.x; i < nPartials; i += blockDim.x) {
         float v = __ldcg(&partial[i]);
         if (IS_MAX) a = (isfinite(a) ? (isfinite(v) ? fmaxf(a, v) : v) : a);
         else a = __fadd_rn(a, v);
@@ -583,52 +586,63 @@ __device__ __forceinline__ void finish_reduction(float mine, float* partial, uns
         *counter = 0;
     }
 }
+constexpr int RED_GRID = 4 * 148;   // CTAs of the level-0 reduction kernels
 enum { MODE_LAPLACIAN = 0, MODE_RESIDUAL = 1 };
 // y = A x (+ sigma = x.y, alpha) or y = b - A x (+ nu = |y|_inf)   (uaamg.cpp:1085-1106)
 template <int MODE>
 __global__ void __launch_bounds__(512) apply_kernel(LevelView L, const float* x, const float* __restrict__ b, float* __restrict__ y,
                                                     float* partial, unsigned* counter, float* s, int defer) {
     __shared__ float sm16[16];
-    const int leaf = blockIdx.x, off = threadIdx.x;
-    const LeafInfo li = load_info(L, leaf);
-    float red = 0.f;
-    if (li.flags & LI_ANY) {  // the reference skips empty rows; vectors stay zero there
-        float out = 0.f;
-        if (dof_bit(L, leaf, off)) {
-            const size_t i = (size_t)leaf * LEAF + off;
-            float ax = ax_voxel<M_LEAF>(L, li, x, leaf, off);
-            if (MODE == MODE_RESIDUAL) { out = __fsub_rn(b[i], ax); red = out; }
-            else { out = ax; red = __fmul_rn(x[i], ax); }
+    const int off = threadIdx.x;
+    for (int leaf = blockIdx.x; leaf < L.t.n; leaf += gridDim.x) {
+        const LeafInfo li = load_info(L, leaf);
+        float red = 0.f;
+        if (li.flags & LI_ANY) {  // the reference skips empty rows; vectors stay zero there
+            float out = 0.f;
+            if (dof_bit(L, leaf, off)) {
+                const size_t i = (size_t)leaf * LEAF + off;
+                float ax = ax_voxel<M_LEAF>(L, li, x, leaf, off);
+                if (MODE == MODE_RESIDUAL) { out = __fsub_rn(b[i], ax); red = out; }
+                else { out = ax; red = __fmul_rn(x[i], ax); }
+            }
+            y[(size_t)leaf * LEAF + off] = out;
         }
-        y[(size_t)leaf * LEAF + off] = out;
+        if (!owned_leaf(L, leaf)) red = 0.f;
+        float r = MODE == MODE_RESIDUAL ? block_absmax_512(red, sm16) : block_sum_512(red, sm16);
+        if (threadIdx.x == 0) partial[leaf] = r;
+        __syncthreads();
     }
-    if (!owned_leaf(L, leaf)) red = 0.f;
-    float r = MODE == MODE_RESIDUAL ? block_absmax_512(red, sm16) : block_sum_512(red, sm16);
-    __syncthreads();
-    finish_reduction<MODE == MODE_RESIDUAL>(r, partial, counter, s, (MODE == MODE_RESIDUAL ? FIN_NU : FIN_SIGMA_ALPHA) | defer, sm16);
+    finish_reduction<MODE == MODE_RESIDUAL>(partial, L.t.n, counter, s, (MODE == MODE_RESIDUAL ? FIN_NU : FIN_SIGMA_ALPHA) | defer, sm16);
 }
 // r -= alpha z ; nu = |r|_inf (levelAlphaXPlusY + levelAbsMax, uaamg.cpp:2447-2479)
 __global__ void __launch_bounds__(512) axpy_absmax_kernel(LevelView L, float* s, const float* __restrict__ z, float* __restrict__ r,
                                                           float* partial, unsigned* counter, int defer) {
     __shared__ float sm16[16];
-    const int leaf = blockIdx.x, off = threadIdx.x;
-    const size_t i = (size_t)leaf * LEAF + off;
-    float v = 0.f;
-    if (dof_bit(L, leaf, off)) { v = __fadd_rn(r[i], __fmul_rn(-s[2], z[i])); r[i] = v; }
-    if (!owned_leaf(L, leaf)) v = 0.f;
-    float m = block_absmax_512(v, sm16);
-    __syncthreads();
-    finish_reduction<true>(m, partial, counter, s, FIN_NU | defer, sm16);
+    const int off = threadIdx.x;
+    const float alpha = s[2];
+    for (int leaf = blockIdx.x; leaf < L.t.n; leaf += gridDim.x) {
+        const size_t i = (size_t)leaf * LEAF + off;
+        float v = 0.f;
+        if (dof_bit(L, leaf, off)) { v = __fadd_rn(r[i], __fmul_rn(-alpha, z[i])); r[i] = v; }
+        if (!owned_leaf(L, leaf)) v = 0.f;
+        float m = block_absmax_512(v, sm16);
+        if (threadIdx.x == 0) partial[leaf] = m;
+        __syncthreads();
+    }
+    finish_reduction<true>(partial, L.t.n, counter, s, FIN_NU | defer, sm16);
 }
 __global__ void __launch_bounds__(512) dot_kernel(LevelView L, const float* __restrict__ a, const float* __restrict__ b, float* partial,
                                                   unsigned* counter, float* s, int fin) {
     __shared__ float sm16[16];
-    const int leaf = blockIdx.x, off = threadIdx.x;
-    const size_t i = (size_t)leaf * LEAF + off;
-    float v = (dof_bit(L, leaf, off) && owned_leaf(L, leaf)) ? __fmul_rn(a[i], b[i]) : 0.f;
-    float m = block_sum_512(v, sm16);
-    __syncthreads();
-    finish_reduction<false>(m, partial, counter, s, fin, sm16);
+    const int off = threadIdx.x;
+    for (int leaf = blockIdx.x; leaf < L.t.n; leaf += gridDim.x) {
+        const size_t i = (size_t)leaf * LEAF + off;
+        float v = (dof_bit(L, leaf, off) && owned_leaf(L, leaf)) ? __fmul_rn(a[i], b[i]) : 0.f;
+        float m = block_sum_512(v, sm16);
+        if (threadIdx.x == 0) partial[leaf] = m;
+        __syncthreads();
+    }
+    finish_reduction<false>(partial, L.t.n, counter, s, fin, sm16);
 }
 // x += alpha p ; p = z + beta p   (uaamg.cpp:2396-2397); final=1: only the x update (:2375)
 __global__ void __launch_bounds__(512) update_kernel(LevelView L, const float* __restrict__ s, float* __restrict__ x, float* __restrict__ p,
@@ -2149,22 +2163,22 @@ struct Solver {
         check_launch("scalar_fin");
     }
     void residual0(Level& L0, float* out, const float* x, const float* b) {
-        FB_LAUNCH(w, "pcg_residual", (uint64_t)L0.numDof * 16) apply_kernel<MODE_RESIDUAL><<<L0.n, 512, 0, w->stream>>>(view_of(L0), x, b, out, partial.p, counter.p, scal.p, defer());
+        FB_LAUNCH(w, "pcg_residual", (uint64_t)L0.numDof * 16) apply_kernel<MODE_RESIDUAL><<<std::min(L0.n, RED_GRID), 512, 0, w->stream>>>(view_of(L0), x, b, out, partial.p, counter.p, scal.p, defer());
         check_launch("residual");
         finish(FIN_NU, true);
     }
     void laplacian0(Level& L0, float* out, const float* x) {
-        FB_LAUNCH(w, "pcg_laplacian_dot", (uint64_t)L0.numDof * 12) apply_kernel<MODE_LAPLACIAN><<<L0.n, 512, 0, w->stream>>>(view_of(L0), x, nullptr, out, partial.p, counter.p, scal.p, defer());
+        FB_LAUNCH(w, "pcg_laplacian_dot", (uint64_t)L0.numDof * 12) apply_kernel<MODE_LAPLACIAN><<<std::min(L0.n, RED_GRID), 512, 0, w->stream>>>(view_of(L0), x, nullptr, out, partial.p, counter.p, scal.p, defer());
         check_launch("laplacian");
         finish(FIN_SIGMA_ALPHA, false);
     }
     void dot0(Level& L0, const float* a, const float* b, int fin) {
-        FB_LAUNCH(w, "pcg_dot", (uint64_t)L0.numDof * 8) dot_kernel<<<L0.n, 512, 0, w->stream>>>(view_of(L0), a, b, partial.p, counter.p, scal.p, fin | defer());
+        FB_LAUNCH(w, "pcg_dot", (uint64_t)L0.numDof * 8) dot_kernel<<<std::min(L0.n, RED_GRID), 512, 0, w->stream>>>(view_of(L0), a, b, partial.p, counter.p, scal.p, fin | defer());
         check_launch("dot");
         finish(fin, false);
     }
     void axpy_absmax0(Level& L0, const float* z, float* r) {
-        FB_LAUNCH(w, "pcg_axpy_absmax", (uint64_t)L0.numDof * 12) axpy_absmax_kernel<<<L0.n, 512, 0, w->stream>>>(view_of(L0), scal.p, z, r, partial.p, counter.p, defer());
+        FB_LAUNCH(w, "pcg_axpy_absmax", (uint64_t)L0.numDof * 12) axpy_absmax_kernel<<<std::min(L0.n, RED_GRID), 512, 0, w->stream>>>(view_of(L0), scal.p, z, r, partial.p, counter.p, defer());
         check_launch("axpy_absmax");
         finish(FIN_NU, true);
     }
