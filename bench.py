@@ -11,6 +11,10 @@ CFL_dt -> G2PAdvectorSheetty(RK3) -> FLIP_P2G -> CutCellWeight -> PushOutLiquidS
 step with the world state uploaded from / downloaded to pinned host buffers every step (`e2e`).
 Prints ONE JSON line. Inputs are synthetic (zeno_b200/scenes.py) and larger than L2 (>= 200 MB of
 particle state per step), so no L2 flush is needed between steps.
+
+    python bench.py --workload c3          # BASELINE config[2]: P2G / G2P alone, 64 M particles, 4 / 8 / 16 ppc
+    python bench.py --workload c4 [--gpus N under torchrun]   # BASELINE config[3]: MGPCG alone, 1024^3 tank, 16.8 M DOF, 1e-6
+print their own JSON line (same contract keys, workload-specific metric); the default line stays on config[1].
 """
 from __future__ import annotations
 
@@ -124,6 +128,16 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+CHAIN = ("one substep = CFL_dt + G2PAdvectorSheetty(RK3) + FLIP_P2G + CutCellWeight + PushOutLiquidSDF + FieldAddVector + "
+         "AssembleSolvePPE(5e-5) + SubtractPressureGradient")
+
+
+def workload_string(N, block, particles_per_gpu, ppc):
+    """The workload name both arms print (the driver compares the two lines' configs)."""
+    return (f"FastFLIP dam-break {N}^3 tank, water block {block[0]}x{block[1]}x{block[2]} voxels, {particles_per_gpu} particles/GPU, "
+            f"{ppc} ppc, {CHAIN}")
+
+
 def cpu_reference_arm(N: int, steps: int, warmup: int):
     """The reference's own CPU implementation of the path on the host cores, on a bounded sample of the workload:
     oracle/_ref (FLIP_vdb.cpp + simd_vdb_poisson_uaamg.cpp + OpenVDB + TBB, all hardware threads) when it was
@@ -161,6 +175,141 @@ def cpu_reference_arm(N: int, steps: int, warmup: int):
             "sample": f"dam-break {N}^3 tank, {n_particles} particles, 8 ppc, {steps} substeps of the same node chain, {what}"}
 
 
+
+def _events_ms(torch, stream, fn, reps, warm=1):
+    """CUDA-event time of `reps` calls of fn on the library's stream, after `warm` untimed calls; ms per call."""
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def workload_c3(args, torch, abi, scenes, local_rank, real_stdout):
+    """BASELINE config[2]: P2G and G2P alone, 64 M particles with a random velocity field, 4 / 8 / 16 particles per cell, one B200.
+    Algorithmic bytes as SURVEY.md 8(d): B_p2g = 12 N_p + 4 V + 28 V_a, B_g2p = 24 N_p + 28 V_a + 4 V (V_a = active band voxels)."""
+    peak, peak_src = measured_peak()
+    N = 1024
+    boxes = {4: (256, 256, 256), 8: (256, 256, 128), 16: (256, 128, 128)}     # 16.8 / 8.4 / 4.2 M voxels -> 67 M particles each
+    rows = []
+    for ppc in (4, 8, 16):
+        bx = boxes[ppc]
+        pos, vel, dx = scenes.dam_break_points(N, seed=1, ppc=ppc, random_velocity=True, box=((0, bx[0]), (0, bx[1]), (0, bx[2])))
+        vel *= np.float32(0.5)
+        w = abi.World(dx, device=local_rank)
+        w.set_grid("SolidSDF", scenes.box_solid_sdf(N, dx))
+        w.PrimToVDBPointDataGrid(pos, vel)
+        n_p = int(pos.shape[0])
+        del pos, vel
+        stream = torch.cuda.ExternalStream(w.stream(), device=torch.device("cuda", local_rank))
+        w.FLIP_P2G(dx, 3)
+        w.profile_reset(); w.profile_enable(True)
+        reps = max(2, min(args.steps, 5))
+        for _ in range(reps):
+            w.FLIP_P2G(dx, 3)
+        dtv = float(min(1.0 * w.CFL_dt(), 1.0 / 24.0))
+        for _ in range(reps):
+            w.G2PAdvectorSheetty(dtv, dx, 4, 3, 0.03, 0.05, True)
+            w.FLIP_P2G(dx, 3)      # a velocity field on the moved particles' pool for the next advection
+        w.profile_enable(False)
+        prof = w.profile_get()
+        V = bx[0] * bx[1] * bx[2]
+        va = (bx[0] + 2) * (bx[1] + 2) * (bx[2] + 2)
+        b_p2g = 12 * n_p + 4 * V + 28 * va
+        b_g2p = 24 * n_p + 28 * va + 4 * V
+        kp, kg = prof["p2g_gather"], prof["g2p_advect"]
+        p2g_ms, g2p_ms = kp["ms"] / kp["launches"], kg["ms"] / kg["launches"]
+        p2g_node = _events_ms(torch, stream, lambda: w.FLIP_P2G(dx, 3), reps)
+        rows.append({"ppc": ppc, "particles": n_p, "band_voxels": va,
+                     "p2g_gather_ms": p2g_ms, "p2g_GBps": b_p2g / (p2g_ms * 1e-3) / 1e9, "p2g_frac": b_p2g / (p2g_ms * 1e-3) / 1e9 / peak,
+                     "FLIP_P2G_node_ms": p2g_node, "p2g_particles_per_s": n_p / (p2g_node * 1e-3),
+                     "g2p_advect_ms": g2p_ms, "g2p_GBps": b_g2p / (g2p_ms * 1e-3) / 1e9, "g2p_frac": b_g2p / (g2p_ms * 1e-3) / 1e9 / peak,
+                     "g2p_particles_per_s": n_p / (g2p_ms * 1e-3)})
+        w.close()
+    r8 = [r for r in rows if r["ppc"] == 8][0]
+    line = {"metric": "P2G + G2P particle transfers/sec (64 M particles, 8 ppc)", "value": r8["particles"] / ((r8["p2g_gather_ms"] + r8["g2p_advect_ms"]) * 1e-3),
+            "unit": "particles/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r8["p2g_gather_ms"] + r8["g2p_advect_ms"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE config[2]: standalone P2G / G2P, 1024^3 tank, ~67 M particles, random velocity field, 4 / 8 / 16 ppc sweep",
+                       "l2": "inputs larger than L2 (800 MB of particle state), no flush"},
+            "roofline": {"kernel": "g2p_advect", "bound": "hbm", "achieved": r8["g2p_GBps"], "peak": peak, "unit": "GB/s", "frac": r8["g2p_frac"], "traffic": None,
+                         "peak_source": peak_src},
+            "sweep": rows}
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
+def workload_c4(args, torch, dist, abi, scenes, rank, world, local_rank, real_stdout):
+    """BASELINE config[3]: the MGPCG pressure solve alone, 1024^3 tank, a 256^3-voxel liquid block = 16.8 M pressure DOFs, relative
+    residual 1e-6 (L-inf, the solver's norm), at 1 / 2 / 4 / 8 GPUs (slabs along x). The band comes from one particle per voxel
+    (the solver only needs the liquid SDF, the face weights and a velocity field). Algorithmic bytes: 205 B per DOF and PCG
+    iteration."""
+    peak, peak_src = measured_peak()
+    N, S = 1024, 256
+    if world == 1:
+        pos, vel, dx = scenes.dam_break_points(N, seed=1, ppc=1, random_velocity=True, box=((0, S), (0, S), (0, S)))
+        w = abi.World(dx, device=local_rank)
+    else:
+        from zeno_b200 import dist_util
+        lo, hi = dist_util.slab_bounds(S // 8, world)[rank]
+        pos, vel, dx = scenes.dam_break_points(N, seed=1 + rank, ppc=1, random_velocity=True, box=((8 * lo, 8 * hi), (0, S), (0, S)))
+        w = abi.World(dx, device=local_rank)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(abi.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        w.comm_init_nccl(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        w.dd_set_slab(lo, hi)
+    vel *= np.float32(0.5)
+    w.set_grid("SolidSDF", scenes.box_solid_sdf(N, dx))
+    w.PrimToVDBPointDataGrid(pos, vel)
+    del pos, vel
+    dt = 0.004
+    w.FLIP_P2G(dx, 3)
+    w.CutCellWeight()
+    w.PushOutLiquidSDF(dx)
+    w.FieldAddVector(0.0, -9.8 * dt, 0.0)
+    stream = torch.cuda.ExternalStream(w.stream(), device=torch.device("cuda", local_rank))
+    out = {}
+    for tol in (1e-6, 5e-5):
+        res = w.AssembleSolvePPE(dt, dx, rel_tol=tol)     # warm-up (first touch of the memory pool)
+        if world > 1:
+            dist.barrier()
+        ms = _events_ms(torch, stream, lambda: w.AssembleSolvePPE(dt, dx, rel_tol=tol), max(2, min(args.steps, 5)), warm=1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        info = w.solver_info()
+        out[tol] = {"ms_per_solve": ms, "iterations": res["iterations"], "status": res["status"], "rel_residual": res["rel_residual"],
+                    "levels": info["levels"], "dofs": info["num_dof"]}
+    w.profile_reset(); w.profile_enable(True)
+    w.AssembleSolvePPE(dt, dx, rel_tol=1e-6)
+    w.profile_enable(False)
+    prof = w.profile_get()
+    top = sorted(((k, v["ms"], v["launches"]) for k, v in prof.items() if v["launches"]), key=lambda x: -x[1])[:10]
+    if rank == 0:
+        r = out[1e-6]
+        dofs, its = r["dofs"], max(r["iterations"], 1)
+        gbs = 205.0 * dofs * its / (r["ms_per_solve"] * 1e-3) / 1e9
+        line = {"metric": "MGPCG pressure DOF-iterations/sec (1024^3 tank, 16.8 M DOF, rel. residual 1e-6)", "value": dofs * its / (r["ms_per_solve"] * 1e-3),
+                "unit": "DOF-iterations/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_solve"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "BASELINE config[3]: AssembleSolvePPE alone (matrix + hierarchy set-up + MGPCG), 1024^3 tank, 256^3-voxel liquid block",
+                           "parallelism": "single GPU" if world == 1 else f"x slabs over {world} ranks, level 0 sharded, coarse levels replicated",
+                           "l2": "level-0 vectors are 67 MB each, the hierarchy > 1 GB: larger than L2"},
+                "solve_1e-6": r, "solve_5e-5": out[5e-5],
+                "roofline": {"kernel": "whole solve (set-up included)", "bound": "hbm", "achieved": gbs / world, "peak": peak, "unit": "GB/s per GPU",
+                             "frac": gbs / world / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes": "205 B per DOF per PCG iteration (SURVEY 8d)"},
+                "kernels_ms_one_solve": {k: {"ms": ms, "launches": n} for k, ms, n in top}}
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    w.close()
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -169,7 +318,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=512, help="tank resolution N (BASELINE config[1]: 512)")
     ap.add_argument("--ppc", type=int, default=8)
-    ap.add_argument("--cpu-grid", type=int, default=256, help="tank resolution of the bounded CPU sample (256 = BASELINE config[0], 2.1 M particles)")
+    ap.add_argument("--cpu-grid", type=int, default=0, help="tank resolution of the CPU arm (0 = the GPU arm's own --grid, i.e. the SAME workload)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"], help="c2 = the substep (default line); c3 / c4 = BASELINE config[2] / config[3]")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the decomposed-vs-single-world result check before the timed region")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -180,14 +331,19 @@ def main():
     metric = "FLIP particle-substeps/sec"
     unit = "particle-substeps/s"
 
+    cpu_grid = args.cpu_grid if args.cpu_grid > 0 else args.grid
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_arm(args.cpu_grid, args.steps, max(args.warmup, 1))
+        r = cpu_reference_arm(cpu_grid, args.steps, max(args.warmup, 1))
+        same = cpu_grid == args.grid and args.gpus == 1
         line = {"impl": "reference", "metric": metric, "value": r["value"], "unit": unit, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / max(args.steps, 1),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"FastFLIP dam-break substep chain on the host CPU; {r['sample']}"},
+                "config": {"workload": workload_string(cpu_grid, (cpu_grid // 4,) * 3, r["particles"], 8),
+                           "cpu_arm": r["sample"], "same_config_as_gpu_arm": same, "nproc": os.cpu_count(),
+                           "note": None if same else ("bounded sample: one GPU's share of the N-GPU tank (the 512^3 tank, 16.8 M particles) -- "
+                                                      "the metric is a per-particle rate" if args.gpus > 1 else "reduced tank")},
                 "cpu_baseline": {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -206,6 +362,22 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+
+    if args.workload == "c3":
+        if rank == 0:
+            workload_c3(args, torch, abi, scenes, local_rank, real_stdout)
+        return
+    if args.workload == "c4":
+        workload_c4(args, torch, dist if world > 1 else None, abi, scenes, rank, world, local_rank, real_stdout)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    dd_report = None
+    if world > 1 and not args.no_check:
+        # results first: the decomposed chain against ONE world on rank 0, same (small) tank, over this job's NCCL transport
+        from tests.dd_nccl_worker import run_check
+        dd_report = run_check(rank, world, local_rank, dist, box=(32, 32))
 
     N = args.grid
     if world == 1:
@@ -240,6 +412,7 @@ def main():
         parallelism = (f"slab decomposition along x over {world} ranks ({hi - lo} leaf layers each + 1 ghost layer per face), "
                        "particle migration / ghost-leaf exchange / sharded MGPCG over NCCL")
     owned_particles = (lambda: w.particles_info()[1]) if world == 1 else w.dd_owned_particles
+    n_particles0 = int(pos.shape[0])
     del pos, vel
     w.FLIP_P2G(dx, 3)
     stream = torch.cuda.ExternalStream(w.stream(), device=torch.device("cuda", local_rank))
@@ -394,16 +567,17 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_reference_arm(args.cpu_grid, 5, 1)
-        cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        r = cpu_reference_arm(cpu_grid, 3, 1)
+        cpu = {"value": r["value"], "unit": unit, "cores": r["cores"], "nproc": os.cpu_count(), "kind": r["kind"], "sample": r["sample"],
+               "same_config": cpu_grid == N and args.ppc == 8}
 
     n_particles = owned_particles()   # collective under the decomposition
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"FastFLIP dam-break {N}^3 tank, water block {block[0]}x{block[1]}x{block[2]} voxels, {n_particles} particles/GPU, {args.ppc} ppc, one substep = CFL_dt + G2PAdvectorSheetty(RK3) + FLIP_P2G + CutCellWeight + PushOutLiquidSDF + FieldAddVector + AssembleSolvePPE(5e-5) + SubtractPressureGradient",
-                           "parallelism": parallelism,
+                "config": {"workload": workload_string(N, block, n_particles0 if world == 1 else n_particles, args.ppc),
+                           "parallelism": parallelism, "dd_result_check": dd_report,
                            "l2": "inputs larger than L2 (>=200 MB particle state per step), no flush",
                            "pcg_iterations": iters, "step_ms_host": step_ms},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

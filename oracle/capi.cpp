@@ -182,6 +182,18 @@ int orc_solve_ppe(void* wp, float dt, float dx, int* iters, float* relResidual, 
     if (status) *status = w->pcgStatus;
     return 0;
 }
+// test hook: the same node with the solver's tolerance / iteration cap overridden (libflipb200's flipb200_solve_ppe_ex)
+int orc_solve_ppe_ex(void* wp, float dt, float dx, float relTol, int maxIter, int* iters, float* relResidual, int* status) {
+    World* w = static_cast<World*>(wp);
+    const float t0 = w->solveRelTol; const int m0 = w->solveMaxIter;
+    w->solveRelTol = relTol; w->solveMaxIter = maxIter;
+    node_AssembleSolvePPE(*w, dt, dx);
+    w->solveRelTol = t0; w->solveMaxIter = m0;
+    if (iters) *iters = w->pcgIterations;
+    if (relResidual) *relResidual = w->pcgRelResidual;
+    if (status) *status = w->pcgStatus;
+    return 0;
+}
 int orc_solver_info(void* wp, int* levels, int* numDof, int* nHistory) {
     World* w = static_cast<World*>(wp);
     *levels = w->mgLevels; *numDof = w->numDof; *nHistory = int(w->residualHistory.size());

@@ -33,6 +33,8 @@ struct World {
     // diagnostics
     int pcgIterations = 0;
     int pcgStatus = 0;
+    float solveRelTol = 5e-5f;   // AssembleSolvePPE: the node's mRelativeTolerance / mMaxIteration (uaamg.cpp defaults), overridable by the tests
+    int solveMaxIter = 100;
     int mgLevels = 0;
     int numDof = 0;
     float pcgRelResidual = 0.f;

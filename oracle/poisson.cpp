@@ -629,8 +629,8 @@ void node_AssembleSolvePPE(World& w, float dt, float dx) {
     buildRhs(w, L0, vel, rhs, dx);
 
     // solveMultigridPCG (uaamg.cpp:2332-2403); mRelativeTolerance 5e-5, mMaxIteration 100
-    const float relTol = 5e-5f;
-    const int maxIter = 100;
+    const float relTol = w.solveRelTol;
+    const int maxIter = w.solveMaxIter;
     int status = 1, iter = 0;
     applyOp(L0, Mode::Residual, r, pressure, &rhs, 1.2f);
     float nu = absMax(L0, r);

@@ -201,7 +201,12 @@ class OracleWorld:
 
     def AssembleSolvePPE(self, dt, dx=None, rel_tol=None, max_iter=100):
         it, res, st = C.c_int(0), C.c_float(0), C.c_int(0)
-        self.lib.orc_solve_ppe(self.h, C.c_float(dt), C.c_float(self.dx if dx is None else dx), C.byref(it), C.byref(res), C.byref(st))
+        d = C.c_float(self.dx if dx is None else dx)
+        if rel_tol is None and max_iter == 100:
+            self.lib.orc_solve_ppe(self.h, C.c_float(dt), d, C.byref(it), C.byref(res), C.byref(st))
+        else:
+            self.lib.orc_solve_ppe_ex(self.h, C.c_float(dt), d, C.c_float(5e-5 if rel_tol is None else rel_tol), C.c_int(max_iter),
+                                      C.byref(it), C.byref(res), C.byref(st))
         return {"iterations": it.value, "rel_residual": res.value, "status": st.value}
 
     def solver_info(self):

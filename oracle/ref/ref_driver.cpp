@@ -404,6 +404,65 @@ int ref_solve_ppe(void* wp, float dt, float dx, int* iters, float* relResidual, 
     if (status) *status = w->status;
     return 0;
 }
+// Test hook: the calls of FLIP_vdb::solve_pressure_simd_uaamg (FF/FLIP_vdb.cpp:3034-3100, tension off), made on the reference's own
+// solver objects, with the PCG's tolerance and iteration cap chosen by the caller -- the node hard-codes 5e-5 / 100, so its
+// pure-multigrid fallback (:3089-3097, uaamg.cpp:2405-2444) cannot be forced through the node. Everything that computes is the
+// reference's library code; only the two numbers differ.
+int ref_solve_ppe_ex(void* wp, float dt, float dx, float relTol, int maxIter, int* iters, float* relResidual, int* status) {
+    RefWorld* w = static_cast<RefWorld*>(wp);
+    if (w->flt[G_LIQUIDSDF]->tree().leafCount() == 0) return 0;
+    packed_FloatGrid3 velocity;
+    velocity.from_vec3(w->vec[G_VELOCITY]);
+    int st = 0, it = 0;
+    std::string log = captureStdout([&] {
+        auto lhs = simd_uaamg::LaplacianWithLevel::createPressurePoissonLaplacian(w->flt[G_LIQUIDSDF], w->vec[G_FACEWEIGHT], dt);
+        auto solver = simd_uaamg::PoissonSolver(lhs);
+        solver.mRelativeTolerance = relTol;
+        solver.mMaxIteration = maxIter;
+        solver.mSmoother = simd_uaamg::PoissonSolver::SmootherOption::RedBlackGaussSeidel;
+        w->flt[G_DIVERGENCE] = lhs->createPressurePoissonRightHandSide(w->vec[G_FACEWEIGHT], velocity.v[0], velocity.v[1], velocity.v[2], w->vec[G_SOLIDVEL], dt);
+        auto pressure = lhs->getZeroVectorGrid();
+        pressure->setName("Pressure");
+        auto state = solver.solveMultigridPCG(pressure, w->flt[G_DIVERGENCE]);
+        it = solver.mIterationTaken;
+        if (state != simd_uaamg::PoissonSolver::SUCCESS) {
+            st = 1;
+            FloatGrid::Ptr old = w->flt[G_PRESSURE];
+            lhs->mDofLeafManager->foreach([&](openvdb::Int32Tree::LeafNodeType& leaf, openvdb::Index) {
+                auto oldAxr{old->getConstUnsafeAccessor()};
+                auto* np = pressure->tree().probeLeaf(leaf.origin());
+                for (auto iter = np->beginValueOn(); iter; ++iter) {
+                    float v = oldAxr.getValue(iter.getCoord());
+                    if (std::isfinite(v)) iter.setValue(v);
+                }
+            });
+            solver.mMaxIteration = 100;
+            solver.solvePureMultigrid(pressure, w->flt[G_DIVERGENCE]);
+        }
+        w->flt[G_PRESSURE] = pressure;
+        w->flt[G_DIVERGENCE]->setName("RHS");
+    });
+    velocity.to_vec3(w->vec[G_VELOCITY]);
+    w->status = st; w->iterations = it;
+    // residual history: the PCG's lines, then (after "pure" would start) the pure-multigrid iteration's "iter:%d err:%e" lines
+    w->history.clear();
+    {
+        size_t pos = 0;
+        while (pos < log.size()) {
+            size_t e = log.find('\n', pos);
+            if (e == std::string::npos) e = log.size();
+            std::string line = log.substr(pos, e - pos);
+            pos = e + 1;
+            int k; float err;
+            if (sscanf(line.c_str(), "iter:%d err:%e", &k, &err) == 2) w->history.push_back(err);
+        }
+    }
+    if (iters) *iters = it;
+    if (relResidual) *relResidual = w->history.empty() ? 0.f : w->history.back();
+    if (status) *status = st;
+    (void)dx;
+    return 0;
+}
 int ref_solver_info(void* wp, int* levels, int* numDof, int* nHistory) {
     RefWorld* w = static_cast<RefWorld*>(wp);
     *levels = w->levels; *numDof = w->numDof; *nHistory = int(w->history.size());

@@ -10,19 +10,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def run_check(rank, world, local, dist, box=None):
+    """The decomposed chain on `world` ranks against ONE world on rank 0, same tank. Returns the report line on rank 0
+    (raises on a mismatch). box = voxel extents (y, z) of the water block; its x extent is 16 voxels (two leaf layers) per rank.
+    Used by tests/test_nccl_gpu.py (cube) and by bench.py --gpus N before the timed region (a thin block, a few seconds)."""
     import torch
-    import torch.distributed as dist
     from tests import util
     from tests.test_dd_gpu import DT, G, owned_part, owned_particles, merge_grids, split_points
     from zeno_b200 import abi, scenes
 
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N, side = 128, 16 * world
     bounds = [(2 * r, 2 * r + 2) for r in range(world)]
-    pos, vel, dx = scenes.dam_break_points(N, seed=3, random_velocity=True, side=side)
+    if box is None:
+        pos, vel, dx = scenes.dam_break_points(N, seed=3, random_velocity=True, side=side)
+    else:
+        pos, vel, dx = scenes.dam_break_points(max(N, side + 16), seed=3, random_velocity=True, box=((0, side), (0, box[0]), (0, box[1])))
+        N = max(N, side + 16)
     vel = vel * 0.2
     solid = scenes.box_solid_sdf(N, dx)
     uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -83,10 +86,25 @@ def main():
         assert abs(parts[0]["dt"] - one.CFL_dt()) <= 1e-5 * parts[0]["dt"]
         one.substep(DT, dx, 4, 3, 0.03, 0.05, G, 3, True)
         assert sum(p["n_after"] for p in parts) == one.particles_info()[1]
-        print(f"NCCL_DD_OK ranks={world} iterations={parts[0]['ppe']['iterations']}/{r1['iterations']} pressure_relL2={e_p:.2e} velocity_relL2={e_v:.2e} same_voxel={same:.6f}")
+        report = (f"NCCL_DD_OK ranks={world} particles={a.shape[0]} iterations={parts[0]['ppe']['iterations']}/{r1['iterations']} "
+                  f"pressure_relL2={e_p:.2e} velocity_relL2={e_v:.2e} same_voxel={same:.6f}")
         one.close()
+    else:
+        report = None
     dist.barrier()
     w.close()
+    return report
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    report = run_check(rank, world, local, dist)
+    if rank == 0:
+        print(report)
     dist.destroy_process_group()
 
 

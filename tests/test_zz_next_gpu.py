@@ -1,9 +1,9 @@
 """GPU parity of the first node beyond the substep chain: KillParticlesInSDF.
 
 The CPU side of this node is pinned in tests/test_ref_pin_cpu.py (the reference's own node class == oracle == the drop-in's node).
-This file compares the CUDA implementation with the oracle through the C ABI. It was written after the round's GPU budget was
-spent, so its first execution is the driver's round-end run: the expected-failure marker is non-strict and says so. The device
-code of these kernels has already been executed on the CPU and matches the oracle bit for bit (tests/test_next_kernels_emul_cpu.py).
+This file compares the CUDA implementation with the oracle through the C ABI (first run on a B200: the round-1 driver run, all green;
+the expected-failure markers of that first run are gone). The device code of these kernels is also executed on the CPU and matches the
+oracle bit for bit (tests/test_next_kernels_emul_cpu.py).
 """
 import numpy as np
 import pytest
@@ -13,10 +13,8 @@ from zeno_b200 import scenes
 
 pytestmark = pytest.mark.gpu
 
-FIRST_RUN = pytest.mark.xfail(strict=False, reason="written after the round-1 GPU budget was spent: the first GPU run is the driver's round-end run")
 
 
-@FIRST_RUN
 @pytest.mark.parametrize("keep", [True, False], ids=["KEEP", "DEL"])
 def test_kill_particles_in_sdf_matches_oracle(gpu_lib, oracle_lib, keep):
     from oracle.pyoracle import OracleWorld
@@ -45,7 +43,6 @@ def test_kill_particles_in_sdf_matches_oracle(gpu_lib, oracle_lib, keep):
     gw.close()
 
 
-@FIRST_RUN
 def test_particle_add_dv_matches_oracle(gpu_lib, oracle_lib):
     from oracle.pyoracle import OracleWorld
     from zeno_b200 import abi
@@ -58,7 +55,6 @@ def test_particle_add_dv_matches_oracle(gpu_lib, oracle_lib):
     gw.close()
 
 
-@FIRST_RUN
 def test_plain_g2p_advector_matches_oracle(gpu_lib, oracle_lib):
     from oracle.pyoracle import OracleWorld
     from zeno_b200 import abi
@@ -79,7 +75,6 @@ def test_plain_g2p_advector_matches_oracle(gpu_lib, oracle_lib):
     gw.close()
 
 
-@FIRST_RUN
 def test_renormalize_sdf_matches_oracle(gpu_lib, oracle_lib):
     from oracle.pyoracle import OracleWorld
     from zeno_b200 import abi
@@ -95,7 +90,6 @@ def test_renormalize_sdf_matches_oracle(gpu_lib, oracle_lib):
     gw.close()
 
 
-@FIRST_RUN
 def test_erode_sdf_matches_oracle(gpu_lib, oracle_lib):
     from oracle.pyoracle import OracleWorld
     from zeno_b200 import abi
@@ -109,7 +103,6 @@ def test_erode_sdf_matches_oracle(gpu_lib, oracle_lib):
     gw.close()
 
 
-@FIRST_RUN
 def test_smooth_sdf_matches_oracle(gpu_lib, oracle_lib):
     from oracle.pyoracle import OracleWorld
     from zeno_b200 import abi
