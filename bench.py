@@ -565,6 +565,45 @@ def main():
                "steps": E_STEPS, "ms_per_step": 1e3 * es / E_STEPS,
                "what": "per step: upload particles + Velocity/PostAdvVelocity/LiquidSDF from pinned host buffers (VDB leaf layout), CFL + the substep's nodes, download the same (asynchronous downloads overlap the nodes that follow)"}
 
+    # ---- the same step through the drop-in's NODE CLASSES on real OpenVDB objects (what a Zeno graph runs): the nodes marshal the
+    # OpenVDB leaves through pinned staging buffers, call the C ABI and rebuild the output trees. Resident mode (default): an input
+    # whose OpenVDB object is the one the device wrote last is not uploaded again; every node's outputs are written back.
+    e2e_nodes = None
+    if not args.no_e2e and world == 1 and rank == 0:
+        try:
+            from oracle import pyoracle
+            if pyoracle.plugin_gpu_available():
+                pos, vel, _ = scenes.dam_break_points(N, seed=1, ppc=args.ppc)
+                pw = pyoracle.PluginGpuWorld(dx)
+                pw.set_grid("SolidSDF", solid)
+                pw.PrimToVDBPointDataGrid(pos, vel)
+                del pos, vel
+                pw.FLIP_P2G(dx, 3)
+
+                def node_step():
+                    dt = float(min(3.0 * pw.CFL_dt(), 1.0 / 24.0))
+                    pw.G2PAdvectorSheetty(dt, dx, 4, 3, 0.03, 0.05, True)
+                    pw.FLIP_P2G(dx, 3)
+                    pw.CutCellWeight()
+                    pw.PushOutLiquidSDF(dx)
+                    pw.FieldAddVector(GRAVITY[0] * dt, GRAVITY[1] * dt, GRAVITY[2] * dt)
+                    pw.AssembleSolvePPE(dt, dx)
+                    pw.SubtractPressureGradient(dt, dx, 3)
+                node_step()
+                NS = 3
+                t0 = time.perf_counter()
+                np_steps = 0
+                for _ in range(NS):
+                    node_step()
+                    np_steps += pw.particles_info()[1]
+                tn = time.perf_counter() - t0
+                e2e_nodes = {"value": np_steps / tn, "unit": unit, "ms_per_step": 1e3 * tn / NS, "steps": NS,
+                             "what": "the substep through the drop-in's node classes (reference node names / sockets) on real OpenVDB objects: "
+                                     "per node, OpenVDB leaves -> pinned staging -> C ABI -> device, outputs written back into new OpenVDB trees"}
+                pw.close()
+        except Exception as exc:   # the harness library is test infrastructure: its absence must not fail the bench
+            e2e_nodes = {"unavailable": str(exc)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_reference_arm(cpu_grid, 3, 1)
@@ -580,7 +619,7 @@ def main():
                            "parallelism": parallelism, "dd_result_check": dd_report,
                            "l2": "inputs larger than L2 (>=200 MB particle state per step), no flush",
                            "pcg_iterations": iters, "step_ms_host": step_ms},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "e2e": e2e, "e2e_nodes": e2e_nodes, "gpu_launches": int(launches),
                 "host_syncs_per_step": host_syncs / max(args.steps, 1), "kernel_ms_sum_per_step": sum(x["ms_per_step"] for x in kern.values()),
                 "roofline": roofline, "cpu_baseline": cpu,
                 "stage_ms": {"g2p_advect_rebin": stage_ms[0], "p2g": stage_ms[1], "stencils": stage_ms[2], "mgpcg": stage_ms[3], "gradient": stage_ms[4]},

@@ -356,3 +356,30 @@ class RefNodeWorld(PluginWorld):
     def _ck(self, rc):
         if rc != 0:
             raise RuntimeError("reference node failed: " + (self.lib.orc_last_error() or b"").decode())
+
+
+_PLUGIN_GPU_LIB = os.path.join(_HERE, "_ref", "libflipplugin_gpu.so")
+_plugin_gpu = None
+
+
+def plugin_gpu_available() -> bool:
+    return os.path.exists(_PLUGIN_GPU_LIB)
+
+
+class PluginGpuWorld(PluginWorld):
+    """The drop-in's NODE CLASSES on real OpenVDB objects with the PRODUCT behind them: oracle/_ref/libflipplugin_gpu.so
+    (oracle/ref/plugin_nodes_gpu.cpp, prefix pg_) links zeno_b200/libflipb200.so. Needs a B200."""
+    PREFIX = "pg_"
+
+    @classmethod
+    def _load(cls):
+        global _plugin_gpu
+        if _plugin_gpu is None:
+            load_ref()   # libflipref.so first: the harness takes its RefWorld helpers from it
+            lib = C.CDLL(_PLUGIN_GPU_LIB)
+            lib.pg_world_create.restype = C.c_void_p
+            lib.pg_cfl.restype = C.c_float
+            lib.pg_dropped.restype = C.c_uint64
+            lib.pg_last_error.restype = C.c_char_p
+            _plugin_gpu = lib
+        return _plugin_gpu

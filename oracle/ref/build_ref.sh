@@ -24,7 +24,7 @@ VDB="$REF/projects/zenvdb/openvdb/openvdb"
 FF="$REF/projects/FastFLIP"
 [ -d "$REF" ] || { echo "no $REF: keeping the prebuilt oracle/_ref"; exit 0; }
 PLUGIN_SRC="$HERE/../../zeno_b200/plugin/flipb200_nodes.cpp"
-if [ -f "$OUT/libflipref.so" ] && [ "$OUT/libflipref.so" -nt "$HERE/ref_driver.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/shims/Eigen/Eigen" ] && [ "$OUT/libflipref.so" -nt "$PLUGIN_SRC" ] && [ "$OUT/libflipref.so" -nt "$HERE/plugin_nodes_test.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/ref_nodes_test.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/node_harness.inc" ] && [ -z "$FORCE" ]; then
+if [ -f "$OUT/libflipref.so" ] && [ "$OUT/libflipref.so" -nt "$HERE/ref_driver.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/shims/Eigen/Eigen" ] && [ "$OUT/libflipref.so" -nt "$PLUGIN_SRC" ] && [ "$OUT/libflipref.so" -nt "$HERE/plugin_nodes_test.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/ref_nodes_test.cpp" ] && [ "$OUT/libflipref.so" -nt "$HERE/node_harness.inc" ] && [ -f "$OUT/libflipplugin_gpu.so" ] && [ "$OUT/libflipplugin_gpu.so" -nt "$HERE/plugin_nodes_gpu.cpp" ] && [ "$OUT/libflipplugin_gpu.so" -nt "$PLUGIN_SRC" ] && [ -z "$FORCE" ]; then
   echo "oracle/_ref/libflipref.so is up to date"; exit 0
 fi
 mkdir -p "$OUT" "$BUILD/gen/openvdb" "$BUILD/vdbobj" "$BUILD/ffobj"
@@ -86,6 +86,16 @@ xargs -P "$JOBS" -d '\n' -I{} bash -c {} < "$BUILD/cmds.txt" || { echo "FastFLIP
 cp "$BUILD/libtbb.so.2" "$OUT/libtbb.so.2"
 $CXX -shared -o "$OUT/libflipref.so" "$BUILD"/ffobj/*.o "$BUILD"/vdbobj/*.o -L"$BUILD" -ltbb -lpthread -ldl -Wl,-rpath,'$ORIGIN' -Wl,-z,defs 2> "$BUILD/link.log" || { head -40 "$BUILD/link.log"; exit 1; }
 echo "built $OUT/libflipref.so"
+
+# ---- 5b. the drop-in's node classes against the PRODUCT (libflipb200.so): oracle/_ref/libflipplugin_gpu.so
+LIBB200="$HERE/../../zeno_b200/libflipb200.so"
+if [ -f "$LIBB200" ]; then
+  $CXX $NODEFLAGS -fvisibility=hidden -fvisibility-inlines-hidden -c "$HERE/plugin_nodes_gpu.cpp" -o "$BUILD/plugin_nodes_gpu.o" 2> "$BUILD/plugin_nodes_gpu.log" \
+      || { grep -m 30 -E 'error|Error' "$BUILD/plugin_nodes_gpu.log"; exit 1; }
+  $CXX -shared -o "$OUT/libflipplugin_gpu.so" "$BUILD/plugin_nodes_gpu.o" -L"$OUT" -lflipref -L"$(dirname "$LIBB200")" -lflipb200 -L"$BUILD" -ltbb -lpthread -ldl \
+      -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../zeno_b200' 2> "$BUILD/link_gpu.log" || { head -40 "$BUILD/link_gpu.log"; exit 1; }
+  echo "built $OUT/libflipplugin_gpu.so"
+fi
 
 # ---- 6. compile check of the Zeno-side drop-in (zeno_b200/plugin/flipb200_nodes.cpp) against the reference's own
 #         headers (zeno core, zenvdb VDBGrid.h, OpenVDB): it is built into the zeno target, so here only -fsyntax-only

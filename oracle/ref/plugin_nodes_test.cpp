@@ -31,6 +31,11 @@
 #define flipb200_renormalize_sdf ob_renormalize_sdf
 #define flipb200_erode_sdf ob_erode_sdf
 #define flipb200_smooth_sdf ob_smooth_sdf
+#define flipb200_host_alloc ob_host_alloc
+#define flipb200_host_free ob_host_free
+#define flipb200_grid_download_begin ob_grid_download_begin
+#define flipb200_particles_download_begin ob_particles_download_begin
+#define flipb200_download_wait ob_download_wait
 #include <tbb/parallel_for.h>
 #include "../../zeno_b200/plugin/flipb200_nodes.cpp"
 
@@ -106,11 +111,25 @@ int ob_grid_download(flipb200_world* w, int grid, int32_t* o, uint64_t* m, float
     }
     return g_orc.grid_get(w->orc, grid, o, m, v, bg);
 }
+int ob_host_alloc(size_t bytes, void** out) { *out = std::malloc(bytes); return *out ? 0 : FLIPB200_ERR_CUDA; }
+int ob_host_free(void* p) { std::free(p); return 0; }
+int ob_download_wait(flipb200_world*) { return 0; }
+int ob_grid_download_begin(flipb200_world* w, int grid, int cap, int32_t* o, uint64_t* m, float* v, int layout, float* bg, int* n) {
+    *n = g_orc.grid_leaf_count(w->orc, grid);
+    if (*n < 0 || *n > cap) { g_err = "grid_download_begin: capacity"; return FLIPB200_ERR_ARG; }
+    return ob_grid_download(w, grid, o, m, v, layout, bg);
+}
 int ob_particles_upload(flipb200_world* w, int nl, const int32_t* o, const uint32_t* ve, uint64_t np, const uint16_t* P, const uint16_t* V) {
     return g_orc.particles_set(w->orc, nl, o, ve, np, P, V);
 }
 int ob_particles_info(flipb200_world* w, int* nl, uint64_t* np) { return g_orc.particles_info(w->orc, nl, np); }
 int ob_particles_download(flipb200_world* w, int32_t* o, uint32_t* ve, uint16_t* P, uint16_t* V) { return g_orc.particles_get(w->orc, o, ve, P, V); }
+int ob_particles_download_begin(flipb200_world* w, int capLeaves, uint64_t capParticles, int32_t* o, uint32_t* ve, uint16_t* P, uint16_t* V, int* nl, uint64_t* np) {
+    int rc = g_orc.particles_info(w->orc, nl, np);
+    if (rc) return rc;
+    if (*nl > capLeaves || *np > capParticles) { g_err = "particles_download_begin: capacity"; return FLIPB200_ERR_ARG; }
+    return g_orc.particles_get(w->orc, o, ve, P, V);
+}
 int ob_p2g(flipb200_world* w, float dx, int n) { return g_orc.p2g(w->orc, dx, n); }
 int ob_g2p_advect_sheetty(flipb200_world* w, float dt, float dx, int ss, int rk, float pmin, float pmax, int flags) {
     return g_orc.g2p(w->orc, dt, dx, ss, rk, pmin, pmax, flags);

@@ -536,6 +536,11 @@ int ref_substep(void* wp, float dt, float dx, int surfaceSize, int rkOrder, floa
 #define flipb200_particles_upload lb_particles_upload
 #define flipb200_particles_info lb_particles_info
 #define flipb200_particles_download lb_particles_download
+#define flipb200_host_alloc lb_host_alloc
+#define flipb200_host_free lb_host_free
+#define flipb200_grid_download_begin lb_grid_download_begin
+#define flipb200_particles_download_begin lb_particles_download_begin
+#define flipb200_download_wait lb_download_wait
 #include <map>
 // (the plugin's namespace zeno::flipb200 is renamed in this translation unit: plugin_nodes_test.cpp compiles the same
 // inline functions against a different ABI, and the two sets must not be merged by the linker)
@@ -599,6 +604,22 @@ int lb_particles_download(flipb200_world* w, int32_t* o, uint32_t* ve, uint16_t*
         at += cnt;
     }
     return 0;
+}
+}  // extern "C"
+
+extern "C" {
+int lb_host_alloc(size_t bytes, void** out) { *out = std::malloc(bytes); return *out ? 0 : 2; }
+int lb_host_free(void* p) { std::free(p); return 0; }
+int lb_download_wait(flipb200_world*) { return 0; }
+int lb_grid_download_begin(flipb200_world* w, int grid, int cap, int32_t* o, uint64_t* m, float* v, int layout, float* bg, int* n) {
+    *n = w->grids[grid].n;
+    if (*n > cap) return 1;
+    return lb_grid_download(w, grid, o, m, v, layout, bg);
+}
+int lb_particles_download_begin(flipb200_world* w, int capLeaves, uint64_t capParticles, int32_t* o, uint32_t* ve, uint16_t* P, uint16_t* V, int* nl, uint64_t* np) {
+    *nl = w->nl; *np = w->np;
+    if (*nl > capLeaves || *np > capParticles) return 1;
+    return lb_particles_download(w, o, ve, P, V);
 }
 }  // extern "C"
 

@@ -10,12 +10,19 @@
 //           nosys/EvalFaceWeight.cpp (CutCellWeight), nosys/FixLiquidSDF.cpp (PushOutLiquidSDF),
 //           nosys/FieldAddVector.cpp, nosys/CFL.cpp (CFL_dt; SurfaceTension_dt is host arithmetic and is kept).
 //
-// State model: one device world per voxel size, created on first use (SetFLIPWorld only creates host objects
-// and stays untouched). Every node uploads the socket grids it READS, runs, and downloads the grids it WRITES, so
-// un-accelerated nodes in between (VDBRenormalizeSDF, viewport, IO) always see current OpenVDB objects -- the
-// conservative mode whose cost bench.py reports as `e2e`. Setting FLIPB200_RESIDENT=1 keeps grids on the device
-// between accelerated nodes: an object is uploaded only when its tree pointer or leaf count changed since we
-// last wrote it, and a node's outputs are still written back (the substep chain itself then never re-uploads).
+// State model: one device world per FLIP world of the graph. A node finds its world through the socket OBJECTS it is handed
+// (the IObject wrappers SetFLIPWorld created: they are stable for the life of the graph, and two FLIP worlds with the same
+// voxel size have different objects); the first node that sees a set of objects creates the device world and registers them.
+// Marshalling goes through page-locked staging buffers owned by the world (flipb200_host_alloc, grown on demand) and the
+// asynchronous download calls (flipb200_*_download_begin / flipb200_download_wait): all outputs of a node cross PCIe
+// concurrently. RESIDENT mode is the default: a socket grid is uploaded only if its OpenVDB object is not the one this world
+// last wrote or read -- decided by a fingerprint (tree address, leaf count, active-voxel count and a hash of the value
+// buffers of up to 64 evenly spaced leaves), so a whole-grid edit by an un-accelerated node in between (VDBRenormalizeSDF,
+// CombineVDB, ...) is seen; FLIPB200_RESIDENT=0 uploads every input of every node (for graphs that edit single voxels of a
+// world grid in place between two accelerated nodes). Every node still writes its outputs back, so un-accelerated nodes,
+// the viewport and IO always see current OpenVDB objects.
+// Grids with non-background TILES (a flood-filled level set carries -background tiles inside) are refused with a clear
+// error: the device grids are leaf-only, and sampling such a grid as "background outside the leaves" would be wrong.
 // FLIPB200_PLUGIN_MARSHAL_ONLY: only the OpenVDB <-> flat-array marshalling below is compiled (no Zeno headers, no
 // node registration). oracle/ref/ref_driver.cpp includes this file that way to round-trip REAL reference grids and
 // particle trees through upload()/download() against a loopback C ABI (tests/test_plugin_cpu.py).
@@ -33,10 +40,14 @@
 #include <openvdb/openvdb.h>
 #include <openvdb/points/PointDataGrid.h>
 #include <openvdb/points/AttributeArray.h>
+#ifndef FLIPB200_PLUGIN_MARSHAL_ONLY
+#include <openvdb/tools/LevelSetTracker.h>
+#endif
 
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <initializer_list>
 #include <mutex>
 #include <vector>
 
@@ -69,48 +80,115 @@ inline void check(int rc, const char* what) {
 #endif
 }
 
+// a page-locked buffer that only grows
+struct Pinned {
+    void* p = nullptr;
+    size_t cap = 0;
+    Pinned() {}
+    Pinned(const Pinned&) = delete;
+    Pinned& operator=(const Pinned&) = delete;
+    ~Pinned() { if (p) flipb200_host_free(p); }
+    template <typename T> T* need(size_t count) {
+        const size_t bytes = count * sizeof(T);
+        if (bytes > cap) {
+            if (p) flipb200_host_free(p);
+            p = nullptr; cap = 0;
+            const size_t c = bytes + bytes / 4 + 4096;
+            check(flipb200_host_alloc(c, &p), "host_alloc");
+            cap = c;
+        }
+        return static_cast<T*>(p);
+    }
+};
+struct Fingerprint {
+    const void* tree = nullptr;
+    size_t leaves = 0;
+    uint64_t active = 0, hash = 0;
+    bool valid = false;
+    bool operator==(const Fingerprint& o) const { return valid && o.valid && tree == o.tree && leaves == o.leaves && active == o.active && hash == o.hash; }
+};
+inline uint64_t fnv(uint64_t h, const void* data, size_t bytes) {
+    const uint64_t* q = static_cast<const uint64_t*>(data);
+    for (size_t i = 0; i < bytes / 8; i++) { h ^= q[i]; h *= 0x100000001b3ull; }
+    return h;
+}
 struct WorldHolder {
     flipb200_world* w = nullptr;
     float dx = 0.f;
-    // resident mode bookkeeping: last tree we uploaded/downloaded per grid id
-    const void* lastTree[FLIPB200_NUM_GRIDS + 1] = {};
-    size_t lastLeaves[FLIPB200_NUM_GRIDS + 1] = {};
+    struct Stage { Pinned o, m, v; int n = 0; float bg[3] = {0.f, 0.f, 0.f}; } stage[FLIPB200_NUM_GRIDS];
+    Pinned po, pve, pP, pV;                       // particle staging
+    int pnl = 0; uint64_t pnp = 0;
+    Fingerprint fp[FLIPB200_NUM_GRIDS + 1];       // what the device copy of each slot corresponds to (last slot: particles)
     ~WorldHolder() { if (w) flipb200_world_destroy(w); }
 };
-inline bool resident() { static const bool r = std::getenv("FLIPB200_RESIDENT") != nullptr; return r; }
+inline bool resident() { static const bool r = !(std::getenv("FLIPB200_RESIDENT") && std::atoi(std::getenv("FLIPB200_RESIDENT")) == 0); return r; }
 
-// one world per voxel size (a scene has one FLIP world; sub-steps reuse it)
-inline WorldHolder& world_for(float dx) {
+// the device world of the FLIP world these socket objects belong to
+inline WorldHolder& world_for(float dx, std::initializer_list<const void*> objects) {
     static std::mutex mtx;
-    static std::map<float, std::unique_ptr<WorldHolder>> worlds;
+    static std::map<const void*, WorldHolder*> byObject;
+    static std::vector<std::unique_ptr<WorldHolder>> worlds;
     std::lock_guard<std::mutex> lock(mtx);
-    auto& slot = worlds[dx];
-    if (!slot) {
-        slot = std::make_unique<WorldHolder>();
-        slot->dx = dx;
-        check(flipb200_world_create(/*device*/ 0, dx, &slot->w), "SetFLIPWorld");
+    WorldHolder* h = nullptr;
+    for (const void* o : objects) {
+        auto it = o ? byObject.find(o) : byObject.end();
+        if (it != byObject.end() && it->second->dx == dx) { h = it->second; break; }
     }
-    return *slot;
+    if (!h) {
+        worlds.push_back(std::make_unique<WorldHolder>());
+        h = worlds.back().get();
+        h->dx = dx;
+        check(flipb200_world_create(/*device*/ 0, dx, &h->w), "SetFLIPWorld");
+    }
+    for (const void* o : objects) if (o) byObject[o] = h;
+    return *h;
 }
 
 // ---------------------------------------------------------------- leaves <-> flat arrays
 template <typename GridT> struct Channels { static constexpr int n = 1; };
 template <> struct Channels<openvdb::Vec3fGrid> { static constexpr int n = 3; };
 
+template <typename TreeT>
+bool has_foreign_tiles(const TreeT& t) {
+    using Root = typename TreeT::RootNodeType;
+    const auto bg = t.background();
+    for (auto it = t.root().cbeginValueAll(); it; ++it) if (!(*it == bg)) return true;
+    for (auto c2 = t.root().cbeginChildOn(); c2; ++c2) {
+        for (auto v = c2->cbeginValueAll(); v; ++v) if (!(*v == bg)) return true;
+        for (auto c1 = c2->cbeginChildOn(); c1; ++c1)
+            for (auto v = c1->cbeginValueAll(); v; ++v) if (!(*v == bg)) return true;
+    }
+    (void)sizeof(Root);
+    return false;
+}
+template <typename GridT, typename LeafT>
+Fingerprint fingerprint(const GridT& g, const std::vector<const LeafT*>& leaves) {
+    Fingerprint f;
+    f.tree = &g.tree(); f.leaves = leaves.size(); f.active = g.tree().activeVoxelCount();
+    uint64_t h = 0xcbf29ce484222325ull;
+    const size_t n = leaves.size(), step = n > 64 ? n / 64 : 1;
+    for (size_t i = 0; i < n; i += step) h = fnv(h, leaves[i]->buffer().data(), sizeof(typename GridT::ValueType) * 512);
+    f.hash = h; f.valid = true;
+    return f;
+}
+
 template <typename GridT>
 void upload(WorldHolder& h, int id, const typename GridT::Ptr& g) {
     if (!g) return;
     using Leaf = typename GridT::TreeType::LeafNodeType;
     constexpr int C = Channels<GridT>::n;
-    const void* treeKey = &g->tree();
-    const size_t nLeaves = g->tree().leafCount();
-    if (resident() && h.lastTree[id] == treeKey && h.lastLeaves[id] == nLeaves) return;  // still what we wrote
     std::vector<const Leaf*> leaves;
     g->tree().getNodes(leaves);
+    const Fingerprint now = fingerprint<GridT, Leaf>(*g, leaves);
+    if (resident() && h.fp[id] == now) return;   // the device copy is this object
+    if (has_foreign_tiles(g->tree()))
+        check(FLIPB200_ERR_ARG, "grid upload: the grid has tiles that differ from its background (e.g. a flood-filled level set); "
+                                "voxelize its narrow band / interior first -- the device grids are leaf-only");
     const size_t n = leaves.size();
-    std::vector<int32_t> o(3 * n);
-    std::vector<uint64_t> m(8 * n);
-    std::vector<float> v(size_t(512) * C * n);
+    WorldHolder::Stage& st = h.stage[id];
+    int32_t* o = st.o.need<int32_t>(3 * n + 1);
+    uint64_t* m = st.m.need<uint64_t>(8 * n + 1);
+    float* v = st.v.need<float>(size_t(512) * C * n + 1);
     tbb::parallel_for(size_t(0), n, [&](size_t i) {
         const auto c = leaves[i]->origin();
         o[3 * i] = c.x(); o[3 * i + 1] = c.y(); o[3 * i + 2] = c.z();
@@ -120,26 +198,37 @@ void upload(WorldHolder& h, int id, const typename GridT::Ptr& g) {
     float bg[3] = {0.f, 0.f, 0.f};
     if constexpr (C == 3) { bg[0] = g->background()[0]; bg[1] = g->background()[1]; bg[2] = g->background()[2]; }
     else bg[0] = g->background();
-    check(flipb200_grid_upload(h.w, id, int(n), o.data(), m.data(), v.data(), C == 3 ? FLIPB200_AOS : FLIPB200_SOA, bg), "grid_upload");
-    h.lastTree[id] = treeKey; h.lastLeaves[id] = nLeaves;
+    check(flipb200_grid_upload(h.w, id, int(n), o, m, v, C == 3 ? FLIPB200_AOS : FLIPB200_SOA, bg), "grid_upload");
+    h.fp[id] = now;
 }
 
-// the reference nodes replace trees (FF/FLIP_vdb.cpp:1302,3087,3488); so does the write-back
+// write-back, part 1: the device stages the grid and the copies start (second stream); nothing is valid before download_wait
 template <typename GridT>
-void download(WorldHolder& h, int id, typename GridT::Ptr& g) {
-    using Tree = typename GridT::TreeType;
+void download_begin(WorldHolder& h, int id) {
     constexpr int C = Channels<GridT>::n;
     int n = 0;
     check(flipb200_grid_leaf_count(h.w, id, &n), "grid_leaf_count");
-    std::vector<int32_t> o(3 * size_t(n));
-    std::vector<uint64_t> m(8 * size_t(n));
-    std::vector<float> v(size_t(512) * C * n);
-    float bg[3] = {0.f, 0.f, 0.f};
-    check(flipb200_grid_download(h.w, id, o.data(), m.data(), v.data(), C == 3 ? FLIPB200_AOS : FLIPB200_SOA, bg), "grid_download");
+    WorldHolder::Stage& st = h.stage[id];
+    int32_t* o = st.o.need<int32_t>(3 * size_t(n) + 1);
+    uint64_t* m = st.m.need<uint64_t>(8 * size_t(n) + 1);
+    float* v = st.v.need<float>(size_t(512) * C * n + 1);
+    check(flipb200_grid_download_begin(h.w, id, n, o, m, v, C == 3 ? FLIPB200_AOS : FLIPB200_SOA, st.bg, &st.n), "grid_download_begin");
+}
+// part 2 (after flipb200_download_wait): the reference nodes replace trees (FF/FLIP_vdb.cpp:1302,3087,3488); so does the write-back
+template <typename GridT>
+void download_finish(WorldHolder& h, int id, typename GridT::Ptr& g) {
+    using Tree = typename GridT::TreeType;
+    using Leaf = typename Tree::LeafNodeType;
+    constexpr int C = Channels<GridT>::n;
+    WorldHolder::Stage& st = h.stage[id];
+    const int n = st.n;
+    const int32_t* o = static_cast<const int32_t*>(st.o.p);
+    const uint64_t* m = static_cast<const uint64_t*>(st.m.p);
+    const float* v = static_cast<const float*>(st.v.p);
     typename Tree::Ptr tree;
-    if constexpr (C == 3) tree = std::make_shared<Tree>(openvdb::Vec3f(bg[0], bg[1], bg[2]));
-    else tree = std::make_shared<Tree>(bg[0]);
-    std::vector<typename Tree::LeafNodeType*> leaves(n);
+    if constexpr (C == 3) tree = std::make_shared<Tree>(openvdb::Vec3f(st.bg[0], st.bg[1], st.bg[2]));
+    else tree = std::make_shared<Tree>(st.bg[0]);
+    std::vector<Leaf*> leaves(n);
     for (int i = 0; i < n; i++) leaves[i] = tree->touchLeaf(openvdb::Coord(o[3 * i], o[3 * i + 1], o[3 * i + 2]));  // serial: tree insertion
     tbb::parallel_for(0, n, [&](int i) {
         Mask mask;
@@ -148,22 +237,48 @@ void download(WorldHolder& h, int id, typename GridT::Ptr& g) {
         leaves[i]->setValueMask(mask);
     });
     g->setTree(tree);
-    h.lastTree[id] = &g->tree(); h.lastLeaves[id] = g->tree().leafCount();
+    std::vector<const Leaf*> cl;
+    g->tree().getNodes(cl);
+    h.fp[id] = fingerprint<GridT, Leaf>(*g, cl);
+}
+inline void download_wait(WorldHolder& h) { check(flipb200_download_wait(h.w), "download_wait"); }
+template <typename GridT>
+void download(WorldHolder& h, int id, typename GridT::Ptr& g) {
+    download_begin<GridT>(h, id);
+    download_wait(h);
+    download_finish<GridT>(h, id, g);
 }
 
+inline Fingerprint fingerprint_particles(const openvdb::points::PointDataGrid& g, const std::vector<const openvdb::points::PointDataTree::LeafNodeType*>& leaves) {
+    Fingerprint f;
+    f.tree = &g.tree(); f.leaves = leaves.size(); f.active = g.tree().activeVoxelCount();
+    uint64_t h = 0xcbf29ce484222325ull;
+    const size_t n = leaves.size(), step = n > 64 ? n / 64 : 1;
+    for (size_t i = 0; i < n; i += step) {
+        const auto cnt = leaves[i]->getLastValue();
+        h ^= cnt; h *= 0x100000001b3ull;
+        if (!cnt) continue;
+        for (const char* a : {"P", "v"}) {
+            const auto& arr = leaves[i]->constAttributeArray(a);
+            h = fnv(h, TestAttributeArray::bytes(arr), arr.isUniform() ? 0 : size_t(cnt) * 6);
+        }
+    }
+    f.hash = h; f.valid = true;
+    return f;
+}
 inline void upload_particles(WorldHolder& h, const openvdb::points::PointDataGrid::Ptr& g) {
     using Leaf = openvdb::points::PointDataTree::LeafNodeType;
-    const void* treeKey = &g->tree();
-    const size_t nLeaves = g->tree().leafCount();
-    if (resident() && h.lastTree[FLIPB200_NUM_GRIDS] == treeKey && h.lastLeaves[FLIPB200_NUM_GRIDS] == nLeaves) return;
     std::vector<const Leaf*> leaves;
     g->tree().getNodes(leaves);
+    const Fingerprint now = fingerprint_particles(*g, leaves);
+    if (resident() && h.fp[FLIPB200_NUM_GRIDS] == now) return;
     const size_t n = leaves.size();
-    std::vector<int32_t> o(3 * n);
-    std::vector<uint32_t> ve(512 * n);
     std::vector<uint64_t> begin(n + 1, 0);
     for (size_t i = 0; i < n; i++) begin[i + 1] = begin[i] + leaves[i]->getLastValue();
-    std::vector<uint16_t> P(3 * begin[n]), V(3 * begin[n]);
+    int32_t* o = h.po.need<int32_t>(3 * n + 1);
+    uint32_t* ve = h.pve.need<uint32_t>(512 * n + 1);
+    uint16_t* P = h.pP.need<uint16_t>(3 * begin[n] + 4);
+    uint16_t* V = h.pV.need<uint16_t>(3 * begin[n] + 4);
     tbb::parallel_for(size_t(0), n, [&](size_t i) {
         const auto c = leaves[i]->origin();
         o[3 * i] = c.x(); o[3 * i + 1] = c.y(); o[3 * i + 2] = c.z();
@@ -174,24 +289,31 @@ inline void upload_particles(WorldHolder& h, const openvdb::points::PointDataGri
         const auto& va = leaves[i]->constAttributeArray("v");
         const uint16_t* ps = reinterpret_cast<const uint16_t*>(TestAttributeArray::bytes(pa));
         const uint16_t* vs = reinterpret_cast<const uint16_t*>(TestAttributeArray::bytes(va));
-        for (uint32_t j = 0; j < cnt; j++)
-            for (int a = 0; a < 3; a++) {
-                P[3 * (begin[i] + j) + a] = ps[pa.isUniform() ? a : 3 * j + a];
-                V[3 * (begin[i] + j) + a] = vs[va.isUniform() ? a : 3 * j + a];
-            }
+        if (!pa.isUniform()) std::memcpy(&P[3 * begin[i]], ps, size_t(cnt) * 6);
+        else for (uint32_t j = 0; j < cnt; j++) for (int a = 0; a < 3; a++) P[3 * (begin[i] + j) + a] = ps[a];
+        if (!va.isUniform()) std::memcpy(&V[3 * begin[i]], vs, size_t(cnt) * 6);
+        else for (uint32_t j = 0; j < cnt; j++) for (int a = 0; a < 3; a++) V[3 * (begin[i] + j) + a] = vs[a];
     });
-    check(flipb200_particles_upload(h.w, int(n), o.data(), ve.data(), begin[n], P.data(), V.data()), "particles_upload");
-    h.lastTree[FLIPB200_NUM_GRIDS] = treeKey; h.lastLeaves[FLIPB200_NUM_GRIDS] = nLeaves;
+    check(flipb200_particles_upload(h.w, int(n), o, ve, begin[n], P, V), "particles_upload");
+    h.fp[FLIPB200_NUM_GRIDS] = now;
 }
 
-inline void download_particles(WorldHolder& h, openvdb::points::PointDataGrid::Ptr& g) {
+inline void download_particles_begin(WorldHolder& h) {
     int nl = 0;
     uint64_t np = 0;
     check(flipb200_particles_info(h.w, &nl, &np), "particles_info");
-    std::vector<int32_t> o(3 * size_t(nl));
-    std::vector<uint32_t> ve(512 * size_t(nl));
-    std::vector<uint16_t> P(3 * np), V(3 * np);
-    check(flipb200_particles_download(h.w, o.data(), ve.data(), P.data(), V.data()), "particles_download");
+    int32_t* o = h.po.need<int32_t>(3 * size_t(nl) + 1);
+    uint32_t* ve = h.pve.need<uint32_t>(512 * size_t(nl) + 1);
+    uint16_t* P = h.pP.need<uint16_t>(3 * np + 4);
+    uint16_t* V = h.pV.need<uint16_t>(3 * np + 4);
+    check(flipb200_particles_download_begin(h.w, nl, np, o, ve, P, V, &h.pnl, &h.pnp), "particles_download_begin");
+}
+inline void download_particles_finish(WorldHolder& h, openvdb::points::PointDataGrid::Ptr& g) {
+    const int nl = h.pnl;
+    const int32_t* o = static_cast<const int32_t*>(h.po.p);
+    const uint32_t* ve = static_cast<const uint32_t*>(h.pve.p);
+    const uint16_t* P = static_cast<const uint16_t*>(h.pP.p);
+    const uint16_t* V = static_cast<const uint16_t*>(h.pV.p);
     // the descriptor the reference builds for a new particle tree (FF/FLIP_vdb.cpp:3398-3404)
     // (initializeAttributes accepts only the one-attribute position descriptor; "v" is appended per leaf, as the reference does)
     auto pdescr = openvdb::points::AttributeSet::Descriptor::create(position_attribute::attributeType());
@@ -217,7 +339,14 @@ inline void download_particles(WorldHolder& h, openvdb::points::PointDataGrid::P
         std::memcpy(TestAttributeArray::bytes(va), &V[3 * begin[i]], size_t(cnt) * 6);
     });
     g->setTree(tree);
-    h.lastTree[FLIPB200_NUM_GRIDS] = &g->tree(); h.lastLeaves[FLIPB200_NUM_GRIDS] = g->tree().leafCount();
+    std::vector<const openvdb::points::PointDataTree::LeafNodeType*> cl;
+    g->tree().getNodes(cl);
+    h.fp[FLIPB200_NUM_GRIDS] = fingerprint_particles(*g, cl);
+}
+inline void download_particles(WorldHolder& h, openvdb::points::PointDataGrid::Ptr& g) {
+    download_particles_begin(h);
+    download_wait(h);
+    download_particles_finish(h, g);
 }
 
 #ifndef FLIPB200_PLUGIN_MARSHAL_ONLY
@@ -243,12 +372,16 @@ struct FLIP_P2G : zeno::INode {
         auto VelGrid = get_input("Velocity")->as<VDBFloat3Grid>();
         auto PostP2GVelGrid = get_input("PostP2GVelocity")->as<VDBFloat3Grid>();
         auto LiquidSDFGrid = get_input("LiquidSDF")->as<VDBFloatGrid>();
-        WorldHolder& h = world_for(dx);
+        WorldHolder& h = world_for(dx, {Particles, VelGrid, PostP2GVelGrid, LiquidSDFGrid});
         upload_particles(h, Particles->m_grid);
         check(flipb200_p2g(h.w, dx, n), "FLIP_P2G");
-        download<openvdb::Vec3fGrid>(h, FLIPB200_VELOCITY, VelGrid->m_grid);
-        download<openvdb::Vec3fGrid>(h, FLIPB200_POSTADV_VELOCITY, PostP2GVelGrid->m_grid);
-        download<openvdb::FloatGrid>(h, FLIPB200_LIQUID_SDF, LiquidSDFGrid->m_grid);
+        download_begin<openvdb::Vec3fGrid>(h, FLIPB200_VELOCITY);
+        download_begin<openvdb::Vec3fGrid>(h, FLIPB200_POSTADV_VELOCITY);
+        download_begin<openvdb::FloatGrid>(h, FLIPB200_LIQUID_SDF);
+        download_wait(h);
+        download_finish<openvdb::Vec3fGrid>(h, FLIPB200_VELOCITY, VelGrid->m_grid);
+        download_finish<openvdb::Vec3fGrid>(h, FLIPB200_POSTADV_VELOCITY, PostP2GVelGrid->m_grid);
+        download_finish<openvdb::FloatGrid>(h, FLIPB200_LIQUID_SDF, LiquidSDFGrid->m_grid);
     }
 };
 static int defFLIP_P2G = zeno::defNodeClass<FLIP_P2G>("FLIP_P2G",
@@ -271,7 +404,7 @@ struct G2PAdvectorSheet : zeno::INode {
         auto liquidsdf = get_input("LiquidSDF")->as<VDBFloatGrid>();
         auto velocity_viscous = get_input("ViscousVelocity")->as<VDBFloat3Grid>();
         auto velocity_after_p2g = get_input("PostAdvVelocity")->as<VDBFloat3Grid>();
-        WorldHolder& h = world_for(dx);
+        WorldHolder& h = world_for(dx, {particles, velocity, liquidsdf, velocity_after_p2g});
         if (has_input("SolidSDF")) upload<openvdb::FloatGrid>(h, FLIPB200_SOLID_SDF, get_input("SolidSDF")->as<VDBFloatGrid>()->m_grid);
         if (has_input("SolidVelocity")) upload<openvdb::Vec3fGrid>(h, FLIPB200_SOLID_VELOCITY, get_input("SolidVelocity")->as<VDBFloat3Grid>()->m_grid);
         upload_particles(h, particles->m_grid);
@@ -297,10 +430,19 @@ struct VDBRenormalizeSDF : zeno::INode {
         auto inoutSDF = get_input("inoutSDF")->as<VDBFloatGrid>();
         const int normIter = get_param<int>("iterations");
         const int dilateIter = get_param<int>("dilateIters");
-        WorldHolder& h = world_for(float(inoutSDF->m_grid->voxelSize()[0]));
+        WorldHolder& h = world_for(float(inoutSDF->m_grid->voxelSize()[0]), {inoutSDF});
+        if (dilateIter != 0) {
+            // the tracker's dilate / erode changes the narrow band's TOPOLOGY (openvdb/tools/LevelSetTracker.h); it is not accelerated and
+            // runs here exactly as in the reference node (projects/zenvdb/VDBRenormalize.cpp:24-31), the normalisation passes follow on the device
+            auto lstracker = openvdb::tools::LevelSetTracker<openvdb::FloatGrid>(*(inoutSDF->m_grid));
+            lstracker.setState({openvdb::math::FIRST_BIAS, openvdb::math::TVD_RK3, 1, 1});
+            lstracker.setTrimming(openvdb::tools::lstrack::TrimMode::kNone);
+            if (dilateIter > 0) lstracker.dilate(dilateIter);
+            else lstracker.erode(dilateIter);
+        }
         // the socket can carry any level set: it travels in the generic float slot, not in the world's LiquidSDF
         upload<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, inoutSDF->m_grid);
-        check(flipb200_renormalize_sdf(h.w, FLIPB200_KILLER_SDF, normIter, dilateIter), "VDBRenormalizeSDF");
+        check(flipb200_renormalize_sdf(h.w, FLIPB200_KILLER_SDF, normIter, 0), "VDBRenormalizeSDF");
         download<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, inoutSDF->m_grid);
         set_output("inoutSDF", get_input("inoutSDF"));
     }
@@ -316,7 +458,7 @@ struct VDBSmoothSDF : zeno::INode {
         auto inoutSDF = get_input("inoutSDF")->as<VDBFloatGrid>();
         const int width = get_param<int>("width");
         const int iterations = get_param<int>("iterations");
-        WorldHolder& h = world_for(float(inoutSDF->m_grid->voxelSize()[0]));
+        WorldHolder& h = world_for(float(inoutSDF->m_grid->voxelSize()[0]), {inoutSDF});
         upload<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, inoutSDF->m_grid);
         check(flipb200_smooth_sdf(h.w, FLIPB200_KILLER_SDF, width, iterations), "VDBSmoothSDF");
         download<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, inoutSDF->m_grid);
@@ -333,7 +475,7 @@ struct VDBErodeSDF : zeno::INode {
     virtual void apply() override {
         auto inoutSDF = get_input("inoutSDF")->as<VDBFloatGrid>();
         const float depth = get_input("depth")->as<zeno::NumericObject>()->get<float>();
-        WorldHolder& h = world_for(float(inoutSDF->m_grid->voxelSize()[0]));
+        WorldHolder& h = world_for(float(inoutSDF->m_grid->voxelSize()[0]), {inoutSDF});
         upload<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, inoutSDF->m_grid);
         check(flipb200_erode_sdf(h.w, FLIPB200_KILLER_SDF, depth), "VDBErodeSDF");
         download<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, inoutSDF->m_grid);
@@ -356,7 +498,7 @@ struct G2P_Advector : zeno::INode {
         if (has_input("SolidSDF"))
             throw makeError("G2P_Advector (libflipb200): with a SolidSDF connected the reference node dereferences a null liquid SDF "
                             "(FF/FLIP_vdb.cpp:3251-3278); use G2PAdvectorSheetty");
-        WorldHolder& h = world_for(dx);
+        WorldHolder& h = world_for(dx, {particles, velocity, velocity_after_p2g});
         upload_particles(h, particles->m_grid);
         upload<openvdb::Vec3fGrid>(h, FLIPB200_VELOCITY, velocity->m_grid);
         upload<openvdb::Vec3fGrid>(h, FLIPB200_POSTADV_VELOCITY, velocity_after_p2g->m_grid);
@@ -375,7 +517,7 @@ struct KillParticlesInSDF : zeno::INode {
         auto points = get_input("Particles")->as<VDBPointsGrid>();
         auto sdf = get_input("KillerSDF")->as<VDBFloatGrid>();
         const std::string op = has_input("OpType:") ? get_param<std::string>("OpType") : std::string("KEEP");
-        WorldHolder& h = world_for(float(points->m_grid->voxelSize()[0]));
+        WorldHolder& h = world_for(float(points->m_grid->voxelSize()[0]), {points});
         upload_particles(h, points->m_grid);
         upload<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, sdf->m_grid);
         check(flipb200_kill_particles_in_sdf(h.w, FLIPB200_KILLER_SDF, op == "KEEP" ? 1 : 0), "KillParticlesInSDF");
@@ -392,7 +534,7 @@ struct ParticleAddDV : zeno::INode {
     virtual void apply() override {
         auto particles = get_input("Particles")->as<VDBPointsGrid>();
         auto dv = get_input("dv")->as<zeno::NumericObject>()->get<zeno::vec3f>();
-        WorldHolder& h = world_for(float(particles->m_grid->voxelSize()[0]));
+        WorldHolder& h = world_for(float(particles->m_grid->voxelSize()[0]), {particles});
         upload_particles(h, particles->m_grid);
         check(flipb200_particles_add_dv(h.w, dv[0], dv[1], dv[2]), "ParticleAddDV");   // the node's channel is always "vel"
         download_particles(h, particles->m_grid);
@@ -409,7 +551,7 @@ struct CutCellWeightEval : zeno::INode {
         auto face_weight = get_input("FaceWeight")->as<VDBFloat3Grid>();
         auto liquid_sdf = get_input("LiquidSDF")->as<VDBFloatGrid>();
         auto solid_sdf = get_input("SolidSDF")->as<VDBFloatGrid>();
-        WorldHolder& h = world_for(float(liquid_sdf->m_grid->voxelSize()[0]));
+        WorldHolder& h = world_for(float(liquid_sdf->m_grid->voxelSize()[0]), {liquid_sdf, face_weight});
         upload<openvdb::FloatGrid>(h, FLIPB200_LIQUID_SDF, liquid_sdf->m_grid);
         upload<openvdb::FloatGrid>(h, FLIPB200_SOLID_SDF, solid_sdf->m_grid);
         check(flipb200_face_weights(h.w), "CutCellWeight");
@@ -425,7 +567,7 @@ struct PushOutLiquidSDF : zeno::INode {
         const float dx = dx_of(this);
         auto liquid_sdf = get_input("LiquidSDF")->as<VDBFloatGrid>();
         auto solid_sdf = get_input("SolidSDF")->as<VDBFloatGrid>();
-        WorldHolder& h = world_for(dx);
+        WorldHolder& h = world_for(dx, {liquid_sdf});
         upload<openvdb::FloatGrid>(h, FLIPB200_LIQUID_SDF, liquid_sdf->m_grid);
         upload<openvdb::FloatGrid>(h, FLIPB200_SOLID_SDF, solid_sdf->m_grid);
         check(flipb200_pushout_sdf(h.w, dx), "PushOutLiquidSDF");
@@ -440,7 +582,7 @@ struct FieldAddVector : zeno::INode {
     virtual void apply() override {
         auto ivec3 = get_input("invec3")->as<NumericObject>()->get<zeno::vec3f>();
         auto velocity = get_input("Velocity")->as<VDBFloat3Grid>();
-        WorldHolder& h = world_for(float(velocity->m_grid->voxelSize()[0]));
+        WorldHolder& h = world_for(float(velocity->m_grid->voxelSize()[0]), {velocity});
         upload<openvdb::Vec3fGrid>(h, FLIPB200_VELOCITY, velocity->m_grid);
         check(flipb200_add_vector(h.w, ivec3[0], ivec3[1], ivec3[2]), "FieldAddVector");
         download<openvdb::Vec3fGrid>(h, FLIPB200_VELOCITY, velocity->m_grid);
@@ -456,7 +598,7 @@ struct CFL : zeno::INode {
         const float vdx = float(velocity->m_grid->voxelSize()[0]);
         float dx = get_param<float>("dx");
         if (has_input("Dx")) dx = get_input("Dx")->as<NumericObject>()->get<float>();
-        WorldHolder& h = world_for(vdx);
+        WorldHolder& h = world_for(vdx, {velocity});
         upload<openvdb::Vec3fGrid>(h, FLIPB200_VELOCITY, velocity->m_grid);
         float dt = 0.f;
         check(flipb200_cfl(h.w, &dt), "CFL_dt");
@@ -482,7 +624,7 @@ struct AssembleSolvePPE : zeno::INode {
         auto solid_velocity = get_input("SolidVelocity")->as<VDBFloat3Grid>();
         const float tension_coef = get_input("SurfaceTension")->as<NumericObject>()->get<float>();
         if (tension_coef > 0) throw makeError("AssembleSolvePPE (libflipb200): the surface-tension right-hand side is not accelerated (SURVEY 8f-4)");
-        WorldHolder& h = world_for(dx);
+        WorldHolder& h = world_for(dx, {liquid_sdf, velocity, curr_pressure, face_weight, rhsgrid});
         upload<openvdb::FloatGrid>(h, FLIPB200_LIQUID_SDF, liquid_sdf->m_grid);
         upload<openvdb::Vec3fGrid>(h, FLIPB200_FACE_WEIGHT, face_weight->m_grid);
         upload<openvdb::Vec3fGrid>(h, FLIPB200_VELOCITY, velocity->m_grid);
@@ -492,8 +634,11 @@ struct AssembleSolvePPE : zeno::INode {
         float res = 0.f;
         check(flipb200_solve_ppe(h.w, dt, dx, &iters, &res, &status), "AssembleSolvePPE");
         printf("iter:%d err:%e%s\n", iters + 1, res, status ? " (pure multigrid fallback)" : "");
-        download<openvdb::FloatGrid>(h, FLIPB200_PRESSURE, curr_pressure->m_grid);
-        download<openvdb::FloatGrid>(h, FLIPB200_DIVERGENCE, rhsgrid->m_grid);
+        download_begin<openvdb::FloatGrid>(h, FLIPB200_PRESSURE);
+        download_begin<openvdb::FloatGrid>(h, FLIPB200_DIVERGENCE);
+        download_wait(h);
+        download_finish<openvdb::FloatGrid>(h, FLIPB200_PRESSURE, curr_pressure->m_grid);
+        download_finish<openvdb::FloatGrid>(h, FLIPB200_DIVERGENCE, rhsgrid->m_grid);
     }
 };
 static int defAssembleSolvePPE = zeno::defNodeClass<AssembleSolvePPE>("AssembleSolvePPE",
@@ -515,7 +660,7 @@ struct SubtractPressureGradient : zeno::INode {
         auto solid_velocity = get_input("SolidVelocity")->as<VDBFloat3Grid>();
         const float tension_coef = get_input("SurfaceTension")->as<NumericObject>()->get<float>();
         if (tension_coef > 0) throw makeError("SubtractPressureGradient (libflipb200): surface tension is not accelerated (SURVEY 8f-4)");
-        WorldHolder& h = world_for(dx);
+        WorldHolder& h = world_for(dx, {liquid_sdf, velocity, curr_pressure, face_weight});
         upload<openvdb::FloatGrid>(h, FLIPB200_LIQUID_SDF, liquid_sdf->m_grid);
         upload<openvdb::FloatGrid>(h, FLIPB200_SOLID_SDF, solid_sdf->m_grid);
         upload<openvdb::FloatGrid>(h, FLIPB200_PRESSURE, curr_pressure->m_grid);
