@@ -499,7 +499,7 @@ def main():
                     "peak_source": peak_src, "avg_launch_us": d["avg_us"],
                     "share_of_step": d["ms_per_step"] / max(sum(x["ms_per_step"] for x in kern.values()), 1e-9),
                     "measured": f"CUDA events around every launch of the family over {PROF_STEPS} substeps following the timed region"}
-    top = sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])[:12]
+    top = sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])[:int(os.environ.get("FLIPB200_BENCH_TOP", "14"))]
 
     # ---- e2e: the same step with the world state crossing PCIe both ways every step
     e2e = None

@@ -229,11 +229,16 @@ __global__ void __launch_bounds__(512) air_ring_kernel(TopoView t, const uint64_
     if ((threadIdx.x & 31) == 0) reinterpret_cast<uint32_t*>(sdfMask)[(size_t)leaf * 16 + (threadIdx.x >> 5)] = b;
 }
 
-// one layer of union_extrapolate for one channel (FF/vdb_velocity_extrapolator.cpp:618-657)
+// one layer of union_extrapolate (FF/vdb_velocity_extrapolator.cpp:618-657); blockIdx.y = channel (the three channels are independent:
+// one launch per layer instead of three)
 __global__ void __launch_bounds__(512) extrapolate_layer_kernel(TopoView t, const uint64_t* __restrict__ target,
-                                                                const uint64_t* __restrict__ validIn,
-                                                                uint64_t* __restrict__ validOut, float* __restrict__ val) {
+                                                                const uint64_t* __restrict__ validIn3,
+                                                                uint64_t* __restrict__ validOut3, float* __restrict__ val0,
+                                                                float* __restrict__ val1, float* __restrict__ val2, size_t stride) {
     int leaf = blockIdx.x, off = threadIdx.x;
+    const uint64_t* validIn = validIn3 + blockIdx.y * stride;
+    uint64_t* validOut = validOut3 + blockIdx.y * stride;
+    float* val = blockIdx.y == 0 ? val0 : (blockIdx.y == 1 ? val1 : val2);
     bool valid = mask_get(validIn, leaf, off);
     bool tgt = mask_get(target, leaf, off);
     bool newOn = valid;
@@ -279,20 +284,18 @@ __global__ void andnot_kernel(uint64_t* __restrict__ a, const uint64_t* __restri
 
 void union_extrapolate(World* w, int nLayer, GridV& vel, uint64_t* chMask, const uint64_t* targetMask) {
     const Topo& t = *vel.topo;
-    if (t.n == 0) return;
+    if (t.n == 0 || nLayer <= 0) return;
     size_t stride = (size_t)t.n * 8;
-    DBuf<uint64_t> tmp(stride, w->stream);
-    for (int ch = 0; ch < 3; ch++) {
-        uint64_t* cur = chMask + ch * stride;
-        uint64_t* nxt = tmp.p;
-        for (int layer = 0; layer < nLayer; layer++) {
-            FB_LAUNCH(w, "extrapolate_layer", (size_t)t.n * (2048 + 192)) extrapolate_layer_kernel<<<t.n, 512, 0, w->stream>>>(t.view(), targetMask, cur, nxt, vel.val[ch].p);
-            check_launch("extrapolate_layer");
-            std::swap(cur, nxt);
-        }
-        if (cur != chMask + ch * stride)
-            FB_CUDA(cudaMemcpyAsync(chMask + ch * stride, cur, stride * 8, cudaMemcpyDeviceToDevice, w->stream));
+    DBuf<uint64_t> tmp(3 * stride, w->stream);
+    uint64_t* cur = chMask;
+    uint64_t* nxt = tmp.p;
+    for (int layer = 0; layer < nLayer; layer++) {
+        FB_LAUNCH(w, "extrapolate_layer", (size_t)3 * t.n * (2048 + 192))
+            extrapolate_layer_kernel<<<dim3(t.n, 3), 512, 0, w->stream>>>(t.view(), targetMask, cur, nxt, vel.val[0].p, vel.val[1].p, vel.val[2].p, stride);
+        check_launch("extrapolate_layer");
+        std::swap(cur, nxt);
     }
+    if (cur != chMask) FB_CUDA(cudaMemcpyAsync(chMask, cur, 3 * stride * 8, cudaMemcpyDeviceToDevice, w->stream));
 }
 
 void finish_vec3(World* w, GridV& vel, const uint64_t* chMask) {

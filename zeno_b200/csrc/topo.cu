@@ -128,34 +128,63 @@ __global__ void pts_counts_remap_kernel(TopoView oldT, TopoView newT, const uint
     }
 }
 // dilation: one CTA of 512 threads per leaf, neighbour masks staged in shared memory
-__global__ void __launch_bounds__(512) dilate_kernel(TopoView t, const uint64_t* __restrict__ in,
+// out = dilate(in) by one voxel, 26- or 6-neighbourhood, on whole 64-bit mask words (word X = the x slice, bit y << 3 | z).
+// The 26-neighbourhood dilation is separable: OR the x slices X-1, X, X+1, then spread the 8x8 slice along y (shifts by 8 bits,
+// rows 7 / 0 of the +-y neighbour leaves carried in), then along z (shifts by 1 bit inside each byte, columns carried in from the
+// +-z neighbours) -- each stage on the stage before, for the leaf AND the neighbour leaves it borrows from, so edge and corner
+// leaves are covered. One warp per leaf, ~100 word operations (round 1: one thread per voxel, 27 shared-memory bit probes each,
+// 34 us per launch at 5800 leaves).
+__global__ void __launch_bounds__(128) dilate_kernel(TopoView t, const uint64_t* __restrict__ in,
                                                      uint64_t* __restrict__ out, int nn26) {
-    __shared__ uint64_t sm[27 * 8];
-    int l = blockIdx.x;
-    for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) {
-        int nb = t.nbr27[l * 27 + i / 8];
-        sm[i] = nb >= 0 ? in[(size_t)nb * 8 + (i & 7)] : 0ull;
+    __shared__ uint64_t sIn[4][27 * 8];
+    __shared__ uint64_t sA[4][9 * 8];     // after the x stage: (ly, lz) columns of leaves, lx = centre
+    __shared__ uint64_t sB[4][3 * 8];     // after the y stage: lz columns, lx = ly = centre
+    const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int l = blockIdx.x * 4 + g;
+    const bool live = l < t.n;
+    uint64_t* I = sIn[g]; uint64_t* A = sA[g]; uint64_t* B = sB[g];
+    if (live)
+        for (int i = lane; i < 27 * 8; i += 32) {
+            const int nb = t.nbr27[(size_t)l * 27 + i / 8];
+            I[i] = nb >= 0 ? in[(size_t)nb * 8 + (i & 7)] : 0ull;
+        }
+    __syncwarp();
+    if (!live) return;
+    if (!nn26) {
+        // faces only: the leaf's own shifts + one plane / row / column of each face neighbour (nbr27 index lx * 9 + ly * 3 + lz)
+        if (lane < 8) {
+            const int X = lane;
+            const uint64_t w = I[13 * 8 + X];
+            uint64_t o = w | (w << 8) | (w >> 8) | ((w << 1) & 0xfefefefefefefefeull) | ((w >> 1) & 0x7f7f7f7f7f7f7f7full);
+            o |= X > 0 ? I[13 * 8 + X - 1] : I[4 * 8 + 7];
+            o |= X < 7 ? I[13 * 8 + X + 1] : I[22 * 8 + 0];
+            o |= I[10 * 8 + X] >> 56;                          // row 7 of the -y leaf -> row 0
+            o |= (I[16 * 8 + X] & 0xffull) << 56;               // row 0 of the +y leaf -> row 7
+            o |= (I[12 * 8 + X] >> 7) & 0x0101010101010101ull;  // column 7 of the -z leaf -> column 0
+            o |= (I[14 * 8 + X] & 0x0101010101010101ull) << 7;  // column 0 of the +z leaf -> column 7
+            out[(size_t)l * 8 + X] = o;
+        }
+        return;
     }
-    __syncthreads();
-    int off = threadIdx.x;
-    int x = off >> 6, y = (off >> 3) & 7, z = off & 7;
-    auto get = [&](int gx, int gy, int gz) -> bool {  // coordinates in [-1, 8]
-        int li = ((gx < 0 ? 0 : (gx < 8 ? 1 : 2)) * 9) + ((gy < 0 ? 0 : (gy < 8 ? 1 : 2)) * 3) +
-                 (gz < 0 ? 0 : (gz < 8 ? 1 : 2));
-        int o = ((gx & 7) << 6) | ((gy & 7) << 3) | (gz & 7);
-        return (sm[li * 8 + (o >> 6)] >> (o & 63)) & 1ull;
-    };
-    bool on = false;
-    if (nn26) {
-        for (int a = -1; a <= 1; a++)
-            for (int b = -1; b <= 1; b++)
-                for (int c = -1; c <= 1; c++) on |= get(x + a, y + b, z + c);
-    } else {
-        on = get(x, y, z) | get(x - 1, y, z) | get(x + 1, y, z) | get(x, y - 1, z) | get(x, y + 1, z) |
-             get(x, y, z - 1) | get(x, y, z + 1);
+    for (int i = lane; i < 72; i += 32) {          // x stage
+        const int col = i >> 3, X = i & 7;          // col = ly * 3 + lz
+        const uint64_t* c0 = I + (0 * 9 + col) * 8;
+        const uint64_t* c1 = I + (1 * 9 + col) * 8;
+        const uint64_t* c2 = I + (2 * 9 + col) * 8;
+        A[i] = c1[X] | (X > 0 ? c1[X - 1] : c0[7]) | (X < 7 ? c1[X + 1] : c2[0]);
     }
-    unsigned b = __ballot_sync(0xffffffffu, on);
-    if ((threadIdx.x & 31) == 0) reinterpret_cast<uint32_t*>(out)[(size_t)l * 16 + (threadIdx.x >> 5)] = b;
+    __syncwarp();
+    if (lane < 24) {                               // y stage
+        const int lz = lane >> 3, X = lane & 7;
+        const uint64_t m = A[(1 * 3 + lz) * 8 + X], lo = A[(0 * 3 + lz) * 8 + X], hi = A[(2 * 3 + lz) * 8 + X];
+        B[lane] = m | (m << 8) | (m >> 8) | (lo >> 56) | ((hi & 0xffull) << 56);
+    }
+    __syncwarp();
+    if (lane < 8) {                                // z stage
+        const uint64_t m = B[8 + lane], lo = B[lane], hi = B[16 + lane];
+        out[(size_t)l * 8 + lane] = m | ((m << 1) & 0xfefefefefefefefeull) | ((m >> 1) & 0x7f7f7f7f7f7f7f7full) |
+                                    ((lo >> 7) & 0x0101010101010101ull) | ((hi & 0x0101010101010101ull) << 7);
+    }
 }
 __global__ void popcount_kernel(const uint64_t* __restrict__ mask, size_t nWords, unsigned long long* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,7 +407,7 @@ void refresh_solid_views(World* w) {
 
 void mask_dilate(World* w, const Topo& t, const uint64_t* in, uint64_t* out, bool nn26) {
     if (t.n == 0) return;
-    FB_LAUNCH(w, "mask_dilate", (size_t)t.n * 128) dilate_kernel<<<t.n, 512, 0, w->stream>>>(t.view(), in, out, nn26 ? 1 : 0);
+    FB_LAUNCH(w, "mask_dilate", (size_t)t.n * 128) dilate_kernel<<<(t.n + 3) / 4, 128, 0, w->stream>>>(t.view(), in, out, nn26 ? 1 : 0);
     check_launch("dilate");
 }
 void mask_count_async(World* w, const uint64_t* mask, int nLeaves, unsigned long long* out) {
