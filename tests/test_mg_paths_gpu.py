@@ -30,7 +30,8 @@ def _world(N, seed=2):
 
 
 def _solve(w, dx, env, tol=None):
-    saved = {k: os.environ.get(k) for k in ("FLIPB200_MG_PATH", "FLIPB200_CLUSTER_FIRST", "FLIPB200_BRICK_MIN", "FLIPB200_CG_COMPAT")}
+    saved = {k: os.environ.get(k) for k in ("FLIPB200_MG_PATH", "FLIPB200_CLUSTER_FIRST", "FLIPB200_BRICK_MIN", "FLIPB200_CG_COMPAT",
+                                            "FLIPB200_NO_CYCLE_KERNEL", "FLIPB200_MG_L1")}
     try:
         for k in saved:
             os.environ.pop(k, None)
@@ -79,4 +80,33 @@ def test_default_coarsest_cg_is_equivalent(gpu_lib, N):
     assert np.array_equal(new[1], again[1]), "the solve must be deterministic"
     util.compare_grids(new[2], ref[2], f"pressure, default CG vs compat CG, N={N}", tol=1e-5)
     util.compare_grids(new[2], again[2], f"pressure, two runs, N={N}", tol=0.0)
+    w.close()
+
+
+@pytest.mark.parametrize("N", [64, 128, 192])
+def test_l1_cached_passes_agree_bitwise(gpu_lib, N):
+    """The one-launch kernel reads the iterate through L1 between grid barriers (M_GRID_L1); FLIPB200_MG_L1=0 selects the
+    L2-coherent loads it replaced. Any stale line would show up as a different residual history."""
+    w, dx = _world(N)
+    _solve(w, dx, {"FLIPB200_MG_L1": "0"}, tol=1e-6)
+    for _ in range(2):
+        ref = _solve(w, dx, {"FLIPB200_MG_L1": "0"}, tol=1e-6)
+        new = _solve(w, dx, {"FLIPB200_MG_L1": "1"}, tol=1e-6)
+        assert ref[0]["status"] == 0 and new[0]["status"] == 0, (ref[0], new[0])
+        assert np.array_equal(ref[1], new[1]), (ref[1], new[1])
+        util.compare_grids(new[2], ref[2], f"pressure, L1 vs L2 loads, N={N}", tol=0.0)
+    w.close()
+
+
+@pytest.mark.parametrize("N", [64, 128])
+def test_one_kernel_per_pass_is_equivalent(gpu_lib, N):
+    """The plain path (one kernel per colour pass, its own coarsest solve and reduction order): same iteration count,
+    pressure within 1e-5."""
+    w, dx = _world(N)
+    _solve(w, dx, {"FLIPB200_MG_PATH": "cycle"}, tol=1e-6)
+    ref = _solve(w, dx, {"FLIPB200_NO_CYCLE_KERNEL": "1"}, tol=1e-6)
+    new = _solve(w, dx, {}, tol=1e-6)
+    assert ref[0]["status"] == 0 and new[0]["status"] == 0, (ref[0], new[0])
+    assert ref[0]["iterations"] == new[0]["iterations"], (ref[0], new[0])
+    util.compare_grids(new[2], ref[2], f"pressure, one-launch vs one kernel per pass, N={N}", tol=1e-5)
     w.close()

@@ -1,10 +1,10 @@
 #!/bin/bash
-# per-op device timestamps of one mg_cycle_kernel application at the bench size
-mkdir -p gpurun_out
-FLIPB200_TRACE_CYCLE=gpurun_out/cycle_trace.csv timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/trace_bench.json 2> gpurun_out/trace_bench.err
+# per-op device timestamps of the mg_cycle_kernel launches (whole cycles or the hybrid path's segments) at the bench size
+mkdir -p gpurun_out; rm -f gpurun_out/cycle_trace.csv
+FLIPB200_TRACE_CYCLE=gpurun_out/cycle_trace.csv timeout 600 python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --no-check > gpurun_out/trace_bench.json 2> gpurun_out/trace_bench.err
 python - <<'PY'
 import csv, collections
-rows=list(csv.DictReader(open("gpurun_out/cycle_trace.csv")))
+rows=[r for r in csv.DictReader(open("gpurun_out/cycle_trace.csv")) if r["k"] != "k"]
 names={0:"zero_red",1:"red",2:"black",3:"resid_restrict",4:"prolong",5:"coarse_cg"}
 agg=collections.OrderedDict()
 for r in rows:

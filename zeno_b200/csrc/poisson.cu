@@ -289,7 +289,12 @@ struct Nbr { int xm, xp, ym, yp, zm, zp; };
 //   M_GRID  mg_cycle_kernel, many CTAs in one launch separated by grid barriers: x and b were written by other
 //           SMs inside this launch, so they are read from L2 (ld.global.cg), never from this SM's L1
 //   M_LOCAL one CTA owns the data for the whole launch (shared memory or its own L1): plain loads
-enum { M_LEAF = 0, M_GRID = 1, M_LOCAL = 2 };
+//   M_GRID_L1  like M_GRID but with plain (L1-cached) loads. Sound because every op of the launch ends in grid_barrier(), whose
+//           ld.acquire.gpu orders all later loads of the CTA after the other SMs' released stores (the hardware invalidates the
+//           SM's L1 there), and inside a colour pass a thread reads only values no other thread writes in that pass (the six
+//           neighbours have the other colour). What it buys: the seven x loads of a voxel touch the same few sectors; served by
+//           L1 they cost one L2 sector read instead of up to seven (a level-0 pass moved ~84 MB through L2 -> SM).
+enum { M_LEAF = 0, M_GRID = 1, M_LOCAL = 2, M_GRID_L1 = 3 };
 // L2-coherent load (LDG.E.STRONG.GPU): never served from this SM's L1
 __device__ __forceinline__ float ld_l2(const float* p) {
     float v;
@@ -360,6 +365,34 @@ __device__ __forceinline__ void rbgs_leaf(const LevelView& L, float* x, const fl
     // is predicated on the DOF bit, so no load waits behind a branch
     const float bi = ldb<M>(&b[i]), inv = __ldg(&L.invdiag[i]), xi = ldx<M>(&x[i]);
     const bool on = dof_bit(L, leaf, off);
+    const Nbr nb = nbr_of(li);
+    const float od = (li.flags & LI_CONST) ? offdiag<true, M>(L, x, leaf, off, nb) : offdiag<false, M>(L, x, leaf, off, nb);
+    const float tt = __fmul_rn(__fmul_rn(__fsub_rn(bi, od), inv), w);
+    if (on) x[i] = __fmaf_rn(xi, oneMinusW, tt);
+}
+// The same pass with the leaf record read from shared memory (mg_cycle_kernel keeps the records of the chunks a CTA visits,
+// which never change inside a launch): one L2 round trip per chunk (the operands) instead of two (record, then operands).
+struct CachedInfo { int nb[6]; uint32_t flags, pad; uint64_t mask[8]; };   // the first 96 bytes of a LeafInfo
+__device__ __forceinline__ LeafInfo cached_info(const CachedInfo& ci) {
+    const int4 a = *reinterpret_cast<const int4*>(&ci.nb[0]);
+    const int4 b = *reinterpret_cast<const int4*>(&ci.nb[4]);
+    LeafInfo li;
+    li.nb[0] = a.x; li.nb[1] = a.y; li.nb[2] = a.z; li.nb[3] = a.w; li.nb[4] = b.x; li.nb[5] = b.y;
+    li.flags = (uint32_t)b.z;
+    return li;
+}
+template <int M>
+__device__ __forceinline__ void rbgs_leaf_cached(const LevelView& L, float* x, const float* b, int leaf, int t, int colour,
+                                                 float w, float oneMinusW, const CachedInfo& ci, float invDefault) {
+    const int X = t >> 5, Y = (t >> 2) & 7;
+    const int Z = ((t & 3) << 1) | ((X + Y + colour) & 1);
+    const int off = (X << 6) | (Y << 3) | Z;
+    const size_t i = (size_t)leaf * LEAF + off;
+    const LeafInfo li = cached_info(ci);
+    if (!(li.flags & LI_ANY)) return;
+    // a leaf whose diagonal is the default everywhere (LI_DIAG) holds 1 / (6 term) in every invdiag entry: not read
+    const float bi = ldb<M>(&b[i]), inv = (li.flags & LI_DIAG) ? invDefault : __ldg(&L.invdiag[i]), xi = ldx<M>(&x[i]);
+    const bool on = (ci.mask[X] >> (off & 63)) & 1ull;
     const Nbr nb = nbr_of(li);
     const float od = (li.flags & LI_CONST) ? offdiag<true, M>(L, x, leaf, off, nb) : offdiag<false, M>(L, x, leaf, off, nb);
     const float tt = __fmul_rn(__fmul_rn(__fsub_rn(bi, od), inv), w);
@@ -1144,7 +1177,10 @@ struct CycleParams {
     unsigned* barrier;                // arrival counter, zero at launch
     unsigned long long* trace;        // optional: %globaltimer at the start of every op (CTA 0), nOps + 1 entries
     int gridOnly;                     // the program holds ops of levels < compactFirst only (hybrid path): no compact staging
+    int cacheInfo;                    // keep the leaf records of the first grid levels in shared memory (CY_CACHE_*)
+    int l1Loads;                      // colour passes read x and b through L1 (M_GRID_L1)
 };
+constexpr int CY_CACHE_LEVELS = 3, CY_CACHE_SLOTS = 48;
 __device__ __forceinline__ unsigned long long globaltimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -1278,30 +1314,55 @@ __global__ void __launch_bounds__(BOT_THREADS) mg_cycle_kernel(const __grid_cons
         }
         __syncthreads();
     }
+    // the leaf records of the chunks this CTA visits on the first grid levels (chunk it of a pass = leaves c*4 + it*G*4 + 0..3)
+    __shared__ CachedInfo sInfo[CY_CACHE_LEVELS][CY_CACHE_SLOTS];
+    if (P.cacheInfo) {
+        const int ncl = P.compactFirst < CY_CACHE_LEVELS ? P.compactFirst : CY_CACHE_LEVELS;
+        for (int l = 0; l < ncl; l++) {
+            const BottomLevel& B = P.lv[l];
+            for (int i = tid; i < CY_CACHE_SLOTS * 6; i += BOT_THREADS) {
+                const int slot = i / 6, q = i - slot * 6;
+                const int leaf = c * 4 + (slot >> 2) * G * 4 + (slot & 3);
+                if (leaf < B.n) reinterpret_cast<int4*>(&sInfo[l][slot])[q] = __ldg(reinterpret_cast<const int4*>(B.v.info + leaf) + q);
+            }
+        }
+        __syncthreads();
+    }
     while (k < P.nOps) {
         const int code = P.prog[k] & 7, li = P.prog[k] >> 3;
         if (li < P.compactFirst) {
             if (P.trace && c == 0 && tid == 0) P.trace[k] = globaltimer();
             const BottomLevel& B = P.lv[li];
+            const bool cached = P.cacheInfo && li < CY_CACHE_LEVELS;
             if (code == OP_ZERO_RED) {
                 for (int base = c * 2; base < B.n; base += G * 2) { int leaf = base + (tid >> 9); if (leaf < B.n) zero_red_leaf<M_GRID>(B.v, B.x, B.b, leaf, tid & 511, P.w); }
             } else if (code == OP_RED || code == OP_BLACK) {
                 // no block barrier inside a pass: warps run ahead into the next chunk, which is what keeps loads in
                 // flight (a shared-memory tile version with two bar.sync per chunk measured 25 us vs 15 us at level 0)
-                for (int base = c * 4; base < B.n; base += G * 4) { int leaf = base + (tid >> 8); if (leaf < B.n) rbgs_leaf<M_GRID>(B.v, B.x, B.b, leaf, tid & 255, code == OP_RED ? 0 : 1, P.w, P.oneMinusW); }
+                int slot = tid >> 8;
+                const float invDefault = __fdiv_rn(1.0f, __fmul_rn(6.0f, B.v.term));
+                for (int base = c * 4; base < B.n; base += G * 4, slot += 4) {
+                    const int leaf = base + (tid >> 8);
+                    if (leaf >= B.n) continue;
+                    if (cached && slot < CY_CACHE_SLOTS) {
+                        if (P.l1Loads) rbgs_leaf_cached<M_GRID_L1>(B.v, B.x, B.b, leaf, tid & 255, code == OP_RED ? 0 : 1, P.w, P.oneMinusW, sInfo[li][slot], invDefault);
+                        else rbgs_leaf_cached<M_GRID>(B.v, B.x, B.b, leaf, tid & 255, code == OP_RED ? 0 : 1, P.w, P.oneMinusW, sInfo[li][slot], invDefault);
+                    } else rbgs_leaf<M_GRID>(B.v, B.x, B.b, leaf, tid & 255, code == OP_RED ? 0 : 1, P.w, P.oneMinusW);
+                }
             } else if (code == OP_RESID_RESTRICT) {
                 // 256 threads per leaf, two z-adjacent voxels each; residual into shared memory, then restrict
                 const BottomLevel& C = P.lv[li + 1];
                 const int g = tid >> 8, t = tid & 255;
                 float* T = tiles + g * TILE;
                 float* R = sresGrid + g * LEAF;
-                for (int base = c * 4; base < B.n; base += G * 4) {
+                int slot = g;
+                for (int base = c * 4; base < B.n; base += G * 4, slot += 4) {
                     const int leaf = base + g;
                     LeafInfo info;
                     bool live = false;
                     float2 bv = make_float2(0.f, 0.f);
                     if (leaf < B.n) {
-                        info = load_info(B.v, leaf);
+                        info = (cached && slot < CY_CACHE_SLOTS) ? cached_info(sInfo[li][slot]) : load_info(B.v, leaf);
                         live = (info.flags & LI_ANY) != 0;
                         if (live) {
                             tile_load(B.x, leaf, info, T, t);
@@ -1994,6 +2055,10 @@ struct Solver {
         }
         P.prog = second ? cycleProg2.p : cycleProg.p; P.nOps = second ? cycleOps2 : cycleOps; P.nLevels = nl; P.compactFirst = compactFirst;
         if (segProg) { P.prog = segProg; P.nOps = segOps; P.gridOnly = 1; }
+        static const int cacheInfo = getenv("FLIPB200_MG_INFO_CACHE") ? atoi(getenv("FLIPB200_MG_INFO_CACHE")) : 1;
+        P.cacheInfo = cacheInfo;
+        const int l1Loads = getenv("FLIPB200_MG_L1") ? atoi(getenv("FLIPB200_MG_L1")) : 1;   // read per launch: the tests compare both
+        P.l1Loads = l1Loads;
         P.scratchOff = scratchOff; P.cgOff = cgOff;
         P.w = 1.2f; P.oneMinusW = 1.0f - 1.2f; P.prolongAlpha = 1.0f;
         P.barrier = cycleBarrier.p;
@@ -2002,8 +2067,8 @@ struct Solver {
         const char* tracePath = tracePathEnv;
         DBuf<unsigned long long> trace;
         P.trace = nullptr;
-        if (second || segProg) tracePath = nullptr;
-        if (tracePath) { trace.alloc(cycleOps + 1, w->stream); trace.zero(); P.trace = trace.p; }
+        if (second) tracePath = nullptr;
+        if (tracePath) { trace.alloc((segProg ? segOps : cycleOps) + 1, w->stream); trace.zero(); P.trace = trace.p; }
         FB_CUDA(cudaMemsetAsync(cycleBarrier.p, 0, sizeof(unsigned), w->stream));
         uint64_t bytes = 0;  // 121 B/DOF per level visit, level l is visited 2^l times
         for (int i = 0; i < nl; i++) bytes += ((uint64_t)levels[i]->numDof * 121) << i;
@@ -2019,14 +2084,15 @@ struct Solver {
             FB_CUDA(cudaLaunchCooperativeKernel((const void*)mg_cycle_kernel, dim3(cycleGrid), dim3(BOT_THREADS), args, cycleSmem, w->stream));
         check_launch("mg_cycle");
         if (tracePath) {
-            std::vector<unsigned long long> t(cycleOps + 1);
-            std::vector<uint8_t> ops(cycleOps);
+            const int nTr = segProg ? segOps : cycleOps;
+            std::vector<unsigned long long> t(nTr + 1);
+            std::vector<uint8_t> ops(nTr);
             FB_CUDA(cudaMemcpyAsync(t.data(), trace.p, t.size() * 8, cudaMemcpyDeviceToHost, w->stream));
-            FB_CUDA(cudaMemcpyAsync(ops.data(), cycleProg.p, ops.size(), cudaMemcpyDeviceToHost, w->stream));
+            FB_CUDA(cudaMemcpyAsync(ops.data(), P.prog, ops.size(), cudaMemcpyDeviceToHost, w->stream));
             sync(w);
-            if (FILE* f = fopen(tracePath, "w")) {
+            if (FILE* f = fopen(tracePath, segProg ? "a" : "w")) {   // the segments of the hybrid path append (one block per launch)
                 fprintf(f, "k,op,level,leaves,dofs,compact,ns\n");
-                for (int k = 0; k < cycleOps; k++)
+                for (int k = 0; k < nTr; k++)
                     fprintf(f, "%d,%d,%d,%d,%d,%d,%llu\n", k, ops[k] & 7, ops[k] >> 3, levels[ops[k] >> 3]->n, levels[ops[k] >> 3]->numDof,
                             (ops[k] >> 3) >= compactFirst ? 1 : 0, t[k + 1] - t[k]);
                 fclose(f);
