@@ -465,9 +465,11 @@ def main():
     w.profile_enable(True)
     stage_ms = np.zeros(5)
     PROF_STEPS = 2
+    iter_hist = []
     for _ in range(PROF_STEPS):
         dt = substep_dt(w, dx)
         stage_ms += np.array(w.substep(dt, dx, 4, 3, 0.03, 0.05, GRAVITY, 3, True, want_stage_ms=True))
+        iter_hist.append(w.solver_info()["history"].shape[0] - 1)
     w.profile_enable(False)
     prof = w.profile_get()
     stage_ms /= PROF_STEPS
@@ -480,24 +482,58 @@ def main():
         gbs = (v["bytes"] / v["launches"]) / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         kern[k] = {"ms_per_step": v["ms"] / PROF_STEPS, "launches_per_step": v["launches"] / PROF_STEPS,
                    "avg_us": 1e3 * avg_ms, "algorithmic_GBps": gbs, "frac": gbs / peak}
-    dominant = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+    # The multigrid preconditioner is ONE op program that the library runs as a few launches split at level
+    # boundaries (mg_cycle_upper: levels 0-1 across the device, mg_cluster: the levels below inside one thread-block cluster, or
+    # the per-pass kernels under slab decomposition). The roofline entry is quoted for that program as a whole, per application:
+    # SURVEY 8d's 121 B/DOF per level visit over the sum of its launches' durations; its member launches stay listed in "kernels".
+    MG_FAMILY = ("mg_cycle", "mg_cycle_upper", "mg_cluster", "mg_dd_passes", "mg_rbgs", "mg_rbgs_rows", "mg_zero_red", "mg_residual_restrict",
+                 "mg_prolong", "mg_bottom", "mg_sweep")
+    fam = {}
+    members = [k for k in kern if k in MG_FAMILY]
+    if members:
+        fam_ms = sum(prof[k]["ms"] for k in members)
+        fam_bytes = sum(prof[k]["bytes"] for k in members)
+        its = [int(x) for x in iter_hist[-PROF_STEPS:]] if iter_hist else []
+        apps = max(sum(its), 1) if its else max(int(sum(prof[k]["launches"] for k in members) / 5), 1)
+        gbs = fam_bytes / (fam_ms * 1e-3) / 1e9 if fam_ms > 0 else 0.0
+        fam = {"ms_per_step": fam_ms / PROF_STEPS, "launches_per_step": sum(prof[k]["launches"] for k in members) / PROF_STEPS,
+               "applications_per_step": apps / PROF_STEPS, "avg_us": 1e3 * fam_ms / apps, "algorithmic_GBps": gbs, "frac": gbs / peak,
+               "bytes_per_application": fam_bytes / apps, "members": {k: kern[k]["launches_per_step"] * PROF_STEPS / apps for k in members}}
+    single = {k: v for k, v in kern.items() if k not in MG_FAMILY}
+    dominant = max(single, key=lambda k: single[k]["ms_per_step"]) if single else None
+    use_family = bool(fam) and (dominant is None or fam["ms_per_step"] >= single[dominant]["ms_per_step"])
     roofline = None
-    if dominant:
-        d = kern[dominant]
-        traffic = None
-        try:  # measured DRAM bytes per launch of this kernel from the committed ncu --set full capture (same workload)
+    if use_family or dominant:
+        tj = {}
+        try:  # measured DRAM bytes per launch from the committed ncu --set full capture (same workload)
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                t = json.load(f).get(dominant)
-            if t and N == 512 and args.ppc == 8:
-                traffic = t["bytes"]
+                tj = json.load(f)
         except Exception:
+            tj = {}
+        same_workload = N == 512 and args.ppc == 8 and world == 1
+        if use_family:
+            d = fam
             traffic = None
-        roofline = {"kernel": dominant, "bound": "hbm", "achieved": d["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
+            if same_workload and all(k in tj for k in fam["members"]):
+                traffic = sum(tj[k]["bytes"] * n for k, n in fam["members"].items())
+            name = "mgpcg preconditioner application = " + " + ".join(f"{n:g} x {k}" for k, n in fam["members"].items())
+            per_launch = fam["bytes_per_application"]
+            share_ms = fam["ms_per_step"]
+            src = "sum over the member launches of one application of dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/ncu_traffic.json, from the ncu --set full capture profiles/r02_hot_kernels.md); below the algorithmic bytes because the level-0 vectors (8 MB each) stay in the 126 MB L2"
+        else:
+            d = kern[dominant]
+            t = tj.get(dominant)
+            traffic = t["bytes"] if (t and same_workload) else None
+            name = dominant
+            per_launch = prof[dominant]["bytes"] / max(prof[dominant]["launches"], 1)
+            share_ms = d["ms_per_step"]
+            src = "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch (profiles/ncu_traffic.json)"
+        roofline = {"kernel": name, "bound": "hbm", "achieved": d["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
                     "frac": d["frac"], "frac_of_nominal_8TBps": d["algorithmic_GBps"] / 8000.0, "traffic": traffic,
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch (profiles/r01f_ncu_full_*; the mg_cycle capture predates the compact-row bottom of the cycle kernel)" if traffic is not None else None,
-                    "algorithmic_bytes_per_launch": prof[dominant]["bytes"] / max(prof[dominant]["launches"], 1),
+                    "traffic_source": src if traffic is not None else None,
+                    "algorithmic_bytes_per_launch": per_launch,
                     "peak_source": peak_src, "avg_launch_us": d["avg_us"],
-                    "share_of_step": d["ms_per_step"] / max(sum(x["ms_per_step"] for x in kern.values()), 1e-9),
+                    "share_of_step": share_ms / max(sum(x["ms_per_step"] for x in kern.values()), 1e-9),
                     "measured": f"CUDA events around every launch of the family over {PROF_STEPS} substeps following the timed region"}
     top = sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])[:int(os.environ.get("FLIPB200_BENCH_TOP", "14"))]
 

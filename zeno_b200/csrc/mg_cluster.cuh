@@ -313,6 +313,47 @@ struct CgSum {
         return make_float2(tree32(buf), tree32(buf + 32));
     }
 };
+// The default order of the sums (any fixed order is as good as another here: the coarsest solve is Eigen's CG in the reference,
+// whose order is its own): a thread's K rows in ascending order, one butterfly per warp, then EVERY thread folds the T / 32 warp
+// partials itself as a balanced tree -- one bar.sync per sum, no second stage.
+template <int T>
+struct CgSumFast {
+    static constexpr int K = 1024 / T, W = T / 32;
+    static __device__ __forceinline__ float fold(const float* p) {
+        float a[W];
+#pragma unroll
+        for (int i = 0; i < W; i += 4) { const float4 q = *reinterpret_cast<const float4*>(p + i); a[i] = q.x; a[i + 1] = q.y; a[i + 2] = q.z; a[i + 3] = q.w; }
+#pragma unroll
+        for (int h = W / 2; h > 0; h >>= 1)
+#pragma unroll
+            for (int i = 0; i < h; i++) a[i] = __fadd_rn(a[i], a[i + h]);
+        return a[0];
+    }
+    static __device__ __forceinline__ float sum(float (&v)[K], float* red, unsigned& phase) {
+        float x = v[0];
+#pragma unroll
+        for (int j = 1; j < K; j++) x = __fadd_rn(x, v[j]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, d));
+        float* buf = red + (phase & 1u) * 64;
+        phase++;
+        if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5] = x;
+        __syncthreads();
+        return fold(buf);
+    }
+    static __device__ __forceinline__ float2 sum2(float (&a)[K], float (&b)[K], float* red, unsigned& phase) {
+        float x = a[0], y = b[0];
+#pragma unroll
+        for (int j = 1; j < K; j++) { x = __fadd_rn(x, a[j]); y = __fadd_rn(y, b[j]); }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { x = __fadd_rn(x, __shfl_xor_sync(0xffffffffu, x, d)); y = __fadd_rn(y, __shfl_xor_sync(0xffffffffu, y, d)); }
+        float* buf = red + (phase & 1u) * 64;
+        phase++;
+        if ((threadIdx.x & 31) == 0) { buf[threadIdx.x >> 5] = x; buf[32 + (threadIdx.x >> 5)] = y; }
+        __syncthreads();
+        return make_float2(fold(buf), fold(buf + 32));
+    }
+};
 // x = S.x, the residual lives in S.b, P and T in `pt` (2 x np floats); red = 128 floats
 template <int T>
 __device__ void compact_cg_k(const CompactSm& S, float* pt, float* red, unsigned& phase) {
@@ -383,10 +424,9 @@ __device__ void compact_cg_k(const CompactSm& S, float* pt, float* red, unsigned
 }
 
 // the same CG with every vector in registers (at most 1024 rows): thread t owns the rows t, t + T, ... of compact_cg's threads
-template <int T>
+template <int T, class Sum>
 __device__ void compact_cg_regk(const CompactSm& S, float* Psm, float* red, unsigned& phase) {
     constexpr int K = 1024 / T;
-    using Sum = CgSum<T>;
     const int n = S.n, np = S.np, tid = threadIdx.x;
     float X[K], R[K], dg[K], di[K], Pv[K], cm[K][3], cp[K][3], s[K], zv[K], acc[K], acc2[K];
     unsigned col[K][6];
@@ -563,7 +603,7 @@ struct ClLevelS {
 };
 __global__ void __launch_bounds__(CL_THREADS, 1) mg_cluster_kernel(const __grid_constant__ ClusterParams P) {
     extern __shared__ __align__(16) unsigned char clsm[];
-    __shared__ float red[128];
+    __shared__ __align__(16) float red[128];
     __shared__ ClLevelS lvs[CL_MAX_LEVELS];
     __shared__ float sW, sOmw, sAlpha;
     __shared__ int sNOps;
@@ -761,8 +801,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) mg_cluster_kernel(const __grid_
                 __syncthreads();
                 const long long g1 = trace ? clock64() : 0;
                 if (cgCompat) {
-                    if (D.n <= 1024) compact_cg_regk<CL_THREADS>(S, pt, red, phase);
+                    if (D.n <= 1024) compact_cg_regk<CL_THREADS, CgSum<CL_THREADS>>(S, pt, red, phase);
                     else compact_cg_k<CL_THREADS>(S, pt, red, phase);
+                } else if (D.n <= 1024) {
+                    // every vector of the solve in registers, all 16 warps, three bar.sync per iteration
+                    compact_cg_regk<CL_THREADS, CgSumFast<CL_THREADS>>(S, pt, red, phase);
                 } else {
                     if (t < CG_FAST_THREADS) compact_cg_fast(S, pt, red, phase);
                     __syncthreads();

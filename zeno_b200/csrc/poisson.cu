@@ -2162,15 +2162,64 @@ struct Solver {
     // slab decomposition, level 0. Whole ghost LEAVES are exchanged, so eight colour passes fit between two exchanges:
     // what pass k computes in the ghost layer is wrong only within k voxels of its far face, and the owned DOFs read
     // just the nearest ghost plane. Per application: r in, the iterate after pre-smoothing, the coarse right-hand side.
+    // The eight colour passes between two exchanges as ONE launch of the cycle kernel (a program of level-0 ops only; grid
+    // barriers between the passes instead of launch boundaries, leaf records in shared memory, iterate read through L1).
+    DBuf<uint8_t> ddProg;
+    DBuf<unsigned> ddBarrier;
+    std::vector<uint8_t> ddHost;
+    int ddGrid = 0, ddDown = 0, ddUp = 0;
+    bool ddPassesReady = false;
+    void dd_passes_prepare(int n) {
+        ddPassesReady = false;
+        if (getenv("FLIPB200_DD_PASS_KERNELS")) return;
+        int dev = 0, sms = 0, perSm = 0, coop = 0;
+        FB_CUDA(cudaGetDevice(&dev));
+        FB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        FB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, mg_cycle_kernel, BOT_THREADS, CYC_GRID_SCRATCH));
+        if (!coop || perSm < 1) return;
+        ddGrid = std::min(sms, (int)cycleGridMax);
+        ddHost.clear();
+        ddHost.push_back(OP_ZERO_RED); ddHost.push_back(OP_BLACK);                              // down: the sweep from a zero guess,
+        for (int i = 1; i < n; i++) { ddHost.push_back(OP_RED); ddHost.push_back(OP_BLACK); }   // then red-first sweeps
+        ddDown = (int)ddHost.size();
+        for (int i = 0; i < n; i++) { ddHost.push_back(OP_BLACK); ddHost.push_back(OP_RED); }   // up: black-first sweeps
+        ddUp = (int)ddHost.size() - ddDown;
+        ddProg.alloc(ddHost.size(), w->stream);
+        FB_CUDA(cudaMemcpyAsync(ddProg.p, ddHost.data(), ddHost.size(), cudaMemcpyHostToDevice, w->stream));
+        ddBarrier.alloc(1, w->stream);
+        ddPassesReady = true;
+    }
+    void launch_dd_passes(float* x, const float* b, bool down) {
+        Level& L = *levels[0];
+        CycleParams P;
+        memset(&P, 0, sizeof(P));
+        P.lv[0].v = view_of(L);
+        P.lv[0].x = x; P.lv[0].b = const_cast<float*>(b); P.lv[0].n = L.n;
+        P.lv[0].xoff = P.lv[0].boff = -1; P.lv[0].bReadOnly = 1;
+        P.prog = down ? ddProg.p : ddProg.p + ddDown; P.nOps = down ? ddDown : ddUp;
+        P.nLevels = 1; P.compactFirst = 1; P.gridOnly = 1;
+        P.w = 1.2f; P.oneMinusW = 1.0f - 1.2f; P.prolongAlpha = 1.0f;
+        P.barrier = ddBarrier.p;
+        P.cacheInfo = 1; P.l1Loads = 1;
+        FB_CUDA(cudaMemsetAsync(ddBarrier.p, 0, sizeof(unsigned), w->stream));
+        void* args[] = {(void*)&P};
+        FB_LAUNCH(w, "mg_dd_passes", (uint64_t)L.numDof * 6 * P.nOps)
+            FB_CUDA(cudaLaunchCooperativeKernel((const void*)mg_cycle_kernel, dim3(ddGrid), dim3(BOT_THREADS), args, CYC_GRID_SCRATCH, w->stream));
+        check_launch("mg_dd_passes");
+    }
     void dd_cycle0(float* x, const float* b, int n) {
         Level& L = *levels[0];
         Solver& G = *coarse;
         Level& P = *G.levels[0];
         const float wS = 1.2f;
         dd_refresh(w, {DDArray{const_cast<float*>(b), LEAF * 4}}, 1);
-        FB_LAUNCH(w, "mg_zero_red", (uint64_t)L.numDof * 10) zero_red_kernel<<<L.n, 512, 0, w->stream>>>(view_of(L), x, b, wS);
-        rbgs_pass(L, x, b, 1, wS);
-        for (int i = 1; i < n; i++) rbgs(L, x, b, true, wS);
+        if (ddPassesReady && n == 4) launch_dd_passes(x, b, true);
+        else {
+            FB_LAUNCH(w, "mg_zero_red", (uint64_t)L.numDof * 10) zero_red_kernel<<<L.n, 512, 0, w->stream>>>(view_of(L), x, b, wS);
+            rbgs_pass(L, x, b, 1, wS);
+            for (int i = 1; i < n; i++) rbgs(L, x, b, true, wS);
+        }
         dd_refresh(w, {DDArray{x, LEAF * 4}}, 1);
         P.b.zero();
         residual_restrict(L, P, x, b, L.ownLo, L.ownHi);
@@ -2179,7 +2228,8 @@ struct Solver {
           G.mu_cycle_precond(P.x.p, P.b.p, 0, n, true);
           G.mu_cycle_precond(P.x.p, P.b.p, 0, n, false); }
         prolong(L, P, x, 1.0f);
-        for (int i = 0; i < n; i++) rbgs(L, x, b, false, wS);
+        if (ddPassesReady && n == 4) launch_dd_passes(x, b, false);
+        else for (int i = 0; i < n; i++) rbgs(L, x, b, false, wS);
     }
     void mu_cycle_precond(float* x, const float* b, int level, int n, bool skipFirst) {
         if (level == 0 && dd) { dd_cycle0(x, b, n); return; }
@@ -2300,7 +2350,7 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
         }
         S.levels.push_back(std::move(Lp));  // level 0 iterates on the PCG vectors; it owns no x/b
     }
-    if (dd) S.dd_build_coarse();
+    if (dd) { S.dd_build_coarse(); S.dd_passes_prepare(4); }
     else {
         while (S.levels.back()->numDof > MAX_COARSEST) S.coarsen();
         S.build_coarsest();
