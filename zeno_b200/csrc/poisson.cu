@@ -26,7 +26,7 @@ constexpr int RED_THREADS = 256;
 // dependent mask -> nbr27 -> flags[nbr] chain): the six face-neighbour slots and
 // bit0 = leaf has a DOF, bit1 = all face coefficients this leaf reads are the default (-term)
 struct __align__(128) LeafInfo { int nb[6]; uint32_t flags; uint32_t pad; uint64_t mask[8]; uint64_t pad2[4]; };
-enum { LI_ANY = 1, LI_CONST = 2, LI_DIAG = 4 };  // LI_DIAG: diag / invdiag read as the default on the whole leaf
+enum { LI_ANY = 1, LI_CONST = 2, LI_DIAG = 4, LI_OCT_SHIFT = 8 };  // LI_DIAG: diag / invdiag read as the default on the whole leaf
 
 struct Level {
     TopoPtr topo;
@@ -36,6 +36,7 @@ struct Level {
     DBuf<uint64_t> dof;
     DBuf<float> diag, invdiag, xe, ye, ze;
     DBuf<uint8_t> flags;   // bit0 diag, bit1 x, bit2 y, bit3 z read as the default
+    bool hasParent = false;   // LeafInfo::pad / octant bits are set (leaf_parent_kernel)
     DBuf<LeafInfo> info;
     DBuf<float> x, b;
     // candidate leaves of the next coarser level, listed speculatively while the DOF count is being read back
@@ -398,6 +399,90 @@ __device__ __forceinline__ void rbgs_leaf_cached(const LevelView& L, float* x, c
     const float tt = __fmul_rn(__fmul_rn(__fsub_rn(bi, od), inv), w);
     if (on) x[i] = __fmaf_rn(xi, oneMinusW, tt);
 }
+// zero_red_leaf with the record in shared memory: t in [0,256) owns the z pair 2t, 2t + 1 (one red, one black voxel)
+template <int M>
+__device__ __forceinline__ void zero_red_pair_cached(const LevelView& L, float* x, const float* b, int leaf, int t, float w,
+                                                     const CachedInfo& ci, float invDefault) {
+    const int X = t >> 5, Y = (t >> 2) & 7, Zp = t & 3;
+    const int h = (X + Y) & 1;                       // the red voxel of the pair: z = 2 Zp + h
+    const size_t i = (size_t)leaf * LEAF + 2 * t;
+    float v = 0.f;
+    if ((ci.mask[X] >> ((Y << 3) | (Zp << 1) | h)) & 1ull) {
+        const float inv = (ci.flags & LI_DIAG) ? invDefault : __ldg(&L.invdiag[i + h]);
+        v = __fmul_rn(__fmul_rn(ldb<M>(&b[i + h]), inv), w);
+    }
+    *reinterpret_cast<float2*>(x + i) = h ? make_float2(0.f, v) : make_float2(v, 0.f);
+}
+// prolongation of one fine leaf with its record in shared memory: t in [0,256) owns the z-adjacent voxels 2t, 2t + 1, which
+// share their coarse parent; the parent leaf and octant come from the record (leaf_parent_kernel). Arithmetic = prolong_voxel.
+template <int M>
+__device__ __forceinline__ void prolong_pair_cached(const LevelView& C, float* fine, const float* coarse, int leaf, int t, float alpha,
+                                                    const CachedInfo& ci) {
+    const int cl = (int)ci.pad;
+    if (cl < 0 || !(ci.flags & LI_ANY)) return;
+    const int X = t >> 5, Y = (t >> 2) & 7, Zp = t & 3;
+    const unsigned bits = (unsigned)(ci.mask[X] >> ((Y << 3) | (Zp << 1))) & 3u;
+    if (!bits) return;
+    const uint32_t oct = ci.flags >> LI_OCT_SHIFT;
+    const int co = ((((oct >> 2) & 1) * 4 + (X >> 1)) << 6) | ((((oct >> 1) & 1) * 4 + (Y >> 1)) << 3) | ((oct & 1) * 4 + Zp);
+    if (!dof_bit(C, cl, co)) return;
+    const float cv = __fmul_rn(alpha, ldx<M>(&coarse[(size_t)cl * LEAF + co]));
+    float2* fp = reinterpret_cast<float2*>(fine + (size_t)leaf * LEAF + 2 * t);
+    float2 f = *fp;
+    if (bits & 1u) f.x = __fadd_rn(f.x, cv);
+    if (bits & 2u) f.y = __fadd_rn(f.y, cv);
+    *fp = f;
+}
+// residual + restriction of one fine leaf without shared memory or block barriers: the 256 threads of the leaf are laid out
+// so that a 2 x 2 x 2 block of fine voxels sits in one warp (lane bit 4 = x parity, bit 2 = y parity, a thread owns the z pair);
+// the thread with even x and y collects the eight residuals by shuffle and adds the active ones in the reference's (ii, jj, kk)
+// order (uaamg.cpp:1773-1833). Arithmetic = the tile version above / residual_restrict_kernel.
+template <int M>
+__device__ __forceinline__ void resid_restrict_cached(const LevelView& F, const float* x, const float* b, bool bReadOnly, float* coarse,
+                                                      int leaf, int t, const CachedInfo& ci) {
+    const LeafInfo li = cached_info(ci);
+    if (!(li.flags & LI_ANY)) return;   // uniform over the leaf's 256 threads (whole warps)
+    const int wq = t >> 5, l = t & 31;
+    const int X = ((wq >> 1) << 1) | (l >> 4), Y = ((wq & 1) << 2) | ((l >> 2) & 3), Zp = l & 3;
+    const int off0 = (X << 6) | (Y << 3) | (Zp << 1);
+    const size_t i0 = (size_t)leaf * LEAF + off0;
+    const unsigned bits = (unsigned)(ci.mask[X] >> ((Y << 3) | (Zp << 1))) & 3u;
+    const float2 bv = bReadOnly ? __ldg(reinterpret_cast<const float2*>(b + i0)) : *reinterpret_cast<const float2*>(b + i0);
+    const Nbr nb = nbr_of(li);
+    float r[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int off = off0 + h;
+        const float od = (li.flags & LI_CONST) ? offdiag<true, M>(F, x, leaf, off, nb) : offdiag<false, M>(F, x, leaf, off, nb);
+        const float dg = (li.flags & LI_DIAG) ? __fmul_rn(6.0f, F.term) : __ldg(&F.diag[i0 + h]);
+        const float ax = __fmaf_rn(ldx<M>(&x[i0 + h]), dg, od);
+        r[h] = ((bits >> h) & 1u) ? __fsub_rn(h == 0 ? bv.x : bv.y, ax) : 0.f;
+    }
+    // (ii, jj) = (0,0) own, (0,1) lane ^ 4, (1,0) lane ^ 16, (1,1) lane ^ 20
+    float rr[4][2];
+    unsigned bb[4];
+    rr[0][0] = r[0]; rr[0][1] = r[1]; bb[0] = bits;
+#pragma unroll
+    for (int q = 1; q < 4; q++) {
+        const int m = ((q & 1) ? 4 : 0) | ((q & 2) ? 16 : 0);
+        rr[q][0] = __shfl_xor_sync(0xffffffffu, r[0], m);
+        rr[q][1] = __shfl_xor_sync(0xffffffffu, r[1], m);
+        bb[q] = __shfl_xor_sync(0xffffffffu, bits, m);
+    }
+    if ((l & 20) != 0) return;   // odd x or odd y: contributed through the shuffles
+    float sum = 0.f;
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++)
+            if ((bb[q] >> kk) & 1u) { sum = __fadd_rn(sum, rr[q][kk]); any = true; }
+    const int cl = (int)ci.pad;
+    if (!any || cl < 0) return;
+    const uint32_t oct = li.flags >> LI_OCT_SHIFT;
+    const int co = ((((oct >> 2) & 1) * 4 + (X >> 1)) << 6) | ((((oct >> 1) & 1) * 4 + (Y >> 1)) << 3) | ((oct & 1) * 4 + Zp);
+    coarse[(size_t)cl * LEAF + co] = __fmul_rn(sum, 0.125f);
+}
 // the first red pass of a sweep that starts from a zero guess (setGridToResultAfterFirstRBGS,
 // uaamg.cpp:1665-1731): every neighbour is 0, so off = ((0*c + 0*c) + ...) = 0 and
 // x_red = fma(0, 1-w, ((b - 0) * invdiag) * w); black voxels are set to 0. No neighbour traffic.
@@ -456,6 +541,16 @@ __device__ __forceinline__ void prolong_voxel(const LevelView& F, const LevelVie
     fine[i] = __fadd_rn(ldx<M>(&fine[i]), __fmul_rn(alpha, ldx<M>(&coarse[(size_t)cl * LEAF + co])));
 }
 
+// the coarse leaf a fine leaf restricts into / prolongs from (the fine leaf is one octant of it): slot in LeafInfo::pad,
+// octant (x, y, z half) in flags bits 8..10. One directory lookup per leaf and solve instead of one per voxel and transfer.
+__global__ void leaf_parent_kernel(TopoView ft, TopoView ct, LeafInfo* __restrict__ info) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= ft.n) return;
+    const int3 o = ft.origin[l];
+    const int cx = o.x >> 1, cy = o.y >> 1, cz = o.z >> 1;
+    info[l].pad = (uint32_t)topo_find(ct, cx, cy, cz);
+    info[l].flags |= (uint32_t)((((cx >> 2) & 1) << 2) | (((cy >> 2) & 1) << 1) | ((cz >> 2) & 1)) << LI_OCT_SHIFT;
+}
 // ---------------------------------------------------------------- per-leaf kernels (large levels)
 __global__ void leaf_info_kernel(TopoView t, const uint64_t* __restrict__ dof, const uint8_t* __restrict__ flags,
                                  LeafInfo* __restrict__ info) {
@@ -818,7 +913,7 @@ __device__ void coarse_cg(const CoarseELL& E, const float* rhsGrid, float* lhsGr
 enum { OP_ZERO_RED = 0, OP_RED = 1, OP_BLACK = 2, OP_RESID_RESTRICT = 3, OP_PROLONG = 4, OP_COARSE = 5 };
 constexpr int BOT_MAX_LEVELS = 6;
 constexpr int BOT_MAX_OPS = 400;
-struct BottomLevel { LevelView v; float* x; float* b; int n; int xoff, boff; int bReadOnly; };  // offsets (floats) into dynamic smem, -1 = global
+struct BottomLevel { LevelView v; float* x; float* b; int n; int xoff, boff; int bReadOnly; int hasParent; };  // offsets (floats) into dynamic smem, -1 = global
 struct BottomParams {
     BottomLevel lv[BOT_MAX_LEVELS];
     CoarseELL ell;
@@ -1334,7 +1429,15 @@ __global__ void __launch_bounds__(BOT_THREADS) mg_cycle_kernel(const __grid_cons
             if (P.trace && c == 0 && tid == 0) P.trace[k] = globaltimer();
             const BottomLevel& B = P.lv[li];
             const bool cached = P.cacheInfo && li < CY_CACHE_LEVELS;
-            if (code == OP_ZERO_RED) {
+            if (code == OP_ZERO_RED && cached) {
+                const float invDefault = __fdiv_rn(1.0f, __fmul_rn(6.0f, B.v.term));
+                int slot = tid >> 8, base = c * 4;
+                for (; base < B.n && slot < CY_CACHE_SLOTS; base += G * 4, slot += 4) {
+                    const int leaf = base + (tid >> 8);
+                    if (leaf < B.n) zero_red_pair_cached<M_GRID_L1>(B.v, B.x, B.b, leaf, tid & 255, P.w, sInfo[li][slot], invDefault);
+                }
+                for (int leaf = base + (tid >> 8); leaf < B.n; leaf += G * 4) { zero_red_leaf<M_GRID>(B.v, B.x, B.b, leaf, (tid & 255) * 2, P.w); zero_red_leaf<M_GRID>(B.v, B.x, B.b, leaf, (tid & 255) * 2 + 1, P.w); }
+            } else if (code == OP_ZERO_RED) {
                 for (int base = c * 2; base < B.n; base += G * 2) { int leaf = base + (tid >> 9); if (leaf < B.n) zero_red_leaf<M_GRID>(B.v, B.x, B.b, leaf, tid & 511, P.w); }
             } else if (code == OP_RED || code == OP_BLACK) {
                 // no block barrier inside a pass: warps run ahead into the next chunk, which is what keeps loads in
@@ -1356,7 +1459,14 @@ __global__ void __launch_bounds__(BOT_THREADS) mg_cycle_kernel(const __grid_cons
                 float* T = tiles + g * TILE;
                 float* R = sresGrid + g * LEAF;
                 int slot = g;
-                for (int base = c * 4; base < B.n; base += G * 4, slot += 4) {
+                int base = c * 4;
+                if (cached && B.hasParent) {   // chunks whose records are in shared memory: no tiles, no block barriers
+                    for (; base < B.n && slot < CY_CACHE_SLOTS; base += G * 4, slot += 4) {
+                        const int leaf = base + g;
+                        if (leaf < B.n) resid_restrict_cached<M_GRID_L1>(B.v, B.x, B.b, B.bReadOnly != 0, C.b, leaf, t, sInfo[li][slot]);
+                    }
+                }
+                for (; base < B.n; base += G * 4, slot += 4) {
                     const int leaf = base + g;
                     LeafInfo info;
                     bool live = false;
@@ -1391,6 +1501,15 @@ __global__ void __launch_bounds__(BOT_THREADS) mg_cycle_kernel(const __grid_cons
                 }
             } else if (code == OP_PROLONG) {
                 const BottomLevel& C = P.lv[li + 1];
+                if (cached && B.hasParent) {
+                    int slot = tid >> 8, base = c * 4;
+                    for (; base < B.n && slot < CY_CACHE_SLOTS; base += G * 4, slot += 4) {
+                        const int leaf = base + (tid >> 8);
+                        if (leaf < B.n) prolong_pair_cached<M_GRID_L1>(C.v, B.x, C.x, leaf, tid & 255, P.prolongAlpha, sInfo[li][slot]);
+                    }
+                    // what the cache does not hold (levels with more than CY_CACHE_SLOTS leaves per CTA): per voxel, through the directory
+                    for (int leaf = base + (tid >> 8); leaf < B.n; leaf += G * 4) { prolong_voxel<M_GRID>(B.v, C.v, B.x, C.x, leaf, (tid & 255) * 2, P.prolongAlpha); prolong_voxel<M_GRID>(B.v, C.v, B.x, C.x, leaf, (tid & 255) * 2 + 1, P.prolongAlpha); }
+                } else
                 for (int base = c * 2; base < B.n; base += G * 2) { int leaf = base + (tid >> 9); if (leaf < B.n) prolong_voxel<M_GRID>(B.v, C.v, B.x, C.x, leaf, tid & 511, P.prolongAlpha); }
             }
             k++;
@@ -1575,6 +1694,10 @@ struct Solver {
         std::unique_ptr<Level> Lp = coarsen_raw();
         finish_level(*Lp);
         alloc_vectors(*Lp);
+        Level& F = *levels.back();
+        FB_LAUNCH(w, "mg_leaf_parent", (size_t)F.n * 24) leaf_parent_kernel<<<(F.n + 127) / 128, 128, 0, w->stream>>>(F.topo->view(), Lp->topo->view(), F.info.p);
+        check_launch("leaf_parent");
+        F.hasParent = true;
         levels.push_back(std::move(Lp));
     }
     // slab decomposition: assemble level 1 globally, then build and keep the rest of the hierarchy replicated
@@ -2047,6 +2170,7 @@ struct Solver {
             P.lv[i].n = L.n;
             P.lv[i].xoff = P.lv[i].boff = -1;
             P.lv[i].bReadOnly = i == 0 ? 1 : 0;  // level 0 iterates on the caller's residual, never written in the launch
+            P.lv[i].hasParent = L.hasParent ? 1 : 0;
             if (i >= compactFirst) {
                 const CompactHost& H = compact[i - compactFirst];
                 P.cl[i] = CompactDev{H.n, H.np, H.nRed, H.hasChild ? 1 : 0, H.oInv, H.oMinus, H.oCols, H.oDiag, H.oParent, H.oChild,
