@@ -206,7 +206,9 @@ int flipb200_world_create(int device, float dx, flipb200_world** out) {
         w->device = device;
         w->dx = dx;
         FB_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
-        FB_CUDA(cudaHostAlloc((void**)&w->hostScratch, 1024, cudaHostAllocDefault));
+        FB_CUDA(cudaHostAlloc((void**)&w->hostScratch, 1024, cudaHostAllocMapped));
+        memset(w->hostScratch, 0, 1024);
+        FB_CUDA(cudaHostGetDevicePointer((void**)&w->hostScratchDev, w->hostScratch, 0));
         // keep freed blocks in the stream-ordered pool: per-substep temporaries are recycled
         cudaMemPool_t pool;
         FB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -231,7 +233,6 @@ int flipb200_world_destroy(flipb200_world* w) {
         dd_destroy(w);
         resolve_profile(w);
         for (auto e : w->evtPool) cudaEventDestroy(e);
-        if (w->p2gOverflowHost) cudaFreeHost(w->p2gOverflowHost);
         if (w->hostScratch) cudaFreeHost(w->hostScratch);
         if (w->copyStream) { cudaStreamSynchronize(w->copyStream); w->held.clear(); cudaStreamDestroy(w->copyStream); cudaEventDestroy(w->copyEvt); }
         cudaStream_t s = w->stream;

@@ -340,7 +340,7 @@ void p2g(World* w, float dx, int velExtraLayer) {
 
     DBuf<uint64_t> chMask((size_t)3 * n * 8, w->stream), topoMask((size_t)n * 8, w->stream), ring((size_t)n * 8, w->stream);
     if (!w->p2gOverflowHost) {
-        FB_CUDA(cudaHostAlloc((void**)&w->p2gOverflowHost, sizeof(int), cudaHostAllocDefault));
+        w->p2gOverflowHost = reinterpret_cast<int*>(w->hostScratch + 768);   // a word of the mapped scratch block
         *w->p2gOverflowHost = 0;
         w->p2gOverflow.alloc(1, w->stream);
     }
@@ -383,7 +383,7 @@ void p2g(World* w, float dx, int velExtraLayer) {
     union_extrapolate(w, velExtraLayer, nvel, chMask.p, nsdf.mask.p);
     finish_vec3(w, nvel, chMask.p);
 
-    FB_CUDA(cudaMemcpyAsync(w->p2gOverflowHost, overflow.p, 4, cudaMemcpyDeviceToHost, w->stream));   // checked by check_p2g_overflow
+    d2h_words(w, w->p2gOverflowHost, overflow.p, 4);   // checked by check_p2g_overflow
     vel = std::move(nvel);
     post = std::move(npost);
     sdf = std::move(nsdf);

@@ -1880,7 +1880,7 @@ struct Solver {
         {   // red row counts of all compact levels (= the last entry of each exclusive scan) in one host wait
             uint32_t* nr = reinterpret_cast<uint32_t*>(w->hostScratch);
             for (size_t i = 0; i < compact.size(); i++)
-                FB_CUDA(cudaMemcpyAsync(&nr[i], compact[i].redStart.p + levels[compactFirst + i]->n, 4, cudaMemcpyDeviceToHost, w->stream));
+                d2h_words(w, &nr[i], compact[i].redStart.p + levels[compactFirst + i]->n, 4);
             sync(w);
             for (size_t i = 0; i < compact.size(); i++) compact[i].nRed = (int)nr[i];
         }
@@ -1993,7 +1993,7 @@ struct Solver {
                 cl_assign_kernel<<<1, 1024, 0, w->stream>>>(levels[l]->info.p, levels[l]->n, clSize - 1, clHost[l].assign.p, clCounts.p + 2 * l);
         }
         check_launch("cl_assign");
-        if (clCandFirst < nl) FB_CUDA(cudaMemcpyAsync(w->hostScratch + 256, clCounts.p, (size_t)8 * nl, cudaMemcpyDeviceToHost, w->stream));
+        if (clCandFirst < nl) d2h_words(w, w->hostScratch + 256, clCounts.p, (size_t)8 * nl);
     }
     void emit_cl(std::vector<uint8_t>& ops, int li, int nb, int n, bool skipFirst) {
         auto put = [&](int code) { ops.push_back((uint8_t)(code | (li << 3))); };
