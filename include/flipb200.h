@@ -147,6 +147,16 @@ int flipb200_particles_add_dv(flipb200_world* w, float dvx, float dvy, float dvz
  * SPACE and survives when the sample is <= 0 (keep != 0, OpType KEEP) or >= 0 (OpType DEL); survivors' positions go through the
  * codec once more, as the reference's write-back does. */
 int flipb200_kill_particles_in_sdf(flipb200_world* w, int sdfGrid, int keep);
+/* FluidReseed (FF/nosys/FLIP_Reseed.cpp:8-16 -> FLIP_vdb::reseed_fluid, FF/FLIP_vdb.cpp:2047-2220): every voxel of
+ * a particle leaf whose LiquidSDF value at the centre is < dx and that holds <= 4 particles is topped up -- up to 16 jittered
+ * candidates from the reference's hash table (FF/FLIP_vdb.h:10-20), taken while the voxel holds < 8 when the SDF at the
+ * candidate is <= -dx and its octant is empty, with the StaggeredBoxSampler velocity of FLIPB200_VELOCITY there. Reads
+ * FLIPB200_LIQUID_SDF and FLIPB200_VELOCITY, replaces the particle store (same leaves). The reference starts the table at a
+ * std::random_device draw per TBB chunk (:2081-2084); here leaf (ox, oy, oz) starts at
+ *   h = seed ^ ox*73856093 ^ oy*19349663 ^ oz*83492791;  h ^= h>>16; h *= 0x7feb352d; h ^= h>>15; h *= 0x846ca68b; h ^= h>>16;
+ *   start = h % 21474836
+ * (uint32 arithmetic) and runs through its voxels in offset order exactly as the reference does inside a chunk. */
+int flipb200_fluid_reseed(flipb200_world* w, uint32_t seed);
 /* debug: keep / fetch the fp32 position (index space) and velocity before the codecs, in the
  * order of the particle store the advect call started from (codec caveat). */
 int flipb200_capture_precodec(flipb200_world* w, int on);

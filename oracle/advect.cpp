@@ -351,6 +351,94 @@ void node_KillParticlesInSDF(World& w, const FloatGrid& sdf, bool keep) {
     w.particles = std::move(out);
 }
 
+// ---- FluidReseed (FF/nosys/FLIP_Reseed.cpp:8-16 -> FLIP_vdb::reseed_fluid, FF/FLIP_vdb.cpp:2047-2220)
+// The jitter table (FF/FLIP_vdb.h:10-20): randomTable[i] = float(double(frand(i)) - 0.5), frand a 32-bit integer hash.
+static inline float reseed_frand(unsigned int i) {
+    unsigned int value = (i ^ 61) ^ (i >> 16);
+    value *= 9;
+    value ^= value << 4;
+    value *= 0x27d4eb2d;
+    value ^= value >> 15;
+    return (float)value / (float)4294967296;
+}
+static inline float reseed_table(uint64_t index) { return float(double(reseed_frand((unsigned int)(index % 21474836ull))) - 0.5); }
+// Where a leaf's draw sequence starts when the caller gives no explicit start. The reference takes std::random_device per TBB
+// chunk (:2081-2084) and runs on through the chunk's leaves, so ANY start is one of its executions for a one-leaf chunk; the
+// seeded variant (also what the CUDA path does) derives it from (seed, leaf origin), which makes leaves independent.
+uint64_t reseed_leaf_start(uint32_t seed, int ox, int oy, int oz) {
+    uint32_t h = seed ^ ((uint32_t)ox * 73856093u) ^ ((uint32_t)oy * 19349663u) ^ ((uint32_t)oz * 83492791u);
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    return (uint64_t)(h % 21474836u);
+}
+// One leaf of seed_leaf2 (:2087-2209). Per voxel in offset order: the voxel's particles are re-emitted through the write handles
+// (position decode -> encode once more, as in KillParticlesInSDF above), their octants (p > 0 per axis, :2128-2129) marked; then,
+// if the liquid SDF at the voxel centre is < dx and the voxel holds <= 4 particles (:2146), up to 16 trials while it holds < 8:
+// a jitter from three consecutive table entries, rejected when the SDF at that point is > -dx (:2157) or its octant is taken
+// (:2164), otherwise appended with the StaggeredBoxSampler velocity at that point (:2173). Every trial consumes three entries.
+// Both grids share the particles' cell-centred transform: indexToWorld = ijk * s, worldToIndex = xyz * (1 / s) in double
+// (math/Maps.h ScaleMap::applyMap / applyInverseMap), which does NOT round-trip to the integer for every ijk -- restated literally.
+static uint64_t reseed_leaf(const World& w, int l, uint64_t index, std::vector<uint16_t>& P, std::vector<uint16_t>& V,
+                            std::array<uint32_t, 512>& ends) {
+    const Points& in = w.particles;
+    const float dx = w.dx;
+    const double s = double(dx), inv = 1.0 / s;
+    const Coord o = in.origins[l];
+    uint32_t emitted = 0;
+    for (int off = 0; off < 512; off++) {
+        const uint32_t b = off ? in.voxelEnd[l][off - 1] : 0u, e = in.voxelEnd[l][off];
+        unsigned occ = 0;
+        uint32_t here = 0;
+        for (uint32_t i = b; i < e; i++) {
+            const size_t gi = in.leafBegin[l] + i;
+            const float px = fxpt16_decode(in.P[3 * gi]), py = fxpt16_decode(in.P[3 * gi + 1]), pz = fxpt16_decode(in.P[3 * gi + 2]);
+            occ |= 1u << (((pz > 0.f) << 2) | ((py > 0.f) << 1) | (px > 0.f));
+            P.push_back(fxpt16_encode(px)); P.push_back(fxpt16_encode(py)); P.push_back(fxpt16_encode(pz));
+            for (int a = 0; a < 3; a++) V.push_back(half_encode(half_decode(in.v[3 * gi + a])));
+            emitted++; here++;
+        }
+        const int vx = o.x + (off >> 6), vy = o.y + ((off >> 3) & 7), vz = o.z + (off & 7);
+        const double wx = double(vx) * s, wy = double(vy) * s, wz = double(vz) * s;
+        const float phi = box_sample_f64(w.liquidSDF, 0, wx * inv, wy * inv, wz * inv);
+        if (phi < dx && here <= 4) {
+            for (int trial = 0; here < 8 && trial < 16; trial++) {
+                const float jx = reseed_table(index++), jy = reseed_table(index++), jz = reseed_table(index++);
+                const double qx = double(jx) * s + wx, qy = double(jy) * s + wy, qz = double(jz) * s + wz;
+                const double ix = qx * inv, iy = qy * inv, iz = qz * inv;
+                const float phi2 = box_sample_f64(w.liquidSDF, 0, ix, iy, iz);
+                if (phi2 > -dx) continue;
+                const unsigned sv = ((double(jz) > 0) << 2) | ((double(jy) > 0) << 1) | (double(jx) > 0);
+                if (occ & (1u << sv)) continue;
+                occ |= 1u << sv;
+                const float vel[3] = {box_sample_f64(w.velocity, 0, ix + 0.5, iy, iz), box_sample_f64(w.velocity, 1, ix, iy + 0.5, iz),
+                                      box_sample_f64(w.velocity, 2, ix, iy, iz + 0.5)};
+                P.push_back(fxpt16_encode(jx)); P.push_back(fxpt16_encode(jy)); P.push_back(fxpt16_encode(jz));
+                for (int a = 0; a < 3; a++) V.push_back(half_encode(vel[a]));
+                emitted++; here++;
+            }
+        }
+        ends[off] = emitted;
+    }
+    return index;
+}
+// leafStart: one draw-sequence start per particle leaf (store order), or nullptr for reseed_leaf_start(seed, origin);
+// leafEnd (optional) receives where each leaf's sequence ended -- what a following leaf of the same TBB chunk starts from.
+void node_FluidReseed(World& w, uint32_t seed, const uint64_t* leafStart, uint64_t* leafEnd) {
+    const Points& in = w.particles;
+    Points out;
+    out.dir = in.dir;
+    out.origins = in.origins;
+    out.voxelEnd.resize(in.leafCount());
+    for (int l = 0; l < in.leafCount(); l++) {
+        out.leafBegin.push_back(out.P.size() / 3);
+        const Coord o = in.origins[l];
+        const uint64_t start = leafStart ? leafStart[l] : reseed_leaf_start(seed, o.x, o.y, o.z);
+        const uint64_t end = reseed_leaf(w, l, start, out.P, out.v, out.voxelEnd[l]);
+        if (leafEnd) leafEnd[l] = end;
+    }
+    out.leafBegin.push_back(out.P.size() / 3);
+    w.particles = std::move(out);
+}
+
 // FLIP_vdb::point_integrate_vector, channel "vel" (FF/FLIP_vdb.cpp:3492-3535): v is read as Vec3R (half -> float -> double),
 // dv (a Vec3R built from the node's float vec3) is added in double, and the sum goes back through the Vec3f write handle:
 // double -> float (round to nearest) -> half (TruncateCodec, round to nearest even). Positions are untouched.

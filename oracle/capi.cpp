@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- see flip_oracle.h.
 // Flat C entry points so tests/ and bench.py can drive the oracle through ctypes.
 // The argument layout mirrors include/flipb200.h so one Python harness drives both.
+#include <random>
 #include "flip_oracle.h"
 #include <chrono>
 #include <cstdio>
@@ -146,6 +147,18 @@ int orc_kill_particles(void* wp, int sdfGrid, int keep) {
     if (!g) return 1;
     node_KillParticlesInSDF(*w, *g, keep != 0);
     return 0;
+}
+// leafStart / leafEnd: nullable, one entry per particle leaf (see node_FluidReseed)
+int orc_fluid_reseed(void* wp, uint32_t seed, const uint64_t* leafStart, uint64_t* leafEnd) {
+    node_FluidReseed(*static_cast<World*>(wp), seed, leafStart, leafEnd);
+    return 0;
+}
+uint64_t orc_reseed_leaf_start(uint32_t seed, int ox, int oy, int oz) { return reseed_leaf_start(seed, ox, oy, oz); }
+// the start the seeded build of the reference draws for a TBB chunk: uniform_int_distribution(0, 21474836)(mt19937(seed)), FF/FLIP_vdb.cpp:2081-2084
+uint64_t orc_reseed_chunk_start(uint32_t seed) {
+    std::uniform_int_distribution<> intdistrib(0, 21474836);
+    std::mt19937 gen(seed);
+    return (uint64_t)(size_t)intdistrib(gen);
 }
 int orc_particles_add_dv(void* wp, float x, float y, float z) { node_ParticleAddDV(*static_cast<World*>(wp), x, y, z); return 0; }
 int orc_g2p_advect(void* wp, float dt, float dx, int rkOrder, float picSmoothness) { node_G2P_Advector(*static_cast<World*>(wp), dt, dx, rkOrder, picSmoothness); return 0; }

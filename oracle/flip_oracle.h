@@ -72,6 +72,10 @@ void node_SubtractPressureGradient(World& w, float dt, float dx, int velExtraLay
 // FF/nosys/KillParticles.cpp:13-158: keep the particles whose KillerSDF sample is <= 0 (keep) / >= 0 (delete)
 void node_KillParticlesInSDF(World& w, const FloatGrid& sdf, bool keep);
 
+// FF/nosys/FLIP_Reseed.cpp:8-16 -> FLIP_vdb::reseed_fluid (FF/FLIP_vdb.cpp:2047-2220)
+void node_FluidReseed(World& w, uint32_t seed, const uint64_t* leafStart, uint64_t* leafEnd);
+uint64_t reseed_leaf_start(uint32_t seed, int ox, int oy, int oz);
+
 // FF/nosys/ParticleAddGravity.cpp:9-19 -> FLIP_vdb::point_integrate_vector (FF/FLIP_vdb.cpp:3492-3535)
 void node_ParticleAddDV(World& w, float dvx, float dvy, float dvz);
 

@@ -149,6 +149,23 @@ class OracleWorld:
         if rc != 0:
             raise RuntimeError("KillParticlesInSDF failed")
 
+    def FluidReseed(self, seed: int = 0, leaf_start=None, want_leaf_end: bool = False):
+        """leaf_start: optional uint64 array, the draw-sequence start of every particle leaf (store order); default = the seeded
+        per-leaf hash. Returns where every leaf's sequence ended when want_leaf_end."""
+        nl = self.particles_info()[0]
+        ls = None if leaf_start is None else _c(leaf_start, np.uint64)
+        le = np.zeros(max(nl, 1), np.uint64) if want_leaf_end else None
+        rc = self.lib.orc_fluid_reseed(self.h, C.c_uint32(seed & 0xffffffff), None if ls is None else _p(ls), None if le is None else _p(le))
+        if rc != 0:
+            raise RuntimeError("FluidReseed failed: " + self._err())
+        return le[:nl] if want_leaf_end else None
+
+    def _err(self):
+        try:
+            return (self.lib.orc_last_error() or b"").decode()
+        except Exception:
+            return ""
+
     def ParticleAddDV(self, x, y, z):
         rc = self.lib.orc_particles_add_dv(self.h, C.c_float(x), C.c_float(y), C.c_float(z))
         if rc != 0:

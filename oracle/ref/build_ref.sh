@@ -72,6 +72,7 @@ for s in "$FF/FLIP_vdb.cpp" "$FF/simd_vdb_poisson_uaamg.cpp" "$FF/vdb_velocity_e
   FL="$FFFLAGS"
   USES_PLUGIN=""
   case "$(basename $s)" in
+    FLIP_vdb.cpp) FL="$FFFLAGS -include random -include $HERE/shims/seeded_random.h"; [ "$HERE/shims/seeded_random.h" -nt "$o" ] && rm -f "$o" ;;   # std::random_device -> a seeded stand-in (reseed / emitter)
     plugin_nodes_test.cpp) FL="$NODEFLAGS"; USES_PLUGIN=1 ;;
     ref_nodes_test.cpp) FL="$COMMON -mavx -mfma -DZENO_APIFREE -I$HERE/shims/zeno_nodes -I$REF/projects/zenvdb/include -I$REF/zeno/include -I$FF -I$REF/projects/zenvdb -I$HERE/../../include" ;;
     ref_driver.cpp) USES_PLUGIN=1 ;;

@@ -55,6 +55,7 @@ namespace zeno { using namespace ::zeno; }
 #include "nosys/KillParticles.cpp"
 #include "nosys/ParticleAddGravity.cpp"     // ParticleAddDV
 #include "nosys/G2P_Advector.cpp"           // the plain advector
+#include "nosys/FLIP_Reseed.cpp"            // FluidReseed
 #include "VDBRenormalize.cpp"               // projects/zenvdb: VDBRenormalizeSDF
 }  // namespace refnodes
 #undef defNodeClass
@@ -63,6 +64,9 @@ namespace zeno { using namespace ::zeno; }
 #include "../../include/flipb200.h"   // grid ids only
 
 namespace { std::string g_err; }
+#include "shims/seeded_random.h"            // flipref::seed(): what FLIP_vdb.cpp's std::random_device returns in this build
+#undef random_device
+#define NH_SET_SEED(s) (flipref::seed() = (s))
 #define NH_FN(name) rn_##name
 #define NH_REGISTRY ::zeno::refNodeRegistry()
 #include "node_harness.inc"

@@ -8,6 +8,7 @@
 (2) live: when oracle/_ref/libflipref.so is present (this container, and the GPU box: the .so travels),
     a second seeded case is run through both on the spot.
 """
+import ctypes as C
 import numpy as np
 import pytest
 
@@ -306,3 +307,125 @@ def test_smooth_sdf_oracle_plugin_and_reference_node(oracle_lib, width, iteratio
     util.compare_grids(orc, ref, "VDBSmoothSDF: oracle vs the reference node", tol=0.0)
     util.compare_grids(plg, orc, "VDBSmoothSDF: plugin node vs oracle", tol=0.0)
     assert not np.array_equal(scenes.canonical_grid(before)["values"], scenes.canonical_grid(ref)["values"])
+
+
+def _leaf_slices(p):
+    counts = p["voxel_end"][:, 511].astype(np.int64)
+    begin = np.concatenate([[0], np.cumsum(counts)])
+    return begin
+
+
+def _one_leaf(p, i):
+    b = _leaf_slices(p)
+    return {"origins": p["origins"][i:i + 1], "voxel_end": p["voxel_end"][i:i + 1], "P": p["P"][b[i]:b[i + 1]], "v": p["v"][b[i]:b[i + 1]]}
+
+
+def _same_leaf(a, i, b, j):
+    ba, bb = _leaf_slices(a), _leaf_slices(b)
+    return (np.array_equal(a["origins"][i], b["origins"][j]) and np.array_equal(a["voxel_end"][i], b["voxel_end"][j])
+            and np.array_equal(a["P"][ba[i]:ba[i + 1]], b["P"][bb[j]:bb[j + 1]]) and np.array_equal(a["v"][ba[i]:ba[i + 1]], b["v"][bb[j]:bb[j + 1]]))
+
+
+def _reseed_scene(seed=5, ppc=3, side=20, W=2):
+    """A 20^3-voxel block (27 particle leaves, all inside one 128^3 node so that tree order == store order) at 3 particles per
+    voxel. FLIP_P2G's liquid SDF never goes below about -0.8 dx, and the reseeder only emits where it is <= -dx (the packaged
+    graph renormalises it first), so the worlds get an analytic SDF of the block on the P2G topology: depth in voxels below the
+    block's faces, with a ripple so that candidate acceptance is not uniform."""
+    from zeno_b200 import scenes
+    pos, vel, dx = scenes.dam_break_points(64, seed=seed, ppc=ppc, side=side, W=W, random_velocity=True)
+    return pos, vel * np.float32(0.3), dx, (W, side)
+
+
+def _analytic_liquid_sdf(grid, dx, W, side):
+    g = {k: np.array(v, copy=True) for k, v in grid.items()}
+    o = g["origins"].astype(np.float64)                                  # [n,3]
+    off = np.arange(512)
+    loc = np.stack([off >> 6, (off >> 3) & 7, off & 7], axis=1).astype(np.float64)  # [512,3]
+    x = o[:, None, :] + loc[None, :, :]                                  # voxel centres, index space
+    c, h = W + side / 2.0 - 0.5, side / 2.0
+    d = np.max(np.abs(x - c) - h, axis=2)                                # < 0 inside the block
+    d += 0.35 * np.sin(1.7 * x[..., 0] + 0.9 * x[..., 1]) * np.cos(1.3 * x[..., 2])
+    g["values"] = (d * dx).astype(np.float32).reshape(g["values"].shape)
+    return g
+
+
+def _reseed_worlds(classes, seed=5):
+    pos, vel, dx, (W, side) = _reseed_scene(seed=seed)
+    worlds = [cls(dx) for cls in classes]
+    for w in worlds:
+        w.PrimToVDBPointDataGrid(pos, vel)
+        w.FLIP_P2G(dx, 3)
+    sdf = _analytic_liquid_sdf(worlds[-1].get_grid("LiquidSDF"), dx, W, side)
+    vel = worlds[-1].get_grid("Velocity")   # one velocity field for all (the reference's own P2G sums in another order: last bits differ)
+    for w in worlds:
+        w.set_grid("LiquidSDF", sdf)
+        w.set_grid("Velocity", vel)
+    return worlds, dx
+
+
+@pytest.mark.parametrize("threads", [1, 0], ids=["one_thread", "all_threads"])
+def test_fluid_reseed_oracle_vs_reference_node(oracle_lib, threads):
+    """FluidReseed (FF/nosys/FLIP_Reseed.cpp -> FLIP_vdb::reseed_fluid, FF/FLIP_vdb.cpp:2047-2220), the REAL node class in the
+    seeded build of the reference (std::random_device replaced by a fixed seed at compile time, oracle/ref/shims/seeded_random.h;
+    the sources are untouched). The reference starts its jitter table once per TBB chunk and runs on through the chunk's leaves,
+    and the chunking is the scheduler's business; so every leaf of its result must be what the oracle's per-leaf restatement gives
+    when started EITHER at the chunk start the seed implies OR where the previous leaf ended. Code-for-code equality, every leaf."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "rn_fluid_reseed"):
+        pytest.skip("oracle/_ref with the FluidReseed reference node is not available here")
+    from oracle.pyoracle import OracleWorld, RefNodeWorld
+    seed = 20240
+    lib = pyoracle.load()
+    lib.orc_reseed_chunk_start.restype = C.c_uint64
+    s0 = int(lib.orc_reseed_chunk_start(C.c_uint32(seed)))
+    (rw, ow), dx = _reseed_worlds((RefNodeWorld, OracleWorld))
+    before = ow.get_particles()
+    util.compare_particles(rw.get_particles(), before, "reseed input: reference vs oracle store")
+    try:
+        pyoracle.ref_set_threads(threads)
+        rw.FluidReseed(seed)
+    finally:
+        pyoracle.ref_set_threads(0)
+    ref = rw.get_particles()
+    n0, n1 = before["P"].shape[0], ref["P"].shape[0]
+    assert n1 > n0 * 1.5, f"the scene must make the reseeder work: {n0} -> {n1} particles"
+    assert np.array_equal(ref["origins"], before["origins"]), "the reference keeps the leaf set (store order == tree order inside one 128^3 block)"
+    # the oracle, one leaf at a time on the same grids
+    lw = OracleWorld(dx)
+    for g in ("LiquidSDF", "Velocity"):
+        lw.set_grid(g, ow.get_grid(g))
+    nl = before["origins"].shape[0]
+    prev_ends = set()
+    chunk_starts = 0
+    for i in range(nl):
+        ok_ends = set()
+        for c in [s0] + sorted(prev_ends - {s0}):
+            lw.set_particles(_one_leaf(before, i))
+            end = lw.FluidReseed(0, leaf_start=np.array([c], np.uint64), want_leaf_end=True)
+            if _same_leaf(lw.get_particles(), 0, ref, i):
+                ok_ends.add(int(end[0]))
+                chunk_starts += int(c == s0 and int(end[0]) != c)
+        assert ok_ends, (f"leaf {i} (origin {before['origins'][i]}) of the reference's result matches the oracle neither from the chunk start {s0} "
+                         f"nor from the previous leaf's end {sorted(prev_ends)}")
+        prev_ends = ok_ends
+    assert chunk_starts >= 1
+
+
+def test_fluid_reseed_plugin_node_equals_oracle(oracle_lib):
+    """The drop-in's FluidReseed node (oracle behind the C ABI) against the oracle, both with the seeded per-leaf starts of
+    include/flipb200.h: identical stores."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "pn_fluid_reseed"):
+        pytest.skip("oracle/_ref with the plugin-node harness is not available here")
+    from oracle.pyoracle import OracleWorld, PluginWorld
+    (pw, ow), dx = _reseed_worlds((PluginWorld, OracleWorld), seed=6)
+    n0 = ow.particles_info()[1]
+    for w in (pw, ow):
+        w.FluidReseed(77)
+    assert ow.particles_info()[1] > 1.5 * n0
+    util.compare_particles(pw.get_particles(), ow.get_particles(), "FluidReseed: plugin node vs oracle")
+    # a second call tops up nothing where every voxel already holds > 4 particles or every octant is taken: the store stops growing
+    n1 = ow.particles_info()[1]
+    ow.FluidReseed(78)
+    n2 = ow.particles_info()[1]
+    assert n1 <= n2 < n1 * 1.2

@@ -114,3 +114,46 @@ def test_smooth_sdf_matches_oracle(gpu_lib, oracle_lib):
         w.VDBSmoothSDF("LiquidSDF", 2, 2)
     util.compare_grids(gw.get_grid("LiquidSDF"), ow.get_grid("LiquidSDF"), "VDBSmoothSDF vs oracle", tol=0.0, check_inactive=False)
     gw.close()
+
+
+@pytest.mark.parametrize("seed", [6, 31])
+def test_fluid_reseed_matches_oracle(gpu_lib, oracle_lib, seed):
+    """FluidReseed (FF/nosys/FLIP_Reseed.cpp -> FLIP_vdb::reseed_fluid): the oracle's restatement is pinned leaf by leaf against the
+    reference's own node class in the seeded build (tests/test_ref_pin_cpu.py); here the CUDA kernels against the oracle with the
+    same per-leaf draw starts (include/flipb200.h): identical stores, and the topped-up store is a valid input of FLIP_P2G."""
+    from oracle.pyoracle import OracleWorld
+    from tests.test_ref_pin_cpu import _reseed_worlds
+    from zeno_b200 import abi
+    (gw, ow), dx = _reseed_worlds((abi.World, OracleWorld), seed=seed)
+    n0 = ow.particles_info()[1]
+    for w in (gw, ow):
+        w.FluidReseed(1000 + seed)
+    n1 = ow.particles_info()[1]
+    assert n1 > 1.5 * n0, f"the scene must make the reseeder work: {n0} -> {n1}"
+    a = scenes.canonical_particles(gw.get_particles())
+    b = scenes.canonical_particles(ow.get_particles())
+    assert a.shape == b.shape, f"{a.shape[0]} particles on the GPU vs {b.shape[0]} in the oracle"
+    assert np.array_equal(a, b), "the reseeded store differs from the oracle"
+    util.check_store_invariants(gw.get_particles())
+    # a second pass with another seed (voxels that are still short of 8 try again), then the transfer
+    for w in (gw, ow):
+        w.FluidReseed(2000 + seed)
+        w.FLIP_P2G(dx, 3)
+    util.compare_particles(gw.get_particles(), ow.get_particles(), "second FluidReseed")
+    for name in ("Velocity", "LiquidSDF"):
+        util.compare_grids(gw.get_grid(name), ow.get_grid(name), f"P2G after FluidReseed: {name}", tol=0.0, check_inactive=False)
+    gw.close()
+
+
+def test_fluid_reseed_through_the_node_class(gpu_lib, oracle_lib):
+    """The drop-in's FluidReseed NODE on real OpenVDB objects with the CUDA library behind it == the oracle."""
+    from oracle import pyoracle
+    if not pyoracle.plugin_gpu_available():
+        pytest.skip("oracle/_ref/libflipplugin_gpu.so is not built")
+    from oracle.pyoracle import OracleWorld, PluginGpuWorld
+    from tests.test_ref_pin_cpu import _reseed_worlds
+    (pw, ow), dx = _reseed_worlds((PluginGpuWorld, OracleWorld), seed=8)
+    for w in (pw, ow):
+        w.FluidReseed(4242)
+    util.compare_particles(pw.get_particles(), ow.get_particles(), "FluidReseed node (GPU) vs oracle")
+    pw.close()

@@ -548,6 +548,14 @@ int flipb200_kill_particles_in_sdf(flipb200_world* w, int sdfGrid, int keep) {
         sync(w);
     });
 }
+int flipb200_fluid_reseed(flipb200_world* w, uint32_t seed) {
+    return guarded([&] {
+        FB_REQUIRE(w, FLIPB200_ERR_ARG, "fluid_reseed: null world");
+        use_device(w);
+        fluid_reseed(w, seed);
+        sync(w);
+    });
+}
 int flipb200_particles_add_dv(flipb200_world* w, float dvx, float dvy, float dvz) {
     return guarded([&] {
         FB_REQUIRE(w, FLIPB200_ERR_ARG, "particles_add_dv: null world");

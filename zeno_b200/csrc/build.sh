@@ -9,7 +9,7 @@ OUT=../libflipb200.so
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xcompiler -O2 --expt-relaxed-constexpr -Xptxas -v"
 mkdir -p _build
 pids=()
-for f in scan topo particles p2g g2p stencils poisson abi comm dd; do
+for f in scan topo particles p2g g2p stencils poisson abi comm dd reseed; do
   stale=0
   [ -f _build/$f.o ] || stale=1
   for dep in $f.cu *.cuh ../../include/flipb200.h build.sh; do [ $dep -nt _build/$f.o ] && stale=1; done

@@ -1,0 +1,213 @@
+// libflipb200 -- FluidReseed (FF/nosys/FLIP_Reseed.cpp:8-16 -> FLIP_vdb::reseed_fluid, FF/FLIP_vdb.cpp:2047-2220).
+//
+// Per particle leaf, voxel by voxel in offset order: the voxel keeps its particles; if the liquid SDF at its centre is < dx and it
+// holds <= 4 of them, up to 16 jittered candidates are tried while it holds < 8 -- a candidate is taken when the SDF at its
+// position is <= -dx and its octant of the voxel is still empty, and gets the StaggeredBoxSampler velocity there. The jitter comes
+// from the reference's hash table (FF/FLIP_vdb.h:10-20) read at a running index: every trial consumes three entries whether it
+// is taken or not, so where a voxel's draws start depends on every voxel before it in the leaf. That chain is kept:
+//   reseed_decide_kernel  one WARP per leaf walks the eligible voxels in order; the 16 trials of a voxel are evaluated by 16
+//                         lanes at once (the SDF samples are the expensive part), then resolved in trial order by every lane
+//                         identically. Output per voxel: the draw index its trials start at and the 16-bit set of taken trials.
+//   (scan of the new per-voxel counts)
+//   reseed_write_kernel   one thread per voxel copies the old particles (position decode -> encode once more, as the reference's
+//                         write handles do) and appends the taken candidates with their sampled velocity.
+// The reference starts each TBB chunk at std::random_device (:2081-2084) and runs on through the chunk's leaves; here a leaf's
+// start is a hash of (seed, leaf origin) -- the seeded variant SURVEY 8f-1 asks for; the oracle takes the same starts.
+// Both grids share the particles' cell-centred transform (FF/nosys/FLIP_Creator.cpp:37-116): index -> world = ijk * s, world ->
+// index = xyz * (1 / s) in double (math/Maps.h ScaleMap), restated literally because it does not round-trip for every ijk.
+#include "world.cuh"
+
+namespace fb {
+namespace {
+
+__device__ __forceinline__ float rs_frand(unsigned int i) {
+    unsigned int value = (i ^ 61u) ^ (i >> 16);
+    value *= 9u;
+    value ^= value << 4;
+    value *= 0x27d4eb2du;
+    value ^= value >> 15;
+    return __fdiv_rn((float)value, 4294967296.0f);
+}
+__device__ __forceinline__ float rs_table(unsigned int index) { return __double2float_rn(__dsub_rn((double)rs_frand(index % 21474836u), 0.5)); }
+__host__ __device__ __forceinline__ unsigned int rs_leaf_start(uint32_t seed, int ox, int oy, int oz) {
+    uint32_t h = seed ^ ((uint32_t)ox * 73856093u) ^ ((uint32_t)oy * 19349663u) ^ ((uint32_t)oz * 83492791u);
+    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+    return h % 21474836u;
+}
+// openvdb BoxSampler with double weights (tools/Interpolation.h:712-737): a + float(double(b - a) * w)
+__device__ __forceinline__ float rs_ip(float a, float b, double w) { return __fadd_rn(a, __double2float_rn(__dmul_rn((double)__fsub_rn(b, a), w))); }
+__device__ __forceinline__ float rs_box(const TopoView& t, const float* __restrict__ val, float bg, double x, double y, double z) {
+    const int bx = (int)floor(x), by = (int)floor(y), bz = (int)floor(z);
+    const double u = __dsub_rn(x, (double)bx), v = __dsub_rn(y, (double)by), w = __dsub_rn(z, (double)bz);
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[i] = grid_get(t, val, bg, bx + (i >> 2), by + ((i >> 1) & 1), bz + (i & 1));
+    return rs_ip(rs_ip(rs_ip(d[0], d[1], w), rs_ip(d[2], d[3], w), v), rs_ip(rs_ip(d[4], d[5], w), rs_ip(d[6], d[7], w), v), u);
+}
+
+struct ReseedParams {
+    TopoView pt;                 // the particle store's topology
+    const uint32_t* voxelStart;
+    const uint32_t *w0, *w1, *w2;
+    TopoView st; const float* sdf; float sdfBg;
+    TopoView vt; const float* vel[3]; float velBg[3];
+    float dx; double s, inv;
+    uint32_t seed;
+    uint32_t* tstart;            // [n*512] draw index of the voxel's first trial
+    uint16_t* accept;            // [n*512] taken trials
+    uint32_t* newCount;          // [n*512 + 1]
+    const uint32_t* newStart;    // exclusive prefix of newCount
+    uint32_t *o0, *o1, *o2;
+};
+
+inline unsigned nblk(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+constexpr int RS_WARPS = 4;
+__global__ void __launch_bounds__(RS_WARPS * 32) reseed_decide_kernel(ReseedParams p) {
+    const int lane = threadIdx.x & 31;
+    const int leaf = blockIdx.x * RS_WARPS + (threadIdx.x >> 5);
+    if (leaf >= p.pt.n) return;
+    const int3 o = p.pt.origin[leaf];
+    const uint32_t* vs = p.voxelStart + (size_t)leaf * LEAF;
+    // phase 1: which voxels try at all (independent of the draws): <= 4 particles and SDF at the centre < dx
+    __shared__ uint32_t sElig[RS_WARPS][16];
+    uint32_t* elig = sElig[threadIdx.x >> 5];
+#pragma unroll 1
+    for (int it = 0; it < 16; it++) {
+        const int off = it * 32 + lane;
+        const uint32_t cnt = vs[off + 1] - vs[off];
+        bool e = false;
+        if (cnt <= 4u) {
+            const double wx = __dmul_rn((double)(o.x + (off >> 6)), p.s), wy = __dmul_rn((double)(o.y + ((off >> 3) & 7)), p.s), wz = __dmul_rn((double)(o.z + (off & 7)), p.s);
+            e = rs_box(p.st, p.sdf, p.sdfBg, __dmul_rn(wx, p.inv), __dmul_rn(wy, p.inv), __dmul_rn(wz, p.inv)) < p.dx;
+        }
+        const uint32_t eb = __ballot_sync(0xffffffffu, e);
+        if (lane == 0) elig[it] = eb;
+        p.newCount[(size_t)leaf * LEAF + off] = cnt;
+        p.accept[(size_t)leaf * LEAF + off] = 0;
+    }
+    __syncwarp();
+    // phase 2: the eligible voxels in offset order
+    unsigned int index = rs_leaf_start(p.seed, o.x, o.y, o.z);
+    const float negDx = -p.dx;
+#pragma unroll 1
+    for (int it = 0; it < 16; it++) {
+        uint32_t m = elig[it];
+        while (m) {
+            const int off = it * 32 + (__ffs(m) - 1);
+            m &= m - 1;
+            const uint32_t b = vs[off], cnt = vs[off + 1] - b;
+            unsigned occBit = 0;
+            if ((uint32_t)lane < cnt) {   // cnt <= 4
+                const uint32_t a0 = __ldg(&p.w0[b + lane]), a1 = __ldg(&p.w1[b + lane]);
+                const float px = fx_decode(a0 & 0xffffu), py = fx_decode(a0 >> 16), pz = fx_decode(a1 & 0xffffu);
+                occBit = 1u << (((pz > 0.f) << 2) | ((py > 0.f) << 1) | (px > 0.f ? 1 : 0));
+            }
+            unsigned occ = __reduce_or_sync(0xffffffffu, occBit);
+            const double wx = __dmul_rn((double)(o.x + (off >> 6)), p.s), wy = __dmul_rn((double)(o.y + ((off >> 3) & 7)), p.s), wz = __dmul_rn((double)(o.z + (off & 7)), p.s);
+            bool pass = false;
+            unsigned sv = 0;
+            if (lane < 16) {
+                const unsigned int at = index + 3u * (unsigned)lane;
+                const float jx = rs_table(at), jy = rs_table(at + 1u), jz = rs_table(at + 2u);
+                const double qx = __dadd_rn(__dmul_rn((double)jx, p.s), wx), qy = __dadd_rn(__dmul_rn((double)jy, p.s), wy), qz = __dadd_rn(__dmul_rn((double)jz, p.s), wz);
+                const float phi2 = rs_box(p.st, p.sdf, p.sdfBg, __dmul_rn(qx, p.inv), __dmul_rn(qy, p.inv), __dmul_rn(qz, p.inv));
+                pass = !(phi2 > negDx);
+                sv = ((jz > 0.f) << 2) | ((jy > 0.f) << 1) | (jx > 0.f ? 1 : 0);
+            }
+            const uint32_t passMask = __ballot_sync(0xffffffffu, pass);
+            const uint32_t s0 = __ballot_sync(0xffffffffu, sv & 1u), s1 = __ballot_sync(0xffffffffu, sv & 2u), s2 = __ballot_sync(0xffffffffu, sv & 4u);
+            uint32_t here = cnt, used = 0, acc = 0;
+            for (int t = 0; t < 16 && here < 8u; t++) {
+                used++;
+                if ((passMask >> t) & 1u) {
+                    const unsigned oc = ((s0 >> t) & 1u) | (((s1 >> t) & 1u) << 1) | (((s2 >> t) & 1u) << 2);
+                    if (!((occ >> oc) & 1u)) { occ |= 1u << oc; acc |= 1u << t; here++; }
+                }
+            }
+            if (lane == 0) {
+                p.tstart[(size_t)leaf * LEAF + off] = index;
+                p.accept[(size_t)leaf * LEAF + off] = (uint16_t)acc;
+                p.newCount[(size_t)leaf * LEAF + off] = here;
+            }
+            index += 3u * used;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) reseed_write_kernel(ReseedParams p) {
+    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= (size_t)p.pt.n * LEAF) return;
+    const uint32_t b = p.voxelStart[v], e = p.voxelStart[v + 1];
+    uint32_t d = p.newStart[v];
+    for (uint32_t i = b; i < e; i++, d++) {   // the write handles re-encode the decoded position; the half velocity round-trips
+        const uint32_t a0 = p.w0[i], a1 = p.w1[i];
+        p.o0[d] = fx_encode(fx_decode(a0 & 0xffffu)) | (fx_encode(fx_decode(a0 >> 16)) << 16);
+        p.o1[d] = fx_encode(fx_decode(a1 & 0xffffu)) | (a1 & 0xffff0000u);
+        p.o2[d] = p.w2[i];
+    }
+    uint32_t acc = p.accept[v];
+    if (!acc) return;
+    const int leaf = (int)(v >> 9), off = (int)(v & 511);
+    const int3 o = p.pt.origin[leaf];
+    const double wx = __dmul_rn((double)(o.x + (off >> 6)), p.s), wy = __dmul_rn((double)(o.y + ((off >> 3) & 7)), p.s), wz = __dmul_rn((double)(o.z + (off & 7)), p.s);
+    const unsigned int index = p.tstart[v];
+    while (acc) {
+        const int t = __ffs(acc) - 1;
+        acc &= acc - 1;
+        const unsigned int at = index + 3u * (unsigned)t;
+        const float jx = rs_table(at), jy = rs_table(at + 1u), jz = rs_table(at + 2u);
+        const double ix = __dmul_rn(__dadd_rn(__dmul_rn((double)jx, p.s), wx), p.inv), iy = __dmul_rn(__dadd_rn(__dmul_rn((double)jy, p.s), wy), p.inv),
+                     iz = __dmul_rn(__dadd_rn(__dmul_rn((double)jz, p.s), wz), p.inv);
+        // StaggeredBoxSampler (tools/Interpolation.h:944-953): component c at the point + 0.5 on axis c
+        const float vx = rs_box(p.vt, p.vel[0], p.velBg[0], __dadd_rn(ix, 0.5), iy, iz);
+        const float vy = rs_box(p.vt, p.vel[1], p.velBg[1], ix, __dadd_rn(iy, 0.5), iz);
+        const float vz = rs_box(p.vt, p.vel[2], p.velBg[2], ix, iy, __dadd_rn(iz, 0.5));
+        p.o0[d] = fx_encode(jx) | (fx_encode(jy) << 16);
+        p.o1[d] = fx_encode(jz) | (h_encode(vx) << 16);
+        p.o2[d] = h_encode(vy) | (h_encode(vz) << 16);
+        d++;
+    }
+}
+
+}  // namespace
+
+void fluid_reseed(World* w, uint32_t seed) {
+    FB_REQUIRE(w->pts.topo != nullptr, FLIPB200_ERR_STATE, "FluidReseed: no particles");
+    GridF& sdf = w->F(FLIPB200_LIQUID_SDF);
+    GridV& vel = w->V(FLIPB200_VELOCITY);
+    FB_REQUIRE(sdf.topo != nullptr && vel.topo != nullptr, FLIPB200_ERR_STATE, "FluidReseed: LiquidSDF / Velocity are not set (run FLIP_P2G or upload them)");
+    FB_REQUIRE(!dd_on(w), FLIPB200_ERR_STATE, "FluidReseed is not available under slab decomposition yet");
+    const TopoPtr topo = w->pts.topo;
+    const int n = topo->n;
+    if (n == 0) return;
+    const size_t nv = (size_t)n * LEAF;
+    DBuf<uint32_t> tstart(nv, w->stream), newCount(nv + 1, w->stream), newStart(nv + 1, w->stream);
+    DBuf<uint16_t> accept(nv, w->stream);
+    FB_CUDA(cudaMemsetAsync(newCount.p + nv, 0, 4, w->stream));
+    ReseedParams p;
+    p.pt = topo->view();
+    p.voxelStart = w->pts.voxelStart.p; p.w0 = w->pts.w0.p; p.w1 = w->pts.w1.p; p.w2 = w->pts.w2.p;
+    p.st = sdf.topo->view(); p.sdf = sdf.val.p; p.sdfBg = sdf.bg;
+    p.vt = vel.topo->view();
+    for (int c = 0; c < 3; c++) { p.vel[c] = vel.val[c].p; p.velBg[c] = vel.bg[c]; }
+    p.dx = w->dx; p.s = (double)w->dx; p.inv = 1.0 / (double)w->dx;
+    p.seed = seed;
+    p.tstart = tstart.p; p.accept = accept.p; p.newCount = newCount.p; p.newStart = nullptr;
+    p.o0 = p.o1 = p.o2 = nullptr;
+    FB_LAUNCH(w, "reseed_decide", nv * 16) reseed_decide_kernel<<<(n + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, 0, w->stream>>>(p);
+    check_launch("reseed_decide");
+    uint64_t total = 0;
+    exclusive_scan_u32(w, newCount.p, newStart.p, nv + 1, &total);
+    Particles out;
+    out.topo = topo;
+    out.n = total;
+    out.w0.alloc(total + 1, w->stream); out.w1.alloc(total + 1, w->stream); out.w2.alloc(total + 1, w->stream);
+    p.newStart = newStart.p;
+    p.o0 = out.w0.p; p.o1 = out.w1.p; p.o2 = out.w2.p;
+    FB_LAUNCH(w, "reseed_write", (w->pts.n + total) * 12 + nv * 14) reseed_write_kernel<<<nblk(nv, 256), 256, 0, w->stream>>>(p);
+    check_launch("reseed_write");
+    out.voxelStart = std::move(newStart);
+    w->pts = std::move(out);
+}
+
+}  // namespace fb

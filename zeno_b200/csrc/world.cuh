@@ -241,6 +241,7 @@ void comm_allreduce(World* w, void* buf, size_t n, int type, bool isMax);   // i
 // keeps one ghost layer of particles on each side and a pool that reaches one further ring layer.
 struct DDArray { void* base; int bytesPerLeaf; };
 bool dd_on(World* w);
+void fluid_reseed(World* w, uint32_t seed);   // reseed.cu
 void dd_destroy(World* w);
 void dd_set_slab(World* w, int lo, int hi);
 void dd_owned_slots(World* w, int* ownLo, int* ownHi);          // slot range of the owned leaves in w->pool (collective)

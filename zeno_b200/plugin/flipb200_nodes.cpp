@@ -118,6 +118,7 @@ struct WorldHolder {
     struct Stage { Pinned o, m, v; int n = 0; float bg[3] = {0.f, 0.f, 0.f}; } stage[FLIPB200_NUM_GRIDS];
     Pinned po, pve, pP, pV;                       // particle staging
     int pnl = 0; uint64_t pnp = 0;
+    uint32_t reseeds = 0;                         // FluidReseed calls so far (seed sequence)
     Fingerprint fp[FLIPB200_NUM_GRIDS + 1];       // what the device copy of each slot corresponds to (last slot: particles)
     ~WorldHolder() { if (w) flipb200_world_destroy(w); }
 };
@@ -528,6 +529,28 @@ struct KillParticlesInSDF : zeno::INode {
 static int defKillParticlesInSDF = zeno::defNodeClass<KillParticlesInSDF>("KillParticlesInSDF",
     {/* inputs: */ {"Particles", "KillerSDF"}, /* outputs: */ {"Particles"}, /* params: */ {{"enum KEEP DEL", "OpType", "KEEP"}},
      /* category: */ {"FLIPSolver"}});
+
+// ---- FluidReseed (FF/nosys/FLIP_Reseed.cpp:8-31). The reference draws where its jitter table starts from std::random_device
+// (FF/FLIP_vdb.cpp:2081-2084); the device path is seeded: FLIPB200_SEED (default 0) + the number of reseeds this world has done,
+// so successive substeps do not repeat a pattern and a run is reproducible. seed_fixed() pins the seed for the parity tests.
+inline uint32_t& seed_base() { static uint32_t s = std::getenv("FLIPB200_SEED") ? uint32_t(std::strtoul(std::getenv("FLIPB200_SEED"), nullptr, 10)) : 0u; return s; }
+inline bool& seed_fixed() { static bool f = false; return f; }
+struct FluidReseed : zeno::INode {
+    virtual void apply() override {
+        auto particles = get_input("Particles")->as<VDBPointsGrid>();
+        auto liquidSDF = get_input("LiquidSDF")->as<VDBFloatGrid>();
+        auto liquidVel = get_input("FluidVel")->as<VDBFloat3Grid>();
+        WorldHolder& h = world_for(float(particles->m_grid->voxelSize()[0]), {particles, liquidSDF, liquidVel});
+        upload_particles(h, particles->m_grid);
+        upload<openvdb::FloatGrid>(h, FLIPB200_LIQUID_SDF, liquidSDF->m_grid);
+        upload<openvdb::Vec3fGrid>(h, FLIPB200_VELOCITY, liquidVel->m_grid);
+        const uint32_t seed = seed_fixed() ? seed_base() : seed_base() + h.reseeds++;
+        check(flipb200_fluid_reseed(h.w, seed), "FluidReseed");
+        download_particles(h, particles->m_grid);
+    }
+};
+static int defFluidReseed = zeno::defNodeClass<FluidReseed>("FluidReseed",
+    {/* inputs: */ {"Particles", "LiquidSDF", "FluidVel"}, /* outputs: */ {}, /* params: */ {}, /* category: */ {"FLIPSolver"}});
 
 // ---- ParticleAddDV (FF/nosys/ParticleAddGravity.cpp:9-41)
 struct ParticleAddDV : zeno::INode {
