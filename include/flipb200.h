@@ -157,6 +157,13 @@ int flipb200_kill_particles_in_sdf(flipb200_world* w, int sdfGrid, int keep);
  *   start = h % 21474836
  * (uint32 arithmetic) and runs through its voxels in offset order exactly as the reference does inside a chunk. */
 int flipb200_fluid_reseed(flipb200_world* w, uint32_t seed);
+/* ParticleEmitter (FF/nosys/ParticleEmitter.cpp:9-62 -> FLIP_vdb::emit_liquid, FF/FLIP_vdb.cpp:2222-2642), the branch WITHOUT a
+ * VelocityVolume (:2488-2624): every particle leaf box one of whose 9^3 lattice corners samples the shape SDF (float grid slot
+ * `shapeGrid`, e.g. FLIPB200_KILLER_SDF) < 0 is filled -- per voxel whose centre samples < dx, up to 16 jittered candidates while
+ * the voxel holds < 8, skipped when their octant is taken, taken when the shape at the candidate is < -0.1 dx; new particles get
+ * the velocity (vx, vy, vz). Missing leaves are created; leaves the shape does not touch are left alone. The shape grid must share
+ * the world's cell-centred transform (voxel size dx). Jitter and seeding as in flipb200_fluid_reseed. */
+int flipb200_emit_liquid(flipb200_world* w, int shapeGrid, float vx, float vy, float vz, uint32_t seed);
 /* debug: keep / fetch the fp32 position (index space) and velocity before the codecs, in the
  * order of the particle store the advect call started from (codec caveat). */
 int flipb200_capture_precodec(flipb200_world* w, int on);

@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- see flip_oracle.h.
 // G2P + advection + re-binning (K2, K7, K8).
+#include <map>
 #include "flip_oracle.h"
 #include <cmath>
 #include <numeric>
@@ -434,6 +435,105 @@ void node_FluidReseed(World& w, uint32_t seed, const uint64_t* leafStart, uint64
         const uint64_t start = leafStart ? leafStart[l] : reseed_leaf_start(seed, o.x, o.y, o.z);
         const uint64_t end = reseed_leaf(w, l, start, out.P, out.v, out.voxelEnd[l]);
         if (leafEnd) leafEnd[l] = end;
+    }
+    out.leafBegin.push_back(out.P.size() / 3);
+    w.particles = std::move(out);
+}
+
+// ---- ParticleEmitter (FF/nosys/ParticleEmitter.cpp:9-40 -> FLIP_vdb::emit_liquid, FF/FLIP_vdb.cpp:2222-2642), the branch
+// without a velocity volume (:2488-2624): new particles carry the constant (vx, vy, vz).
+// Leaves: every particle-index leaf box one of whose 9^3 lattice corners samples the shape SDF < 0 (:2270-2312; the loop range,
+// the shape's leaf bounding box +- 8 voxels, only has to be a superset: outside it the shape reads its positive background) --
+// existing leaves are reused, missing ones created. Per voxel of such a leaf, in offset order: the particles stay (re-emitted
+// through the write handles); if the shape at the voxel centre is < dx, up to 16 trials while the voxel holds < 8: three table
+// entries per trial, skipped when its octant is taken (:2577-2581), taken when the shape at the candidate is < -0.1 dx (:2585).
+// Leaves the shape does not touch are not visited at all (their positions are NOT re-encoded). The shape is sampled through
+// shape.worldToIndex(particles.indexToWorld(.)); here both share the cell-centred transform of voxel size dx (the restriction the
+// device path has; ScaleMap arithmetic as in reseed_leaf).
+static bool emitter_touches(const FloatGrid& shape, double s, double inv, int ox, int oy, int oz) {
+    for (int ii = 0; ii <= 8; ii++)
+        for (int jj = 0; jj <= 8; jj++)
+            for (int kk = 0; kk <= 8; kk++) {
+                const double wx = double(ox + ii) * s, wy = double(oy + jj) * s, wz = double(oz + kk) * s;
+                if (box_sample_f64(shape, 0, wx * inv, wy * inv, wz * inv) < 0) return true;
+            }
+    return false;
+}
+void node_ParticleEmitter(World& w, const FloatGrid& shape, float vx, float vy, float vz, uint32_t seed, const uint64_t* leafStart,
+                          uint64_t* leafEnd) {
+    const Points& in = w.particles;
+    const float dx = w.dx;
+    const double s = double(dx), inv = 1.0 / s;
+    const float thr = float(double(-dx) * 0.1);
+    // candidate leaves: the shape's leaves and their 26 neighbours
+    std::map<uint64_t, Coord> cand;
+    for (const Coord& o : shape.origins)
+        for (int a = -8; a <= 8; a += 8)
+            for (int b = -8; b <= 8; b += 8)
+                for (int c = -8; c <= 8; c += 8) cand.emplace(leafKeyOf(o.x + a, o.y + b, o.z + c), Coord(o.x + a, o.y + b, o.z + c));
+    std::map<uint64_t, std::pair<Coord, bool>> leaves;   // key -> (origin, touched by the shape); std::map = the store's leaf order
+    for (int l = 0; l < in.leafCount(); l++) leaves[leafKeyOf(in.origins[l].x, in.origins[l].y, in.origins[l].z)] = {in.origins[l], false};
+    for (auto& kv : cand)
+        if (emitter_touches(shape, s, inv, kv.second.x, kv.second.y, kv.second.z)) {
+            auto it = leaves.find(kv.first);
+            if (it == leaves.end()) leaves[kv.first] = {kv.second, true};
+            else it->second.second = true;
+        }
+    Points out;
+    int li = 0;
+    for (auto& kv : leaves) {
+        const Coord o = kv.second.first;
+        const int l = in.findLeaf(o.x, o.y, o.z);
+        out.dir.emplace(kv.first, li);
+        out.origins.push_back(o);
+        out.voxelEnd.emplace_back();
+        out.leafBegin.push_back(out.P.size() / 3);
+        std::array<uint32_t, 512>& ends = out.voxelEnd.back();
+        if (!kv.second.second) {   // untouched: copied as it is
+            const size_t b = in.leafBegin[l], e = in.leafBegin[l + 1];
+            out.P.insert(out.P.end(), in.P.begin() + 3 * b, in.P.begin() + 3 * e);
+            out.v.insert(out.v.end(), in.v.begin() + 3 * b, in.v.begin() + 3 * e);
+            ends = in.voxelEnd[l];
+            if (leafEnd) leafEnd[li] = ~0ull;
+            li++;
+            continue;
+        }
+        uint64_t index = leafStart ? leafStart[li] : reseed_leaf_start(seed, o.x, o.y, o.z);
+        uint32_t emitted = 0;
+        for (int off = 0; off < 512; off++) {
+            unsigned occ = 0;
+            uint32_t here = 0;
+            if (l >= 0) {
+                const uint32_t b = off ? in.voxelEnd[l][off - 1] : 0u, e = in.voxelEnd[l][off];
+                for (uint32_t i = b; i < e; i++) {
+                    const size_t gi = in.leafBegin[l] + i;
+                    const float px = fxpt16_decode(in.P[3 * gi]), py = fxpt16_decode(in.P[3 * gi + 1]), pz = fxpt16_decode(in.P[3 * gi + 2]);
+                    occ |= 1u << (((pz > 0.f) << 2) | ((py > 0.f) << 1) | (px > 0.f));
+                    out.P.push_back(fxpt16_encode(px)); out.P.push_back(fxpt16_encode(py)); out.P.push_back(fxpt16_encode(pz));
+                    for (int a = 0; a < 3; a++) out.v.push_back(half_encode(half_decode(in.v[3 * gi + a])));
+                    emitted++; here++;
+                }
+            }
+            const int ix = o.x + (off >> 6), iy = o.y + ((off >> 3) & 7), iz = o.z + (off & 7);
+            const double wx = double(ix) * s, wy = double(iy) * s, wz = double(iz) * s;
+            if (box_sample_f64(shape, 0, wx * inv, wy * inv, wz * inv) < dx) {
+                for (int trial = 0; here < 8 && trial < 16; trial++) {
+                    const float jx = reseed_table(index++), jy = reseed_table(index++), jz = reseed_table(index++);
+                    const unsigned sv = ((double(jz) > 0) << 2) | ((double(jy) > 0) << 1) | (double(jx) > 0);
+                    if (occ & (1u << sv)) continue;
+                    const double qx = double(jx) * s + wx, qy = double(jy) * s + wy, qz = double(jz) * s + wz;
+                    if (box_sample_f64(shape, 0, qx * inv, qy * inv, qz * inv) < thr) {
+                        occ |= 1u << sv;
+                        out.P.push_back(fxpt16_encode(jx)); out.P.push_back(fxpt16_encode(jy)); out.P.push_back(fxpt16_encode(jz));
+                        out.v.push_back(half_encode(vx)); out.v.push_back(half_encode(vy)); out.v.push_back(half_encode(vz));
+                        emitted++; here++;
+                    }
+                }
+            }
+            ends[off] = emitted;
+        }
+        if (leafEnd) leafEnd[li] = index;
+        li++;
     }
     out.leafBegin.push_back(out.P.size() / 3);
     w.particles = std::move(out);

@@ -75,6 +75,9 @@ void node_KillParticlesInSDF(World& w, const FloatGrid& sdf, bool keep);
 // FF/nosys/FLIP_Reseed.cpp:8-16 -> FLIP_vdb::reseed_fluid (FF/FLIP_vdb.cpp:2047-2220)
 void node_FluidReseed(World& w, uint32_t seed, const uint64_t* leafStart, uint64_t* leafEnd);
 uint64_t reseed_leaf_start(uint32_t seed, int ox, int oy, int oz);
+// FF/nosys/ParticleEmitter.cpp:9-40 -> FLIP_vdb::emit_liquid (FF/FLIP_vdb.cpp:2222-2642), constant-velocity branch; leafStart / leafEnd
+// are indexed by the leaves of the RESULT (store order); leafEnd = ~0 for leaves the shape does not touch
+void node_ParticleEmitter(World& w, const FloatGrid& shape, float vx, float vy, float vz, uint32_t seed, const uint64_t* leafStart, uint64_t* leafEnd);
 
 // FF/nosys/ParticleAddGravity.cpp:9-19 -> FLIP_vdb::point_integrate_vector (FF/FLIP_vdb.cpp:3492-3535)
 void node_ParticleAddDV(World& w, float dvx, float dvy, float dvz);

@@ -160,6 +160,16 @@ class OracleWorld:
             raise RuntimeError("FluidReseed failed: " + self._err())
         return le[:nl] if want_leaf_end else None
 
+    def ParticleEmitter(self, shape_grid: str = "KillerSDF", vx=0.0, vy=0.0, vz=0.0, seed: int = 0, leaf_start=None, want_leaf_end: bool = False, max_leaves: int = 0):
+        """leaf_start / the returned ends are indexed by the leaves of the RESULT; ~0 marks leaves the shape does not touch."""
+        ls = None if leaf_start is None else _c(leaf_start, np.uint64)
+        le = np.full(max(max_leaves, 1), np.uint64(0), np.uint64) if want_leaf_end else None
+        rc = self.lib.orc_emit_liquid(self.h, C.c_int(GRID_IDS[shape_grid]), C.c_float(vx), C.c_float(vy), C.c_float(vz), C.c_uint32(seed & 0xffffffff),
+                                      None if ls is None else _p(ls), None if le is None else _p(le))
+        if rc != 0:
+            raise RuntimeError("ParticleEmitter failed: " + self._err())
+        return le[:self.particles_info()[0]] if want_leaf_end else None
+
     def _err(self):
         try:
             return (self.lib.orc_last_error() or b"").decode()

@@ -22,6 +22,7 @@
 #include <openvdb/tree/LeafManager.h>
 #include "levelset_util.h"
 #include <zeno/StringObject.h>
+#include <zeno/ConditionObject.h>
 #include <vector>
 #include <openvdb/tools/Morphology.h>
 #include <openvdb/tools/MeshToVolume.h>
@@ -56,6 +57,7 @@ namespace zeno { using namespace ::zeno; }
 #include "nosys/ParticleAddGravity.cpp"     // ParticleAddDV
 #include "nosys/G2P_Advector.cpp"           // the plain advector
 #include "nosys/FLIP_Reseed.cpp"            // FluidReseed
+#include "nosys/ParticleEmitter.cpp"        // ParticleEmitter
 #include "VDBRenormalize.cpp"               // projects/zenvdb: VDBRenormalizeSDF
 }  // namespace refnodes
 #undef defNodeClass

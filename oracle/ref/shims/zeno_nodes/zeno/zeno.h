@@ -60,6 +60,11 @@ struct INode {
     bool has_input(std::string const& id) const {
         return is_param(id) ? params.count(id.substr(0, id.size() - 1)) != 0 : inputs.count(id) != 0;
     }
+    template <class T> bool has_input(std::string const& id) const {   // zeno/include/zeno/core/INode.h:84-89
+        if (!has_input(id)) return false;
+        auto it = inputs.find(id);
+        return it != inputs.end() && dynamic_cast<T*>(it->second.get()) != nullptr;
+    }
     std::shared_ptr<IObject> get_input(std::string const& id) const {
         auto it = inputs.find(id);
         if (it == inputs.end() || !it->second) throw std::runtime_error("INode::get_input: socket `" + id + "` is not connected");

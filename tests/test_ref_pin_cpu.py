@@ -429,3 +429,102 @@ def test_fluid_reseed_plugin_node_equals_oracle(oracle_lib):
     ow.FluidReseed(78)
     n2 = ow.particles_info()[1]
     assert n1 <= n2 < n1 * 1.2
+
+
+def _emitter_scene(seed=3):
+    """A 12^3 block at 8 particles per voxel and a sphere shape (world-unit distances on the world's own transform) that overlaps
+    the block's corner and reaches into empty space: existing leaves get topped up, new leaves are created, leaves of the block
+    the sphere does not touch must come through untouched."""
+    from zeno_b200 import scenes
+    pos, vel, dx = scenes.dam_break_points(64, seed=seed, ppc=8, side=12, W=2, random_velocity=True)
+    shape = scenes.sphere_sdf(centre=(17.3, 12.1, 9.7), radius=7.6, lo=(0, 0, 0), hi=(32, 24, 24), bg=3.0)
+    shape["values"] = (shape["values"] * np.float32(dx)).astype(np.float32)
+    shape["bg"] = np.array([3.0 * dx], np.float32)
+    return pos, vel * np.float32(0.3), dx, shape
+
+
+def _by_origin(p):
+    b = _leaf_slices(p)
+    return {tuple(int(x) for x in p["origins"][i]): i for i in range(p["origins"].shape[0]) if b[i + 1] > b[i]}
+
+
+@pytest.mark.parametrize("threads", [1, 0], ids=["one_thread", "all_threads"])
+def test_particle_emitter_oracle_vs_reference_node(oracle_lib, threads):
+    """ParticleEmitter (FF/nosys/ParticleEmitter.cpp -> FLIP_vdb::emit_liquid, FF/FLIP_vdb.cpp:2222-2642), constant-velocity branch, the
+    REAL node class in the seeded build of the reference. The reference walks its touched leaves in the order of a concurrent hash
+    map, one jitter-table start per TBB chunk, so a leaf of its result must equal the oracle's per-leaf restatement started either
+    at the chunk start the seed implies or where SOME other leaf ended. Same leaf set, and code-for-code equality on every leaf."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "rn_emit_liquid"):
+        pytest.skip("oracle/_ref with the ParticleEmitter reference node is not available here")
+    from oracle.pyoracle import OracleWorld, RefNodeWorld
+    pos, vel, dx, shape = _emitter_scene()
+    seed = 777
+    lib = pyoracle.load()
+    lib.orc_reseed_chunk_start.restype = C.c_uint64
+    s0 = int(lib.orc_reseed_chunk_start(C.c_uint32(seed)))
+    rw, ow = RefNodeWorld(dx), OracleWorld(dx)
+    for w in (rw, ow):
+        w.PrimToVDBPointDataGrid(pos, vel)
+        w.set_grid("KillerSDF", shape)
+    before = ow.get_particles()
+    V = (0.25, -1.5, 0.125)
+    try:
+        pyoracle.ref_set_threads(threads)
+        rw.ParticleEmitter("KillerSDF", *V, seed=seed)
+    finally:
+        pyoracle.ref_set_threads(0)
+    ref = rw.get_particles()
+    ends = ow.ParticleEmitter("KillerSDF", *V, seed=seed, want_leaf_end=True, max_leaves=4096)
+    orc = ow.get_particles()
+    n0, n1 = before["P"].shape[0], ref["P"].shape[0]
+    assert n1 > n0 + 1000, f"the emitter must add particles: {n0} -> {n1}"
+    ro, oo = _by_origin(ref), _by_origin(orc)
+    assert set(ro) == set(oo), "non-empty leaves of the reference's result vs the oracle's"
+    assert len(ro) > len(_by_origin(before)), "the scene must create leaves"
+    touched = {tuple(int(x) for x in orc["origins"][i]) for i in range(orc["origins"].shape[0]) if int(ends[i]) != 0xFFFFFFFFFFFFFFFF}
+    # untouched leaves: identical to the input; touched ones: the oracle leaf by leaf from the candidate starts
+    bo = _by_origin(before)
+    for k, i in ro.items():
+        if k not in touched:
+            assert _same_leaf(ref, i, before, bo[k]), f"leaf {k} is not touched by the shape and must be unchanged"
+    lw = OracleWorld(dx)
+    lw.set_grid("KillerSDF", shape)
+    pending = [k for k in sorted(ro) if k in touched]
+    known_ends = set()
+    progress = True
+    while pending and progress:
+        progress = False
+        for k in list(pending):
+            one = _one_leaf(before, bo[k]) if k in bo else {"origins": np.zeros((0, 3), np.int32), "voxel_end": np.zeros((0, 512), np.uint32),
+                                                          "P": np.zeros((0, 3), np.uint16), "v": np.zeros((0, 3), np.uint16)}
+            for c in [s0] + sorted(known_ends - {s0}):
+                lw.set_particles(one)
+                e = lw.ParticleEmitter("KillerSDF", *V, seed=0, leaf_start=np.full(4096, c, np.uint64), want_leaf_end=True, max_leaves=4096)
+                got = lw.get_particles()
+                j = _by_origin(got).get(k)
+                if j is not None and _same_leaf(got, j, ref, ro[k]):
+                    known_ends.add(int(e[j]))
+                    pending.remove(k)
+                    progress = True
+                    break
+    assert not pending, f"{len(pending)} leaves of the reference's result match the oracle from no candidate start, e.g. {pending[:3]}"
+
+
+def test_particle_emitter_plugin_node_equals_oracle(oracle_lib):
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "pn_emit_liquid"):
+        pytest.skip("oracle/_ref with the plugin-node harness is not available here")
+    from oracle.pyoracle import OracleWorld, PluginWorld
+    pos, vel, dx, shape = _emitter_scene(seed=4)
+    pw, ow = PluginWorld(dx), OracleWorld(dx)
+    for w in (pw, ow):
+        w.PrimToVDBPointDataGrid(pos, vel)
+        w.set_grid("KillerSDF", shape)
+        w.ParticleEmitter("KillerSDF", 0.5, 0.0, -0.75, seed=99)
+    util.compare_particles(pw.get_particles(), ow.get_particles(), "ParticleEmitter: plugin node vs oracle")
+    # emitting into an EMPTY world creates the store
+    ew = OracleWorld(dx)
+    ew.set_grid("KillerSDF", shape)
+    ew.ParticleEmitter("KillerSDF", 0.0, 1.0, 0.0, seed=5)
+    assert ew.particles_info()[1] > 1000

@@ -157,3 +157,48 @@ def test_fluid_reseed_through_the_node_class(gpu_lib, oracle_lib):
         w.FluidReseed(4242)
     util.compare_particles(pw.get_particles(), ow.get_particles(), "FluidReseed node (GPU) vs oracle")
     pw.close()
+
+
+@pytest.mark.parametrize("seed", [4, 12])
+def test_particle_emitter_matches_oracle(gpu_lib, oracle_lib, seed):
+    """ParticleEmitter (FF/nosys/ParticleEmitter.cpp -> FLIP_vdb::emit_liquid), constant-velocity branch: the oracle is pinned against
+    the reference's node class (tests/test_ref_pin_cpu.py); here CUDA == oracle: same leaves created, identical stores, twice in a
+    row (the second call tops up what the first left short), and the result feeds FLIP_P2G."""
+    from oracle.pyoracle import OracleWorld
+    from tests.test_ref_pin_cpu import _emitter_scene
+    from zeno_b200 import abi
+    pos, vel, dx, shape = _emitter_scene(seed=seed)
+    gw, ow = abi.World(dx), OracleWorld(dx)
+    for w in (gw, ow):
+        w.PrimToVDBPointDataGrid(pos, vel)
+        w.set_grid("KillerSDF", shape)
+    n0 = ow.particles_info()[1]
+    for k in range(2):
+        for w in (gw, ow):
+            w.ParticleEmitter("KillerSDF", 0.5, 0.0, -0.75, seed=100 * seed + k)
+        a = scenes.canonical_particles(gw.get_particles())
+        b = scenes.canonical_particles(ow.get_particles())
+        assert a.shape == b.shape, f"call {k}: {a.shape[0]} particles on the GPU vs {b.shape[0]} in the oracle"
+        assert np.array_equal(a, b), f"call {k}: the store differs from the oracle"
+    assert ow.particles_info()[1] > n0 + 1000
+    util.check_store_invariants(gw.get_particles())
+    for w in (gw, ow):
+        w.FLIP_P2G(dx, 3)
+    for name in ("Velocity", "LiquidSDF"):
+        util.compare_grids(gw.get_grid(name), ow.get_grid(name), f"P2G after ParticleEmitter: {name}", tol=0.0, check_inactive=False)
+    gw.close()
+
+
+def test_particle_emitter_into_an_empty_world(gpu_lib, oracle_lib):
+    from oracle.pyoracle import OracleWorld
+    from tests.test_ref_pin_cpu import _emitter_scene
+    from zeno_b200 import abi
+    _, _, dx, shape = _emitter_scene()
+    gw, ow = abi.World(dx), OracleWorld(dx)
+    for w in (gw, ow):
+        w.set_grid("KillerSDF", shape)
+        w.ParticleEmitter("KillerSDF", 0.0, 1.0, 0.0, seed=5)
+    a = scenes.canonical_particles(gw.get_particles())
+    b = scenes.canonical_particles(ow.get_particles())
+    assert b.shape[0] > 1000 and a.shape == b.shape and np.array_equal(a, b)
+    gw.close()

@@ -556,6 +556,14 @@ int flipb200_fluid_reseed(flipb200_world* w, uint32_t seed) {
         sync(w);
     });
 }
+int flipb200_emit_liquid(flipb200_world* w, int shapeGrid, float vx, float vy, float vz, uint32_t seed) {
+    return guarded([&] {
+        FB_REQUIRE(w, FLIPB200_ERR_ARG, "emit_liquid: null world");
+        use_device(w);
+        emit_liquid(w, shapeGrid, vx, vy, vz, seed);
+        sync(w);
+    });
+}
 int flipb200_particles_add_dv(flipb200_world* w, float dvx, float dvy, float dvz) {
     return guarded([&] {
         FB_REQUIRE(w, FLIPB200_ERR_ARG, "particles_add_dv: null world");

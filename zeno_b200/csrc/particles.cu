@@ -143,6 +143,13 @@ void sort_by_key(World* w, const TopoPtr& topo, const uint32_t* keys, uint64_t n
 }
 }  // namespace
 
+// the stable counting sort without the per-voxel cap, for the other translation units (reseed.cu)
+void sort_store_by_key(World* w, const TopoPtr& topo, const uint32_t* keys, uint64_t n, const uint32_t* i0, const uint32_t* i1, const uint32_t* i2,
+                       Particles& out) {
+    uint64_t kept = 0;
+    sort_by_key(w, topo, keys, n, /*cap=*/0, i0, i1, i2, out, &kept);
+}
+
 void origins_from_ijk(World* w, const int3* ijk, uint64_t n, int3* origins);
 
 void bin_from_points(World* w, const float* pos_host, const float* vel_host, uint64_t n) {

@@ -16,6 +16,7 @@
 // Both grids share the particles' cell-centred transform (FF/nosys/FLIP_Creator.cpp:37-116): index -> world = ijk * s, world ->
 // index = xyz * (1 / s) in double (math/Maps.h ScaleMap), restated literally because it does not round-trip for every ijk.
 #include "world.cuh"
+#include <cuda_fp16.h>
 
 namespace fb {
 namespace {
@@ -169,7 +170,225 @@ __global__ void __launch_bounds__(256) reseed_write_kernel(ReseedParams p) {
     }
 }
 
+// ---------------------------------------------------------------- ParticleEmitter (FF/nosys/ParticleEmitter.cpp:9-40 ->
+// FLIP_vdb::emit_liquid, FF/FLIP_vdb.cpp:2222-2642), the branch without a velocity volume (:2488-2624).
+// A leaf box takes part when one of its 9^3 lattice corners samples the shape SDF < 0 (:2270-2312). Per voxel of such a leaf: shape at
+// the centre < dx -> up to 16 trials while the voxel holds < 8; a trial is skipped when its octant is taken and taken when the shape
+// at the candidate is < -0.1 dx; new particles carry the constant velocity. Other leaves are not visited (no re-encode).
+struct EmitParams {
+    TopoView pt;
+    const uint32_t* voxelStart;
+    const uint32_t *w0, *w1, *w2;
+    TopoView st; const float* sdf; float sdfBg;
+    float dx, thr; double s, inv;
+    uint32_t seed;
+    const uint8_t* touched;      // [n] 1 = the shape touches this leaf
+    uint32_t* tstart; uint16_t* accept; uint32_t* newCount; const uint32_t* newStart;
+    uint32_t *o0, *o1, *o2;
+    uint32_t velLo, velHi;       // the constant velocity as the store's half codes: w1 high half, w2
+};
+// one CTA per leaf box of `t`: flag = any lattice corner with shape < 0
+__global__ void __launch_bounds__(256) emit_touch_kernel(TopoView t, TopoView st, const float* __restrict__ sdf, float bg, double s, double inv,
+                                                         uint8_t* __restrict__ flag) {
+    const int3 o = t.origin[blockIdx.x];
+    bool hit = false;
+    for (int q = threadIdx.x; q < 729; q += 256) {
+        const int ii = q / 81, jj = (q / 9) % 9, kk = q % 9;
+        const double wx = __dmul_rn((double)(o.x + ii), s), wy = __dmul_rn((double)(o.y + jj), s), wz = __dmul_rn((double)(o.z + kk), s);
+        hit |= rs_box(st, sdf, bg, __dmul_rn(wx, inv), __dmul_rn(wy, inv), __dmul_rn(wz, inv)) < 0.f;
+    }
+    const int any = __syncthreads_or(hit ? 1 : 0);
+    if (threadIdx.x == 0) flag[blockIdx.x] = any ? 1 : 0;
+}
+// selection for the new pool: leaves of the store that hold particles, candidate leaves the shape touches
+__global__ void emit_select_kernel(int nP, const uint32_t* __restrict__ voxelStart, int nC, const uint8_t* __restrict__ candFlag, uint32_t* __restrict__ sel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nP) sel[i] = voxelStart[(size_t)(i + 1) * LEAF] > voxelStart[(size_t)i * LEAF] ? 1u : 0u;
+    else if (i < nP + nC) sel[i] = candFlag[i - nP];
+}
+__global__ void emit_gather_kernel(int nP, const int3* __restrict__ po, int nC, const int3* __restrict__ co, const uint32_t* __restrict__ sel,
+                                   const uint32_t* __restrict__ pos, int3* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nP + nC || !sel[i]) return;
+    out[pos[i]] = i < nP ? po[i] : co[i - nP];
+}
+// key of every particle on the new pool (thread per old voxel)
+__global__ void emit_rekey_kernel(TopoView ot, const uint32_t* __restrict__ voxelStart, TopoView nt, uint32_t* __restrict__ keys) {
+    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= (size_t)ot.n * LEAF) return;
+    const uint32_t b = voxelStart[v], e = voxelStart[v + 1];
+    if (b == e) return;
+    const int3 o = ot.origin[v >> 9];
+    const uint32_t key = (uint32_t)topo_find(nt, o.x, o.y, o.z) * LEAF + (uint32_t)(v & 511);
+    for (uint32_t i = b; i < e; i++) keys[i] = key;
+}
+__global__ void __launch_bounds__(RS_WARPS * 32) emit_decide_kernel(EmitParams p) {
+    const int lane = threadIdx.x & 31;
+    const int leaf = blockIdx.x * RS_WARPS + (threadIdx.x >> 5);
+    if (leaf >= p.pt.n) return;
+    const int3 o = p.pt.origin[leaf];
+    const uint32_t* vs = p.voxelStart + (size_t)leaf * LEAF;
+    __shared__ uint32_t sElig[RS_WARPS][16];
+    uint32_t* elig = sElig[threadIdx.x >> 5];
+    const bool touched = p.touched[leaf] != 0;
+#pragma unroll 1
+    for (int it = 0; it < 16; it++) {
+        const int off = it * 32 + lane;
+        const uint32_t cnt = vs[off + 1] - vs[off];
+        bool e = false;
+        if (touched && cnt < 8u) {
+            const double wx = __dmul_rn((double)(o.x + (off >> 6)), p.s), wy = __dmul_rn((double)(o.y + ((off >> 3) & 7)), p.s), wz = __dmul_rn((double)(o.z + (off & 7)), p.s);
+            e = rs_box(p.st, p.sdf, p.sdfBg, __dmul_rn(wx, p.inv), __dmul_rn(wy, p.inv), __dmul_rn(wz, p.inv)) < p.dx;
+        }
+        const uint32_t eb = __ballot_sync(0xffffffffu, e);
+        if (lane == 0) elig[it] = eb;
+        p.newCount[(size_t)leaf * LEAF + off] = cnt;
+        p.accept[(size_t)leaf * LEAF + off] = 0;
+    }
+    __syncwarp();
+    if (!touched) return;
+    unsigned int index = rs_leaf_start(p.seed, o.x, o.y, o.z);
+#pragma unroll 1
+    for (int it = 0; it < 16; it++) {
+        uint32_t m = elig[it];
+        while (m) {
+            const int off = it * 32 + (__ffs(m) - 1);
+            m &= m - 1;
+            const uint32_t b = vs[off], cnt = vs[off + 1] - b;
+            unsigned occBit = 0;
+            if ((uint32_t)lane < cnt) {   // cnt < 8
+                const uint32_t a0 = __ldg(&p.w0[b + lane]), a1 = __ldg(&p.w1[b + lane]);
+                const float px = fx_decode(a0 & 0xffffu), py = fx_decode(a0 >> 16), pz = fx_decode(a1 & 0xffffu);
+                occBit = 1u << (((pz > 0.f) << 2) | ((py > 0.f) << 1) | (px > 0.f ? 1 : 0));
+            }
+            unsigned occ = __reduce_or_sync(0xffffffffu, occBit);
+            const double wx = __dmul_rn((double)(o.x + (off >> 6)), p.s), wy = __dmul_rn((double)(o.y + ((off >> 3) & 7)), p.s), wz = __dmul_rn((double)(o.z + (off & 7)), p.s);
+            bool pass = false;
+            unsigned sv = 0;
+            if (lane < 16) {
+                const unsigned int at = index + 3u * (unsigned)lane;
+                const float jx = rs_table(at), jy = rs_table(at + 1u), jz = rs_table(at + 2u);
+                const double qx = __dadd_rn(__dmul_rn((double)jx, p.s), wx), qy = __dadd_rn(__dmul_rn((double)jy, p.s), wy), qz = __dadd_rn(__dmul_rn((double)jz, p.s), wz);
+                pass = rs_box(p.st, p.sdf, p.sdfBg, __dmul_rn(qx, p.inv), __dmul_rn(qy, p.inv), __dmul_rn(qz, p.inv)) < p.thr;
+                sv = ((jz > 0.f) << 2) | ((jy > 0.f) << 1) | (jx > 0.f ? 1 : 0);
+            }
+            const uint32_t passMask = __ballot_sync(0xffffffffu, pass);
+            const uint32_t s0 = __ballot_sync(0xffffffffu, sv & 1u), s1 = __ballot_sync(0xffffffffu, sv & 2u), s2 = __ballot_sync(0xffffffffu, sv & 4u);
+            uint32_t here = cnt, used = 0, acc = 0;
+            for (int t = 0; t < 16 && here < 8u; t++) {
+                used++;
+                const unsigned oc = ((s0 >> t) & 1u) | (((s1 >> t) & 1u) << 1) | (((s2 >> t) & 1u) << 2);
+                if ((occ >> oc) & 1u) continue;
+                if ((passMask >> t) & 1u) { occ |= 1u << oc; acc |= 1u << t; here++; }
+            }
+            if (lane == 0) {
+                p.tstart[(size_t)leaf * LEAF + off] = index;
+                p.accept[(size_t)leaf * LEAF + off] = (uint16_t)acc;
+                p.newCount[(size_t)leaf * LEAF + off] = here;
+            }
+            index += 3u * used;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) emit_write_kernel(EmitParams p) {
+    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= (size_t)p.pt.n * LEAF) return;
+    const uint32_t b = p.voxelStart[v], e = p.voxelStart[v + 1];
+    uint32_t d = p.newStart[v];
+    const bool touched = p.touched[v >> 9] != 0;
+    for (uint32_t i = b; i < e; i++, d++) {
+        const uint32_t a0 = p.w0[i], a1 = p.w1[i];
+        p.o0[d] = touched ? (fx_encode(fx_decode(a0 & 0xffffu)) | (fx_encode(fx_decode(a0 >> 16)) << 16)) : a0;
+        p.o1[d] = touched ? (fx_encode(fx_decode(a1 & 0xffffu)) | (a1 & 0xffff0000u)) : a1;
+        p.o2[d] = p.w2[i];
+    }
+    uint32_t acc = p.accept[v];
+    const unsigned int index = acc ? p.tstart[v] : 0u;
+    while (acc) {
+        const int t = __ffs(acc) - 1;
+        acc &= acc - 1;
+        const unsigned int at = index + 3u * (unsigned)t;
+        p.o0[d] = fx_encode(rs_table(at)) | (fx_encode(rs_table(at + 1u)) << 16);
+        p.o1[d] = fx_encode(rs_table(at + 2u)) | p.velLo;
+        p.o2[d] = p.velHi;
+        d++;
+    }
+}
+
 }  // namespace
+
+void emit_liquid(World* w, int shapeGrid, float vx, float vy, float vz, uint32_t seed) {
+    FB_REQUIRE(is_float_grid(shapeGrid) && w->F(shapeGrid).topo != nullptr, FLIPB200_ERR_STATE, "ParticleEmitter: the shape SDF grid was not uploaded");
+    FB_REQUIRE(!dd_on(w), FLIPB200_ERR_STATE, "ParticleEmitter is not available under slab decomposition yet");
+    GridF& g = w->F(shapeGrid);
+    if (g.topo->n == 0) return;   // evalLeafBoundingBox fails on an empty shape: the reference returns (:2233-2236)
+    const double s = (double)w->dx, inv = 1.0 / s;
+    // 1. candidate leaf boxes = the shape's leaves and their 26 neighbours; which of them the shape touches
+    TopoPtr cand = topo_from_origins_dev(w, g.topo->origin.p, g.topo->n, /*ring=*/true);
+    DBuf<uint8_t> candFlag(cand->n + 1, w->stream);
+    FB_LAUNCH(w, "emit_touch", (size_t)cand->n * 729 * 32) emit_touch_kernel<<<cand->n, 256, 0, w->stream>>>(cand->view(), g.topo->view(), g.val.p, g.bg, s, inv, candFlag.p);
+    check_launch("emit_touch");
+    // 2. the new pool: leaves that hold particles + touched candidates (+ ring)
+    const bool have = w->pts.topo != nullptr && w->pts.topo->n > 0;
+    const int nP = have ? w->pts.topo->n : 0, nC = cand->n;
+    DBuf<uint32_t> sel(nP + nC + 1, w->stream), pos(nP + nC + 1, w->stream);
+    FB_CUDA(cudaMemsetAsync(sel.p + nP + nC, 0, 4, w->stream));
+    emit_select_kernel<<<nblk(nP + nC, 256), 256, 0, w->stream>>>(nP, have ? w->pts.voxelStart.p : nullptr, nC, candFlag.p, sel.p);
+    check_launch("emit_select");
+    uint64_t nSel = 0;
+    exclusive_scan_u32(w, sel.p, pos.p, (size_t)nP + nC + 1, &nSel);
+    if (nSel == 0) return;
+    DBuf<int3> origins(nSel + 1, w->stream);
+    emit_gather_kernel<<<nblk(nP + nC, 256), 256, 0, w->stream>>>(nP, have ? w->pts.topo->origin.p : nullptr, nC, cand->origin.p, sel.p, pos.p, origins.p);
+    check_launch("emit_gather");
+    TopoPtr pool = topo_from_origins_dev(w, origins.p, (int)nSel, /*ring=*/true);
+    // 3. the store on the new pool (stable: the order inside every voxel is kept)
+    Particles cur;
+    const uint64_t n = have ? w->pts.n : 0;
+    {
+        DBuf<uint32_t> keys(n + 1, w->stream);
+        if (n) {
+            emit_rekey_kernel<<<nblk((size_t)nP * LEAF, 256), 256, 0, w->stream>>>(w->pts.topo->view(), w->pts.voxelStart.p, pool->view(), keys.p);
+            check_launch("emit_rekey");
+        }
+        DBuf<uint32_t> i0 = std::move(w->pts.w0), i1 = std::move(w->pts.w1), i2 = std::move(w->pts.w2);
+        sort_store_by_key(w, pool, keys.p, n, i0.p, i1.p, i2.p, cur);
+    }
+    // 4. which pool leaves the shape touches, then decide / scan / write as in FluidReseed
+    const int nl = pool->n;
+    const size_t nv = (size_t)nl * LEAF;
+    DBuf<uint8_t> touched(nl + 1, w->stream);
+    FB_LAUNCH(w, "emit_touch", (size_t)nl * 729 * 32) emit_touch_kernel<<<nl, 256, 0, w->stream>>>(pool->view(), g.topo->view(), g.val.p, g.bg, s, inv, touched.p);
+    check_launch("emit_touch");
+    DBuf<uint32_t> tstart(nv, w->stream), newCount(nv + 1, w->stream), newStart(nv + 1, w->stream);
+    DBuf<uint16_t> accept(nv, w->stream);
+    FB_CUDA(cudaMemsetAsync(newCount.p + nv, 0, 4, w->stream));
+    EmitParams p;
+    p.pt = pool->view();
+    p.voxelStart = cur.voxelStart.p; p.w0 = cur.w0.p; p.w1 = cur.w1.p; p.w2 = cur.w2.p;
+    p.st = g.topo->view(); p.sdf = g.val.p; p.sdfBg = g.bg;
+    p.dx = w->dx; p.thr = (float)((double)(-w->dx) * 0.1); p.s = s; p.inv = inv;
+    p.seed = seed; p.touched = touched.p;
+    p.tstart = tstart.p; p.accept = accept.p; p.newCount = newCount.p; p.newStart = nullptr;
+    p.o0 = p.o1 = p.o2 = nullptr;
+    p.velLo = (uint32_t)__half_as_ushort(__float2half_rn(vx)) << 16;
+    p.velHi = (uint32_t)__half_as_ushort(__float2half_rn(vy)) | ((uint32_t)__half_as_ushort(__float2half_rn(vz)) << 16);
+    FB_LAUNCH(w, "emit_decide", nv * 16) emit_decide_kernel<<<(nl + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, 0, w->stream>>>(p);
+    check_launch("emit_decide");
+    uint64_t total = 0;
+    exclusive_scan_u32(w, newCount.p, newStart.p, nv + 1, &total);
+    Particles out;
+    out.topo = pool;
+    out.n = total;
+    out.w0.alloc(total + 1, w->stream); out.w1.alloc(total + 1, w->stream); out.w2.alloc(total + 1, w->stream);
+    p.newStart = newStart.p;
+    p.o0 = out.w0.p; p.o1 = out.w1.p; p.o2 = out.w2.p;
+    FB_LAUNCH(w, "emit_write", (n + total) * 12 + nv * 14) emit_write_kernel<<<nblk(nv, 256), 256, 0, w->stream>>>(p);
+    check_launch("emit_write");
+    out.voxelStart = std::move(newStart);
+    w->pts = std::move(out);
+    w->pool = pool;
+}
 
 void fluid_reseed(World* w, uint32_t seed) {
     FB_REQUIRE(w->pts.topo != nullptr, FLIPB200_ERR_STATE, "FluidReseed: no particles");

@@ -552,6 +552,35 @@ struct FluidReseed : zeno::INode {
 static int defFluidReseed = zeno::defNodeClass<FluidReseed>("FluidReseed",
     {/* inputs: */ {"Particles", "LiquidSDF", "FluidVel"}, /* outputs: */ {}, /* params: */ {}, /* category: */ {"FLIPSolver"}});
 
+// ---- ParticleEmitter (FF/nosys/ParticleEmitter.cpp:9-62). Accelerated: the constant-velocity branch (vx / vy / vz or VelocityInit)
+// with a ShapeSDF on the world's own transform; a VelocityVolume or a shape grid with another transform is refused with a message
+// (the device grids carry no transform of their own).
+struct ParticleEmitter : zeno::INode {
+    virtual void apply() override {
+        auto particles = get_input("Particles")->as<VDBPointsGrid>();
+        auto shape = get_input("ShapeSDF")->as<VDBFloatGrid>();
+        float vx = get_param<float>("vx"), vy = get_param<float>("vy"), vz = get_param<float>("vz");
+        if (has_input("VelocityVolume") && std::dynamic_pointer_cast<VDBFloat3Grid>(get_input("VelocityVolume")))
+            check(FLIPB200_ERR_ARG, "ParticleEmitter: the VelocityVolume branch is not accelerated (constant emission velocity only)");
+        if (has_input("VelocityInit")) {
+            auto vel = get_input("VelocityInit")->as<zeno::NumericObject>()->get<zeno::vec3f>();
+            vx = vel[0]; vy = vel[1]; vz = vel[2];
+        }
+        if (!(shape->m_grid->transform() == particles->m_grid->transform()))
+            check(FLIPB200_ERR_ARG, "ParticleEmitter: the ShapeSDF must share the particle grid's transform (voxel size dx, cell centred)");
+        WorldHolder& h = world_for(float(particles->m_grid->voxelSize()[0]), {particles});
+        upload_particles(h, particles->m_grid);
+        upload<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, shape->m_grid);
+        const uint32_t seed = seed_fixed() ? seed_base() : seed_base() + 0x9e3779b9u + h.reseeds++;
+        check(flipb200_emit_liquid(h.w, FLIPB200_KILLER_SDF, vx, vy, vz, seed), "ParticleEmitter");
+        download_particles(h, particles->m_grid);
+        set_output("Particles", get_input("Particles"));
+    }
+};
+static int defParticleEmitter = zeno::defNodeClass<ParticleEmitter>("ParticleEmitter",
+    {/* inputs: */ {"Particles", "ShapeSDF", "VelocityVolume", "VelocityInit", "LiquidSDF"}, /* outputs: */ {"Particles"},
+     /* params: */ {{"float", "vx", "0.0"}, {"float", "vy", "0.0"}, {"float", "vz", "0.0"}}, /* category: */ {"FLIPSolver"}});
+
 // ---- ParticleAddDV (FF/nosys/ParticleAddGravity.cpp:9-41)
 struct ParticleAddDV : zeno::INode {
     virtual void apply() override {
