@@ -164,6 +164,12 @@ int flipb200_fluid_reseed(flipb200_world* w, uint32_t seed);
  * the velocity (vx, vy, vz). Missing leaves are created; leaves the shape does not touch are left alone. The shape grid must share
  * the world's cell-centred transform (voxel size dx). Jitter and seeding as in flipb200_fluid_reseed. */
 int flipb200_emit_liquid(flipb200_world* w, int shapeGrid, float vx, float vy, float vz, uint32_t seed);
+/* FLIPApplyBoundary (FF/nosys/Update_Solid_SDF.cpp:9-49 -> FLIP_vdb::update_solid_sdf, FF/FLIP_vdb.cpp:1976-2046) with one moving
+ * solid (float grid slot `movingGrid`, on the world's cell-centred transform or, movingVertexCentred != 0, on the static SDF's
+ * vertex-centred one): FLIPB200_SOLID_SDF gains the leaf under every moving-solid leaf origin and every particle leaf with a box
+ * corner inside the moving solid; then every voxel of every leaf = min(own value, moving solid sampled at the voxel's world
+ * position) and is active. (Particle leaves that hold no particles are not considered: the device store does not keep them.) */
+int flipb200_apply_boundary(flipb200_world* w, int movingGrid, int movingVertexCentred);
 /* debug: keep / fetch the fp32 position (index space) and velocity before the codecs, in the
  * order of the particle store the advect call started from (codec caveat). */
 int flipb200_capture_precodec(flipb200_world* w, int on);

@@ -79,6 +79,9 @@ uint64_t reseed_leaf_start(uint32_t seed, int ox, int oy, int oz);
 // are indexed by the leaves of the RESULT (store order); leafEnd = ~0 for leaves the shape does not touch
 void node_ParticleEmitter(World& w, const FloatGrid& shape, float vx, float vy, float vz, uint32_t seed, const uint64_t* leafStart, uint64_t* leafEnd);
 
+// FF/nosys/Update_Solid_SDF.cpp:9-31 -> FLIP_vdb::update_solid_sdf (FF/FLIP_vdb.cpp:1976-2046), one moving solid
+void node_FLIPApplyBoundary(World& w, const FloatGrid& moving, bool movingVertexCentred);
+
 // FF/nosys/ParticleAddGravity.cpp:9-19 -> FLIP_vdb::point_integrate_vector (FF/FLIP_vdb.cpp:3492-3535)
 void node_ParticleAddDV(World& w, float dvx, float dvy, float dvz);
 

@@ -170,6 +170,11 @@ class OracleWorld:
             raise RuntimeError("ParticleEmitter failed: " + self._err())
         return le[:self.particles_info()[0]] if want_leaf_end else None
 
+    def FLIPApplyBoundary(self, moving_grid: str = "KillerSDF", moving_vertex_centred: bool = False):
+        rc = self.lib.orc_apply_boundary(self.h, C.c_int(GRID_IDS[moving_grid]), C.c_int(1 if moving_vertex_centred else 0))
+        if rc != 0:
+            raise RuntimeError("FLIPApplyBoundary failed: " + self._err())
+
     def _err(self):
         try:
             return (self.lib.orc_last_error() or b"").decode()

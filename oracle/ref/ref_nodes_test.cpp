@@ -58,6 +58,7 @@ namespace zeno { using namespace ::zeno; }
 #include "nosys/G2P_Advector.cpp"           // the plain advector
 #include "nosys/FLIP_Reseed.cpp"            // FluidReseed
 #include "nosys/ParticleEmitter.cpp"        // ParticleEmitter
+#include "nosys/Update_Solid_SDF.cpp"       // FLIPApplyBoundary
 #include "VDBRenormalize.cpp"               // projects/zenvdb: VDBRenormalizeSDF
 }  // namespace refnodes
 #undef defNodeClass

@@ -329,4 +329,49 @@ void node_VDBSmoothSDF(FloatGrid& g, int width, int iterations) {
             }
 }
 
+// ---- FLIPApplyBoundary (FF/nosys/Update_Solid_SDF.cpp:9-31 -> FLIP_vdb::update_solid_sdf, FF/FLIP_vdb.cpp:1976-2046) with one
+// moving solid. (1) every leaf of the moving solid touches the static-SDF leaf under its origin (:1982-1990); (2) every particle
+// leaf one of whose eight box corners samples the moving solid < 0 touches the static-SDF leaf at ITS origin (:1995-2024, the
+// particle-index coordinate is used as it is); (3) EVERY voxel of EVERY leaf of the static SDF becomes min(own value, moving
+// solid sampled at the voxel's world position) and active (:2026-2045). New leaves start at the background, inactive.
+// Transforms (FF/nosys/FLIP_Creator.cpp:37-43,95-96): particles cell centred (x = i s), the static SDF vertex centred
+// (x = i s + t, t = -0.5 s; inverse (x - t) (1 / s), math/Maps.h:1273-1288); the moving solid on either of the two.
+void node_FLIPApplyBoundary(World& w, const FloatGrid& moving, bool movingVertexCentred) {
+    const double s = double(w.dx), inv = 1.0 / s, t = -0.5 * s, mt = movingVertexCentred ? t : 0.0;
+    auto moving_index = [&](double wx, double wy, double wz, double out[3]) {
+        if (movingVertexCentred) { out[0] = (wx - mt) * inv; out[1] = (wy - mt) * inv; out[2] = (wz - mt) * inv; }
+        else { out[0] = wx * inv; out[1] = wy * inv; out[2] = wz * inv; }
+    };
+    FloatGrid& solid = w.solidSDF;
+    for (const Coord& o : moving.origins) {
+        const double wx = movingVertexCentred ? double(o.x) * s + mt : double(o.x) * s, wy = movingVertexCentred ? double(o.y) * s + mt : double(o.y) * s,
+                     wz = movingVertexCentred ? double(o.z) * s + mt : double(o.z) * s;
+        solid.touchLeaf(int(std::floor((wx - t) * inv)), int(std::floor((wy - t) * inv)), int(std::floor((wz - t) * inv)));
+    }
+    const Points& pts = w.particles;
+    for (int l = 0; l < pts.leafCount(); l++) {
+        const Coord o = pts.origins[l];
+        bool hit = false;
+        for (int ii = 0; ii <= 8 && !hit; ii += 8)
+            for (int jj = 0; jj <= 8 && !hit; jj += 8)
+                for (int kk = 0; kk <= 8 && !hit; kk += 8) {
+                    double ip[3];
+                    moving_index(double(o.x + ii) * s, double(o.y + jj) * s, double(o.z + kk) * s, ip);
+                    hit = box_sample_f64(moving, ip[0], ip[1], ip[2]) < 0;
+                }
+        if (hit) solid.touchLeaf(o.x, o.y, o.z);
+    }
+    for (int l = 0; l < solid.leafCount(); l++) {
+        const Coord o = solid.origins[l];
+        float* v = solid.leafVals(l);
+        for (int off = 0; off < 512; off++) {
+            double ip[3];
+            moving_index(double(o.x + (off >> 6)) * s + t, double(o.y + ((off >> 3) & 7)) * s + t, double(o.z + (off & 7)) * s + t, ip);
+            v[off] = std::min(v[off], box_sample_f64(moving, ip[0], ip[1], ip[2]));
+        }
+        solid.masks[l].fill(~uint64_t(0));
+    }
+    w.hasSolidSDF = true;
+}
+
 }  // namespace orc

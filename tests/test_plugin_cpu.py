@@ -10,7 +10,7 @@ REF = "/root/reference/projects/FastFLIP/nosys"
 REF_FILES = {"FLIP_P2G": "P2G.cpp", "G2PAdvectorSheetty": "SheetG2PAdvector.cpp", "AssembleSolvePPE": "SolvePoissonPressureEqn.cpp",
              "SubtractPressureGradient": "SubtractPressureGradient.cpp", "CutCellWeight": "EvalFaceWeight.cpp",
              "PushOutLiquidSDF": "FixLiquidSDF.cpp", "FieldAddVector": "FieldAddVector.cpp", "CFL_dt": "CFL.cpp",
-             "KillParticlesInSDF": "KillParticles.cpp", "ParticleAddDV": "ParticleAddGravity.cpp", "FluidReseed": "FLIP_Reseed.cpp", "ParticleEmitter": "ParticleEmitter.cpp",
+             "KillParticlesInSDF": "KillParticles.cpp", "ParticleAddDV": "ParticleAddGravity.cpp", "FluidReseed": "FLIP_Reseed.cpp", "ParticleEmitter": "ParticleEmitter.cpp", "FLIPApplyBoundary": "Update_Solid_SDF.cpp",
              "G2P_Advector": "G2P_Advector.cpp", "VDBRenormalizeSDF": "../../zenvdb/VDBRenormalize.cpp",
              "VDBErodeSDF": "../../zenvdb/VDBRenormalize.cpp", "VDBSmoothSDF": "../../zenvdb/VDBRenormalize.cpp"}
 # (inputs, outputs, params) by name only, recorded from the reference files above
@@ -29,6 +29,7 @@ EXPECTED = {
     "KillParticlesInSDF": (["Particles", "KillerSDF"], ["Particles"], ["OpType"]),
     "ParticleAddDV": (["Particles", "dv"], [], ["channel", "vx", "vy", "vz"]),
     "FluidReseed": (["Particles", "LiquidSDF", "FluidVel"], [], []),
+    "FLIPApplyBoundary": (["Particles", "DynaSolid_SDF", "StatSolid_SDF"], [], []),
     "ParticleEmitter": (["Particles", "ShapeSDF", "VelocityVolume", "VelocityInit", "LiquidSDF"], ["Particles"], ["vx", "vy", "vz"]),
     "G2P_Advector": (["dt", "Dx", "Particles", "Velocity", "PostAdvVelocity", "SolidSDF", "SolidVelocity"], [], ["dx", "RK_ORDER", "pic_smoothness"]),
     "VDBRenormalizeSDF": (["inoutSDF"], ["inoutSDF"], ["method", "iterations", "dilateIters"]),

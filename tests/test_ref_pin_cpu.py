@@ -528,3 +528,39 @@ def test_particle_emitter_plugin_node_equals_oracle(oracle_lib):
     ew.set_grid("KillerSDF", shape)
     ew.ParticleEmitter("KillerSDF", 0.0, 1.0, 0.0, seed=5)
     assert ew.particles_info()[1] > 1000
+
+
+def _boundary_scene(seed=3):
+    """The tank's analytic solid SDF (vertex centred), a 12^3 water block, and a moving sphere (cell-centred grid, world-unit
+    distances) that overlaps tank leaves, water leaves and empty space."""
+    from zeno_b200 import scenes
+    N = 64
+    pos, vel, dx = scenes.dam_break_points(N, seed=seed, ppc=8, side=12, W=2, random_velocity=True)
+    solid = scenes.box_solid_sdf(N, dx)
+    sphere = scenes.sphere_sdf(centre=(15.3, 9.1, 11.7), radius=6.4, lo=(0, -8, 0), hi=(32, 24, 24), bg=3.0)
+    sphere["values"] = (sphere["values"] * np.float32(dx)).astype(np.float32)
+    sphere["bg"] = np.array([3.0 * dx], np.float32)
+    return pos, vel, dx, solid, sphere
+
+
+def test_flip_apply_boundary_oracle_plugin_and_reference_node(oracle_lib):
+    """FLIPApplyBoundary (FF/nosys/Update_Solid_SDF.cpp -> FLIP_vdb::update_solid_sdf, FF/FLIP_vdb.cpp:1976-2046): the REAL node class,
+    the oracle and the drop-in's node merge the same moving sphere into the same static SDF: same leaves, every voxel active,
+    values bit for bit."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "rn_apply_boundary"):
+        pytest.skip("oracle/_ref with the FLIPApplyBoundary reference node is not available here")
+    from oracle.pyoracle import OracleWorld, PluginWorld, RefNodeWorld
+    pos, vel, dx, solid, sphere = _boundary_scene()
+    worlds = [cls(dx) for cls in (RefNodeWorld, OracleWorld, PluginWorld)]
+    for w in worlds:
+        w.set_grid("SolidSDF", solid)
+        w.set_grid("KillerSDF", sphere)
+        w.PrimToVDBPointDataGrid(pos, vel)
+        w.FLIPApplyBoundary("KillerSDF")
+    ref = worlds[0].get_grid("SolidSDF")
+    assert ref["origins"].shape[0] > solid["origins"].shape[0], "the moving solid must add leaves"
+    assert np.all(ref["masks"] == np.uint64(0xFFFFFFFFFFFFFFFF))
+    assert int((ref["values"] < 0).sum()) > int((solid["values"] < 0).sum()) + 500, "the sphere must add solid voxels"
+    for w, what in zip(worlds[1:], ("oracle", "plugin node")):
+        util.compare_grids(w.get_grid("SolidSDF"), ref, f"FLIPApplyBoundary: {what} vs the reference node", tol=0.0, check_inactive=True)

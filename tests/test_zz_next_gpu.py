@@ -202,3 +202,26 @@ def test_particle_emitter_into_an_empty_world(gpu_lib, oracle_lib):
     b = scenes.canonical_particles(ow.get_particles())
     assert b.shape[0] > 1000 and a.shape == b.shape and np.array_equal(a, b)
     gw.close()
+
+
+def test_flip_apply_boundary_matches_oracle(gpu_lib, oracle_lib):
+    """FLIPApplyBoundary: CUDA == oracle (pinned against the reference's node class in tests/test_ref_pin_cpu.py), bit for bit, and the
+    merged SDF is what the following nodes see (CutCellWeight after it agrees too)."""
+    from oracle.pyoracle import OracleWorld
+    from tests.test_ref_pin_cpu import _boundary_scene
+    from zeno_b200 import abi
+    pos, vel, dx, solid, sphere = _boundary_scene(seed=5)
+    gw, ow = abi.World(dx), OracleWorld(dx)
+    for w in (gw, ow):
+        w.set_grid("SolidSDF", solid)
+        w.set_grid("KillerSDF", sphere)
+        w.PrimToVDBPointDataGrid(pos, vel)
+        w.FLIP_P2G(dx, 3)
+        w.FLIPApplyBoundary("KillerSDF")
+    a, b = gw.get_grid("SolidSDF"), ow.get_grid("SolidSDF")
+    assert b["origins"].shape[0] > solid["origins"].shape[0]
+    util.compare_grids(a, b, "FLIPApplyBoundary: SolidSDF", tol=0.0, check_inactive=True)
+    for w in (gw, ow):
+        w.CutCellWeight()
+    util.compare_grids(gw.get_grid("CellFWeight"), ow.get_grid("CellFWeight"), "CutCellWeight after FLIPApplyBoundary", tol=0.0, check_inactive=False)
+    gw.close()

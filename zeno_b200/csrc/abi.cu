@@ -564,6 +564,14 @@ int flipb200_emit_liquid(flipb200_world* w, int shapeGrid, float vx, float vy, f
         sync(w);
     });
 }
+int flipb200_apply_boundary(flipb200_world* w, int movingGrid, int movingVertexCentred) {
+    return guarded([&] {
+        FB_REQUIRE(w, FLIPB200_ERR_ARG, "apply_boundary: null world");
+        use_device(w);
+        apply_boundary(w, movingGrid, movingVertexCentred != 0);
+        sync(w);
+    });
+}
 int flipb200_particles_add_dv(flipb200_world* w, float dvx, float dvy, float dvz) {
     return guarded([&] {
         FB_REQUIRE(w, FLIPB200_ERR_ARG, "particles_add_dv: null world");

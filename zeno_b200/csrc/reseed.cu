@@ -390,6 +390,104 @@ void emit_liquid(World* w, int shapeGrid, float vx, float vy, float vz, uint32_t
     w->pool = pool;
 }
 
+// ---------------------------------------------------------------- FLIPApplyBoundary (FF/nosys/Update_Solid_SDF.cpp:9-31 ->
+// FLIP_vdb::update_solid_sdf, FF/FLIP_vdb.cpp:1976-2046), one moving solid. Leaves of the new static SDF = its old leaves + the
+// leaf under every moving-solid leaf origin + every particle leaf with a box corner inside the moving solid; then every voxel of
+// every leaf = min(old value or background, moving solid sampled at the voxel's world position), all active.
+// Transforms: particles x = i s; static SDF x = i s + t, t = -0.5 s (vertex centred); the moving solid on either.
+namespace {
+struct BoundaryParams {
+    int nS, nM, nP;
+    const int3 *so, *mo, *po;
+    const uint8_t *sAlloc, *mAlloc;
+    const uint32_t* voxelStart;
+    TopoView mt; const float* mval; float mbg;
+    double s, inv, t, mtr;       // mtr = the moving solid's translation (0 or t)
+};
+__device__ __forceinline__ float bd_sample(const BoundaryParams& p, double wx, double wy, double wz) {
+    return rs_box(p.mt, p.mval, p.mbg, __dmul_rn(__dsub_rn(wx, p.mtr), p.inv), __dmul_rn(__dsub_rn(wy, p.mtr), p.inv), __dmul_rn(__dsub_rn(wz, p.mtr), p.inv));
+}
+__global__ void boundary_select_kernel(BoundaryParams p, uint32_t* __restrict__ sel, int3* __restrict__ org) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.nS + p.nM + p.nP) return;
+    int3 o = make_int3(0, 0, 0);
+    uint32_t on = 0;
+    if (i < p.nS) { o = p.so[i]; on = p.sAlloc[i] ? 1u : 0u; }
+    else if (i < p.nS + p.nM) {
+        const int3 m = p.mo[i - p.nS];
+        on = p.mAlloc[i - p.nS] ? 1u : 0u;
+        const double wx = __dadd_rn(__dmul_rn((double)m.x, p.s), p.mtr), wy = __dadd_rn(__dmul_rn((double)m.y, p.s), p.mtr), wz = __dadd_rn(__dmul_rn((double)m.z, p.s), p.mtr);
+        o.x = (int)floor(__dmul_rn(__dsub_rn(wx, p.t), p.inv)) & ~7; o.y = (int)floor(__dmul_rn(__dsub_rn(wy, p.t), p.inv)) & ~7; o.z = (int)floor(__dmul_rn(__dsub_rn(wz, p.t), p.inv)) & ~7;
+    } else {
+        const int l = i - p.nS - p.nM;
+        o = p.po[l];
+        if (p.voxelStart[(size_t)(l + 1) * LEAF] > p.voxelStart[(size_t)l * LEAF]) {
+            for (int c = 0; c < 8 && !on; c++)
+                on = bd_sample(p, __dmul_rn((double)(o.x + ((c >> 2) & 1) * 8), p.s), __dmul_rn((double)(o.y + ((c >> 1) & 1) * 8), p.s), __dmul_rn((double)(o.z + (c & 1) * 8), p.s)) < 0.f ? 1u : 0u;
+        }
+    }
+    sel[i] = on; org[i] = o;
+}
+__global__ void boundary_gather_kernel(int n, const int3* __restrict__ org, const uint32_t* __restrict__ sel, const uint32_t* __restrict__ pos, int3* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && sel[i]) out[pos[i]] = org[i];
+}
+__global__ void __launch_bounds__(512) boundary_min_kernel(TopoView nt, TopoView ot, const float* __restrict__ oval, const uint8_t* __restrict__ oalloc, float bg,
+                                                           BoundaryParams p, float* __restrict__ val, uint64_t* __restrict__ mask, uint8_t* __restrict__ alloc) {
+    const int leaf = blockIdx.x, off = threadIdx.x;
+    const int3 o = nt.origin[leaf];
+    float cur = bg;
+    if (ot.n > 0) {
+        const int l = topo_find(ot, o.x, o.y, o.z);
+        if (l >= 0 && oalloc[l]) cur = oval[(size_t)l * LEAF + off];
+    }
+    const double wx = __dadd_rn(__dmul_rn((double)(o.x + (off >> 6)), p.s), p.t), wy = __dadd_rn(__dmul_rn((double)(o.y + ((off >> 3) & 7)), p.s), p.t),
+                 wz = __dadd_rn(__dmul_rn((double)(o.z + (off & 7)), p.s), p.t);
+    val[(size_t)leaf * LEAF + off] = fminf(cur, bd_sample(p, wx, wy, wz));
+    if (off < 8) mask[(size_t)leaf * 8 + off] = ~0ull;
+    if (off == 0) alloc[leaf] = 1;
+}
+}  // namespace
+
+void apply_boundary(World* w, int movingGrid, bool movingVertexCentred) {
+    FB_REQUIRE(is_float_grid(movingGrid) && movingGrid != FLIPB200_SOLID_SDF && w->F(movingGrid).topo != nullptr, FLIPB200_ERR_STATE,
+               "FLIPApplyBoundary: the moving solid SDF grid was not uploaded");
+    FB_REQUIRE(!dd_on(w), FLIPB200_ERR_STATE, "FLIPApplyBoundary is not available under slab decomposition yet");
+    GridF& mv = w->F(movingGrid);
+    GridF& sd = w->F(FLIPB200_SOLID_SDF);
+    const bool haveS = sd.topo != nullptr && sd.topo->n > 0, haveP = w->pts.topo != nullptr && w->pts.topo->n > 0;
+    BoundaryParams p;
+    p.nS = haveS ? sd.topo->n : 0; p.nM = mv.topo->n; p.nP = haveP ? w->pts.topo->n : 0;
+    p.so = haveS ? sd.topo->origin.p : nullptr; p.mo = mv.topo->origin.p; p.po = haveP ? w->pts.topo->origin.p : nullptr;
+    p.sAlloc = haveS ? sd.alloc.p : nullptr; p.mAlloc = mv.alloc.p;
+    p.voxelStart = haveP ? w->pts.voxelStart.p : nullptr;
+    p.mt = mv.topo->view(); p.mval = mv.val.p; p.mbg = mv.bg;
+    p.s = (double)w->dx; p.inv = 1.0 / p.s; p.t = -0.5 * p.s; p.mtr = movingVertexCentred ? p.t : 0.0;
+    const int n = p.nS + p.nM + p.nP;
+    if (n == 0) return;
+    DBuf<uint32_t> sel(n + 1, w->stream), pos(n + 1, w->stream);
+    DBuf<int3> org(n + 1, w->stream);
+    FB_CUDA(cudaMemsetAsync(sel.p + n, 0, 4, w->stream));
+    FB_LAUNCH(w, "boundary_select", (size_t)n * 300) boundary_select_kernel<<<nblk(n, 128), 128, 0, w->stream>>>(p, sel.p, org.p);
+    check_launch("boundary_select");
+    uint64_t cnt = 0;
+    exclusive_scan_u32(w, sel.p, pos.p, (size_t)n + 1, &cnt);
+    if (cnt == 0) return;
+    DBuf<int3> origins(cnt + 1, w->stream);
+    boundary_gather_kernel<<<nblk(n, 256), 256, 0, w->stream>>>(n, org.p, sel.p, pos.p, origins.p);
+    check_launch("boundary_gather");
+    TopoPtr nt = topo_from_origins_dev(w, origins.p, (int)cnt, /*ring=*/false);
+    GridF g;
+    grid_alloc(w, g, nt, sd.bg);
+    const TopoView ot = haveS ? sd.topo->view() : TopoView{0, make_int3(0, 0, 0), make_int3(0, 0, 0), nullptr, nullptr, nullptr};
+    FB_LAUNCH(w, "boundary_min", (size_t)nt->n * LEAF * 40) boundary_min_kernel<<<nt->n, 512, 0, w->stream>>>(nt->view(), ot, haveS ? sd.val.p : nullptr, haveS ? sd.alloc.p : nullptr,
+                                                                                                       sd.bg, p, g.val.p, g.mask.p, g.alloc.p);
+    check_launch("boundary_min");
+    w->F(FLIPB200_SOLID_SDF) = std::move(g);
+    w->hasSolidSDF = true;
+    w->solidViewEpoch = ~0ull;
+}
+
 void fluid_reseed(World* w, uint32_t seed) {
     FB_REQUIRE(w->pts.topo != nullptr, FLIPB200_ERR_STATE, "FluidReseed: no particles");
     GridF& sdf = w->F(FLIPB200_LIQUID_SDF);

@@ -581,6 +581,30 @@ static int defParticleEmitter = zeno::defNodeClass<ParticleEmitter>("ParticleEmi
     {/* inputs: */ {"Particles", "ShapeSDF", "VelocityVolume", "VelocityInit", "LiquidSDF"}, /* outputs: */ {"Particles"},
      /* params: */ {{"float", "vx", "0.0"}, {"float", "vy", "0.0"}, {"float", "vz", "0.0"}}, /* category: */ {"FLIPSolver"}});
 
+// ---- FLIPApplyBoundary (FF/nosys/Update_Solid_SDF.cpp:9-49). The reference reads the socket "Static_SDF" although its descriptor
+// lists "StatSolid_SDF": either name is accepted. Without a DynaSolid_SDF the reference's update is a no-op; so is this.
+struct FLIP_Solid_Modifier : zeno::INode {
+    virtual void apply() override {
+        auto particles = get_input("Particles")->as<VDBPointsGrid>();
+        auto stat = get_input(has_input("Static_SDF") ? "Static_SDF" : "StatSolid_SDF")->as<VDBFloatGrid>();
+        if (!has_input("DynaSolid_SDF")) return;
+        auto dyna = get_input("DynaSolid_SDF")->as<VDBFloatGrid>();
+        int vertexCentred = -1;
+        if (dyna->m_grid->transform() == particles->m_grid->transform()) vertexCentred = 0;
+        else if (dyna->m_grid->transform() == stat->m_grid->transform()) vertexCentred = 1;
+        if (vertexCentred < 0)
+            check(FLIPB200_ERR_ARG, "FLIPApplyBoundary: the DynaSolid_SDF must be on the particle grid's or on the static SDF's transform");
+        WorldHolder& h = world_for(float(particles->m_grid->voxelSize()[0]), {particles, stat});
+        upload_particles(h, particles->m_grid);
+        upload<openvdb::FloatGrid>(h, FLIPB200_SOLID_SDF, stat->m_grid);
+        upload<openvdb::FloatGrid>(h, FLIPB200_KILLER_SDF, dyna->m_grid);
+        check(flipb200_apply_boundary(h.w, FLIPB200_KILLER_SDF, vertexCentred), "FLIPApplyBoundary");
+        download<openvdb::FloatGrid>(h, FLIPB200_SOLID_SDF, stat->m_grid);
+    }
+};
+static int defFLIP_Solid_Modifier = zeno::defNodeClass<FLIP_Solid_Modifier>("FLIPApplyBoundary",
+    {/* inputs: */ {"Particles", "DynaSolid_SDF", "StatSolid_SDF"}, /* outputs: */ {}, /* params: */ {}, /* category: */ {"FLIPSolver"}});
+
 // ---- ParticleAddDV (FF/nosys/ParticleAddGravity.cpp:9-41)
 struct ParticleAddDV : zeno::INode {
     virtual void apply() override {
