@@ -158,3 +158,31 @@ def test_slab_decomposition_matches_single_world(gpu_lib, bounds):
           f"velocity rel L2 {e_v:.2e}, same-voxel after advection {same:.6f}")
     for w in dd + [one]:
         w.close()
+
+
+def test_slab_rules_are_enforced(gpu_lib):
+    """include/flipb200.h: a slab holds at least two leaf layers, and the ranks' slabs continue each other without gap or
+    overlap. A thin slab is refused at once; a gap is found at the first exchange, on every rank together."""
+    from zeno_b200 import abi
+    N = 128
+    pos, vel, dx = scenes.dam_break_points(N, seed=3, side=32)
+    solid = scenes.box_solid_sdf(N, dx)
+    worlds = [abi.World(dx) for _ in range(2)]
+    abi.comm_init_local(worlds)
+    with pytest.raises(abi.FlipB200Error, match="at least two leaf layers"):
+        worlds[0].dd_set_slab(0, 1)
+    bounds = [(0, 2), (3, 5)]   # layer 2 belongs to nobody
+    parts = split_points(pos, vel, dx, bounds)
+
+    def setup(r, w):
+        w.dd_set_slab(*bounds[r])
+        w.set_grid("SolidSDF", solid)
+        try:
+            w.PrimToVDBPointDataGrid(*parts[r])
+        except abi.FlipB200Error as e:
+            return str(e)
+        return None
+    errs = abi.run_ranks(worlds, setup)
+    assert all(e is not None and "contiguous" in e for e in errs), errs
+    for w in worlds:
+        w.close()

@@ -32,6 +32,9 @@ struct DDMaps {
 struct DDState {
     bool on = false;
     int lo = -DD_OPEN, hi = DD_OPEN;
+    bool boundsChecked = false;          // the neighbours' slabs were compared with mine (gap-free, no overlap)
+    int leftLo = -DD_OPEN, rightHi = DD_OPEN;   // the neighbours' far bounds: a particle beyond them cannot be routed in one hop
+    DBuf<int> strayed;                   // device counter of such particles
     DDMaps maps;
 };
 
@@ -71,12 +74,14 @@ __global__ void unpack_kernel(UnpackArgs a, const int* __restrict__ map) {
 // migration: 1 = goes to the left neighbour, 2 = to the right, 4 = stays in this rank's extended region
 __global__ void migrate_flags_kernel(const int3* __restrict__ ijk, const uint8_t* __restrict__ alive, uint64_t pLo, uint64_t m,
                                      int lo, int hi, int hasLeft, int hasRight, uint32_t* __restrict__ fL,
-                                     uint32_t* __restrict__ fR, uint32_t* __restrict__ fK) {
+                                     uint32_t* __restrict__ fR, uint32_t* __restrict__ fK, int leftLo, int rightHi, int* __restrict__ strayed) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const uint64_t g = pLo + i;
     const bool a = alive ? alive[g] != 0 : true;
     const int lx = ijk[g].x >> 3;
+    // beyond the neighbour's own slab: it would sit there as a ghost nobody advects (migration is one hop)
+    if (a && ((hasLeft && lx < leftLo) || (hasRight && lx >= rightHi))) atomicAdd(strayed, 1);
     fL[i] = (a && hasLeft && lx < lo + 1) ? 1u : 0u;
     fR[i] = (a && hasRight && lx >= hi - 1) ? 1u : 0u;
     fK[i] = (a && (!hasLeft || lx >= lo - 1) && (!hasRight || lx < hi + 1)) ? 1u : 0u;
@@ -167,12 +172,31 @@ bool dd_on(World* w) { return w->dd && w->dd->on && comm_active(w); }
 void dd_destroy(World* w) { delete w->dd; w->dd = nullptr; }
 void dd_set_slab(World* w, int lo, int hi) {
     FB_REQUIRE(comm_active(w), FLIPB200_ERR_COMM, "dd_set_slab: initialise the communicator first");
-    FB_REQUIRE(lo < hi, FLIPB200_ERR_ARG, "dd_set_slab: empty slab");
+    FB_REQUIRE(hi - lo >= 2, FLIPB200_ERR_ARG, "dd_set_slab: a slab must hold at least two leaf layers (ghost exchange reads the two layers next to each face)");
     if (!w->dd) w->dd = new DDState();
     w->dd->on = true;
     w->dd->lo = lo; w->dd->hi = hi;
+    w->dd->boundsChecked = false;
     w->dd->maps.epoch = ~0ull;
 }
+namespace {
+// once per dd_set_slab (collective, at the first exchange): my neighbours' slabs must continue mine without gap or overlap
+void check_bounds(World* w) {
+    DDState& D = *w->dd;
+    if (D.boundsChecked) return;
+    const int mine[2] = {D.lo, D.hi};
+    int fromLeft[2] = {0, 0}, fromRight[2] = {0, 0};
+    exchange_counts(w, mine, mine, fromLeft, fromRight);
+    const bool hasL = w->rank > 0, hasR = w->rank < w->nRanks - 1;
+    FB_REQUIRE(!hasL || fromLeft[1] == D.lo, FLIPB200_ERR_ARG, "dd_set_slab: rank " + std::to_string(w->rank - 1) + " owns leaf layers [" + std::to_string(fromLeft[0]) + ", " +
+               std::to_string(fromLeft[1]) + "), rank " + std::to_string(w->rank) + " starts at " + std::to_string(D.lo) + ": the slabs must be contiguous");
+    FB_REQUIRE(!hasR || fromRight[0] == D.hi, FLIPB200_ERR_ARG, "dd_set_slab: rank " + std::to_string(w->rank + 1) + " starts at leaf layer " + std::to_string(fromRight[0]) +
+               ", rank " + std::to_string(w->rank) + " ends at " + std::to_string(D.hi) + ": the slabs must be contiguous");
+    D.leftLo = hasL ? (w->rank - 1 > 0 ? fromLeft[0] : -DD_OPEN) : -DD_OPEN;
+    D.rightHi = hasR ? (w->rank + 1 < w->nRanks - 1 ? fromRight[1] : DD_OPEN) : DD_OPEN;
+    D.boundsChecked = true;
+}
+}  // namespace
 void dd_owned_slots(World* w, int* ownLo, int* ownHi) {
     DDMaps& M = dd_maps(w);
     *ownLo = M.b[0]; *ownHi = M.b[5];
@@ -241,8 +265,13 @@ void dd_migrate(World* w, uint64_t pLo, uint64_t pHi, const uint32_t* w0, const 
     DBuf<uint32_t> fL(m + 1, w->stream), fR(m + 1, w->stream), fK(m + 1, w->stream);
     DBuf<uint32_t> pL(m + 1, w->stream), pR(m + 1, w->stream), pK(m + 1, w->stream);
     fL.zero(); fR.zero(); fK.zero();
+    check_bounds(w);
+    DDState& D = *w->dd;
+    if (!D.strayed.p) D.strayed.alloc(1, w->stream);
+    D.strayed.zero();
     if (m) {
-        FB_LAUNCH(w, "dd_migrate_flags", m * 25) migrate_flags_kernel<<<nblk(m, 256), 256, 0, w->stream>>>(ijk, alive, pLo, m, w->dd->lo, w->dd->hi, hasL ? 1 : 0, hasR ? 1 : 0, fL.p, fR.p, fK.p);
+        FB_LAUNCH(w, "dd_migrate_flags", m * 25) migrate_flags_kernel<<<nblk(m, 256), 256, 0, w->stream>>>(ijk, alive, pLo, m, w->dd->lo, w->dd->hi, hasL ? 1 : 0, hasR ? 1 : 0, fL.p, fR.p, fK.p,
+                                                                                                       D.leftLo, D.rightHi, D.strayed.p);
         check_launch("migrate_flags");
     }
     uint64_t cL = 0, cR = 0, cK = 0;
@@ -252,7 +281,11 @@ void dd_migrate(World* w, uint64_t pLo, uint64_t pHi, const uint32_t* w0, const 
     exclusive_scan_u32(w, fK.p, pK.p, m + 1, &cK);
     const int toLeft[2] = {(int)cL, 0}, toRight[2] = {(int)cR, 0};
     int fromLeft[2], fromRight[2];
+    comm_allreduce(w, D.strayed.p, 1, CT_I32, false);     // every rank must see the same verdict (a lone throw would hang the others)
+    d2h_words(w, w->hostScratch + 512, D.strayed.p, 4);   // arrives with the wait inside exchange_counts
     exchange_counts(w, toLeft, toRight, fromLeft, fromRight);
+    const int strayed = *reinterpret_cast<const int*>(w->hostScratch + 512);
+    FB_REQUIRE(strayed == 0, FLIPB200_ERR_DOMAIN, std::to_string(strayed) + " particles moved past a neighbour's whole slab in one step (migration is one hop): use thicker slabs or a smaller time step");
     const uint64_t rL = hasL ? (uint64_t)fromLeft[0] : 0, rR = hasR ? (uint64_t)fromRight[0] : 0;
     const uint64_t n = rL + cK + rR;
     o0.alloc(n + 1, w->stream); o1.alloc(n + 1, w->stream); o2.alloc(n + 1, w->stream); oijk.alloc(n + 1, w->stream);

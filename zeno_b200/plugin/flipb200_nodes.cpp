@@ -203,6 +203,10 @@ void upload(WorldHolder& h, int id, const typename GridT::Ptr& g) {
     h.fp[id] = now;
 }
 
+// the tree a write-back replaces: when nobody else holds it, Tree::clear() frees its nodes in parallel (the destructor would do it
+// one leaf at a time on this thread: milliseconds per grid at a few thousand leaves)
+template <typename TreePtrT>
+void release_tree(TreePtrT old) { if (old && old.use_count() <= 2) old->clear(); }
 // write-back, part 1: the device stages the grid and the copies start (second stream); nothing is valid before download_wait
 template <typename GridT>
 void download_begin(WorldHolder& h, int id) {
@@ -229,14 +233,17 @@ void download_finish(WorldHolder& h, int id, typename GridT::Ptr& g) {
     typename Tree::Ptr tree;
     if constexpr (C == 3) tree = std::make_shared<Tree>(openvdb::Vec3f(st.bg[0], st.bg[1], st.bg[2]));
     else tree = std::make_shared<Tree>(st.bg[0]);
+    // leaves are allocated and filled in parallel; only the pointer insertion into the tree is serial
     std::vector<Leaf*> leaves(n);
-    for (int i = 0; i < n; i++) leaves[i] = tree->touchLeaf(openvdb::Coord(o[3 * i], o[3 * i + 1], o[3 * i + 2]));  // serial: tree insertion
     tbb::parallel_for(0, n, [&](int i) {
+        leaves[i] = new Leaf(openvdb::Coord(o[3 * i], o[3 * i + 1], o[3 * i + 2]), tree->background(), /*active=*/false);
         Mask mask;
         for (int k = 0; k < 8; k++) mask.template getWord<Mask::Word>(k) = m[8 * size_t(i) + k];
         std::memcpy(leaves[i]->buffer().data(), &v[size_t(512) * C * i], sizeof(float) * 512 * C);
         leaves[i]->setValueMask(mask);
     });
+    for (int i = 0; i < n; i++) tree->addLeaf(leaves[i]);
+    release_tree(g->treePtr());
     g->setTree(tree);
     std::vector<const Leaf*> cl;
     g->tree().getNodes(cl);
@@ -320,13 +327,12 @@ inline void download_particles_finish(WorldHolder& h, openvdb::points::PointData
     auto pdescr = openvdb::points::AttributeSet::Descriptor::create(position_attribute::attributeType());
     auto pvdescr = pdescr->duplicateAppend("v", velocity_attribute::attributeType());
     auto tree = std::make_shared<openvdb::points::PointDataTree>();
-    std::vector<openvdb::points::PointDataTree::LeafNodeType*> leaves(nl);
+    using PLeaf = openvdb::points::PointDataTree::LeafNodeType;
+    std::vector<PLeaf*> leaves(nl);
     std::vector<uint64_t> begin(size_t(nl) + 1, 0);
-    for (int i = 0; i < nl; i++) {
-        leaves[i] = tree->touchLeaf(openvdb::Coord(o[3 * i], o[3 * i + 1], o[3 * i + 2]));
-        begin[i + 1] = begin[i] + ve[512 * size_t(i) + 511];
-    }
+    for (int i = 0; i < nl; i++) begin[i + 1] = begin[i] + ve[512 * size_t(i) + 511];
     tbb::parallel_for(0, nl, [&](int i) {
+        leaves[i] = new PLeaf(openvdb::Coord(o[3 * i], o[3 * i + 1], o[3 * i + 2]), 0, /*active=*/false);
         const uint32_t cnt = ve[512 * size_t(i) + 511];
         leaves[i]->initializeAttributes(pdescr, cnt);
         leaves[i]->appendAttribute(leaves[i]->attributeSet().descriptor(), pvdescr, 1);
@@ -339,6 +345,8 @@ inline void download_particles_finish(WorldHolder& h, openvdb::points::PointData
         std::memcpy(TestAttributeArray::bytes(pa), &P[3 * begin[i]], size_t(cnt) * 6);
         std::memcpy(TestAttributeArray::bytes(va), &V[3 * begin[i]], size_t(cnt) * 6);
     });
+    for (int i = 0; i < nl; i++) tree->addLeaf(leaves[i]);
+    release_tree(g->treePtr());
     g->setTree(tree);
     std::vector<const openvdb::points::PointDataTree::LeafNodeType*> cl;
     g->tree().getNodes(cl);
