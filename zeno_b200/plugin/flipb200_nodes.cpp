@@ -46,6 +46,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <initializer_list>
 #include <mutex>
@@ -233,6 +234,32 @@ void download_finish(WorldHolder& h, int id, typename GridT::Ptr& g) {
     typename Tree::Ptr tree;
     if constexpr (C == 3) tree = std::make_shared<Tree>(openvdb::Vec3f(st.bg[0], st.bg[1], st.bg[2]));
     else tree = std::make_shared<Tree>(st.bg[0]);
+    // same leaf set as the tree the grid holds now (FieldAddVector, CutCellWeight on a warm world, ...): overwrite its leaves in
+    // place -- no allocation, no page faults, nothing to free. The values and masks end up exactly as in a rebuilt tree.
+    if (g->tree().leafCount() == openvdb::Index32(n) && n > 0 && !has_foreign_tiles(g->tree())) {
+        std::vector<Leaf*> have(n, nullptr);
+        std::atomic<bool> all{true};
+        auto& cur = g->tree();
+        tbb::parallel_for(0, n, [&](int i) {
+            have[i] = cur.probeLeaf(openvdb::Coord(o[3 * i], o[3 * i + 1], o[3 * i + 2]));
+            if (!have[i]) all = false;
+        });
+        bool sameBg = true;
+        if constexpr (C == 3) sameBg = cur.background() == openvdb::Vec3f(st.bg[0], st.bg[1], st.bg[2]);
+        else sameBg = cur.background() == st.bg[0];
+        if (all && sameBg) {
+            tbb::parallel_for(0, n, [&](int i) {
+                Mask mask;
+                for (int k = 0; k < 8; k++) mask.template getWord<Mask::Word>(k) = m[8 * size_t(i) + k];
+                std::memcpy(have[i]->buffer().data(), &v[size_t(512) * C * i], sizeof(float) * 512 * C);
+                have[i]->setValueMask(mask);
+            });
+            std::vector<const Leaf*> cl;
+            g->tree().getNodes(cl);   // tree order: what the next upload's fingerprint walks
+            h.fp[id] = fingerprint<GridT, Leaf>(*g, cl);
+            return;
+        }
+    }
     // leaves are allocated and filled in parallel; only the pointer insertion into the tree is serial
     std::vector<Leaf*> leaves(n);
     tbb::parallel_for(0, n, [&](int i) {
