@@ -229,38 +229,62 @@ __global__ void __launch_bounds__(512) air_ring_kernel(TopoView t, const uint64_
     if ((threadIdx.x & 31) == 0) reinterpret_cast<uint32_t*>(sdfMask)[(size_t)leaf * 16 + (threadIdx.x >> 5)] = b;
 }
 
-// one layer of union_extrapolate (FF/vdb_velocity_extrapolator.cpp:618-657); blockIdx.y = channel (the three channels are independent:
-// one launch per layer instead of three)
-__global__ void __launch_bounds__(512) extrapolate_layer_kernel(TopoView t, const uint64_t* __restrict__ target,
-                                                                const uint64_t* __restrict__ validIn3,
-                                                                uint64_t* __restrict__ validOut3, float* __restrict__ val0,
-                                                                float* __restrict__ val1, float* __restrict__ val2, size_t stride) {
-    int leaf = blockIdx.x, off = threadIdx.x;
-    const uint64_t* validIn = validIn3 + blockIdx.y * stride;
-    uint64_t* validOut = validOut3 + blockIdx.y * stride;
-    float* val = blockIdx.y == 0 ? val0 : (blockIdx.y == 1 ? val1 : val2);
-    bool valid = mask_get(validIn, leaf, off);
-    bool tgt = mask_get(target, leaf, off);
-    bool newOn = valid;
-    if (tgt && !valid) {
-        int3 o = t.origin[leaf];
-        int x = o.x + (off >> 6), y = o.y + ((off >> 3) & 7), z = o.z + (off & 7);
-        int tw = 0;
-        float sum = 0.f;
+// one layer of union_extrapolate (FF/vdb_velocity_extrapolator.cpp:618-657). One WARP per (leaf, channel): a lane owns 16
+// consecutive voxels and walks only the candidates among them (in the target topology, not valid yet) -- on all but the leaves at
+// the rim of the valid region that is nothing, so a layer costs a read of the masks (round 1 and 2 launched 512 threads per leaf
+// and channel: 45 us per layer, bound by the 17 K CTAs, for work on a few hundred leaves). Same arithmetic per voxel.
+constexpr int EX_WARPS = 8;
+__global__ void __launch_bounds__(EX_WARPS * 32) extrapolate_layer_kernel(TopoView t, const uint64_t* __restrict__ target,
+                                                                           const uint64_t* __restrict__ validIn3,
+                                                                           uint64_t* __restrict__ validOut3, float* __restrict__ val0,
+                                                                           float* __restrict__ val1, float* __restrict__ val2, size_t stride) {
+    const int item = blockIdx.x * EX_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (item >= t.n * 3) return;
+    const int ch = item / t.n, leaf = item - ch * t.n;
+    const uint64_t* validIn = validIn3 + ch * stride;
+    uint64_t* validOut = validOut3 + ch * stride;
+    float* val = ch == 0 ? val0 : (ch == 1 ? val1 : val2);
+    const uint32_t tg = (reinterpret_cast<const uint32_t*>(target)[(size_t)leaf * 16 + (lane >> 1)] >> ((lane & 1) * 16)) & 0xffffu;
+    const uint32_t vd = (reinterpret_cast<const uint32_t*>(validIn)[(size_t)leaf * 16 + (lane >> 1)] >> ((lane & 1) * 16)) & 0xffffu;
+    uint32_t cand = tg & ~vd, newv = vd;
+    if (__any_sync(0xffffffffu, cand != 0)) {
+        // the warp's candidates as one list, dealt round-robin to the lanes (a rim leaf holds a few dozen to ~200, unevenly spread)
+        __shared__ uint16_t sList[EX_WARPS][LEAF];
+        __shared__ uint32_t sNew[EX_WARPS][16];
+        uint16_t* list = sList[threadIdx.x >> 5];
+        uint32_t* snew = sNew[threadIdx.x >> 5];
+        const int mine = __popc(cand);
+        int pre = mine;
 #pragma unroll
-        for (int d = 0; d < 6; d++) {
-            int dir = d >> 1, s = (d & 1) ? 1 : -1;
-            int nx = x + (dir == 0 ? s : 0), ny = y + (dir == 1 ? s : 0), nz = z + (dir == 2 ? s : 0);
-            int nl, no;
-            int lx = (off >> 6) + (dir == 0 ? s : 0), ly = ((off >> 3) & 7) + (dir == 1 ? s : 0), lz = (off & 7) + (dir == 2 ? s : 0);
-            if ((unsigned)lx < 8u && (unsigned)ly < 8u && (unsigned)lz < 8u) { nl = leaf; no = (lx << 6) | (ly << 3) | lz; }
-            else { nl = topo_find(t, nx, ny, nz); no = voxel_off(nx, ny, nz); }
-            if (nl >= 0 && mask_get(validIn, nl, no)) { tw++; sum = __fadd_rn(sum, val[(size_t)nl * LEAF + no]); }
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, d); if (lane >= d) pre += v; }
+        const int total = __shfl_sync(0xffffffffu, pre, 31);
+        int at = pre - mine;
+        while (cand) { const int bit = __ffs(cand) - 1; cand &= cand - 1; list[at++] = (uint16_t)(lane * 16 + bit); }
+        if (lane < 16) snew[lane] = 0u;
+        __syncwarp();
+        const int3 o = t.origin[leaf];
+        for (int k = lane; k < total; k += 32) {
+            const int off = list[k];
+            const int x = o.x + (off >> 6), y = o.y + ((off >> 3) & 7), z = o.z + (off & 7);
+            int tw = 0;
+            float sum = 0.f;
+#pragma unroll
+            for (int d = 0; d < 6; d++) {
+                const int dir = d >> 1, s = (d & 1) ? 1 : -1;
+                const int nx = x + (dir == 0 ? s : 0), ny = y + (dir == 1 ? s : 0), nz = z + (dir == 2 ? s : 0);
+                int nl, no;
+                const int lx = (off >> 6) + (dir == 0 ? s : 0), ly = ((off >> 3) & 7) + (dir == 1 ? s : 0), lz = (off & 7) + (dir == 2 ? s : 0);
+                if ((unsigned)lx < 8u && (unsigned)ly < 8u && (unsigned)lz < 8u) { nl = leaf; no = (lx << 6) | (ly << 3) | lz; }
+                else { nl = topo_find(t, nx, ny, nz); no = voxel_off(nx, ny, nz); }
+                if (nl >= 0 && mask_get(validIn, nl, no)) { tw++; sum = __fadd_rn(sum, val[(size_t)nl * LEAF + no]); }
+            }
+            if (tw != 0) { val[(size_t)leaf * LEAF + off] = __fdiv_rn(sum, (float)tw); atomicOr(&snew[off >> 5], 1u << (off & 31)); }
         }
-        if (tw != 0) { val[(size_t)leaf * LEAF + off] = __fdiv_rn(sum, (float)tw); newOn = true; }
+        __syncwarp();
+        newv |= (snew[lane >> 1] >> ((lane & 1) * 16)) & 0xffffu;
     }
-    unsigned b = __ballot_sync(0xffffffffu, newOn);
-    if ((threadIdx.x & 31) == 0) reinterpret_cast<uint32_t*>(validOut)[(size_t)leaf * 16 + (threadIdx.x >> 5)] = b;
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, newv, 1);
+    if ((lane & 1) == 0) reinterpret_cast<uint32_t*>(validOut)[(size_t)leaf * 16 + (lane >> 1)] = newv | (other << 16);
 }
 // to_vec3 (packed3grids.cpp:49-83): union mask; a channel that is off contributes 0
 __global__ void __launch_bounds__(512) to_vec3_kernel(int n, const uint64_t* __restrict__ chMask, float* __restrict__ v0,
@@ -291,7 +315,7 @@ void union_extrapolate(World* w, int nLayer, GridV& vel, uint64_t* chMask, const
     uint64_t* nxt = tmp.p;
     for (int layer = 0; layer < nLayer; layer++) {
         FB_LAUNCH(w, "extrapolate_layer", (size_t)3 * t.n * (2048 + 192))
-            extrapolate_layer_kernel<<<dim3(t.n, 3), 512, 0, w->stream>>>(t.view(), targetMask, cur, nxt, vel.val[0].p, vel.val[1].p, vel.val[2].p, stride);
+            extrapolate_layer_kernel<<<(3 * t.n + EX_WARPS - 1) / EX_WARPS, EX_WARPS * 32, 0, w->stream>>>(t.view(), targetMask, cur, nxt, vel.val[0].p, vel.val[1].p, vel.val[2].p, stride);
         check_launch("extrapolate_layer");
         std::swap(cur, nxt);
     }
