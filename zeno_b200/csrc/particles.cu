@@ -76,18 +76,29 @@ __global__ void scatter_kernel(const uint32_t* __restrict__ keys, uint64_t n, co
 }
 // per voxel: ascending order of the source indices (= stable), then apply the per-voxel cap
 __global__ void fixup_kernel(const uint32_t* __restrict__ startU, const uint32_t* __restrict__ startC,
-                             size_t nv, uint32_t* __restrict__ perm, uint32_t* __restrict__ perm2) {
+                             size_t nv, uint32_t* perm, uint32_t* __restrict__ perm2) {
     size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nv) return;
-    uint32_t b = startU[v], e = startU[v + 1];
+    const uint32_t b = startU[v], e = startU[v + 1];
+    const uint32_t cb = startC[v], keep = startC[v + 1] - cb;
+    if (e - b <= 64u) {
+        // rank sort: an entry goes to (number of smaller entries); the source indices are distinct. No store feeds a later load,
+        // unlike the in-place insertion sort this replaces (214 us: every step waited for its own write to come back).
+        for (uint32_t i = b; i < e; i++) {
+            const uint32_t x = __ldg(&perm[i]);
+            uint32_t r = 0;
+            for (uint32_t j = b; j < e; j++) r += __ldg(&perm[j]) < x ? 1u : 0u;
+            if (r < keep) perm2[cb + r] = x;
+        }
+        return;
+    }
     for (uint32_t i = b + 1; i < e; i++) {
         uint32_t x = perm[i];
         uint32_t j = i;
         while (j > b && perm[j - 1] > x) { perm[j] = perm[j - 1]; j--; }
         perm[j] = x;
     }
-    uint32_t cb = startC[v], ce = startC[v + 1];
-    for (uint32_t j = 0; j < ce - cb; j++) perm2[cb + j] = perm[b + j];
+    for (uint32_t j = 0; j < keep; j++) perm2[cb + j] = perm[b + j];
 }
 __global__ void gather_kernel(const uint32_t* __restrict__ perm, uint64_t m, const uint32_t* __restrict__ i0,
                               const uint32_t* __restrict__ i1, const uint32_t* __restrict__ i2,
