@@ -591,7 +591,7 @@ void g2p_advect_sheetty(World* w, float dt, float dx, int surfaceSize, int rkOrd
         mask_dilate(w, *pool, lsdf.mask.p, nm.p, true);
         for (int i = 1; i < 5; i++) { mask_dilate(w, *pool, nm.p, nm2.p, true); std::swap(nm, nm2); }
     }
-    DBuf<int3> ijk(n + 1, w->stream), origins(n + 1, w->stream);
+    DBuf<int3> ijk(n + 1, w->stream);
     DBuf<uint8_t> alive(n + 1, w->stream);
     if (w->capturePreCodec) {
         w->preCodecPos.alloc(3 * n + 1, w->stream);
@@ -669,11 +669,9 @@ void g2p_advect_sheetty(World* w, float dt, float dx, int surfaceSize, int rkOrd
         DBuf<int3> mijk;
         uint64_t nm = 0;
         { FB_PHASE(w, "g2p dd_migrate"); dd_migrate(w, range[0], range[1], i0.p, i1.p, i2.p, ijk.p, alive.p, m0, m1, m2, mijk, &nm); }
-        DBuf<int3> morig(nm + 1, w->stream);
         TopoPtr newPool;
         { FB_PHASE(w, "g2p topo");
-          origins_from_ijk(w, mijk.p, nm, morig.p);
-          newPool = topo_from_origins_dev(w, morig.p, (int)nm, true); }
+          newPool = topo_from_origins_dev(w, mijk.p, (int)nm, true); }   // the topology kernels only use (coordinate >> 3): voxel coordinates do
         DBuf<uint32_t> keys(nm + 1, w->stream);
         FB_PHASE(w, "g2p rebin");
         keys_from_ijk(w, newPool, mijk.p, nullptr, nm, keys.p);
@@ -684,8 +682,7 @@ void g2p_advect_sheetty(World* w, float dt, float dx, int surfaceSize, int rkOrd
     // K2: new pool from the target leaves (+ring), keys, stable counting sort with the voxel cap
     TopoPtr newPool;
     { FB_PHASE(w, "g2p topo");
-      origins_from_ijk(w, ijk.p, n, origins.p);
-      newPool = topo_from_origins_dev(w, origins.p, (int)n, true); }
+      newPool = topo_from_origins_dev(w, ijk.p, (int)n, true); }   // the topology kernels only use (coordinate >> 3): voxel coordinates do
     FB_PHASE(w, "g2p rebin");
     DBuf<uint32_t> keys(n + 1, w->stream);
     keys_from_ijk(w, newPool, ijk.p, alive.p, n, keys.p);
