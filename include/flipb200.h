@@ -57,7 +57,7 @@ enum {
     FLIPB200_SOLID_SDF = 6,       /* "SolidSDF"          float, VERTEX centred, background 3dx */
     FLIPB200_PRESSURE = 7,        /* "Pressure"          float */
     FLIPB200_DIVERGENCE = 8,      /* "Divergence"        float (the PPE right-hand side) */
-    FLIPB200_CURVATURE = 9,       /* "Curvature"         float (unused: tension path is out of scope) */
+    FLIPB200_CURVATURE = 9,       /* "Curvature"         float, read when flipb200_set_surface_tension enabled the tension terms */
     FLIPB200_KILLER_SDF = 10,     /* "KillerSDF" socket of KillParticlesInSDF: any float grid, sampled in ITS index space */
     FLIPB200_NUM_GRIDS = 11
 };
@@ -200,6 +200,13 @@ int flipb200_residual_history(flipb200_world* w, float* out);
 /* SubtractPressureGradient::apply (FF/nosys/SubtractPressureGradient.cpp:25-66) ->
  * apply_pressure_gradient (FF/FLIP_vdb.cpp:2863-2967) + union_extrapolate */
 int flipb200_subtract_grad(flipb200_world* w, float dt, float dx, int velExtraLayer);
+/* The Density / SurfaceTension sockets of AssembleSolvePPE and SubtractPressureGradient (FF/nosys/SolvePoissonPressureEqn.cpp:43-45,
+ * SubtractPressureGradient.cpp:21-23): state of the world, read by the two calls above. tensionCoef > 0 enables the reference's tension
+ * terms with tension = 2 tensionCoef / density -- BuildPoissonRhs_withTension (FF/simd_vdb_poisson_uaamg.cpp:95-209: a face towards an
+ * air cell adds dt/dx^2 * weight * tension * (theta curvOther + (1 - theta) curvThis) / theta to the right-hand side) and the ghost
+ * pressure of the gradient (FF/FLIP_vdb.cpp:2932-2939). The curvature is grid slot FLIPB200_CURVATURE (read by voxel coordinate, any
+ * leaf set; background where absent, as the reference's accessor). Default: density 1000, tensionCoef 0 (off). */
+int flipb200_set_surface_tension(flipb200_world* w, float density, float tensionCoef);
 
 /* One substep of the packaged chain, device resident (no host copies in between):
  * G2PAdvectorSheetty -> FLIP_P2G -> CutCellWeight -> PushOutLiquidSDF -> FieldAddVector(g*dt)

@@ -33,6 +33,9 @@ struct World {
     // diagnostics
     int pcgIterations = 0;
     int pcgStatus = 0;
+    // AssembleSolvePPE / SubtractPressureGradient sockets Density and SurfaceTension (FF/nosys/SolvePoissonPressureEqn.cpp:43-45):
+    // tension is enabled when the coefficient is > 0 and enters as 2 coef / density (FF/FLIP_vdb.cpp:3052, :2875)
+    float density = 1000.f, tensionCoef = 0.f;
     float solveRelTol = 5e-5f;   // AssembleSolvePPE: the node's mRelativeTolerance / mMaxIteration (uaamg.cpp defaults), overridable by the tests
     int solveMaxIter = 100;
     int mgLevels = 0;

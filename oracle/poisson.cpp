@@ -577,9 +577,13 @@ void xpay(const Level& L, float alpha, const Vec& x, Vec& y) {  // y = x + a*y (
                 y[size_t(l) * 512 + off] = x[size_t(l) * 512 + off] + alpha * y[size_t(l) * 512 + off];
 }
 
-// BuildPoissonRhs (uaamg.cpp:18-93)
-void buildRhs(const World& w, const Level& L, const Packed3& vel, Vec& rhs, float dx) {
+// BuildPoissonRhs (uaamg.cpp:18-93); with SurfaceTension > 0 BuildPoissonRhs_withTension (uaamg.cpp:95-209): a face towards an
+// air cell adds dt/dx^2 * weight * tension * (theta curvOther + (1 - theta) curvThis) / theta, tension = 2 coef / density
+void buildRhs(const World& w, const Level& L, const Packed3& vel, Vec& rhs, float dx, float dt) {
     float invdx = 1.0f / dx;
+    const bool enableTension = w.tensionCoef > 0;
+    const float tension = 2 * w.tensionCoef / w.density;
+    const float dtOverDxSqr = dt / (dx * dx);
     for (int l = 0; l < L.leafCount(); l++) {
         Coord o = L.origins[l];
         for (int off = 0; off < 512; off++) {
@@ -587,6 +591,7 @@ void buildRhs(const World& w, const Level& L, const Packed3& vel, Vec& rhs, floa
             Coord g(o.x + (off >> 6), o.y + ((off >> 3) & 7), o.z + (off & 7));
             float r = 0, weightSum = 0;
             bool hasNonZero = false;
+            const float phiThis = enableTension ? w.liquidSDF.get(g) : 0.f, curvThis = enableTension ? w.curvature.get(g) : 0.f;
             for (int i = 0; i < 6; i++) {
                 int ch = i / 2;
                 bool pos = (i % 2) == 0;
@@ -599,6 +604,16 @@ void buildRhs(const World& w, const Level& L, const Packed3& vel, Vec& rhs, floa
                 float sv = w.solidVelocity.get(ch, nc);
                 if (pos) r -= invdx * (weight * v + (1.0f - weight) * sv);
                 else r += invdx * (weight * v + (1.0f - weight) * sv);
+                if (enableTension) {
+                    Coord pc = g;
+                    pc[ch] += pos ? 1 : -1;
+                    const float phiOther = w.liquidSDF.get(pc), curvOther = w.curvature.get(pc);
+                    if (phiThis < 0.f && phiOther >= 0.f) {
+                        float theta = fraction_inside(phiThis, phiOther);
+                        if (theta < 0.02f) theta = 0.02f;
+                        r += dtOverDxSqr * weight * tension * (theta * curvOther + (1.f - theta) * curvThis) / theta;
+                    }
+                }
             }
             if (!hasNonZero || weightSum < 0.1) r = 0;
             rhs[size_t(l) * 512 + off] = r;
@@ -626,7 +641,7 @@ void node_AssembleSolvePPE(World& w, float dt, float dx) {
     w.numDof = L0.numDof;
     size_t n = size_t(L0.leafCount()) * 512;
     Vec rhs(n, 0.f), pressure(n, 0.f), r(n, 0.f), p(n, 0.f), z(n, 0.f);
-    buildRhs(w, L0, vel, rhs, dx);
+    buildRhs(w, L0, vel, rhs, dx, dt);
 
     // solveMultigridPCG (uaamg.cpp:2332-2403); mRelativeTolerance 5e-5, mMaxIteration 100
     const float relTol = w.solveRelTol;

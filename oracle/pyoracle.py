@@ -175,6 +175,12 @@ class OracleWorld:
         if rc != 0:
             raise RuntimeError("FLIPApplyBoundary failed: " + self._err())
 
+    def set_surface_tension(self, density: float = 1000.0, coef: float = 0.0):
+        """the Density / SurfaceTension sockets of AssembleSolvePPE and SubtractPressureGradient (coef > 0 enables the tension terms)"""
+        rc = self.lib.orc_set_surface_tension(self.h, C.c_float(density), C.c_float(coef))
+        if rc != 0:
+            raise RuntimeError("set_surface_tension failed")
+
     def _err(self):
         try:
             return (self.lib.orc_last_error() or b"").decode()

@@ -57,6 +57,7 @@ struct RefWorld {
     Vec3fGrid::Ptr vec[5];
     FloatGrid::Ptr flt[G_NUM];
     bool hasSolidSDF = false, hasSolidVel = false, hasCurvature = false;
+    float density = 1000.f, tensionCoef = 0.f;   // the Density / SurfaceTension sockets
     int iterations = 0, status = 0, levels = 0, numDof = 0;
     float relResidual = 0.f;
     std::vector<float> history;
@@ -378,7 +379,7 @@ int ref_solve_ppe(void* wp, float dt, float dx, int* iters, float* relResidual, 
     packed_velocity.from_vec3(w->vec[G_VELOCITY]);
     std::string log = captureStdout([&] {
         FLIP_vdb::solve_pressure_simd_uaamg(w->flt[G_LIQUIDSDF], curvatureGrid, w->flt[G_DIVERGENCE], w->flt[G_PRESSURE],
-                                            w->vec[G_FACEWEIGHT], packed_velocity, w->vec[G_SOLIDVEL], 1000.f, 0.f, false, dt, dx);
+                                            w->vec[G_FACEWEIGHT], packed_velocity, w->vec[G_SOLIDVEL], w->density, w->tensionCoef, w->tensionCoef > 0, dt, dx);
     });
     packed_velocity.to_vec3(w->vec[G_VELOCITY]);
     // progress lines printed by the reference: "levels: %zd Dof:%d" (uaamg.cpp:1990), "init error%e" (:2346),
@@ -473,6 +474,13 @@ int ref_residual_history(void* wp, float* out) {
     std::memcpy(out, w->history.data(), sizeof(float) * w->history.size());
     return 0;
 }
+int ref_set_surface_tension(void* wp, float density, float coef) {
+    RefWorld* w = static_cast<RefWorld*>(wp);
+    w->density = density; w->tensionCoef = coef;
+    return 0;
+}
+float ref_density(void* wp) { return static_cast<RefWorld*>(wp)->density; }
+float ref_tension_coef(void* wp) { return static_cast<RefWorld*>(wp)->tensionCoef; }
 // SubtractPressureGradient::apply (FF/nosys/SubtractPressureGradient.cpp:25-66)
 int ref_subtract_grad(void* wp, float dt, float dx, int velExtraLayer) {
     RefWorld* w = static_cast<RefWorld*>(wp);
@@ -480,7 +488,7 @@ int ref_subtract_grad(void* wp, float dt, float dx, int velExtraLayer) {
     packed_FloatGrid3 packed_velocity;
     packed_velocity.from_vec3(w->vec[G_VELOCITY]);
     FLIP_vdb::apply_pressure_gradient(w->flt[G_LIQUIDSDF], w->flt[G_SOLIDSDF], w->flt[G_PRESSURE], w->vec[G_FACEWEIGHT], packed_velocity,
-                                      w->vec[G_SOLIDVEL], curvatureGrid, 1000.f, 0.f, false, dt, dx);
+                                      w->vec[G_SOLIDVEL], curvatureGrid, w->density, w->tensionCoef, w->tensionCoef > 0, dt, dx);
     vdb_velocity_extrapolator::union_extrapolate(velExtraLayer, packed_velocity.v[0], packed_velocity.v[1], packed_velocity.v[2],
                                                  &(w->flt[G_LIQUIDSDF]->tree()));
     packed_velocity.to_vec3(w->vec[G_VELOCITY]);

@@ -191,8 +191,11 @@ float node_CFL_dt(World& w) {
     return w.dx / (std::fabs(mv) + 1e-6f);
 }
 
-// FLIP_vdb::apply_pressure_gradient (FF/FLIP_vdb.cpp:2863-2967), tension disabled.
+// FLIP_vdb::apply_pressure_gradient (FF/FLIP_vdb.cpp:2863-2967); with SurfaceTension > 0 the pressure of an air cell next to the
+// face is replaced by tension * (curvature mixed by theta), :2932-2939
 static void apply_pressure_gradient(World& w, Packed3& vel, float dt, float dx) {
+    const bool enableTension = w.tensionCoef > 0;
+    const float tension = 2 * w.tensionCoef / w.density;
     for (int ch = 0; ch < 3; ch++) {
         FloatGrid& g = vel.v[ch];
         for (int l = 0; l < g.leafCount(); l++) {
@@ -215,6 +218,11 @@ static void apply_pressure_gradient(World& w, Packed3& vel, float dt, float dx) 
                         if (phiThis >= 0 || phiBelow >= 0) {
                             theta = fraction_inside(phiBelow, phiThis);
                             if (theta < 0.02f) theta = 0.02f;
+                            if (enableTension) {
+                                const float curvThis = w.curvature.get(c), curvBelow = w.curvature.get(lo);
+                                if (phiThis >= 0) pThis = tension * (theta * curvThis + (1.f - theta) * curvBelow);
+                                else if (phiBelow >= 0) pBelow = tension * (theta * curvBelow + (1.f - theta) * curvThis);
+                            }
                         }
                         float velUpdate = -dt * (float)(pThis - pBelow) / dx / theta;
                         updated += velUpdate;

@@ -564,3 +564,66 @@ def test_flip_apply_boundary_oracle_plugin_and_reference_node(oracle_lib):
     assert int((ref["values"] < 0).sum()) > int((solid["values"] < 0).sum()) + 500, "the sphere must add solid voxels"
     for w, what in zip(worlds[1:], ("oracle", "plugin node")):
         util.compare_grids(w.get_grid("SolidSDF"), ref, f"FLIPApplyBoundary: {what} vs the reference node", tol=0.0, check_inactive=True)
+
+
+def _tension_worlds(classes, seed=4):
+    """A dam-break state right before the pressure solve, a synthetic curvature field on the liquid SDF's leaves (the reference reads
+    it by voxel coordinate), Density 1000 and SurfaceTension 5 (tension = 2 coef / density = 0.01: ghost pressures of +-0.2)."""
+    from zeno_b200 import scenes
+    N = 48
+    pos, vel, dx = scenes.dam_break_points(N, seed=seed, random_velocity=True)
+    solid = scenes.box_solid_sdf(N, dx)
+    worlds = [cls(dx) for cls in classes]
+    dt = 0.006
+    for w in worlds:
+        w.set_grid("SolidSDF", solid)
+        w.PrimToVDBPointDataGrid(pos, vel * np.float32(0.3))
+        w.FLIP_P2G(dx, 3)
+        w.CutCellWeight()
+        w.PushOutLiquidSDF(dx)
+        w.FieldAddVector(0.0, -9.8 * dt, 0.0)
+    sdf = worlds[-1].get_grid("LiquidSDF")
+    curv = {k: np.array(v, copy=True) for k, v in sdf.items()}
+    o = curv["origins"].astype(np.float64)
+    off = np.arange(512)
+    loc = np.stack([off >> 6, (off >> 3) & 7, off & 7], axis=1).astype(np.float64)
+    x = o[:, None, :] + loc[None, :, :]
+    curv["values"] = (20.0 * np.sin(0.7 * x[..., 0] + 0.3 * x[..., 2]) * np.cos(0.5 * x[..., 1])).astype(np.float32).reshape(curv["values"].shape)
+    curv["bg"] = np.array([0.0], np.float32)
+    for w in worlds:
+        w.set_grid("Curvature", curv)
+        w.set_surface_tension(1000.0, 5.0)
+    return worlds, dx, dt
+
+
+def test_surface_tension_oracle_plugin_and_reference_nodes(oracle_lib):
+    """SURVEY 8f-4, the tension terms of the two core nodes: BuildPoissonRhs_withTension (FF/simd_vdb_poisson_uaamg.cpp:95-209) inside
+    AssembleSolvePPE and the ghost pressure of apply_pressure_gradient (FF/FLIP_vdb.cpp:2932-2939) inside SubtractPressureGradient.
+    The REAL node classes (Density / SurfaceTension / Curvature sockets wired), the oracle and the drop-in's nodes from the same state."""
+    from oracle import pyoracle
+    if not pyoracle.ref_available() or not hasattr(pyoracle.load_ref(), "rn_set_surface_tension"):
+        pytest.skip("oracle/_ref with the tension hooks is not available here")
+    from oracle.pyoracle import OracleWorld, PluginWorld, RefNodeWorld
+    (rw, ow, pw), dx, dt = _tension_worlds((RefNodeWorld, OracleWorld, PluginWorld))
+    plain = OracleWorld(dx)   # the same state without tension: the terms must matter in this scene
+    for g in ("SolidSDF", "LiquidSDF", "Velocity", "CellFWeight", "SolidVelocity"):
+        try:
+            plain.set_grid(g, ow.get_grid(g))
+        except Exception:
+            pass
+    for w in (rw, ow, pw, plain):
+        w.AssembleSolvePPE(dt, dx)
+    ref_rhs, ref_p = rw.get_grid("Divergence"), rw.get_grid("Pressure")
+    e0 = util.compare_grids(plain.get_grid("Divergence"), ow.get_grid("Divergence"), "rhs without vs with tension", tol=10.0, check_inactive=False)
+    assert e0 > 1e-2, f"the tension term must change the right-hand side (relative L2 {e0})"
+    util.compare_grids(ow.get_grid("Divergence"), ref_rhs, "tension RHS: oracle vs reference node", tol=1e-6, check_inactive=False)
+    util.compare_grids(ow.get_grid("Pressure"), ref_p, "tension pressure: oracle vs reference node", tol=util.REF_TOL["ppe"], check_inactive=False)
+    util.compare_grids(pw.get_grid("Divergence"), ow.get_grid("Divergence"), "tension RHS: plugin node vs oracle", tol=0.0, check_inactive=False)
+    util.compare_grids(pw.get_grid("Pressure"), ow.get_grid("Pressure"), "tension pressure: plugin node vs oracle", tol=0.0, check_inactive=False)
+    # the gradient from ONE pressure field (the reference's), so that only the gradient's own arithmetic is compared
+    for w in (ow, pw):
+        w.set_grid("Pressure", ref_p)
+    for w in (rw, ow, pw):
+        w.SubtractPressureGradient(dt, dx, 3)
+    util.compare_grids(ow.get_grid("Velocity"), rw.get_grid("Velocity"), "tension gradient: oracle vs reference node", tol=1e-6, check_inactive=False)
+    util.compare_grids(pw.get_grid("Velocity"), ow.get_grid("Velocity"), "tension gradient: plugin node vs oracle", tol=0.0, check_inactive=False)

@@ -225,3 +225,27 @@ def test_flip_apply_boundary_matches_oracle(gpu_lib, oracle_lib):
         w.CutCellWeight()
     util.compare_grids(gw.get_grid("CellFWeight"), ow.get_grid("CellFWeight"), "CutCellWeight after FLIPApplyBoundary", tol=0.0, check_inactive=False)
     gw.close()
+
+
+def test_surface_tension_matches_oracle(gpu_lib, oracle_lib):
+    """The tension terms of AssembleSolvePPE / SubtractPressureGradient (pinned against the reference's node classes in
+    tests/test_ref_pin_cpu.py): CUDA right-hand side == oracle bit for bit, pressure within the solver tolerance, same iterations
+    (<= 1.1x), projected velocity from one pressure field bit for bit."""
+    import math
+    from oracle.pyoracle import OracleWorld
+    from tests.test_ref_pin_cpu import _tension_worlds
+    from zeno_b200 import abi
+    (gw, ow), dx, dt = _tension_worlds((abi.World, OracleWorld))
+    rg, ro = gw.AssembleSolvePPE(dt, dx), ow.AssembleSolvePPE(dt, dx)
+    util.compare_grids(gw.get_grid("Divergence"), ow.get_grid("Divergence"), "tension RHS", tol=0.0, check_inactive=False)
+    assert rg["status"] == 0 and ro["status"] == 0 and rg["iterations"] <= math.ceil(1.1 * ro["iterations"]), (rg, ro)
+    util.compare_grids(gw.get_grid("Pressure"), ow.get_grid("Pressure"), "tension pressure", tol=util.REF_TOL["ppe"], check_inactive=False)
+    gw.set_grid("Pressure", ow.get_grid("Pressure"))
+    for w in (gw, ow):
+        w.SubtractPressureGradient(dt, dx, 3)
+    util.compare_grids(gw.get_grid("Velocity"), ow.get_grid("Velocity"), "tension gradient", tol=0.0, check_inactive=False)
+    # switching the terms off again restores the plain right-hand side
+    gw.set_surface_tension(1000.0, 0.0); ow.set_surface_tension(1000.0, 0.0)
+    gw.AssembleSolvePPE(dt, dx); ow.AssembleSolvePPE(dt, dx)
+    util.compare_grids(gw.get_grid("Divergence"), ow.get_grid("Divergence"), "plain RHS after tension", tol=0.0, check_inactive=False)
+    gw.close()

@@ -572,6 +572,13 @@ int flipb200_apply_boundary(flipb200_world* w, int movingGrid, int movingVertexC
         sync(w);
     });
 }
+int flipb200_set_surface_tension(flipb200_world* w, float density, float tensionCoef) {
+    return guarded([&] {
+        FB_REQUIRE(w && density > 0.f, FLIPB200_ERR_ARG, "set_surface_tension: bad argument");
+        FB_REQUIRE(!(tensionCoef > 0.f) || !dd_on(w), FLIPB200_ERR_STATE, "surface tension is not available under slab decomposition yet (the curvature grid has no ghost refresh)");
+        w->density = density; w->tensionCoef = tensionCoef;
+    });
+}
 int flipb200_particles_add_dv(flipb200_world* w, float dvx, float dvy, float dvz) {
     return guarded([&] {
         FB_REQUIRE(w, FLIPB200_ERR_ARG, "particles_add_dv: null world");

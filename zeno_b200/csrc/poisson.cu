@@ -242,11 +242,13 @@ __global__ void __launch_bounds__(512) coarsen_kernel(LevelView F, TopoView ct, 
 }
 
 // BuildPoissonRhs (uaamg.cpp:44-86)
+// the surface-tension terms of the right-hand side (enabled by SurfaceTension > 0): liquid SDF on the pool, curvature on its own topology
+struct TensionArgs { int on; float tension, dtOverDxSqr; const float* phi; float phiBg; TopoView ct; const float* curv; float curvBg; };
 __global__ void __launch_bounds__(512) rhs_kernel(TopoView t, const uint64_t* __restrict__ dof,
                                                   const float* __restrict__ fw0, const float* __restrict__ fw1, const float* __restrict__ fw2,
                                                   const float* __restrict__ v0, const float* __restrict__ v1, const float* __restrict__ v2,
                                                   const float* __restrict__ s0, const float* __restrict__ s1, const float* __restrict__ s2,
-                                                  float invdx, float* __restrict__ rhs) {
+                                                  float invdx, float* __restrict__ rhs, TensionArgs T) {
     int leaf = blockIdx.x, off = threadIdx.x;
     size_t i = (size_t)leaf * LEAF + off;
     float r = 0.f;
@@ -255,6 +257,8 @@ __global__ void __launch_bounds__(512) rhs_kernel(TopoView t, const uint64_t* __
         int g[3] = {o.x + (off >> 6), o.y + ((off >> 3) & 7), o.z + (off & 7)};
         float weightSum = 0.f;
         bool nonZero = false;
+        const float phiThis = T.on ? T.phi[i] : 0.f;
+        const float curvThis = T.on ? grid_get(T.ct, T.curv, T.curvBg, g[0], g[1], g[2]) : 0.f;
 #pragma unroll
         for (int f = 0; f < 6; f++) {
             int ch = f >> 1;
@@ -274,6 +278,18 @@ __global__ void __launch_bounds__(512) rhs_kernel(TopoView t, const uint64_t* __
             if (weight != 0.f) nonZero = true;
             float flux = __fmul_rn(invdx, __fadd_rn(__fmul_rn(weight, vel), __fmul_rn(__fsub_rn(1.0f, weight), svel)));
             if (pos) r = __fsub_rn(r, flux); else r = __fadd_rn(r, flux);
+            if (T.on) {   // BuildPoissonRhs_withTension (uaamg.cpp:187-192): the cell across this face is air
+                int c[3] = {g[0], g[1], g[2]};
+                c[ch] += pos ? 1 : -1;
+                const float phiOther = grid_get(t, T.phi, T.phiBg, c[0], c[1], c[2]);
+                if (phiThis < 0.f && phiOther >= 0.f) {
+                    const float curvOther = grid_get(T.ct, T.curv, T.curvBg, c[0], c[1], c[2]);
+                    float theta = fraction_inside2(phiThis, phiOther);
+                    if (theta < 0.02f) theta = 0.02f;
+                    const float mix = __fadd_rn(__fmul_rn(theta, curvOther), __fmul_rn(__fsub_rn(1.f, theta), curvThis));
+                    r = __fadd_rn(r, __fdiv_rn(__fmul_rn(__fmul_rn(__fmul_rn(T.dtOverDxSqr, weight), T.tension), mix), theta));
+                }
+            }
         }
         if (!nonZero || (double)weightSum < 0.1) r = 0.f;
     }
@@ -2503,8 +2519,17 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
     const size_t nv = (size_t)n * LEAF;
     DBuf<float> rhs(nv, w->stream), x(nv, w->stream), r(nv, w->stream), p(nv, w->stream), z(nv, w->stream);
     x.zero(); p.zero(); z.zero(); r.zero();
+    TensionArgs T;
+    memset(&T, 0, sizeof(T));
+    if (w->tensionCoef > 0.f) {   // enable_tension (FF/nosys/SolvePoissonPressureEqn.cpp:45); tension = 2 coef / density (FF/FLIP_vdb.cpp:3052)
+        GridF& cv = w->F(FLIPB200_CURVATURE);
+        T.on = 1; T.tension = 2 * w->tensionCoef / w->density; T.dtOverDxSqr = dt / (dx * dx);
+        T.phi = phi.val.p; T.phiBg = phi.bg;
+        if (cv.topo) { T.ct = cv.topo->view(); T.curv = cv.val.p; }
+        T.curvBg = cv.bg;
+    }
     FB_LAUNCH(w, "mg_rhs", nv * 40) rhs_kernel<<<n, 512, 0, w->stream>>>(pool->view(), L0.dof.p, fw.val[0].p, fw.val[1].p, fw.val[2].p, vel.val[0].p, vel.val[1].p, vel.val[2].p,
-                                                                        w->solidVelView[0].p, w->solidVelView[1].p, w->solidVelView[2].p, 1.0f / dx, rhs.p);
+                                                                        w->solidVelView[0].p, w->solidVelView[1].p, w->solidVelView[2].p, 1.0f / dx, rhs.p, T);
     check_launch("rhs");
 
     // solveMultigridPCG (uaamg.cpp:2332-2403)

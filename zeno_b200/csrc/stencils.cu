@@ -125,12 +125,13 @@ __global__ void __launch_bounds__(512) absmax3_kernel(const uint64_t* __restrict
 }
 
 // apply_pressure_gradient (FF/FLIP_vdb.cpp:2863-2967), one channel; tension disabled
+struct GradTension { int on; float tension; TopoView ct; const float* curv; float curvBg; };
 __global__ void __launch_bounds__(512) pressure_gradient_kernel(TopoView t, int ch, const uint64_t* __restrict__ velMask,
                                                                 float* __restrict__ vel, const float* __restrict__ fw,
                                                                 const float* __restrict__ phi, float phiBg,
                                                                 const float* __restrict__ prs, const uint64_t* __restrict__ prsMask,
                                                                 const float* __restrict__ svel, uint64_t* __restrict__ chMaskOut,
-                                                                float dt, float dx) {
+                                                                float dt, float dx, GradTension T) {
     int leaf = blockIdx.x, off = threadIdx.x;
     bool on = mask_get(velMask, leaf, off);
     bool keep = false;
@@ -155,6 +156,11 @@ __global__ void __launch_bounds__(512) pressure_gradient_kernel(TopoView t, int 
                 if (phiThis >= 0.f || phiBelow >= 0.f) {
                     theta = fraction_inside2(phiBelow, phiThis);
                     if (theta < 0.02f) theta = 0.02f;
+                    if (T.on) {   // FF/FLIP_vdb.cpp:2932-2939: the air cell's pressure is the tension jump
+                        const float curvThis = grid_get(T.ct, T.curv, T.curvBg, x, y, z), curvBelow = grid_get(T.ct, T.curv, T.curvBg, lx, ly, lz);
+                        if (phiThis >= 0.f) pThis = __fmul_rn(T.tension, __fadd_rn(__fmul_rn(theta, curvThis), __fmul_rn(__fsub_rn(1.f, theta), curvBelow)));
+                        else if (phiBelow >= 0.f) pBelow = __fmul_rn(T.tension, __fadd_rn(__fmul_rn(theta, curvBelow), __fmul_rn(__fsub_rn(1.f, theta), curvThis)));
+                    }
                 }
                 float velUpdate = __fdiv_rn(__fdiv_rn(__fmul_rn(-dt, __fsub_rn(pThis, pBelow)), dx), theta);
                 float updated = __fadd_rn(vel[i], velUpdate);
@@ -342,10 +348,18 @@ void subtract_grad(World* w, float dt, float dx, int velExtraLayer) {
     GridF& phi = w->F(FLIPB200_LIQUID_SDF);
     GridF& prs = w->F(FLIPB200_PRESSURE);
     DBuf<uint64_t> chMask((size_t)3 * n * 8, w->stream);
+    GradTension T;
+    memset(&T, 0, sizeof(T));
+    if (w->tensionCoef > 0.f) {   // enable_tension (FF/nosys/SubtractPressureGradient.cpp:23); tension = 2 coef / density (FF/FLIP_vdb.cpp:2875)
+        GridF& cv = w->F(FLIPB200_CURVATURE);
+        T.on = 1; T.tension = 2 * w->tensionCoef / w->density;
+        if (cv.topo) { T.ct = cv.topo->view(); T.curv = cv.val.p; }
+        T.curvBg = cv.bg;
+    }
     for (int ch = 0; ch < 3; ch++) {
         FB_LAUNCH(w, "pressure_gradient", (size_t)n * LEAF * 20)
             pressure_gradient_kernel<<<n, 512, 0, w->stream>>>(pool->view(), ch, vel.mask.p, vel.val[ch].p, fw.val[ch].p, phi.val.p, phi.bg,
-                                                               prs.val.p, prs.mask.p, w->solidVelView[ch].p, chMask.p + (size_t)ch * n * 8, dt, dx);
+                                                               prs.val.p, prs.mask.p, w->solidVelView[ch].p, chMask.p + (size_t)ch * n * 8, dt, dx, T);
         check_launch("pressure_gradient");
     }
     union_extrapolate(w, velExtraLayer, vel, chMask.p, phi.mask.p);

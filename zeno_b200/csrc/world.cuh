@@ -45,6 +45,7 @@ struct flipb200_world {
 
     // views of the static solid grids resampled onto the pool (rebuilt when the pool changes)
     uint64_t solidViewEpoch = ~0ull;
+    float density = 1000.f, tensionCoef = 0.f;   // the Density / SurfaceTension sockets (flipb200_set_surface_tension); coef > 0 enables the tension terms
     fb::DBuf<float> solidSdfView;        // [pool n][512]
     fb::DBuf<float> solidVelView[3];     // [pool n][512]
     fb::DBuf<uint8_t> solidLeafExists;   // [pool n]

@@ -734,8 +734,10 @@ struct AssembleSolvePPE : zeno::INode {
         auto velocity = get_input("Velocity")->as<VDBFloat3Grid>();
         auto solid_velocity = get_input("SolidVelocity")->as<VDBFloat3Grid>();
         const float tension_coef = get_input("SurfaceTension")->as<NumericObject>()->get<float>();
-        if (tension_coef > 0) throw makeError("AssembleSolvePPE (libflipb200): the surface-tension right-hand side is not accelerated (SURVEY 8f-4)");
+        const float density = get_input("Density")->as<NumericObject>()->get<float>();
         WorldHolder& h = world_for(dx, {liquid_sdf, velocity, curr_pressure, face_weight, rhsgrid});
+        if (tension_coef > 0 && has_input("Curvature")) upload<openvdb::FloatGrid>(h, FLIPB200_CURVATURE, get_input("Curvature")->as<VDBFloatGrid>()->m_grid);
+        check(flipb200_set_surface_tension(h.w, density, tension_coef > 0 ? tension_coef : 0.f), "AssembleSolvePPE");
         upload<openvdb::FloatGrid>(h, FLIPB200_LIQUID_SDF, liquid_sdf->m_grid);
         upload<openvdb::Vec3fGrid>(h, FLIPB200_FACE_WEIGHT, face_weight->m_grid);
         upload<openvdb::Vec3fGrid>(h, FLIPB200_VELOCITY, velocity->m_grid);
@@ -770,8 +772,10 @@ struct SubtractPressureGradient : zeno::INode {
         auto velocity = get_input("Velocity")->as<VDBFloat3Grid>();
         auto solid_velocity = get_input("SolidVelocity")->as<VDBFloat3Grid>();
         const float tension_coef = get_input("SurfaceTension")->as<NumericObject>()->get<float>();
-        if (tension_coef > 0) throw makeError("SubtractPressureGradient (libflipb200): surface tension is not accelerated (SURVEY 8f-4)");
+        const float density = get_input("Density")->as<NumericObject>()->get<float>();
         WorldHolder& h = world_for(dx, {liquid_sdf, velocity, curr_pressure, face_weight});
+        if (tension_coef > 0 && has_input("Curvature")) upload<openvdb::FloatGrid>(h, FLIPB200_CURVATURE, get_input("Curvature")->as<VDBFloatGrid>()->m_grid);
+        check(flipb200_set_surface_tension(h.w, density, tension_coef > 0 ? tension_coef : 0.f), "SubtractPressureGradient");
         upload<openvdb::FloatGrid>(h, FLIPB200_LIQUID_SDF, liquid_sdf->m_grid);
         upload<openvdb::FloatGrid>(h, FLIPB200_SOLID_SDF, solid_sdf->m_grid);
         upload<openvdb::FloatGrid>(h, FLIPB200_PRESSURE, curr_pressure->m_grid);
