@@ -157,6 +157,11 @@ int flipb200_kill_particles_in_sdf(flipb200_world* w, int sdfGrid, int keep);
  *   start = h % 21474836
  * (uint32 arithmetic) and runs through its voxels in offset order exactly as the reference does inside a chunk. */
 int flipb200_fluid_reseed(flipb200_world* w, uint32_t seed);
+/* VDBPointsToPrimitive (projects/zenvdb/GetVDBPoints.cpp:76-258; SURVEY 8f-3, the viewport / export path): world position
+ * float((double(P) + double(voxel)) * dx) and decoded velocity of every particle, [N][3] floats each (N from flipb200_particles_info),
+ * store order (leaf, voxel, index; the reference walks leaves in tree order -- a primitive is an unordered point set). vel may be
+ * NULL. The caller's arrays should be page-locked (flipb200_host_alloc). No OpenVDB tree is built on the way. */
+int flipb200_particles_to_points(flipb200_world* w, float* pos, float* vel);
 /* ParticleEmitter (FF/nosys/ParticleEmitter.cpp:9-62 -> FLIP_vdb::emit_liquid, FF/FLIP_vdb.cpp:2222-2642), the branch WITHOUT a
  * VelocityVolume (:2488-2624): every particle leaf box one of whose 9^3 lattice corners samples the shape SDF (float grid slot
  * `shapeGrid`, e.g. FLIPB200_KILLER_SDF) < 0 is filled -- per voxel whose centre samples < dx, up to 16 jittered candidates while

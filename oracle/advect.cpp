@@ -539,6 +539,29 @@ void node_ParticleEmitter(World& w, const FloatGrid& shape, float vx, float vy, 
     w.particles = std::move(out);
 }
 
+// VDBPointsToPrimitive (projects/zenvdb/GetVDBPoints.cpp:76-258): per particle, in store order, the world position
+// Vec3f(indexToWorld(Vec3d(decoded P) + Vec3d(voxel))) -- the sum and the scaling in double, one rounding to float -- and the
+// decoded velocity. (The reference walks leaves in tree order; a primitive is an unordered point set.)
+void node_VDBPointsToPrimitive(const World& w, float* pos, float* vel) {
+    const Points& in = w.particles;
+    const double s = double(w.dx);
+    size_t k = 0;
+    for (int l = 0; l < in.leafCount(); l++) {
+        const Coord o = in.origins[l];
+        for (int off = 0; off < 512; off++) {
+            const uint32_t b = off ? in.voxelEnd[l][off - 1] : 0u, e = in.voxelEnd[l][off];
+            const int c[3] = {o.x + (off >> 6), o.y + ((off >> 3) & 7), o.z + (off & 7)};
+            for (uint32_t i = b; i < e; i++, k++) {
+                const size_t gi = in.leafBegin[l] + i;
+                for (int a = 0; a < 3; a++) {
+                    pos[3 * k + a] = float((double(fxpt16_decode(in.P[3 * gi + a])) + double(c[a])) * s);
+                    if (vel) vel[3 * k + a] = half_decode(in.v[3 * gi + a]);
+                }
+            }
+        }
+    }
+}
+
 // FLIP_vdb::point_integrate_vector, channel "vel" (FF/FLIP_vdb.cpp:3492-3535): v is read as Vec3R (half -> float -> double),
 // dv (a Vec3R built from the node's float vec3) is added in double, and the sum goes back through the Vec3f write handle:
 // double -> float (round to nearest) -> half (TruncateCodec, round to nearest even). Positions are untouched.

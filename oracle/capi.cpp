@@ -172,6 +172,7 @@ int orc_set_surface_tension(void* wp, float density, float coef) {
     w->density = density; w->tensionCoef = coef;
     return 0;
 }
+int orc_particles_to_points(void* wp, float* pos, float* vel) { node_VDBPointsToPrimitive(*static_cast<World*>(wp), pos, vel); return 0; }
 uint64_t orc_reseed_leaf_start(uint32_t seed, int ox, int oy, int oz) { return reseed_leaf_start(seed, ox, oy, oz); }
 // the start the seeded build of the reference draws for a TBB chunk: uniform_int_distribution(0, 21474836)(mt19937(seed)), FF/FLIP_vdb.cpp:2081-2084
 uint64_t orc_reseed_chunk_start(uint32_t seed) {

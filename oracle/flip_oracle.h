@@ -85,6 +85,9 @@ void node_ParticleEmitter(World& w, const FloatGrid& shape, float vx, float vy, 
 // FF/nosys/Update_Solid_SDF.cpp:9-31 -> FLIP_vdb::update_solid_sdf (FF/FLIP_vdb.cpp:1976-2046), one moving solid
 void node_FLIPApplyBoundary(World& w, const FloatGrid& moving, bool movingVertexCentred);
 
+// projects/zenvdb/GetVDBPoints.cpp:76-258: pos / vel = [N][3] floats, vel may be null
+void node_VDBPointsToPrimitive(const World& w, float* pos, float* vel);
+
 // FF/nosys/ParticleAddGravity.cpp:9-19 -> FLIP_vdb::point_integrate_vector (FF/FLIP_vdb.cpp:3492-3535)
 void node_ParticleAddDV(World& w, float dvx, float dvy, float dvz);
 

@@ -181,6 +181,15 @@ class OracleWorld:
         if rc != 0:
             raise RuntimeError("set_surface_tension failed")
 
+    def VDBPointsToPrimitive(self):
+        """world positions and velocities of all particles, store order: (pos [N,3] f32, vel [N,3] f32)"""
+        n = self.particles_info()[1]
+        pos, vel = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        rc = self.lib.orc_particles_to_points(self.h, _p(pos), _p(vel))
+        if rc != 0:
+            raise RuntimeError("VDBPointsToPrimitive failed: " + self._err())
+        return pos, vel
+
     def _err(self):
         try:
             return (self.lib.orc_last_error() or b"").decode()

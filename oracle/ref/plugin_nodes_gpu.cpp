@@ -12,6 +12,7 @@
 
 namespace { std::string g_err; }
 
+#define NH_HAS_PRIMITIVE 1
 #define NH_SET_SEED(s) (zeno::seed_base() = (s), zeno::seed_fixed() = true)
 #define NH_FN(name) pg_##name
 #define NH_REGISTRY ::zeno::nodeRegistry()

@@ -30,6 +30,7 @@
 #define flipb200_fluid_reseed ob_fluid_reseed
 #define flipb200_emit_liquid ob_emit_liquid
 #define flipb200_apply_boundary ob_apply_boundary
+#define flipb200_particles_to_points ob_particles_to_points
 #define flipb200_set_surface_tension ob_set_surface_tension
 #define flipb200_g2p_advect ob_g2p_advect
 #define flipb200_renormalize_sdf ob_renormalize_sdf
@@ -69,6 +70,7 @@ struct OracleApi {
     int (*add_dv)(void*, float, float, float) = nullptr;
     int (*reseed)(void*, uint32_t, const uint64_t*, uint64_t*) = nullptr;
     int (*boundary)(void*, int, int) = nullptr;
+    int (*to_points)(void*, float*, float*) = nullptr;
     int (*tension)(void*, float, float) = nullptr;
     int (*emit)(void*, int, float, float, float, uint32_t, const uint64_t*, uint64_t*) = nullptr;
     int (*g2p_plain)(void*, float, float, int, float) = nullptr;
@@ -152,6 +154,7 @@ int ob_kill_particles_in_sdf(flipb200_world* w, int grid, int keep) { return g_o
 int ob_particles_add_dv(flipb200_world* w, float x, float y, float z) { return g_orc.add_dv(w->orc, x, y, z); }
 int ob_fluid_reseed(flipb200_world* w, uint32_t seed) { return g_orc.reseed(w->orc, seed, nullptr, nullptr); }
 int ob_set_surface_tension(flipb200_world* w, float density, float coef) { return g_orc.tension(w->orc, density, coef); }
+int ob_particles_to_points(flipb200_world* w, float* pos, float* vel) { return g_orc.to_points(w->orc, pos, vel); }
 int ob_apply_boundary(flipb200_world* w, int grid, int vc) { return g_orc.boundary(w->orc, grid, vc); }
 int ob_emit_liquid(flipb200_world* w, int grid, float vx, float vy, float vz, uint32_t seed) { return g_orc.emit(w->orc, grid, vx, vy, vz, seed, nullptr, nullptr); }
 int ob_g2p_advect(flipb200_world* w, float dt, float dx, int rk, float s) { return g_orc.g2p_plain(w->orc, dt, dx, rk, s); }
@@ -160,6 +163,7 @@ int ob_erode_sdf(flipb200_world* w, int grid, float d) { return g_orc.erode(w->o
 int ob_smooth_sdf(flipb200_world* w, int grid, int wd, int it) { return g_orc.smooth(w->orc, grid, wd, it); }
 }  // extern "C"
 
+#define NH_HAS_PRIMITIVE 1
 #define NH_SET_SEED(s) (zeno::seed_base() = (s), zeno::seed_fixed() = true)
 #define NH_FN(name) pn_##name
 #define NH_REGISTRY ::zeno::nodeRegistry()
@@ -176,7 +180,7 @@ int pn_backend(const char* liboracle) {
         bind(g_orc.particles_set, "orc_particles_set"); bind(g_orc.particles_info, "orc_particles_info"); bind(g_orc.particles_get, "orc_particles_get");
         bind(g_orc.p2g, "orc_p2g"); bind(g_orc.g2p, "orc_g2p_advect_sheetty"); bind(g_orc.face_weights, "orc_face_weights");
         bind(g_orc.pushout, "orc_pushout_sdf"); bind(g_orc.add_vector, "orc_add_vector"); bind(g_orc.cfl, "orc_cfl");
-        bind(g_orc.solve, "orc_solve_ppe"); bind(g_orc.subtract, "orc_subtract_grad"); bind(g_orc.kill, "orc_kill_particles"); bind(g_orc.add_dv, "orc_particles_add_dv"); bind(g_orc.reseed, "orc_fluid_reseed"); bind(g_orc.emit, "orc_emit_liquid"); bind(g_orc.boundary, "orc_apply_boundary"); bind(g_orc.tension, "orc_set_surface_tension"); bind(g_orc.g2p_plain, "orc_g2p_advect"); bind(g_orc.renorm, "orc_renormalize_sdf"); bind(g_orc.erode, "orc_erode_sdf"); bind(g_orc.smooth, "orc_smooth_sdf");
+        bind(g_orc.solve, "orc_solve_ppe"); bind(g_orc.subtract, "orc_subtract_grad"); bind(g_orc.kill, "orc_kill_particles"); bind(g_orc.add_dv, "orc_particles_add_dv"); bind(g_orc.reseed, "orc_fluid_reseed"); bind(g_orc.emit, "orc_emit_liquid"); bind(g_orc.boundary, "orc_apply_boundary"); bind(g_orc.to_points, "orc_particles_to_points"); bind(g_orc.tension, "orc_set_surface_tension"); bind(g_orc.g2p_plain, "orc_g2p_advect"); bind(g_orc.renorm, "orc_renormalize_sdf"); bind(g_orc.erode, "orc_erode_sdf"); bind(g_orc.smooth, "orc_smooth_sdf");
     });
 }
 }  // extern "C"

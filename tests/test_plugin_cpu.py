@@ -10,7 +10,7 @@ REF = "/root/reference/projects/FastFLIP/nosys"
 REF_FILES = {"FLIP_P2G": "P2G.cpp", "G2PAdvectorSheetty": "SheetG2PAdvector.cpp", "AssembleSolvePPE": "SolvePoissonPressureEqn.cpp",
              "SubtractPressureGradient": "SubtractPressureGradient.cpp", "CutCellWeight": "EvalFaceWeight.cpp",
              "PushOutLiquidSDF": "FixLiquidSDF.cpp", "FieldAddVector": "FieldAddVector.cpp", "CFL_dt": "CFL.cpp",
-             "KillParticlesInSDF": "KillParticles.cpp", "ParticleAddDV": "ParticleAddGravity.cpp", "FluidReseed": "FLIP_Reseed.cpp", "ParticleEmitter": "ParticleEmitter.cpp", "FLIPApplyBoundary": "Update_Solid_SDF.cpp",
+             "KillParticlesInSDF": "KillParticles.cpp", "ParticleAddDV": "ParticleAddGravity.cpp", "FluidReseed": "FLIP_Reseed.cpp", "ParticleEmitter": "ParticleEmitter.cpp", "FLIPApplyBoundary": "Update_Solid_SDF.cpp", "VDBPointsToPrimitive": "../../zenvdb/GetVDBPoints.cpp",
              "G2P_Advector": "G2P_Advector.cpp", "VDBRenormalizeSDF": "../../zenvdb/VDBRenormalize.cpp",
              "VDBErodeSDF": "../../zenvdb/VDBRenormalize.cpp", "VDBSmoothSDF": "../../zenvdb/VDBRenormalize.cpp"}
 # (inputs, outputs, params) by name only, recorded from the reference files above
@@ -29,6 +29,7 @@ EXPECTED = {
     "KillParticlesInSDF": (["Particles", "KillerSDF"], ["Particles"], ["OpType"]),
     "ParticleAddDV": (["Particles", "dv"], [], ["channel", "vx", "vy", "vz"]),
     "FluidReseed": (["Particles", "LiquidSDF", "FluidVel"], [], []),
+    "VDBPointsToPrimitive": (["grid"], ["prim"], []),
     "FLIPApplyBoundary": (["Particles", "DynaSolid_SDF", "StatSolid_SDF"], [], []),
     "ParticleEmitter": (["Particles", "ShapeSDF", "VelocityVolume", "VelocityInit", "LiquidSDF"], ["Particles"], ["vx", "vy", "vz"]),
     "G2P_Advector": (["dt", "Dx", "Particles", "Velocity", "PostAdvVelocity", "SolidSDF", "SolidVelocity"], [], ["dx", "RK_ORDER", "pic_smoothness"]),
@@ -199,3 +200,36 @@ def test_plugin_resident_mode():
     direct = digest(["oracle"], {})
     assert plain == direct, "plugin nodes (upload-everything mode) differ from the oracle driven directly"
     assert resident == plain, "FLIPB200_RESIDENT=1 changes the results"
+
+
+def test_points_to_primitive_node_and_oracle():
+    """VDBPointsToPrimitive (projects/zenvdb/GetVDBPoints.cpp:163-177): world position = float((double(P) + double(voxel)) * dx), decoded
+    velocity. The oracle's restatement against the same arithmetic written with numpy on the stored codes, and the drop-in's node
+    class (oracle behind the ABI, real OpenVDB particle grid in, PrimitiveObject out) against the oracle."""
+    import numpy as np
+    from oracle import pyoracle
+    from oracle.pyoracle import OracleWorld, PluginWorld
+    from zeno_b200 import scenes
+    pos, vel, dx = scenes.dam_break_points(32, seed=11, random_velocity=True)
+    ow = OracleWorld(dx)
+    ow.PrimToVDBPointDataGrid(pos, vel)
+    p = ow.get_particles()
+    counts = np.diff(np.concatenate([np.zeros((p["voxel_end"].shape[0], 1), np.uint32), p["voxel_end"]], axis=1).astype(np.int64), axis=1)   # [leaf, 512]
+    off = np.arange(512)
+    loc = np.stack([off >> 6, (off >> 3) & 7, off & 7], axis=1)
+    vox = (p["origins"][:, None, :].astype(np.int64) + loc[None, :, :]).reshape(-1, 3)
+    ijk = np.repeat(vox, counts.reshape(-1), axis=0)
+    Pdec = p["P"].astype(np.float32) / np.float32(65535.0) - np.float32(0.5)
+    want_pos = ((Pdec.astype(np.float64) + ijk.astype(np.float64)) * np.float64(np.float32(dx))).astype(np.float32)
+    want_vel = p["v"].view(np.float16).astype(np.float32)
+    got_pos, got_vel = ow.VDBPointsToPrimitive()
+    assert np.array_equal(got_pos, want_pos) and np.array_equal(got_vel, want_vel)
+    if pyoracle.ref_available() and hasattr(pyoracle.load_ref(), "pn_particles_to_points"):
+        pw = PluginWorld(dx)
+        pw.PrimToVDBPointDataGrid(pos, vel)
+        node_pos, node_vel = pw.VDBPointsToPrimitive()
+        a = np.concatenate([node_pos, node_vel], axis=1)
+        b = np.concatenate([got_pos, got_vel], axis=1)
+        a = a[np.lexsort(tuple(a[:, k] for k in range(5, -1, -1)))]
+        b = b[np.lexsort(tuple(b[:, k] for k in range(5, -1, -1)))]
+        assert np.array_equal(a, b), "plugin node primitive differs from the oracle"

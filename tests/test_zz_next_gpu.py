@@ -249,3 +249,20 @@ def test_surface_tension_matches_oracle(gpu_lib, oracle_lib):
     gw.AssembleSolvePPE(dt, dx); ow.AssembleSolvePPE(dt, dx)
     util.compare_grids(gw.get_grid("Divergence"), ow.get_grid("Divergence"), "plain RHS after tension", tol=0.0, check_inactive=False)
     gw.close()
+
+
+def test_points_to_primitive_matches_oracle(gpu_lib, oracle_lib):
+    """VDBPointsToPrimitive (projects/zenvdb/GetVDBPoints.cpp): world positions and velocities straight from the device
+    store == the oracle (pinned against the node's arithmetic in tests/test_plugin_cpu.py), bit for bit, same order."""
+    from oracle.pyoracle import OracleWorld
+    from zeno_b200 import abi
+    pos, vel, dx = scenes.dam_break_points(64, seed=11, random_velocity=True)
+    gw, ow = abi.World(dx), OracleWorld(dx)
+    for w in (gw, ow):
+        w.PrimToVDBPointDataGrid(pos, vel)
+    gp, gv = gw.VDBPointsToPrimitive()
+    op, ov = ow.VDBPointsToPrimitive()
+    assert gp.shape == op.shape and np.array_equal(gp, op), "world positions differ"
+    assert np.array_equal(gv, ov), "velocities differ"
+    assert np.abs(np.sort(gp, axis=0) - np.sort(pos, axis=0)).max() < dx, "positions must be the input points up to the codec"
+    gw.close()

@@ -39,7 +39,7 @@ EXPORTS = [
     "flipb200_profile_reset", "flipb200_profile_get", "flipb200_stream", "flipb200_comm_unique_id",
     "flipb200_comm_init", "flipb200_comm_init_local", "flipb200_comm_abort", "flipb200_dd_set_slab", "flipb200_dd_owned",
     "flipb200_dd_owned_particles",
-    "flipb200_sync_count", "flipb200_smooth_sdf", "flipb200_renormalize_sdf", "flipb200_erode_sdf", "flipb200_g2p_advect", "flipb200_kill_particles_in_sdf", "flipb200_fluid_reseed", "flipb200_emit_liquid", "flipb200_apply_boundary", "flipb200_set_surface_tension", "flipb200_particles_add_dv", "flipb200_particles_download_begin", "flipb200_grid_download_begin", "flipb200_download_wait",
+    "flipb200_sync_count", "flipb200_smooth_sdf", "flipb200_renormalize_sdf", "flipb200_erode_sdf", "flipb200_g2p_advect", "flipb200_kill_particles_in_sdf", "flipb200_fluid_reseed", "flipb200_emit_liquid", "flipb200_apply_boundary", "flipb200_particles_to_points", "flipb200_set_surface_tension", "flipb200_particles_add_dv", "flipb200_particles_download_begin", "flipb200_grid_download_begin", "flipb200_download_wait",
 ]
 
 
@@ -238,6 +238,12 @@ class World:
 
     def set_surface_tension(self, density: float = 1000.0, coef: float = 0.0):
         self._ck(self.lib.flipb200_set_surface_tension(self.h, C.c_float(density), C.c_float(coef)))
+
+    def VDBPointsToPrimitive(self):
+        n = self.particles_info()[1]
+        pos, vel = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+        self._ck(self.lib.flipb200_particles_to_points(self.h, pos.ctypes.data_as(C.c_void_p), vel.ctypes.data_as(C.c_void_p)))
+        return pos, vel
 
     def KillParticlesInSDF(self, sdf_grid: str = "KillerSDF", keep: bool = True):
         self._ck(self.lib.flipb200_kill_particles_in_sdf(self.h, C.c_int(GRID_IDS[sdf_grid]), C.c_int(1 if keep else 0)))

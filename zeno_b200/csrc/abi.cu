@@ -579,6 +579,13 @@ int flipb200_set_surface_tension(flipb200_world* w, float density, float tension
         w->density = density; w->tensionCoef = tensionCoef;
     });
 }
+int flipb200_particles_to_points(flipb200_world* w, float* pos, float* vel) {
+    return guarded([&] {
+        FB_REQUIRE(w && pos, FLIPB200_ERR_ARG, "particles_to_points: bad argument");
+        use_device(w);
+        particles_to_points(w, pos, vel);
+    });
+}
 int flipb200_particles_add_dv(flipb200_world* w, float dvx, float dvy, float dvz) {
     return guarded([&] {
         FB_REQUIRE(w, FLIPB200_ERR_ARG, "particles_add_dv: null world");

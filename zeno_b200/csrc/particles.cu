@@ -262,6 +262,42 @@ void kill_particles_in_sdf(World* w, int sdfGrid, bool keep) {
     w->pts = std::move(out);
 }
 
+// VDBPointsToPrimitive (projects/zenvdb/GetVDBPoints.cpp:76-258): world position = float((double(P) + double(voxel)) * dx) and the decoded
+// velocity of every particle, store order; one thread per voxel. Written into device staging, copied to the caller's host arrays.
+namespace {
+__global__ void points_export_kernel(TopoView t, const uint32_t* __restrict__ voxelStart, const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1,
+                                     const uint32_t* __restrict__ w2, double s, float* __restrict__ pos, float* __restrict__ vel) {
+    const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= (size_t)t.n * LEAF) return;
+    const uint32_t b = voxelStart[v], e = voxelStart[v + 1];
+    if (b == e) return;
+    const int3 o = t.origin[v >> 9];
+    const int off = (int)(v & 511);
+    const double cx = (double)(o.x + (off >> 6)), cy = (double)(o.y + ((off >> 3) & 7)), cz = (double)(o.z + (off & 7));
+    for (uint32_t i = b; i < e; i++) {
+        const uint32_t a0 = w0[i], a1 = w1[i], a2 = w2[i];
+        pos[3 * (size_t)i] = __double2float_rn(__dmul_rn(__dadd_rn((double)fx_decode(a0 & 0xffffu), cx), s));
+        pos[3 * (size_t)i + 1] = __double2float_rn(__dmul_rn(__dadd_rn((double)fx_decode(a0 >> 16), cy), s));
+        pos[3 * (size_t)i + 2] = __double2float_rn(__dmul_rn(__dadd_rn((double)fx_decode(a1 & 0xffffu), cz), s));
+        if (vel) { vel[3 * (size_t)i] = h_decode(a1 >> 16); vel[3 * (size_t)i + 1] = h_decode(a2 & 0xffffu); vel[3 * (size_t)i + 2] = h_decode(a2 >> 16); }
+    }
+}
+}  // namespace
+void particles_to_points(World* w, float* posHost, float* velHost) {
+    FB_REQUIRE(w->pts.topo != nullptr, FLIPB200_ERR_STATE, "VDBPointsToPrimitive: no particles");
+    const uint64_t n = w->pts.n;
+    if (n == 0) return;
+    DBuf<float> pos(3 * n, w->stream), vel;
+    if (velHost) vel.alloc(3 * n, w->stream);
+    const size_t nv = (size_t)w->pts.topo->n * LEAF;
+    FB_LAUNCH(w, "points_export", n * (12 + 24)) points_export_kernel<<<nblk(nv, 256), 256, 0, w->stream>>>(w->pts.topo->view(), w->pts.voxelStart.p, w->pts.w0.p, w->pts.w1.p, w->pts.w2.p,
+                                                                                                       (double)w->dx, pos.p, velHost ? vel.p : nullptr);
+    check_launch("points_export");
+    FB_CUDA(cudaMemcpyAsync(posHost, pos.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, w->stream));
+    if (velHost) FB_CUDA(cudaMemcpyAsync(velHost, vel.p, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, w->stream));
+    sync(w);
+}
+
 // helpers shared with g2p.cu
 void origins_from_ijk(World* w, const int3* ijk, uint64_t n, int3* origins) {
     if (!n) return;

@@ -243,6 +243,7 @@ void comm_allreduce(World* w, void* buf, size_t n, int type, bool isMax);   // i
 struct DDArray { void* base; int bytesPerLeaf; };
 bool dd_on(World* w);
 void sort_store_by_key(World* w, const TopoPtr& topo, const uint32_t* keys, uint64_t n, const uint32_t* i0, const uint32_t* i1, const uint32_t* i2, Particles& out);   // particles.cu
+void particles_to_points(World* w, float* posHost, float* velHost);   // particles.cu
 void fluid_reseed(World* w, uint32_t seed);   // reseed.cu
 void apply_boundary(World* w, int movingGrid, bool movingVertexCentred);   // reseed.cu
 void emit_liquid(World* w, int shapeGrid, float vx, float vy, float vz, uint32_t seed);   // reseed.cu

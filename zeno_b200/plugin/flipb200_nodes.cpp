@@ -30,6 +30,7 @@
 #include <zeno/zeno.h>
 #include <zeno/VDBGrid.h>
 #include <zeno/types/NumericObject.h>
+#include <zeno/types/PrimitiveObject.h>
 #else
 #include <stdexcept>
 #include <string>
@@ -118,6 +119,7 @@ struct WorldHolder {
     float dx = 0.f;
     struct Stage { Pinned o, m, v; int n = 0; float bg[3] = {0.f, 0.f, 0.f}; } stage[FLIPB200_NUM_GRIDS];
     Pinned po, pve, pP, pV;                       // particle staging
+    Pinned primPos, primVel;                      // VDBPointsToPrimitive staging
     int pnl = 0; uint64_t pnp = 0;
     uint32_t reseeds = 0;                         // FluidReseed calls so far (seed sequence)
     Fingerprint fp[FLIPB200_NUM_GRIDS + 1];       // what the device copy of each slot corresponds to (last slot: particles)
@@ -639,6 +641,35 @@ struct FLIP_Solid_Modifier : zeno::INode {
 };
 static int defFLIP_Solid_Modifier = zeno::defNodeClass<FLIP_Solid_Modifier>("FLIPApplyBoundary",
     {/* inputs: */ {"Particles", "DynaSolid_SDF", "StatSolid_SDF"}, /* outputs: */ {}, /* params: */ {}, /* category: */ {"FLIPSolver"}});
+
+// ---- VDBPointsToPrimitive (projects/zenvdb/GetVDBPoints.cpp:76-266): the particles as a point primitive for the viewport
+// or an exporter. With the store resident on the device (the usual case after an accelerated substep) nothing is uploaded and no
+// OpenVDB tree is walked: the device writes world positions and velocities straight into pinned staging. A grid without the "v"
+// attribute (not a FLIP particle grid) is not handled here.
+struct VDBPointsToPrimitive : zeno::INode {
+    virtual void apply() override {
+        auto grid = get_input("grid")->as<VDBPointsGrid>();
+        WorldHolder& h = world_for(float(grid->m_grid->voxelSize()[0]), {grid});
+        upload_particles(h, grid->m_grid);
+        int nl = 0;
+        uint64_t np = 0;
+        check(flipb200_particles_info(h.w, &nl, &np), "particles_info");
+        float* pos = h.primPos.need<float>(3 * np + 4);
+        float* vel = h.primVel.need<float>(3 * np + 4);
+        check(flipb200_particles_to_points(h.w, pos, vel), "VDBPointsToPrimitive");
+        auto ret = std::make_shared<zeno::PrimitiveObject>();
+        ret->resize(np);
+        auto& retpos = ret->add_attr<zeno::vec3f>("pos");
+        auto& retvel = ret->add_attr<zeno::vec3f>("vel");
+        tbb::parallel_for(uint64_t(0), np, [&](uint64_t i) {
+            retpos[i] = zeno::vec3f(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+            retvel[i] = zeno::vec3f(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2]);
+        });
+        set_output("prim", ret);
+    }
+};
+static int defVDBPointsToPrimitive = zeno::defNodeClass<VDBPointsToPrimitive>("VDBPointsToPrimitive",
+    {/* inputs: */ {"grid"}, /* outputs: */ {"prim"}, /* params: */ {}, /* category: */ {"openvdb"}});
 
 // ---- ParticleAddDV (FF/nosys/ParticleAddGravity.cpp:9-41)
 struct ParticleAddDV : zeno::INode {
