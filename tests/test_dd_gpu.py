@@ -186,3 +186,29 @@ def test_slab_rules_are_enforced(gpu_lib):
     assert all(e is not None and "contiguous" in e for e in errs), errs
     for w in worlds:
         w.close()
+
+
+@pytest.mark.parametrize("bounds", [[(0, 2), (2, 4)], [(0, 2), (2, 4), (4, 6)]], ids=["2ranks", "3ranks"])
+def test_sdf_nodes_under_decomposition(gpu_lib, bounds):
+    """VDBRenormalizeSDF (4 iterations) and VDBSmoothSDF on the liquid SDF of a decomposed world: the ghost layers are refreshed
+    between the passes that read across a slab face, so the owned leaves equal the single world's bit for bit."""
+    from zeno_b200 import abi
+    N = 128
+    side = 32 if len(bounds) == 2 else 48
+    pos, vel, dx = scenes.dam_break_points(N, seed=5, random_velocity=True, side=side)
+    solid = scenes.box_solid_sdf(N, dx)
+    one = abi.World(dx)
+    one.set_grid("SolidSDF", solid)
+    one.PrimToVDBPointDataGrid(pos, vel)
+    dd = make_dd(abi, N, bounds, pos, vel, dx, solid)
+    one.FLIP_P2G(dx, 3)
+    abi.run_ranks(dd, lambda r, w: w.FLIP_P2G(dx, 3))
+    one.VDBRenormalizeSDF("LiquidSDF", 4)
+    abi.run_ranks(dd, lambda r, w: w.VDBRenormalizeSDF("LiquidSDF", 4))
+    util.compare_grids(gather_grid(dd, "LiquidSDF"), one.get_grid("LiquidSDF"), "dd VDBRenormalizeSDF", tol=0.0, check_inactive=False)
+    for width in (1, 2):
+        one.VDBSmoothSDF("LiquidSDF", width, 1)
+        abi.run_ranks(dd, lambda r, w: w.VDBSmoothSDF("LiquidSDF", width, 1))
+        util.compare_grids(gather_grid(dd, "LiquidSDF"), one.get_grid("LiquidSDF"), f"dd VDBSmoothSDF width {width}", tol=0.0, check_inactive=False)
+    for w in dd + [one]:
+        w.close()

@@ -281,9 +281,10 @@ __global__ void __launch_bounds__(512) add_active_kernel(const uint64_t* __restr
 // (tools/Filter.h:574-630): per iteration four box filters, each as three one-dimensional passes in the order X, Z, Y
 void smooth_sdf(World* w, int grid, int width, int iterations) {
     FB_REQUIRE(is_float_grid(grid) && w->F(grid).topo != nullptr, FLIPB200_ERR_STATE, "VDBSmoothSDF: the grid does not exist");
-    // every pass reads `width` voxels across a slab face; the ghost-leaf refresh between passes is not wired up yet
-    FB_REQUIRE(!dd_on(w), FLIPB200_ERR_STATE, "VDBSmoothSDF is not available under slab decomposition yet");
     GridF& g = w->F(grid);
+    // slab decomposition: an x pass reads `width` voxels across a slab face; the two ghost leaf layers are refreshed after every x pass
+    const bool dd = dd_on(w);
+    FB_REQUIRE(!dd || (g.topo == w->pool && width <= 8), FLIPB200_ERR_STATE, "VDBSmoothSDF under slab decomposition: the grid must live on the pool (e.g. LiquidSDF) and width <= 8");
     const int n = g.topo->n;
     if (!n || iterations <= 0) return;
     const int wd = width < 1 ? 1 : width;
@@ -297,6 +298,7 @@ void smooth_sdf(World* w, int grid, int width, int iterations) {
                 FB_LAUNCH(w, "box_avg", (size_t)n * LEAF * 8) box_avg_kernel<<<n, 512, 0, w->stream>>>(t, g.mask.p, g.val.p, a.p, g.bg, order[k], wd, frac);
                 check_launch("box_avg");
                 std::swap(g.val, a);
+                if (dd && order[k] == 0) dd_refresh(w, {DDArray{g.val.p, LEAF * 4}}, 2);
             }
 }
 
@@ -314,9 +316,10 @@ void erode_sdf(World* w, int grid, float depth) {
 // `iterations` x normalize(); each normalize = three Euler stages (Normalizer::normalize, LevelSetTracker.h:535-604)
 void renormalize_sdf(World* w, int grid, int iterations) {
     FB_REQUIRE(is_float_grid(grid) && w->F(grid).topo != nullptr, FLIPB200_ERR_STATE, "VDBRenormalizeSDF: the grid does not exist");
-    // twelve stencil passes read across a slab face; the ghost-leaf refresh between them is not wired up yet
-    FB_REQUIRE(!dd_on(w), FLIPB200_ERR_STATE, "VDBRenormalizeSDF is not available under slab decomposition yet");
     GridF& g = w->F(grid);
+    // slab decomposition: the three stages of an iteration reach three voxels into the ghost layer; it is refreshed once per iteration
+    const bool dd = dd_on(w);
+    FB_REQUIRE(!dd || g.topo == w->pool, FLIPB200_ERR_STATE, "VDBRenormalizeSDF under slab decomposition: the grid must live on the pool (e.g. LiquidSDF)");
     const int n = g.topo->n;
     if (!n || iterations <= 0) return;
     const size_t nv = (size_t)n * LEAF;
@@ -334,6 +337,7 @@ void renormalize_sdf(World* w, int grid, int iterations) {
         stage(a.p, g.val.p, 3, 4);      // Phi_t2
         stage(g.val.p, a.p, 1, 3);      // Phi_t3
         std::swap(g.val, a);
+        if (dd) dd_refresh(w, {DDArray{g.val.p, LEAF * 4}}, 2);
     }
 }
 
