@@ -30,8 +30,9 @@ struct P2GParams {
     int* overflow;
 };
 
-__global__ void __launch_bounds__(P2G_THREADS) p2g_gather_kernel(P2GParams p) {
+__global__ void __launch_bounds__(P2G_THREADS) p2g_gather_kernel(P2GParams p, const uint8_t* __restrict__ todo) {
     extern __shared__ float smem[];
+    if (todo && !todo[blockIdx.x]) return;   // fallback pass: only the leaves p2g_xrow_kernel handed back
     float* sP = smem;                          // [PLANE_CAP][6] px,py,pz,vx,vy,vz
     float* acc = sP + PLANE_CAP * 6;           // [8][512]: wv0..2, w0..2, mind2, count
     __shared__ uint32_t cBeg[PLANE_CELLS];
@@ -193,6 +194,212 @@ __global__ void __launch_bounds__(P2G_THREADS) p2g_gather_kernel(P2GParams p) {
             reinterpret_cast<uint32_t*>(p.chMask)[nW + wi] = b1;
             reinterpret_cast<uint32_t*>(p.chMask)[2 * nW + wi] = b2;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// p2g_xrow_kernel (round 2): the same collect-style sums in the same order, a third of the instructions.
+// One CTA per pool leaf, 64 threads; thread (y, z) owns the whole x-row of eight target voxels. The shell is still
+// streamed one x-plane at a time, but a staged particle now serves the THREE targets x = cx+1, cx, cx-1 of its thread
+// at once: everything that depends on y and z only (two of the three distances, hats, staggered hats) is computed
+// once per particle instead of once per (particle, target), a particle record is loaded once instead of three times,
+// and the accumulators of the three live targets stay in registers (they rotate as the plane advances; a target is
+// finished after the plane at its ox = +1 and written straight to global memory -- no accumulator array in shared
+// memory). Each target still sees its 27 source cells in (ox, oy, oz) order and a cell's particles in store order, and
+// every product / sum is the same single-rounded operation as before, so the result is bit-identical to
+// p2g_gather_kernel (tests/test_parity_gpu.py::test_p2g_paths_identical) and to the oracle.
+// Staging: a plane's records are decoded once per CTA into 24-byte records [px py pz vx vy vz], cell after cell in
+// (y, z) order with ONE PAD RECORD per cell: with exactly 8 particles in every voxel (the state a scene starts in)
+// un-padded cell starts are 48 words apart and the 32 lanes of a warp would hit two bank pairs.
+// Planes that do not fit the staging buffer are processed in batches of whole cell rows (ascending y keeps a target's
+// oy order); a single row that does not fit hands the leaf back to p2g_gather_kernel through `todo`.
+constexpr int XR_THREADS = 64;
+#ifndef FB_XR_CAP
+#define FB_XR_CAP 1344
+#endif
+constexpr int XR_CAP = FB_XR_CAP;   // staged records per batch, pad records included
+
+struct XAcc { float a0, a1, a2, g0, g1, g2, md; int cn; };
+__device__ __forceinline__ void xacc_reset(XAcc& A) { A.a0 = A.a1 = A.a2 = A.g0 = A.g1 = A.g2 = 0.f; A.md = 3.0e38f; A.cn = 0; }
+
+// one (particle, target) pair; OX/OY/OZ = source cell - target voxel
+template <int OX, int OY, int OZ>
+__device__ __forceinline__ void xr_pair(XAcc& A, float px, float vx, float vy, float vz, float ty2, float tz2, float hy, float hz,
+                                        float ysh, float zsh) {
+    const float fx = (float)(-OX);
+    const float tx = fabsf(__fsub_rn(fx, px));
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(tx, tx), ty2), tz2);
+    A.md = fminf(A.md, d2);
+    const float hx = fmaxf(0.f, __fsub_rn(1.0f, tx));
+    if (OX != 1) {   // u sample at -0.5 in x; a source cell at +1 is always out of reach
+        const float xs = fabsf(__fsub_rn(fx - 0.5f, px));
+        const float wgt = __fmul_rn(__fmul_rn(fmaxf(0.f, __fsub_rn(1.0f, xs)), hy), hz);
+        A.a0 = __fadd_rn(__fmul_rn(vx, wgt), A.a0);
+        A.g0 = __fadd_rn(wgt, A.g0);
+    }
+    if (OY != 1) {
+        const float wgt = __fmul_rn(__fmul_rn(hx, ysh), hz);
+        A.a1 = __fadd_rn(__fmul_rn(vy, wgt), A.a1);
+        A.g1 = __fadd_rn(wgt, A.g1);
+    }
+    if (OZ != 1) {
+        const float wgt = __fmul_rn(__fmul_rn(hx, hy), zsh);
+        A.a2 = __fadd_rn(__fmul_rn(vz, wgt), A.a2);
+        A.g2 = __fadd_rn(wgt, A.g2);
+    }
+}
+
+// the particles of one source cell against the thread's three live targets (M: x = cx+1, Z: x = cx, P: x = cx-1)
+template <int OY, int OZ, bool ALL>
+__device__ __forceinline__ void xr_cell(const float* __restrict__ rec, int cnt, XAcc& M, XAcc& Z, XAcc& P, bool vM, bool vZ, bool vP) {
+    const float fy = (float)(-OY), fz = (float)(-OZ);
+    const float2* __restrict__ src = reinterpret_cast<const float2*>(rec);
+    if (ALL || vM) M.cn += cnt;
+    if (ALL || vZ) Z.cn += cnt;
+    if (ALL || vP) P.cn += cnt;
+    for (int j = 0; j < cnt; j++) {
+        const float2 q0 = src[3 * j], q1 = src[3 * j + 1], q2 = src[3 * j + 2];
+        const float px = q0.x, py = q0.y, pz = q1.x, vx = q1.y, vy = q2.x, vz = q2.y;
+        const float ty = fabsf(__fsub_rn(fy, py)), tz = fabsf(__fsub_rn(fz, pz));
+        const float ty2 = __fmul_rn(ty, ty), tz2 = __fmul_rn(tz, tz);
+        const float hy = fmaxf(0.f, __fsub_rn(1.0f, ty)), hz = fmaxf(0.f, __fsub_rn(1.0f, tz));
+        float ysh = 0.f, zsh = 0.f;
+        if (OY != 1) ysh = fmaxf(0.f, __fsub_rn(1.0f, fabsf(__fsub_rn(fy - 0.5f, py))));
+        if (OZ != 1) zsh = fmaxf(0.f, __fsub_rn(1.0f, fabsf(__fsub_rn(fz - 0.5f, pz))));
+        if (ALL || vM) xr_pair<-1, OY, OZ>(M, px, vx, vy, vz, ty2, tz2, hy, hz, ysh, zsh);
+        if (ALL || vZ) xr_pair<0, OY, OZ>(Z, px, vx, vy, vz, ty2, tz2, hy, hz, ysh, zsh);
+        if (ALL || vP) xr_pair<1, OY, OZ>(P, px, vx, vy, vz, ty2, tz2, hy, hz, ysh, zsh);
+    }
+}
+
+template <bool ALL>
+__device__ __forceinline__ void xr_rows(const float* __restrict__ sP, const int* __restrict__ cPre, const int* __restrict__ cCnt, int base,
+                                        int r0, int r1, int y, int z, XAcc& M, XAcc& Z, XAcc& P, bool vM, bool vZ, bool vP) {
+#define XR_CELL(OY, OZ)                                                                                          \
+    {                                                                                                            \
+        const int c = (y + (OY) + 1) * 10 + (z + (OZ) + 1);                                                      \
+        xr_cell<OY, OZ, ALL>(sP + (size_t)(cPre[c] - base) * 6, cCnt[c], M, Z, P, vM, vZ, vP);                   \
+    }
+    if (y >= r0 && y < r1) { XR_CELL(-1, -1) XR_CELL(-1, 0) XR_CELL(-1, 1) }
+    if (y + 1 >= r0 && y + 1 < r1) { XR_CELL(0, -1) XR_CELL(0, 0) XR_CELL(0, 1) }
+    if (y + 2 >= r0 && y + 2 < r1) { XR_CELL(1, -1) XR_CELL(1, 0) XR_CELL(1, 1) }
+#undef XR_CELL
+}
+
+__global__ void __launch_bounds__(XR_THREADS) p2g_xrow_kernel(P2GParams p, uint8_t* __restrict__ todo) {
+    __shared__ __align__(16) float sP[XR_CAP * 6];
+    __shared__ uint8_t cellOf[XR_CAP];
+    __shared__ uint32_t cBeg[PLANE_CELLS];
+    __shared__ int cCnt[PLANE_CELLS];
+    __shared__ int cPre[PLANE_CELLS + 1];   // first record of the cell, counted over the whole plane (pads included)
+    __shared__ int sRow[12];                // batch b = cell rows [sRow[b], sRow[b+1])
+    __shared__ int sNB;
+
+    const int leaf = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int y = tid >> 3, z = tid & 7;
+    const int* nbr = p.t.nbr27 + (size_t)leaf * 27;
+    XAcc M, Z, P;
+    xacc_reset(M); xacc_reset(Z); xacc_reset(P);
+
+    for (int cx = -1; cx <= 8; cx++) {
+        __syncthreads();   // the previous plane's readers are done
+        for (int c = tid; c < PLANE_CELLS; c += XR_THREADS) {
+            int cy = c / 10 - 1, cz = c % 10 - 1;
+            int li = (cx < 0 ? 0 : (cx < 8 ? 1 : 2)) * 9 + (cy < 0 ? 0 : (cy < 8 ? 1 : 2)) * 3 + (cz < 0 ? 0 : (cz < 8 ? 1 : 2));
+            int nl = nbr[li];
+            uint32_t b = 0, n = 0;
+            if (nl >= 0) {
+                size_t v = (size_t)nl * LEAF + (((cx & 7) << 6) | ((cy & 7) << 3) | (cz & 7));
+                b = __ldg(&p.voxelStart[v]);
+                n = __ldg(&p.voxelStart[v + 1]) - b;
+            }
+            cBeg[c] = b; cCnt[c] = (int)n;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            int run = 0;
+            for (int base = 0; base < PLANE_CELLS; base += 32) {
+                int c = base + tid;
+                int v = c < PLANE_CELLS ? cCnt[c] + 1 : 0;
+                int incl = v;
+                for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, d); if (tid >= d) incl += u; }
+                if (c < PLANE_CELLS) cPre[c] = run + incl - v;
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (tid == 0) cPre[PLANE_CELLS] = run;
+            __syncwarp();
+            if (tid == 0) {
+                int nb = 0, r = 0;
+                sRow[0] = 0;
+                if (run > PLANE_CELLS) {   // a plane without particles has no batches
+                    while (r < 10) {
+                        int start = cPre[r * 10], e = r;
+                        while (e < 10 && cPre[(e + 1) * 10] - start <= XR_CAP) e++;
+                        if (e == r) { nb = -1; break; }
+                        r = e; sRow[++nb] = r;
+                    }
+                }
+                sNB = nb;
+            }
+        }
+        __syncthreads();
+        const int nB = sNB;
+        if (nB < 0) { if (tid == 0) todo[leaf] = 1; return; }
+        const bool vM = cx <= 6, vZ = cx >= 0 && cx <= 7, vP = cx >= 1;
+        for (int b = 0; b < nB; b++) {
+            const int r0 = sRow[b], r1 = sRow[b + 1];
+            const int base = cPre[r0 * 10];
+            const int total = cPre[r1 * 10] - base;
+            if (b > 0) __syncthreads();
+            // slot -> cell map: thread c marks the records of cell c (pad included)
+            for (int c = r0 * 10 + tid; c < r1 * 10; c += XR_THREADS) {
+                const int s0 = cPre[c] - base, n = cCnt[c];
+                for (int j = 0; j <= n; j++) cellOf[s0 + j] = (uint8_t)c;
+            }
+            __syncthreads();
+            for (int sl = tid; sl < total; sl += XR_THREADS) {
+                const int c = cellOf[sl];
+                const int j = sl + base - cPre[c];
+                if (j < cCnt[c]) {
+                    const uint32_t gi = cBeg[c] + (uint32_t)j;
+                    const uint32_t a0 = __ldg(&p.w0[gi]), a1 = __ldg(&p.w1[gi]), a2 = __ldg(&p.w2[gi]);
+                    float2* dst = reinterpret_cast<float2*>(sP + (size_t)sl * 6);
+                    dst[0] = make_float2(fx_decode_fast(a0 & 0xffffu), fx_decode_fast(a0 >> 16));
+                    dst[1] = make_float2(fx_decode_fast(a1 & 0xffffu), h_decode(a1 >> 16));
+                    dst[2] = make_float2(h_decode(a2 & 0xffffu), h_decode(a2 >> 16));
+                }
+            }
+            __syncthreads();
+            if (vM && vZ && vP) xr_rows<true>(sP, cPre, cCnt, base, r0, r1, y, z, M, Z, P, true, true, true);
+            else xr_rows<false>(sP, cPre, cCnt, base, r0, r1, y, z, M, Z, P, vM, vZ, vP);
+        }
+        // target x = cx-1 has seen its last plane: normalize_p2g_velocity (FF/FLIP_vdb.cpp:120-165) + sdf transform (:1199-1204)
+        if (vP) {
+            const int vo = ((cx - 1) << 6) | tid;
+            const bool touched = P.cn > 0;
+            bool on0 = false, on1 = false, on2 = false;
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+            if (touched && P.g0 != 0.f) { o0 = __fdiv_rn(P.a0, __fadd_rn(P.g0, 0.001f)); on0 = true; }
+            if (touched && P.g1 != 0.f) { o1 = __fdiv_rn(P.a1, __fadd_rn(P.g1, 0.001f)); on1 = true; }
+            if (touched && P.g2 != 0.f) { o2 = __fdiv_rn(P.a2, __fadd_rn(P.g2, 0.001f)); on2 = true; }
+            const size_t gi = (size_t)leaf * LEAF + vo;
+            p.vel[0][gi] = o0; p.vel[1][gi] = o1; p.vel[2][gi] = o2;
+            float s = p.sdfBg;
+            if (touched) s = fminf(s, __fsub_rn(__fmul_rn(p.dx, sqrtf(P.md)), p.radius));
+            p.sdf[gi] = s;
+            const unsigned bt = __ballot_sync(0xffffffffu, touched);
+            const unsigned b0 = __ballot_sync(0xffffffffu, on0), b1 = __ballot_sync(0xffffffffu, on1), b2 = __ballot_sync(0xffffffffu, on2);
+            if ((tid & 31) == 0) {
+                const size_t wi = (size_t)leaf * 16 + (vo >> 5);
+                const size_t nW = (size_t)p.t.n * 16;
+                reinterpret_cast<uint32_t*>(p.topoMask)[wi] = bt;
+                reinterpret_cast<uint32_t*>(p.chMask)[wi] = b0;
+                reinterpret_cast<uint32_t*>(p.chMask)[nW + wi] = b1;
+                reinterpret_cast<uint32_t*>(p.chMask)[2 * nW + wi] = b2;
+            }
+        }
+        P = Z; Z = M; xacc_reset(M);
     }
 }
 
@@ -389,9 +596,22 @@ void p2g(World* w, float dx, int velExtraLayer) {
         attrSet = true;
     }
     // algorithmic bytes: 12 B/particle + 4 B/voxel offsets + 16 B/voxel outputs
-    FB_LAUNCH(w, "p2g_gather", w->pts.n * 12 + (size_t)n * LEAF * 20)
-        p2g_gather_kernel<<<n, P2G_THREADS, smemBytes, w->stream>>>(p);
-    check_launch("p2g_gather");
+    const bool oldPath = getenv("FLIPB200_P2G_OLD") != nullptr;   // read per call: tests/test_p2g_paths_gpu.py compares both
+    if (oldPath) {
+        FB_LAUNCH(w, "p2g_gather", w->pts.n * 12 + (size_t)n * LEAF * 20)
+            p2g_gather_kernel<<<n, P2G_THREADS, smemBytes, w->stream>>>(p, nullptr);
+        check_launch("p2g_gather");
+    } else {
+        DBuf<uint8_t> todo((size_t)n, w->stream);
+        todo.zero();
+        FB_LAUNCH(w, "p2g_gather", w->pts.n * 12 + (size_t)n * LEAF * 20)
+            p2g_xrow_kernel<<<n, XR_THREADS, 0, w->stream>>>(p, todo.p);
+        check_launch("p2g_xrow");
+        // leaves with a cell row beyond the staging buffer (only an un-capped initial binning can produce one)
+        FB_LAUNCH(w, "p2g_gather_fallback", 0)
+            p2g_gather_kernel<<<n, P2G_THREADS, smemBytes, w->stream>>>(p, todo.p);
+        check_launch("p2g_gather_fallback");
+    }
 
     // air ring: airmask = dilate26(topo) \ topo ; final sdf mask = topo + ring voxels with a liquid face neighbour
     mask_dilate(w, *pool, topoMask.p, ring.p, true);
