@@ -215,15 +215,24 @@ __global__ void __launch_bounds__(P2G_THREADS) p2g_gather_kernel(P2GParams p, co
 // oy order); a single row that does not fit hands the leaf back to p2g_gather_kernel through `todo`.
 constexpr int XR_THREADS = 64;
 #ifndef FB_XR_CAP
-#define FB_XR_CAP 1344
+#define FB_XR_CAP 1024   // 8 CTAs per SM; measured 1178 us against 1304 us at 1344 (6 CTAs) and 1458 us at 1600 (5 CTAs)
+#endif
+#ifndef FB_XR_UNROLL
+#define FB_XR_UNROLL 8
+#endif
+#ifndef FB_XR_JUNROLL
+#define FB_XR_JUNROLL 2
 #endif
 constexpr int XR_CAP = FB_XR_CAP;   // staged records per batch, pad records included
+constexpr int XR_JUNROLL = FB_XR_JUNROLL;
+constexpr int XR_MIN_CTAS = 8;
+constexpr int XR_STAGE_UNROLL = FB_XR_UNROLL;
 
 struct XAcc { float a0, a1, a2, g0, g1, g2, md; int cn; };
 __device__ __forceinline__ void xacc_reset(XAcc& A) { A.a0 = A.a1 = A.a2 = A.g0 = A.g1 = A.g2 = 0.f; A.md = 3.0e38f; A.cn = 0; }
 
-// one (particle, target) pair; OX/OY/OZ = source cell - target voxel
-template <int OX, int OY, int OZ>
+// one (particle, target) pair; OX = source cell - target voxel in x
+template <int OX>
 __device__ __forceinline__ void xr_pair(XAcc& A, float px, float vx, float vy, float vz, float ty2, float tz2, float hy, float hz,
                                         float ysh, float zsh) {
     const float fx = (float)(-OX);
@@ -237,56 +246,74 @@ __device__ __forceinline__ void xr_pair(XAcc& A, float px, float vx, float vy, f
         A.a0 = __fadd_rn(__fmul_rn(vx, wgt), A.a0);
         A.g0 = __fadd_rn(wgt, A.g0);
     }
-    if (OY != 1) {
+    {   // v / w from a source cell at oy / oz = +1: the staggered hat is exactly 0 there (|-1.5 - p| >= 1 for every decodable p),
+        // the products are +-0 and the sums do not change -- the same bits as skipping the term, without a branch per cell offset
         const float wgt = __fmul_rn(__fmul_rn(hx, ysh), hz);
         A.a1 = __fadd_rn(__fmul_rn(vy, wgt), A.a1);
         A.g1 = __fadd_rn(wgt, A.g1);
     }
-    if (OZ != 1) {
+    {
         const float wgt = __fmul_rn(__fmul_rn(hx, hy), zsh);
         A.a2 = __fadd_rn(__fmul_rn(vz, wgt), A.a2);
         A.g2 = __fadd_rn(wgt, A.g2);
     }
 }
 
-// the particles of one source cell against the thread's three live targets (M: x = cx+1, Z: x = cx, P: x = cx-1)
-template <int OY, int OZ, bool ALL>
-__device__ __forceinline__ void xr_cell(const float* __restrict__ rec, int cnt, XAcc& M, XAcc& Z, XAcc& P, bool vM, bool vZ, bool vP) {
-    const float fy = (float)(-OY), fz = (float)(-OZ);
+// the particles of one source cell against the thread's three live targets (M: x = cx+1, Z: x = cx, P: x = cx-1).
+// ONE loop body serves all nine (oy, oz) offsets (fy = -oy, fz = -oz at run time): nine specialised copies (x 2 variants) were
+// 64 KB of code and the kernel spent 29 % of its warp samples waiting for instructions (ncu: stall_no_inst).
+template <bool ALL>
+__device__ __forceinline__ void xr_cell(const float* __restrict__ rec, int cnt, float fy, float fz, XAcc& M, XAcc& Z, XAcc& P, bool vM, bool vZ, bool vP) {
     const float2* __restrict__ src = reinterpret_cast<const float2*>(rec);
+    const float fyh = fy - 0.5f, fzh = fz - 0.5f;
     if (ALL || vM) M.cn += cnt;
     if (ALL || vZ) Z.cn += cnt;
     if (ALL || vP) P.cn += cnt;
+    // the record of the next visit is loaded while this one is evaluated; past the last particle that is the cell's pad record
+    float2 n0 = src[0], n1 = src[1], n2 = src[2];
+#pragma unroll XR_JUNROLL
     for (int j = 0; j < cnt; j++) {
-        const float2 q0 = src[3 * j], q1 = src[3 * j + 1], q2 = src[3 * j + 2];
+        const float2 q0 = n0, q1 = n1, q2 = n2;
+        n0 = src[3 * j + 3]; n1 = src[3 * j + 4]; n2 = src[3 * j + 5];
         const float px = q0.x, py = q0.y, pz = q1.x, vx = q1.y, vy = q2.x, vz = q2.y;
         const float ty = fabsf(__fsub_rn(fy, py)), tz = fabsf(__fsub_rn(fz, pz));
         const float ty2 = __fmul_rn(ty, ty), tz2 = __fmul_rn(tz, tz);
         const float hy = fmaxf(0.f, __fsub_rn(1.0f, ty)), hz = fmaxf(0.f, __fsub_rn(1.0f, tz));
-        float ysh = 0.f, zsh = 0.f;
-        if (OY != 1) ysh = fmaxf(0.f, __fsub_rn(1.0f, fabsf(__fsub_rn(fy - 0.5f, py))));
-        if (OZ != 1) zsh = fmaxf(0.f, __fsub_rn(1.0f, fabsf(__fsub_rn(fz - 0.5f, pz))));
-        if (ALL || vM) xr_pair<-1, OY, OZ>(M, px, vx, vy, vz, ty2, tz2, hy, hz, ysh, zsh);
-        if (ALL || vZ) xr_pair<0, OY, OZ>(Z, px, vx, vy, vz, ty2, tz2, hy, hz, ysh, zsh);
-        if (ALL || vP) xr_pair<1, OY, OZ>(P, px, vx, vy, vz, ty2, tz2, hy, hz, ysh, zsh);
+        const float ysh = fmaxf(0.f, __fsub_rn(1.0f, fabsf(__fsub_rn(fyh, py))));
+        const float zsh = fmaxf(0.f, __fsub_rn(1.0f, fabsf(__fsub_rn(fzh, pz))));
+        if (ALL || vM) xr_pair<-1>(M, px, vx, vy, vz, ty2, tz2, hy, hz, ysh, zsh);
+        if (ALL || vZ) xr_pair<0>(Z, px, vx, vy, vz, ty2, tz2, hy, hz, ysh, zsh);
+        if (ALL || vP) xr_pair<1>(P, px, vx, vy, vz, ty2, tz2, hy, hz, ysh, zsh);
     }
 }
 
 template <bool ALL>
 __device__ __forceinline__ void xr_rows(const float* __restrict__ sP, const int* __restrict__ cPre, const int* __restrict__ cCnt, int base,
                                         int r0, int r1, int y, int z, XAcc& M, XAcc& Z, XAcc& P, bool vM, bool vZ, bool vP) {
-#define XR_CELL(OY, OZ)                                                                                          \
-    {                                                                                                            \
-        const int c = (y + (OY) + 1) * 10 + (z + (OZ) + 1);                                                      \
-        xr_cell<OY, OZ, ALL>(sP + (size_t)(cPre[c] - base) * 6, cCnt[c], M, Z, P, vM, vZ, vP);                   \
+#pragma unroll 1
+    for (int k = 0; k < 9; k++) {   // (oy, oz) in lexicographic order
+        const int oy = k / 3 - 1, oz = k - (k / 3) * 3 - 1;
+        const int row = y + oy + 1;
+        if (row < r0 || row >= r1) continue;   // only a plane split into row batches diverges here
+        const int c = row * 10 + (z + oz + 1);
+        xr_cell<ALL>(sP + (size_t)(cPre[c] - base) * 6, cCnt[c], (float)(-oy), (float)(-oz), M, Z, P, vM, vZ, vP);
     }
-    if (y >= r0 && y < r1) { XR_CELL(-1, -1) XR_CELL(-1, 0) XR_CELL(-1, 1) }
-    if (y + 1 >= r0 && y + 1 < r1) { XR_CELL(0, -1) XR_CELL(0, 0) XR_CELL(0, 1) }
-    if (y + 2 >= r0 && y + 2 < r1) { XR_CELL(1, -1) XR_CELL(1, 0) XR_CELL(1, 1) }
-#undef XR_CELL
 }
 
-__global__ void __launch_bounds__(XR_THREADS) p2g_xrow_kernel(P2GParams p, uint8_t* __restrict__ todo) {
+// voxelStart range of plane cell c (c = (cy+1)*10 + cz+1) at source plane cx
+__device__ __forceinline__ void xr_cell_range(const P2GParams& p, const int* __restrict__ sNbr, int cx, int c, uint32_t& b, uint32_t& n) {
+    const int cy = c / 10 - 1, cz = c % 10 - 1;
+    const int li = (cx < 0 ? 0 : (cx < 8 ? 1 : 2)) * 9 + (cy < 0 ? 0 : (cy < 8 ? 1 : 2)) * 3 + (cz < 0 ? 0 : (cz < 8 ? 1 : 2));
+    const int nl = sNbr[li];
+    b = 0; n = 0;
+    if (nl >= 0 && c < PLANE_CELLS) {
+        const size_t v = (size_t)nl * LEAF + (((cx & 7) << 6) | ((cy & 7) << 3) | (cz & 7));
+        b = __ldg(&p.voxelStart[v]);
+        n = __ldg(&p.voxelStart[v + 1]) - b;
+    }
+}
+
+__global__ void __launch_bounds__(XR_THREADS, XR_MIN_CTAS) p2g_xrow_kernel(P2GParams p, uint8_t* __restrict__ todo) {
     __shared__ __align__(16) float sP[XR_CAP * 6];
     __shared__ uint8_t cellOf[XR_CAP];
     __shared__ uint32_t cBeg[PLANE_CELLS];
@@ -294,27 +321,28 @@ __global__ void __launch_bounds__(XR_THREADS) p2g_xrow_kernel(P2GParams p, uint8
     __shared__ int cPre[PLANE_CELLS + 1];   // first record of the cell, counted over the whole plane (pads included)
     __shared__ int sRow[12];                // batch b = cell rows [sRow[b], sRow[b+1])
     __shared__ int sNB;
+    __shared__ int sNbr[27];
 
     const int leaf = blockIdx.x;
     const int tid = threadIdx.x;
     const int y = tid >> 3, z = tid & 7;
-    const int* nbr = p.t.nbr27 + (size_t)leaf * 27;
+    if (tid < 27) sNbr[tid] = p.t.nbr27[(size_t)leaf * 27 + tid];
+    __syncthreads();
     XAcc M, Z, P;
     xacc_reset(M); xacc_reset(Z); xacc_reset(P);
+    // the cell ranges of a plane are fetched one plane ahead (two cells per thread), so that the plane's staging starts
+    // with the particle loads instead of a dependent voxelStart round trip
+    uint32_t nb0, nn0, nb1, nn1;
+    xr_cell_range(p, sNbr, -1, tid, nb0, nn0);
+    xr_cell_range(p, sNbr, -1, tid + XR_THREADS, nb1, nn1);
 
     for (int cx = -1; cx <= 8; cx++) {
         __syncthreads();   // the previous plane's readers are done
-        for (int c = tid; c < PLANE_CELLS; c += XR_THREADS) {
-            int cy = c / 10 - 1, cz = c % 10 - 1;
-            int li = (cx < 0 ? 0 : (cx < 8 ? 1 : 2)) * 9 + (cy < 0 ? 0 : (cy < 8 ? 1 : 2)) * 3 + (cz < 0 ? 0 : (cz < 8 ? 1 : 2));
-            int nl = nbr[li];
-            uint32_t b = 0, n = 0;
-            if (nl >= 0) {
-                size_t v = (size_t)nl * LEAF + (((cx & 7) << 6) | ((cy & 7) << 3) | (cz & 7));
-                b = __ldg(&p.voxelStart[v]);
-                n = __ldg(&p.voxelStart[v + 1]) - b;
-            }
-            cBeg[c] = b; cCnt[c] = (int)n;
+        cBeg[tid] = nb0; cCnt[tid] = (int)nn0;
+        if (tid + XR_THREADS < PLANE_CELLS) { cBeg[tid + XR_THREADS] = nb1; cCnt[tid + XR_THREADS] = (int)nn1; }
+        if (cx < 8) {
+            xr_cell_range(p, sNbr, cx + 1, tid, nb0, nn0);
+            xr_cell_range(p, sNbr, cx + 1, tid + XR_THREADS, nb1, nn1);
         }
         __syncthreads();
         if (tid < 32) {
@@ -358,16 +386,31 @@ __global__ void __launch_bounds__(XR_THREADS) p2g_xrow_kernel(P2GParams p, uint8
                 for (int j = 0; j <= n; j++) cellOf[s0 + j] = (uint8_t)c;
             }
             __syncthreads();
-            for (int sl = tid; sl < total; sl += XR_THREADS) {
-                const int c = cellOf[sl];
-                const int j = sl + base - cPre[c];
-                if (j < cCnt[c]) {
-                    const uint32_t gi = cBeg[c] + (uint32_t)j;
-                    const uint32_t a0 = __ldg(&p.w0[gi]), a1 = __ldg(&p.w1[gi]), a2 = __ldg(&p.w2[gi]);
-                    float2* dst = reinterpret_cast<float2*>(sP + (size_t)sl * 6);
-                    dst[0] = make_float2(fx_decode_fast(a0 & 0xffffu), fx_decode_fast(a0 >> 16));
-                    dst[1] = make_float2(fx_decode_fast(a1 & 0xffffu), h_decode(a1 >> 16));
-                    dst[2] = make_float2(h_decode(a2 & 0xffffu), h_decode(a2 >> 16));
+            for (int s0 = 0; s0 < total; s0 += XR_STAGE_UNROLL * XR_THREADS) {
+                uint32_t a0[XR_STAGE_UNROLL], a1[XR_STAGE_UNROLL], a2[XR_STAGE_UNROLL];
+                bool ok[XR_STAGE_UNROLL];
+#pragma unroll
+                for (int k = 0; k < XR_STAGE_UNROLL; k++) {   // every load of the round is issued before the first decode
+                    const int sl = s0 + k * XR_THREADS + tid;
+                    ok[k] = false;
+                    if (sl < total) {
+                        const int c = cellOf[sl];
+                        const int j = sl + base - cPre[c];
+                        if (j < cCnt[c]) {
+                            const uint32_t gi = cBeg[c] + (uint32_t)j;
+                            a0[k] = __ldg(&p.w0[gi]); a1[k] = __ldg(&p.w1[gi]); a2[k] = __ldg(&p.w2[gi]);
+                            ok[k] = true;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < XR_STAGE_UNROLL; k++) {
+                    if (ok[k]) {
+                        float2* dst = reinterpret_cast<float2*>(sP + (size_t)(s0 + k * XR_THREADS + tid) * 6);
+                        dst[0] = make_float2(fx_decode_fast(a0[k] & 0xffffu), fx_decode_fast(a0[k] >> 16));
+                        dst[1] = make_float2(fx_decode_fast(a1[k] & 0xffffu), h_decode(a1[k] >> 16));
+                        dst[2] = make_float2(h_decode(a2[k] & 0xffffu), h_decode(a2[k] >> 16));
+                    }
                 }
             }
             __syncthreads();
