@@ -48,6 +48,9 @@ __global__ void layer_bounds_kernel(const int3* __restrict__ origin, int n, cons
     int a = 0, b = n;   // first slot whose leaf x >= x (origins are sorted by x first)
     while (a < b) { int m = (a + b) >> 1; if ((origin[m].x >> 3) < x) a = m + 1; else b = m; }
     out[k] = a;
+    __syncwarp();
+    // what the neighbours receive from me: one / two layers to the left, one / two to the right (out[6..9])
+    if (k == 0) { out[6] = out[1] - out[0]; out[7] = out[2] - out[0]; out[8] = out[5] - out[4]; out[9] = out[5] - out[3]; }
 }
 __global__ void map_kernel(TopoView t, const int3* __restrict__ origins, int n, int* __restrict__ map) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,35 +74,126 @@ __global__ void unpack_kernel(UnpackArgs a, const int* __restrict__ map) {
         for (int i = threadIdx.x; i < bpl; i += blockDim.x) dst[i] = src[i];
     }
 }
-// migration: 1 = goes to the left neighbour, 2 = to the right, 4 = stays in this rank's extended region
-__global__ void migrate_flags_kernel(const int3* __restrict__ ijk, const uint8_t* __restrict__ alive, uint64_t pLo, uint64_t m,
-                                     int lo, int hi, int hasLeft, int hasRight, uint32_t* __restrict__ fL,
-                                     uint32_t* __restrict__ fR, uint32_t* __restrict__ fK, int leftLo, int rightHi, int* __restrict__ strayed) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const uint64_t g = pLo + i;
-    const bool a = alive ? alive[g] != 0 : true;
-    const int lx = ijk[g].x >> 3;
+// migration: a particle goes to the left neighbour (1), to the right one (2) and / or stays in this rank's extended region (4).
+// One stable three-way partition in two passes over the particles (count per block of 1024, scatter) with a one-CTA scan of the
+// block counts between them; round 1 wrote three flag arrays, scanned each over all particles (three host-read totals) and
+// compacted in a fourth pass.
+constexpr int MG_THREADS = 256, MG_ITEMS = 4, MG_BLOCK = MG_THREADS * MG_ITEMS;
+struct MigrateArgs {
+    const int3* ijk; const uint8_t* alive; uint64_t pLo, m;
+    int lo, hi, hasLeft, hasRight, leftLo, rightHi;
+};
+__device__ __forceinline__ unsigned migrate_flags(const MigrateArgs& A, uint64_t i, bool& stray) {
+    const uint64_t g = A.pLo + i;
+    const bool a = A.alive ? A.alive[g] != 0 : true;
+    const int lx = A.ijk[g].x >> 3;
     // beyond the neighbour's own slab: it would sit there as a ghost nobody advects (migration is one hop)
-    if (a && ((hasLeft && lx < leftLo) || (hasRight && lx >= rightHi))) atomicAdd(strayed, 1);
-    fL[i] = (a && hasLeft && lx < lo + 1) ? 1u : 0u;
-    fR[i] = (a && hasRight && lx >= hi - 1) ? 1u : 0u;
-    fK[i] = (a && (!hasLeft || lx >= lo - 1) && (!hasRight || lx < hi + 1)) ? 1u : 0u;
+    stray = a && ((A.hasLeft && lx < A.leftLo) || (A.hasRight && lx >= A.rightHi));
+    unsigned f = 0;
+    if (a && A.hasLeft && lx < A.lo + 1) f |= 1u;
+    if (a && A.hasRight && lx >= A.hi - 1) f |= 2u;
+    if (a && (!A.hasLeft || lx >= A.lo - 1) && (!A.hasRight || lx < A.hi + 1)) f |= 4u;
+    return f;
+}
+__global__ void __launch_bounds__(MG_THREADS) migrate_count_kernel(MigrateArgs A, uint32_t* __restrict__ blockCnt, unsigned nb, int* __restrict__ strayed) {
+    __shared__ uint32_t sm[3][MG_THREADS / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * MG_BLOCK + (uint64_t)threadIdx.x * MG_ITEMS;
+    uint32_t c[3] = {0, 0, 0};
+    int ns = 0;
+#pragma unroll
+    for (int k = 0; k < MG_ITEMS; k++) {
+        if (base + k < A.m) {
+            bool st;
+            const unsigned f = migrate_flags(A, base + k, st);
+            c[0] += f & 1u; c[1] += (f >> 1) & 1u; c[2] += (f >> 2) & 1u;
+            ns += st ? 1 : 0;
+        }
+    }
+    if (ns) atomicAdd(strayed, ns);
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        uint32_t v = c[a];
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if ((threadIdx.x & 31) == 0) sm[a][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        uint32_t t = 0;
+        for (int k = 0; k < MG_THREADS / 32; k++) t += sm[threadIdx.x][k];
+        blockCnt[(size_t)threadIdx.x * nb + blockIdx.x] = t;
+    }
+}
+// exclusive scan of the three block-count rows in place, totals to tot[0..2] (one CTA: a row holds m / 1024 entries)
+__global__ void __launch_bounds__(1024) migrate_scan_kernel(uint32_t* __restrict__ blockCnt, unsigned nb, int* __restrict__ tot) {
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t carry;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int a = 0; a < 3; a++) {
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        for (unsigned base = 0; base < nb; base += 1024) {
+            const unsigned i = base + threadIdx.x;
+            const uint32_t v = i < nb ? blockCnt[(size_t)a * nb + i] : 0u;
+            uint32_t incl = v;
+            for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+            if (lane == 31) ws[wid] = incl;
+            __syncthreads();
+            if (wid == 0) {
+                uint32_t t = ws[lane], ti = t;
+                for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= d) ti += u; }
+                ws[lane] = ti - t;
+            }
+            __syncthreads();
+            const uint32_t excl = carry + ws[wid] + incl - v;
+            if (i < nb) blockCnt[(size_t)a * nb + i] = excl;
+            __syncthreads();
+            if (threadIdx.x == 1023) carry = excl + v;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) tot[a] = (int)carry;
+        __syncthreads();
+    }
 }
 struct CompactDst { uint32_t *w0, *w1, *w2; int3* ijk; };
-__global__ void migrate_compact_kernel(const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1, const uint32_t* __restrict__ w2,
-                                       const int3* __restrict__ ijk, uint64_t pLo, uint64_t m, const uint32_t* __restrict__ fL,
-                                       const uint32_t* __restrict__ fR, const uint32_t* __restrict__ fK, const uint32_t* __restrict__ pL,
-                                       const uint32_t* __restrict__ pR, const uint32_t* __restrict__ pK, CompactDst L, CompactDst R,
-                                       CompactDst K) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const uint64_t g = pLo + i;
-    const uint32_t a = w0[g], b = w1[g], c = w2[g];
-    const int3 v = ijk[g];
-    if (fL[i]) { uint32_t d = pL[i]; L.w0[d] = a; L.w1[d] = b; L.w2[d] = c; L.ijk[d] = v; }
-    if (fR[i]) { uint32_t d = pR[i]; R.w0[d] = a; R.w1[d] = b; R.w2[d] = c; R.ijk[d] = v; }
-    if (fK[i]) { uint32_t d = pK[i]; K.w0[d] = a; K.w1[d] = b; K.w2[d] = c; K.ijk[d] = v; }
+__global__ void __launch_bounds__(MG_THREADS) migrate_scatter_kernel(MigrateArgs A, const uint32_t* __restrict__ w0, const uint32_t* __restrict__ w1,
+                                                                     const uint32_t* __restrict__ w2, const uint32_t* __restrict__ blockOff, unsigned nb,
+                                                                     CompactDst L, CompactDst R, CompactDst K) {
+    __shared__ uint32_t sm[3][MG_THREADS / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * MG_BLOCK + (uint64_t)threadIdx.x * MG_ITEMS;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned f[MG_ITEMS];
+    uint32_t c[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < MG_ITEMS; k++) {
+        f[k] = 0;
+        if (base + k < A.m) { bool st; f[k] = migrate_flags(A, base + k, st); }
+        c[0] += f[k] & 1u; c[1] += (f[k] >> 1) & 1u; c[2] += (f[k] >> 2) & 1u;
+    }
+    uint32_t pos[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {   // exclusive scan over the block's threads (items of a thread are consecutive: the order is kept)
+        uint32_t incl = c[a];
+        for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        if (lane == 31) sm[a][wid] = incl;
+        pos[a] = incl - c[a];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        uint32_t before = 0;
+        for (unsigned k = 0; k < wid; k++) before += sm[a][k];
+        pos[a] += before + blockOff[(size_t)a * nb + blockIdx.x];
+    }
+#pragma unroll
+    for (int k = 0; k < MG_ITEMS; k++) {
+        if (!f[k]) continue;
+        const uint64_t g = A.pLo + base + k;
+        const uint32_t a = w0[g], b = w1[g], c2 = w2[g];
+        const int3 v = A.ijk[g];
+        if (f[k] & 1u) { const uint32_t d = pos[0]++; L.w0[d] = a; L.w1[d] = b; L.w2[d] = c2; L.ijk[d] = v; }
+        if (f[k] & 2u) { const uint32_t d = pos[1]++; R.w0[d] = a; R.w1[d] = b; R.w2[d] = c2; R.ijk[d] = v; }
+        if (f[k] & 4u) { const uint32_t d = pos[2]++; K.w0[d] = a; K.w1[d] = b; K.w2[d] = c2; K.ijk[d] = v; }
+    }
 }
 
 // two ints to each neighbour, two from each
@@ -127,19 +221,25 @@ DDMaps& dd_maps(World* w) {
     const bool hasL = w->rank > 0, hasR = w->rank < w->nRanks - 1;
     const int lo = hasL ? D.lo : -DD_OPEN, hi = hasR ? D.hi : DD_OPEN;
     int xs[6] = {lo, std::min(lo + 1, hi), std::min(lo + 2, hi), std::max(hi - 2, lo), std::max(hi - 1, lo), hi};
-    if (t.n > 0) {
-        DBuf<int> d(12, w->stream);
-        FB_CUDA(cudaMemcpyAsync(d.p, xs, sizeof(xs), cudaMemcpyHostToDevice, w->stream));
-        FB_LAUNCH(w, "dd_layer_bounds", 64) layer_bounds_kernel<<<1, 32, 0, w->stream>>>(t.origin.p, t.n, d.p, d.p + 6);
-        check_launch("layer_bounds");
-        FB_CUDA(cudaMemcpyAsync(M.b, d.p + 6, sizeof(M.b), cudaMemcpyDeviceToHost, w->stream));
-        sync(w);
-    } else {
-        for (int k = 0; k < 6; k++) M.b[k] = 0;
-    }
+    // layer bounds and the neighbours' layer sizes in ONE read-back: the bounds stay on the device, the counts derived from
+    // them travel device to device (round 1: a read-back of the bounds, then a host round trip for the counts)
+    DBuf<int> d(24, w->stream);   // [0..5] xs, [6..11] b, [12..15] toLeft[2] toRight[2], [16..19] fromLeft[2] fromRight[2]
+    d.zero();
+    FB_CUDA(cudaMemcpyAsync(d.p, xs, sizeof(xs), cudaMemcpyHostToDevice, w->stream));
+    FB_LAUNCH(w, "dd_layer_bounds", 64) layer_bounds_kernel<<<1, 32, 0, w->stream>>>(t.origin.p, t.n, d.p, d.p + 6);
+    check_launch("layer_bounds");
+    comm_group_begin(w);
+    if (hasL) { comm_send(w, w->rank - 1, d.p + 12, 8); comm_recv(w, w->rank - 1, d.p + 16, 8); }
+    if (hasR) { comm_send(w, w->rank + 1, d.p + 14, 8); comm_recv(w, w->rank + 1, d.p + 18, 8); }
+    comm_group_end(w);
+    int hb[14];
+    read_back(w, hb, d.p + 6, sizeof(hb));
+    for (int k = 0; k < 6; k++) M.b[k] = hb[k];
     const int toLeft[2] = {M.b[1] - M.b[0], M.b[2] - M.b[0]};
     const int toRight[2] = {M.b[5] - M.b[4], M.b[5] - M.b[3]};
-    exchange_counts(w, toLeft, toRight, M.recvCnt[0], M.recvCnt[1]);
+    FB_REQUIRE(hb[6] == toLeft[0] && hb[7] == toLeft[1] && hb[8] == toRight[0] && hb[9] == toRight[1], FLIPB200_ERR_STATE, "dd_maps: layer counts");
+    M.recvCnt[0][0] = hasL ? hb[10] : 0; M.recvCnt[0][1] = hasL ? hb[11] : 0;
+    M.recvCnt[1][0] = hasR ? hb[12] : 0; M.recvCnt[1][1] = hasR ? hb[13] : 0;
     // origins of the two-layer lists, then where each received leaf lives in my pool
     DBuf<int3> in[2];
     in[0].alloc(M.recvCnt[0][1] + 1, w->stream);
@@ -162,8 +262,7 @@ DDMaps& dd_maps(World* w) {
             check_launch("dd_map");
         }
     }
-    sync(w);
-    M.epoch = t.epoch;
+    M.epoch = t.epoch;   // everything above is ordered on the world's stream; the temporaries are freed stream-ordered
     return M;
 }
 }  // namespace
@@ -262,29 +361,31 @@ void dd_migrate(World* w, uint64_t pLo, uint64_t pHi, const uint32_t* w0, const 
                 const uint8_t* alive, DBuf<uint32_t>& o0, DBuf<uint32_t>& o1, DBuf<uint32_t>& o2, DBuf<int3>& oijk, uint64_t* nOut) {
     const bool hasL = w->rank > 0, hasR = w->rank < w->nRanks - 1;
     const uint64_t m = pHi - pLo;
-    DBuf<uint32_t> fL(m + 1, w->stream), fR(m + 1, w->stream), fK(m + 1, w->stream);
-    DBuf<uint32_t> pL(m + 1, w->stream), pR(m + 1, w->stream), pK(m + 1, w->stream);
-    fL.zero(); fR.zero(); fK.zero();
     check_bounds(w);
     DDState& D = *w->dd;
-    if (!D.strayed.p) D.strayed.alloc(1, w->stream);
-    D.strayed.zero();
+    const unsigned nb = (unsigned)std::max<uint64_t>(1, (m + MG_BLOCK - 1) / MG_BLOCK);
+    DBuf<uint32_t> blockCnt((size_t)3 * nb, w->stream);
+    DBuf<int> tot(8, w->stream);   // [0..2] to left / to right / kept, [3] strayed, [4] from left, [5] from right
+    blockCnt.zero(); tot.zero();
+    MigrateArgs A{ijk, alive, pLo, m, D.lo, D.hi, hasL ? 1 : 0, hasR ? 1 : 0, D.leftLo, D.rightHi};
     if (m) {
-        FB_LAUNCH(w, "dd_migrate_flags", m * 25) migrate_flags_kernel<<<nblk(m, 256), 256, 0, w->stream>>>(ijk, alive, pLo, m, w->dd->lo, w->dd->hi, hasL ? 1 : 0, hasR ? 1 : 0, fL.p, fR.p, fK.p,
-                                                                                                       D.leftLo, D.rightHi, D.strayed.p);
-        check_launch("migrate_flags");
+        FB_LAUNCH(w, "dd_migrate_count", m * 13) migrate_count_kernel<<<nb, MG_THREADS, 0, w->stream>>>(A, blockCnt.p, nb, tot.p + 3);
+        check_launch("migrate_count");
     }
-    uint64_t cL = 0, cR = 0, cK = 0;
-    FB_PHASE(w, "dd_migrate after flags");
-    exclusive_scan_u32(w, fL.p, pL.p, m + 1, &cL);
-    exclusive_scan_u32(w, fR.p, pR.p, m + 1, &cR);
-    exclusive_scan_u32(w, fK.p, pK.p, m + 1, &cK);
-    const int toLeft[2] = {(int)cL, 0}, toRight[2] = {(int)cR, 0};
-    int fromLeft[2], fromRight[2];
-    comm_allreduce(w, D.strayed.p, 1, CT_I32, false);     // every rank must see the same verdict (a lone throw would hang the others)
-    d2h_words(w, w->hostScratch + 512, D.strayed.p, 4);   // arrives with the wait inside exchange_counts
-    exchange_counts(w, toLeft, toRight, fromLeft, fromRight);
-    const int strayed = *reinterpret_cast<const int*>(w->hostScratch + 512);
+    FB_LAUNCH(w, "dd_migrate_scan", (size_t)nb * 24) migrate_scan_kernel<<<1, 1024, 0, w->stream>>>(blockCnt.p, nb, tot.p);
+    check_launch("migrate_scan");
+    FB_PHASE(w, "dd_migrate after counts");
+    // the counts travel device to device; one read-back brings mine, the neighbours' and the (all-reduced) stray verdict
+    comm_allreduce(w, tot.p + 3, 1, CT_I32, false);     // every rank must see the same verdict (a lone throw would hang the others)
+    comm_group_begin(w);
+    if (hasL) { comm_send(w, w->rank - 1, tot.p + 0, 4); comm_recv(w, w->rank - 1, tot.p + 4, 4); }
+    if (hasR) { comm_send(w, w->rank + 1, tot.p + 1, 4); comm_recv(w, w->rank + 1, tot.p + 5, 4); }
+    comm_group_end(w);
+    int h[6] = {0, 0, 0, 0, 0, 0};
+    read_back(w, h, tot.p, sizeof(h));
+    const uint64_t cL = (uint64_t)h[0], cR = (uint64_t)h[1], cK = (uint64_t)h[2];
+    const int strayed = h[3];
+    const int fromLeft[2] = {h[4], 0}, fromRight[2] = {h[5], 0};
     FB_REQUIRE(strayed == 0, FLIPB200_ERR_DOMAIN, std::to_string(strayed) + " particles moved past a neighbour's whole slab in one step (migration is one hop): use thicker slabs or a smaller time step");
     const uint64_t rL = hasL ? (uint64_t)fromLeft[0] : 0, rR = hasR ? (uint64_t)fromRight[0] : 0;
     const uint64_t n = rL + cK + rR;
@@ -293,8 +394,8 @@ void dd_migrate(World* w, uint64_t pLo, uint64_t pHi, const uint32_t* w0, const 
     DBuf<int3> sLi(cL + 1, w->stream), sRi(cR + 1, w->stream);
     if (m) {
         CompactDst L{sL0.p, sL1.p, sL2.p, sLi.p}, R{sR0.p, sR1.p, sR2.p, sRi.p}, K{o0.p + rL, o1.p + rL, o2.p + rL, oijk.p + rL};
-        FB_LAUNCH(w, "dd_migrate_compact", m * 48) migrate_compact_kernel<<<nblk(m, 256), 256, 0, w->stream>>>(w0, w1, w2, ijk, pLo, m, fL.p, fR.p, fK.p, pL.p, pR.p, pK.p, L, R, K);
-        check_launch("migrate_compact");
+        FB_LAUNCH(w, "dd_migrate_scatter", m * 49) migrate_scatter_kernel<<<nb, MG_THREADS, 0, w->stream>>>(A, w0, w1, w2, blockCnt.p, nb, L, R, K);
+        check_launch("migrate_scatter");
     }
     comm_group_begin(w);
     if (hasL) {
