@@ -212,3 +212,142 @@ def test_sdf_nodes_under_decomposition(gpu_lib, bounds):
         util.compare_grids(gather_grid(dd, "LiquidSDF"), one.get_grid("LiquidSDF"), f"dd VDBSmoothSDF width {width}", tol=0.0, check_inactive=False)
     for w in dd + [one]:
         w.close()
+
+
+def _sorted_rows(rows):
+    return rows[np.lexsort(tuple(rows[:, k] for k in range(8, -1, -1)))]
+
+
+@pytest.mark.parametrize("bounds", [[(0, 2), (2, 4)], [(0, 2), (2, 4), (4, 6)]], ids=["2ranks", "3ranks"])
+def test_reseed_and_emitter_under_decomposition(gpu_lib, bounds):
+    """FluidReseed and ParticleEmitter on a decomposed world. A leaf's draws start at a hash of (seed, leaf origin) and read only
+    the leaf's own particles and grids within two voxels of it, so the owner of a leaf and the neighbour that holds it as a ghost
+    decide alike with no exchange: owned particles == the single world's, every rank's ghost layer == the owner's copy, and the
+    P2G that follows is bit-identical on the owned leaves."""
+    from zeno_b200 import abi
+    N = 128
+    side = 32 if len(bounds) == 2 else 48
+    pos, vel, dx = scenes.dam_break_points(N, seed=9, random_velocity=True, side=side)
+    rng = np.random.default_rng(9)
+    keep = rng.random(pos.shape[0]) < 0.4          # ~3 particles per voxel: the reseeder has work everywhere
+    pos, vel = pos[keep], (vel[keep] * 0.2).astype(np.float32)
+    solid = scenes.box_solid_sdf(N, dx)
+    one = abi.World(dx)
+    one.set_grid("SolidSDF", solid)
+    one.PrimToVDBPointDataGrid(pos, vel)
+    dd = make_dd(abi, N, bounds, pos, vel, dx, solid)
+    one.FLIP_P2G(dx, 3)
+    abi.run_ranks(dd, lambda r, w: w.FLIP_P2G(dx, 3))
+
+    def check(what):
+        ref_rows = scenes.canonical_particles(one.get_particles())
+        got = _sorted_rows(gather_particles(dd))
+        assert got.shape == ref_rows.shape, f"{what}: {got.shape[0]} owned particles vs {ref_rows.shape[0]} in the single world"
+        assert np.array_equal(got, ref_rows), f"{what}: owned particles differ from the single world"
+        for r, w in enumerate(dd):
+            lo, hi = w.dd_owned()
+            rows = scenes.canonical_particles(w.get_particles())
+            lx = ref_rows[:, 0] >> 3
+            want = ref_rows[(lx >= lo - 1) & (lx < hi + 1)]
+            assert np.array_equal(rows, want), f"{what}: rank {r} owned + ghost particle set differs"
+
+    # FLIP_P2G's liquid SDF never goes below about -0.8 dx and the reseeder only emits where it is <= -dx (the packaged graph
+    # renormalises it first): every world gets the analytic SDF of the block, as in tests/test_ref_pin_cpu.py
+    from tests.test_ref_pin_cpu import _analytic_liquid_sdf
+    sdf = _analytic_liquid_sdf(one.get_grid("LiquidSDF"), dx, 0, side)
+    one.set_grid("LiquidSDF", sdf)
+    abi.run_ranks(dd, lambda r, w: w.set_grid("LiquidSDF", sdf))
+    n0 = one.particles_info()[1]
+    one.FluidReseed(77)
+    abi.run_ranks(dd, lambda r, w: w.FluidReseed(77))
+    assert one.particles_info()[1] > 1.3 * n0, "the scene must make the reseeder work"
+    check("FluidReseed")
+
+    # a sphere across the slab face(s), partly over the block, partly in empty space (new leaves on both sides of a face)
+    cx = 8.0 * bounds[0][1] + 1.3
+    top = float(side)
+    shape = scenes.sphere_sdf(centre=(cx, top + 2.1, 9.7), radius=7.6, lo=(int(cx) - 16, int(top) - 16, -8), hi=(int(cx) + 16, int(top) + 16, 24), bg=3.0)
+    shape["values"] = (shape["values"] * np.float32(dx)).astype(np.float32)
+    shape["bg"] = np.array([3.0 * dx], np.float32)
+    n1 = one.particles_info()[1]
+    one.set_grid("KillerSDF", shape)
+    one.ParticleEmitter("KillerSDF", 0.5, 0.0, -0.75, seed=5)
+
+    def emit(r, w):
+        w.set_grid("KillerSDF", shape)
+        w.ParticleEmitter("KillerSDF", 0.5, 0.0, -0.75, seed=5)
+    abi.run_ranks(dd, emit)
+    assert one.particles_info()[1] > n1 + 1000, "the emitter must add particles"
+    check("ParticleEmitter")
+
+    one.FLIP_P2G(dx, 3)
+    abi.run_ranks(dd, lambda r, w: w.FLIP_P2G(dx, 3))
+    for name in ("Velocity", "LiquidSDF"):
+        util.compare_grids(gather_grid(dd, name), one.get_grid(name), f"dd P2G after reseed + emit: {name}", tol=0.0, check_inactive=False)
+    for w in dd + [one]:
+        w.close()
+
+
+def test_tension_and_boundary_under_decomposition(gpu_lib):
+    """Surface-tension terms and FLIPApplyBoundary on a decomposed world: both read caller-supplied grids by voxel coordinate
+    (curvature, moving solid), every rank is given the same grid, nothing is exchanged. Owned results == the single world's."""
+    from zeno_b200 import abi
+    bounds = [(0, 2), (2, 4)]
+    N, side = 128, 32
+    pos, vel, dx = scenes.dam_break_points(N, seed=4, random_velocity=True, side=side)
+    vel = vel * 0.2
+    solid = scenes.box_solid_sdf(N, dx)
+    one = abi.World(dx)
+    one.set_grid("SolidSDF", solid)
+    one.PrimToVDBPointDataGrid(pos, vel)
+    dd = make_dd(abi, N, bounds, pos, vel, dx, solid)
+    moving = scenes.sphere_sdf(centre=(17.0, 10.0, 12.0), radius=6.0, lo=(0, -8, -8), hi=(40, 32, 32), bg=3.0)
+    moving["values"] = (moving["values"] * np.float32(dx)).astype(np.float32)
+    moving["bg"] = np.array([3.0 * dx], np.float32)
+
+    def prep(w):
+        w.set_grid("KillerSDF", moving)
+        w.FLIPApplyBoundary("KillerSDF", False)
+        w.FLIP_P2G(dx, 3)
+    prep(one)
+    abi.run_ranks(dd, lambda r, w: prep(w))
+    # the static solid of a rank holds what its particles can reach: compare where the single world's leaves overlap the slab
+    ref_s = one.get_grid("SolidSDF")
+    for r, w in enumerate(dd):
+        lo, hi = w.dd_owned()
+        mine = scenes.canonical_grid(w.get_grid("SolidSDF"))
+        ref = scenes.canonical_grid(ref_s)
+        idx = {tuple(o): i for i, o in enumerate(ref["origins"].tolist())}
+        hit = 0
+        for i, o in enumerate(mine["origins"].tolist()):
+            j = idx.get(tuple(o))
+            if j is None:
+                continue
+            hit += 1
+            assert np.array_equal(mine["values"][i], ref["values"][j]), f"rank {r}: static solid leaf {o} differs"
+        assert hit > 0
+    # curvature = a smooth function of the voxel coordinate on the liquid SDF's leaves (any leaf set works)
+    curv = one.get_grid("LiquidSDF")
+    o = curv["origins"].astype(np.float32)
+    curv = {k: v.copy() for k, v in curv.items()}
+    wave = np.sin(0.05 * o[:, 0]).reshape((-1,) + (1,) * (curv["values"].ndim - 1))
+    curv["values"] = (wave * np.ones_like(curv["values"]) * np.float32(3.0)).astype(np.float32)
+    curv["bg"] = np.array([0.0], np.float32)
+
+    def solve(w):
+        w.set_grid("Curvature", curv)
+        w.set_surface_tension(1000.0, 0.07)
+        w.CutCellWeight()
+        w.PushOutLiquidSDF(dx)
+        w.FieldAddVector(G[0] * DT, G[1] * DT, G[2] * DT)
+        res = w.AssembleSolvePPE(DT, dx)
+        w.SubtractPressureGradient(DT, dx, 3)
+        return res
+    r1 = solve(one)
+    rd = abi.run_ranks(dd, lambda r, w: solve(w))
+    assert r1["status"] == 0 and all(r["status"] == 0 for r in rd)
+    util.compare_grids(gather_grid(dd, "Divergence"), one.get_grid("Divergence"), "dd tension right-hand side", tol=0.0, check_inactive=False)
+    util.compare_grids(gather_grid(dd, "Pressure"), one.get_grid("Pressure"), "dd tension Pressure", tol=1e-5, check_inactive=False)
+    util.compare_grids(gather_grid(dd, "Velocity"), one.get_grid("Velocity"), "dd tension projected Velocity", tol=1e-5, check_inactive=False)
+    for w in dd + [one]:
+        w.close()

@@ -575,7 +575,7 @@ int flipb200_apply_boundary(flipb200_world* w, int movingGrid, int movingVertexC
 int flipb200_set_surface_tension(flipb200_world* w, float density, float tensionCoef) {
     return guarded([&] {
         FB_REQUIRE(w && density > 0.f, FLIPB200_ERR_ARG, "set_surface_tension: bad argument");
-        FB_REQUIRE(!(tensionCoef > 0.f) || !dd_on(w), FLIPB200_ERR_STATE, "surface tension is not available under slab decomposition yet (the curvature grid has no ghost refresh)");
+        // (slab decomposition: the curvature grid is read by voxel coordinate; the caller gives every rank the grid over its owned + ghost layers)
         w->density = density; w->tensionCoef = tensionCoef;
     });
 }

@@ -16,6 +16,7 @@
 // Both grids share the particles' cell-centred transform (FF/nosys/FLIP_Creator.cpp:37-116): index -> world = ijk * s, world ->
 // index = xyz * (1 / s) in double (math/Maps.h ScaleMap), restated literally because it does not round-trip for every ijk.
 #include "world.cuh"
+#include <climits>
 #include <cuda_fp16.h>
 
 namespace fb {
@@ -54,6 +55,7 @@ struct ReseedParams {
     TopoView vt; const float* vel[3]; float velBg[3];
     float dx; double s, inv;
     uint32_t seed;
+    int xLo, xHi;                // slab decomposition: only leaves with xLo <= leaf x < xHi (owned + one ghost layer) are topped up
     uint32_t* tstart;            // [n*512] draw index of the voxel's first trial
     uint16_t* accept;            // [n*512] taken trials
     uint32_t* newCount;          // [n*512 + 1]
@@ -77,7 +79,7 @@ __global__ void __launch_bounds__(RS_WARPS * 32) reseed_decide_kernel(ReseedPara
         const int off = it * 32 + lane;
         const uint32_t cnt = vs[off + 1] - vs[off];
         bool e = false;
-        if (cnt <= 4u) {
+        if (cnt <= 4u && (o.x >> 3) >= p.xLo && (o.x >> 3) < p.xHi) {
             const double wx = __dmul_rn((double)(o.x + (off >> 6)), p.s), wy = __dmul_rn((double)(o.y + ((off >> 3) & 7)), p.s), wz = __dmul_rn((double)(o.z + (off & 7)), p.s);
             e = rs_box(p.st, p.sdf, p.sdfBg, __dmul_rn(wx, p.inv), __dmul_rn(wy, p.inv), __dmul_rn(wz, p.inv)) < p.dx;
         }
@@ -201,6 +203,11 @@ __global__ void __launch_bounds__(256) emit_touch_kernel(TopoView t, TopoView st
     if (threadIdx.x == 0) flag[blockIdx.x] = any ? 1 : 0;
 }
 // selection for the new pool: leaves of the store that hold particles, candidate leaves the shape touches
+// slab decomposition: leaves outside [xLo, xHi) (owned + one ghost layer) are not this rank's to fill
+__global__ void emit_slab_kernel(const int3* __restrict__ origin, int n, int xLo, int xHi, uint8_t* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && ((origin[i].x >> 3) < xLo || (origin[i].x >> 3) >= xHi)) flag[i] = 0;
+}
 __global__ void emit_select_kernel(int nP, const uint32_t* __restrict__ voxelStart, int nC, const uint8_t* __restrict__ candFlag, uint32_t* __restrict__ sel) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nP) sel[i] = voxelStart[(size_t)(i + 1) * LEAF] > voxelStart[(size_t)i * LEAF] ? 1u : 0u;
@@ -319,8 +326,11 @@ __global__ void __launch_bounds__(256) emit_write_kernel(EmitParams p) {
 
 void emit_liquid(World* w, int shapeGrid, float vx, float vy, float vz, uint32_t seed) {
     FB_REQUIRE(is_float_grid(shapeGrid) && w->F(shapeGrid).topo != nullptr, FLIPB200_ERR_STATE, "ParticleEmitter: the shape SDF grid was not uploaded");
-    FB_REQUIRE(!dd_on(w), FLIPB200_ERR_STATE, "ParticleEmitter is not available under slab decomposition yet");
     GridF& g = w->F(shapeGrid);
+    // Slab decomposition: every rank is given the same shape; it emits into the leaves of its owned + ghost layers only. The
+    // draws of a leaf depend on (seed, leaf origin), its own particles and the shape, so owner and ghost holder agree.
+    int xLo = INT_MIN, xHi = INT_MAX;
+    if (dd_on(w)) { int lo, hi; dd_owned_coords(w, &lo, &hi); xLo = lo - 1; xHi = hi + 1; }
     if (g.topo->n == 0) return;   // evalLeafBoundingBox fails on an empty shape: the reference returns (:2233-2236)
     const double s = (double)w->dx, inv = 1.0 / s;
     // 1. candidate leaf boxes = the shape's leaves and their 26 neighbours; which of them the shape touches
@@ -328,6 +338,7 @@ void emit_liquid(World* w, int shapeGrid, float vx, float vy, float vz, uint32_t
     DBuf<uint8_t> candFlag(cand->n + 1, w->stream);
     FB_LAUNCH(w, "emit_touch", (size_t)cand->n * 729 * 32) emit_touch_kernel<<<cand->n, 256, 0, w->stream>>>(cand->view(), g.topo->view(), g.val.p, g.bg, s, inv, candFlag.p);
     check_launch("emit_touch");
+    if (xLo != INT_MIN || xHi != INT_MAX) { emit_slab_kernel<<<nblk(cand->n, 256), 256, 0, w->stream>>>(cand->origin.p, cand->n, xLo, xHi, candFlag.p); check_launch("emit_slab"); }
     // 2. the new pool: leaves that hold particles + touched candidates (+ ring)
     const bool have = w->pts.topo != nullptr && w->pts.topo->n > 0;
     const int nP = have ? w->pts.topo->n : 0, nC = cand->n;
@@ -360,6 +371,7 @@ void emit_liquid(World* w, int shapeGrid, float vx, float vy, float vz, uint32_t
     DBuf<uint8_t> touched(nl + 1, w->stream);
     FB_LAUNCH(w, "emit_touch", (size_t)nl * 729 * 32) emit_touch_kernel<<<nl, 256, 0, w->stream>>>(pool->view(), g.topo->view(), g.val.p, g.bg, s, inv, touched.p);
     check_launch("emit_touch");
+    if (xLo != INT_MIN || xHi != INT_MAX) { emit_slab_kernel<<<nblk(nl, 256), 256, 0, w->stream>>>(pool->origin.p, nl, xLo, xHi, touched.p); check_launch("emit_slab"); }
     DBuf<uint32_t> tstart(nv, w->stream), newCount(nv + 1, w->stream), newStart(nv + 1, w->stream);
     DBuf<uint16_t> accept(nv, w->stream);
     FB_CUDA(cudaMemsetAsync(newCount.p + nv, 0, 4, w->stream));
@@ -452,7 +464,8 @@ __global__ void __launch_bounds__(512) boundary_min_kernel(TopoView nt, TopoView
 void apply_boundary(World* w, int movingGrid, bool movingVertexCentred) {
     FB_REQUIRE(is_float_grid(movingGrid) && movingGrid != FLIPB200_SOLID_SDF && w->F(movingGrid).topo != nullptr, FLIPB200_ERR_STATE,
                "FLIPApplyBoundary: the moving solid SDF grid was not uploaded");
-    FB_REQUIRE(!dd_on(w), FLIPB200_ERR_STATE, "FLIPApplyBoundary is not available under slab decomposition yet");
+    // (slab decomposition: every rank is given the same moving solid; its static SDF gains the leaves its own owned + ghost
+    // particle leaves call for -- everything a rank's particles can sample. Nothing is exchanged.)
     GridF& mv = w->F(movingGrid);
     GridF& sd = w->F(FLIPB200_SOLID_SDF);
     const bool haveS = sd.topo != nullptr && sd.topo->n > 0, haveP = w->pts.topo != nullptr && w->pts.topo->n > 0;
@@ -493,7 +506,6 @@ void fluid_reseed(World* w, uint32_t seed) {
     GridF& sdf = w->F(FLIPB200_LIQUID_SDF);
     GridV& vel = w->V(FLIPB200_VELOCITY);
     FB_REQUIRE(sdf.topo != nullptr && vel.topo != nullptr, FLIPB200_ERR_STATE, "FluidReseed: LiquidSDF / Velocity are not set (run FLIP_P2G or upload them)");
-    FB_REQUIRE(!dd_on(w), FLIPB200_ERR_STATE, "FluidReseed is not available under slab decomposition yet");
     const TopoPtr topo = w->pts.topo;
     const int n = topo->n;
     if (n == 0) return;
@@ -509,6 +521,12 @@ void fluid_reseed(World* w, uint32_t seed) {
     for (int c = 0; c < 3; c++) { p.vel[c] = vel.val[c].p; p.velBg[c] = vel.bg[c]; }
     p.dx = w->dx; p.s = (double)w->dx; p.inv = 1.0 / (double)w->dx;
     p.seed = seed;
+    // Slab decomposition: a leaf's draws start at a hash of (seed, leaf origin) and read the leaf's own particles plus the
+    // liquid SDF / velocity within two voxels of it, so the owner of a leaf and the neighbour that holds it as a ghost make the
+    // same decisions without an exchange -- as long as the grids' ghost layers are current (FLIP_P2G refreshes two). Leaves
+    // beyond the ghost layer (the pool's ring) hold none of their particles here and are left alone.
+    p.xLo = INT_MIN; p.xHi = INT_MAX;
+    if (dd_on(w)) { int lo, hi; dd_owned_coords(w, &lo, &hi); p.xLo = lo - 1; p.xHi = hi + 1; }
     p.tstart = tstart.p; p.accept = accept.p; p.newCount = newCount.p; p.newStart = nullptr;
     p.o0 = p.o1 = p.o2 = nullptr;
     FB_LAUNCH(w, "reseed_decide", nv * 16) reseed_decide_kernel<<<(n + RS_WARPS - 1) / RS_WARPS, RS_WARPS * 32, 0, w->stream>>>(p);
