@@ -322,6 +322,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"], help="c2 = the substep (default line); c3 / c4 = BASELINE config[2] / config[3]")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the decomposed-vs-single-world result check before the timed region")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--emitter", action="store_true",
+                    help="BASELINE config[4] 'with emitter': a ParticleEmitter sphere above the block (across the middle slab face) tops up every step")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
 
@@ -417,7 +419,20 @@ def main():
     w.FLIP_P2G(dx, 3)
     stream = torch.cuda.ExternalStream(w.stream(), device=torch.device("cuda", local_rank))
 
+    emit_calls = [0]
+    if args.emitter:
+        # a sphere of radius 12 voxels whose centre sits on the block's top face, above the middle of the block in x (a slab face
+        # for every even rank count): it tops up the block's leaves it overlaps and creates new leaves above them
+        c = (block[0] / 2.0 + 0.3, block[1] + 2.0, block[2] / 2.0)
+        shape = scenes.sphere_sdf(centre=c, radius=12.0, lo=tuple(int(v) - 24 for v in c), hi=tuple(int(v) + 24 for v in c), bg=3.0)
+        shape["values"] = (shape["values"] * np.float32(dx)).astype(np.float32)
+        shape["bg"] = np.array([3.0 * dx], np.float32)
+        w.set_grid("KillerSDF", shape)
+
     def step():
+        if args.emitter:
+            w.ParticleEmitter("KillerSDF", 0.0, -1.0, 0.0, seed=1000 + emit_calls[0])
+            emit_calls[0] += 1
         dt = substep_dt(w, dx)
         w.substep(dt, dx, 4, 3, 0.03, 0.05, GRAVITY, 3, True)
 
@@ -654,7 +669,8 @@ def main():
                 "config": {"workload": workload_string(N, block, n_particles0 if world == 1 else n_particles, args.ppc),
                            "parallelism": parallelism, "dd_result_check": dd_report,
                            "l2": "inputs larger than L2 (>=200 MB particle state per step), no flush",
-                           "pcg_iterations": iters, "step_ms_host": step_ms},
+                           "pcg_iterations": iters, "step_ms_host": step_ms,
+                           **({"emitter": "ParticleEmitter sphere (radius 12 voxels) on the block's top face, one call per substep"} if args.emitter else {})},
                 "clocks": clocks, "e2e": e2e, "e2e_nodes": e2e_nodes, "gpu_launches": int(launches),
                 "host_syncs_per_step": host_syncs / max(args.steps, 1), "kernel_ms_sum_per_step": sum(x["ms_per_step"] for x in kern.values()),
                 "roofline": roofline, "cpu_baseline": cpu,

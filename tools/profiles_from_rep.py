@@ -50,7 +50,7 @@ for name, i in rep_id.items():
         w = csv.writer(f); w.writerow(dh)
         for r in det[1:]:
             if r[idc] == i: w.writerow(r)
-keymap = {"mg_cycle_kernel": "mg_cycle_upper", "mg_cluster_kernel": "mg_cluster", "g2p_tile_kernel": "g2p_advect", "p2g_gather_kernel": "p2g_gather"}
+keymap = {"mg_cycle_kernel": "mg_cycle_upper", "mg_cluster_kernel": "mg_cluster", "g2p_tile_kernel": "g2p_advect", "p2g_gather_kernel": "p2g_gather", "p2g_xrow_kernel": "p2g_gather"}
 tj = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch (mean over the launches of one substep) from the `ncu --set full` capture named in each entry, bench workload (512^3 tank, 16.8 M particles); bench.py copies the matching entry into roofline.traffic"}
 for name, bs in traffic.items():
     tj[keymap.get(name, name)] = {"bytes": int(sum(bs) / len(bs)), "launches": len(bs), "capture": f"profiles/{tag}_ncu_full_{name}.details.csv"}

@@ -5,7 +5,7 @@
 TAG=${1:-r02}
 SO=zeno_b200/libflipb200.so
 cuobjdump -sass $SO > /tmp/flipb200.sass 2>/dev/null
-for K in mg_cluster_kernel mg_cycle_kernel g2p_tile_kernelILb1 p2g_gather_kernel; do
+for K in mg_cluster_kernel mg_cycle_kernel g2p_tile_kernelILb1 p2g_gather_kernel p2g_xrow_kernel; do
   OUT=profiles/${TAG}_sass_$(echo $K | sed 's/ILb1//').txt
   awk -v k="$K" '/Function :/ {on = index($0, k) > 0} on {print}' /tmp/flipb200.sass > /tmp/k.sass
   {

@@ -27,7 +27,9 @@ struct P2GParams {
     float* sdf;           // out: liquid sdf values
     uint64_t* topoMask;   // out: dilated-occupancy mask [n][8]
     float dx, radius, sdfBg;
-    int* overflow;
+    int* overflow;      // [0] a cell beyond the gather kernel's staging depth; [2..3] / [4..5] 64-bit sums of (records per plane)^2 and
+                        // of records per plane over all leaves: their ratio sizes the next call's staging buffer
+    int cap;            // p2g_xrow_kernel: staged records per batch (dynamic shared memory = cap * 25 bytes)
 };
 
 __global__ void __launch_bounds__(P2G_THREADS) p2g_gather_kernel(P2GParams p, const uint8_t* __restrict__ todo) {
@@ -217,13 +219,17 @@ constexpr int XR_THREADS = 64;
 #ifndef FB_XR_CAP
 #define FB_XR_CAP 1024   // 8 CTAs per SM; measured 1178 us against 1304 us at 1344 (6 CTAs) and 1458 us at 1600 (5 CTAs)
 #endif
+#ifndef FB_XR_CAP_MAX
+#define FB_XR_CAP_MAX 2304   // 4 CTAs per SM; beyond that a plane is split into row batches instead
+#endif
 #ifndef FB_XR_UNROLL
 #define FB_XR_UNROLL 8
 #endif
 #ifndef FB_XR_JUNROLL
 #define FB_XR_JUNROLL 2
 #endif
-constexpr int XR_CAP = FB_XR_CAP;   // staged records per batch, pad records included
+constexpr int XR_CAP = FB_XR_CAP;   // staged records per batch, pad records included: the default, at 8 particles per voxel
+constexpr int XR_CAP_MAX = FB_XR_CAP_MAX;
 constexpr int XR_JUNROLL = FB_XR_JUNROLL;
 constexpr int XR_MIN_CTAS = 8;
 constexpr int XR_STAGE_UNROLL = FB_XR_UNROLL;
@@ -314,8 +320,11 @@ __device__ __forceinline__ void xr_cell_range(const P2GParams& p, const int* __r
 }
 
 __global__ void __launch_bounds__(XR_THREADS, XR_MIN_CTAS) p2g_xrow_kernel(P2GParams p, uint8_t* __restrict__ todo) {
-    __shared__ __align__(16) float sP[XR_CAP * 6];
-    __shared__ uint8_t cellOf[XR_CAP];
+    extern __shared__ __align__(16) float xrSmem[];
+    float* sP = xrSmem;                                              // [cap][6]
+    uint8_t* cellOf = reinterpret_cast<uint8_t*>(xrSmem + (size_t)p.cap * 6);   // [cap]
+    const int XR_CAP = p.cap;
+    unsigned long long planeSq = 0, planeSum = 0;
     __shared__ uint32_t cBeg[PLANE_CELLS];
     __shared__ int cCnt[PLANE_CELLS];
     __shared__ int cPre[PLANE_CELLS + 1];   // first record of the cell, counted over the whole plane (pads included)
@@ -358,6 +367,7 @@ __global__ void __launch_bounds__(XR_THREADS, XR_MIN_CTAS) p2g_xrow_kernel(P2GPa
             if (tid == 0) cPre[PLANE_CELLS] = run;
             __syncwarp();
             if (tid == 0) {
+                if (run > PLANE_CELLS) { planeSq += (unsigned long long)run * (unsigned)run; planeSum += (unsigned)run; }
                 int nb = 0, r = 0;
                 sRow[0] = 0;
                 if (run > PLANE_CELLS) {   // a plane without particles has no batches
@@ -443,6 +453,10 @@ __global__ void __launch_bounds__(XR_THREADS, XR_MIN_CTAS) p2g_xrow_kernel(P2GPa
             }
         }
         P = Z; Z = M; xacc_reset(M);
+    }
+    if (tid == 0 && planeSum) {   // the work-weighted mean plane (sum of squares / sum) sizes the next call's staging buffer
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.overflow + 2), planeSq);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.overflow + 4), planeSum);
     }
 }
 
@@ -614,13 +628,14 @@ void p2g(World* w, float dx, int velExtraLayer) {
 
     DBuf<uint64_t> chMask((size_t)3 * n * 8, w->stream), topoMask((size_t)n * 8, w->stream), ring((size_t)n * 8, w->stream);
     if (!w->p2gOverflowHost) {
-        w->p2gOverflowHost = reinterpret_cast<int*>(w->hostScratch + 768);   // a word of the mapped scratch block
-        *w->p2gOverflowHost = 0;
-        w->p2gOverflow.alloc(1, w->stream);
+        w->p2gOverflowHost = reinterpret_cast<int*>(w->hostScratch + 768);   // two words of the mapped scratch block
+        for (int k = 0; k < 6; k++) w->p2gOverflowHost[k] = 0;
+        w->p2gOverflow.alloc(6, w->stream);
     }
     DBuf<int>& overflow = w->p2gOverflow;
     overflow.zero();
     P2GParams p;
+    p.cap = 0;
     p.t = pool->view();
     p.voxelStart = w->pts.voxelStart.p;
     p.w0 = w->pts.w0.p; p.w1 = w->pts.w1.p; p.w2 = w->pts.w2.p;
@@ -647,8 +662,24 @@ void p2g(World* w, float dx, int velExtraLayer) {
     } else {
         DBuf<uint8_t> todo((size_t)n, w->stream);
         todo.zero();
+        // staging depth: the work-weighted mean plane (sum of squares / sum of the per-plane record counts) of the PREVIOUS call (read back without a wait, so it is one call old) plus head
+        // room; 1024 records = 8 CTAs per SM at 8 particles per voxel, up to 2304 (4 CTAs) for denser stores; a plane beyond the
+        // depth is processed in row batches
+        int cap = XR_CAP;
+        unsigned long long sq = 0, sum = 0;
+        memcpy(&sq, w->p2gOverflowHost + 2, 8); memcpy(&sum, w->p2gOverflowHost + 4, 8);
+        const int seen = sum ? (int)(sq / sum) : 0;
+        if (seen + 64 > cap) cap = std::min(XR_CAP_MAX, (seen + 64 + 127) & ~127);
+        if (const char* e = getenv("FLIPB200_P2G_CAP")) cap = std::max(512, std::min(XR_CAP_MAX, atoi(e) & ~63));
+        p.cap = cap;
+        const size_t xrSmem = (size_t)cap * 25;
+        static size_t attrSmem = 0;
+        if (xrSmem > attrSmem) {
+            FB_CUDA(cudaFuncSetAttribute(p2g_xrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)XR_CAP_MAX * 25)));
+            attrSmem = (size_t)XR_CAP_MAX * 25;
+        }
         FB_LAUNCH(w, "p2g_gather", w->pts.n * 12 + (size_t)n * LEAF * 20)
-            p2g_xrow_kernel<<<n, XR_THREADS, 0, w->stream>>>(p, todo.p);
+            p2g_xrow_kernel<<<n, XR_THREADS, xrSmem, w->stream>>>(p, todo.p);
         check_launch("p2g_xrow");
         // leaves with a cell row beyond the staging buffer (only an un-capped initial binning can produce one)
         FB_LAUNCH(w, "p2g_gather_fallback", 0)
@@ -670,7 +701,7 @@ void p2g(World* w, float dx, int velExtraLayer) {
     union_extrapolate(w, velExtraLayer, nvel, chMask.p, nsdf.mask.p);
     finish_vec3(w, nvel, chMask.p);
 
-    d2h_words(w, w->p2gOverflowHost, overflow.p, 4);   // checked by check_p2g_overflow
+    d2h_words(w, w->p2gOverflowHost, overflow.p, 24);   // [0] checked by check_p2g_overflow, [2..5] size the next call's staging
     vel = std::move(nvel);
     post = std::move(npost);
     sdf = std::move(nsdf);
