@@ -534,7 +534,7 @@ def main():
             name = "mgpcg preconditioner application = " + " + ".join(f"{n:g} x {k}" for k, n in fam["members"].items())
             per_launch = fam["bytes_per_application"]
             share_ms = fam["ms_per_step"]
-            src = "sum over the member launches of one application of dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/ncu_traffic.json, from the ncu --set full capture profiles/r02_hot_kernels.md); below the algorithmic bytes because the level-0 vectors (8 MB each) stay in the 126 MB L2"
+            src = "sum over the member launches of one application of dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/ncu_traffic.json, from the ncu --set full capture profiles/r03_hot_kernels.md); below the algorithmic bytes because the level-0 vectors (8 MB each) stay in the 126 MB L2"
         else:
             d = kern[dominant]
             t = tj.get(dominant)
