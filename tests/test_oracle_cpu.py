@@ -244,3 +244,24 @@ def test_projection_removes_divergence(oracle_lib):
     # refills keep a residual (reference behaviour); everywhere else the field is divergence free
     assert np.linalg.norm(b) < 1e-2 * np.linalg.norm(a)
     assert (np.abs(b) > 1e-2).sum() <= 3 < (np.abs(a) > 1e-2).sum()
+
+
+def test_fx_decode_fast_is_exact():
+    """The division-free position decode of the CUDA kernels (zeno_b200/csrc/common.cuh:fx_decode_fast: q = u * fl(1/65535),
+    rem = fma(-q, 65535, u), q' = fma(rem, fl(1/65535), q)) returns the correctly rounded u / 65535 of FixedPointCodec's decode
+    (openvdb/points/AttributeArray.h) for every one of the 65536 codes. Exact rational arithmetic, one rounding per operation."""
+    from fractions import Fraction
+
+    def rn32(fr):
+        f = np.float32(float(fr))
+        cands = [f, np.nextafter(f, np.float32(np.inf)), np.nextafter(f, np.float32(-np.inf))]
+        return min(cands, key=lambda c: (abs(Fraction(float(c)) - fr), int(np.float32(c).view(np.uint32)) & 1))
+
+    r = Fraction(float(rn32(Fraction(1, 65535))))
+    assert float(r).hex() == "0x1.0001000000000p-16"
+    for u in range(65536):
+        want = rn32(Fraction(u, 65535))
+        q = Fraction(float(rn32(u * r)))
+        rem = Fraction(float(rn32(u - q * 65535)))
+        got = rn32(q + rem * r)
+        assert got == want, (u, float(got), float(want))

@@ -87,8 +87,8 @@ __device__ __forceinline__ bool grid_on(const TopoView& t, const uint64_t* mask,
 // FixedPointCodec<false, PositionRange> (openvdb/points/AttributeArray.h:47-65,953-976)
 __device__ __forceinline__ float fx_decode(uint32_t u) { return __fsub_rn(__fdiv_rn((float)u, 65535.0f), 0.5f); }
 // The same value without the IEEE-division sequence: q = u * fl(1/65535), one exact remainder and one correction FMA.
-// Equal to fx_decode for every one of the 65536 codes (checked exhaustively in exact arithmetic and on the device,
-// tests/test_parity_gpu.py::test_fx_decode_fast_is_exact).
+// Equal to fx_decode for every one of the 65536 codes (checked exhaustively in exact arithmetic,
+// tests/test_oracle_cpu.py::test_fx_decode_fast_is_exact; on the device by every bit-exact P2G parity test).
 __device__ __forceinline__ float fx_decode_fast(uint32_t u) {
     const float r = 0x1.0001p-16f;   // fl(1/65535)
     const float uf = (float)u;
