@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(P2G_THREADS) p2g_gather_kernel(P2GParams p, co
 // finished after the plane at its ox = +1 and written straight to global memory -- no accumulator array in shared
 // memory). Each target still sees its 27 source cells in (ox, oy, oz) order and a cell's particles in store order, and
 // every product / sum is the same single-rounded operation as before, so the result is bit-identical to
-// p2g_gather_kernel (tests/test_parity_gpu.py::test_p2g_paths_identical) and to the oracle.
+// p2g_gather_kernel (tests/test_p2g_paths_gpu.py) and to the oracle.
 // Staging: a plane's records are decoded once per CTA into 24-byte records [px py pz vx vy vz], cell after cell in
 // (y, z) order with ONE PAD RECORD per cell: with exactly 8 particles in every voxel (the state a scene starts in)
 // un-padded cell starts are 48 words apart and the 32 lanes of a warp would hit two bank pairs.
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(XR_THREADS, XR_MIN_CTAS) p2g_xrow_kernel(P2GPa
     extern __shared__ __align__(16) float xrSmem[];
     float* sP = xrSmem;                                              // [cap][6]
     uint8_t* cellOf = reinterpret_cast<uint8_t*>(xrSmem + (size_t)p.cap * 6);   // [cap]
-    const int XR_CAP = p.cap;
+    const int cap = p.cap;
     unsigned long long planeSq = 0, planeSum = 0;
     __shared__ uint32_t cBeg[PLANE_CELLS];
     __shared__ int cCnt[PLANE_CELLS];
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(XR_THREADS, XR_MIN_CTAS) p2g_xrow_kernel(P2GPa
                 if (run > PLANE_CELLS) {   // a plane without particles has no batches
                     while (r < 10) {
                         int start = cPre[r * 10], e = r;
-                        while (e < 10 && cPre[(e + 1) * 10] - start <= XR_CAP) e++;
+                        while (e < 10 && cPre[(e + 1) * 10] - start <= cap) e++;
                         if (e == r) { nb = -1; break; }
                         r = e; sRow[++nb] = r;
                     }
