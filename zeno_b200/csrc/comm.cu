@@ -110,6 +110,7 @@ void comm_destroy(World* w) {
     w->rank = 0; w->nRanks = 1;
 }
 bool comm_active(World* w) { return w->comm && w->nRanks > 1; }
+bool comm_is_local(World* w) { return w->comm && w->comm->grp != nullptr; }
 
 void comm_group_begin(World* w) {
     FB_REQUIRE(comm_active(w), FLIPB200_ERR_COMM, "communicator not initialised");
@@ -232,6 +233,17 @@ int flipb200_comm_init_local(flipb200_world** worlds, int n) {
         G->done.assign((size_t)n * n, 0);
         G->arPtr.assign(8, nullptr);
         G->refs = n;
+        {
+            // The worlds of one process share the device's default stream-ordered pool. By default the pool may hand a block that
+            // one world's stream has freed-but-not-yet-reached to another world's stream and insert a dependency on the freeing
+            // stream. Worlds that exchange ghost leaves through peer memory WAIT for each other on the device (dd_wait_kernel), so
+            // such a dependency can close a cycle (A waits for B's push, B's push waits for A's free point behind A's wait).
+            // Reuse across streams stays allowed once the free has completed (opportunistic reuse).
+            cudaMemPool_t pool;
+            int dev = worlds[0]->device, zero = 0;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &zero);
+            cudaGetLastError();
+        }
         for (int r = 0; r < n; r++) {
             flipb200_world* w = worlds[r];
             cudaSetDevice(w->device);

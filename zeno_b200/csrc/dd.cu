@@ -29,7 +29,32 @@ struct DDMaps {
     int recvCnt[2][2] = {{0, 0}, {0, 0}};   // [0 = from left, 1 = from right][1 layer, 2 layers]
     DBuf<int> map[2];                // received leaf (sender's 2-layer list order) -> my slot or -1
 };
+// Peer-memory ghost exchange (dd_refresh): every rank owns one device allocation [4 boxes | flags] -- a receive box per
+// (side, parity) and a 32-bit epoch flag per box -- that its two neighbours map (cudaIpc between processes, the plain pointer
+// inside one process). An exchange is then two launches per side instead of an NCCL send/recv group + unpack: a push kernel
+// copies my boundary leaves STRAIGHT INTO the neighbour's box over NVLink and, from its last CTA, stores the exchange's epoch
+// into the neighbour's flag (system-scope fence before it); a one-thread kernel waits for MY flag to reach the epoch, then the
+// usual unpack kernel scatters the box into my ghost leaves. Boxes alternate by epoch parity: the neighbour's push k+2 into a box
+// is ordered after its wait for my push k+1, which my stream issued after my unpack k of that box.
+struct DDPeer {
+    bool tried = false, ready = false;
+    size_t boxBytes = 0;
+    char* mine = nullptr;              // [2 sides][2 parities] boxes, then the flags
+    char* remote[2] = {nullptr, nullptr};   // the neighbour's allocation (left, right)
+    bool opened[2] = {false, false};   // remote[s] came from cudaIpcOpenMemHandle
+    unsigned epoch[2] = {0, 0};        // exchanges done with each side
+    DBuf<unsigned> counter;            // last-CTA counters of the push kernels, one per side
+    int* errHost = nullptr;            // a word of the world's mapped scratch block: a wait ran into its time limit
+    char* box(char* base, int side, int parity) const { return base + (size_t)(side * 2 + parity) * boxBytes; }
+    unsigned* flag(char* base, int side, int parity) const { return reinterpret_cast<unsigned*>(base + 4 * boxBytes) + (side * 2 + parity) * 32; }
+    size_t total() const { return 4 * boxBytes + 4 * 32 * sizeof(unsigned); }
+    ~DDPeer() {
+        for (int s = 0; s < 2; s++) if (opened[s] && remote[s]) cudaIpcCloseMemHandle(remote[s]);
+        if (mine) cudaFree(mine);
+    }
+};
 struct DDState {
+    DDPeer peer;
     bool on = false;
     int lo = -DD_OPEN, hi = DD_OPEN;
     bool boundsChecked = false;          // the neighbours' slabs were compared with mine (gap-free, no overlap)
@@ -74,6 +99,45 @@ __global__ void unpack_kernel(UnpackArgs a, const int* __restrict__ map) {
         for (int i = threadIdx.x; i < bpl; i += blockDim.x) dst[i] = src[i];
     }
 }
+// ---- peer-memory exchange
+struct PushArgs { int nArr; const char* src[DD_MAX_ARRAYS]; size_t bytes[DD_MAX_ARRAYS]; size_t off[DD_MAX_ARRAYS]; };
+__global__ void __launch_bounds__(256) dd_push_kernel(PushArgs a, char* __restrict__ box, unsigned* __restrict__ remoteFlag, unsigned epoch,
+                                                      unsigned* __restrict__ counter) {
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    for (int k = 0; k < a.nArr; k++) {
+        char* dst = box + a.off[k];   // box offsets are 256-byte aligned
+        if ((reinterpret_cast<uintptr_t>(a.src[k]) & 15) == 0) {
+            const size_t n16 = a.bytes[k] >> 4;
+            const uint4* sp = reinterpret_cast<const uint4*>(a.src[k]);
+            uint4* dp = reinterpret_cast<uint4*>(dst);
+            for (size_t i = gtid; i < n16; i += gsz) dp[i] = sp[i];
+            for (size_t i = (n16 << 4) + gtid; i < a.bytes[k]; i += gsz) dst[i] = a.src[k][i];
+        } else {   // the one-byte-per-leaf arrays start anywhere
+            for (size_t i = gtid; i < a.bytes[k]; i += gsz) dst[i] = a.src[k][i];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(counter, 1u) == gridDim.x - 1) {   // every CTA's stores are fenced: publish
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned*>(remoteFlag) = epoch;
+            __threadfence_system();
+            *counter = 0;
+        }
+    }
+}
+__global__ void dd_wait_kernel(const unsigned* __restrict__ flag, unsigned epoch, int* __restrict__ err) {
+    const volatile unsigned* f = reinterpret_cast<const volatile unsigned*>(flag);
+    long long t0 = clock64();
+    // epochs only grow; a (wrapping) difference >= 0 means the neighbour's push of this exchange has landed
+    while ((int)(*f - epoch) < 0) {
+        if (clock64() - t0 > 8000000000ll) { *err = 1; break; }   // ~4 s: a peer that never pushes must not hang the device
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
 // migration: a particle goes to the left neighbour (1), to the right one (2) and / or stays in this rank's extended region (4).
 // One stable three-way partition in two passes over the particles (count per block of 1024, scatter) with a one-CTA scan of the
 // block counts between them; round 1 wrote three flag arrays, scanned each over all particles (three host-read totals) and
@@ -305,6 +369,74 @@ void dd_owned_coords(World* w, int* lo, int* hi) {
     *hi = w->rank < w->nRanks - 1 ? w->dd->hi : DD_OPEN;
 }
 
+namespace {
+// collective, once per world: allocate my boxes, swap the allocation's handle (IPC) or address (in-process) with both neighbours
+void peer_setup(World* w) {
+    DDPeer& P = w->dd->peer;
+    if (P.tried) return;
+    P.tried = true;
+    const char* e = getenv("FLIPB200_DD_P2P");
+    int want = e ? atoi(e) : 1;
+    const bool has[2] = {w->rank > 0, w->rank < w->nRanks - 1};
+    const bool local = comm_is_local(w);
+    size_t mb = 32;
+    if (const char* b = getenv("FLIPB200_DD_P2P_MB")) mb = (size_t)std::max(1, atoi(b));
+    struct Blob { unsigned char h[64]; unsigned long long ptr; int ok; int pad; };   // 80 bytes
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
+    Blob mine;
+    memset(&mine, 0, sizeof(mine));
+    if (want) {
+        P.boxBytes = mb << 20;
+        if (cudaMalloc((void**)&P.mine, P.total()) != cudaSuccess) { cudaGetLastError(); P.mine = nullptr; }
+        if (P.mine) {
+            FB_CUDA(cudaMemsetAsync(P.mine + 4 * P.boxBytes, 0, P.total() - 4 * P.boxBytes, w->stream));
+            mine.ptr = (unsigned long long)(uintptr_t)P.mine;
+            mine.ok = 1;
+            if (!local) {
+                cudaIpcMemHandle_t h;
+                if (cudaIpcGetMemHandle(&h, P.mine) == cudaSuccess) memcpy(mine.h, &h, 64);
+                else { cudaGetLastError(); mine.ok = 0; }
+            }
+        }
+    }
+    // every rank takes part in the swap, whatever it could allocate: the verdict must be the same on both sides of a face
+    DBuf<unsigned char> d(3 * sizeof(Blob), w->stream);
+    FB_CUDA(cudaMemsetAsync(d.p, 0, 3 * sizeof(Blob), w->stream));
+    FB_CUDA(cudaMemcpyAsync(d.p, &mine, sizeof(Blob), cudaMemcpyHostToDevice, w->stream));
+    comm_group_begin(w);
+    if (has[0]) { comm_send(w, w->rank - 1, d.p, sizeof(Blob)); comm_recv(w, w->rank - 1, d.p + sizeof(Blob), sizeof(Blob)); }
+    if (has[1]) { comm_send(w, w->rank + 1, d.p, sizeof(Blob)); comm_recv(w, w->rank + 1, d.p + 2 * sizeof(Blob), sizeof(Blob)); }
+    comm_group_end(w);
+    Blob theirs[2];
+    read_back(w, theirs, d.p + sizeof(Blob), 2 * sizeof(Blob));
+    bool ok = mine.ok != 0;
+    for (int s = 0; s < 2 && ok; s++) {
+        if (!has[s]) continue;
+        if (!theirs[s].ok) { ok = false; break; }
+        if (local) P.remote[s] = reinterpret_cast<char*>((uintptr_t)theirs[s].ptr);
+        else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, theirs[s].h, 64);
+            void* rp = nullptr;
+            if (cudaIpcOpenMemHandle(&rp, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+            P.remote[s] = (char*)rp; P.opened[s] = true;
+        }
+    }
+    // both ends of every face must agree: all-reduce the verdict (a rank whose neighbour failed must not push into nothing)
+    DBuf<int> v(1, w->stream);
+    const int mineOk = ok ? 0 : 1;
+    FB_CUDA(cudaMemcpyAsync(v.p, &mineOk, 4, cudaMemcpyHostToDevice, w->stream));
+    comm_allreduce(w, v.p, 1, CT_I32, false);
+    int bad = 0;
+    read_back(w, &bad, v.p, 4);
+    P.counter.alloc(2, w->stream);
+    P.counter.zero();
+    P.errHost = reinterpret_cast<int*>(w->hostScratch + 800);
+    *P.errHost = 0;
+    P.ready = bad == 0;
+}
+}  // namespace
+
 void dd_refresh(World* w, const std::vector<DDArray>& arrays, int layers) {
     if (!dd_on(w) || arrays.empty()) return;
     FB_REQUIRE((int)arrays.size() <= DD_MAX_ARRAYS && (layers == 1 || layers == 2), FLIPB200_ERR_ARG, "dd_refresh: bad argument");
@@ -318,32 +450,93 @@ void dd_refresh(World* w, const std::vector<DDArray>& arrays, int layers) {
     // what I receive: from the left its last layers (the single layer is the tail of its two-layer list), from the right its first
     const int recvCnt[2] = {M.recvCnt[0][layers - 1], M.recvCnt[1][layers - 1]};
     const int mapOff[2] = {layers == 1 ? M.recvCnt[0][1] - M.recvCnt[0][0] : 0, 0};
+    peer_setup(w);
+    DDPeer& P = w->dd->peer;
     DBuf<char> stage[2];
-    std::vector<size_t> off[2];
+    std::vector<size_t> off[2], soff[2];   // layout of what I receive from side s / of what I send to it (the neighbour's layout)
+    size_t rbytes[2] = {0, 0}, sbytes[2] = {0, 0};
     uint64_t bytes = 0;
+    bool viaPeer[2] = {false, false};
     for (int s = 0; s < 2; s++) {
-        size_t cur = 0;
-        for (auto& a : arrays) { off[s].push_back(cur); cur += (((size_t)recvCnt[s] * a.bytesPerLeaf) + 255) & ~(size_t)255; }
-        stage[s].alloc(cur + 256, w->stream);
+        size_t cur = 0, scur = 0;
+        for (auto& a : arrays) {
+            off[s].push_back(cur); cur += (((size_t)recvCnt[s] * a.bytesPerLeaf) + 255) & ~(size_t)255;
+            soff[s].push_back(scur); scur += (((size_t)sendCnt[s] * a.bytesPerLeaf) + 255) & ~(size_t)255;
+        }
+        rbytes[s] = cur; sbytes[s] = scur;
+        // both ends of a face see the same two sizes (my send is its receive), so they take the same route
+        viaPeer[s] = has[s] && P.ready && std::max(cur, scur) <= P.boxBytes;
+        if (!viaPeer[s]) stage[s].alloc(cur + 256, w->stream);
         if (has[s]) bytes += cur;
     }
-    comm_group_begin(w);
+    // peer route: push my boundary leaves into the neighbour's box, then wait for its push into mine
+    for (int s = 0; s < 2; s++) {
+        if (!viaPeer[s]) continue;
+        const unsigned ep = ++P.epoch[s];
+        const int par = (int)(ep & 1u);
+        PushArgs pa;
+        pa.nArr = (int)arrays.size();
+        size_t most = 0;
+        for (size_t k = 0; k < arrays.size(); k++) {
+            pa.src[k] = (const char*)arrays[k].base + (size_t)sendStart[s] * arrays[k].bytesPerLeaf;
+            pa.bytes[k] = (size_t)sendCnt[s] * arrays[k].bytesPerLeaf;
+            pa.off[k] = soff[s][k];
+            most = std::max(most, pa.bytes[k]);
+        }
+        // the neighbour's box for ITS side facing me: I am its right neighbour when it is my left one
+        char* rbox = P.box(P.remote[s], 1 - s, par);
+        unsigned* rflag = P.flag(P.remote[s], 1 - s, par);
+        const unsigned grid = (unsigned)std::min<size_t>(296, std::max<size_t>(1, (most / 16 + 255) / 256));
+        FB_LAUNCH(w, "dd_push", sbytes[s]) dd_push_kernel<<<grid, 256, 0, w->stream>>>(pa, rbox, rflag, ep, P.counter.p + s);
+        check_launch("dd_push");
+    }
+    bool anyNccl = false;
+    for (int s = 0; s < 2; s++) anyNccl = anyNccl || (has[s] && !viaPeer[s]);
+    if (anyNccl) {
+        comm_group_begin(w);
+        for (int s = 0; s < 2; s++) {
+            if (!has[s] || viaPeer[s]) continue;
+            for (size_t k = 0; k < arrays.size(); k++) {
+                const auto& a = arrays[k];
+                comm_send(w, peer[s], (const char*)a.base + (size_t)sendStart[s] * a.bytesPerLeaf, (size_t)sendCnt[s] * a.bytesPerLeaf);
+                comm_recv(w, peer[s], stage[s].p + off[s][k], (size_t)recvCnt[s] * a.bytesPerLeaf);
+            }
+        }
+        comm_group_end(w);
+    }
+    // In-process worlds share ONE device: a kernel that spins for a neighbour's push can sit in front of that very push in a
+    // hardware work queue two streams happen to share (measured: 3 worlds deadlock until the time limit). There the wait is a
+    // host rendezvous -- a 4-byte message each way, which in that backend synchronises both streams -- and the device-side wait
+    // is exercised where it belongs, between GPUs (tests/test_nccl_gpu.py, bench.py --gpus N).
+    const bool hostWait = comm_is_local(w);
+    if (hostWait && (viaPeer[0] || viaPeer[1])) {
+        DBuf<int> token(4, w->stream);
+        token.zero();
+        comm_group_begin(w);
+        for (int s = 0; s < 2; s++) if (viaPeer[s]) { comm_send(w, peer[s], token.p + s, 4); comm_recv(w, peer[s], token.p + 2 + s, 4); }
+        comm_group_end(w);
+    }
     for (int s = 0; s < 2; s++) {
         if (!has[s]) continue;
-        for (size_t k = 0; k < arrays.size(); k++) {
-            const auto& a = arrays[k];
-            comm_send(w, peer[s], (const char*)a.base + (size_t)sendStart[s] * a.bytesPerLeaf, (size_t)sendCnt[s] * a.bytesPerLeaf);
-            comm_recv(w, peer[s], stage[s].p + off[s][k], (size_t)recvCnt[s] * a.bytesPerLeaf);
+        const char* src = stage[s].p;
+        if (viaPeer[s]) {
+            const int par = (int)(P.epoch[s] & 1u);
+            src = P.box(P.mine, s, par);
+            if (!hostWait) {
+                FB_LAUNCH(w, "dd_wait", 4) dd_wait_kernel<<<1, 1, 0, w->stream>>>(P.flag(P.mine, s, par), P.epoch[s], reinterpret_cast<int*>(w->hostScratchDev + 800));
+                check_launch("dd_wait");
+            }
         }
-    }
-    comm_group_end(w);
-    for (int s = 0; s < 2; s++) {
-        if (!has[s] || recvCnt[s] == 0) continue;
+        if (recvCnt[s] == 0) continue;
         UnpackArgs u;
         u.nArr = (int)arrays.size();
-        for (size_t k = 0; k < arrays.size(); k++) { u.dst[k] = (char*)arrays[k].base; u.src[k] = stage[s].p + off[s][k]; u.bpl[k] = arrays[k].bytesPerLeaf; }
+        for (size_t k = 0; k < arrays.size(); k++) { u.dst[k] = (char*)arrays[k].base; u.src[k] = src + off[s][k]; u.bpl[k] = arrays[k].bytesPerLeaf; }
         FB_LAUNCH(w, "dd_unpack", 2 * bytes) unpack_kernel<<<dim3(recvCnt[s], u.nArr), 128, 0, w->stream>>>(u, M.map[s].p + mapOff[s]);
         check_launch("dd_unpack");
+    }
+    if (P.ready && P.errHost && *P.errHost) {
+        *P.errHost = 0;
+        throw Error(FLIPB200_ERR_COMM, "ghost exchange: a neighbour's push did not arrive within the time limit");
     }
 }
 void dd_refresh(World* w, GridF& g, int layers) {

@@ -155,7 +155,13 @@ inline void reserve_pool(World* w, uint64_t bytes) {
     else cudaGetLastError();
 }
 void set_last_error(const std::string& m);   // abi.cu: what flipb200_last_error() returns on this thread
-inline void sync(World* w) { w->syncs++; FB_CUDA(cudaStreamSynchronize(w->stream)); }
+inline void sync(World* w) {
+    w->syncs++;
+    FB_CUDA(cudaStreamSynchronize(w->stream));
+    // a ghost exchange over peer memory whose neighbour never pushed (dd.cu: dd_wait_kernel's time limit) reports here
+    int* err = reinterpret_cast<int*>(w->hostScratch + 800);
+    if (w->hostScratch && *err) { *err = 0; throw Error(FLIPB200_ERR_COMM, "ghost exchange: a neighbour's push did not arrive within the time limit"); }
+}
 
 // ---- host-phase trace (FLIPB200_PHASE_TRACE=1): wall clock of named host phases, stream-synchronised on both
 // sides, accumulated per world and printed when the world is destroyed. A diagnosis aid, off by default.
@@ -231,6 +237,7 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter);
 enum { CT_F32 = 0, CT_U32 = 1, CT_I32 = 2 };
 void comm_destroy(World* w);
 bool comm_active(World* w);
+bool comm_is_local(World* w);   // the in-process backend (several worlds of one process, same address space)
 void comm_group_begin(World* w);
 void comm_send(World* w, int peer, const void* buf, size_t bytes);
 void comm_recv(World* w, int peer, void* buf, size_t bytes);
