@@ -110,15 +110,20 @@ __global__ void __launch_bounds__(256) dd_push_kernel(PushArgs a, char* __restri
             const size_t n16 = a.bytes[k] >> 4;
             const uint4* sp = reinterpret_cast<const uint4*>(a.src[k]);
             uint4* dp = reinterpret_cast<uint4*>(dst);
-            for (size_t i = gtid; i < n16; i += gsz) dp[i] = sp[i];
+            size_t i = gtid;
+            for (; i + 3 * gsz < n16; i += 4 * gsz) {   // four 16-byte stores in flight per thread
+                const uint4 v0 = sp[i], v1 = sp[i + gsz], v2 = sp[i + 2 * gsz], v3 = sp[i + 3 * gsz];
+                dp[i] = v0; dp[i + gsz] = v1; dp[i + 2 * gsz] = v2; dp[i + 3 * gsz] = v3;
+            }
+            for (; i < n16; i += gsz) dp[i] = sp[i];
             for (size_t i = (n16 << 4) + gtid; i < a.bytes[k]; i += gsz) dst[i] = a.src[k][i];
         } else {   // the one-byte-per-leaf arrays start anywhere
             for (size_t i = gtid; i < a.bytes[k]; i += gsz) dst[i] = a.src[k][i];
         }
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();   // one fence per CTA, behind the barrier: cumulative over the stores of all its threads
         if (atomicAdd(counter, 1u) == gridDim.x - 1) {   // every CTA's stores are fenced: publish
             __threadfence_system();
             *reinterpret_cast<volatile unsigned*>(remoteFlag) = epoch;
@@ -486,7 +491,7 @@ void dd_refresh(World* w, const std::vector<DDArray>& arrays, int layers) {
         // the neighbour's box for ITS side facing me: I am its right neighbour when it is my left one
         char* rbox = P.box(P.remote[s], 1 - s, par);
         unsigned* rflag = P.flag(P.remote[s], 1 - s, par);
-        const unsigned grid = (unsigned)std::min<size_t>(296, std::max<size_t>(1, (most / 16 + 255) / 256));
+        const unsigned grid = (unsigned)std::min<size_t>(148, std::max<size_t>(1, (most / 64 + 255) / 256));   // <= one CTA per SM, 64 bytes per thread and round
         FB_LAUNCH(w, "dd_push", sbytes[s]) dd_push_kernel<<<grid, 256, 0, w->stream>>>(pa, rbox, rflag, ep, P.counter.p + s);
         check_launch("dd_push");
     }
