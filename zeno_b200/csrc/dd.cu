@@ -384,7 +384,7 @@ void peer_setup(World* w) {
     int want = e ? atoi(e) : 1;
     const bool has[2] = {w->rank > 0, w->rank < w->nRanks - 1};
     const bool local = comm_is_local(w);
-    size_t mb = 32;
+    size_t mb = 64;   // per box; four boxes per rank (a fused two-layer refresh of Velocity + PostAdvVelocity + LiquidSDF across a 32 x 32-leaf face is 30 MB)
     if (const char* b = getenv("FLIPB200_DD_P2P_MB")) mb = (size_t)std::max(1, atoi(b));
     struct Blob { unsigned char h[64]; unsigned long long ptr; int ok; int pad; };   // 80 bytes
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");

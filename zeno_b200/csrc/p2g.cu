@@ -707,9 +707,10 @@ void p2g(World* w, float dx, int velExtraLayer) {
     sdf = std::move(nsdf);
     if (dd_on(w)) {
         // the two leaf layers beyond each slab face were computed from an incomplete particle set: take the owner's
-        dd_refresh(w, vel, 2);
-        dd_refresh(w, post, 2);
-        dd_refresh(w, sdf, 2);
+        // (one exchange for the three grids: 11 arrays of the same leaf layers)
+        dd_refresh(w, {DDArray{vel.val[0].p, LEAF * 4}, DDArray{vel.val[1].p, LEAF * 4}, DDArray{vel.val[2].p, LEAF * 4}, DDArray{vel.mask.p, 64},
+                       DDArray{post.val[0].p, LEAF * 4}, DDArray{post.val[1].p, LEAF * 4}, DDArray{post.val[2].p, LEAF * 4}, DDArray{post.mask.p, 64},
+                       DDArray{sdf.val.p, LEAF * 4}, DDArray{sdf.mask.p, 64}, DDArray{sdf.alloc.p, 1}}, 2);
     }
 }
 

@@ -2598,7 +2598,10 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
     FB_CUDA(cudaMemcpyAsync(nd.mask.p, L0.dof.p, (size_t)n * 64, cudaMemcpyDeviceToDevice, w->stream));
     w->F(FLIPB200_PRESSURE) = std::move(np);
     w->F(FLIPB200_DIVERGENCE) = std::move(nd);
-    if (dd) { dd_refresh(w, w->F(FLIPB200_PRESSURE), 2); dd_refresh(w, w->F(FLIPB200_DIVERGENCE), 2); }
+    if (dd) {   // one exchange for both grids
+        GridF& gp = w->F(FLIPB200_PRESSURE); GridF& gd = w->F(FLIPB200_DIVERGENCE);
+        dd_refresh(w, {DDArray{gp.val.p, LEAF * 4}, DDArray{gp.mask.p, 64}, DDArray{gp.alloc.p, 1}, DDArray{gd.val.p, LEAF * 4}, DDArray{gd.mask.p, 64}, DDArray{gd.alloc.p, 1}}, 2);
+    }
     sync(w);
 }
 
