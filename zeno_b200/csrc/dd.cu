@@ -127,8 +127,7 @@ __global__ void __launch_bounds__(256) dd_push_kernel(PushArgs a, char* __restri
         if (atomicAdd(counter, 1u) == gridDim.x - 1) {   // every CTA's stores are fenced: publish
             __threadfence_system();
             *reinterpret_cast<volatile unsigned*>(remoteFlag) = epoch;
-            __threadfence_system();
-            *counter = 0;
+            *counter = 0;   // for the next push to this side (a later kernel of this stream)
         }
     }
 }
