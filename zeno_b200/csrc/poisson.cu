@@ -1734,6 +1734,7 @@ struct Solver {
                    "slab decomposition needs at least two multigrid levels (more than 4000 pressure DOFs)");
         std::unique_ptr<Level> loc = coarsen_raw();
         const int R = w->nRanks, me = w->rank;
+        auto ph = std::make_unique<PhaseTimer>(w, "ppe coarse: gather leaf lists");
         DBuf<int> cnt(R, w->stream);
         cnt.zero();
         const int mine = loc->n;
@@ -1751,6 +1752,7 @@ struct Solver {
         DBuf<int3> cand(total + 1, w->stream);
         for (int r = 0, at = 0; r < R; at += counts[r], r++)
             if (counts[r]) FB_CUDA(cudaMemcpyAsync(cand.p + at, gath.p + (size_t)r * maxCnt * 3, (size_t)counts[r] * 12, cudaMemcpyDeviceToDevice, w->stream));
+        ph.reset(); ph = std::make_unique<PhaseTimer>(w, "ppe coarse: global level-1 topology + scatter");
         auto Gp = std::make_unique<Level>();
         Level& G = *Gp;
         G.topo = topo_from_origins_dev(w, cand.p, total, false);
@@ -1766,11 +1768,26 @@ struct Solver {
         FB_LAUNCH(w, "dd_scatter_coarse", nv * 40) dd_scatter_coarse_kernel<<<G.n, 512, 0, w->stream>>>(G.topo->view(), lt, loc->dof.p, loc->diag.p, loc->xe.p, loc->ye.p, loc->ze.p,
                                                                                                        xlo, xhi, G.term, G.dof.p, G.diag.p, G.xe.p, G.ye.p, G.ze.p);
         check_launch("dd_scatter_coarse");
-        comm_allreduce(w, G.diag.p, nv, CT_F32, false);
-        comm_allreduce(w, G.xe.p, nv, CT_F32, false);
-        comm_allreduce(w, G.ye.p, nv, CT_F32, false);
-        comm_allreduce(w, G.ze.p, nv, CT_F32, false);
+        ph.reset(); ph = std::make_unique<PhaseTimer>(w, "ppe coarse: all-reduce coefficients");
+        // every cell has exactly one non-zero contributor: sum == assembly. The four coefficient arrays travel as ONE message
+        // through a persistent staging buffer (five all-reduces of freshly allocated arrays took 5.8 ms per solve at N = 8,
+        // profiles/r03_phase_trace_n8.txt)
+        static const bool stageAr = !(getenv("FLIPB200_DD_AR_STAGE") && atoi(getenv("FLIPB200_DD_AR_STAGE")) == 0);
+        if (stageAr) {
+            if (w->ddStage.n < 4 * nv) w->ddStage.alloc(4 * nv + nv / 2, w->stream);
+            float* st = w->ddStage.p;
+            float* src[4] = {G.diag.p, G.xe.p, G.ye.p, G.ze.p};
+            for (int k = 0; k < 4; k++) FB_CUDA(cudaMemcpyAsync(st + (size_t)k * nv, src[k], nv * 4, cudaMemcpyDeviceToDevice, w->stream));
+            comm_allreduce(w, st, 4 * nv, CT_F32, false);
+            for (int k = 0; k < 4; k++) FB_CUDA(cudaMemcpyAsync(src[k], st + (size_t)k * nv, nv * 4, cudaMemcpyDeviceToDevice, w->stream));
+        } else {
+            comm_allreduce(w, G.diag.p, nv, CT_F32, false);
+            comm_allreduce(w, G.xe.p, nv, CT_F32, false);
+            comm_allreduce(w, G.ye.p, nv, CT_F32, false);
+            comm_allreduce(w, G.ze.p, nv, CT_F32, false);
+        }
         comm_allreduce(w, G.dof.p, (size_t)G.n * 16, CT_U32, false);   // disjoint bits: sum == or
+        ph.reset(); ph = std::make_unique<PhaseTimer>(w, "ppe coarse: replicated hierarchy set-up");
         coarse = std::make_unique<Solver>();
         coarse->w = w; coarse->dt = dt; coarse->coarseOnly = true; coarse->tiles = tiles;
         coarse->finish_level(G);
@@ -1779,6 +1796,7 @@ struct Solver {
         while (coarse->levels.back()->numDof > MAX_COARSEST) coarse->coarsen();
         coarse->build_coarsest();
         if (!getenv("FLIPB200_NO_CYCLE_KERNEL")) coarse->prepare_cycle(4);
+        ph.reset();
     }
     void build_coarsest() {
         Level& L = *levels.back();
@@ -2474,6 +2492,7 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
     int ownLo = 0, ownHi = n;
     if (dd) dd_owned_slots(w, &ownLo, &ownHi);
 
+    auto ph0 = std::make_unique<PhaseTimer>(w, "ppe level-0 matrix");
     Solver S;
     S.w = w;
     S.dt = dt;
@@ -2501,6 +2520,7 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
         }
         S.levels.push_back(std::move(Lp));  // level 0 iterates on the PCG vectors; it owns no x/b
     }
+    ph0.reset();
     if (dd) { S.dd_build_coarse(); S.dd_passes_prepare(4); }
     else {
         while (S.levels.back()->numDof > MAX_COARSEST) S.coarsen();

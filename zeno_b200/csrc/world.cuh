@@ -53,6 +53,7 @@ struct flipb200_world {
     // FLIP_P2G's staging-overflow flag: written by the kernel, copied to page-locked host memory in stream order and
     // checked at the next host wait that happens anyway (flipb200_p2g / flipb200_substep), not with a wait of its own
     fb::DBuf<int> p2gOverflow;
+    fb::DBuf<float> ddStage;   // slab decomposition: persistent operand of the coarse-level all-reduce (NCCL sees the same buffer every solve)
     int* p2gOverflowHost = nullptr;
 
     // page-locked scratch for the few-byte read-backs (a pageable destination makes the driver stage the copy)
