@@ -1,3 +1,4 @@
+"""Leaves per x layer of the P2G outputs on every rank of a two-rank in-process decomposition against the single world (a quick look at what the ghost refresh delivered). usage: python tools/dd_layers_probe.py"""
 import os, sys, numpy as np
 sys.path.insert(0, os.getcwd())
 from zeno_b200 import abi, scenes
