@@ -247,8 +247,14 @@ int flipb200_comm_abort(flipb200_world* w);
 /* Slab decomposition (no reference counterpart: the reference runs one TBB process).
  * This rank owns the leaf layers [leafLo, leafHi) along x (leaf coordinate = voxel >> 3); the first rank's lower and
  * the last rank's upper bound are open. Slabs must be at least two layers thick and cover the axis without gaps.
- * (VDBRenormalizeSDF and VDBSmoothSDF are refused in this mode for now: FLIPB200_ERR_STATE; the particle-local nodes
- * KillParticlesInSDF / ParticleAddDV / VDBErodeSDF need no exchange.)
+ * Every node of the packaged substep runs in this mode: VDBRenormalizeSDF / VDBSmoothSDF refresh the ghost layers between the
+ * passes that read across a slab face; KillParticlesInSDF / ParticleAddDV / VDBErodeSDF need no exchange; FluidReseed and
+ * ParticleEmitter decide per leaf from (seed, leaf origin) and data within two voxels of the leaf, so owner and ghost holder
+ * agree without an exchange (pass the same seed and the same shape grid on every rank); FLIPApplyBoundary and the Curvature
+ * socket read caller-supplied grids by voxel coordinate (give every rank the grid over its owned + ghost layers). Not
+ * available: the pure-multigrid fallback after a failed PCG (the status is returned).
+ * Ghost leaves travel over peer memory (cudaIpc-mapped receive boxes, device-side flags) when the GPUs can map each other,
+ * else over NCCL send/recv; FLIPB200_DD_P2P=0 forces the latter.
  * From here on every node call is COLLECTIVE (all ranks issue the same sequence): flipb200_bin_from_points routes
  * points to their owners and fills the ghost layers, flipb200_g2p_advect_sheetty migrates particles,
  * P2G / solve / gradient exchange ghost leaves, CFL and the PCG scalars are all-reduced. Grids and particles
