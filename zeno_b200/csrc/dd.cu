@@ -136,7 +136,7 @@ __global__ void dd_wait_kernel(const unsigned* __restrict__ flag, unsigned epoch
     long long t0 = clock64();
     // epochs only grow; a (wrapping) difference >= 0 means the neighbour's push of this exchange has landed
     while ((int)(*f - epoch) < 0) {
-        if (clock64() - t0 > 8000000000ll) { *err = 1; break; }   // ~4 s: a peer that never pushes must not hang the device
+        if (clock64() - t0 > 30000000000ll) { *err = 1; break; }   // ~15 s: a peer that never pushes must not hang the device
         __nanosleep(100);
     }
     __threadfence_system();
