@@ -1760,7 +1760,13 @@ struct Solver {
         G.dx = loc->dx; G.term = loc->term;
         const size_t nv = (size_t)G.n * LEAF;
         G.dof.alloc((size_t)G.n * 8, w->stream);
-        G.diag.alloc(nv, w->stream); G.xe.alloc(nv, w->stream); G.ye.alloc(nv, w->stream); G.ze.alloc(nv, w->stream);
+        {   // the four arrays of the previous solve are reused when they are large enough (dd_scatter_coarse_kernel writes every element)
+            DBuf<float>* dst[4] = {&G.diag, &G.xe, &G.ye, &G.ze};
+            for (int k = 0; k < 4; k++) {
+                if (w->ddCoarse[k].n >= nv) *dst[k] = std::move(w->ddCoarse[k]);
+                else dst[k]->alloc(nv + nv / 4, w->stream);
+            }
+        }
         int lo, hi;
         dd_owned_coords(w, &lo, &hi);
         const int xlo = me > 0 ? 4 * lo : INT_MIN, xhi = me < R - 1 ? 4 * hi : INT_MAX;   // level-1 cells: fine voxel / 2
@@ -2618,6 +2624,10 @@ void solve_ppe(World* w, float dt, float dx, float relTol, int maxIter) {
     FB_CUDA(cudaMemcpyAsync(nd.mask.p, L0.dof.p, (size_t)n * 64, cudaMemcpyDeviceToDevice, w->stream));
     w->F(FLIPB200_PRESSURE) = std::move(np);
     w->F(FLIPB200_DIVERGENCE) = std::move(nd);
+    if (dd && S.coarse && !S.coarse->levels.empty()) {   // keep the global level-1 arrays for the next solve (ownership only: nothing is freed or copied)
+        Level& G1 = *S.coarse->levels[0];
+        w->ddCoarse[0] = std::move(G1.diag); w->ddCoarse[1] = std::move(G1.xe); w->ddCoarse[2] = std::move(G1.ye); w->ddCoarse[3] = std::move(G1.ze);
+    }
     if (dd) {   // one exchange for both grids
         GridF& gp = w->F(FLIPB200_PRESSURE); GridF& gd = w->F(FLIPB200_DIVERGENCE);
         dd_refresh(w, {DDArray{gp.val.p, LEAF * 4}, DDArray{gp.mask.p, 64}, DDArray{gp.alloc.p, 1}, DDArray{gd.val.p, LEAF * 4}, DDArray{gd.mask.p, 64}, DDArray{gd.alloc.p, 1}}, 2);

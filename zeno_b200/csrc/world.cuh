@@ -53,6 +53,7 @@ struct flipb200_world {
     // FLIP_P2G's staging-overflow flag: written by the kernel, copied to page-locked host memory in stream order and
     // checked at the next host wait that happens anyway (flipb200_p2g / flipb200_substep), not with a wait of its own
     fb::DBuf<int> p2gOverflow;
+    fb::DBuf<float> ddCoarse[4];   // slab decomposition: the global level-1 coefficient arrays, kept between solves (no pool traffic for 4 x nv floats per solve)
     fb::DBuf<float> ddStage;   // slab decomposition: persistent operand of the coarse-level all-reduce (NCCL sees the same buffer every solve)
     int* p2gOverflowHost = nullptr;
 
